@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- ns/day of the MD hot path on BASELINE.json's headline configuration (C4: the
+1,000,000-atom LJ fluid, strong scaling over 1/2/4/8 B200) plus the pair-force kernel's
+HBM-roofline fraction, next to the CPU restatement timed on the host cores.
+
+    python bench.py --gpus N --steps K --warmup W          # this engine
+    python bench.py --impl reference --steps K --warmup W  # CPU arm (oracle port)
+
+A "step" is one velocity-Verlet MD step of the whole system: kick+drift, (Verlet-list rebuild
+when the displacement criterion fires), pair forces, kick.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ns_per_day_1M_atom_lj_fluid"
+UNIT = "ns/day"
+DT_PS = 0.002
+
+
+def ns_per_day(steps, seconds, dt_ps=DT_PS):
+    return steps * dt_ps * 1e-3 / seconds * 86400.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_arm(side, steps, warmup):
+    """The CPU path (oracle port, OpenMP over all host cores) on a bounded sample: the same
+    fluid at the same density in a side^3-atom box; ns/day is reported for the 1M-atom system by
+    scaling with atoms (the work per atom is identical)."""
+    from molchanica_b200 import workloads as W
+    from oracle import oracle_py as O
+    O.lib()
+    w = W.lj_fluid(m=side)
+    n = len(w["xyzq"])
+    st = O.md_run(w, warmup, precision=32)
+    t0 = time.perf_counter()
+    O.md_run(w, steps, precision=32, xyzq=st["xyzq"], vel=st["vel"])
+    dt = time.perf_counter() - t0
+    v_sample = ns_per_day(steps, dt)
+    v_1m = v_sample * n / 1.0e6
+    return dict(value=v_1m, unit=UNIT, cores=O.num_threads(), kind="port",
+                sample=f"{n}-atom box of the same LJ fluid (side {side}), {steps} steps incl. list rebuilds, "
+                       f"{dt:.2f} s; scaled by atoms to 1M",
+                seconds=dt, steps=steps)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--side", type=int, default=100, help="atoms per box edge (100 -> 1,000,000 atoms)")
+    ap.add_argument("--cpu-side", type=int, default=40)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    W_ = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb = cpu_arm(args.cpu_side, min(K, 200), min(W_, 10))
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": cb["steps"], "warmup": min(W_, 10), "ms_per_step": cb["seconds"] / cb["steps"] * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C4 1M-atom LJ fluid (argon, rho*=0.8442, rc=2.5 sigma, skin 1 A, dt 2 fs), "
+                                       "CPU restatement on a bounded sample"},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from molchanica_b200 import _lib
+    from molchanica_b200 import workloads as W
+    from molchanica_b200.engine import MdEngine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = W.lj_fluid(m=args.side)
+    n = len(w["xyzq"])
+    e = MdEngine(device=local)
+    if world > 1:
+        uid = np.zeros(128, np.uint8)
+        if rank == 0:
+            e._chk(e._L.mc_comm_unique_id(uid.ctypes.data_as(C.c_void_p)))
+        t = torch.from_numpy(uid).cuda()
+        dist.broadcast(t, 0)
+        uid = t.cpu().numpy()
+        e._chk(e._L.mc_comm_init(e._h, uid.ctypes.data_as(C.c_void_p), rank, world))
+    lo = np.asarray(w["box_lo"], np.float32)
+    e.set_box(lo, lo + w["box_ext"], True)
+    e.set_cutoffs(w["rc_lj"], w["rc_q"], w["skin"], w["coul_mode"], 0.35)
+    e.set_lj_table(w["ljtab"])
+    e.set_atoms(w["xyzq"], w["type"], w["vel"])
+    if args.lanes:
+        e.set_option("pair_lanes", args.lanes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident, CUDA events on the engine's stream around all K steps ----------
+    e.step(DT_PS, W_)
+    e.set_option("profiling", 1)
+    e.reset_timers()
+    s0 = e.stats()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    e.step(DT_PS, K)
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = e.last_step_ms()
+    clocks = sampler.stop() if rank == 0 else None
+    s1 = e.stats()
+    e.set_option("profiling", 0)
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = ns_per_day(K, ms * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, one call per step, H2D + D2H inside the timing ----
+    # per step: H2D of the step's external forces (the Some(forces) argument of MdState::step,
+    # reference src/mol_alignment.rs:346) from pinned memory, mc_step(dt, 1, ext), D2H of the new
+    # positions (what the viewer reads back, reference src/md/mod.rs:843-852) into pinned memory.
+    e2e = None
+    if world == 1:
+        ext = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
+        pos = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+        ext_p, pos_p = C.c_void_p(ext.data_ptr()), C.c_void_p(pos.data_ptr())
+        for _ in range(3):
+            e.step_raw(DT_PS, 1, ext_p)
+            e.get_positions_into(pos_p)
+        torch.cuda.synchronize()
+        ke = min(K, 200)
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            e.step_raw(DT_PS, 1, ext_p)
+            e.get_positions_into(pos_p)
+        torch.cuda.synchronize()
+        te = time.perf_counter() - t0
+        e2e = {"value": ns_per_day(ke, te), "unit": UNIT, "h2d_bytes_per_step": int(ext.numel() * 4),
+               "d2h_bytes_per_step": int(pos.numel() * 4), "steps": ke, "ms_per_step": te / ke * 1e3,
+               "api": "mc_step(ctx, dt, 1, ext_forces) + mc_get_positions(ctx, out), pinned host buffers"}
+
+    # ---- roofline of the dominant kernel (pair force), live CUDA-event average over the timed region
+    pair_ms = (s1["pair_ms_sum"] - 0.0) / max(s1["pair_launches_timed"], 1)
+    p_full = s1["n_pairs_listed"]
+    n_rows = s1["n_atoms"]
+    alg_bytes = 32.0 * n_rows + 20.0 * p_full
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "pair_force_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "pair_force_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": pair_ms,
+                "launches_timed": s1["pair_launches_timed"],
+                "share_of_step": pair_ms * s1["pair_launches_timed"] / ms if ms > 0 else None,
+                "build_ms_avg": s1["build_ms_sum"] / max(s1["builds_timed"], 1),
+                "integrate_ms_avg": s1["integrate_ms_sum"] / max(s1["integrate_launches_timed"], 1)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb = cpu_arm(args.cpu_side, 60, 5)
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"C4 {n}-atom LJ fluid (argon, rho*=0.8442, rc=2.5 sigma=8.5125 A, skin 1 A, "
+                                       f"dt 2 fs, PBC {w['box_ext'][0]:.1f} A), velocity Verlet, Verlet list rebuilt on "
+                                       f"displacement > skin/2",
+                           "atoms": n, "l2_policy": "inputs larger than L2: list+positions = "
+                                                    f"{(4 * p_full + 16 * n) / 1e6:.0f} MB per step vs 126 MB L2",
+                           "parallelism": f"slab-dd{world}" if world > 1 else "single-gpu",
+                           "pair_lanes": args.lanes or 8},
+                "e2e": e2e, "gpu_launches": int(s1["n_kernel_launches"] - s0["n_kernel_launches"]),
+                "rebuilds_in_timed_region": int(s1["n_rebuilds"] - s0["n_rebuilds"]),
+                "wall_ms_per_step": wall / K * 1e3, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                "loaded_library": _lib.LIB_PATH}
+        print(json.dumps(line))
+    e.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

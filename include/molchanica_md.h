@@ -1,0 +1,199 @@
+/*
+ * molchanica_md.h -- C ABI of libmolchanica_md.so, the B200 (sm_100a) force-evaluation engine
+ * for Molchanica's src/md hot path and the src/docking pose-energy scan.
+ *
+ * This library replaces the reference's device boundary -- the PTX module built from
+ * src/cuda/{cuda,util}.cu by build.rs:10-16 and loaded in src/util.rs:1072-1119 -- and the
+ * force / neighbour-list / integrator loops that the `dynamics` crate runs behind
+ * `MdState::step(dev, dt, ext_forces)` (call sites: reference src/md/mod.rs:716,748,
+ * src/mol_editor/mod.rs:388, src/mol_alignment.rs:346).  A Rust `extern "C"` binding for it is
+ * shown in INTEGRATION.md; include/molchanica_md.hpp mirrors the `dynamics` API surface on top
+ * of it for C++ hosts.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer; the library copies in
+ *     `mc_set_*`, owns all device memory until `mc_destroy`, and fills caller-allocated buffers
+ *     in `mc_get_*` (the ownership model of clone_htod / clone_dtoh, src/reflection.rs:146-214)
+ *   - every function returns 0 on success, a negative MC_E_* code otherwise; the message is
+ *     available from mc_last_error(); nothing throws or aborts across the ABI
+ *   - there is NO CPU fallback: without a usable CUDA device mc_create fails (the reference
+ *     degrades to ComputationDevice::Cpu, src/util.rs:1065-1070; BASELINE.json forbids that here)
+ *   - a handle is not re-entrant; distinct handles may be used from distinct threads; all work
+ *     of a handle runs on its own non-blocking stream
+ *   - units: Angstrom, ps, amu, kcal/mol; charges pre-multiplied by sqrt(332.0522); atom ids are
+ *     the caller's ("original") ids everywhere on this boundary, whatever order the engine keeps
+ *     internally
+ */
+#ifndef MOLCHANICA_MD_H
+#define MOLCHANICA_MD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_ABI_VERSION 1
+
+#define MC_OK 0
+#define MC_E_INVALID (-1)   /* bad argument / call order                      */
+#define MC_E_CUDA (-2)      /* CUDA runtime error (see mc_last_error)          */
+#define MC_E_NODEVICE (-3)  /* no usable sm_100 device -- there is no fallback */
+#define MC_E_CAPACITY (-4)  /* caller buffer too small                         */
+#define MC_E_COMM (-5)      /* NCCL / peer-exchange error                      */
+
+#define MC_COULOMB_NONE 0   /* q ignored                                                  */
+#define MC_COULOMB_PLAIN 1  /* q_i q_j /(r^2 + 1e-6), truncated at rc_q (src/cuda/util.cu:54-63) */
+#define MC_COULOMB_ERFC 2   /* Ewald real-space erfc(alpha r)/r (util.cu:15-18 INV_SQRT_PI)       */
+
+#define MC_FLAG_STATIC 1u   /* AtomDynamics.static_ : exerts forces, never moves (src/md/mod.rs:843-852) */
+
+typedef struct mc_ctx mc_ctx;
+
+/* One float4 per atom everywhere: {x, y, z, q} positions+charge, {vx, vy, vz, 1/m} velocities,
+ * {fx, fy, fz, e_i} forces + per-atom pair-energy row sum. */
+typedef struct { float x, y, z, w; } mc_float4;
+
+/* SnapshotEnergyData subset (reference src/md/mod.rs:1242-1245, ui/panels/md_viewer.rs:202-256) */
+typedef struct {
+    double energy_potential;            /* = nonbonded here (bonded terms are outside this path) */
+    double energy_potential_nonbonded;  /* LJ + Coulomb + scaled 1-4, kcal/mol                   */
+    double energy_potential_bonded;     /* always 0: bonded terms are a "next" row   */
+    double energy_kinetic;              /* sum 1/2 m v^2 / 418.4, kcal/mol                       */
+    double temperature;                 /* 2 KE / (3 N_mobile k_B), K                            */
+} mc_energy;
+
+/* Counters for the caller / benchmarks.  The *_ms_sum fields accumulate CUDA-event durations
+ * measured on the handle's stream while option "profiling" is on. */
+typedef struct {
+    int64_t n_atoms;             /* atoms owned by this handle                          */
+    int64_t n_ghosts;            /* ghost atoms held (domain decomposition), else 0     */
+    int64_t n_pairs_listed;      /* full-list entries of the current Verlet list        */
+    int64_t n_rebuilds;          /* list builds since mc_create                         */
+    int64_t n_steps;             /* integrator steps since mc_create                    */
+    int64_t n_kernel_launches;   /* kernels launched by this handle since mc_create     */
+    int64_t n_cells[3];          /* current cell grid (periodic boxes)                  */
+    double  pair_ms_sum;      int64_t pair_launches_timed;
+    double  build_ms_sum;     int64_t builds_timed;
+    double  integrate_ms_sum; int64_t integrate_launches_timed;
+    double  halo_ms_sum;      int64_t halos_timed;
+} mc_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Replaces get_computation_device (src/util.rs:1072-1119): binds CUDA device `device`, creates
+ * the stream.  Fails with MC_E_NODEVICE when no device is usable. */
+int mc_create(int device, mc_ctx **out);
+int mc_destroy(mc_ctx *ctx);
+/* Message of the last failure on this handle (or of the last failed mc_create when ctx==NULL). */
+const char *mc_last_error(const mc_ctx *ctx);
+int mc_abi_version(void);
+
+/* ---- system definition (what MdState::new hands over, src/md/mod.rs:641-693) ------------ */
+
+/* SimBox {bounds_low, bounds_high} (properties/sol_shrinking_box.rs:600-603).  periodic = 0
+ * means vacuum (Solvent::None, src/md/mod.rs:784): the box is then ignored and the cell grid
+ * follows the atoms' bounding box. */
+int mc_set_box(mc_ctx *ctx, const float lo[3], const float hi[3], int periodic);
+
+/* n atoms; type may be NULL (all 0), vel may be NULL (zero velocities, unit mass), flags may be
+ * NULL.  Resets the neighbour list. */
+int mc_set_atoms(mc_ctx *ctx, int64_t n, const mc_float4 *xyzq, const uint16_t *type,
+                 const mc_float4 *vel_invmass, const uint8_t *flags);
+
+/* T x T table of (sigma_ij [A], eps_ij [kcal/mol]) pairs, row-major -- replaces the dense
+ * [N_tgt x N_src] sigma/eps arrays of lj_force_kernel (src/cuda/cuda.cu:73-102). */
+int mc_set_lj_table(mc_ctx *ctx, int n_types, const float *sigma_eps);
+
+/* Excluded partners per atom (1-2, 1-3 and 1-4), CSR: start[n+1], idx[start[n]]. NULL clears. */
+int mc_set_exclusions(mc_ctx *ctx, const int32_t *start, const int32_t *idx);
+
+/* Amber 1-4 pairs (pairs[2*m]) evaluated without cutoff, LJ x scale_lj, Coulomb x scale_q. */
+int mc_set_pairs14(mc_ctx *ctx, int64_t m, const int32_t *pairs, float scale_lj, float scale_q);
+
+/* cfg.lj_cutoff / cfg.coulomb_cutoff (ui/panels/md.rs:260-261), Verlet skin, Coulomb form. */
+int mc_set_cutoffs(mc_ctx *ctx, float rc_lj, float rc_q, float skin, int coulomb_mode, float alpha);
+
+/* MdOverrides.lj_disabled / coulomb_disabled (src/md/mod.rs:671-686). */
+int mc_set_overrides(mc_ctx *ctx, int lj_disabled, int coulomb_disabled);
+
+/* Tuning / instrumentation knobs: "pair_lanes" (4, 8, 16, 32 lanes per list row),
+ * "profiling" (0/1: bracket the hot kernels with CUDA events), "rebuild_every" (0 = rebuild on
+ * the displacement criterion, k > 0 = every k steps like GROMACS nstlist). */
+int mc_set_option(mc_ctx *ctx, const char *name, double value);
+
+/* Replace positions (and optionally velocities) of the existing atoms, original order. */
+int mc_set_positions(mc_ctx *ctx, const mc_float4 *xyzq);
+int mc_set_velocities(mc_ctx *ctx, const mc_float4 *vel_invmass);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+
+/* md.rebuild_spatial_caches(dev) (properties/sol_shrinking_box.rs:632): wrap into the box, cell
+ * ids, on-device radix sort + prefix scan, spatial reorder, Verlet list of radius
+ * max(rc_lj, rc_q) + skin. */
+int mc_build_neighbors(mc_ctx *ctx);
+
+/* One nonbonded force evaluation on the current positions (rebuilds the list first when it is
+ * stale).  The single-point path of compute_energy_snapshot (src/md/mod.rs:1036). */
+int mc_compute_forces(mc_ctx *ctx);
+
+/* MdState::step(dev, dt, ext) x n_steps (src/md/mod.rs:716,748): velocity Verlet, list rebuilt
+ * on the device-side displacement criterion (> skin/2).  ext_forces: n x {fx,fy,fz} in original
+ * order added at every evaluation, or NULL (mol_alignment.rs:346 passes Some(forces)). */
+int mc_step(mc_ctx *ctx, float dt, int n_steps, const float *ext_forces);
+/* Device time of the last mc_step call: CUDA events on the handle's stream around all of its
+ * steps (kernels, rebuilds and any idle gaps between them). */
+double mc_last_step_ms(mc_ctx *ctx);
+
+/* ---- read-back (caller-allocated, original atom order) ---------------------------------- */
+int mc_get_positions(mc_ctx *ctx, mc_float4 *out);
+int mc_get_velocities(mc_ctx *ctx, mc_float4 *out);
+int mc_get_forces(mc_ctx *ctx, mc_float4 *out);
+int mc_get_energy(mc_ctx *ctx, mc_energy *out);
+int mc_get_stats(mc_ctx *ctx, mc_stats *out);
+
+/* Verlet list as CSR in original ids, rows ascending.  start: n+1 entries.  Two-call protocol:
+ * idx == NULL or cap too small -> start[] is still filled, *total set, MC_E_CAPACITY returned
+ * when idx != NULL. */
+int mc_get_neighbors(mc_ctx *ctx, int64_t *start, int32_t *idx, int64_t cap, int64_t *total);
+
+int mc_reset_timers(mc_ctx *ctx);
+
+/* Times `reps` stand-alone launches of the pair-force kernel on the current state with CUDA
+ * events on the handle's stream (3 untimed warm-ups first); the mean is returned by
+ * mc_last_pair_kernel_ms.  flush_l2 != 0 writes a buffer twice the L2 size between launches. */
+int mc_time_kernels(mc_ctx *ctx, int reps, int flush_l2);
+double mc_last_pair_kernel_ms(mc_ctx *ctx);
+
+/* ---- docking pose-energy scan (src/docking/legacy/mod.rs:210-383, :174-200) ------------- */
+
+/* receptor: n_rec atoms (xyzq, type, hydrophobic flag); ligand: n_lig atoms in their reference
+ * conformation + anchor point; ljtab: n_rec_types x n_lig_types (sigma, eps); poses: n_poses x
+ * {ax, ay, az, qw, qx, qy, qz}.  out: n_poses x {score, vdw, hydrophobic, electrostatic,
+ * coulomb_e}.  All host pointers; runs on the handle's stream and returns when done. */
+int mc_dock_score(mc_ctx *ctx, int64_t n_rec, const mc_float4 *rec_xyzq, const uint16_t *rec_type,
+                  const uint8_t *rec_hydrophobic, int64_t n_lig, const mc_float4 *lig_xyzq,
+                  const uint16_t *lig_type, const uint8_t *lig_hydrophobic, const float lig_anchor[3],
+                  int n_rec_types, int n_lig_types, const float *ljtab,
+                  int64_t n_poses, const float *poses, float *out);
+/* CUDA-event duration of the scan kernel of the last mc_dock_score call (profiling on). */
+double mc_last_dock_kernel_ms(mc_ctx *ctx);
+
+/* ---- domain decomposition: one handle per GPU / process ---------------------- */
+
+/* 128-byte NCCL unique id, produced on rank 0 and distributed by the host (any transport). */
+int mc_comm_unique_id(uint8_t id[128]);
+/* Join the communicator; slabs along z.  Must precede mc_set_atoms; afterwards mc_set_atoms
+ * takes the GLOBAL system on every rank and keeps the atoms this rank owns. */
+int mc_comm_init(mc_ctx *ctx, const uint8_t id[128], int rank, int n_ranks);
+/* Number of atoms this rank currently owns / holds as ghosts. */
+int mc_comm_counts(mc_ctx *ctx, int64_t *n_owned, int64_t *n_ghost);
+/* Gather global arrays (original ids, length n_global) -- valid on every rank. */
+int mc_get_positions_global(mc_ctx *ctx, mc_float4 *out);
+int mc_get_forces_global(mc_ctx *ctx, mc_float4 *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLCHANICA_MD_H */

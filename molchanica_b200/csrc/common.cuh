@@ -1,0 +1,51 @@
+// common.cuh -- shared declarations of the sm_100a engine behind include/molchanica_md.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/molchanica_md.h"
+
+#define MC_WARP 32
+#define MC_FULL_MASK 0xffffffffu
+#define MC_ACCEL_CONV 418.4f       // kcal/mol/A/amu -> A/ps^2
+#define MC_SOFTENING_SQ 0.000001f  // reference src/cuda/util.cu:9-10
+#define MC_INV_SQRT_PI 0.5641895835477563f  // util.cu:15-18
+#define MC_KB 0.0019872041         // kcal/mol/K
+
+// Device-resident description of the cell grid; written by the host (periodic box) or by
+// grid_from_bbox_kernel (vacuum), read by every neighbour-build kernel.
+struct GridParams {
+    float lo[3];       // origin
+    float ext[3];      // box extent (periodic) / bounding extent (vacuum)
+    float inv_ext[3];
+    float inv_cw[3];   // 1 / cell width
+    int nc[3];
+    int ncell;
+    int periodic;
+};
+
+// Nonbonded parameters passed by value to the pair kernels.
+struct NbParams {
+    float ext[3], inv_ext[3];
+    float rc2_lj, rc2_q;   // squared cutoffs (fp32 products, same rounding as the oracle)
+    float alpha;           // Ewald splitting parameter
+    float sig2, eps24;     // single-type fast path: sigma^2, 24*eps
+    int periodic;
+    int n_types;
+};
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- sort_scan.cu -------------------------------------------------------------------------
+// Exclusive prefix sum of f(in[i]) into out[0..n] (out[n] = total).  align8 != 0 rounds every
+// input up to a multiple of 8 first (row starts of the Verlet list are 32-byte aligned).
+// scratch: >= scan_scratch_elems(n) uint32.
+size_t scan_scratch_elems(size_t n);
+void exclusive_scan_u32(const uint32_t *in, uint32_t *out, size_t n, int align8, uint32_t *scratch,
+                        cudaStream_t st, int64_t *launches);
+// Stable LSD radix sort of (key, val) pairs on `bits` low key bits.  Results end in keys[0] /
+// vals[0] when the returned value is 0, in keys[1] / vals[1] when it is 1.
+size_t radix_scratch_elems(size_t n);
+int radix_sort_pairs(uint32_t *keys[2], uint32_t *vals[2], size_t n, int bits, uint32_t *scratch,
+                     cudaStream_t st, int64_t *launches);

@@ -1,0 +1,759 @@
+// engine.cu -- the C ABI of include/molchanica_md.h: handle lifetime, system upload, the
+// rebuild / force / step orchestration on the handle's stream, and read-back.
+//
+// Internal data layout (all device-resident, "cell order" = the order produced by the last
+// neighbour build, tracked by orig[] / slot_of_orig[]):
+//   xyzq[2]   float4  x, y, z, q          (ping-pong across reorders)
+//   vel[2]    float4  vx, vy, vz, 1/m
+//   force     float4  fx, fy, fz, e_i
+//   xref      float4  positions at the last build (displacement criterion)
+//   type[2] u16, flags[2] u8, orig[2] i32, slot_of_orig i32
+//   cell_start u32[ncell+1]; nbr_count u32[n]; nbr_start u32[n+1] (rows padded to 8 entries);
+//   nbr_list u32[capacity]
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "dock.cuh"
+#include "engine.cuh"
+#include "integrate.cuh"
+#include "neighbor.cuh"
+#include "pair_force.cuh"
+
+static std::string g_create_err;
+
+#define MC_CUDA(ctx, call)                                                                                 \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +          \
+                         std::to_string(__LINE__) + ")";                                                   \
+            return MC_E_CUDA;                                                                              \
+        }                                                                                                  \
+    } while (0)
+
+#define MC_REQUIRE(ctx, cond, msg) \
+    do {                           \
+        if (!(cond)) {             \
+            (ctx)->err = (msg);    \
+            return MC_E_INVALID;   \
+        }                          \
+    } while (0)
+
+static int fail(mc_ctx *c, int code, const std::string &m) {
+    c->err = m;
+    return code;
+}
+
+// ---- lifetime ------------------------------------------------------------------------------------
+
+extern "C" int mc_abi_version(void) { return MC_ABI_VERSION; }
+
+extern "C" const char *mc_last_error(const mc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int mc_create(int device, mc_ctx **out) {
+    if (!out) { g_create_err = "mc_create: out is NULL"; return MC_E_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        g_create_err = std::string("mc_create: no CUDA device (") + cudaGetErrorString(e) +
+                       "); this engine has no CPU fallback";
+        return MC_E_NODEVICE;
+    }
+    if (device < 0 || device >= count) {
+        g_create_err = "mc_create: device ordinal " + std::to_string(device) + " out of range (" + std::to_string(count) + " devices)";
+        return MC_E_NODEVICE;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_err = std::string("mc_create: ") + cudaGetErrorString(e);
+        return MC_E_NODEVICE;
+    }
+    if (prop.major != 10) {
+        g_create_err = "mc_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                       "; this library carries sm_100a code only";
+        return MC_E_NODEVICE;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_err = std::string("mc_create: cudaSetDevice: ") + cudaGetErrorString(e);
+        return MC_E_NODEVICE;
+    }
+    mc_ctx *c = new mc_ctx();
+    c->device = device;
+    c->n_sms = prop.multiProcessorCount;
+    c->l2_bytes = (size_t)prop.l2CacheSize;
+    if ((e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = pair_force_prepare()) != cudaSuccess || (e = dock_prepare()) != cudaSuccess ||
+        (e = cudaMallocHost(&c->h_pinned, 256)) != cudaSuccess) {
+        g_create_err = std::string("mc_create: ") + cudaGetErrorString(e);
+        delete c;
+        return MC_E_CUDA;
+    }
+    const char *ln = getenv("MC_PAIR_LANES");
+    if (ln) c->pair_lanes = atoi(ln);
+    *out = c;
+    return MC_OK;
+}
+
+extern "C" int mc_destroy(mc_ctx *c) {
+    if (!c) return MC_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    comm_destroy(c);
+    for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    if (c->ev_step_a) { cudaEventDestroy(c->ev_step_a); cudaEventDestroy(c->ev_step_b); }
+    c->free_all();
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    cudaStreamDestroy(c->st);
+    delete c;
+    return MC_OK;
+}
+
+// ---- system definition ---------------------------------------------------------------------------
+
+extern "C" int mc_set_box(mc_ctx *c, const float lo[3], const float hi[3], int periodic) {
+    if (!c) return MC_E_INVALID;
+    MC_REQUIRE(c, lo && hi, "mc_set_box: NULL bounds");
+    for (int a = 0; a < 3; ++a) {
+        MC_REQUIRE(c, !periodic || hi[a] > lo[a], "mc_set_box: periodic box needs hi > lo on every axis");
+        c->lo[a] = lo[a];
+        c->ext[a] = hi[a] - lo[a];
+    }
+    c->periodic = periodic != 0;
+    c->grid_dirty = true;
+    c->list_valid = false;
+    c->forces_valid = false;
+    return MC_OK;
+}
+
+extern "C" int mc_set_cutoffs(mc_ctx *c, float rc_lj, float rc_q, float skin, int coulomb_mode, float alpha) {
+    if (!c) return MC_E_INVALID;
+    MC_REQUIRE(c, rc_lj > 0.f && rc_q > 0.f && skin >= 0.f, "mc_set_cutoffs: cutoffs must be positive, skin >= 0");
+    MC_REQUIRE(c, coulomb_mode >= MC_COULOMB_NONE && coulomb_mode <= MC_COULOMB_ERFC, "mc_set_cutoffs: bad coulomb_mode");
+    c->rc_lj = rc_lj; c->rc_q = rc_q; c->skin = skin; c->coul_mode = coulomb_mode; c->alpha = alpha;
+    c->grid_dirty = true;
+    c->list_valid = false;
+    c->forces_valid = false;
+    return MC_OK;
+}
+
+extern "C" int mc_set_overrides(mc_ctx *c, int lj_disabled, int coulomb_disabled) {
+    if (!c) return MC_E_INVALID;
+    c->lj_disabled = lj_disabled != 0;
+    c->coul_disabled = coulomb_disabled != 0;
+    c->forces_valid = false;
+    return MC_OK;
+}
+
+extern "C" int mc_set_lj_table(mc_ctx *c, int n_types, const float *sigma_eps) {
+    if (!c) return MC_E_INVALID;
+    MC_REQUIRE(c, n_types >= 1 && n_types <= pair_force_max_types() && sigma_eps,
+               "mc_set_lj_table: 1 <= n_types <= " + std::to_string(pair_force_max_types()) + " and a table are required");
+    cudaSetDevice(c->device);
+    std::vector<float2> t((size_t)n_types * n_types);
+    for (size_t k = 0; k < t.size(); ++k) {
+        const float s = sigma_eps[2 * k], e = sigma_eps[2 * k + 1];
+        t[k] = make_float2(s * s, 24.f * e);
+    }
+    MC_CUDA(c, c->ljtab.ensure(t.size()));
+    MC_CUDA(c, cudaMemcpyAsync(c->ljtab.p, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice, c->st));
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
+    c->n_types = n_types;
+    c->sig2_0 = t[0].x;
+    c->eps24_0 = t[0].y;
+    c->forces_valid = false;
+    return MC_OK;
+}
+
+static int upload_atoms_local(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type, const mc_float4 *vel,
+                              const uint8_t *flags, const int *orig_ids) {
+    // allocate every per-atom array for n local atoms and upload in the given order
+    MC_CUDA(c, c->alloc_atoms((size_t)n));
+    c->n = n;
+    c->cur = 0;
+    cudaStream_t st = c->st;
+    std::vector<uint16_t> ty;
+    std::vector<uint8_t> fl;
+    std::vector<mc_float4> v;
+    std::vector<int> ids;
+    if (!type) { ty.assign((size_t)n, 0); type = ty.data(); }
+    if (!flags) { fl.assign((size_t)n, 0); flags = fl.data(); }
+    if (!vel) { v.assign((size_t)n, mc_float4{0.f, 0.f, 0.f, 1.f}); vel = v.data(); }
+    if (!orig_ids) { ids.resize((size_t)n); for (int64_t k = 0; k < n; ++k) ids[(size_t)k] = (int)k; orig_ids = ids.data(); }
+    if (n > 0) {
+        MC_CUDA(c, cudaMemcpyAsync(c->xyzq[0].p, xyzq, n * sizeof(float4), cudaMemcpyHostToDevice, st));
+        MC_CUDA(c, cudaMemcpyAsync(c->vel[0].p, vel, n * sizeof(float4), cudaMemcpyHostToDevice, st));
+        MC_CUDA(c, cudaMemcpyAsync(c->type[0].p, type, n * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+        MC_CUDA(c, cudaMemcpyAsync(c->flags[0].p, flags, n * sizeof(uint8_t), cudaMemcpyHostToDevice, st));
+        MC_CUDA(c, cudaMemcpyAsync(c->orig[0].p, orig_ids, n * sizeof(int), cudaMemcpyHostToDevice, st));
+        MC_CUDA(c, cudaMemsetAsync(c->force.p, 0, n * sizeof(float4), st));
+    }
+    MC_CUDA(c, cudaStreamSynchronize(st));
+    c->identity_order = true;
+    return MC_OK;
+}
+
+extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type,
+                            const mc_float4 *vel_invmass, const uint8_t *flags) {
+    if (!c) return MC_E_INVALID;
+    MC_REQUIRE(c, n >= 0 && n < (int64_t)1 << 31, "mc_set_atoms: 0 <= n < 2^31 required");
+    MC_REQUIRE(c, n == 0 || xyzq, "mc_set_atoms: xyzq is NULL");
+    cudaSetDevice(c->device);
+    c->n_global = n;
+    c->list_valid = false;
+    c->forces_valid = false;
+    c->have_excl = false;
+    c->have_p14 = false;
+    c->n_pairs_listed = 0;
+    if (c->comm_active) return comm_set_atoms(c, n, xyzq, type, vel_invmass, flags);
+    c->n_rows = n;
+    if (type)
+        for (int64_t k = 0; k < n; ++k) MC_REQUIRE(c, type[k] < pair_force_max_types(), "mc_set_atoms: type id out of range");
+    int rc = upload_atoms_local(c, n, xyzq, type, vel_invmass, flags, nullptr);
+    if (rc != MC_OK) return rc;
+    // slot_of_orig = identity
+    std::vector<int> ids((size_t)n);
+    for (int64_t k = 0; k < n; ++k) ids[(size_t)k] = (int)k;
+    if (n) MC_CUDA(c, cudaMemcpy(c->slot_of_orig.p, ids.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    return MC_OK;
+}
+
+int engine_upload_local(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type, const mc_float4 *vel,
+                        const uint8_t *flags, const int *orig_ids) {
+    return upload_atoms_local(c, n, xyzq, type, vel, flags, orig_ids);
+}
+
+extern "C" int mc_set_exclusions(mc_ctx *c, const int32_t *start, const int32_t *idx) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    c->list_valid = false;
+    c->forces_valid = false;
+    if (!start || !idx || start[c->n_global] == 0) { c->have_excl = false; return MC_OK; }
+    const int64_t n = c->n_global, m = start[n];
+    MC_REQUIRE(c, m >= 0, "mc_set_exclusions: negative total");
+    MC_CUDA(c, c->excl_start.ensure((size_t)n + 1));
+    MC_CUDA(c, c->excl_idx.ensure((size_t)m));
+    MC_CUDA(c, cudaMemcpy(c->excl_start.p, start, (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    MC_CUDA(c, cudaMemcpy(c->excl_idx.p, idx, m * sizeof(int32_t), cudaMemcpyHostToDevice));
+    c->have_excl = true;
+    return MC_OK;
+}
+
+extern "C" int mc_set_pairs14(mc_ctx *c, int64_t m, const int32_t *pairs, float scale_lj, float scale_q) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    c->forces_valid = false;
+    c->scale14_lj = scale_lj;
+    c->scale14_q = scale_q;
+    if (m <= 0 || !pairs) { c->have_p14 = false; return MC_OK; }
+    const int64_t n = c->n_global;
+    // symmetric per-atom rows (original ids) so that each atom sums its own partners
+    std::vector<int32_t> start((size_t)n + 1, 0), idx((size_t)2 * m);
+    for (int64_t k = 0; k < m; ++k) {
+        const int32_t i = pairs[2 * k], j = pairs[2 * k + 1];
+        MC_REQUIRE(c, i >= 0 && j >= 0 && i < n && j < n && i != j, "mc_set_pairs14: atom id out of range");
+        start[(size_t)i + 1]++; start[(size_t)j + 1]++;
+    }
+    for (int64_t i = 0; i < n; ++i) start[(size_t)i + 1] += start[(size_t)i];
+    std::vector<int32_t> cur(start.begin(), start.end() - 1);
+    for (int64_t k = 0; k < m; ++k) {
+        const int32_t i = pairs[2 * k], j = pairs[2 * k + 1];
+        idx[(size_t)cur[(size_t)i]++] = j;
+        idx[(size_t)cur[(size_t)j]++] = i;
+    }
+    MC_CUDA(c, c->p14_start.ensure((size_t)n + 1));
+    MC_CUDA(c, c->p14_idx.ensure(idx.size()));
+    MC_CUDA(c, cudaMemcpy(c->p14_start.p, start.data(), start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    MC_CUDA(c, cudaMemcpy(c->p14_idx.p, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    c->have_p14 = true;
+    return MC_OK;
+}
+
+extern "C" int mc_set_positions(mc_ctx *c, const mc_float4 *xyzq) {
+    if (!c || !xyzq) return MC_E_INVALID;
+    MC_REQUIRE(c, !c->comm_active, "mc_set_positions: not available on a decomposed handle; use mc_set_atoms");
+    cudaSetDevice(c->device);
+    const int64_t n = c->n;
+    if (n == 0) return MC_OK;
+    MC_CUDA(c, c->stage.ensure((size_t)n));
+    MC_CUDA(c, cudaMemcpyAsync(c->stage.p, xyzq, n * sizeof(float4), cudaMemcpyHostToDevice, c->st));
+    launch_scatter_from_orig((int)n, c->stage.p, c->orig[c->cur].p, c->xyzq[c->cur].p, 0, c->st, &c->launches);
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
+    c->list_valid = false;
+    c->forces_valid = false;
+    return MC_OK;
+}
+
+extern "C" int mc_set_velocities(mc_ctx *c, const mc_float4 *vel) {
+    if (!c || !vel) return MC_E_INVALID;
+    MC_REQUIRE(c, !c->comm_active, "mc_set_velocities: not available on a decomposed handle; use mc_set_atoms");
+    cudaSetDevice(c->device);
+    const int64_t n = c->n;
+    if (n == 0) return MC_OK;
+    MC_CUDA(c, c->stage.ensure((size_t)n));
+    MC_CUDA(c, cudaMemcpyAsync(c->stage.p, vel, n * sizeof(float4), cudaMemcpyHostToDevice, c->st));
+    launch_scatter_from_orig((int)n, c->stage.p, c->orig[c->cur].p, c->vel[c->cur].p, 0, c->st, &c->launches);
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
+    return MC_OK;
+}
+
+extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
+    if (!c || !name) return MC_E_INVALID;
+    const std::string k(name);
+    if (k == "pair_lanes") {
+        const int v = (int)value;
+        MC_REQUIRE(c, v == 4 || v == 8 || v == 16 || v == 32, "mc_set_option: pair_lanes must be 4, 8, 16 or 32");
+        c->pair_lanes = v;
+    } else if (k == "profiling") {
+        c->profiling = value != 0.0;
+    } else if (k == "rebuild_every") {
+        c->rebuild_every = (int)value;
+    } else {
+        return fail(c, MC_E_INVALID, "mc_set_option: unknown option '" + k + "'");
+    }
+    return MC_OK;
+}
+
+// ---- neighbour build -------------------------------------------------------------------------------
+
+static float list_radius(const mc_ctx *c) { return std::max(c->rc_lj, c->rc_q) + c->skin; }
+
+static int setup_grid(mc_ctx *c) {
+    const float r_list = list_radius(c);
+    MC_CUDA(c, c->grid.ensure(1));
+    MC_CUDA(c, c->bbox.ensure(8));
+    const double cw_min = (double)r_list * 1.001 + 1e-3;  // same margin as oracle/md_oracle.c
+    if (c->periodic) {
+        GridParams g;
+        long long ncell = 1;
+        for (int a = 0; a < 3; ++a) {
+            if (2.0f * r_list > c->ext[a])
+                return fail(c, MC_E_INVALID, "neighbour build: cutoff + skin exceeds half the periodic box on axis " +
+                                                 std::to_string(a) + " (minimum image would be ambiguous)");
+            int m = (int)std::floor((double)c->ext[a] / cw_min);
+            m = std::max(1, std::min(m, 1024));
+            g.nc[a] = m;
+            g.lo[a] = c->lo[a];
+            g.ext[a] = c->ext[a];
+            g.inv_ext[a] = 1.0f / c->ext[a];
+            g.inv_cw[a] = (float)((double)m / (double)c->ext[a]);
+            ncell *= m;
+        }
+        g.ncell = (int)ncell;
+        g.periodic = 1;
+        c->ncell_cap = (size_t)ncell;
+        c->h_grid = g;
+        MC_CUDA(c, cudaMemcpyAsync(c->grid.p, &c->h_grid, sizeof(GridParams), cudaMemcpyHostToDevice, c->st));
+    } else {
+        // vacuum: the grid follows the bounding box at every build; cap the cell count
+        c->ncell_cap = std::max<size_t>(4096, std::min<size_t>((size_t)c->n, (size_t)1 << 22));
+        c->cw_min = (float)cw_min;
+    }
+    MC_CUDA(c, c->cell_start.ensure(c->ncell_cap + 2));
+    int bits = 1;
+    while (((size_t)1 << bits) < c->ncell_cap) ++bits;
+    c->key_bits = bits;
+    c->grid_dirty = false;
+    return MC_OK;
+}
+
+int engine_build_list(mc_ctx *c) {
+    const int n = (int)c->n;
+    cudaStream_t st = c->st;
+    if (c->grid_dirty) { int rc = setup_grid(c); if (rc != MC_OK) return rc; }
+    if (n == 0) { c->list_valid = true; return MC_OK; }
+    TimedRegion tr(c, c->build_acc);
+    if (!c->periodic)
+        launch_bbox(c->xyzq[c->cur].p, n, c->bbox.p, c->cw_min, (int)c->ncell_cap, c->grid.p, st, &c->launches);
+    MC_CUDA(c, c->keys[0].ensure((size_t)n)); MC_CUDA(c, c->keys[1].ensure((size_t)n));
+    MC_CUDA(c, c->vals[0].ensure((size_t)n)); MC_CUDA(c, c->vals[1].ensure((size_t)n));
+    MC_CUDA(c, c->scratch.ensure(std::max(radix_scratch_elems((size_t)n), scan_scratch_elems((size_t)n + 1)) + 64));
+    launch_wrap_key(c->xyzq[c->cur].p, n, c->grid.p, c->keys[0].p, c->vals[0].p, st, &c->launches);
+    uint32_t *kk[2] = {c->keys[0].p, c->keys[1].p}, *vv[2] = {c->vals[0].p, c->vals[1].p};
+    const int which = radix_sort_pairs(kk, vv, (size_t)n, c->key_bits, c->scratch.p, st, &c->launches);
+    const int nx = c->cur ^ 1;
+    ReorderArrays ra;
+    ra.xyzq_in = c->xyzq[c->cur].p; ra.xyzq_out = c->xyzq[nx].p; ra.xref = c->xref.p;
+    ra.vel_in = c->vel[c->cur].p; ra.vel_out = c->vel[nx].p;
+    ra.type_in = c->type[c->cur].p; ra.type_out = c->type[nx].p;
+    ra.flags_in = c->flags[c->cur].p; ra.flags_out = c->flags[nx].p;
+    ra.orig_in = c->orig[c->cur].p; ra.orig_out = c->orig[nx].p; ra.slot_of_orig = c->slot_of_orig.p;
+    ra.cell_start = c->cell_start.p;
+    launch_reorder(n, kk[which], vv[which], c->grid.p, ra, st, &c->launches);
+    c->cur = nx;
+    c->identity_order = false;
+    const float r_list = list_radius(c);
+    const float rl2 = r_list * r_list;
+    const int n_rows = (int)c->n_rows_sorted();
+    const int32_t *es = c->have_excl ? c->excl_start.p : nullptr, *ei = c->have_excl ? c->excl_idx.p : nullptr;
+    launch_sweep(false, n_rows, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, c->orig[c->cur].p, es, ei,
+                 c->nbr_count.p, nullptr, nullptr, st, &c->launches);
+    exclusive_scan_u32(c->nbr_count.p, c->nbr_start.p, (size_t)n_rows, 1, c->scratch.p, st, &c->launches);
+    uint32_t *h_total = reinterpret_cast<uint32_t *>(c->h_pinned);
+    MC_CUDA(c, cudaMemcpyAsync(h_total, c->nbr_start.p + n_rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    MC_CUDA(c, cudaStreamSynchronize(st));
+    const size_t total = *h_total;
+    if (total > c->nbr_list.n) MC_CUDA(c, c->nbr_list.ensure(total + total / 8 + 1024));
+    launch_sweep(true, n_rows, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, c->orig[c->cur].p, es, ei,
+                 c->nbr_count.p, c->nbr_start.p, c->nbr_list.p, st, &c->launches);
+    MC_CUDA(c, cudaMemsetAsync(c->rebuild_flag.p, 0, sizeof(int), st));
+    tr.stop();
+    MC_CUDA(c, cudaGetLastError());
+    c->n_padded_entries = (int64_t)total;
+    c->list_valid = true;
+    c->forces_valid = false;
+    c->n_rebuilds++;
+    c->steps_since_build = 0;
+    c->pairs_dirty = true;
+    return MC_OK;
+}
+
+extern "C" int mc_build_neighbors(mc_ctx *c) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, c->rc_lj > 0.f, "mc_build_neighbors: call mc_set_cutoffs first");
+    MC_REQUIRE(c, c->n_types > 0, "mc_build_neighbors: call mc_set_lj_table first");
+    if (c->comm_active) return comm_rebuild(c);
+    int rc = engine_build_list(c);
+    if (rc != MC_OK) return rc;
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
+    return MC_OK;
+}
+
+// ---- forces ------------------------------------------------------------------------------------------
+
+static NbParams make_params(const mc_ctx *c) {
+    NbParams p;
+    for (int a = 0; a < 3; ++a) {
+        p.ext[a] = c->periodic ? c->ext[a] : 1.f;
+        p.inv_ext[a] = c->periodic ? 1.0f / c->ext[a] : 1.f;
+    }
+    p.rc2_lj = c->rc_lj * c->rc_lj;
+    p.rc2_q = c->rc_q * c->rc_q;
+    p.alpha = c->alpha;
+    p.sig2 = c->sig2_0;
+    p.eps24 = c->eps24_0;
+    p.periodic = c->periodic ? 1 : 0;
+    p.n_types = c->n_types;
+    return p;
+}
+
+int engine_launch_forces(mc_ctx *c) {
+    PairLaunch L;
+    L.n_rows = (int)c->n_rows_sorted();
+    L.xyzq = c->xyzq[c->cur].p;
+    L.type = c->type[c->cur].p;
+    L.nbr_start = c->nbr_start.p; L.nbr_count = c->nbr_count.p; L.nbr_list = c->nbr_list.p;
+    L.ljtab = c->ljtab.p;
+    L.p = make_params(c);
+    L.lj_on = c->lj_disabled ? 0 : 1;
+    L.coul = c->coul_disabled ? MC_COULOMB_NONE : c->coul_mode;
+    L.multi = c->n_types > 1;
+    L.lanes = c->pair_lanes;
+    L.force = c->force.p;
+    {
+        TimedRegion tr(c, c->pair_acc);
+        launch_pair_force(L, c->st, &c->launches);
+        tr.stop();
+    }
+    if (c->have_p14)
+        launch_pairs14(L.n_rows, L.xyzq, L.type, c->orig[c->cur].p, c->slot_of_orig.p, c->p14_start.p, c->p14_idx.p,
+                       c->ljtab.p, L.p, c->scale14_lj, c->scale14_q, L.lj_on, (L.coul != MC_COULOMB_NONE) ? 1 : 0,
+                       c->force.p, c->st, &c->launches);
+    MC_CUDA(c, cudaGetLastError());
+    c->forces_valid = true;
+    return MC_OK;
+}
+
+static int ensure_ready(mc_ctx *c, const char *who) {
+    MC_REQUIRE(c, c->rc_lj > 0.f, std::string(who) + ": call mc_set_cutoffs first");
+    MC_REQUIRE(c, c->n_types > 0, std::string(who) + ": call mc_set_lj_table first");
+    if (!c->list_valid) {
+        int rc = c->comm_active ? comm_rebuild(c) : engine_build_list(c);
+        if (rc != MC_OK) return rc;
+    }
+    return MC_OK;
+}
+
+extern "C" int mc_compute_forces(mc_ctx *c) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    int rc = ensure_ready(c, "mc_compute_forces");
+    if (rc != MC_OK) return rc;
+    if (c->comm_active && (rc = comm_halo_positions(c)) != MC_OK) return rc;
+    if ((rc = engine_launch_forces(c)) != MC_OK) return rc;
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
+    c->collect_timings();
+    return MC_OK;
+}
+
+// ---- velocity Verlet -----------------------------------------------------------------------------------
+
+extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, n_steps >= 0 && dt > 0.f, "mc_step: n_steps >= 0 and dt > 0 required");
+    int rc = ensure_ready(c, "mc_step");
+    if (rc != MC_OK) return rc;
+    cudaStream_t st = c->st;
+    const float *d_ext = nullptr;
+    if (ext_forces) {
+        MC_CUDA(c, c->ext_force.ensure((size_t)3 * c->n_global));
+        MC_CUDA(c, cudaMemcpyAsync(c->ext_force.p, ext_forces, sizeof(float) * 3 * c->n_global, cudaMemcpyHostToDevice, st));
+        d_ext = c->ext_force.p;
+    }
+    if (!c->forces_valid) {
+        if (c->comm_active && (rc = comm_halo_positions(c)) != MC_OK) return rc;
+        if ((rc = engine_launch_forces(c)) != MC_OK) return rc;
+    }
+    const float max_disp2 = 0.25f * c->skin * c->skin;
+    int *h_flag = reinterpret_cast<int *>(c->h_pinned) + 8;
+    if (!c->ev_step_a) { MC_CUDA(c, cudaEventCreate(&c->ev_step_a)); MC_CUDA(c, cudaEventCreate(&c->ev_step_b)); }
+    MC_CUDA(c, cudaEventRecord(c->ev_step_a, st));
+    for (int s = 0; s < n_steps; ++s) {
+        const int rows = (int)c->n_rows_sorted();
+        {
+            TimedRegion tr(c, c->integ_acc);
+            launch_kick_drift(rows, c->xyzq[c->cur].p, c->vel[c->cur].p, c->force.p, d_ext, c->orig[c->cur].p,
+                              c->flags[c->cur].p, c->xref.p, 0.5f * dt, dt, max_disp2, c->rebuild_flag.p, st, &c->launches);
+            tr.stop();
+        }
+        c->steps_since_build++;
+        bool rebuild;
+        if (c->rebuild_every > 0) {
+            rebuild = c->steps_since_build >= c->rebuild_every;
+        } else {
+            MC_CUDA(c, cudaMemcpyAsync(h_flag, c->rebuild_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            MC_CUDA(c, cudaStreamSynchronize(st));
+            rebuild = *h_flag != 0;
+            if (c->comm_active && (rc = comm_agree_flag(c, &rebuild)) != MC_OK) return rc;
+        }
+        if (rebuild) {
+            rc = c->comm_active ? comm_rebuild(c) : engine_build_list(c);
+            if (rc != MC_OK) return rc;
+        } else if (c->comm_active && (rc = comm_halo_positions(c)) != MC_OK) {
+            return rc;
+        }
+        if ((rc = engine_launch_forces(c)) != MC_OK) return rc;
+        {
+            TimedRegion tr(c, c->integ_acc);
+            launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p, c->vel[c->cur].p, c->force.p, d_ext,
+                              c->orig[c->cur].p, c->flags[c->cur].p, c->xref.p, 0.5f * dt, 0.f, 0.f, c->rebuild_flag.p, st,
+                              &c->launches);
+            tr.stop();
+        }
+        c->n_steps++;
+    }
+    MC_CUDA(c, cudaEventRecord(c->ev_step_b, st));
+    MC_CUDA(c, cudaGetLastError());
+    MC_CUDA(c, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    MC_CUDA(c, cudaEventElapsedTime(&ms, c->ev_step_a, c->ev_step_b));
+    c->last_step_ms = ms;
+    c->collect_timings();
+    return MC_OK;
+}
+
+extern "C" double mc_last_step_ms(mc_ctx *c) { return c ? c->last_step_ms : 0.0; }
+
+// ---- read-back -------------------------------------------------------------------------------------------
+
+static int read_sorted_to_orig(mc_ctx *c, const float4 *sorted, mc_float4 *out) {
+    const int64_t n = c->n_rows_sorted();
+    if (n == 0) return MC_OK;
+    MC_CUDA(c, c->stage.ensure((size_t)c->n_global));
+    if (c->comm_active) MC_CUDA(c, cudaMemsetAsync(c->stage.p, 0, sizeof(float4) * c->n_global, c->st));
+    launch_gather_to_orig((int)n, sorted, c->orig[c->cur].p, c->stage.p, c->st, &c->launches);
+    MC_CUDA(c, cudaMemcpyAsync(out, c->stage.p, sizeof(float4) * c->n_global, cudaMemcpyDeviceToHost, c->st));
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
+    return MC_OK;
+}
+
+extern "C" int mc_get_positions(mc_ctx *c, mc_float4 *out) {
+    if (!c || !out) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    return read_sorted_to_orig(c, c->xyzq[c->cur].p, out);
+}
+
+extern "C" int mc_get_velocities(mc_ctx *c, mc_float4 *out) {
+    if (!c || !out) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    return read_sorted_to_orig(c, c->vel[c->cur].p, out);
+}
+
+extern "C" int mc_get_forces(mc_ctx *c, mc_float4 *out) {
+    if (!c || !out) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, c->forces_valid, "mc_get_forces: no force evaluation since the last change; call mc_compute_forces");
+    return read_sorted_to_orig(c, c->force.p, out);
+}
+
+extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
+    if (!c || !out) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, c->forces_valid, "mc_get_energy: no force evaluation since the last change; call mc_compute_forces");
+    MC_CUDA(c, c->red_partial.ensure((size_t)energy_partial_elems()));
+    MC_CUDA(c, c->red_out.ensure(4));
+    launch_energy_reduce((int)c->n_rows_sorted(), c->force.p, c->vel[c->cur].p, c->red_partial.p, c->red_out.p, c->st,
+                         &c->launches);
+    double h[3];
+    MC_CUDA(c, cudaMemcpyAsync(h, c->red_out.p, sizeof(h), cudaMemcpyDeviceToHost, c->st));
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
+    if (c->comm_active) { int rc = comm_allreduce3(c, h); if (rc != MC_OK) return rc; }
+    memset(out, 0, sizeof(*out));
+    out->energy_potential_nonbonded = 0.5 * h[0];  // every pair sits in two rows
+    out->energy_potential_bonded = 0.0;
+    out->energy_potential = out->energy_potential_nonbonded;
+    out->energy_kinetic = h[1] / (double)MC_ACCEL_CONV;
+    out->temperature = h[2] > 0 ? 2.0 * out->energy_kinetic / (3.0 * h[2] * MC_KB) : 0.0;
+    return MC_OK;
+}
+
+extern "C" int mc_get_stats(mc_ctx *c, mc_stats *out) {
+    if (!c || !out) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    memset(out, 0, sizeof(*out));
+    if (c->pairs_dirty && c->list_valid && c->n_rows_sorted() > 0) {
+        // true (unpadded) entry count = sum of the row lengths
+        MC_CUDA(c, c->scratch.ensure(scan_scratch_elems((size_t)c->n + 1) + 64));
+        MC_CUDA(c, c->cnt_orig.ensure((size_t)c->n + 1));
+        exclusive_scan_u32(c->nbr_count.p, c->cnt_orig.p, (size_t)c->n_rows_sorted(), 0, c->scratch.p, c->st, &c->launches);
+        uint32_t tot = 0;
+        MC_CUDA(c, cudaMemcpyAsync(&tot, c->cnt_orig.p + c->n_rows_sorted(), sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
+        MC_CUDA(c, cudaStreamSynchronize(c->st));
+        c->n_pairs_listed = tot;
+        c->pairs_dirty = false;
+    }
+    out->n_atoms = c->n_rows_sorted();
+    out->n_ghosts = c->n - c->n_rows_sorted();
+    out->n_pairs_listed = c->n_pairs_listed;
+    out->n_rebuilds = c->n_rebuilds;
+    out->n_steps = c->n_steps;
+    out->n_kernel_launches = c->launches;
+    for (int a = 0; a < 3; ++a) out->n_cells[a] = c->periodic ? c->h_grid.nc[a] : 0;
+    out->pair_ms_sum = c->pair_acc.ms; out->pair_launches_timed = c->pair_acc.count;
+    out->build_ms_sum = c->build_acc.ms; out->builds_timed = c->build_acc.count;
+    out->integrate_ms_sum = c->integ_acc.ms; out->integrate_launches_timed = c->integ_acc.count;
+    out->halo_ms_sum = c->halo_acc.ms; out->halos_timed = c->halo_acc.count;
+    return MC_OK;
+}
+
+extern "C" int mc_reset_timers(mc_ctx *c) {
+    if (!c) return MC_E_INVALID;
+    c->pair_acc = c->build_acc = c->integ_acc = c->halo_acc = TimeAcc();
+    return MC_OK;
+}
+
+extern "C" int mc_get_neighbors(mc_ctx *c, int64_t *start, int32_t *idx, int64_t cap, int64_t *total) {
+    if (!c || !start || !total) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, !c->comm_active, "mc_get_neighbors: single-GPU handles only");
+    MC_REQUIRE(c, c->list_valid, "mc_get_neighbors: no current list; call mc_build_neighbors");
+    const int n = (int)c->n;
+    if (n == 0) { start[0] = 0; *total = 0; return MC_OK; }
+    MC_CUDA(c, c->cnt_orig.ensure((size_t)n + 1));
+    MC_CUDA(c, c->start_orig.ensure((size_t)n + 1));
+    MC_CUDA(c, c->export_rows.ensure((size_t)c->n_padded_entries + 1));
+    MC_CUDA(c, c->scratch.ensure(scan_scratch_elems((size_t)n + 1) + 64));
+    launch_export_rows(n, c->orig[c->cur].p, c->nbr_count.p, c->nbr_start.p, c->nbr_list.p, c->cnt_orig.p,
+                       c->start_orig.p, c->export_rows.p, c->scratch.p, c->st, &c->launches);
+    std::vector<uint32_t> hs((size_t)n + 1);
+    MC_CUDA(c, cudaMemcpyAsync(hs.data(), c->start_orig.p, hs.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
+    for (int k = 0; k <= n; ++k) start[k] = hs[(size_t)k];
+    *total = hs[(size_t)n];
+    if (!idx) return MC_OK;
+    if (cap < *total) return fail(c, MC_E_CAPACITY, "mc_get_neighbors: idx capacity too small");
+    MC_CUDA(c, cudaMemcpy(idx, c->export_rows.p, (size_t)*total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return MC_OK;
+}
+
+// ---- stand-alone kernel timing ----------------------------------------------------------------------------
+
+extern "C" int mc_time_kernels(mc_ctx *c, int reps, int flush_l2) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, reps > 0, "mc_time_kernels: reps > 0 required");
+    int rc = ensure_ready(c, "mc_time_kernels");
+    if (rc != MC_OK) return rc;
+    const bool prof = c->profiling;
+    c->profiling = true;
+    const size_t flush_n = flush_l2 ? (std::max<size_t>(c->l2_bytes, (size_t)128 << 20) * 2) / sizeof(float4) : 0;
+    if (flush_n) MC_CUDA(c, c->flush.ensure(flush_n));
+    const TimeAcc keep_pair = c->pair_acc;
+    c->pair_acc = TimeAcc();
+    for (int r = 0; r < reps + 3; ++r) {
+        if (r == 3) { MC_CUDA(c, cudaStreamSynchronize(c->st)); c->collect_timings(); c->pair_acc = TimeAcc(); }
+        if (flush_n) launch_l2_flush(c->flush.p, flush_n, c->st, &c->launches);
+        if ((rc = engine_launch_forces(c)) != MC_OK) return rc;
+    }
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
+    c->collect_timings();
+    c->last_pair_ms = c->pair_acc.count ? c->pair_acc.ms / c->pair_acc.count : 0.0;
+    c->pair_acc = keep_pair;
+    c->profiling = prof;
+    return MC_OK;
+}
+
+extern "C" double mc_last_pair_kernel_ms(mc_ctx *c) { return c ? c->last_pair_ms : 0.0; }
+
+// ---- docking scan -------------------------------------------------------------------------------------------
+
+extern "C" int mc_dock_score(mc_ctx *c, int64_t n_rec, const mc_float4 *rec_xyzq, const uint16_t *rec_type,
+                             const uint8_t *rec_hydrophobic, int64_t n_lig, const mc_float4 *lig_xyzq,
+                             const uint16_t *lig_type, const uint8_t *lig_hydrophobic, const float lig_anchor[3],
+                             int n_rec_types, int n_lig_types, const float *ljtab, int64_t n_poses, const float *poses,
+                             float *out) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, n_rec > 0 && n_lig > 0 && n_poses >= 0 && rec_xyzq && lig_xyzq && rec_type && lig_type && ljtab &&
+                      lig_anchor && (n_poses == 0 || (poses && out)),
+               "mc_dock_score: NULL or empty argument");
+    MC_REQUIRE(c, n_rec_types > 0 && n_lig_types > 0, "mc_dock_score: type counts must be positive");
+    MC_REQUIRE(c, dock_smem_bytes((int)n_lig, n_rec_types, n_lig_types) <= 200 * 1024,
+               "mc_dock_score: ligand + LJ table exceed the 200 KB shared-memory tile");
+    if (n_poses == 0) return MC_OK;
+    cudaStream_t st = c->st;
+    std::vector<uint32_t> rm((size_t)n_rec), lm((size_t)n_lig);
+    for (int64_t r = 0; r < n_rec; ++r) {
+        MC_REQUIRE(c, rec_type[r] < n_rec_types, "mc_dock_score: receptor type out of range");
+        rm[(size_t)r] = rec_type[r] | ((rec_hydrophobic && rec_hydrophobic[r]) ? 0x10000u : 0u);
+    }
+    for (int64_t a = 0; a < n_lig; ++a) {
+        MC_REQUIRE(c, lig_type[a] < n_lig_types, "mc_dock_score: ligand type out of range");
+        lm[(size_t)a] = lig_type[a] | ((lig_hydrophobic && lig_hydrophobic[a]) ? 0x10000u : 0u);
+    }
+    std::vector<float2> tab((size_t)n_rec_types * n_lig_types);
+    for (size_t k = 0; k < tab.size(); ++k) tab[k] = make_float2(ljtab[2 * k] * ljtab[2 * k], 4.f * ljtab[2 * k + 1]);
+    MC_CUDA(c, c->d_rec.ensure((size_t)n_rec)); MC_CUDA(c, c->d_rec_meta.ensure((size_t)n_rec));
+    MC_CUDA(c, c->d_lig.ensure((size_t)n_lig)); MC_CUDA(c, c->d_lig_meta.ensure((size_t)n_lig));
+    MC_CUDA(c, c->d_dock_tab.ensure(tab.size()));
+    MC_CUDA(c, c->d_poses.ensure((size_t)7 * n_poses)); MC_CUDA(c, c->d_scores.ensure((size_t)5 * n_poses));
+    MC_CUDA(c, cudaMemcpyAsync(c->d_rec.p, rec_xyzq, n_rec * sizeof(float4), cudaMemcpyHostToDevice, st));
+    MC_CUDA(c, cudaMemcpyAsync(c->d_rec_meta.p, rm.data(), n_rec * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    MC_CUDA(c, cudaMemcpyAsync(c->d_lig.p, lig_xyzq, n_lig * sizeof(float4), cudaMemcpyHostToDevice, st));
+    MC_CUDA(c, cudaMemcpyAsync(c->d_lig_meta.p, lm.data(), n_lig * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    MC_CUDA(c, cudaMemcpyAsync(c->d_dock_tab.p, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+    MC_CUDA(c, cudaMemcpyAsync(c->d_poses.p, poses, sizeof(float) * 7 * n_poses, cudaMemcpyHostToDevice, st));
+    {
+        TimedRegion tr(c, c->dock_acc);
+        launch_dock_score((int)n_rec, c->d_rec.p, c->d_rec_meta.p, (int)n_lig, c->d_lig.p, c->d_lig_meta.p,
+                          make_float3(lig_anchor[0], lig_anchor[1], lig_anchor[2]), n_rec_types, n_lig_types,
+                          c->d_dock_tab.p, (int)n_poses, c->d_poses.p, c->d_scores.p, st, &c->launches);
+        tr.stop();
+    }
+    MC_CUDA(c, cudaGetLastError());
+    MC_CUDA(c, cudaMemcpyAsync(out, c->d_scores.p, sizeof(float) * 5 * n_poses, cudaMemcpyDeviceToHost, st));
+    MC_CUDA(c, cudaStreamSynchronize(st));
+    c->collect_timings();
+    c->last_dock_ms = c->dock_acc.count ? c->dock_acc.ms / c->dock_acc.count : 0.0;
+    c->dock_acc = TimeAcc();
+    return MC_OK;
+}
+
+extern "C" double mc_last_dock_kernel_ms(mc_ctx *c) { return c ? c->last_dock_ms : 0.0; }

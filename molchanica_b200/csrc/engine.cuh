@@ -1,0 +1,189 @@
+// engine.cuh -- the handle behind include/molchanica_md.h (shared by engine.cu and comm.cu)
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    // grow-only; contents are NOT preserved across a growth
+    cudaError_t ensure(size_t want) {
+        if (want <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        if (want == 0) want = 1;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct TimeAcc {
+    double ms = 0.0;
+    int64_t count = 0;
+};
+
+struct EventPair {
+    cudaEvent_t a, b;
+};
+
+struct CommState;  // comm.cu
+
+struct mc_ctx {
+    int device = 0;
+    int n_sms = 148;
+    size_t l2_bytes = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+    void *h_pinned = nullptr;
+
+    // system
+    int64_t n = 0;         // atoms held locally (owned + ghosts)
+    int64_t n_rows = 0;    // atoms owned locally (rows of the list); == n on a single GPU
+    int64_t n_global = 0;  // atoms of the whole system (original ids run over this range)
+    bool periodic = false;
+    float lo[3] = {0, 0, 0}, ext[3] = {1, 1, 1};
+    float rc_lj = 0, rc_q = 0, skin = 0, alpha = 0.35f;
+    int coul_mode = MC_COULOMB_NONE;
+    bool lj_disabled = false, coul_disabled = false;
+    int n_types = 0;
+    float sig2_0 = 0, eps24_0 = 0;
+    float scale14_lj = 0.5f, scale14_q = 1.0f / 1.2f;
+    bool have_excl = false, have_p14 = false;
+
+    // state flags
+    bool grid_dirty = true, list_valid = false, forces_valid = false, identity_order = true, pairs_dirty = true;
+    int cur = 0;
+    int key_bits = 1;
+    size_t ncell_cap = 0;
+    float cw_min = 0;
+    GridParams h_grid{};
+    int pair_lanes = 8;
+    int rebuild_every = 0;
+    int steps_since_build = 0;
+    bool profiling = false;
+
+    // counters
+    int64_t launches = 0, n_rebuilds = 0, n_steps = 0, n_pairs_listed = 0, n_padded_entries = 0;
+    TimeAcc pair_acc, build_acc, integ_acc, halo_acc, dock_acc;
+    double last_pair_ms = 0, last_dock_ms = 0, last_step_ms = 0;
+    cudaEvent_t ev_step_a = nullptr, ev_step_b = nullptr;
+
+    // device arrays
+    DevBuf<float4> xyzq[2], vel[2], force, xref, stage, flush;
+    DevBuf<uint16_t> type[2];
+    DevBuf<uint8_t> flags[2];
+    DevBuf<int> orig[2], slot_of_orig, rebuild_flag;
+    DevBuf<uint32_t> keys[2], vals[2], scratch, cell_start, nbr_count, nbr_start, nbr_list;
+    DevBuf<uint32_t> cnt_orig, start_orig, export_rows;
+    DevBuf<int32_t> excl_start, excl_idx, p14_start, p14_idx;
+    DevBuf<float2> ljtab, d_dock_tab;
+    DevBuf<float> bbox, ext_force, d_poses, d_scores;
+    DevBuf<GridParams> grid;
+    DevBuf<double> red_partial, red_out;
+    DevBuf<float4> d_rec, d_lig;
+    DevBuf<uint32_t> d_rec_meta, d_lig_meta;
+
+    // event timing
+    std::vector<EventPair> ev_pool;
+    struct Pending { int ev; TimeAcc *acc; };
+    std::vector<Pending> pending;
+    size_t ev_used = 0;
+
+    // domain decomposition
+    bool comm_active = false;
+    CommState *comm = nullptr;
+
+    int64_t n_rows_sorted() const { return n_rows; }
+
+    cudaError_t alloc_atoms(size_t m) {
+        cudaError_t e;
+        const size_t cap = m + 8;
+        for (int b = 0; b < 2; ++b) {
+            if ((e = xyzq[b].ensure(cap)) != cudaSuccess) return e;
+            if ((e = vel[b].ensure(cap)) != cudaSuccess) return e;
+            if ((e = type[b].ensure(cap)) != cudaSuccess) return e;
+            if ((e = flags[b].ensure(cap)) != cudaSuccess) return e;
+            if ((e = orig[b].ensure(cap)) != cudaSuccess) return e;
+        }
+        if ((e = force.ensure(cap)) != cudaSuccess) return e;
+        if ((e = xref.ensure(cap)) != cudaSuccess) return e;
+        if ((e = slot_of_orig.ensure(std::max<size_t>(cap, (size_t)n_global + 8))) != cudaSuccess) return e;
+        if ((e = nbr_count.ensure(cap)) != cudaSuccess) return e;
+        if ((e = nbr_start.ensure(cap + 1)) != cudaSuccess) return e;
+        if ((e = rebuild_flag.ensure(4)) != cudaSuccess) return e;
+        return cudaMemset(rebuild_flag.p, 0, 4 * sizeof(int));
+    }
+
+    void free_all() {
+        for (int b = 0; b < 2; ++b) { xyzq[b].release(); vel[b].release(); type[b].release(); flags[b].release(); orig[b].release(); keys[b].release(); vals[b].release(); }
+        force.release(); xref.release(); stage.release(); flush.release(); slot_of_orig.release(); rebuild_flag.release();
+        scratch.release(); cell_start.release(); nbr_count.release(); nbr_start.release(); nbr_list.release();
+        cnt_orig.release(); start_orig.release(); export_rows.release();
+        excl_start.release(); excl_idx.release(); p14_start.release(); p14_idx.release();
+        ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); d_poses.release(); d_scores.release();
+        grid.release(); red_partial.release(); red_out.release(); d_rec.release(); d_lig.release();
+        d_rec_meta.release(); d_lig_meta.release();
+    }
+
+    // resolve the CUDA-event pairs recorded since the last call (stream must be idle)
+    void collect_timings() {
+        for (const Pending &p : pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev_pool[(size_t)p.ev].a, ev_pool[(size_t)p.ev].b) == cudaSuccess) {
+                p.acc->ms += ms;
+                p.acc->count += 1;
+            }
+        }
+        pending.clear();
+        ev_used = 0;
+    }
+};
+
+// Brackets kernel launches with CUDA events on the handle's stream when profiling is on.
+struct TimedRegion {
+    mc_ctx *c;
+    TimeAcc &acc;
+    int ev = -1;
+    TimedRegion(mc_ctx *c_, TimeAcc &a) : c(c_), acc(a) {
+        if (!c->profiling || c->ev_used >= 8192) return;
+        if (c->ev_used >= c->ev_pool.size()) {
+            EventPair p;
+            if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+            c->ev_pool.push_back(p);
+        }
+        ev = (int)c->ev_used++;
+        cudaEventRecord(c->ev_pool[(size_t)ev].a, c->st);
+    }
+    void stop() {
+        if (ev < 0) return;
+        cudaEventRecord(c->ev_pool[(size_t)ev].b, c->st);
+        c->pending.push_back({ev, &acc});
+        ev = -1;
+    }
+    ~TimedRegion() { stop(); }
+};
+
+// engine.cu
+int engine_build_list(mc_ctx *c);
+int engine_launch_forces(mc_ctx *c);
+int engine_upload_local(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type, const mc_float4 *vel,
+                        const uint8_t *flags, const int *orig_ids);
+
+// comm.cu -- slab domain decomposition + ghost-atom halo exchange
+int comm_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type, const mc_float4 *vel,
+                   const uint8_t *flags);
+int comm_rebuild(mc_ctx *c);          // migrate + re-select ghosts + engine_build_list
+int comm_halo_positions(mc_ctx *c);   // per-step ghost position refresh
+int comm_agree_flag(mc_ctx *c, bool *flag);
+int comm_allreduce3(mc_ctx *c, double v[3]);
+void comm_destroy(mc_ctx *c);

@@ -1,0 +1,14 @@
+// integrate.cuh -- host-side launchers of integrate.cu
+#pragma once
+#include "common.cuh"
+
+// v += (F + F_ext) / m * kick * 418.4 ; then (drift != 0) x += v * drift and the displacement
+// since the last list build is checked against max_disp2 (flag raised when exceeded).
+void launch_kick_drift(int n_rows, float4 *xyzq, float4 *vel, const float4 *force, const float *ext_force,
+                       const int *orig, const uint8_t *flags, const float4 *xref, float kick, float drift,
+                       float max_disp2, int *rebuild_flag, cudaStream_t st, int64_t *launches);
+// original-order <-> cell-order copies
+void launch_gather_to_orig(int n, const float4 *sorted, const int *orig, float4 *out, cudaStream_t st, int64_t *launches);
+void launch_scatter_from_orig(int n, const float4 *in_orig, const int *orig, float4 *sorted, int keep_w, cudaStream_t st,
+                              int64_t *launches);
+void launch_l2_flush(float4 *buf, size_t n_float4, cudaStream_t st, int64_t *launches);

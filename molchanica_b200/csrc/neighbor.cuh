@@ -1,0 +1,25 @@
+// neighbor.cuh -- host-side launchers of neighbor.cu
+#pragma once
+#include "common.cuh"
+
+struct ReorderArrays {
+    const float4 *xyzq_in; float4 *xyzq_out; float4 *xref;
+    const float4 *vel_in; float4 *vel_out;
+    const uint16_t *type_in; uint16_t *type_out;
+    const uint8_t *flags_in; uint8_t *flags_out;
+    const int *orig_in; int *orig_out; int *slot_of_orig;
+    uint32_t *cell_start;
+};
+
+void launch_bbox(const float4 *xyzq, int n, float *bb, float cw_min, int max_cells, GridParams *g, cudaStream_t st,
+                 int64_t *launches);
+void launch_wrap_key(float4 *xyzq, int n, const GridParams *g, uint32_t *keys, uint32_t *vals, cudaStream_t st,
+                     int64_t *launches);
+void launch_reorder(int n, const uint32_t *skeys, const uint32_t *svals, const GridParams *g, const ReorderArrays &a,
+                    cudaStream_t st, int64_t *launches);
+void launch_sweep(bool fill, int n_rows, const float4 *xyzq, const uint32_t *cell_start, const GridParams *g, float rl2,
+                  const int *orig, const int32_t *excl_start, const int32_t *excl_idx, uint32_t *nbr_count,
+                  const uint32_t *nbr_start, uint32_t *nbr_list, cudaStream_t st, int64_t *launches);
+void launch_export_rows(int n, const int *orig, const uint32_t *nbr_count, const uint32_t *nbr_start,
+                        const uint32_t *nbr_list, uint32_t *cnt_orig, uint32_t *start_orig, uint32_t *rows,
+                        uint32_t *scan_scratch, cudaStream_t st, int64_t *launches);

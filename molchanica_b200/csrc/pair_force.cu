@@ -1,0 +1,291 @@
+// pair_force.cu -- the nonbonded pair-force inner loop: Lennard-Jones 12-6 + cutoff Coulomb over a
+// full Verlet neighbour list.  Replaces lj_force_kernel / coulomb_force_kernel
+// of reference src/cuda/cuda.cu:10-102 (all-pairs, dense per-pair sigma/eps arrays, RMW of out[i]
+// in the inner loop) with:
+//   - float4 xyzq records (one 16-byte gather per neighbour instead of float3 + charge)
+//   - a T x T (sigma^2, 24 eps) table in shared memory instead of 8 B/pair of parameters in HBM
+//   - LANES lanes per target atom reading LANES consecutive list entries (one 32-byte sector for
+//     LANES = 8), partial forces reduced with warp shuffles -- no atomics, no RMW of the output
+//   - full lists: every atom owns its row, so the result needs no scatter and no reverse halo
+//
+// Roofline: HBM.  Algorithmic bytes per launch = 32 N + 20 P_full: per atom 16 B xyzq
+// read + 16 B (fx, fy, fz, e) write; per list entry 4 B index + 16 B gathered xyzq_j.
+//
+// Pair arithmetic follows reference src/cuda/util.cu:
+//   LJ       sr = sigma/r; |F| = 24 eps (2 sr^12 - sr^6)/r; E = 4 eps (sr^12 - sr^6)      (:93-139)
+//   Coulomb  F = dir * q_i q_j / (r^2 + 1e-6), dir = (r_i - r_j)/r                         (:54-63)
+//   min image d -= rintf(d/ext)*ext                                                         (:65-71)
+// The cutoff decision uses the oracle's exact fp32 r^2 (no fma) so that both sides mask the
+// same pairs; everything after the mask is free to use fma / approximate reciprocals.
+#include "common.cuh"
+#include "pair_force.cuh"
+
+namespace {
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct Acc { float fx, fy, fz, e; };
+
+template <bool MULTI, int COUL, bool PBC>
+__device__ __forceinline__ void pair_term(const float4 xi, const float4 xj, const float2 lj, const NbParams &p,
+                                          bool lj_on, Acc &a) {
+    float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+    if (PBC) {
+        // rintf(d * inv_ext) == rintf(d / ext) except within rounding of |d| = ext/2, where both
+        // images are beyond any legal cutoff (rc < ext/2 is enforced by mc_set_cutoffs)
+        dx = __fmaf_rn(-rintf(dx * p.inv_ext[0]), p.ext[0], dx);
+        dy = __fmaf_rn(-rintf(dy * p.inv_ext[1]), p.ext[1], dy);
+        dz = __fmaf_rn(-rintf(dz * p.inv_ext[2]), p.ext[2], dz);
+    }
+    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    float f = 0.f, e = 0.f;
+    if (lj_on && r2 < p.rc2_lj) {
+        const float ir2 = rcp_approx(r2);
+        const float s2 = lj.x * ir2;
+        const float s6 = s2 * s2 * s2;
+        f = lj.y * s6 * __fmaf_rn(2.f, s6, -1.f) * ir2;
+        e = lj.y * (1.f / 6.f) * s6 * (s6 - 1.f);
+    }
+    if (COUL != MC_COULOMB_NONE) {
+        if (r2 < p.rc2_q) {
+            const float qq = xi.w * xj.w;
+            const float ir = rsqrt_approx(r2);
+            if (COUL == MC_COULOMB_PLAIN) {
+                f = __fmaf_rn(qq * ir, rcp_approx(r2 + MC_SOFTENING_SQ), f);
+                e = __fmaf_rn(qq, ir, e);
+            } else {
+                const float r = r2 * ir;
+                const float ar = p.alpha * r;
+                const float erfc_ar = erfcf(ar);
+                const float ex = __expf(-ar * ar);
+                const float ir2 = ir * ir;
+                // |F|/r = qq (erfc(ar)/r^2 + 2a/sqrt(pi) exp(-a^2 r^2)/r) / r
+                f = __fmaf_rn(qq * ir, __fmaf_rn(erfc_ar, ir2, 2.f * p.alpha * MC_INV_SQRT_PI * ex * ir), f);
+                e = __fmaf_rn(qq * erfc_ar, ir, e);
+            }
+        }
+    }
+    a.fx = __fmaf_rn(dx, f, a.fx);
+    a.fy = __fmaf_rn(dy, f, a.fy);
+    a.fz = __fmaf_rn(dz, f, a.fz);
+    a.e += e;
+}
+
+template <int LANES, bool MULTI, int COUL, bool PBC>
+__global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, const float4 *__restrict__ xyzq,
+                                                          const uint16_t *__restrict__ type,
+                                                          const uint32_t *__restrict__ nbr_start,
+                                                          const uint32_t *__restrict__ nbr_count,
+                                                          const uint32_t *__restrict__ nbr_list,
+                                                          const float2 *__restrict__ ljtab, const NbParams p,
+                                                          const int lj_on, float4 *__restrict__ force) {
+    extern __shared__ float2 s_tab[];
+    if (MULTI) {
+        for (int t = threadIdx.x; t < p.n_types * p.n_types; t += blockDim.x) s_tab[t] = ljtab[t];
+        __syncthreads();
+    }
+    const int sub = threadIdx.x % LANES;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const bool live = i < n_rows;
+    Acc a = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+        const float4 xi = __ldg(xyzq + i);
+        const uint32_t start = __ldg(nbr_start + i), cnt = __ldg(nbr_count + i);
+        const float2 *row = MULTI ? s_tab + (int)__ldg(type + i) * p.n_types : nullptr;
+        const float2 lj1 = make_float2(p.sig2, p.eps24);
+        const uint32_t *lst = nbr_list + start;
+        uint32_t k = sub;
+        // two gathers in flight per lane
+        for (; k + LANES < cnt; k += 2 * LANES) {
+            const uint32_t j0 = __ldg(lst + k), j1 = __ldg(lst + k + LANES);
+            const float4 x0 = __ldg(xyzq + j0), x1 = __ldg(xyzq + j1);
+            float2 l0 = lj1, l1 = lj1;
+            if (MULTI) { l0 = row[__ldg(type + j0)]; l1 = row[__ldg(type + j1)]; }
+            pair_term<MULTI, COUL, PBC>(xi, x0, l0, p, lj_on, a);
+            pair_term<MULTI, COUL, PBC>(xi, x1, l1, p, lj_on, a);
+        }
+        if (k < cnt) {
+            const uint32_t j0 = __ldg(lst + k);
+            const float4 x0 = __ldg(xyzq + j0);
+            float2 l0 = lj1;
+            if (MULTI) l0 = row[__ldg(type + j0)];
+            pair_term<MULTI, COUL, PBC>(xi, x0, l0, p, lj_on, a);
+        }
+    }
+    // warp-shuffle partial-force reduction across the LANES lanes of this row
+#pragma unroll
+    for (int d = LANES / 2; d > 0; d >>= 1) {
+        a.fx += __shfl_xor_sync(MC_FULL_MASK, a.fx, d);
+        a.fy += __shfl_xor_sync(MC_FULL_MASK, a.fy, d);
+        a.fz += __shfl_xor_sync(MC_FULL_MASK, a.fz, d);
+        a.e += __shfl_xor_sync(MC_FULL_MASK, a.e, d);
+    }
+    if (live && sub == 0) force[i] = make_float4(a.fx, a.fy, a.fz, a.e);
+}
+
+// Amber 1-4 rows: every atom sums its own 1-4 partners (deterministic, no atomics), no cutoff,
+// LJ x scale_lj, Coulomb x scale_q.  Partner ids are original ids.
+__global__ void __launch_bounds__(128) pairs14_kernel(int n_rows, const float4 *__restrict__ xyzq,
+                                                       const uint16_t *__restrict__ type, const int *__restrict__ orig,
+                                                       const int *__restrict__ slot_of_orig,
+                                                       const int32_t *__restrict__ p14_start,
+                                                       const int32_t *__restrict__ p14_idx,
+                                                       const float2 *__restrict__ ljtab, const NbParams p,
+                                                       float scale_lj, float scale_q, int lj_on, int coul_on,
+                                                       float4 *__restrict__ force) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_rows) return;
+    const int oi = orig[k];
+    const int e0 = p14_start[oi], e1 = p14_start[oi + 1];
+    if (e0 == e1) return;
+    const float4 xi = xyzq[k];
+    const int ti = type[k];
+    float4 acc = force[k];
+    for (int e = e0; e < e1; ++e) {
+        const int j = slot_of_orig[p14_idx[e]];
+        const float4 xj = xyzq[j];
+        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        if (p.periodic) {
+            dx -= rintf(dx * p.inv_ext[0]) * p.ext[0];
+            dy -= rintf(dy * p.inv_ext[1]) * p.ext[1];
+            dz -= rintf(dz * p.inv_ext[2]) * p.ext[2];
+        }
+        const float r2 = dx * dx + dy * dy + dz * dz;
+        const float ir2 = 1.0f / r2;
+        float f = 0.f, en = 0.f;
+        if (lj_on) {
+            const float2 lj = ljtab[ti * p.n_types + type[j]];
+            const float s2 = lj.x * ir2, s6 = s2 * s2 * s2;
+            f += scale_lj * lj.y * s6 * (2.f * s6 - 1.f) * ir2;
+            en += scale_lj * lj.y * (1.f / 6.f) * s6 * (s6 - 1.f);
+        }
+        if (coul_on) {
+            const float qq = xi.w * xj.w, ir = rsqrtf(r2);
+            f += scale_q * qq * ir / (r2 + MC_SOFTENING_SQ);
+            en += scale_q * qq * ir;
+        }
+        acc.x += dx * f; acc.y += dy * f; acc.z += dz * f; acc.w += en;
+    }
+    force[k] = acc;
+}
+
+// Two-stage deterministic reduction: per-block partials {sum e_i, sum 1/2 m v^2, n_mobile}.
+constexpr int RED_BLOCKS = 592;  // 4 x 148 SMs
+__global__ void __launch_bounds__(256) energy_partial_kernel(int n_rows, const float4 *__restrict__ force,
+                                                              const float4 *__restrict__ vel,
+                                                              double *__restrict__ partial) {
+    double e = 0.0, ke = 0.0, nm = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
+        e += (double)force[i].w;
+        const float4 v = vel[i];
+        if (v.w > 0.f) {
+            ke += 0.5 * ((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z) / (double)v.w;
+            nm += 1.0;
+        }
+    }
+    __shared__ double s[3][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        e += __shfl_xor_sync(MC_FULL_MASK, e, d);
+        ke += __shfl_xor_sync(MC_FULL_MASK, ke, d);
+        nm += __shfl_xor_sync(MC_FULL_MASK, nm, d);
+    }
+    if (lane == 0) { s[0][w] = e; s[1][w] = ke; s[2][w] = nm; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += s[threadIdx.x][k];
+        partial[threadIdx.x * RED_BLOCKS + blockIdx.x] = t;
+    }
+}
+
+__global__ void energy_final_kernel(const double *__restrict__ partial, int nb, double *__restrict__ out) {
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int k = 0; k < nb; ++k) t += partial[threadIdx.x * RED_BLOCKS + k];
+        out[threadIdx.x] = t;
+    }
+}
+
+template <int LANES>
+void launch_lanes(const PairLaunch &L, cudaStream_t st) {
+    const int rows_per_block = 128 / LANES;
+    const unsigned blocks = div_up(L.n_rows, rows_per_block);
+    const size_t smem = L.multi ? sizeof(float2) * L.p.n_types * L.p.n_types : 0;
+#define MC_PF(M, C, P)                                                                                           \
+    pair_force_kernel<LANES, M, C, P><<<blocks, 128, smem, st>>>(L.n_rows, L.xyzq, L.type, L.nbr_start, L.nbr_count, \
+                                                                 L.nbr_list, L.ljtab, L.p, L.lj_on, L.force)
+#define MC_PF_C(M, P)                                              \
+    switch (L.coul) {                                              \
+        case MC_COULOMB_NONE: MC_PF(M, MC_COULOMB_NONE, P); break; \
+        case MC_COULOMB_PLAIN: MC_PF(M, MC_COULOMB_PLAIN, P); break; \
+        default: MC_PF(M, MC_COULOMB_ERFC, P); break;              \
+    }
+    if (L.multi) { if (L.p.periodic) { MC_PF_C(true, true) } else { MC_PF_C(true, false) } }
+    else { if (L.p.periodic) { MC_PF_C(false, true) } else { MC_PF_C(false, false) } }
+#undef MC_PF_C
+#undef MC_PF
+}
+
+}  // namespace
+
+int pair_force_max_types() { return 160; }  // 160^2 * 8 B = 200 KB of the 227 KB shared memory
+
+cudaError_t pair_force_prepare() {
+    // opt in to large dynamic shared memory for the multi-type instantiations
+    cudaError_t e = cudaSuccess;
+#define MC_ATTR(LN, C, P)                                                                                  \
+    if (e == cudaSuccess)                                                                                  \
+        e = cudaFuncSetAttribute(pair_force_kernel<LN, true, C, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 200 * 1024);
+#define MC_ATTR_L(LN)                                                                              \
+    MC_ATTR(LN, MC_COULOMB_NONE, true) MC_ATTR(LN, MC_COULOMB_NONE, false) MC_ATTR(LN, MC_COULOMB_PLAIN, true) \
+    MC_ATTR(LN, MC_COULOMB_PLAIN, false) MC_ATTR(LN, MC_COULOMB_ERFC, true) MC_ATTR(LN, MC_COULOMB_ERFC, false)
+    MC_ATTR_L(4) MC_ATTR_L(8) MC_ATTR_L(16) MC_ATTR_L(32)
+#undef MC_ATTR_L
+#undef MC_ATTR
+    return e;
+}
+
+void launch_pair_force(const PairLaunch &L, cudaStream_t st, int64_t *launches) {
+    if (L.n_rows <= 0) return;
+    switch (L.lanes) {
+        case 4: launch_lanes<4>(L, st); break;
+        case 16: launch_lanes<16>(L, st); break;
+        case 32: launch_lanes<32>(L, st); break;
+        default: launch_lanes<8>(L, st); break;
+    }
+    *launches += 1;
+}
+
+void launch_pairs14(int n_rows, const float4 *xyzq, const uint16_t *type, const int *orig, const int *slot_of_orig,
+                    const int32_t *p14_start, const int32_t *p14_idx, const float2 *ljtab, const NbParams &p,
+                    float scale_lj, float scale_q, int lj_on, int coul_on, float4 *force, cudaStream_t st,
+                    int64_t *launches) {
+    if (n_rows <= 0) return;
+    pairs14_kernel<<<div_up(n_rows, 128), 128, 0, st>>>(n_rows, xyzq, type, orig, slot_of_orig, p14_start, p14_idx, ljtab,
+                                                       p, scale_lj, scale_q, lj_on, coul_on, force);
+    *launches += 1;
+}
+
+int energy_partial_elems() { return 3 * RED_BLOCKS; }
+
+void launch_energy_reduce(int n_rows, const float4 *force, const float4 *vel, double *partial, double *out3,
+                          cudaStream_t st, int64_t *launches) {
+    int nb = (int)div_up(n_rows > 0 ? n_rows : 1, 256);
+    if (nb > RED_BLOCKS) nb = RED_BLOCKS;
+    energy_partial_kernel<<<nb, 256, 0, st>>>(n_rows, force, vel, partial);
+    energy_final_kernel<<<1, 32, 0, st>>>(partial, nb, out3);
+    *launches += 2;
+}

@@ -1,0 +1,28 @@
+// pair_force.cuh -- host-side launchers of pair_force.cu
+#pragma once
+#include "common.cuh"
+
+struct PairLaunch {
+    int n_rows;
+    const float4 *xyzq;
+    const uint16_t *type;
+    const uint32_t *nbr_start, *nbr_count, *nbr_list;
+    const float2 *ljtab;  // T*T (sigma^2, 24 eps)
+    NbParams p;
+    int lj_on;
+    int coul;   // MC_COULOMB_*
+    bool multi; // more than one LJ type
+    int lanes;  // lanes per row: 4, 8, 16 or 32
+    float4 *force;
+};
+
+int pair_force_max_types();
+cudaError_t pair_force_prepare();
+void launch_pair_force(const PairLaunch &L, cudaStream_t st, int64_t *launches);
+void launch_pairs14(int n_rows, const float4 *xyzq, const uint16_t *type, const int *orig, const int *slot_of_orig,
+                    const int32_t *p14_start, const int32_t *p14_idx, const float2 *ljtab, const NbParams &p,
+                    float scale_lj, float scale_q, int lj_on, int coul_on, float4 *force, cudaStream_t st,
+                    int64_t *launches);
+int energy_partial_elems();
+void launch_energy_reduce(int n_rows, const float4 *force, const float4 *vel, double *partial, double *out3,
+                          cudaStream_t st, int64_t *launches);

@@ -1,0 +1,210 @@
+"""Thin Python handle over the C ABI (include/molchanica_md.h) -- the harness that tests/ and
+bench.py drive.  It adds nothing to the data path: every method is one C call on host numpy
+buffers, exactly what a Rust `extern "C"` caller would do.
+
+Method names follow the reference-side surface they stand in for:
+    MdState::new                 -> MdEngine.from_workload / set_* (src/md/mod.rs:641-693)
+    MdState::step(dev, dt, ext)  -> MdEngine.step(dt, n_steps, ext_forces)  (src/md/mod.rs:716,748)
+    rebuild_spatial_caches(dev)  -> MdEngine.build_neighbors()  (properties/sol_shrinking_box.rs:632)
+    compute_energy_snapshot      -> MdEngine.compute_forces() + energy()  (src/md/mod.rs:1036)
+    calc_binding_energy          -> MdEngine.dock_score(...)  (src/docking/legacy/mod.rs:210-383)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class McError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"molchanica_md error {code}: {msg}")
+        self.code = code
+
+
+def _f4(a, n=None):
+    a = np.ascontiguousarray(a, np.float32)
+    assert a.ndim == 2 and a.shape[1] == 4 and (n is None or len(a) == n), a.shape
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class MdEngine:
+    """One engine handle == one CUDA device + stream (ComputationDevice::Gpu in the reference,
+    src/util.rs:1072-1119).  Raises McError(MC_E_NODEVICE) when no B200 is visible."""
+
+    def __init__(self, device=0):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        rc = self._L.mc_create(int(device), C.byref(h))
+        if rc != 0:
+            raise McError(rc, self._L.mc_last_error(None).decode())
+        self._h = h
+        self.n = 0
+
+    # -- plumbing
+    def _chk(self, rc):
+        if rc != 0:
+            raise McError(rc, self._L.mc_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- system definition
+    def set_box(self, lo, hi, periodic):
+        lo = np.ascontiguousarray(lo, np.float32)
+        hi = np.ascontiguousarray(hi, np.float32)
+        self._chk(self._L.mc_set_box(self._h, _ptr(lo), _ptr(hi), int(bool(periodic))))
+
+    def set_atoms(self, xyzq, type=None, vel=None, flags=None):
+        xyzq = _f4(xyzq)
+        n = len(xyzq)
+        t = None if type is None else np.ascontiguousarray(type, np.uint16)
+        v = None if vel is None else _f4(vel, n)
+        f = None if flags is None else np.ascontiguousarray(flags, np.uint8)
+        self._chk(self._L.mc_set_atoms(self._h, n, _ptr(xyzq), _ptr(t), _ptr(v), _ptr(f)))
+        self.n = n
+
+    def set_lj_table(self, sigma_eps):
+        t = np.ascontiguousarray(sigma_eps, np.float32)
+        assert t.ndim == 3 and t.shape[0] == t.shape[1] and t.shape[2] == 2
+        self._chk(self._L.mc_set_lj_table(self._h, t.shape[0], _ptr(t)))
+
+    def set_exclusions(self, start, idx):
+        if start is None or idx is None or len(idx) == 0:
+            self._chk(self._L.mc_set_exclusions(self._h, None, None))
+            return
+        s = np.ascontiguousarray(start, np.int32)
+        i = np.ascontiguousarray(idx, np.int32)
+        self._chk(self._L.mc_set_exclusions(self._h, _ptr(s), _ptr(i)))
+
+    def set_pairs14(self, pairs, scale_lj=0.5, scale_q=1.0 / 1.2):
+        p = None if pairs is None or len(pairs) == 0 else np.ascontiguousarray(pairs, np.int32)
+        self._chk(self._L.mc_set_pairs14(self._h, 0 if p is None else len(p), _ptr(p), scale_lj, scale_q))
+
+    def set_cutoffs(self, rc_lj, rc_q, skin, coulomb_mode, alpha=0.35):
+        self._chk(self._L.mc_set_cutoffs(self._h, rc_lj, rc_q, skin, int(coulomb_mode), alpha))
+
+    def set_overrides(self, lj_disabled=False, coulomb_disabled=False):
+        self._chk(self._L.mc_set_overrides(self._h, int(lj_disabled), int(coulomb_disabled)))
+
+    def set_option(self, name, value):
+        self._chk(self._L.mc_set_option(self._h, name.encode(), float(value)))
+
+    def set_positions(self, xyzq):
+        a = _f4(xyzq, self.n)
+        self._chk(self._L.mc_set_positions(self._h, _ptr(a)))
+
+    def set_velocities(self, vel):
+        a = _f4(vel, self.n)
+        self._chk(self._L.mc_set_velocities(self._h, _ptr(a)))
+
+    @classmethod
+    def from_workload(cls, w, device=0):
+        """Everything MdState::new hands to the engine, from a workloads.py dict."""
+        e = cls(device)
+        lo = np.asarray(w["box_lo"], np.float32)
+        e.set_box(lo, lo + np.asarray(w["box_ext"], np.float32), w["periodic"])
+        e.set_cutoffs(w["rc_lj"], w["rc_q"], w["skin"], w["coul_mode"], w.get("alpha", 0.35))
+        e.set_lj_table(w["ljtab"])
+        e.set_atoms(w["xyzq"], w["type"], w["vel"], w.get("flags"))
+        e.set_exclusions(w.get("excl_start"), w.get("excl_idx"))
+        e.set_pairs14(w.get("pairs14"), w.get("scale14_lj", 0.5), w.get("scale14_q", 1 / 1.2))
+        return e
+
+    # -- hot path
+    def build_neighbors(self):
+        self._chk(self._L.mc_build_neighbors(self._h))
+
+    def compute_forces(self):
+        self._chk(self._L.mc_compute_forces(self._h))
+
+    def step(self, dt, n_steps=1, ext_forces=None):
+        ef = None if ext_forces is None else np.ascontiguousarray(ext_forces, np.float32)
+        self._chk(self._L.mc_step(self._h, dt, int(n_steps), _ptr(ef)))
+
+    def last_step_ms(self):
+        return self._L.mc_last_step_ms(self._h)
+
+    def step_raw(self, dt, n_steps, ext_ptr):
+        """mc_step with a caller-held host pointer (pinned memory), no numpy conversion."""
+        self._chk(self._L.mc_step(self._h, dt, int(n_steps), ext_ptr))
+
+    def get_positions_into(self, ptr):
+        self._chk(self._L.mc_get_positions(self._h, ptr))
+
+    # -- read-back
+    def _get4(self, fn, n=None):
+        out = np.empty((self.n if n is None else n, 4), np.float32)
+        self._chk(fn(self._h, _ptr(out)))
+        return out
+
+    def positions(self):
+        return self._get4(self._L.mc_get_positions)
+
+    def velocities(self):
+        return self._get4(self._L.mc_get_velocities)
+
+    def forces(self):
+        return self._get4(self._L.mc_get_forces)
+
+    def energy(self):
+        e = _lib.McEnergy()
+        self._chk(self._L.mc_get_energy(self._h, C.byref(e)))
+        return {k: getattr(e, k) for k, _ in e._fields_}
+
+    def stats(self):
+        s = _lib.McStats()
+        self._chk(self._L.mc_get_stats(self._h, C.byref(s)))
+        d = {k: getattr(s, k) for k, _ in s._fields_}
+        d["n_cells"] = list(s.n_cells)
+        return d
+
+    def reset_timers(self):
+        self._chk(self._L.mc_reset_timers(self._h))
+
+    def neighbors(self):
+        """Verlet list as CSR (start int64 n+1, idx int32) in original ids, rows ascending."""
+        start = np.zeros(self.n + 1, np.int64)
+        tot = C.c_int64(0)
+        self._chk(self._L.mc_get_neighbors(self._h, _ptr(start), None, 0, C.byref(tot)))
+        idx = np.zeros(max(tot.value, 1), np.int32)
+        self._chk(self._L.mc_get_neighbors(self._h, _ptr(start), _ptr(idx), len(idx), C.byref(tot)))
+        return start, idx[:tot.value]
+
+    def time_pair_kernel(self, reps=20, flush_l2=True):
+        self._chk(self._L.mc_time_kernels(self._h, int(reps), int(flush_l2)))
+        return self._L.mc_last_pair_kernel_ms(self._h)
+
+    # -- docking
+    def dock_score(self, d, poses=None):
+        """(P,5) f32 {score, vdw, hydrophobic, electrostatic, coulomb_e} for a docking_c5 dict."""
+        poses = np.ascontiguousarray(d["poses"] if poses is None else poses, np.float32)
+        rec, lig = _f4(d["rec"]), _f4(d["lig"])
+        rt = np.ascontiguousarray(d["rec_type"], np.uint16)
+        lt = np.ascontiguousarray(d["lig_type"], np.uint16)
+        rh = np.ascontiguousarray(d["rec_hphob"], np.uint8)
+        lh = np.ascontiguousarray(d["lig_hphob"], np.uint8)
+        anchor = np.ascontiguousarray(d["lig_anchor"], np.float32)
+        tab = np.ascontiguousarray(d["ljtab"], np.float32)
+        out = np.empty((len(poses), 5), np.float32)
+        self._chk(self._L.mc_dock_score(self._h, len(rec), _ptr(rec), _ptr(rt), _ptr(rh), len(lig), _ptr(lig), _ptr(lt),
+                                        _ptr(lh), _ptr(anchor), tab.shape[0], tab.shape[1], _ptr(tab), len(poses),
+                                        _ptr(poses), _ptr(out)))
+        return out
+
+    def last_dock_kernel_ms(self):
+        return self._L.mc_last_dock_kernel_ms(self._h)

@@ -1,0 +1,202 @@
+"""ctypes front-end of the CPU oracle (oracle/md_oracle.c) and of the host-compiled reference
+helpers (oracle/_ref/libref_cuda.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+
+def build(quiet=True):
+    """(Re)build liboracle.so and, when /root/reference is present, oracle/_ref."""
+    r = subprocess.run(["make", "-C", _HERE, "-s"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    if not quiet:
+        print(r.stdout)
+
+
+class NbParams(C.Structure):
+    _fields_ = [("rc_lj", C.c_float), ("rc_q", C.c_float), ("coul_mode", C.c_int),
+                ("alpha", C.c_float), ("lj_on", C.c_int), ("coul_on", C.c_int)]
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "_build", "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_neighbors_brute.restype = C.c_int64
+        _LIB.orc_neighbors_cell.restype = C.c_int64
+        _LIB.orc_min_image.restype = C.c_float
+        _LIB.orc_min_image.argtypes = [C.c_float, C.c_float]
+        _LIB.orc_dist2.restype = C.c_float
+        _LIB.orc_kinetic.restype = C.c_double
+        _LIB.orc_md_run.restype = C.c_int
+    return _LIB
+
+
+def ref_lib():
+    """The reference's own util.cu/cuda.cu, host-compiled (None when never built)."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(_HERE, "_ref", "libref_cuda.so")
+        if not os.path.exists(path):
+            return None
+        _REF = C.CDLL(path)
+        _REF.ref_lj_V.restype = C.c_float
+        _REF.ref_lj_V.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float]
+        _REF.ref_lj_force.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        _REF.ref_coulomb_force.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        _REF.ref_softening_sq.restype = C.c_float
+        _REF.ref_inv_sqrt_pi.restype = C.c_float
+    return _REF
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
+
+
+def nb_params(w, lj_on=True, coul_on=True):
+    return NbParams(float(w["rc_lj"]), float(w["rc_q"]), int(w["coul_mode"]), float(w.get("alpha", 0.35)),
+                    int(lj_on), int(coul_on))
+
+
+def _excl(w):
+    es = w.get("excl_start")
+    ei = w.get("excl_idx")
+    if es is None or ei is None or len(ei) == 0:
+        return None, None
+    return np.ascontiguousarray(es, np.int32), np.ascontiguousarray(ei, np.int32)
+
+
+def neighbors(w, xyzq=None, brute=False):
+    """Verlet list (CSR: start int64 n+1, idx int32), rows ascending, radius max(rc)+skin."""
+    xyzq = np.ascontiguousarray(w["xyzq"] if xyzq is None else xyzq, np.float32)
+    n = len(xyzq)
+    ext = np.ascontiguousarray(w["box_ext"], np.float32)
+    lo = np.ascontiguousarray(w["box_lo"], np.float32)
+    if not w["periodic"]:
+        lo = (xyzq[:, :3].min(0) - 0.5).astype(np.float32)
+        ext = (xyzq[:, :3].max(0) + 0.5 - lo).astype(np.float32)
+    r_list = np.float32(max(w["rc_lj"], w["rc_q"])) + np.float32(w["skin"])
+    es, ei = _excl(w)
+    start = np.zeros(n + 1, np.int64)
+    L = lib()
+    if brute:
+        def call(idx, cap):
+            return L.orc_neighbors_brute(C.c_int(n), _p(xyzq, C.c_float), _p(ext, C.c_float), C.c_int(int(w["periodic"])),
+                                         C.c_float(r_list), _p(es, C.c_int32), _p(ei, C.c_int32),
+                                         _p(start, C.c_int64), _p(idx, C.c_int32), C.c_int64(cap))
+    else:
+        def call(idx, cap):
+            return L.orc_neighbors_cell(C.c_int(n), _p(xyzq, C.c_float), _p(lo, C.c_float), _p(ext, C.c_float),
+                                        C.c_int(int(w["periodic"])), C.c_float(r_list), _p(es, C.c_int32),
+                                        _p(ei, C.c_int32), _p(start, C.c_int64), _p(idx, C.c_int32), C.c_int64(cap))
+    tot = call(None, 0)
+    idx = np.zeros(max(int(tot), 1), np.int32)
+    got = call(idx, len(idx))
+    assert got == tot, (got, tot)
+    return start, idx[:tot]
+
+
+def forces(w, nbr, xyzq=None, precision=64, lj_on=True, coul_on=True, with_pairs14=True):
+    """(f (n,4) f32 = fx,fy,fz,e_i ; sumabs (n,) ; energy [E_lj, E_coul] f64)."""
+    xyzq = np.ascontiguousarray(w["xyzq"] if xyzq is None else xyzq, np.float32)
+    n = len(xyzq)
+    start, idx = nbr
+    typ = np.ascontiguousarray(w["type"], np.uint16)
+    tab = np.ascontiguousarray(w["ljtab"], np.float32)
+    T = tab.shape[0]
+    ext = np.ascontiguousarray(w["box_ext"], np.float32)
+    p = nb_params(w, lj_on, coul_on)
+    f = np.zeros((n, 4), np.float32)
+    sa = np.zeros(n, np.float32)
+    en = np.zeros(2, np.float64)
+    idx_c = np.ascontiguousarray(idx, np.int32) if len(idx) else np.zeros(1, np.int32)
+    lib().orc_forces(C.c_int(n), _p(xyzq, C.c_float), _p(typ, C.c_uint16), C.c_int(T), _p(tab, C.c_float),
+                     _p(ext, C.c_float), C.c_int(int(w["periodic"])), C.byref(p), _p(start, C.c_int64),
+                     _p(idx_c, C.c_int32), C.c_int(precision), _p(f, C.c_float), _p(sa, C.c_float), _p(en, C.c_double))
+    p14 = w.get("pairs14")
+    if with_pairs14 and p14 is not None and len(p14):
+        p14 = np.ascontiguousarray(p14, np.int32)
+        lib().orc_pairs14(C.c_int(len(p14)), _p(p14, C.c_int32), _p(xyzq, C.c_float), _p(typ, C.c_uint16), C.c_int(T),
+                          _p(tab, C.c_float), _p(ext, C.c_float), C.c_int(int(w["periodic"])),
+                          C.c_float(w["scale14_lj"]), C.c_float(w["scale14_q"]), C.c_int(int(lj_on)),
+                          C.c_int(int(coul_on)), _p(f, C.c_float), _p(en, C.c_double))
+    return f, sa, en
+
+
+def md_run(w, n_steps, precision=32, xyzq=None, vel=None, want_energies=False, ext_force=None,
+           with_bonds=False):
+    """n_steps of velocity Verlet on the CPU. Returns dict(xyzq, vel, forces, rebuilds, energies)."""
+    xyzq = np.array(w["xyzq"] if xyzq is None else xyzq, np.float32, copy=True)
+    vel = np.array(w["vel"] if vel is None else vel, np.float32, copy=True)
+    n = len(xyzq)
+    typ = np.ascontiguousarray(w["type"], np.uint16)
+    tab = np.ascontiguousarray(w["ljtab"], np.float32)
+    ext = np.ascontiguousarray(w["box_ext"], np.float32)
+    lo = np.ascontiguousarray(w["box_lo"], np.float32)
+    if not w["periodic"]:
+        # generous static bounding box for the cell grid (coordinates are clamped into it)
+        lo = (xyzq[:, :3].min(0) - 8.0).astype(np.float32)
+        ext = (xyzq[:, :3].max(0) + 8.0 - lo).astype(np.float32)
+    es, ei = _excl(w)
+    p14 = w.get("pairs14")
+    p14 = np.ascontiguousarray(p14, np.int32) if p14 is not None and len(p14) else None
+    bonds = kr0 = None
+    if with_bonds and "bonds" in w:
+        bonds = np.ascontiguousarray(w["bonds"], np.int32)
+        kr0 = np.ascontiguousarray(w["bond_kr0"], np.float32)
+    ef = np.ascontiguousarray(ext_force, np.float32) if ext_force is not None else None
+    en = np.zeros((n_steps + 1, 4), np.float64) if want_energies else None
+    fo = np.zeros((n, 4), np.float32)
+    p = nb_params(w)
+    rb = lib().orc_md_run(C.c_int(n), _p(xyzq, C.c_float), _p(vel, C.c_float), _p(typ, C.c_uint16),
+                          C.c_int(tab.shape[0]), _p(tab, C.c_float), _p(lo, C.c_float), _p(ext, C.c_float),
+                          C.c_int(int(w["periodic"])), C.byref(p), C.c_float(w["skin"]), _p(es, C.c_int32),
+                          _p(ei, C.c_int32), C.c_int(0 if p14 is None else len(p14)), _p(p14, C.c_int32),
+                          C.c_float(w["scale14_lj"]), C.c_float(w["scale14_q"]),
+                          C.c_int(0 if bonds is None else len(bonds)), _p(bonds, C.c_int32), _p(kr0, C.c_float),
+                          _p(ef, C.c_float), C.c_float(w["dt"]), C.c_int(n_steps), C.c_int(precision),
+                          _p(en, C.c_double), _p(fo, C.c_float))
+    if rb < 0:
+        raise RuntimeError("orc_md_run failed")
+    return dict(xyzq=xyzq, vel=vel, forces=fo, rebuilds=rb, energies=en)
+
+
+def dock_score(d, precision=64, poses=None):
+    """(P,5) f32: score, vdw, hydrophobic, electrostatic, coulomb_e."""
+    poses = np.ascontiguousarray(d["poses"] if poses is None else poses, np.float32)
+    rec = np.ascontiguousarray(d["rec"], np.float32)
+    lig = np.ascontiguousarray(d["lig"], np.float32)
+    tab = np.ascontiguousarray(d["ljtab"], np.float32)
+    out = np.zeros((len(poses), 5), np.float32)
+    anchor = np.ascontiguousarray(d["lig_anchor"], np.float32)
+    lib().orc_dock_score(C.c_int(len(rec)), _p(rec, C.c_float), _p(np.ascontiguousarray(d["rec_type"], np.uint16), C.c_uint16),
+                         _p(np.ascontiguousarray(d["rec_hphob"], np.uint8), C.c_uint8), C.c_int(len(lig)),
+                         _p(lig, C.c_float), _p(np.ascontiguousarray(d["lig_type"], np.uint16), C.c_uint16),
+                         _p(np.ascontiguousarray(d["lig_hphob"], np.uint8), C.c_uint8), _p(anchor, C.c_float),
+                         C.c_int(tab.shape[1]), _p(tab, C.c_float), C.c_int(len(poses)), _p(poses, C.c_float),
+                         C.c_int(precision), _p(out, C.c_float))
+    return out
