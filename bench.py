@@ -114,8 +114,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--side", type=int, default=100, help="atoms per box edge (100 -> 1,000,000 atoms)")
-    ap.add_argument("--cpu-side", type=int, default=40)
+    ap.add_argument("--cpu-side", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiler runs)")
     ap.add_argument("--lanes", type=int, default=0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -201,7 +202,7 @@ def main():
     # reference src/mol_alignment.rs:346) from pinned memory, mc_step(dt, 1, ext), D2H of the new
     # positions (what the viewer reads back, reference src/md/mod.rs:843-852) into pinned memory.
     e2e = None
-    if world == 1:
+    if world == 1 and not args.no_e2e:
         ext = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
         pos = torch.empty((n, 4), dtype=torch.float32).pin_memory()
         ext_p, pos_p = C.c_void_p(ext.data_ptr()), C.c_void_p(pos.data_ptr())
@@ -241,7 +242,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cb = cpu_arm(args.cpu_side, 60, 5)
+        cb = cpu_arm(args.cpu_side, 100, 5)
         cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:

@@ -48,17 +48,30 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
     const int pose = blockIdx.x;
     const float *ps = poses + 7 * (size_t)pose;
     {
-        float qw = ps[3], qx = ps[4], qy = ps[5], qz = ps[6];
-        const float qn = rsqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
-        qw *= qn; qx *= qn; qy *= qn; qz *= qn;
+        // The pose transform runs in f64 and is rounded once to f32, exactly as the reference does
+        // (Pose{anchor_posit, orientation} are f64, lig_posits are Vec3F32; legacy/mod.rs:149-158,
+        // :210-214).  Explicit _rn intrinsics (no fma contraction) keep the L posed points
+        // bit-identical to the CPU path; it is ~40 atoms per pose, invisible next to R x L pairs.
+        double qw = ps[3], qx = ps[4], qy = ps[5], qz = ps[6];
+        const double qn = sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(qw, qw), __dmul_rn(qx, qx)), __dmul_rn(qy, qy)),
+                                         __dmul_rn(qz, qz)));
+        qw = __ddiv_rn(qw, qn); qx = __ddiv_rn(qx, qn); qy = __ddiv_rn(qy, qn); qz = __ddiv_rn(qz, qn);
         for (int a = threadIdx.x; a < n_lig; a += DOCK_THREADS) {
             const float4 l = lig[a];
-            const float vx = l.x - anchor0.x, vy = l.y - anchor0.y, vz = l.z - anchor0.z;
-            // v' = v + 2 w (u x v) + 2 u x (u x v)
-            const float cx = qy * vz - qz * vy, cy = qz * vx - qx * vz, cz = qx * vy - qy * vx;
-            const float dx = qy * cz - qz * cy, dy = qz * cx - qx * cz, dz = qx * cy - qy * cx;
-            lp[a] = make_float4(ps[0] + vx + 2.f * (qw * cx + dx), ps[1] + vy + 2.f * (qw * cy + dy),
-                                ps[2] + vz + 2.f * (qw * cz + dz), l.w);
+            const double vx = __dsub_rn((double)l.x, (double)anchor0.x), vy = __dsub_rn((double)l.y, (double)anchor0.y),
+                         vz = __dsub_rn((double)l.z, (double)anchor0.z);
+            // v' = v + 2 (w (u x v) + u x (u x v))
+            const double cx = __dsub_rn(__dmul_rn(qy, vz), __dmul_rn(qz, vy));
+            const double cy = __dsub_rn(__dmul_rn(qz, vx), __dmul_rn(qx, vz));
+            const double cz = __dsub_rn(__dmul_rn(qx, vy), __dmul_rn(qy, vx));
+            const double dx = __dsub_rn(__dmul_rn(qy, cz), __dmul_rn(qz, cy));
+            const double dy = __dsub_rn(__dmul_rn(qz, cx), __dmul_rn(qx, cz));
+            const double dz = __dsub_rn(__dmul_rn(qx, cy), __dmul_rn(qy, cx));
+            const double ox = __dadd_rn(vx, __dmul_rn(2.0, __dadd_rn(__dmul_rn(qw, cx), dx)));
+            const double oy = __dadd_rn(vy, __dmul_rn(2.0, __dadd_rn(__dmul_rn(qw, cy), dy)));
+            const double oz = __dadd_rn(vz, __dmul_rn(2.0, __dadd_rn(__dmul_rn(qw, cz), dz)));
+            lp[a] = make_float4((float)__dadd_rn(ox, (double)ps[0]), (float)__dadd_rn(oy, (double)ps[1]),
+                                (float)__dadd_rn(oz, (double)ps[2]), l.w);
             lmeta[a] = lig_meta[a];
         }
         for (int t = threadIdx.x; t < n_rec_types * n_lig_types; t += DOCK_THREADS) tab[t] = ljtab[t];

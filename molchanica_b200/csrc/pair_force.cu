@@ -47,17 +47,25 @@ __device__ __forceinline__ void pair_term(const float4 xi, const float4 xj, cons
         dy = __fmaf_rn(-rintf(dy * p.inv_ext[1]), p.ext[1], dy);
         dz = __fmaf_rn(-rintf(dz * p.inv_ext[2]), p.ext[2], dz);
     }
-    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    // r2 for the arithmetic: fma chain (1.5 roundings).  The cutoff masks must reproduce the
+    // oracle's non-fused ((dx*dx)+(dy*dy))+(dz*dz) bit for bit; the two expressions differ by
+    // < 4e-7 relative, so the exact one is evaluated only inside a 1e-6 window around a cutoff.
+    const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+    float r2m = r2;
+    if (fabsf(r2 - p.rc2_lj) <= 1e-6f * p.rc2_lj || fabsf(r2 - p.rc2_q) <= 1e-6f * p.rc2_q)
+        r2m = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
     float f = 0.f, e = 0.f;
-    if (lj_on && r2 < p.rc2_lj) {
-        const float ir2 = rcp_approx(r2);
+    if (lj_on && r2m < p.rc2_lj) {
+        // the 12 and 6 terms cancel near the LJ minimum, so 1/r^2 gets one Newton step (<= 0.5 ulp)
+        float ir2 = rcp_approx(r2);
+        ir2 = __fmaf_rn(ir2, __fmaf_rn(-r2, ir2, 1.f), ir2);
         const float s2 = lj.x * ir2;
         const float s6 = s2 * s2 * s2;
         f = lj.y * s6 * __fmaf_rn(2.f, s6, -1.f) * ir2;
         e = lj.y * (1.f / 6.f) * s6 * (s6 - 1.f);
     }
     if (COUL != MC_COULOMB_NONE) {
-        if (r2 < p.rc2_q) {
+        if (r2m < p.rc2_q) {
             const float qq = xi.w * xj.w;
             const float ir = rsqrt_approx(r2);
             if (COUL == MC_COULOMB_PLAIN) {

@@ -304,18 +304,20 @@ static inline void pair_f32(const float *d, float r2, float sigma, float eps, fl
         }
     }
     f[0] += d[0] * fr; f[1] += d[1] * fr; f[2] += d[2] * fr;
-    *fabs_ += fabsf(fr) * sqrtf(r2);
+    fabs_[0] += fabsf(fr) * sqrtf(r2);
+    fabs_[1] += fabsf(fr) * sqrtf(r2);
 }
 
 /* fp64 pair arithmetic from the fp32 positions; the cutoff masks still use the fp32 r2. */
 static inline void pair_f64(const double *d, float r2_f32, double sigma, double eps, double qq,
                             const orc_nb_params *p, double *f, double *e_lj, double *e_q, double *fabs_) {
     double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-    double fr = 0.0, fa = 0.0;
+    double fr = 0.0, fa = 0.0, ft = 0.0;
     if (p->lj_on && eps != 0.0 && r2_f32 < p->rc_lj * p->rc_lj) {
         double r = sqrt(r2), sr = sigma / r, sr2 = sr * sr, sr6 = sr2 * sr2 * sr2, sr12 = sr6 * sr6;
         double mag = 24.0 * eps * (2.0 * sr12 - sr6) / r;
         fr += mag / r; fa += fabs(mag);
+        ft += 24.0 * fabs(eps) * (2.0 * sr12 + sr6) / r; /* |repulsive term| + |attractive term| */
         *e_lj += 4.0 * eps * (sr12 - sr6);
     }
     if (p->coul_on && p->coul_mode != ORC_COUL_NONE && qq != 0.0 && r2_f32 < p->rc_q * p->rc_q) {
@@ -328,43 +330,47 @@ static inline void pair_f64(const double *d, float r2_f32, double sigma, double 
             mag = qq * (erfc(ar) / r2 + 2.0 * a * ORC_INV_SQRT_PI * exp(-ar * ar) / r);
             *e_q += qq * erfc(ar) / r;
         }
-        fr += mag / r; fa += fabs(mag);
+        fr += mag / r; fa += fabs(mag); ft += fabs(mag);
     }
     f[0] += d[0] * fr; f[1] += d[1] * fr; f[2] += d[2] * fr;
-    *fabs_ += fa;
+    fabs_[0] += fa;
+    fabs_[1] += ft;
 }
 
 /*
  * Forces on every atom from its (full) neighbour row; energy per atom = sum over the row of
  * the pair energy (so the system energy is half the total).  ljtab: T*T pairs (sigma, eps).
- * out_f: n*4 floats (fx, fy, fz, e_i).  out_sumabs: n floats, sum_j |f_ij| (tolerance scale),
- * may be NULL.  out_energy: {E_lj, E_coulomb} system totals (already halved), fp64.
+ * out_f: n*4 floats (fx, fy, fz, e_i).  out_sumabs: n floats, sum_j |f_ij| of the NET pair
+ * forces; out_sumterms: n floats, sum_j (|LJ repulsive term| + |LJ attractive term| + |Coulomb
+ * term|) -- the scale an fp32 evaluation can be held to (the 12 and 6 terms cancel near the LJ
+ * minimum); either may be NULL.  out_energy: {E_lj, E_coulomb} system totals (already halved), fp64.
  * precision: 32 -> fp32 arithmetic in row order; 64 -> fp64 arithmetic (truth).
  */
 void orc_forces(int n, const float *xyzq, const uint16_t *type, int T, const float *ljtab,
                 const float *ext, int periodic, const orc_nb_params *p,
                 const int64_t *nbr_start, const int32_t *nbr_idx, int precision,
-                float *out_f, float *out_sumabs, double *out_energy) {
+                float *out_f, float *out_sumabs, float *out_sumterms, double *out_energy) {
     double e_lj_tot = 0.0, e_q_tot = 0.0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : e_lj_tot, e_q_tot)
     for (int i = 0; i < n; ++i) {
         const float *xi = xyzq + 4 * i;
         const int ti = type ? type[i] : 0;
         if (precision == 32) {
-            float f[3] = {0, 0, 0}, e_lj = 0, e_q = 0, fa = 0, d[3];
+            float f[3] = {0, 0, 0}, e_lj = 0, e_q = 0, fa[2] = {0, 0}, d[3];
             for (int64_t k = nbr_start[i]; k < nbr_start[i + 1]; ++k) {
                 int j = nbr_idx[k];
                 const float *xj = xyzq + 4 * j;
                 float r2 = dist2_f32(xi, xj, ext, periodic, d);
                 const float *lj = ljtab + 2 * ((size_t)ti * T + (type ? type[j] : 0));
-                pair_f32(d, r2, lj[0], lj[1], xi[3] * xj[3], p, f, &e_lj, &e_q, &fa);
+                pair_f32(d, r2, lj[0], lj[1], xi[3] * xj[3], p, f, &e_lj, &e_q, fa);
             }
             out_f[4 * i] = f[0]; out_f[4 * i + 1] = f[1]; out_f[4 * i + 2] = f[2];
             out_f[4 * i + 3] = e_lj + e_q;
-            if (out_sumabs) out_sumabs[i] = fa;
+            if (out_sumabs) out_sumabs[i] = fa[0];
+            if (out_sumterms) out_sumterms[i] = fa[1];
             e_lj_tot += e_lj; e_q_tot += e_q;
         } else {
-            double f[3] = {0, 0, 0}, e_lj = 0, e_q = 0, fa = 0, d[3];
+            double f[3] = {0, 0, 0}, e_lj = 0, e_q = 0, fa[2] = {0, 0}, d[3];
             float df[3];
             for (int64_t k = nbr_start[i]; k < nbr_start[i + 1]; ++k) {
                 int j = nbr_idx[k];
@@ -376,11 +382,12 @@ void orc_forces(int n, const float *xyzq, const uint16_t *type, int T, const flo
                     d[a] = dd;
                 }
                 const float *lj = ljtab + 2 * ((size_t)ti * T + (type ? type[j] : 0));
-                pair_f64(d, r2, lj[0], lj[1], (double)xi[3] * (double)xj[3], p, f, &e_lj, &e_q, &fa);
+                pair_f64(d, r2, lj[0], lj[1], (double)xi[3] * (double)xj[3], p, f, &e_lj, &e_q, fa);
             }
             out_f[4 * i] = (float)f[0]; out_f[4 * i + 1] = (float)f[1]; out_f[4 * i + 2] = (float)f[2];
             out_f[4 * i + 3] = (float)(e_lj + e_q);
-            if (out_sumabs) out_sumabs[i] = (float)fa;
+            if (out_sumabs) out_sumabs[i] = (float)fa[0];
+            if (out_sumterms) out_sumterms[i] = (float)fa[1];
             e_lj_tot += e_lj; e_q_tot += e_q;
         }
     }
@@ -394,7 +401,7 @@ void orc_forces(int n, const float *xyzq, const uint16_t *type, int T, const flo
  */
 void orc_pairs14(int npairs, const int32_t *pairs, const float *xyzq, const uint16_t *type, int T,
                  const float *ljtab, const float *ext, int periodic, float scale_lj, float scale_q,
-                 int lj_on, int coul_on, float *f, double *energy) {
+                 int lj_on, int coul_on, float *f, double *energy, float *sumabs, float *sumterms) {
     for (int k = 0; k < npairs; ++k) {
         int i = pairs[2 * k], j = pairs[2 * k + 1];
         double d[3], r2 = 0;
@@ -404,16 +411,20 @@ void orc_pairs14(int npairs, const int32_t *pairs, const float *xyzq, const uint
             d[a] = dd; r2 += dd * dd;
         }
         const float *lj = ljtab + 2 * ((size_t)(type ? type[i] : 0) * T + (type ? type[j] : 0));
-        double r = sqrt(r2), fr = 0, e = 0;
+        double r = sqrt(r2), fr = 0, e = 0, fa = 0, ft = 0;
         if (lj_on && lj[1] != 0.f) {
             double sr = lj[0] / r, sr6 = pow(sr, 6), sr12 = sr6 * sr6;
             fr += scale_lj * 24.0 * lj[1] * (2.0 * sr12 - sr6) / r2;
+            fa += fabs(scale_lj * 24.0 * lj[1] * (2.0 * sr12 - sr6) / r);
+            ft += fabs(scale_lj * 24.0 * lj[1]) * (2.0 * sr12 + sr6) / r;
             e += scale_lj * 4.0 * lj[1] * (sr12 - sr6);
             if (energy) energy[0] += scale_lj * 4.0 * lj[1] * (sr12 - sr6);
         }
         if (coul_on) {
             double qq = (double)xyzq[4 * i + 3] * (double)xyzq[4 * j + 3];
             fr += scale_q * qq / (r2 + (double)ORC_SOFTENING_SQ) / r;
+            fa += fabs(scale_q * qq / (r2 + (double)ORC_SOFTENING_SQ));
+            ft += fabs(scale_q * qq / (r2 + (double)ORC_SOFTENING_SQ));
             e += scale_q * qq / r;
             if (energy) energy[1] += scale_q * qq / r;
         }
@@ -424,6 +435,8 @@ void orc_pairs14(int npairs, const int32_t *pairs, const float *xyzq, const uint
         /* per-atom energy keeps the "row sum" convention: each end carries the full pair energy */
         f[4 * i + 3] += (float)e;
         f[4 * j + 3] += (float)e;
+        if (sumabs) { sumabs[i] += (float)fa; sumabs[j] += (float)fa; }
+        if (sumterms) { sumterms[i] += (float)ft; sumterms[j] += (float)ft; }
     }
 }
 
@@ -520,10 +533,10 @@ int orc_md_run(int n, float *xyzq, float *vel, const uint16_t *type, int T, cons
         }
         en[0] = en[1] = en[2] = 0;
         double e2[2] = {0, 0};
-        orc_forces(n, xyzq, type, T, ljtab, ext, periodic, p, nstart, nidx, precision, f, NULL, e2);
+        orc_forces(n, xyzq, type, T, ljtab, ext, periodic, p, nstart, nidx, precision, f, NULL, NULL, e2);
         en[0] = e2[0]; en[1] = e2[1];
         if (npairs14) orc_pairs14(npairs14, pairs14, xyzq, type, T, ljtab, ext, periodic, scale14_lj, scale14_q,
-                                  p->lj_on, p->coul_on, f, en);
+                                  p->lj_on, p->coul_on, f, en, NULL, NULL);
         if (nbonds) orc_bonds(nbonds, bonds, bond_kr0, xyzq, ext, periodic, f, &en[2]);
         if (ext_force)
             for (int i = 0; i < n; ++i)
@@ -570,27 +583,33 @@ static inline void quat_rot(const double *q, const double *v, double *o) {
  *                  the H-bond finder lives in the external crate mol_defs -> n_hbond = 0 here.
  * rec: R*4 xyzq, rec_type R, rec_hphob R (0/1); lig: L*4 xyzq (reference conformation),
  * lig_type, lig_hphob; lig_anchor[3]; poses: P*7 doubles-as-float (ax,ay,az,qw,qx,qy,qz);
- * ljtab: Trec*Tlig (sigma, eps).  out: P*5 floats {score, vdw, hydrophobic, electrostatic, coulomb_e}.
+ * ljtab: Trec*Tlig (sigma, eps).  out: P*5 floats {score, vdw, hydrophobic, electrostatic, coulomb_e};
+ * out_abs (may be NULL): P*3 floats {sum|vdw terms|, sum|coulomb pair forces|, sum|q q / r|}.
  * precision 32: fp32 arithmetic as the reference (:221-229); 64: fp64 truth.
  */
 void orc_dock_score(int R, const float *rec, const uint16_t *rec_type, const uint8_t *rec_hphob,
                     int L, const float *lig, const uint16_t *lig_type, const uint8_t *lig_hphob,
                     const float *lig_anchor, int Tlig, const float *ljtab,
-                    int P, const float *poses, int precision, float *out) {
+                    int P, const float *poses, int precision, float *out, float *out_abs) {
 #pragma omp parallel for schedule(dynamic, 8)
     for (int p = 0; p < P; ++p) {
         const float *ps = poses + 7 * p;
         double q[4] = {ps[3], ps[4], ps[5], ps[6]};
-        double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        double qn = sqrt(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
         for (int a = 0; a < 4; ++a) q[a] /= qn;
+        /* the pose transform runs in f64 and is rounded ONCE to f32, as the reference does
+           (Pose{anchor_posit, orientation} are f64, lig_posits: &[Vec3F32], legacy/mod.rs:149-158,210-214);
+           the CUDA kernel performs the identical f64 operations, so both sides score the same points */
         double *lp = (double *)malloc(sizeof(double) * 3 * (size_t)L);
         for (int a = 0; a < L; ++a) {
             double v[3] = {(double)lig[4 * a] - lig_anchor[0], (double)lig[4 * a + 1] - lig_anchor[1],
                            (double)lig[4 * a + 2] - lig_anchor[2]}, o[3];
             quat_rot(q, v, o);
-            lp[3 * a] = o[0] + ps[0]; lp[3 * a + 1] = o[1] + ps[1]; lp[3 * a + 2] = o[2] + ps[2];
+            lp[3 * a] = (double)(float)(o[0] + ps[0]);
+            lp[3 * a + 1] = (double)(float)(o[1] + ps[1]);
+            lp[3 * a + 2] = (double)(float)(o[2] + ps[2]);
         }
-        double vdw = 0, hyd = 0, ecoul = 0, fe[3] = {0, 0, 0};
+        double vdw = 0, hyd = 0, ecoul = 0, fe[3] = {0, 0, 0}, a_vdw = 0, a_f = 0, a_e = 0;
         for (int r = 0; r < R; ++r) {
             for (int a = 0; a < L; ++a) {
                 const float *lj = ljtab + 2 * ((size_t)rec_type[r] * Tlig + lig_type[a]);
@@ -601,22 +620,26 @@ void orc_dock_score(int R, const float *rec, const uint16_t *rec_type, const uin
                     float r2 = dx * dx + dy * dy + dz * dz, rr = sqrtf(r2);
                     float sr = lj[0] / rr, sr6 = sr * sr * sr * sr * sr * sr;
                     vdw += 4.f * lj[1] * (sr6 * sr6 - sr6);
+                    a_vdw += fabsf(4.f * lj[1] * (sr6 * sr6 - sr6));
                     if (rec_hphob[r] && lig_hphob[a] && rr < ORC_HYDROPHOBIC_CUTOFF)
                         hyd += -0.2f * fmaxf(1.0f - rr / ORC_HYDROPHOBIC_CUTOFF, 0.f);
                     float mag = (float)qq / (r2 + ORC_SOFTENING_SQ) / rr;
                     fe[0] += dx * mag; fe[1] += dy * mag; fe[2] += dz * mag;
                     ecoul += (float)qq / rr;
+                    a_f += fabsf(mag) * rr; a_e += fabsf((float)qq / rr);
                 } else {
                     double dx = lp[3 * a] - rec[4 * r], dy = lp[3 * a + 1] - rec[4 * r + 1],
                            dz = lp[3 * a + 2] - rec[4 * r + 2];
                     double r2 = dx * dx + dy * dy + dz * dz, rr = sqrt(r2);
                     double sr = lj[0] / rr, sr6 = pow(sr, 6);
                     vdw += 4.0 * lj[1] * (sr6 * sr6 - sr6);
+                    a_vdw += fabs(4.0 * lj[1] * (sr6 * sr6 - sr6));
                     if (rec_hphob[r] && lig_hphob[a] && rr < (double)ORC_HYDROPHOBIC_CUTOFF)
                         hyd += -0.2 * fmax(1.0 - rr / (double)ORC_HYDROPHOBIC_CUTOFF, 0.0);
                     double mag = qq / (r2 + (double)ORC_SOFTENING_SQ) / rr;
                     fe[0] += dx * mag; fe[1] += dy * mag; fe[2] += dz * mag;
                     ecoul += qq / rr;
+                    a_f += fabs(mag) * rr; a_e += fabs(qq / rr);
                 }
             }
         }
@@ -626,6 +649,9 @@ void orc_dock_score(int R, const float *rec, const uint16_t *rec_type, const uin
         out[5 * p + 2] = (float)hyd;
         out[5 * p + 3] = (float)es;
         out[5 * p + 4] = (float)ecoul;
+        if (out_abs) { /* sums of term magnitudes: the scale fp32 summation error is judged against */
+            out_abs[3 * p] = (float)a_vdw; out_abs[3 * p + 1] = (float)a_f; out_abs[3 * p + 2] = (float)a_e;
+        }
         free(lp);
     }
 }

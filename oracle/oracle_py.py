@@ -120,8 +120,10 @@ def neighbors(w, xyzq=None, brute=False):
     return start, idx[:tot]
 
 
-def forces(w, nbr, xyzq=None, precision=64, lj_on=True, coul_on=True, with_pairs14=True):
-    """(f (n,4) f32 = fx,fy,fz,e_i ; sumabs (n,) ; energy [E_lj, E_coul] f64)."""
+def forces(w, nbr, xyzq=None, precision=64, lj_on=True, coul_on=True, with_pairs14=True, scale="terms"):
+    """(f (n,4) f32 = fx,fy,fz,e_i ; scale (n,) ; energy [E_lj, E_coul] f64).
+    scale="terms": per atom sum over pairs of |LJ repulsive| + |LJ attractive| + |Coulomb| term
+    magnitudes (the parity scale, tests/util.py); scale="net": sum of the net pair-force magnitudes."""
     xyzq = np.ascontiguousarray(w["xyzq"] if xyzq is None else xyzq, np.float32)
     n = len(xyzq)
     start, idx = nbr
@@ -132,19 +134,22 @@ def forces(w, nbr, xyzq=None, precision=64, lj_on=True, coul_on=True, with_pairs
     p = nb_params(w, lj_on, coul_on)
     f = np.zeros((n, 4), np.float32)
     sa = np.zeros(n, np.float32)
+    st = np.zeros(n, np.float32)
     en = np.zeros(2, np.float64)
     idx_c = np.ascontiguousarray(idx, np.int32) if len(idx) else np.zeros(1, np.int32)
     lib().orc_forces(C.c_int(n), _p(xyzq, C.c_float), _p(typ, C.c_uint16), C.c_int(T), _p(tab, C.c_float),
                      _p(ext, C.c_float), C.c_int(int(w["periodic"])), C.byref(p), _p(start, C.c_int64),
-                     _p(idx_c, C.c_int32), C.c_int(precision), _p(f, C.c_float), _p(sa, C.c_float), _p(en, C.c_double))
+                     _p(idx_c, C.c_int32), C.c_int(precision), _p(f, C.c_float), _p(sa, C.c_float), _p(st, C.c_float),
+                     _p(en, C.c_double))
     p14 = w.get("pairs14")
     if with_pairs14 and p14 is not None and len(p14):
         p14 = np.ascontiguousarray(p14, np.int32)
         lib().orc_pairs14(C.c_int(len(p14)), _p(p14, C.c_int32), _p(xyzq, C.c_float), _p(typ, C.c_uint16), C.c_int(T),
                           _p(tab, C.c_float), _p(ext, C.c_float), C.c_int(int(w["periodic"])),
                           C.c_float(w["scale14_lj"]), C.c_float(w["scale14_q"]), C.c_int(int(lj_on)),
-                          C.c_int(int(coul_on)), _p(f, C.c_float), _p(en, C.c_double))
-    return f, sa, en
+                          C.c_int(int(coul_on)), _p(f, C.c_float), _p(en, C.c_double), _p(sa, C.c_float),
+                          _p(st, C.c_float))
+    return f, (st if scale == "terms" else sa), en
 
 
 def md_run(w, n_steps, precision=32, xyzq=None, vel=None, want_energies=False, ext_force=None,
@@ -185,18 +190,20 @@ def md_run(w, n_steps, precision=32, xyzq=None, vel=None, want_energies=False, e
     return dict(xyzq=xyzq, vel=vel, forces=fo, rebuilds=rb, energies=en)
 
 
-def dock_score(d, precision=64, poses=None):
-    """(P,5) f32: score, vdw, hydrophobic, electrostatic, coulomb_e."""
+def dock_score(d, precision=64, poses=None, with_abs=False):
+    """(P,5) f32: score, vdw, hydrophobic, electrostatic, coulomb_e
+    [+ (P,3) sums of term magnitudes: vdw, coulomb force, coulomb energy]."""
     poses = np.ascontiguousarray(d["poses"] if poses is None else poses, np.float32)
     rec = np.ascontiguousarray(d["rec"], np.float32)
     lig = np.ascontiguousarray(d["lig"], np.float32)
     tab = np.ascontiguousarray(d["ljtab"], np.float32)
     out = np.zeros((len(poses), 5), np.float32)
+    out_abs = np.zeros((len(poses), 3), np.float32)
     anchor = np.ascontiguousarray(d["lig_anchor"], np.float32)
     lib().orc_dock_score(C.c_int(len(rec)), _p(rec, C.c_float), _p(np.ascontiguousarray(d["rec_type"], np.uint16), C.c_uint16),
                          _p(np.ascontiguousarray(d["rec_hphob"], np.uint8), C.c_uint8), C.c_int(len(lig)),
                          _p(lig, C.c_float), _p(np.ascontiguousarray(d["lig_type"], np.uint16), C.c_uint16),
                          _p(np.ascontiguousarray(d["lig_hphob"], np.uint8), C.c_uint8), _p(anchor, C.c_float),
                          C.c_int(tab.shape[1]), _p(tab, C.c_float), C.c_int(len(poses)), _p(poses, C.c_float),
-                         C.c_int(precision), _p(out, C.c_float))
-    return out
+                         C.c_int(precision), _p(out, C.c_float), _p(out_abs, C.c_float))
+    return (out, out_abs) if with_abs else out

@@ -109,7 +109,7 @@ def md_small():
     for k, v in d.items():
         if k != "name":
             out[f"dock.{k}"] = np.asarray(v)
-    out["dock.scores64"] = O.dock_score(d, precision=64)
+    out["dock.scores64"], out["dock.abs64"] = O.dock_score(d, precision=64, with_abs=True)
     np.savez_compressed(os.path.join(HERE, "md_small.npz"), **out)
 
 

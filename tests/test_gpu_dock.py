@@ -8,17 +8,21 @@ from molchanica_b200 import workloads as W
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "md_small.npz")
+RTOL = 1e-5  # BASELINE.json north_star: 1e-5 relative fp32
 
 
-def _check(gpu, ref):
-    # columns: score, vdw, hydrophobic, electrostatic, coulomb_e.  vdw spans ~15 orders of magnitude
-    # over clashing poses, so every column is compared relative to its own magnitude per pose, with
-    # an absolute floor for poses whose sum cancels.
-    for col, floor in ((1, 1e-3), (2, 1e-4), (3, 1e-3), (4, 2e-2)):
-        tol = 2e-5 * np.abs(ref[:, col]) + floor
-        assert np.all(np.abs(gpu[:, col] - ref[:, col]) <= tol), (col, np.abs(gpu[:, col] - ref[:, col]).max())
-    score_ref = ref[:, 1] + ref[:, 2] + 10.0 * ref[:, 3]
-    assert np.all(np.abs(gpu[:, 0] - score_ref) <= 2e-5 * np.abs(score_ref) + 2e-2)
+def _check(gpu, ref, ref_abs):
+    """columns: score, vdw, hydrophobic, electrostatic, coulomb_e.  Each pose sum is compared with
+    the fp64 truth relative to the sum of the MAGNITUDES of its terms (ref_abs: vdw, coulomb force,
+    coulomb energy) -- the only scale an fp32 summation of cancelling terms can be held to; for
+    clashing poses (vdw up to 1e12) that scale equals |vdw| itself."""
+    assert np.all(np.abs(gpu[:, 1] - ref[:, 1]) <= RTOL * ref_abs[:, 0] + 1e-6)
+    assert np.all(np.abs(gpu[:, 2] - ref[:, 2]) <= 1e-5 * np.abs(ref[:, 2]) + 1e-5)
+    assert np.all(np.abs(gpu[:, 3] - ref[:, 3]) <= RTOL * ref_abs[:, 1] + 1e-6)
+    assert np.all(np.abs(gpu[:, 4] - ref[:, 4]) <= RTOL * ref_abs[:, 2] + 1e-6)
+    score_ref = ref[:, 1].astype(np.float64) + ref[:, 2] + 10.0 * ref[:, 3]
+    scale = ref_abs[:, 0] + 10.0 * ref_abs[:, 1] + np.abs(ref[:, 2])
+    assert np.all(np.abs(gpu[:, 0] - score_ref) <= 2 * RTOL * scale + 1e-5)
 
 
 def test_dock_scan_matches_oracle():
@@ -26,7 +30,8 @@ def test_dock_scan_matches_oracle():
     from oracle import oracle_py as O
     d = W.docking_c5(n_rec=1500, n_lig=24, n_poses=300, seeds=(525, 526, 527))
     e = MdEngine()
-    _check(e.dock_score(d), O.dock_score(d, precision=64))
+    ref, ref_abs = O.dock_score(d, precision=64, with_abs=True)
+    _check(e.dock_score(d), ref, ref_abs)
     e.close()
 
 
@@ -35,7 +40,7 @@ def test_dock_scan_matches_golden():
     g = np.load(GOLD)
     d = {k.split(".", 1)[1]: g[k] for k in g.files if k.startswith("dock.")}
     e = MdEngine()
-    _check(e.dock_score(d), d["scores64"])
+    _check(e.dock_score(d), d["scores64"], d["abs64"])
     e.close()
 
 
