@@ -89,6 +89,7 @@ extern "C" int mc_create(int device, mc_ctx **out) {
     c->l2_bytes = (size_t)prop.l2CacheSize;
     if ((e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = pair_force_prepare()) != cudaSuccess || (e = dock_prepare()) != cudaSuccess ||
+        (e = tile_sweep_prepare()) != cudaSuccess ||
         (e = cudaMallocHost(&c->h_pinned, 256)) != cudaSuccess) {
         g_create_err = std::string("mc_create: ") + cudaGetErrorString(e);
         delete c;
@@ -106,7 +107,10 @@ extern "C" int mc_destroy(mc_ctx *c) {
     cudaStreamSynchronize(c->st);
     comm_destroy(c);
     for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
-    if (c->ev_step_a) { cudaEventDestroy(c->ev_step_a); cudaEventDestroy(c->ev_step_b); }
+    if (c->ev_step_a) {
+        cudaEventDestroy(c->ev_step_a); cudaEventDestroy(c->ev_step_b);
+        cudaEventDestroy(c->ev_flag[0]); cudaEventDestroy(c->ev_flag[1]);
+    }
     c->free_all();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaStreamDestroy(c->st);
@@ -309,6 +313,10 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         const int v = (int)value;
         MC_REQUIRE(c, v == 4 || v == 8 || v == 16 || v == 32, "mc_set_option: pair_lanes must be 4, 8, 16 or 32");
         c->pair_lanes = v;
+    } else if (k == "sync_rebuild") {
+        c->sync_rebuild = value != 0.0;
+    } else if (k == "tile_sweep") {
+        c->use_tile = value != 0.0;
     } else if (k == "profiling") {
         c->profiling = value != 0.0;
     } else if (k == "rebuild_every") {
@@ -384,6 +392,7 @@ int engine_build_list(mc_ctx *c) {
     ra.flags_in = c->flags[c->cur].p; ra.flags_out = c->flags[nx].p;
     ra.orig_in = c->orig[c->cur].p; ra.orig_out = c->orig[nx].p; ra.slot_of_orig = c->slot_of_orig.p;
     ra.cell_start = c->cell_start.p;
+    ra.mark_interior = (c->skin < 0.5f * list_radius(c)) ? 1 : 0;
     launch_reorder(n, kk[which], vv[which], c->grid.p, ra, st, &c->launches);
     c->cur = nx;
     c->identity_order = false;
@@ -391,16 +400,47 @@ int engine_build_list(mc_ctx *c) {
     const float rl2 = r_list * r_list;
     const int n_rows = (int)c->n_rows_sorted();
     const int32_t *es = c->have_excl ? c->excl_start.p : nullptr, *ei = c->have_excl ? c->excl_idx.p : nullptr;
-    launch_sweep(false, n_rows, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, c->orig[c->cur].p, es, ei,
-                 c->nbr_count.p, nullptr, nullptr, st, &c->launches);
-    exclusive_scan_u32(c->nbr_count.p, c->nbr_start.p, (size_t)n_rows, 1, c->scratch.p, st, &c->launches);
-    uint32_t *h_total = reinterpret_cast<uint32_t *>(c->h_pinned);
-    MC_CUDA(c, cudaMemcpyAsync(h_total, c->nbr_start.p + n_rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    MC_CUDA(c, cudaStreamSynchronize(st));
-    const size_t total = *h_total;
-    if (total > c->nbr_list.n) MC_CUDA(c, c->nbr_list.ensure(total + total / 8 + 1024));
-    launch_sweep(true, n_rows, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, c->orig[c->cur].p, es, ei,
-                 c->nbr_count.p, c->nbr_start.p, c->nbr_list.p, st, &c->launches);
+    uint32_t *h_ctl = reinterpret_cast<uint32_t *>(c->h_pinned);
+    size_t total = 0;
+    bool tiled = c->use_tile;
+    const float rc_in = std::max(c->rc_lj, c->rc_q);
+    const float rc2_inner = rc_in * rc_in;
+    const int grid_cells = c->periodic ? c->h_grid.ncell : (int)c->ncell_cap;
+    const int est_cells = c->periodic ? c->h_grid.ncell : std::max(1, n / 256);
+    const int split = std::max(1, std::min(8, (4 * c->n_sms + est_cells - 1) / est_cells));
+    while (tiled) {
+        // single-pass TMA-staged build (tile_build.cu); tile and list capacities adapt on demand
+        MC_CUDA(c, c->tile_need.ensure(4));
+        if (!c->nbr_list.p) MC_CUDA(c, c->nbr_list.ensure(1024));
+        launch_tile_build(n_rows, grid_cells, split, c->n_sms, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, rc2_inner,
+                          c->orig[c->cur].p, es, ei, c->nbr_count.p, c->nbr_start.p, c->nbr_list.p,
+                          (uint32_t)std::min<size_t>(c->nbr_list.n, 0xffffffffu), c->tile_cap, c->tile_need.p, st, &c->launches);
+        MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->tile_need.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        MC_CUDA(c, cudaStreamSynchronize(st));
+        if (h_ctl[3] != 0) {  // a neighbourhood did not fit the tile
+            const uint32_t need = (h_ctl[2] + h_ctl[2] / 4 + 127u) & ~31u;  // + NaN padding to whole chunks
+            if (need <= tile_sweep_max_atoms()) { c->tile_cap = need; continue; }
+            tiled = c->use_tile = false;  // too dense for shared memory: two-pass global sweep from now on
+            break;
+        }
+        total = h_ctl[1];
+        if (total > c->nbr_list.n) {  // the cursor ran past the list: grow it and build again
+            MC_CUDA(c, c->nbr_list.ensure(total + total / 8 + 1024));
+            continue;
+        }
+        break;
+    }
+    if (!tiled) {
+        launch_sweep(false, n_rows, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, c->orig[c->cur].p, es, ei,
+                     c->nbr_count.p, nullptr, nullptr, st, &c->launches);
+        exclusive_scan_u32(c->nbr_count.p, c->nbr_start.p, (size_t)n_rows, 1, c->scratch.p, st, &c->launches);
+        MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->nbr_start.p + n_rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        MC_CUDA(c, cudaStreamSynchronize(st));
+        total = h_ctl[0];
+        if (total > c->nbr_list.n) MC_CUDA(c, c->nbr_list.ensure(total + total / 8 + 1024));
+        launch_sweep(true, n_rows, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, c->orig[c->cur].p, es, ei,
+                     c->nbr_count.p, c->nbr_start.p, c->nbr_list.p, st, &c->launches);
+    }
     MC_CUDA(c, cudaMemsetAsync(c->rebuild_flag.p, 0, sizeof(int), st));
     tr.stop();
     MC_CUDA(c, cudaGetLastError());
@@ -443,11 +483,13 @@ static NbParams make_params(const mc_ctx *c) {
     return p;
 }
 
-int engine_launch_forces(mc_ctx *c) {
+int engine_launch_forces(mc_ctx *c, bool want_energy) {
     PairLaunch L;
     L.n_rows = (int)c->n_rows_sorted();
     L.xyzq = c->xyzq[c->cur].p;
     L.type = c->type[c->cur].p;
+    L.flags = c->flags[c->cur].p;
+    L.energy = want_energy;
     L.nbr_start = c->nbr_start.p; L.nbr_count = c->nbr_count.p; L.nbr_list = c->nbr_list.p;
     L.ljtab = c->ljtab.p;
     L.p = make_params(c);
@@ -467,6 +509,7 @@ int engine_launch_forces(mc_ctx *c) {
                        c->force.p, c->st, &c->launches);
     MC_CUDA(c, cudaGetLastError());
     c->forces_valid = true;
+    c->forces_have_energy = want_energy;
     return MC_OK;
 }
 
@@ -486,7 +529,7 @@ extern "C" int mc_compute_forces(mc_ctx *c) {
     int rc = ensure_ready(c, "mc_compute_forces");
     if (rc != MC_OK) return rc;
     if (c->comm_active && (rc = comm_halo_positions(c)) != MC_OK) return rc;
-    if ((rc = engine_launch_forces(c)) != MC_OK) return rc;
+    if ((rc = engine_launch_forces(c, true)) != MC_OK) return rc;
     MC_CUDA(c, cudaStreamSynchronize(c->st));
     c->collect_timings();
     return MC_OK;
@@ -509,24 +552,45 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     }
     if (!c->forces_valid) {
         if (c->comm_active && (rc = comm_halo_positions(c)) != MC_OK) return rc;
-        if ((rc = engine_launch_forces(c)) != MC_OK) return rc;
+        if ((rc = engine_launch_forces(c, false)) != MC_OK) return rc;
     }
-    const float max_disp2 = 0.25f * c->skin * c->skin;
-    int *h_flag = reinterpret_cast<int *>(c->h_pinned) + 8;
-    if (!c->ev_step_a) { MC_CUDA(c, cudaEventCreate(&c->ev_step_a)); MC_CUDA(c, cudaEventCreate(&c->ev_step_b)); }
+    // Velocity Verlet, two kernels per step: [kick + drift] and [pair forces].  The second half
+    // kick of step s and the first half kick of step s+1 are one full kick in the same launch.
+    // The rebuild decision is pipelined: kick_drift raises the flag with a look-ahead margin, the
+    // flag travels to pinned host memory asynchronously, and the host acts on the flag of the
+    // PREVIOUS step while the GPU is already busy -- no per-step stream synchronisation.
+    const float max_disp = 0.5f * c->skin;
+    const bool pipelined = !c->comm_active && c->rebuild_every <= 0 && !c->sync_rebuild;
+    const float lookahead = pipelined ? 2.5f : 0.f;
+    int *h_flag = reinterpret_cast<int *>(c->h_pinned) + 8;  // two slots
+    if (!c->ev_step_a) {
+        MC_CUDA(c, cudaEventCreate(&c->ev_step_a)); MC_CUDA(c, cudaEventCreate(&c->ev_step_b));
+        MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_flag[0], cudaEventDisableTiming));
+        MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_flag[1], cudaEventDisableTiming));
+    }
     MC_CUDA(c, cudaEventRecord(c->ev_step_a, st));
+    bool have_prev = false, skip_prev = false;
     for (int s = 0; s < n_steps; ++s) {
-        const int rows = (int)c->n_rows_sorted();
         {
             TimedRegion tr(c, c->integ_acc);
-            launch_kick_drift(rows, c->xyzq[c->cur].p, c->vel[c->cur].p, c->force.p, d_ext, c->orig[c->cur].p,
-                              c->flags[c->cur].p, c->xref.p, 0.5f * dt, dt, max_disp2, c->rebuild_flag.p, st, &c->launches);
+            launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p, c->vel[c->cur].p, c->force.p, d_ext,
+                              c->orig[c->cur].p, c->flags[c->cur].p, c->xref.p, s == 0 ? 0.5f * dt : dt, dt, max_disp,
+                              lookahead, c->rebuild_flag.p, st, &c->launches);
             tr.stop();
         }
         c->steps_since_build++;
-        bool rebuild;
+        bool rebuild = false;
         if (c->rebuild_every > 0) {
             rebuild = c->steps_since_build >= c->rebuild_every;
+        } else if (pipelined) {
+            MC_CUDA(c, cudaMemcpyAsync(h_flag + (s & 1), c->rebuild_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            MC_CUDA(c, cudaEventRecord(c->ev_flag[s & 1], st));
+            if (have_prev && !skip_prev) {
+                MC_CUDA(c, cudaEventSynchronize(c->ev_flag[(s - 1) & 1]));  // completed one kernel ago
+                rebuild = h_flag[(s - 1) & 1] != 0;
+            }
+            have_prev = true;
+            skip_prev = rebuild;  // the flag copied just above still refers to the old reference positions
         } else {
             MC_CUDA(c, cudaMemcpyAsync(h_flag, c->rebuild_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             MC_CUDA(c, cudaStreamSynchronize(st));
@@ -539,15 +603,15 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         } else if (c->comm_active && (rc = comm_halo_positions(c)) != MC_OK) {
             return rc;
         }
-        if ((rc = engine_launch_forces(c)) != MC_OK) return rc;
-        {
-            TimedRegion tr(c, c->integ_acc);
-            launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p, c->vel[c->cur].p, c->force.p, d_ext,
-                              c->orig[c->cur].p, c->flags[c->cur].p, c->xref.p, 0.5f * dt, 0.f, 0.f, c->rebuild_flag.p, st,
-                              &c->launches);
-            tr.stop();
-        }
+        if ((rc = engine_launch_forces(c, false)) != MC_OK) return rc;
         c->n_steps++;
+    }
+    if (n_steps > 0) {
+        TimedRegion tr(c, c->integ_acc);
+        launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p, c->vel[c->cur].p, c->force.p, d_ext,
+                          c->orig[c->cur].p, c->flags[c->cur].p, c->xref.p, 0.5f * dt, 0.f, 0.f, 0.f, c->rebuild_flag.p, st,
+                          &c->launches);
+        tr.stop();
     }
     MC_CUDA(c, cudaEventRecord(c->ev_step_b, st));
     MC_CUDA(c, cudaGetLastError());
@@ -555,6 +619,8 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     float ms = 0.f;
     MC_CUDA(c, cudaEventElapsedTime(&ms, c->ev_step_a, c->ev_step_b));
     c->last_step_ms = ms;
+    // the flag of the last drift has not been acted upon: make the next evaluation rebuild first
+    if (pipelined && n_steps > 0 && !skip_prev && h_flag[(n_steps - 1) & 1] != 0) c->list_valid = false;
     c->collect_timings();
     return MC_OK;
 }
@@ -597,6 +663,11 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
     if (!c || !out) return MC_E_INVALID;
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->forces_valid, "mc_get_energy: no force evaluation since the last change; call mc_compute_forces");
+    if (!c->forces_have_energy) {
+        // the step path skips the energy row sums; evaluate them now on the unchanged positions
+        int rc = engine_launch_forces(c, true);
+        if (rc != MC_OK) return rc;
+    }
     MC_CUDA(c, c->red_partial.ensure((size_t)energy_partial_elems()));
     MC_CUDA(c, c->red_out.ensure(4));
     launch_energy_reduce((int)c->n_rows_sorted(), c->force.p, c->vel[c->cur].p, c->red_partial.p, c->red_out.p, c->st,
@@ -690,7 +761,7 @@ extern "C" int mc_time_kernels(mc_ctx *c, int reps, int flush_l2) {
     for (int r = 0; r < reps + 3; ++r) {
         if (r == 3) { MC_CUDA(c, cudaStreamSynchronize(c->st)); c->collect_timings(); c->pair_acc = TimeAcc(); }
         if (flush_n) launch_l2_flush(c->flush.p, flush_n, c->st, &c->launches);
-        if ((rc = engine_launch_forces(c)) != MC_OK) return rc;
+        if ((rc = engine_launch_forces(c, false)) != MC_OK) return rc;
     }
     MC_CUDA(c, cudaStreamSynchronize(c->st));
     c->collect_timings();

@@ -61,6 +61,7 @@ struct mc_ctx {
     bool have_excl = false, have_p14 = false;
 
     // state flags
+    bool forces_have_energy = false;
     bool grid_dirty = true, list_valid = false, forces_valid = false, identity_order = true, pairs_dirty = true;
     int cur = 0;
     int key_bits = 1;
@@ -71,12 +72,15 @@ struct mc_ctx {
     int rebuild_every = 0;
     int steps_since_build = 0;
     bool profiling = false;
+    bool use_tile = true;      // TMA-staged tile sweep for the list build (neighbor_tile.cu)
+    uint32_t tile_cap = 1024;  // tile capacity in atoms, grows on demand
 
     // counters
     int64_t launches = 0, n_rebuilds = 0, n_steps = 0, n_pairs_listed = 0, n_padded_entries = 0;
     TimeAcc pair_acc, build_acc, integ_acc, halo_acc, dock_acc;
     double last_pair_ms = 0, last_dock_ms = 0, last_step_ms = 0;
-    cudaEvent_t ev_step_a = nullptr, ev_step_b = nullptr;
+    cudaEvent_t ev_step_a = nullptr, ev_step_b = nullptr, ev_flag[2] = {nullptr, nullptr};
+    bool sync_rebuild = false;  // poll the displacement flag synchronously every step (debug / comparison)
 
     // device arrays
     DevBuf<float4> xyzq[2], vel[2], force, xref, stage, flush;
@@ -84,7 +88,7 @@ struct mc_ctx {
     DevBuf<uint8_t> flags[2];
     DevBuf<int> orig[2], slot_of_orig, rebuild_flag;
     DevBuf<uint32_t> keys[2], vals[2], scratch, cell_start, nbr_count, nbr_start, nbr_list;
-    DevBuf<uint32_t> cnt_orig, start_orig, export_rows;
+    DevBuf<uint32_t> cnt_orig, start_orig, export_rows, tile_need;
     DevBuf<int32_t> excl_start, excl_idx, p14_start, p14_idx;
     DevBuf<float2> ljtab, d_dock_tab;
     DevBuf<float> bbox, ext_force, d_poses, d_scores;
@@ -128,7 +132,7 @@ struct mc_ctx {
         for (int b = 0; b < 2; ++b) { xyzq[b].release(); vel[b].release(); type[b].release(); flags[b].release(); orig[b].release(); keys[b].release(); vals[b].release(); }
         force.release(); xref.release(); stage.release(); flush.release(); slot_of_orig.release(); rebuild_flag.release();
         scratch.release(); cell_start.release(); nbr_count.release(); nbr_start.release(); nbr_list.release();
-        cnt_orig.release(); start_orig.release(); export_rows.release();
+        cnt_orig.release(); start_orig.release(); export_rows.release(); tile_need.release();
         excl_start.release(); excl_idx.release(); p14_start.release(); p14_idx.release();
         ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); d_poses.release(); d_scores.release();
         grid.release(); red_partial.release(); red_out.release(); d_rec.release(); d_lig.release();
@@ -175,7 +179,7 @@ struct TimedRegion {
 
 // engine.cu
 int engine_build_list(mc_ctx *c);
-int engine_launch_forces(mc_ctx *c);
+int engine_launch_forces(mc_ctx *c, bool want_energy);
 int engine_upload_local(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type, const mc_float4 *vel,
                         const uint8_t *flags, const int *orig_ids);
 

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(int n_rows, float4 *__r
                                                           const float4 *__restrict__ force,
                                                           const float *__restrict__ ext_force, const int *__restrict__ orig,
                                                           const uint8_t *__restrict__ flags, const float4 *__restrict__ xref,
-                                                          float kick, float drift, float max_disp2,
+                                                          float kick, float drift, float max_disp, float lookahead,
                                                           int *__restrict__ rebuild_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool moved_far = false;
@@ -35,7 +35,11 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(int n_rows, float4 *__r
             xyzq[i] = x;
             const float4 r = xref[i];
             const float dx = x.x - r.x, dy = x.y - r.y, dz = x.z - r.z;
-            moved_far = dx * dx + dy * dy + dz * dz > max_disp2;
+            // displacement criterion (> skin/2 since the last build).  lookahead > 0 raises the flag
+            // early enough that the host may act on it one step late: an upper bound (L1 norm) of the
+            // distance this atom can cover in the next `lookahead` drifts is subtracted from the limit.
+            const float thr = max_disp - lookahead * (fabsf(v.x) + fabsf(v.y) + fabsf(v.z)) * fabsf(drift);
+            moved_far = thr <= 0.f || dx * dx + dy * dy + dz * dz > thr * thr;
         }
     }
     if (drift != 0.f && __any_sync(MC_FULL_MASK, moved_far) && (threadIdx.x & 31) == 0) *rebuild_flag = 1;
@@ -65,10 +69,10 @@ __global__ void l2_flush_kernel(float4 *buf, size_t n) {
 
 void launch_kick_drift(int n_rows, float4 *xyzq, float4 *vel, const float4 *force, const float *ext_force,
                        const int *orig, const uint8_t *flags, const float4 *xref, float kick, float drift,
-                       float max_disp2, int *rebuild_flag, cudaStream_t st, int64_t *launches) {
+                       float max_disp, float lookahead, int *rebuild_flag, cudaStream_t st, int64_t *launches) {
     if (n_rows <= 0) return;
     kick_drift_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(n_rows, xyzq, vel, force, ext_force, orig, flags, xref, kick,
-                                                          drift, max_disp2, rebuild_flag);
+                                                          drift, max_disp, lookahead, rebuild_flag);
     *launches += 1;
 }
 

@@ -3,10 +3,11 @@
 #include "common.cuh"
 
 // v += (F + F_ext) / m * kick * 418.4 ; then (drift != 0) x += v * drift and the displacement
-// since the last list build is checked against max_disp2 (flag raised when exceeded).
+// since the last list build is checked against max_disp minus a look-ahead margin of `lookahead`
+// further drifts (flag raised when exceeded).
 void launch_kick_drift(int n_rows, float4 *xyzq, float4 *vel, const float4 *force, const float *ext_force,
                        const int *orig, const uint8_t *flags, const float4 *xref, float kick, float drift,
-                       float max_disp2, int *rebuild_flag, cudaStream_t st, int64_t *launches);
+                       float max_disp, float lookahead, int *rebuild_flag, cudaStream_t st, int64_t *launches);
 // original-order <-> cell-order copies
 void launch_gather_to_orig(int n, const float4 *sorted, const int *orig, float4 *out, cudaStream_t st, int64_t *launches);
 void launch_scatter_from_orig(int n, const float4 *in_orig, const int *orig, float4 *sorted, int keep_w, cudaStream_t st,

@@ -135,7 +135,18 @@ __global__ void __launch_bounds__(256) reorder_kernel(int n, const uint32_t *__r
     a.xref[k] = p;
     a.vel_out[k] = a.vel_in[src];
     a.type_out[k] = a.type_in[src];
-    a.flags_out[k] = a.flags_in[src];
+    // MC_FLAG_INTERIOR: the cell's 27-cell stencil never wraps around the box, so every listed
+    // partner stays within ext/2 of this atom until the next build and the force kernel can skip
+    // the minimum image for this row (d - rintf(d/ext)*ext with n == 0 is d itself, bit for bit).
+    uint8_t fl = a.flags_in[src] & (uint8_t)~MC_FLAG_INTERIOR;
+    if (gp->periodic && a.mark_interior) {
+        const int nc0 = gp->nc[0], nc1 = gp->nc[1], nc2 = gp->nc[2];
+        const int c0 = cur % nc0, c1 = (cur / nc0) % nc1, c2 = cur / (nc0 * nc1);
+        if (nc0 >= 3 && nc1 >= 3 && nc2 >= 3 && c0 >= 1 && c0 <= nc0 - 2 && c1 >= 1 && c1 <= nc1 - 2 && c2 >= 1 &&
+            c2 <= nc2 - 2)
+            fl |= MC_FLAG_INTERIOR;
+    }
+    a.flags_out[k] = fl;
     const int o = a.orig_in[src];
     a.orig_out[k] = o;
     a.slot_of_orig[o] = k;

@@ -9,6 +9,7 @@ struct ReorderArrays {
     const uint8_t *flags_in; uint8_t *flags_out;
     const int *orig_in; int *orig_out; int *slot_of_orig;
     uint32_t *cell_start;
+    int mark_interior;  // set MC_FLAG_INTERIOR on atoms whose stencil never wraps
 };
 
 void launch_bbox(const float4 *xyzq, int n, float *bb, float cw_min, int max_cells, GridParams *g, cudaStream_t st,
@@ -23,3 +24,11 @@ void launch_sweep(bool fill, int n_rows, const float4 *xyzq, const uint32_t *cel
 void launch_export_rows(int n, const int *orig, const uint32_t *nbr_count, const uint32_t *nbr_start,
                         const uint32_t *nbr_list, uint32_t *cnt_orig, uint32_t *start_orig, uint32_t *rows,
                         uint32_t *scan_scratch, cudaStream_t st, int64_t *launches);
+
+// tile_build.cu -- single-pass TMA-staged build
+cudaError_t tile_sweep_prepare();
+uint32_t tile_sweep_max_atoms();
+void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
+                       const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
+                       const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, uint32_t *nbr_list,
+                       uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches);

@@ -17,6 +17,11 @@
 //   min image d -= rintf(d/ext)*ext                                                         (:65-71)
 // The cutoff decision uses the oracle's exact fp32 r^2 (no fma) so that both sides mask the
 // same pairs; everything after the mask is free to use fma / approximate reciprocals.
+//
+// Measured (profiles/): the kernel is instruction-issue bound, not HBM bound -- DRAM carries only
+// the index stream, the 16-byte gathers hit L1/L2 -- so the variants trim instructions: the
+// minimum image is applied only to rows of boundary-cell atoms (MC_FLAG_INTERIOR), the energy
+// row sum only when a caller asks for it (ENERGY), and rows are cutoff-partitioned at build time.
 #include "common.cuh"
 #include "pair_force.cuh"
 
@@ -36,41 +41,35 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 
 struct Acc { float fx, fy, fz, e; };
 
-template <bool MULTI, int COUL, bool PBC>
+// One listed pair.  WRAP: apply the minimum image (only rows of atoms in boundary cells need it).
+template <int COUL, bool WRAP, bool ENERGY>
 __device__ __forceinline__ void pair_term(const float4 xi, const float4 xj, const float2 lj, const NbParams &p,
                                           bool lj_on, Acc &a) {
     float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-    if (PBC) {
+    if (WRAP) {
         // rintf(d * inv_ext) == rintf(d / ext) except within rounding of |d| = ext/2, where both
-        // images are beyond any legal cutoff (rc < ext/2 is enforced by mc_set_cutoffs)
+        // images are beyond any legal cutoff (rc + skin <= ext/2 is enforced at build time)
         dx = __fmaf_rn(-rintf(dx * p.inv_ext[0]), p.ext[0], dx);
         dy = __fmaf_rn(-rintf(dy * p.inv_ext[1]), p.ext[1], dy);
         dz = __fmaf_rn(-rintf(dz * p.inv_ext[2]), p.ext[2], dz);
     }
-    // r2 for the arithmetic: fma chain (1.5 roundings).  The cutoff masks must reproduce the
-    // oracle's non-fused ((dx*dx)+(dy*dy))+(dz*dz) bit for bit; the two expressions differ by
-    // < 4e-7 relative, so the exact one is evaluated only inside a 1e-6 window around a cutoff.
-    const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-    float r2m = r2;
-    if (fabsf(r2 - p.rc2_lj) <= 1e-6f * p.rc2_lj || fabsf(r2 - p.rc2_q) <= 1e-6f * p.rc2_q)
-        r2m = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    // the oracle's fp32 expression, no fma contraction: both sides mask exactly the same pairs
+    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
     float f = 0.f, e = 0.f;
-    if (lj_on && r2m < p.rc2_lj) {
-        // the 12 and 6 terms cancel near the LJ minimum, so 1/r^2 gets one Newton step (<= 0.5 ulp)
-        float ir2 = rcp_approx(r2);
-        ir2 = __fmaf_rn(ir2, __fmaf_rn(-r2, ir2, 1.f), ir2);
+    if (lj_on && r2 < p.rc2_lj) {
+        const float ir2 = rcp_approx(r2);
         const float s2 = lj.x * ir2;
         const float s6 = s2 * s2 * s2;
         f = lj.y * s6 * __fmaf_rn(2.f, s6, -1.f) * ir2;
-        e = lj.y * (1.f / 6.f) * s6 * (s6 - 1.f);
+        if (ENERGY) e = lj.y * (1.f / 6.f) * s6 * (s6 - 1.f);
     }
     if (COUL != MC_COULOMB_NONE) {
-        if (r2m < p.rc2_q) {
+        if (r2 < p.rc2_q) {
             const float qq = xi.w * xj.w;
             const float ir = rsqrt_approx(r2);
             if (COUL == MC_COULOMB_PLAIN) {
                 f = __fmaf_rn(qq * ir, rcp_approx(r2 + MC_SOFTENING_SQ), f);
-                e = __fmaf_rn(qq, ir, e);
+                if (ENERGY) e = __fmaf_rn(qq, ir, e);
             } else {
                 const float r = r2 * ir;
                 const float ar = p.alpha * r;
@@ -79,19 +78,44 @@ __device__ __forceinline__ void pair_term(const float4 xi, const float4 xj, cons
                 const float ir2 = ir * ir;
                 // |F|/r = qq (erfc(ar)/r^2 + 2a/sqrt(pi) exp(-a^2 r^2)/r) / r
                 f = __fmaf_rn(qq * ir, __fmaf_rn(erfc_ar, ir2, 2.f * p.alpha * MC_INV_SQRT_PI * ex * ir), f);
-                e = __fmaf_rn(qq * erfc_ar, ir, e);
+                if (ENERGY) e = __fmaf_rn(qq * erfc_ar, ir, e);
             }
         }
     }
     a.fx = __fmaf_rn(dx, f, a.fx);
     a.fy = __fmaf_rn(dy, f, a.fy);
     a.fz = __fmaf_rn(dz, f, a.fz);
-    a.e += e;
+    if (ENERGY) a.e += e;
 }
 
-template <int LANES, bool MULTI, int COUL, bool PBC>
+template <int LANES, bool MULTI, int COUL, bool WRAP, bool ENERGY>
+__device__ __forceinline__ void row_loop(const float4 xi, const uint32_t *__restrict__ lst, uint32_t cnt, int sub,
+                                         const float4 *__restrict__ xyzq, const uint16_t *__restrict__ type,
+                                         const float2 *row, const NbParams &p, bool lj_on, Acc &a) {
+    const float2 lj1 = make_float2(p.sig2, p.eps24);
+    uint32_t k = sub;
+    // two gathers in flight per lane
+    for (; k + LANES < cnt; k += 2 * LANES) {
+        const uint32_t j0 = __ldg(lst + k), j1 = __ldg(lst + k + LANES);
+        const float4 x0 = __ldg(xyzq + j0), x1 = __ldg(xyzq + j1);
+        float2 l0 = lj1, l1 = lj1;
+        if (MULTI) { l0 = row[__ldg(type + j0)]; l1 = row[__ldg(type + j1)]; }
+        pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, lj_on, a);
+        pair_term<COUL, WRAP, ENERGY>(xi, x1, l1, p, lj_on, a);
+    }
+    if (k < cnt) {
+        const uint32_t j0 = __ldg(lst + k);
+        const float4 x0 = __ldg(xyzq + j0);
+        float2 l0 = lj1;
+        if (MULTI) l0 = row[__ldg(type + j0)];
+        pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, lj_on, a);
+    }
+}
+
+template <int LANES, bool MULTI, int COUL, bool PBC, bool ENERGY>
 __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, const float4 *__restrict__ xyzq,
                                                           const uint16_t *__restrict__ type,
+                                                          const uint8_t *__restrict__ flags,
                                                           const uint32_t *__restrict__ nbr_start,
                                                           const uint32_t *__restrict__ nbr_count,
                                                           const uint32_t *__restrict__ nbr_list,
@@ -110,25 +134,12 @@ __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, const float
         const float4 xi = __ldg(xyzq + i);
         const uint32_t start = __ldg(nbr_start + i), cnt = __ldg(nbr_count + i);
         const float2 *row = MULTI ? s_tab + (int)__ldg(type + i) * p.n_types : nullptr;
-        const float2 lj1 = make_float2(p.sig2, p.eps24);
         const uint32_t *lst = nbr_list + start;
-        uint32_t k = sub;
-        // two gathers in flight per lane
-        for (; k + LANES < cnt; k += 2 * LANES) {
-            const uint32_t j0 = __ldg(lst + k), j1 = __ldg(lst + k + LANES);
-            const float4 x0 = __ldg(xyzq + j0), x1 = __ldg(xyzq + j1);
-            float2 l0 = lj1, l1 = lj1;
-            if (MULTI) { l0 = row[__ldg(type + j0)]; l1 = row[__ldg(type + j1)]; }
-            pair_term<MULTI, COUL, PBC>(xi, x0, l0, p, lj_on, a);
-            pair_term<MULTI, COUL, PBC>(xi, x1, l1, p, lj_on, a);
-        }
-        if (k < cnt) {
-            const uint32_t j0 = __ldg(lst + k);
-            const float4 x0 = __ldg(xyzq + j0);
-            float2 l0 = lj1;
-            if (MULTI) l0 = row[__ldg(type + j0)];
-            pair_term<MULTI, COUL, PBC>(xi, x0, l0, p, lj_on, a);
-        }
+        // Atoms of interior cells never see a wrapped neighbour between two list builds: their raw
+        // differences already are the minimum image (n == 0), so the 9-instruction wrap is skipped.
+        const bool wrap = PBC && !(__ldg(flags + i) & MC_FLAG_INTERIOR);
+        if (wrap) row_loop<LANES, MULTI, COUL, true, ENERGY>(xi, lst, cnt, sub, xyzq, type, row, p, lj_on, a);
+        else row_loop<LANES, MULTI, COUL, false, ENERGY>(xi, lst, cnt, sub, xyzq, type, row, p, lj_on, a);
     }
     // warp-shuffle partial-force reduction across the LANES lanes of this row
 #pragma unroll
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, const float
         a.fx += __shfl_xor_sync(MC_FULL_MASK, a.fx, d);
         a.fy += __shfl_xor_sync(MC_FULL_MASK, a.fy, d);
         a.fz += __shfl_xor_sync(MC_FULL_MASK, a.fz, d);
-        a.e += __shfl_xor_sync(MC_FULL_MASK, a.e, d);
+        if (ENERGY) a.e += __shfl_xor_sync(MC_FULL_MASK, a.e, d);
     }
     if (live && sub == 0) force[i] = make_float4(a.fx, a.fy, a.fz, a.e);
 }
@@ -231,18 +242,21 @@ void launch_lanes(const PairLaunch &L, cudaStream_t st) {
     const int rows_per_block = 128 / LANES;
     const unsigned blocks = div_up(L.n_rows, rows_per_block);
     const size_t smem = L.multi ? sizeof(float2) * L.p.n_types * L.p.n_types : 0;
-#define MC_PF(M, C, P)                                                                                           \
-    pair_force_kernel<LANES, M, C, P><<<blocks, 128, smem, st>>>(L.n_rows, L.xyzq, L.type, L.nbr_start, L.nbr_count, \
-                                                                 L.nbr_list, L.ljtab, L.p, L.lj_on, L.force)
-#define MC_PF_C(M, P)                                              \
-    switch (L.coul) {                                              \
-        case MC_COULOMB_NONE: MC_PF(M, MC_COULOMB_NONE, P); break; \
-        case MC_COULOMB_PLAIN: MC_PF(M, MC_COULOMB_PLAIN, P); break; \
-        default: MC_PF(M, MC_COULOMB_ERFC, P); break;              \
+#define MC_PF(M, C, P, E)                                                                                          \
+    pair_force_kernel<LANES, M, C, P, E><<<blocks, 128, smem, st>>>(L.n_rows, L.xyzq, L.type, L.flags, L.nbr_start, \
+                                                                    L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on, L.force)
+#define MC_PF_E(M, C, P) \
+    if (L.energy) MC_PF(M, C, P, true); else MC_PF(M, C, P, false)
+#define MC_PF_C(M, P)                                                    \
+    switch (L.coul) {                                                    \
+        case MC_COULOMB_NONE: MC_PF_E(M, MC_COULOMB_NONE, P); break;     \
+        case MC_COULOMB_PLAIN: MC_PF_E(M, MC_COULOMB_PLAIN, P); break;   \
+        default: MC_PF_E(M, MC_COULOMB_ERFC, P); break;                  \
     }
     if (L.multi) { if (L.p.periodic) { MC_PF_C(true, true) } else { MC_PF_C(true, false) } }
     else { if (L.p.periodic) { MC_PF_C(false, true) } else { MC_PF_C(false, false) } }
 #undef MC_PF_C
+#undef MC_PF_E
 #undef MC_PF
 }
 
@@ -253,15 +267,15 @@ int pair_force_max_types() { return 160; }  // 160^2 * 8 B = 200 KB of the 227 K
 cudaError_t pair_force_prepare() {
     // opt in to large dynamic shared memory for the multi-type instantiations
     cudaError_t e = cudaSuccess;
-#define MC_ATTR(LN, C, P)                                                                                  \
-    if (e == cudaSuccess)                                                                                  \
-        e = cudaFuncSetAttribute(pair_force_kernel<LN, true, C, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+#define MC_ATTR(LN, C, P, E)                                                                                     \
+    if (e == cudaSuccess)                                                                                        \
+        e = cudaFuncSetAttribute(pair_force_kernel<LN, true, C, P, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  200 * 1024);
-#define MC_ATTR_L(LN)                                                                              \
-    MC_ATTR(LN, MC_COULOMB_NONE, true) MC_ATTR(LN, MC_COULOMB_NONE, false) MC_ATTR(LN, MC_COULOMB_PLAIN, true) \
-    MC_ATTR(LN, MC_COULOMB_PLAIN, false) MC_ATTR(LN, MC_COULOMB_ERFC, true) MC_ATTR(LN, MC_COULOMB_ERFC, false)
+#define MC_ATTR_C(LN, C) MC_ATTR(LN, C, true, true) MC_ATTR(LN, C, true, false) MC_ATTR(LN, C, false, true) MC_ATTR(LN, C, false, false)
+#define MC_ATTR_L(LN) MC_ATTR_C(LN, MC_COULOMB_NONE) MC_ATTR_C(LN, MC_COULOMB_PLAIN) MC_ATTR_C(LN, MC_COULOMB_ERFC)
     MC_ATTR_L(4) MC_ATTR_L(8) MC_ATTR_L(16) MC_ATTR_L(32)
 #undef MC_ATTR_L
+#undef MC_ATTR_C
 #undef MC_ATTR
     return e;
 }

@@ -6,6 +6,7 @@ struct PairLaunch {
     int n_rows;
     const float4 *xyzq;
     const uint16_t *type;
+    const uint8_t *flags;  // MC_FLAG_INTERIOR decides whether a row needs the minimum image
     const uint32_t *nbr_start, *nbr_count, *nbr_list;
     const float2 *ljtab;  // T*T (sigma^2, 24 eps)
     NbParams p;
@@ -13,6 +14,7 @@ struct PairLaunch {
     int coul;   // MC_COULOMB_*
     bool multi; // more than one LJ type
     int lanes;  // lanes per row: 4, 8, 16 or 32
+    bool energy;  // also accumulate the per-atom energy row sum into force.w
     float4 *force;
 };
 

@@ -1,0 +1,499 @@
+// tile_build.cu -- single-pass Verlet-list build with the candidate tile staged in shared memory
+// by TMA (the production path; neighbor.cu's two-pass global sweep is the fallback for
+// neighbourhoods that do not fit shared memory).
+//
+// Persistent, warp-specialised kernel: as many CTAs as fit the chip, each pulling (cell, slice)
+// work items from a global counter.  The 27-cell neighbourhood of a cell is at most 9 (+ periodic
+// wrap splits) CONTIGUOUS slot ranges of the cell-ordered xyzq array, so the whole candidate tile
+// is brought on chip by 1-D bulk-tensor copies (cp.async.bulk.shared::cluster.global, SASS UBLKCP)
+// that complete on an mbarrier -- no register staging, no per-thread loads:
+//   warp 0 (producer)    : claims the NEXT work item, looks up its ranges, waits for a free stage
+//                          (empty barrier), arms the full barrier with the byte count and issues the
+//                          bulk copies; also writes the slot ids of the staged atoms
+//   warps 1..8 (consumers): wait on the full barrier, sweep the staged tile out of shared memory for
+//                          1..4 atoms each (conflict-free LDS.128, lanes = consecutive candidates,
+//                          one tile load shared by all atoms of the warp), then release the stage
+// so the copy of item k+1 overlaps the sweep of item k (2-stage ring).
+//
+// Single pass: a warp records the accept decisions of its atoms as per-lane bit masks, reduces
+// them to row lengths, claims room for its rows with ONE atomicAdd on the list cursor (rows padded
+// to 8 entries = 32-byte sectors) and writes the rows.  Row placement in nbr_list therefore follows
+// completion order, but every row's CONTENT and ORDER are deterministic (chunk-major, lane-major),
+// so forces are bit-reproducible; mc_get_neighbors exports rows sorted by atom id regardless.
+// Each row is partitioned: entries already inside the force cutoff at build time at the front,
+// skin-shell entries at the back, so the tail iterations of the force kernel fail the cutoff test
+// warp-wide.  The accept test is the oracle's fp32 expression bit for bit (see neighbor.cu).
+#include <algorithm>
+
+#include "common.cuh"
+#include "neighbor.cuh"
+
+namespace {
+
+struct TileRange { uint32_t src, cnt, off; };
+constexpr int TILE_WARPS = 8;   // consumer warps
+constexpr int TILE_STAGES = 2;  // tiles in flight per CTA
+constexpr int TILE_A = 4;       // atoms swept together by one warp
+
+__device__ __forceinline__ float min_image_exact(float d, float ext, float inv_ext) {
+    float q = __fmul_rn(d, inv_ext);
+    float n = rintf(q);
+    if (fabsf(q - n) > 0.4999f) n = rintf(__fdiv_rn(d, ext));
+    return __fmaf_rn(-n, ext, d);
+}
+
+__device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t *total) {
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(MC_FULL_MASK, inc, d);
+        if (lane >= d) inc += t;
+    }
+    *total = __shfl_sync(MC_FULL_MASK, inc, 31);
+    return inc - v;
+}
+
+struct StageMeta {
+    uint32_t m;         // staged atoms (the tile is padded with NaN positions to whole chunks)
+    uint32_t a0, a1;    // atoms of the work item's cell (0xffffffff = no more work)
+    uint32_t slice;     // which slice of the cell's atoms this item covers
+    uint32_t self_off;  // tile index of atom a0 (the own cell is part of the tile)
+    int wrap;           // 0: the cell's stencil never wraps; 1: wraps, >= 3 cells per axis; 2: wraps, tiny grid (exact path)
+};
+
+// Candidates are swept in chunks of 32 x B (B odd, <= 31): lane L owns the B CONSECUTIVE tile entries
+// t0 + L*B .. t0 + L*B + B-1, so "lane-major" order is plain tile order (rows keep the memory
+// locality of the cell-sorted atoms), and the odd stride keeps the 16-byte shared-memory reads of a
+// quarter warp on distinct banks.
+__device__ __forceinline__ uint32_t chunk_B(uint32_t remaining) {
+    if (remaining >= 992u) return 31u;
+    uint32_t b = (remaining + 31u) >> 5;
+    if (b == 0u) b = 1u;
+    return b | 1u;
+}
+__device__ __forceinline__ uint32_t padded_size(uint32_t m) {  // tile entries incl. NaN padding
+    const uint32_t full = m / 992u, rem = m - full * 992u;
+    return full * 992u + (rem ? 32u * chunk_B(rem) : 0u);
+}
+
+// Accept decisions of NA atoms against one chunk: bit `it` of hit[k] / inn[k] (per lane) = candidate
+// t0 + lane*B + it is listed / is inside the force cutoff.  WRAP is warp-uniform: cells whose
+// stencil does not wrap skip the minimum image -- for such a cell every candidate's raw difference
+// either IS the minimum image (|d| <= ext/2, n == 0) or belongs to a pair whose nearest image is
+// beyond the list radius as well, so the decision is unchanged.  Parked atoms and tile padding are
+// NaN: never accepted.
+template <int NA, int WRAP>
+__device__ __forceinline__ void sweep_chunk(const float4 *tile, uint32_t t0, uint32_t B, const GridParams &g, float rl2,
+                                            float rc2_inner, const float4 (&pi)[TILE_A], const uint32_t (&t_self)[TILE_A],
+                                            int lane, uint32_t (&hit)[TILE_A], uint32_t (&inn)[TILE_A]) {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) hit[k] = inn[k] = 0u;
+    const uint32_t tl = t0 + (uint32_t)lane * B;
+    for (uint32_t it = 0; it < B; ++it) {
+        const uint32_t t = tl + it;
+        const float4 pj = tile[t];
+        const uint32_t bit = 1u << it;
+#pragma unroll
+        for (int k = 0; k < NA; ++k) {
+            float dx = __fsub_rn(pi[k].x, pj.x), dy = __fsub_rn(pi[k].y, pj.y), dz = __fsub_rn(pi[k].z, pj.z);
+            if (WRAP == 2) {
+                dx = min_image_exact(dx, g.ext[0], g.inv_ext[0]);
+                dy = min_image_exact(dy, g.ext[1], g.inv_ext[1]);
+                dz = min_image_exact(dz, g.ext[2], g.inv_ext[2]);
+            } else if (WRAP == 1) {
+                // >= 3 cells per axis: ext >= 3 r_list, so whenever rintf(d * inv_ext) could differ from
+                // rintf(d / ext) (|d| within rounding of ext/2) both images lie beyond 1.4 r_list and the
+                // decision is the same; everywhere else the two agree and d - n*ext is exact
+                dx = __fmaf_rn(-rintf(__fmul_rn(dx, g.inv_ext[0])), g.ext[0], dx);
+                dy = __fmaf_rn(-rintf(__fmul_rn(dy, g.inv_ext[1])), g.ext[1], dy);
+                dz = __fmaf_rn(-rintf(__fmul_rn(dz, g.inv_ext[2])), g.ext[2], dz);
+            }
+            const float r2 = dist2_exact(dx, dy, dz);
+            if (r2 < rl2 && t != t_self[k]) hit[k] |= bit;
+            if (r2 < rc2_inner) inn[k] |= bit;
+        }
+    }
+}
+
+// Drop excluded partners (1-2 / 1-3 / 1-4, original ids) from the hit masks.  Rare: only atoms that
+// carry exclusions pay for it, and only for their hits.
+template <int NA>
+__device__ __forceinline__ void apply_exclusions(const uint32_t *tile_slot, uint32_t tl /* t0 + lane*B */,
+                                                 const int (&ex_lo)[TILE_A], const int (&ex_hi)[TILE_A],
+                                                 const int *__restrict__ orig, const int32_t *__restrict__ excl_idx,
+                                                 uint32_t (&hit)[TILE_A]) {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        if (ex_hi[k] <= ex_lo[k]) continue;
+        uint32_t mleft = hit[k];
+        while (mleft) {
+            const int it = __ffs(mleft) - 1;
+            mleft &= mleft - 1u;
+            const int oj = orig[tile_slot[tl + (uint32_t)it]];
+            for (int e = ex_lo[k]; e < ex_hi[k]; ++e)
+                if (excl_idx[e] == oj) { hit[k] &= ~(1u << it); break; }
+        }
+    }
+}
+
+struct RowState {
+    float4 pi[TILE_A];
+    uint32_t t_self[TILE_A];
+    int ex_lo[TILE_A], ex_hi[TILE_A];
+    uint32_t hit[TILE_A], inn[TILE_A];          // masks of the (single / current) chunk
+    uint32_t lane_in[TILE_A], lane_out[TILE_A];  // exclusive lane prefixes of the per-lane totals
+    uint32_t len[TILE_A], n_inner[TILE_A];
+};
+
+// phase 1: accept decisions and row lengths of the NA atoms of this warp
+template <int NA, int WRAP>
+__device__ __forceinline__ void rows_phase1(const float4 *tile, const uint32_t *tile_slot, const StageMeta &M, const GridParams &g,
+                                            float rl2, float rc2_inner, const uint32_t (&ia)[TILE_A],
+                                            const float4 *__restrict__ xyzq, const int *__restrict__ orig,
+                                            const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx,
+                                            int lane, int na, RowState &R) {
+    const float qnan = __int_as_float(0x7fffffff);
+#pragma unroll
+    for (int k = 0; k < TILE_A; ++k) {
+        R.pi[k] = make_float4(qnan, qnan, qnan, 0.f);
+        R.t_self[k] = 0xffffffffu;
+        R.ex_lo[k] = R.ex_hi[k] = 0;
+        R.hit[k] = R.inn[k] = 0u;
+        R.len[k] = R.n_inner[k] = 0u;
+        if (k < NA && k < na) {
+            R.pi[k] = xyzq[ia[k]];
+            R.t_self[k] = M.self_off + (ia[k] - M.a0);
+            if (excl_start) {
+                const int oi = orig[ia[k]];
+                R.ex_lo[k] = excl_start[oi];
+                R.ex_hi[k] = excl_start[oi + 1];
+            }
+        }
+    }
+    uint32_t n_in[TILE_A], n_out[TILE_A];
+#pragma unroll
+    for (int k = 0; k < TILE_A; ++k) n_in[k] = n_out[k] = 0u;
+    for (uint32_t t0 = 0; t0 < M.m;) {
+        const uint32_t B = chunk_B(M.m - t0);
+        sweep_chunk<NA, WRAP>(tile, t0, B, g, rl2, rc2_inner, R.pi, R.t_self, lane, R.hit, R.inn);
+        apply_exclusions<NA>(tile_slot, t0 + (uint32_t)lane * B, R.ex_lo, R.ex_hi, orig, excl_idx, R.hit);
+#pragma unroll
+        for (int k = 0; k < NA; ++k) {
+            n_in[k] += __popc(R.hit[k] & R.inn[k]);
+            n_out[k] += __popc(R.hit[k] & ~R.inn[k]);
+        }
+        t0 += 32u * B;
+    }
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        uint32_t tot_in, tot_out;
+        R.lane_in[k] = warp_excl_scan(n_in[k], lane, &tot_in);
+        R.lane_out[k] = warp_excl_scan(n_out[k], lane, &tot_out);
+        R.len[k] = tot_in + tot_out;
+        R.n_inner[k] = tot_in;
+    }
+}
+
+// phase 2: write the rows in tile order; inner entries from the front, skin-shell entries from the back
+template <int NA, int WRAP>
+__device__ __forceinline__ void rows_phase2(const float4 *tile, const uint32_t *tile_slot, const StageMeta &M, const GridParams &g,
+                                            float rl2, float rc2_inner, const uint32_t (&row)[TILE_A],
+                                            const int *__restrict__ orig, const int32_t *__restrict__ excl_idx,
+                                            uint32_t *__restrict__ nbr_list, int lane, RowState &R) {
+    const bool one_chunk = M.m <= 992u;
+    uint32_t run_in[TILE_A], run_out[TILE_A];
+#pragma unroll
+    for (int k = 0; k < TILE_A; ++k) run_in[k] = run_out[k] = 0u;
+    for (uint32_t t0 = 0; t0 < M.m;) {
+        const uint32_t B = chunk_B(M.m - t0);
+        const uint32_t tl = t0 + (uint32_t)lane * B;
+        if (!one_chunk) {
+            sweep_chunk<NA, WRAP>(tile, t0, B, g, rl2, rc2_inner, R.pi, R.t_self, lane, R.hit, R.inn);
+            apply_exclusions<NA>(tile_slot, tl, R.ex_lo, R.ex_hi, orig, excl_idx, R.hit);
+        }
+#pragma unroll
+        for (int k = 0; k < NA; ++k) {
+            uint32_t li = R.lane_in[k], lo = R.lane_out[k];
+            if (!one_chunk) {  // per-chunk lane offsets
+                uint32_t ti, to;
+                li = warp_excl_scan(__popc(R.hit[k] & R.inn[k]), lane, &ti);
+                lo = warp_excl_scan(__popc(R.hit[k] & ~R.inn[k]), lane, &to);
+                li += run_in[k]; lo += run_out[k];
+                run_in[k] += ti; run_out[k] += to;
+            }
+            uint32_t p_in = row[k] + li;
+            uint32_t p_out = row[k] + R.len[k] - 1u - lo;
+            uint32_t mleft = R.hit[k];
+            while (mleft) {
+                const int it = __ffs(mleft) - 1;
+                mleft &= mleft - 1u;
+                const uint32_t j = tile_slot[tl + (uint32_t)it];
+                if ((R.inn[k] >> it) & 1u) nbr_list[p_in++] = j;
+                else nbr_list[p_out--] = j;
+            }
+        }
+        t0 += 32u * B;
+    }
+}
+
+__global__ void __launch_bounds__((TILE_WARPS + 1) * 32, 3) tile_build_kernel(
+    int n_rows, const float4 *__restrict__ xyzq, const uint32_t *__restrict__ cell_start,
+    const GridParams *__restrict__ gp, float rl2, float rc2_inner, const int *__restrict__ orig,
+    const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx, uint32_t *__restrict__ nbr_count,
+    uint32_t *__restrict__ nbr_start, uint32_t *__restrict__ nbr_list, uint32_t list_cap, uint32_t tile_cap, int split,
+    uint32_t *__restrict__ ctl /* [0] work counter, [1] list cursor, [2] max tile atoms seen, [3] tile overflow */) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // per stage: tile_cap float4 positions, then tile_cap slot ids
+    const size_t stage_bytes = (size_t)tile_cap * (sizeof(float4) + sizeof(uint32_t));
+    __shared__ __align__(8) uint64_t full_bar[TILE_STAGES], empty_bar[TILE_STAGES];
+    __shared__ StageMeta meta[TILE_STAGES];
+    __shared__ uint32_t s_len[2][TILE_WARPS * TILE_A], s_off[2][TILE_WARPS * TILE_A];
+    __shared__ int s_fits[2];
+
+    const GridParams g = *gp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TILE_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], TILE_WARPS);
+        }
+    }
+    __syncthreads();
+    const long long n_items = (long long)g.ncell * split;
+
+    if (warp == 0) {
+        // ===== producer =====
+        uint32_t it = 0;
+        for (;;) {
+            long long w = 0;
+            if (lane == 0) w = (long long)atomicAdd(ctl, 1u);  // dynamic distribution: boundary cells cost more
+            w = __shfl_sync(MC_FULL_MASK, w, 0);
+            const bool done = w >= n_items;
+            const int c = done ? 0 : (int)(w / split);
+            uint32_t a0 = 0xffffffffu, a1 = 0xffffffffu, m = 0, self_off = 0;
+            TileRange r0 = {0u, 0u, 0u}, r1 = {0u, 0u, 0u};
+            int wrap = 0;
+            if (!done) {
+                a0 = cell_start[c];
+                a1 = cell_start[c + 1];
+                if (a0 == a1) continue;  // empty cell: nothing to stage (warp-uniform)
+                const int c0 = c % g.nc[0], c1 = (c / g.nc[0]) % g.nc[1], c2 = c / (g.nc[0] * g.nc[1]);
+                if (lane < 9) {  // one (dz, dy) stencil row per lane -> up to two contiguous slot ranges
+                    const int dy = lane % 3 - 1, dz = lane / 3 - 1;
+                    const int lo_y = (g.nc[1] >= 3 || !g.periodic) ? -1 : 0, hi_y = (g.nc[1] >= 2 || !g.periodic) ? 1 : 0;
+                    const int lo_z = (g.nc[2] >= 3 || !g.periodic) ? -1 : 0, hi_z = (g.nc[2] >= 2 || !g.periodic) ? 1 : 0;
+                    int ky = c1 + dy, kz = c2 + dz;
+                    bool ok = dy >= lo_y && dy <= hi_y && dz >= lo_z && dz <= hi_z;
+                    if (g.periodic) { ky = (ky + g.nc[1]) % g.nc[1]; kz = (kz + g.nc[2]) % g.nc[2]; }
+                    else if (ky < 0 || ky >= g.nc[1] || kz < 0 || kz >= g.nc[2]) ok = false;
+                    if (ok) {
+                        const int rowbase = (kz * g.nc[1] + ky) * g.nc[0];
+                        int x0, x1, y0 = 0, y1 = -1;  // second run empty unless the x stencil wraps
+                        if (!g.periodic) { x0 = max(c0 - 1, 0); x1 = min(c0 + 1, g.nc[0] - 1); }
+                        else if (g.nc[0] < 3) { x0 = 0; x1 = g.nc[0] - 1; }
+                        else if (c0 == 0) { x0 = 0; x1 = 1; y0 = y1 = g.nc[0] - 1; }
+                        else if (c0 == g.nc[0] - 1) { x0 = 0; x1 = 0; y0 = g.nc[0] - 2; y1 = g.nc[0] - 1; }
+                        else { x0 = c0 - 1; x1 = c0 + 1; }
+                        r0.src = cell_start[rowbase + x0];
+                        r0.cnt = cell_start[rowbase + x1 + 1] - r0.src;
+                        if (y1 >= y0) {
+                            r1.src = cell_start[rowbase + y0];
+                            r1.cnt = cell_start[rowbase + y1 + 1] - r1.src;
+                        }
+                    }
+                }
+                // exclusive prefix of the range lengths across lanes (lane order = range order)
+                const uint32_t mine = r0.cnt + r1.cnt;
+                uint32_t inc = mine;
+#pragma unroll
+                for (int d = 1; d < 16; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(MC_FULL_MASK, inc, d);
+                    if (lane >= d) inc += v;
+                }
+                r0.off = inc - mine;
+                r1.off = r0.off + r0.cnt;
+                m = __shfl_sync(MC_FULL_MASK, inc, 8);
+                // the own cell lives in stencil row (dz, dy) = (0, 0) = lane 4: in range r0 unless it is the
+                // wrapped remainder r1 (c0 == nc0-1 with a wrapping x stencil)
+                uint32_t so = 0;
+                if (lane == 4) so = (a0 >= r0.src && a0 < r0.src + r0.cnt) ? r0.off + (a0 - r0.src) : r1.off + (a0 - r1.src);
+                self_off = __shfl_sync(MC_FULL_MASK, so, 4);
+                const bool interior = g.periodic && g.nc[0] >= 3 && g.nc[1] >= 3 && g.nc[2] >= 3 && c0 >= 1 &&
+                                      c0 <= g.nc[0] - 2 && c1 >= 1 && c1 <= g.nc[1] - 2 && c2 >= 1 && c2 <= g.nc[2] - 2;
+                wrap = (g.periodic && !interior) ? ((g.nc[0] >= 3 && g.nc[1] >= 3 && g.nc[2] >= 3) ? 1 : 2) : 0;
+                if (lane == 0) atomicMax(ctl + 2, m);
+                if (padded_size(m) > tile_cap) {  // does not fit: the host enlarges the tile (or falls back)
+                    if (lane == 0) ctl[3] = 1u;
+                    continue;
+                }
+            }
+            const int s = it % TILE_STAGES;
+            mbar_wait(&empty_bar[s], ((it / TILE_STAGES) & 1) ^ 1);
+            float4 *tile = reinterpret_cast<float4 *>(smem_raw + (size_t)s * stage_bytes);
+            uint32_t *tile_slot = reinterpret_cast<uint32_t *>(tile + tile_cap);
+            if (lane == 0) {
+                meta[s].m = m; meta[s].a0 = a0; meta[s].a1 = a1; meta[s].wrap = wrap; meta[s].self_off = self_off;
+                meta[s].slice = done ? 0u : (uint32_t)(w % split);
+            }
+            // slot ids of the staged atoms (lanes 0..8 own the ranges; every lane helps to write them)
+            for (int src_lane = 0; src_lane < 9; ++src_lane) {
+                const uint32_t s0 = __shfl_sync(MC_FULL_MASK, r0.src, src_lane), n0 = __shfl_sync(MC_FULL_MASK, r0.cnt, src_lane),
+                               o0 = __shfl_sync(MC_FULL_MASK, r0.off, src_lane), s1 = __shfl_sync(MC_FULL_MASK, r1.src, src_lane),
+                               n1 = __shfl_sync(MC_FULL_MASK, r1.cnt, src_lane), o1 = __shfl_sync(MC_FULL_MASK, r1.off, src_lane);
+                for (uint32_t t = lane; t < n0; t += 32) tile_slot[o0 + t] = s0 + t;
+                for (uint32_t t = lane; t < n1; t += 32) tile_slot[o1 + t] = s1 + t;
+            }
+            // pad the tile to whole chunks with NaN positions: the sweep needs no bounds test
+            {
+                const float qnan = __int_as_float(0x7fffffff);
+                const uint32_t pend = padded_size(m);
+                for (uint32_t t = m + lane; t < pend; t += 32) tile[t] = make_float4(qnan, qnan, qnan, 0.f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&full_bar[s], m * (uint32_t)sizeof(float4));  // release: meta + slots visible
+            __syncwarp();
+            if (lane < 9) {
+                if (r0.cnt) tma_bulk_g2s(tile + r0.off, xyzq + r0.src, r0.cnt * (uint32_t)sizeof(float4), &full_bar[s]);
+                if (r1.cnt) tma_bulk_g2s(tile + r1.off, xyzq + r1.src, r1.cnt * (uint32_t)sizeof(float4), &full_bar[s]);
+            }
+            ++it;
+            if (done) break;
+        }
+    } else {
+        // ===== consumers =====
+        const int cw = warp - 1;
+        int pp = 0;
+        for (uint32_t it = 0;; ++it) {
+            const int s = it % TILE_STAGES;
+            mbar_wait(&full_bar[s], (it / TILE_STAGES) & 1);
+            const StageMeta M = meta[s];
+            if (M.a0 == 0xffffffffu) break;
+            const float4 *tile = reinterpret_cast<const float4 *>(smem_raw + (size_t)s * stage_bytes);
+            const uint32_t *tile_slot = reinterpret_cast<const uint32_t *>(tile + tile_cap);
+            for (uint32_t base = M.a0 + M.slice * (TILE_WARPS * TILE_A); base < M.a1; base += TILE_WARPS * TILE_A * split) {
+                uint32_t ia[TILE_A];
+                int na = 0;
+#pragma unroll
+                for (int k = 0; k < TILE_A; ++k) {
+                    const uint32_t i = base + cw + k * TILE_WARPS;  // round-robin: every warp gets 2-3 atoms of a ~20-atom cell
+                    ia[k] = i;
+                    if (i < M.a1 && (int)i < n_rows) na = k + 1;
+                }
+                // every warp of the CTA runs the SAME instantiation (atoms in this pass / 8, rounded up): one hot
+                // loop in the instruction cache; surplus slots are parked on NaN positions
+                const uint32_t n_pass = min((uint32_t)(TILE_WARPS * TILE_A), M.a1 - base);
+                const int na_u = (int)((n_pass + TILE_WARPS - 1) / TILE_WARPS);
+                RowState R;
+#define MC_P1(NA_, W_) rows_phase1<NA_, W_>(tile, tile_slot, M, g, rl2, rc2_inner, ia, xyzq, orig, excl_start, excl_idx, lane, na, R)
+#define MC_P1W(NA_) \
+    if (M.wrap == 0) MC_P1(NA_, 0); else if (M.wrap == 1) MC_P1(NA_, 1); else MC_P1(NA_, 2)
+                switch (na_u) { case 1: MC_P1W(1); break; case 2: MC_P1W(2); break; case 3: MC_P1W(3); break; default: MC_P1W(4); break; }
+#undef MC_P1W
+#undef MC_P1
+                // ---- row allocation for the whole pass (up to 32 atoms of the cell, in atom order): the padded
+                // lengths go through shared memory, consumer warp 0 scans them and claims the space with ONE
+                // atomicAdd, so the rows of a cell are contiguous and ordered like its atoms
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < TILE_A; ++k) s_len[pp][cw + k * TILE_WARPS] = k < na ? ((R.len[k] + 7u) & ~7u) : 0u;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(TILE_WARPS * 32) : "memory");
+                if (cw == 0) {
+                    uint32_t tot;
+                    const uint32_t off = warp_excl_scan(s_len[pp][lane], lane, &tot);
+                    uint32_t b0 = 0;
+                    if (lane == 0) b0 = atomicAdd(ctl + 1, tot);
+                    b0 = __shfl_sync(MC_FULL_MASK, b0, 0);
+                    s_off[pp][lane] = b0 + off;
+                    if (lane == 0) s_fits[pp] = ((uint64_t)b0 + tot <= (uint64_t)list_cap) ? 1 : 0;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(TILE_WARPS * 32) : "memory");
+                uint32_t row[TILE_A];
+#pragma unroll
+                for (int k = 0; k < TILE_A; ++k) {
+                    row[k] = s_off[pp][cw + k * TILE_WARPS];
+                    if (k < na && lane == 0) {
+                        nbr_start[ia[k]] = row[k];
+                        nbr_count[ia[k]] = R.len[k];
+                    }
+                }
+                const bool fits = s_fits[pp] != 0;  // otherwise the host grows the list and rebuilds
+                pp ^= 1;  // the other buffer serves the next pass: no third barrier needed
+                if (fits && na > 0) {
+#define MC_P2(NA_, W_) rows_phase2<NA_, W_>(tile, tile_slot, M, g, rl2, rc2_inner, row, orig, excl_idx, nbr_list, lane, R)
+#define MC_P2W(NA_) \
+    if (M.wrap == 0) MC_P2(NA_, 0); else if (M.wrap == 1) MC_P2(NA_, 1); else MC_P2(NA_, 2)
+                    switch (na_u) { case 1: MC_P2W(1); break; case 2: MC_P2W(2); break; case 3: MC_P2W(3); break; default: MC_P2W(4); break; }
+#undef MC_P2W
+#undef MC_P2
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t tile_sweep_prepare() {
+    return cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+// 16 B position + 4 B slot id per staged atom, TILE_STAGES stages in 200 KB
+uint32_t tile_sweep_max_atoms() { return ((200u * 1024u) / (20u * TILE_STAGES)) & ~31u; }
+
+void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
+                       const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
+                       const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, uint32_t *nbr_list,
+                       uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches) {
+    // persistent: exactly one resident wave of CTAs pulls (cell, slice) items from ctl[0]
+    const long long items = (long long)grid_cells * split;
+    const size_t smem = (size_t)TILE_STAGES * tile_cap * (sizeof(float4) + sizeof(uint32_t));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_build_kernel, (TILE_WARPS + 1) * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, (long long)n_sms * per_sm));
+    cudaMemsetAsync(ctl, 0, 4 * sizeof(uint32_t), st);
+    tile_build_kernel<<<grid, (TILE_WARPS + 1) * 32, smem, st>>>(n_rows, xyzq, cell_start, g, rl2, rc2_inner, orig, excl_start,
+                                                                 excl_idx, nbr_count, nbr_start, nbr_list, list_cap, tile_cap,
+                                                                 split, ctl);
+    *launches += 1;
+}
