@@ -202,21 +202,25 @@ def main():
     # reference src/mol_alignment.rs:346) from pinned memory, mc_step(dt, 1, ext), D2H of the new
     # positions (what the viewer reads back, reference src/md/mod.rs:843-852) into pinned memory.
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if not args.no_e2e:
         ext = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
         pos = torch.empty((n, 4), dtype=torch.float32).pin_memory()
         ext_p, pos_p = C.c_void_p(ext.data_ptr()), C.c_void_p(pos.data_ptr())
         for _ in range(3):
             e.step_raw(DT_PS, 1, ext_p)
             e.get_positions_into(pos_p)
-        torch.cuda.synchronize()
         ke = min(K, 200)
+        barrier()
         t0 = time.perf_counter()
         for _ in range(ke):
             e.step_raw(DT_PS, 1, ext_p)
             e.get_positions_into(pos_p)
-        torch.cuda.synchronize()
+        barrier()
         te = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([te], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            te = float(tt.item())
         e2e = {"value": ns_per_day(ke, te), "unit": UNIT, "h2d_bytes_per_step": int(ext.numel() * 4),
                "d2h_bytes_per_step": int(pos.numel() * 4), "steps": ke, "ms_per_step": te / ke * 1e3,
                "api": "mc_step(ctx, dt, 1, ext_forces) + mc_get_positions(ctx, out), pinned host buffers"}
@@ -238,7 +242,10 @@ def main():
                 "launches_timed": s1["pair_launches_timed"],
                 "share_of_step": pair_ms * s1["pair_launches_timed"] / ms if ms > 0 else None,
                 "build_ms_avg": s1["build_ms_sum"] / max(s1["builds_timed"], 1),
-                "integrate_ms_avg": s1["integrate_ms_sum"] / max(s1["integrate_launches_timed"], 1)}
+                "integrate_ms_avg": s1["integrate_ms_sum"] / max(s1["integrate_launches_timed"], 1),
+                "halo_ms_avg": s1["halo_ms_sum"] / max(s1["halos_timed"], 1) if world > 1 else None,
+                "rank0_atoms_owned": int(s1["n_atoms"]), "rank0_ghosts": int(s1["n_ghosts"]),
+                "list_violations": int(s1["n_list_violations"])}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -78,6 +78,7 @@ typedef struct {
     double  build_ms_sum;     int64_t builds_timed;
     double  integrate_ms_sum; int64_t integrate_launches_timed;
     double  halo_ms_sum;      int64_t halos_timed;
+    int64_t n_list_violations;   /* fixed-schedule rebuilds only: times an atom outran skin/2 between builds */
 } mc_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------- */

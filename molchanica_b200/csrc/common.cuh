@@ -21,9 +21,14 @@ struct GridParams {
     float ext[3];      // box extent (periodic) / bounding extent (vacuum)
     float inv_ext[3];
     float inv_cw[3];   // 1 / cell width
-    int nc[3];
+    int nc[3];         // local grid; nc[2] counts the LOCAL z layers
     int ncell;
-    int periodic;
+    int periodic;      // minimum image in the pair distance, stencil wraps in x and y
+    int z_ring;        // 1: the local z layers are the whole periodic ring (stencil wraps in z);
+                       // 0: a segment of it (domain decomposition: owned layers + one ghost layer each side) or vacuum
+    int kz_off;        // global z layer of local layer 0
+    int ncz_global;    // global number of z layers (== nc[2] unless decomposed)
+    int row_l0, row_l1;  // local z layers [row_l0, row_l1) carry list rows (the others are ghost layers)
 };
 
 // Nonbonded parameters passed by value to the pair kernels.

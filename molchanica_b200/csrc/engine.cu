@@ -175,9 +175,9 @@ extern "C" int mc_set_lj_table(mc_ctx *c, int n_types, const float *sigma_eps) {
 }
 
 static int upload_atoms_local(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type, const mc_float4 *vel,
-                              const uint8_t *flags, const int *orig_ids) {
-    // allocate every per-atom array for n local atoms and upload in the given order
-    MC_CUDA(c, c->alloc_atoms((size_t)n));
+                              const uint8_t *flags, const int *orig_ids, size_t alloc_n) {
+    // allocate every per-atom array for alloc_n >= n local atoms and upload n in the given order
+    MC_CUDA(c, c->alloc_atoms(std::max<size_t>((size_t)n, alloc_n)));
     c->n = n;
     c->cur = 0;
     cudaStream_t st = c->st;
@@ -218,7 +218,7 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
     c->n_rows = n;
     if (type)
         for (int64_t k = 0; k < n; ++k) MC_REQUIRE(c, type[k] < pair_force_max_types(), "mc_set_atoms: type id out of range");
-    int rc = upload_atoms_local(c, n, xyzq, type, vel_invmass, flags, nullptr);
+    int rc = upload_atoms_local(c, n, xyzq, type, vel_invmass, flags, nullptr, (size_t)n);
     if (rc != MC_OK) return rc;
     // slot_of_orig = identity
     std::vector<int> ids((size_t)n);
@@ -228,8 +228,8 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
 }
 
 int engine_upload_local(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type, const mc_float4 *vel,
-                        const uint8_t *flags, const int *orig_ids) {
-    return upload_atoms_local(c, n, xyzq, type, vel, flags, orig_ids);
+                        const uint8_t *flags, const int *orig_ids, size_t alloc_n) {
+    return upload_atoms_local(c, n, xyzq, type, vel, flags, orig_ids, alloc_n);
 }
 
 extern "C" int mc_set_exclusions(mc_ctx *c, const int32_t *start, const int32_t *idx) {
@@ -354,6 +354,11 @@ static int setup_grid(mc_ctx *c) {
         }
         g.ncell = (int)ncell;
         g.periodic = 1;
+        g.z_ring = 1;
+        g.kz_off = 0;
+        g.ncz_global = g.nc[2];
+        g.row_l0 = 0;
+        g.row_l1 = g.nc[2];
         c->ncell_cap = (size_t)ncell;
         c->h_grid = g;
         MC_CUDA(c, cudaMemcpyAsync(c->grid.p, &c->h_grid, sizeof(GridParams), cudaMemcpyHostToDevice, c->st));
@@ -394,11 +399,23 @@ int engine_build_list(mc_ctx *c) {
     ra.cell_start = c->cell_start.p;
     ra.mark_interior = (c->skin < 0.5f * list_radius(c)) ? 1 : 0;
     launch_reorder(n, kk[which], vv[which], c->grid.p, ra, st, &c->launches);
+    c->cell_of_slot = kk[which];  // sorted keys = cell of every slot, valid until the next sort
     c->cur = nx;
     c->identity_order = false;
+    tr.stop();
+    return engine_build_rows(c);
+}
+
+// Verlet rows for the atoms of the row layers, from cell-ordered arrays + cell_start (shared by the
+// single-GPU path above and the decomposed path in comm.cu).
+int engine_build_rows(mc_ctx *c) {
+    const int n = (int)c->n;
+    cudaStream_t st = c->st;
+    TimedRegion tr(c, c->build_acc);
     const float r_list = list_radius(c);
     const float rl2 = r_list * r_list;
-    const int n_rows = (int)c->n_rows_sorted();
+    const int n_rows = n;  // every local slot may carry a row; ghost layers are skipped by the grid's row_l0/row_l1
+    MC_CUDA(c, cudaMemsetAsync(c->nbr_count.p, 0, sizeof(uint32_t) * (size_t)n, st));
     const int32_t *es = c->have_excl ? c->excl_start.p : nullptr, *ei = c->have_excl ? c->excl_idx.p : nullptr;
     uint32_t *h_ctl = reinterpret_cast<uint32_t *>(c->h_pinned);
     size_t total = 0;
@@ -418,7 +435,8 @@ int engine_build_list(mc_ctx *c) {
         MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->tile_need.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         MC_CUDA(c, cudaStreamSynchronize(st));
         if (h_ctl[3] != 0) {  // a neighbourhood did not fit the tile
-            const uint32_t need = (h_ctl[2] + h_ctl[2] / 4 + 127u) & ~31u;  // + NaN padding to whole chunks
+            uint32_t need = (h_ctl[2] + h_ctl[2] / 4 + 127u) & ~31u;  // 25 % head-room + NaN padding to whole chunks
+            if (need > tile_sweep_max_atoms() && ((h_ctl[2] + 127u) & ~31u) <= tile_sweep_max_atoms()) need = tile_sweep_max_atoms();
             if (need <= tile_sweep_max_atoms()) { c->tile_cap = need; continue; }
             tiled = c->use_tile = false;  // too dense for shared memory: two-pass global sweep from now on
             break;
@@ -431,14 +449,14 @@ int engine_build_list(mc_ctx *c) {
         break;
     }
     if (!tiled) {
-        launch_sweep(false, n_rows, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, c->orig[c->cur].p, es, ei,
+        launch_sweep(false, n_rows, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, c->cell_of_slot, c->orig[c->cur].p, es, ei,
                      c->nbr_count.p, nullptr, nullptr, st, &c->launches);
         exclusive_scan_u32(c->nbr_count.p, c->nbr_start.p, (size_t)n_rows, 1, c->scratch.p, st, &c->launches);
         MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->nbr_start.p + n_rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         MC_CUDA(c, cudaStreamSynchronize(st));
         total = h_ctl[0];
         if (total > c->nbr_list.n) MC_CUDA(c, c->nbr_list.ensure(total + total / 8 + 1024));
-        launch_sweep(true, n_rows, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, c->orig[c->cur].p, es, ei,
+        launch_sweep(true, n_rows, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, c->cell_of_slot, c->orig[c->cur].p, es, ei,
                      c->nbr_count.p, c->nbr_start.p, c->nbr_list.p, st, &c->launches);
     }
     MC_CUDA(c, cudaMemsetAsync(c->rebuild_flag.p, 0, sizeof(int), st));
@@ -486,6 +504,7 @@ static NbParams make_params(const mc_ctx *c) {
 int engine_launch_forces(mc_ctx *c, bool want_energy) {
     PairLaunch L;
     L.n_rows = (int)c->n_rows_sorted();
+    L.row0 = (int)c->row0;
     L.xyzq = c->xyzq[c->cur].p;
     L.type = c->type[c->cur].p;
     L.flags = c->flags[c->cur].p;
@@ -504,7 +523,7 @@ int engine_launch_forces(mc_ctx *c, bool want_energy) {
         tr.stop();
     }
     if (c->have_p14)
-        launch_pairs14(L.n_rows, L.xyzq, L.type, c->orig[c->cur].p, c->slot_of_orig.p, c->p14_start.p, c->p14_idx.p,
+        launch_pairs14(L.n_rows, L.row0, L.xyzq, L.type, c->orig[c->cur].p, c->slot_of_orig.p, c->p14_start.p, c->p14_idx.p,
                        c->ljtab.p, L.p, c->scale14_lj, c->scale14_q, L.lj_on, (L.coul != MC_COULOMB_NONE) ? 1 : 0,
                        c->force.p, c->st, &c->launches);
     MC_CUDA(c, cudaGetLastError());
@@ -560,6 +579,7 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     // flag travels to pinned host memory asynchronously, and the host acts on the flag of the
     // PREVIOUS step while the GPU is already busy -- no per-step stream synchronisation.
     const float max_disp = 0.5f * c->skin;
+    if (c->comm_active && c->rebuild_every <= 0) c->rebuild_every = 20;  // decomposed runs rebuild on a fixed schedule
     const bool pipelined = !c->comm_active && c->rebuild_every <= 0 && !c->sync_rebuild;
     const float lookahead = pipelined ? 2.5f : 0.f;
     int *h_flag = reinterpret_cast<int *>(c->h_pinned) + 8;  // two slots
@@ -573,9 +593,10 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     for (int s = 0; s < n_steps; ++s) {
         {
             TimedRegion tr(c, c->integ_acc);
-            launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p, c->vel[c->cur].p, c->force.p, d_ext,
-                              c->orig[c->cur].p, c->flags[c->cur].p, c->xref.p, s == 0 ? 0.5f * dt : dt, dt, max_disp,
-                              lookahead, c->rebuild_flag.p, st, &c->launches);
+            const size_t r0 = (size_t)c->row0;
+            launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, d_ext,
+                              c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, s == 0 ? 0.5f * dt : dt, dt,
+                              max_disp, lookahead, c->rebuild_flag.p, st, &c->launches);
             tr.stop();
         }
         c->steps_since_build++;
@@ -608,9 +629,10 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     }
     if (n_steps > 0) {
         TimedRegion tr(c, c->integ_acc);
-        launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p, c->vel[c->cur].p, c->force.p, d_ext,
-                          c->orig[c->cur].p, c->flags[c->cur].p, c->xref.p, 0.5f * dt, 0.f, 0.f, 0.f, c->rebuild_flag.p, st,
-                          &c->launches);
+        const size_t r0 = (size_t)c->row0;
+        launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, d_ext,
+                          c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, 0.5f * dt, 0.f, 0.f, 0.f,
+                          c->rebuild_flag.p, st, &c->launches);
         tr.stop();
     }
     MC_CUDA(c, cudaEventRecord(c->ev_step_b, st));
@@ -621,6 +643,12 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     c->last_step_ms = ms;
     // the flag of the last drift has not been acted upon: make the next evaluation rebuild first
     if (pipelined && n_steps > 0 && !skip_prev && h_flag[(n_steps - 1) & 1] != 0) c->list_valid = false;
+    if (c->rebuild_every > 0 && n_steps > 0) {
+        // fixed schedule: the displacement flag is only a safety net -- an atom that moved more than skin/2
+        // between two builds means rebuild_every is too large for this system
+        MC_CUDA(c, cudaMemcpy(h_flag, c->rebuild_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (*h_flag != 0) { c->n_list_violations++; c->list_valid = false; }
+    }
     c->collect_timings();
     return MC_OK;
 }
@@ -634,7 +662,8 @@ static int read_sorted_to_orig(mc_ctx *c, const float4 *sorted, mc_float4 *out) 
     if (n == 0) return MC_OK;
     MC_CUDA(c, c->stage.ensure((size_t)c->n_global));
     if (c->comm_active) MC_CUDA(c, cudaMemsetAsync(c->stage.p, 0, sizeof(float4) * c->n_global, c->st));
-    launch_gather_to_orig((int)n, sorted, c->orig[c->cur].p, c->stage.p, c->st, &c->launches);
+    launch_gather_to_orig((int)n, sorted + c->row0, c->orig[c->cur].p + c->row0, c->stage.p, c->st, &c->launches);
+    if (c->comm_active) { int rc = comm_allreduce_f4(c, c->stage.p, c->n_global); if (rc != MC_OK) return rc; }
     MC_CUDA(c, cudaMemcpyAsync(out, c->stage.p, sizeof(float4) * c->n_global, cudaMemcpyDeviceToHost, c->st));
     MC_CUDA(c, cudaStreamSynchronize(c->st));
     return MC_OK;
@@ -670,7 +699,7 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
     }
     MC_CUDA(c, c->red_partial.ensure((size_t)energy_partial_elems()));
     MC_CUDA(c, c->red_out.ensure(4));
-    launch_energy_reduce((int)c->n_rows_sorted(), c->force.p, c->vel[c->cur].p, c->red_partial.p, c->red_out.p, c->st,
+    launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + c->row0, c->vel[c->cur].p + c->row0, c->red_partial.p, c->red_out.p, c->st,
                          &c->launches);
     double h[3];
     MC_CUDA(c, cudaMemcpyAsync(h, c->red_out.p, sizeof(h), cudaMemcpyDeviceToHost, c->st));
@@ -693,9 +722,10 @@ extern "C" int mc_get_stats(mc_ctx *c, mc_stats *out) {
         // true (unpadded) entry count = sum of the row lengths
         MC_CUDA(c, c->scratch.ensure(scan_scratch_elems((size_t)c->n + 1) + 64));
         MC_CUDA(c, c->cnt_orig.ensure((size_t)c->n + 1));
-        exclusive_scan_u32(c->nbr_count.p, c->cnt_orig.p, (size_t)c->n_rows_sorted(), 0, c->scratch.p, c->st, &c->launches);
+        // ghost slots carry zero-length rows (cleared at build time), so the sum runs over every local slot
+        exclusive_scan_u32(c->nbr_count.p, c->cnt_orig.p, (size_t)c->n, 0, c->scratch.p, c->st, &c->launches);
         uint32_t tot = 0;
-        MC_CUDA(c, cudaMemcpyAsync(&tot, c->cnt_orig.p + c->n_rows_sorted(), sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
+        MC_CUDA(c, cudaMemcpyAsync(&tot, c->cnt_orig.p + c->n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
         MC_CUDA(c, cudaStreamSynchronize(c->st));
         c->n_pairs_listed = tot;
         c->pairs_dirty = false;
@@ -711,6 +741,7 @@ extern "C" int mc_get_stats(mc_ctx *c, mc_stats *out) {
     out->build_ms_sum = c->build_acc.ms; out->builds_timed = c->build_acc.count;
     out->integrate_ms_sum = c->integ_acc.ms; out->integrate_launches_timed = c->integ_acc.count;
     out->halo_ms_sum = c->halo_acc.ms; out->halos_timed = c->halo_acc.count;
+    out->n_list_violations = c->n_list_violations;
     return MC_OK;
 }
 

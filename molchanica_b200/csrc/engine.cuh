@@ -49,6 +49,7 @@ struct mc_ctx {
     // system
     int64_t n = 0;         // atoms held locally (owned + ghosts)
     int64_t n_rows = 0;    // atoms owned locally (rows of the list); == n on a single GPU
+    int64_t row0 = 0;      // first owned slot of the cell-ordered arrays (ghost layer in front when decomposed)
     int64_t n_global = 0;  // atoms of the whole system (original ids run over this range)
     bool periodic = false;
     float lo[3] = {0, 0, 0}, ext[3] = {1, 1, 1};
@@ -64,6 +65,7 @@ struct mc_ctx {
     bool forces_have_energy = false;
     bool grid_dirty = true, list_valid = false, forces_valid = false, identity_order = true, pairs_dirty = true;
     int cur = 0;
+    const uint32_t *cell_of_slot = nullptr;  // sorted cell keys of the current build (slot -> local cell)
     int key_bits = 1;
     size_t ncell_cap = 0;
     float cw_min = 0;
@@ -76,6 +78,7 @@ struct mc_ctx {
     uint32_t tile_cap = 1024;  // tile capacity in atoms, grows on demand
 
     // counters
+    int64_t n_list_violations = 0;
     int64_t launches = 0, n_rebuilds = 0, n_steps = 0, n_pairs_listed = 0, n_padded_entries = 0;
     TimeAcc pair_acc, build_acc, integ_acc, halo_acc, dock_acc;
     double last_pair_ms = 0, last_dock_ms = 0, last_step_ms = 0;
@@ -179,9 +182,10 @@ struct TimedRegion {
 
 // engine.cu
 int engine_build_list(mc_ctx *c);
+int engine_build_rows(mc_ctx *c);
 int engine_launch_forces(mc_ctx *c, bool want_energy);
 int engine_upload_local(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type, const mc_float4 *vel,
-                        const uint8_t *flags, const int *orig_ids);
+                        const uint8_t *flags, const int *orig_ids, size_t alloc_n);
 
 // comm.cu -- slab domain decomposition + ghost-atom halo exchange
 int comm_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type, const mc_float4 *vel,
@@ -190,4 +194,5 @@ int comm_rebuild(mc_ctx *c);          // migrate + re-select ghosts + engine_bui
 int comm_halo_positions(mc_ctx *c);   // per-step ghost position refresh
 int comm_agree_flag(mc_ctx *c, bool *flag);
 int comm_allreduce3(mc_ctx *c, double v[3]);
+int comm_allreduce_f4(mc_ctx *c, float4 *buf, int64_t n);  // in-place sum over ranks
 void comm_destroy(mc_ctx *c);

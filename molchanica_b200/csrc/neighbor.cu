@@ -89,6 +89,11 @@ __global__ void grid_from_bbox_kernel(const float *__restrict__ bb, float cw_min
     }
     g->ncell = nc[0] * nc[1] * nc[2];
     g->periodic = 0;
+    g->z_ring = 0;
+    g->kz_off = 0;
+    g->ncz_global = nc[2];
+    g->row_l0 = 0;
+    g->row_l1 = nc[2];
 }
 
 // ---- wrap + cell key --------------------------------------------------------------------------
@@ -140,8 +145,8 @@ __global__ void __launch_bounds__(256) reorder_kernel(int n, const uint32_t *__r
     // the minimum image for this row (d - rintf(d/ext)*ext with n == 0 is d itself, bit for bit).
     uint8_t fl = a.flags_in[src] & (uint8_t)~MC_FLAG_INTERIOR;
     if (gp->periodic && a.mark_interior) {
-        const int nc0 = gp->nc[0], nc1 = gp->nc[1], nc2 = gp->nc[2];
-        const int c0 = cur % nc0, c1 = (cur / nc0) % nc1, c2 = cur / (nc0 * nc1);
+        const int nc0 = gp->nc[0], nc1 = gp->nc[1], nc2 = gp->ncz_global;
+        const int c0 = cur % nc0, c1 = (cur / nc0) % nc1, c2 = (cur / (nc0 * nc1) + gp->kz_off) % nc2;  // global layer
         if (nc0 >= 3 && nc1 >= 3 && nc2 >= 3 && c0 >= 1 && c0 <= nc0 - 2 && c1 >= 1 && c1 <= nc1 - 2 && c2 >= 1 &&
             c2 <= nc2 - 2)
             fl |= MC_FLAG_INTERIOR;
@@ -162,6 +167,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) sweep_kernel(int n_rows, const float4 *__restrict__ xyzq,
                                                      const uint32_t *__restrict__ cell_start,
                                                      const GridParams *__restrict__ gp, float rl2,
+                                                     const uint32_t *__restrict__ cell_of_slot,
                                                      const int *__restrict__ orig,
                                                      const int32_t *__restrict__ excl_start,
                                                      const int32_t *__restrict__ excl_idx,
@@ -173,10 +179,14 @@ __global__ void __launch_bounds__(256) sweep_kernel(int n_rows, const float4 *__
     if (i >= n_rows) return;
     const GridParams g = *gp;
     const float4 pi = xyzq[i];
-    int ci[3];
-    ci[0] = min(max((int)floorf((pi.x - g.lo[0]) * g.inv_cw[0]), 0), g.nc[0] - 1);
-    ci[1] = min(max((int)floorf((pi.y - g.lo[1]) * g.inv_cw[1]), 0), g.nc[1] - 1);
-    ci[2] = min(max((int)floorf((pi.z - g.lo[2]) * g.inv_cw[2]), 0), g.nc[2] - 1);
+    // the (local) cell of this slot comes from the sorted keys: on a decomposed rank the local z layer
+    // is not a function of the coordinate alone
+    const int cell = (int)cell_of_slot[i];
+    int ci[3] = {cell % g.nc[0], (cell / g.nc[0]) % g.nc[1], cell / (g.nc[0] * g.nc[1])};
+    if (ci[2] < g.row_l0 || ci[2] >= g.row_l1) {  // ghost layer: no row
+        if (!FILL && lane == 0) nbr_count[i] = 0;
+        return;
+    }
     int ex_lo = 0, ex_hi = 0;
     if (excl_start) {
         const int oi = orig[i];
@@ -188,11 +198,11 @@ __global__ void __launch_bounds__(256) sweep_kernel(int n_rows, const float4 *__
 
     // offsets per axis, de-duplicated for tiny periodic grids (oracle/md_oracle.c does the same)
     const int lo_y = (g.nc[1] >= 3 || !g.periodic) ? -1 : 0, hi_y = (g.nc[1] >= 2 || !g.periodic) ? 1 : 0;
-    const int lo_z = (g.nc[2] >= 3 || !g.periodic) ? -1 : 0, hi_z = (g.nc[2] >= 2 || !g.periodic) ? 1 : 0;
+    const int lo_z = (g.nc[2] >= 3 || !g.z_ring) ? -1 : 0, hi_z = (g.nc[2] >= 2 || !g.z_ring) ? 1 : 0;
 
     for (int dz = lo_z; dz <= hi_z; ++dz) {
         int kz = ci[2] + dz;
-        if (g.periodic) kz = (kz + g.nc[2]) % g.nc[2];
+        if (g.z_ring) kz = (kz + g.nc[2]) % g.nc[2];
         else if (kz < 0 || kz >= g.nc[2]) continue;
         for (int dy = lo_y; dy <= hi_y; ++dy) {
             int ky = ci[1] + dy;
@@ -324,14 +334,14 @@ void launch_reorder(int n, const uint32_t *skeys, const uint32_t *svals, const G
 }
 
 void launch_sweep(bool fill, int n_rows, const float4 *xyzq, const uint32_t *cell_start, const GridParams *g, float rl2,
-                  const int *orig, const int32_t *excl_start, const int32_t *excl_idx, uint32_t *nbr_count,
+                  const uint32_t *cell_of_slot, const int *orig, const int32_t *excl_start, const int32_t *excl_idx, uint32_t *nbr_count,
                   const uint32_t *nbr_start, uint32_t *nbr_list, cudaStream_t st, int64_t *launches) {
     const unsigned blocks = div_up((size_t)n_rows * 32, 256);
     if (fill)
-        sweep_kernel<true><<<blocks, 256, 0, st>>>(n_rows, xyzq, cell_start, g, rl2, orig, excl_start, excl_idx, nbr_count,
+        sweep_kernel<true><<<blocks, 256, 0, st>>>(n_rows, xyzq, cell_start, g, rl2, cell_of_slot, orig, excl_start, excl_idx, nbr_count,
                                                    nbr_start, nbr_list);
     else
-        sweep_kernel<false><<<blocks, 256, 0, st>>>(n_rows, xyzq, cell_start, g, rl2, orig, excl_start, excl_idx, nbr_count,
+        sweep_kernel<false><<<blocks, 256, 0, st>>>(n_rows, xyzq, cell_start, g, rl2, cell_of_slot, orig, excl_start, excl_idx, nbr_count,
                                                     nbr_start, nbr_list);
     *launches += 1;
 }

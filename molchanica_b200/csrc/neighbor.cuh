@@ -19,7 +19,7 @@ void launch_wrap_key(float4 *xyzq, int n, const GridParams *g, uint32_t *keys, u
 void launch_reorder(int n, const uint32_t *skeys, const uint32_t *svals, const GridParams *g, const ReorderArrays &a,
                     cudaStream_t st, int64_t *launches);
 void launch_sweep(bool fill, int n_rows, const float4 *xyzq, const uint32_t *cell_start, const GridParams *g, float rl2,
-                  const int *orig, const int32_t *excl_start, const int32_t *excl_idx, uint32_t *nbr_count,
+                  const uint32_t *cell_of_slot, const int *orig, const int32_t *excl_start, const int32_t *excl_idx, uint32_t *nbr_count,
                   const uint32_t *nbr_start, uint32_t *nbr_list, cudaStream_t st, int64_t *launches);
 void launch_export_rows(int n, const int *orig, const uint32_t *nbr_count, const uint32_t *nbr_start,
                         const uint32_t *nbr_list, uint32_t *cnt_orig, uint32_t *start_orig, uint32_t *rows,

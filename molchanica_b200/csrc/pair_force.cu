@@ -113,7 +113,7 @@ __device__ __forceinline__ void row_loop(const float4 xi, const uint32_t *__rest
 }
 
 template <int LANES, bool MULTI, int COUL, bool PBC, bool ENERGY>
-__global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, const float4 *__restrict__ xyzq,
+__global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, int row0, const float4 *__restrict__ xyzq,
                                                           const uint16_t *__restrict__ type,
                                                           const uint8_t *__restrict__ flags,
                                                           const uint32_t *__restrict__ nbr_start,
@@ -127,8 +127,9 @@ __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, const float
         __syncthreads();
     }
     const int sub = threadIdx.x % LANES;
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-    const bool live = i < n_rows;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const bool live = r < n_rows;
+    const int i = row0 + r;
     Acc a = {0.f, 0.f, 0.f, 0.f};
     if (live) {
         const float4 xi = __ldg(xyzq + i);
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, const float
 
 // Amber 1-4 rows: every atom sums its own 1-4 partners (deterministic, no atomics), no cutoff,
 // LJ x scale_lj, Coulomb x scale_q.  Partner ids are original ids.
-__global__ void __launch_bounds__(128) pairs14_kernel(int n_rows, const float4 *__restrict__ xyzq,
+__global__ void __launch_bounds__(128) pairs14_kernel(int n_rows, int row0, const float4 *__restrict__ xyzq,
                                                        const uint16_t *__restrict__ type, const int *__restrict__ orig,
                                                        const int *__restrict__ slot_of_orig,
                                                        const int32_t *__restrict__ p14_start,
@@ -162,8 +163,9 @@ __global__ void __launch_bounds__(128) pairs14_kernel(int n_rows, const float4 *
                                                        const float2 *__restrict__ ljtab, const NbParams p,
                                                        float scale_lj, float scale_q, int lj_on, int coul_on,
                                                        float4 *__restrict__ force) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_rows) return;
+    const int kr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kr >= n_rows) return;
+    const int k = row0 + kr;
     const int oi = orig[k];
     const int e0 = p14_start[oi], e1 = p14_start[oi + 1];
     if (e0 == e1) return;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(128) pairs14_kernel(int n_rows, const float4 *
     float4 acc = force[k];
     for (int e = e0; e < e1; ++e) {
         const int j = slot_of_orig[p14_idx[e]];
+        if (j < 0) continue;  // partner not held by this rank (cannot happen within one ghost layer)
         const float4 xj = xyzq[j];
         float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
         if (p.periodic) {
@@ -243,7 +246,7 @@ void launch_lanes(const PairLaunch &L, cudaStream_t st) {
     const unsigned blocks = div_up(L.n_rows, rows_per_block);
     const size_t smem = L.multi ? sizeof(float2) * L.p.n_types * L.p.n_types : 0;
 #define MC_PF(M, C, P, E)                                                                                          \
-    pair_force_kernel<LANES, M, C, P, E><<<blocks, 128, smem, st>>>(L.n_rows, L.xyzq, L.type, L.flags, L.nbr_start, \
+    pair_force_kernel<LANES, M, C, P, E><<<blocks, 128, smem, st>>>(L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, \
                                                                     L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on, L.force)
 #define MC_PF_E(M, C, P) \
     if (L.energy) MC_PF(M, C, P, true); else MC_PF(M, C, P, false)
@@ -291,12 +294,12 @@ void launch_pair_force(const PairLaunch &L, cudaStream_t st, int64_t *launches) 
     *launches += 1;
 }
 
-void launch_pairs14(int n_rows, const float4 *xyzq, const uint16_t *type, const int *orig, const int *slot_of_orig,
+void launch_pairs14(int n_rows, int row0, const float4 *xyzq, const uint16_t *type, const int *orig, const int *slot_of_orig,
                     const int32_t *p14_start, const int32_t *p14_idx, const float2 *ljtab, const NbParams &p,
                     float scale_lj, float scale_q, int lj_on, int coul_on, float4 *force, cudaStream_t st,
                     int64_t *launches) {
     if (n_rows <= 0) return;
-    pairs14_kernel<<<div_up(n_rows, 128), 128, 0, st>>>(n_rows, xyzq, type, orig, slot_of_orig, p14_start, p14_idx, ljtab,
+    pairs14_kernel<<<div_up(n_rows, 128), 128, 0, st>>>(n_rows, row0, xyzq, type, orig, slot_of_orig, p14_start, p14_idx, ljtab,
                                                        p, scale_lj, scale_q, lj_on, coul_on, force);
     *launches += 1;
 }

@@ -4,6 +4,7 @@
 
 struct PairLaunch {
     int n_rows;
+    int row0;  // first row slot (rows are slots row0 .. row0 + n_rows - 1)
     const float4 *xyzq;
     const uint16_t *type;
     const uint8_t *flags;  // MC_FLAG_INTERIOR decides whether a row needs the minimum image
@@ -21,7 +22,7 @@ struct PairLaunch {
 int pair_force_max_types();
 cudaError_t pair_force_prepare();
 void launch_pair_force(const PairLaunch &L, cudaStream_t st, int64_t *launches);
-void launch_pairs14(int n_rows, const float4 *xyzq, const uint16_t *type, const int *orig, const int *slot_of_orig,
+void launch_pairs14(int n_rows, int row0, const float4 *xyzq, const uint16_t *type, const int *orig, const int *slot_of_orig,
                     const int32_t *p14_start, const int32_t *p14_idx, const float2 *ljtab, const NbParams &p,
                     float scale_lj, float scale_q, int lj_on, int coul_on, float4 *force, cudaStream_t st,
                     int64_t *launches);

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, 3) tile_build_kernel(
     const GridParams *__restrict__ gp, float rl2, float rc2_inner, const int *__restrict__ orig,
     const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx, uint32_t *__restrict__ nbr_count,
     uint32_t *__restrict__ nbr_start, uint32_t *__restrict__ nbr_list, uint32_t list_cap, uint32_t tile_cap, int split,
-    uint32_t *__restrict__ ctl /* [0] work counter, [1] list cursor, [2] max tile atoms seen, [3] tile overflow */) {
+    int n_stages /* 1 or 2 tiles in flight */, uint32_t *__restrict__ ctl /* [0] work counter, [1] list cursor, [2] max tile atoms seen, [3] tile overflow */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // per stage: tile_cap float4 positions, then tile_cap slot ids
     const size_t stage_bytes = (size_t)tile_cap * (sizeof(float4) + sizeof(uint32_t));
@@ -315,14 +315,17 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, 3) tile_build_kernel(
                 a1 = cell_start[c + 1];
                 if (a0 == a1) continue;  // empty cell: nothing to stage (warp-uniform)
                 const int c0 = c % g.nc[0], c1 = (c / g.nc[0]) % g.nc[1], c2 = c / (g.nc[0] * g.nc[1]);
+                if (c2 < g.row_l0 || c2 >= g.row_l1) continue;  // ghost layer: its atoms carry no rows
                 if (lane < 9) {  // one (dz, dy) stencil row per lane -> up to two contiguous slot ranges
                     const int dy = lane % 3 - 1, dz = lane / 3 - 1;
                     const int lo_y = (g.nc[1] >= 3 || !g.periodic) ? -1 : 0, hi_y = (g.nc[1] >= 2 || !g.periodic) ? 1 : 0;
-                    const int lo_z = (g.nc[2] >= 3 || !g.periodic) ? -1 : 0, hi_z = (g.nc[2] >= 2 || !g.periodic) ? 1 : 0;
+                    const int lo_z = (g.nc[2] >= 3 || !g.z_ring) ? -1 : 0, hi_z = (g.nc[2] >= 2 || !g.z_ring) ? 1 : 0;
                     int ky = c1 + dy, kz = c2 + dz;
                     bool ok = dy >= lo_y && dy <= hi_y && dz >= lo_z && dz <= hi_z;
-                    if (g.periodic) { ky = (ky + g.nc[1]) % g.nc[1]; kz = (kz + g.nc[2]) % g.nc[2]; }
-                    else if (ky < 0 || ky >= g.nc[1] || kz < 0 || kz >= g.nc[2]) ok = false;
+                    if (g.periodic) ky = (ky + g.nc[1]) % g.nc[1];
+                    else if (ky < 0 || ky >= g.nc[1]) ok = false;
+                    if (g.z_ring) kz = (kz + g.nc[2]) % g.nc[2];
+                    else if (kz < 0 || kz >= g.nc[2]) ok = false;
                     if (ok) {
                         const int rowbase = (kz * g.nc[1] + ky) * g.nc[0];
                         int x0, x1, y0 = 0, y1 = -1;  // second run empty unless the x stencil wraps
@@ -355,17 +358,21 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, 3) tile_build_kernel(
                 uint32_t so = 0;
                 if (lane == 4) so = (a0 >= r0.src && a0 < r0.src + r0.cnt) ? r0.off + (a0 - r0.src) : r1.off + (a0 - r1.src);
                 self_off = __shfl_sync(MC_FULL_MASK, so, 4);
-                const bool interior = g.periodic && g.nc[0] >= 3 && g.nc[1] >= 3 && g.nc[2] >= 3 && c0 >= 1 &&
-                                      c0 <= g.nc[0] - 2 && c1 >= 1 && c1 <= g.nc[1] - 2 && c2 >= 1 && c2 <= g.nc[2] - 2;
-                wrap = (g.periodic && !interior) ? ((g.nc[0] >= 3 && g.nc[1] >= 3 && g.nc[2] >= 3) ? 1 : 2) : 0;
+                // the minimum image is decided on the GLOBAL cell coordinates (a decomposed rank sees the seam of the
+                // periodic box only in the layers next to it)
+                const int c2g = (c2 + g.kz_off) % g.ncz_global;
+                const bool roomy = g.nc[0] >= 3 && g.nc[1] >= 3 && g.ncz_global >= 3;
+                const bool interior = g.periodic && roomy && c0 >= 1 && c0 <= g.nc[0] - 2 && c1 >= 1 && c1 <= g.nc[1] - 2 &&
+                                      c2g >= 1 && c2g <= g.ncz_global - 2;
+                wrap = (g.periodic && !interior) ? (roomy ? 1 : 2) : 0;
                 if (lane == 0) atomicMax(ctl + 2, m);
                 if (padded_size(m) > tile_cap) {  // does not fit: the host enlarges the tile (or falls back)
                     if (lane == 0) ctl[3] = 1u;
                     continue;
                 }
             }
-            const int s = it % TILE_STAGES;
-            mbar_wait(&empty_bar[s], ((it / TILE_STAGES) & 1) ^ 1);
+            const int s = it % n_stages;
+            mbar_wait(&empty_bar[s], ((it / n_stages) & 1) ^ 1);
             float4 *tile = reinterpret_cast<float4 *>(smem_raw + (size_t)s * stage_bytes);
             uint32_t *tile_slot = reinterpret_cast<uint32_t *>(tile + tile_cap);
             if (lane == 0) {
@@ -401,8 +408,8 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, 3) tile_build_kernel(
         const int cw = warp - 1;
         int pp = 0;
         for (uint32_t it = 0;; ++it) {
-            const int s = it % TILE_STAGES;
-            mbar_wait(&full_bar[s], (it / TILE_STAGES) & 1);
+            const int s = it % n_stages;
+            mbar_wait(&full_bar[s], (it / n_stages) & 1);
             const StageMeta M = meta[s];
             if (M.a0 == 0xffffffffu) break;
             const float4 *tile = reinterpret_cast<const float4 *>(smem_raw + (size_t)s * stage_bytes);
@@ -477,8 +484,9 @@ cudaError_t tile_sweep_prepare() {
     return cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
-// 16 B position + 4 B slot id per staged atom, TILE_STAGES stages in 200 KB
-uint32_t tile_sweep_max_atoms() { return ((200u * 1024u) / (20u * TILE_STAGES)) & ~31u; }
+// 16 B position + 4 B slot id per staged atom in 200 KB of shared memory; tiles above half of that run
+// single-buffered (no copy/sweep overlap, but still one L2 read per cell instead of one per atom)
+uint32_t tile_sweep_max_atoms() { return ((200u * 1024u) / 20u) & ~31u; }
 
 void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
                        const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
@@ -486,7 +494,8 @@ void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const f
                        uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches) {
     // persistent: exactly one resident wave of CTAs pulls (cell, slice) items from ctl[0]
     const long long items = (long long)grid_cells * split;
-    const size_t smem = (size_t)TILE_STAGES * tile_cap * (sizeof(float4) + sizeof(uint32_t));
+    const int n_stages = (size_t)2 * tile_cap * 20u <= 200u * 1024u ? 2 : 1;
+    const size_t smem = (size_t)n_stages * tile_cap * (sizeof(float4) + sizeof(uint32_t));
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_build_kernel, (TILE_WARPS + 1) * 32, smem);
     if (per_sm < 1) per_sm = 1;
@@ -494,6 +503,6 @@ void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const f
     cudaMemsetAsync(ctl, 0, 4 * sizeof(uint32_t), st);
     tile_build_kernel<<<grid, (TILE_WARPS + 1) * 32, smem, st>>>(n_rows, xyzq, cell_start, g, rl2, rc2_inner, orig, excl_start,
                                                                  excl_idx, nbr_count, nbr_start, nbr_list, list_cap, tile_cap,
-                                                                 split, ctl);
+                                                                 split, n_stages, ctl);
     *launches += 1;
 }

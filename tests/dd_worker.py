@@ -1,0 +1,67 @@
+"""One rank of a domain-decomposed run (spawned by tests/test_gpu_multi.py, one process per GPU).
+usage: dd_worker.py <rank> <world> <id_file> <case> <out_npz>"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from molchanica_b200 import workloads as W  # noqa: E402
+from molchanica_b200.engine import MdEngine  # noqa: E402
+
+
+def case_workload(name):
+    if name == "lj":
+        return W.lj_fluid(m=24), 30
+    if name == "solv":
+        w = W.solvated_c3()
+        w["coul_mode"] = 2  # continuous at the cutoff: trajectories are comparable
+        return w, 6
+    raise ValueError(name)
+
+
+def main():
+    rank, world, id_file, case, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4], sys.argv[5]
+    w, n_steps = case_workload(case)
+    e = MdEngine(device=rank)
+    uid = np.zeros(128, np.uint8)
+    if rank == 0:
+        e._chk(e._L.mc_comm_unique_id(uid.ctypes.data_as(C.c_void_p)))
+        with open(id_file + ".tmp", "wb") as f:
+            f.write(uid.tobytes())
+        os.replace(id_file + ".tmp", id_file)
+    else:
+        t0 = time.time()
+        while not os.path.exists(id_file):
+            if time.time() - t0 > 120:
+                raise SystemExit("timed out waiting for the NCCL id")
+            time.sleep(0.05)
+        uid = np.frombuffer(open(id_file, "rb").read(), np.uint8).copy()
+    e._chk(e._L.mc_comm_init(e._h, uid.ctypes.data_as(C.c_void_p), rank, world))
+    lo = np.asarray(w["box_lo"], np.float32)
+    e.set_box(lo, lo + np.asarray(w["box_ext"], np.float32), True)
+    e.set_cutoffs(w["rc_lj"], w["rc_q"], w["skin"], w["coul_mode"], w.get("alpha", 0.35))
+    e.set_lj_table(w["ljtab"])
+    e.set_atoms(w["xyzq"], w["type"], w["vel"])
+    e.set_exclusions(w.get("excl_start"), w.get("excl_idx"))
+    e.set_pairs14(w.get("pairs14"), w.get("scale14_lj", 0.5), w.get("scale14_q", 1 / 1.2))
+    e.set_option("rebuild_every", 5)
+    e.compute_forces()
+    f0 = e.forces()
+    en0 = e.energy()
+    st0 = e.stats()
+    e.step(w["dt"], n_steps)
+    x = e.positions()
+    v = e.velocities()
+    st = e.stats()
+    if rank == 0:
+        np.savez(out, f0=f0, x=x, v=v, e_pot=en0["energy_potential_nonbonded"], n_owned=st0["n_atoms"],
+                 n_ghosts=st0["n_ghosts"], rebuilds=st["n_rebuilds"], violations=st["n_list_violations"])
+    e.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,53 @@
+"""Domain decomposition (slabs of cell layers along z + NCCL ghost exchange) against the oracle and
+the single-GPU path.  Needs >= 2 B200s on the box (gpurun --gpus 2); skipped otherwise."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from molchanica_b200 import workloads as W
+from util import FORCE_RTOL, energy_close, force_rel_err, trajectory_close
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _n_gpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout
+        return sum(1 for ln in out.splitlines() if ln.startswith("GPU "))
+    except Exception:
+        return 0
+
+
+def _run(world, case):
+    d = tempfile.mkdtemp()
+    idf, out = os.path.join(d, "nccl_id"), os.path.join(d, "out.npz")
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dd_worker.py"), str(r), str(world), idf, case, out],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    logs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    return np.load(out)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("case", ["lj", "solv"])
+def test_decomposed_run_matches_oracle(world, case, oracle):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    sys.path.insert(0, HERE)
+    from dd_worker import case_workload
+    w, n_steps = case_workload(case)
+    r = _run(world, case)
+    nb = oracle.neighbors(w)
+    f64, scale, en = oracle.forces(w, nb, precision=64)
+    assert force_rel_err(r["f0"], f64, scale).max() < FORCE_RTOL
+    assert energy_close(float(r["e_pot"]), en.sum(), f64[:, 3])
+    ref = oracle.md_run(w, n_steps, precision=64)
+    ok, worst, sc = trajectory_close(r["x"], ref["xyzq"], w["xyzq"], w["box_ext"])
+    assert ok, (worst, sc)
+    assert int(r["violations"]) == 0
+    assert int(r["n_owned"]) < len(w["xyzq"]) and int(r["n_ghosts"]) > 0
