@@ -13,9 +13,10 @@ from molchanica_b200 import workloads as W  # noqa: E402
 from molchanica_b200.engine import MdEngine  # noqa: E402
 
 
-def case_workload(name):
+def case_workload(name, world=2):
     if name == "lj":
-        return W.lj_fluid(m=24), 30
+        # two cell layers per rank are the minimum: 24^3 atoms give 8 layers, 48^3 give 16
+        return W.lj_fluid(m=24 if world <= 4 else 48), 30
     if name == "solv":
         w = W.solvated_c3()
         w["coul_mode"] = 2  # continuous at the cutoff: trajectories are comparable
@@ -25,7 +26,7 @@ def case_workload(name):
 
 def main():
     rank, world, id_file, case, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4], sys.argv[5]
-    w, n_steps = case_workload(case)
+    w, n_steps = case_workload(case, world)
     e = MdEngine(device=rank)
     uid = np.zeros(128, np.uint8)
     if rank == 0:
@@ -48,7 +49,7 @@ def main():
     e.set_atoms(w["xyzq"], w["type"], w["vel"])
     e.set_exclusions(w.get("excl_start"), w.get("excl_idx"))
     e.set_pairs14(w.get("pairs14"), w.get("scale14_lj", 0.5), w.get("scale14_q", 1 / 1.2))
-    e.set_option("rebuild_every", 5)
+    e.set_option("rebuild_every", 5 if case == "lj" else 2)  # the unbonded solvated system has very fast hydrogens
     e.compute_forces()
     f0 = e.forces()
     en0 = e.energy()
