@@ -118,6 +118,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiler runs)")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,6 +169,9 @@ def main():
     e.set_atoms(w["xyzq"], w["type"], w["vel"])
     if args.lanes:
         e.set_option("pair_lanes", args.lanes)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        e.set_option(k, float(v))
 
     def barrier():
         if world > 1:

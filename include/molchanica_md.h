@@ -188,6 +188,10 @@ int mc_comm_unique_id(uint8_t id[128]);
 /* Join the communicator; slabs along z.  Must precede mc_set_atoms; afterwards mc_set_atoms
  * takes the GLOBAL system on every rank and keeps the atoms this rank owns. */
 int mc_comm_init(mc_ctx *ctx, const uint8_t id[128], int rank, int n_ranks);
+/* The decomposition arithmetic on its own (host only, usable without a GPU): out = {ncx, ncy, ncz
+ * global cell grid, kz0, kz1 owned z layers [kz0, kz1), ghost layer from prev, ghost layer from
+ * next, next rank}.  r_list = max(rc_lj, rc_q) + skin. */
+int mc_dd_plan(const float box_ext[3], float r_list, int rank, int n_ranks, int32_t out[8]);
 /* Number of atoms this rank currently owns / holds as ghosts. */
 int mc_comm_counts(mc_ctx *ctx, int64_t *n_owned, int64_t *n_ghost);
 /* Gather global arrays (original ids, length n_global) -- valid on every rank. */

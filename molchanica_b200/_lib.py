@@ -104,5 +104,6 @@ def lib():
     L.mc_comm_unique_id.argtypes = [vp]
     L.mc_comm_init.argtypes = [vp, vp, i32, i32]
     L.mc_comm_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.mc_dd_plan.argtypes = [vp, f32, i32, i32, vp]
     _LIB = L
     return L

@@ -231,30 +231,55 @@ int comm_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *
     return MC_OK;
 }
 
+// The decomposition arithmetic, shared by the device path below and by mc_dd_plan (host only, no GPU):
+// global cell grid of the periodic box and the z layers [kz0, kz1) a rank owns.
+static int dd_plan_grid(const float ext[3], float r_list, int rank, int n_ranks, int ncg[3], int *kz0, int *kz1,
+                        std::string *err) {
+    const double cw_min = (double)r_list * 1.001 + 1e-3;
+    for (int a = 0; a < 3; ++a) {
+        if (2.0f * r_list > ext[a]) { *err = "cutoff + skin exceeds half the periodic box"; return MC_E_INVALID; }
+        int m = (int)std::floor((double)ext[a] / cw_min);
+        m = std::max(1, std::min(m, 1024));
+        if (a == 2 && m >= 2 * n_ranks) m -= m % n_ranks;  // equal layer counts per rank when the box allows
+        ncg[a] = m;
+    }
+    if (ncg[2] < 2 * n_ranks) {
+        *err = "domain decomposition: the box holds " + std::to_string(ncg[2]) + " cell layers along z, need >= 2 per rank";
+        return MC_E_INVALID;
+    }
+    *kz0 = (int)((long long)ncg[2] * rank / n_ranks);
+    *kz1 = (int)((long long)ncg[2] * (rank + 1) / n_ranks);
+    return MC_OK;
+}
+
+extern "C" int mc_dd_plan(const float box_ext[3], float r_list, int rank, int n_ranks, int32_t out[8]) {
+    if (!box_ext || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return MC_E_INVALID;
+    int ncg[3], kz0, kz1;
+    std::string err;
+    int rc = dd_plan_grid(box_ext, r_list, rank, n_ranks, ncg, &kz0, &kz1, &err);
+    if (rc != MC_OK) return rc;
+    out[0] = ncg[0]; out[1] = ncg[1]; out[2] = ncg[2];
+    out[3] = kz0; out[4] = kz1;
+    out[5] = (kz0 - 1 + ncg[2]) % ncg[2];     // ghost layer received from the previous rank
+    out[6] = kz1 % ncg[2];                    // ghost layer received from the next rank
+    out[7] = (rank + 1) % n_ranks;            // next rank (prev = (rank + n - 1) % n)
+    return MC_OK;
+}
+
 static int dd_setup_grid(mc_ctx *c) {
     CommState *cs = c->comm;
     const float r_list = std::max(c->rc_lj, c->rc_q) + c->skin;
-    const double cw_min = (double)r_list * 1.001 + 1e-3;
     GridParams g;
     int ncg[3];
+    int rc = dd_plan_grid(c->ext, r_list, cs->rank, cs->n, ncg, &cs->kz0, &cs->kz1, &c->err);
+    if (rc != MC_OK) return rc;
     for (int a = 0; a < 3; ++a) {
-        if (2.0f * r_list > c->ext[a]) { c->err = "cutoff + skin exceeds half the periodic box"; return MC_E_INVALID; }
-        int m = (int)std::floor((double)c->ext[a] / cw_min);
-        m = std::max(1, std::min(m, 1024));
-        if (a == 2 && m >= 2 * cs->n) m -= m % cs->n;  // equal layer counts per rank when the box allows
-        ncg[a] = m;
         g.lo[a] = c->lo[a];
         g.ext[a] = c->ext[a];
         g.inv_ext[a] = 1.0f / c->ext[a];
-        g.inv_cw[a] = (float)((double)m / (double)c->ext[a]);
-    }
-    if (ncg[2] < 2 * cs->n) {
-        c->err = "domain decomposition: the box holds " + std::to_string(ncg[2]) + " cell layers along z, need >= 2 per rank";
-        return MC_E_INVALID;
+        g.inv_cw[a] = (float)((double)ncg[a] / (double)c->ext[a]);
     }
     cs->ncz = ncg[2];
-    cs->kz0 = (int)((long long)ncg[2] * cs->rank / cs->n);
-    cs->kz1 = (int)((long long)ncg[2] * (cs->rank + 1) / cs->n);
     cs->nl = cs->kz1 - cs->kz0;
     g.nc[0] = ncg[0]; g.nc[1] = ncg[1]; g.nc[2] = cs->nl + 2;
     g.ncell = g.nc[0] * g.nc[1] * g.nc[2];

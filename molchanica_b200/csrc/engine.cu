@@ -313,6 +313,8 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         const int v = (int)value;
         MC_REQUIRE(c, v == 4 || v == 8 || v == 16 || v == 32, "mc_set_option: pair_lanes must be 4, 8, 16 or 32");
         c->pair_lanes = v;
+    } else if (k == "pair_uniform") {
+        c->pair_uniform = value != 0.0;
     } else if (k == "sync_rebuild") {
         c->sync_rebuild = value != 0.0;
     } else if (k == "tile_sweep") {
@@ -476,10 +478,17 @@ extern "C" int mc_build_neighbors(mc_ctx *c) {
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->rc_lj > 0.f, "mc_build_neighbors: call mc_set_cutoffs first");
     MC_REQUIRE(c, c->n_types > 0, "mc_build_neighbors: call mc_set_lj_table first");
-    if (c->comm_active) return comm_rebuild(c);
+    if (c->comm_active) {
+        int rc = comm_rebuild(c);
+        if (rc != MC_OK) return rc;
+        MC_CUDA(c, cudaStreamSynchronize(c->st));
+        c->collect_timings();
+        return MC_OK;
+    }
     int rc = engine_build_list(c);
     if (rc != MC_OK) return rc;
     MC_CUDA(c, cudaStreamSynchronize(c->st));
+    c->collect_timings();
     return MC_OK;
 }
 
@@ -509,6 +518,7 @@ int engine_launch_forces(mc_ctx *c, bool want_energy) {
     L.type = c->type[c->cur].p;
     L.flags = c->flags[c->cur].p;
     L.energy = want_energy;
+    L.uniform = c->pair_uniform;
     L.nbr_start = c->nbr_start.p; L.nbr_count = c->nbr_count.p; L.nbr_list = c->nbr_list.p;
     L.ljtab = c->ljtab.p;
     L.p = make_params(c);
@@ -608,14 +618,16 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
             MC_CUDA(c, cudaEventRecord(c->ev_flag[s & 1], st));
             if (have_prev && !skip_prev) {
                 MC_CUDA(c, cudaEventSynchronize(c->ev_flag[(s - 1) & 1]));  // completed one kernel ago
-                rebuild = h_flag[(s - 1) & 1] != 0;
+                rebuild = (h_flag[(s - 1) & 1] & 1) != 0;
+                if (h_flag[(s - 1) & 1] & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
             }
             have_prev = true;
             skip_prev = rebuild;  // the flag copied just above still refers to the old reference positions
         } else {
             MC_CUDA(c, cudaMemcpyAsync(h_flag, c->rebuild_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             MC_CUDA(c, cudaStreamSynchronize(st));
-            rebuild = *h_flag != 0;
+            rebuild = (*h_flag & 1) != 0;
+            if (*h_flag & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
             if (c->comm_active && (rc = comm_agree_flag(c, &rebuild)) != MC_OK) return rc;
         }
         if (rebuild) {
@@ -643,10 +655,13 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     c->last_step_ms = ms;
     // the flag of the last drift has not been acted upon: make the next evaluation rebuild first
     if (pipelined && n_steps > 0 && !skip_prev && h_flag[(n_steps - 1) & 1] != 0) c->list_valid = false;
+    if (pipelined && n_steps > 0 && (h_flag[(n_steps - 1) & 1] & 2))
+        return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
     if (c->rebuild_every > 0 && n_steps > 0) {
         // fixed schedule: the displacement flag is only a safety net -- an atom that moved more than skin/2
         // between two builds means rebuild_every is too large for this system
         MC_CUDA(c, cudaMemcpy(h_flag, c->rebuild_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (*h_flag & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
         if (*h_flag != 0) { c->n_list_violations++; c->list_valid = false; }
     }
     c->collect_timings();

@@ -71,6 +71,7 @@ struct mc_ctx {
     float cw_min = 0;
     GridParams h_grid{};
     int pair_lanes = 8;
+    bool pair_uniform = false;  // warp-uniform pair loop (skips warp-wide skin-shell iterations)
     int rebuild_every = 0;
     int steps_since_build = 0;
     bool profiling = false;

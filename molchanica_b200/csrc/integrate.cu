@@ -40,9 +40,12 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(int n_rows, float4 *__r
             // distance this atom can cover in the next `lookahead` drifts is subtracted from the limit.
             const float thr = max_disp - lookahead * (fabsf(v.x) + fabsf(v.y) + fabsf(v.z)) * fabsf(drift);
             moved_far = thr <= 0.f || dx * dx + dy * dy + dz * dz > thr * thr;
+            // a simulation that blew up (overlapping atoms, time step too long) must surface as an error,
+            // not as out-of-range cell indices: bit 1 of the flag word reports non-finite coordinates
+            if (!(fabsf(x.x) + fabsf(x.y) + fabsf(x.z) < 1.0e30f)) atomicOr(rebuild_flag, 2);
         }
     }
-    if (drift != 0.f && __any_sync(MC_FULL_MASK, moved_far) && (threadIdx.x & 31) == 0) *rebuild_flag = 1;
+    if (drift != 0.f && __any_sync(MC_FULL_MASK, moved_far) && (threadIdx.x & 31) == 0) atomicOr(rebuild_flag, 1);
 }
 
 __global__ void gather_to_orig_kernel(int n, const float4 *__restrict__ sorted, const int *__restrict__ orig,

@@ -71,6 +71,10 @@ __global__ void grid_from_bbox_kernel(const float *__restrict__ bb, float cw_min
     for (int a = 0; a < 3; ++a) {
         g->lo[a] = bb[a] - 0.5f;
         ext[a] = bb[3 + a] - bb[a] + 1.0f;
+        if (!(ext[a] > 0.f && ext[a] < 1.0e7f)) {  // non-finite or absurd coordinates: keep the grid sane,
+            g->lo[a] = 0.f;                          // the step loop reports the blow-up (integrate.cu)
+            ext[a] = 1.0e7f;
+        }
     }
     int nc[3];
     for (int a = 0; a < 3; ++a) {

@@ -112,7 +112,74 @@ __device__ __forceinline__ void row_loop(const float4 xi, const uint32_t *__rest
     }
 }
 
+// Warp-uniform variant of the row loop: all 32 lanes run the same trip count (the longest of the
+// warp's 32/LANES rows), so a full-mask vote is legal inside it.  Rows are cutoff-partitioned at
+// build time (inner entries first, skin shell last): once every lane of the warp is in its skin
+// shell the vote fails and the whole warp skips the force arithmetic of that iteration.
 template <int LANES, bool MULTI, int COUL, bool PBC, bool ENERGY>
+__device__ __forceinline__ void row_loop_uniform(const float4 xi, const uint32_t *__restrict__ lst, uint32_t cnt, int sub,
+                                                 bool wrap, const float4 *__restrict__ xyzq,
+                                                 const uint16_t *__restrict__ type, const float2 *row, const NbParams &p,
+                                                 bool lj_on, Acc &a) {
+    uint32_t cnt_max = cnt;
+#pragma unroll
+    for (int d = LANES; d < 32; d <<= 1) cnt_max = max(cnt_max, __shfl_xor_sync(MC_FULL_MASK, cnt_max, d));
+    const bool any_wrap = PBC && __any_sync(MC_FULL_MASK, wrap);
+    const float2 lj1 = make_float2(p.sig2, p.eps24);
+    const float rc2_max = fmaxf(p.rc2_lj, COUL != MC_COULOMB_NONE ? p.rc2_q : 0.f);
+    for (uint32_t kk = 0; kk < cnt_max; kk += LANES) {
+        const uint32_t k = kk + sub;
+        const bool valid = k < cnt;
+        float dx = 0.f, dy = 0.f, dz = 0.f, r2 = 3.0e38f;
+        float4 xj = xi;
+        float2 lj = lj1;
+        if (valid) {
+            const uint32_t j = __ldg(lst + k);
+            xj = __ldg(xyzq + j);
+            if (MULTI) lj = row[__ldg(type + j)];
+            dx = xi.x - xj.x; dy = xi.y - xj.y; dz = xi.z - xj.z;
+            if (any_wrap && wrap) {
+                dx = __fmaf_rn(-rintf(dx * p.inv_ext[0]), p.ext[0], dx);
+                dy = __fmaf_rn(-rintf(dy * p.inv_ext[1]), p.ext[1], dy);
+                dz = __fmaf_rn(-rintf(dz * p.inv_ext[2]), p.ext[2], dz);
+            }
+            r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        }
+        if (!__any_sync(MC_FULL_MASK, r2 < rc2_max)) continue;  // the whole warp is in its skin shell
+        float f = 0.f, e = 0.f;
+        if (lj_on && r2 < p.rc2_lj) {
+            const float ir2 = rcp_approx(r2);
+            const float s2 = lj.x * ir2;
+            const float s6 = s2 * s2 * s2;
+            f = lj.y * s6 * __fmaf_rn(2.f, s6, -1.f) * ir2;
+            if (ENERGY) e = lj.y * (1.f / 6.f) * s6 * (s6 - 1.f);
+        }
+        if (COUL != MC_COULOMB_NONE) {
+            if (r2 < p.rc2_q) {
+                const float qq = xi.w * xj.w;
+                const float ir = rsqrt_approx(r2);
+                if (COUL == MC_COULOMB_PLAIN) {
+                    f = __fmaf_rn(qq * ir, rcp_approx(r2 + MC_SOFTENING_SQ), f);
+                    if (ENERGY) e = __fmaf_rn(qq, ir, e);
+                } else {
+                    const float r = r2 * ir;
+                    const float ar = p.alpha * r;
+                    const float erfc_ar = erfcf(ar);
+                    const float ex = __expf(-ar * ar);
+                    const float ir2 = ir * ir;
+                    f = __fmaf_rn(qq * ir, __fmaf_rn(erfc_ar, ir2, 2.f * p.alpha * MC_INV_SQRT_PI * ex * ir), f);
+                    if (ENERGY) e = __fmaf_rn(qq * erfc_ar, ir, e);
+                }
+            }
+        }
+        a.fx = __fmaf_rn(dx, f, a.fx);
+        a.fy = __fmaf_rn(dy, f, a.fy);
+        a.fz = __fmaf_rn(dz, f, a.fz);
+        if (ENERGY) a.e += e;
+    }
+}
+
+template <int LANES, bool MULTI, int COUL, bool PBC, bool ENERGY, bool UNIFORM>
 __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, int row0, const float4 *__restrict__ xyzq,
                                                           const uint16_t *__restrict__ type,
                                                           const uint8_t *__restrict__ flags,
@@ -131,7 +198,15 @@ __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, int row0, c
     const bool live = r < n_rows;
     const int i = row0 + r;
     Acc a = {0.f, 0.f, 0.f, 0.f};
-    if (live) {
+    if (UNIFORM) {
+        // every lane of the warp enters the loop (dead rows with a zero count)
+        const int ii = live ? i : row0;
+        const float4 xi = __ldg(xyzq + ii);
+        const uint32_t start = __ldg(nbr_start + ii), cnt = live ? __ldg(nbr_count + ii) : 0u;
+        const float2 *row = MULTI ? s_tab + (int)__ldg(type + ii) * p.n_types : nullptr;
+        const bool wrap = PBC && !(__ldg(flags + ii) & MC_FLAG_INTERIOR);
+        row_loop_uniform<LANES, MULTI, COUL, PBC, ENERGY>(xi, nbr_list + start, cnt, sub, wrap, xyzq, type, row, p, lj_on, a);
+    } else if (live) {
         const float4 xi = __ldg(xyzq + i);
         const uint32_t start = __ldg(nbr_start + i), cnt = __ldg(nbr_count + i);
         const float2 *row = MULTI ? s_tab + (int)__ldg(type + i) * p.n_types : nullptr;
@@ -245,9 +320,15 @@ void launch_lanes(const PairLaunch &L, cudaStream_t st) {
     const int rows_per_block = 128 / LANES;
     const unsigned blocks = div_up(L.n_rows, rows_per_block);
     const size_t smem = L.multi ? sizeof(float2) * L.p.n_types * L.p.n_types : 0;
-#define MC_PF(M, C, P, E)                                                                                          \
-    pair_force_kernel<LANES, M, C, P, E><<<blocks, 128, smem, st>>>(L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, \
-                                                                    L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on, L.force)
+#define MC_PF(M, C, P, E)                                                                                               \
+    do {                                                                                                                \
+        if (L.uniform)                                                                                                  \
+            pair_force_kernel<LANES, M, C, P, E, true><<<blocks, 128, smem, st>>>(                                      \
+                L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on, L.force); \
+        else                                                                                                            \
+            pair_force_kernel<LANES, M, C, P, E, false><<<blocks, 128, smem, st>>>(                                     \
+                L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on, L.force); \
+    } while (0)
 #define MC_PF_E(M, C, P) \
     if (L.energy) MC_PF(M, C, P, true); else MC_PF(M, C, P, false)
 #define MC_PF_C(M, P)                                                    \
@@ -272,7 +353,10 @@ cudaError_t pair_force_prepare() {
     cudaError_t e = cudaSuccess;
 #define MC_ATTR(LN, C, P, E)                                                                                     \
     if (e == cudaSuccess)                                                                                        \
-        e = cudaFuncSetAttribute(pair_force_kernel<LN, true, C, P, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        e = cudaFuncSetAttribute(pair_force_kernel<LN, true, C, P, E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 200 * 1024);                                                                    \
+    if (e == cudaSuccess)                                                                                        \
+        e = cudaFuncSetAttribute(pair_force_kernel<LN, true, C, P, E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  200 * 1024);
 #define MC_ATTR_C(LN, C) MC_ATTR(LN, C, true, true) MC_ATTR(LN, C, true, false) MC_ATTR(LN, C, false, true) MC_ATTR(LN, C, false, false)
 #define MC_ATTR_L(LN) MC_ATTR_C(LN, MC_COULOMB_NONE) MC_ATTR_C(LN, MC_COULOMB_PLAIN) MC_ATTR_C(LN, MC_COULOMB_ERFC)

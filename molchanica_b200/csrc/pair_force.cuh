@@ -16,6 +16,7 @@ struct PairLaunch {
     bool multi; // more than one LJ type
     int lanes;  // lanes per row: 4, 8, 16 or 32
     bool energy;  // also accumulate the per-atom energy row sum into force.w
+    bool uniform; // warp-uniform row loop with warp-wide skin-shell skipping
     float4 *force;
 };
 

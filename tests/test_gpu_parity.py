@@ -188,3 +188,35 @@ def test_full_size_c4_properties(Engine):
     assert np.abs(f[:, :3].sum(0)).max() < 1e-6 * np.abs(f[:, :3]).sum()
     assert abs(e.energy()["energy_potential_nonbonded"] - 0.5 * f[:, 3].sum()) < 1e-6 * abs(f[:, 3].sum())
     e.close()
+
+
+@pytest.mark.parametrize("uniform", [0, 1])
+def test_pair_loop_variants_agree_with_the_oracle(uniform, Engine, oracle):
+    """Option pair_uniform switches to the warp-uniform row loop (warp-wide skin-shell skipping)."""
+    for w in (W.solvated_c3(), W.lj_fluid(m=20)):
+        e = Engine.from_workload(w)
+        e.set_option("pair_uniform", uniform)
+        e.compute_forces()
+        nb = oracle.neighbors(w)
+        f64, scale, en = oracle.forces(w, nb, precision=64)
+        assert force_rel_err(e.forces(), f64, scale).max() < FORCE_RTOL
+        assert energy_close(e.energy()["energy_potential_nonbonded"], en.sum(), f64[:, 3])
+        e.close()
+
+
+def test_blow_up_is_reported_not_crashed(Engine):
+    """Two overlapping atoms and an absurd time step: the engine must return an error (non-finite
+    coordinates) and leave the device usable -- the reference panics on CUDA errors
+    (src/reflection.rs:200); a library must not."""
+    from molchanica_b200.engine import McError
+    w = W.lj_fluid(m=8)
+    w["xyzq"][1, :3] = w["xyzq"][0, :3] + np.float32(1e-4)
+    e = Engine.from_workload(w)
+    with pytest.raises(McError):
+        for _ in range(50):
+            e.step(0.5, 10)
+    e.close()
+    e2 = Engine.from_workload(W.lj_fluid(m=8))  # the context survived
+    e2.step(0.002, 5)
+    assert np.isfinite(e2.positions()).all()
+    e2.close()
