@@ -117,6 +117,8 @@ def main():
     ap.add_argument("--cpu-side", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiler runs)")
+    ap.add_argument("--no-profile", action="store_true", help="experiment: no CUDA events around the kernels")
+    ap.add_argument("--profile-every", type=int, default=8)
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     args = ap.parse_args()
@@ -180,7 +182,8 @@ def main():
 
     # ---- value: device-resident, CUDA events on the engine's stream around all K steps ----------
     e.step(DT_PS, W_)
-    e.set_option("profiling", 1)
+    e.set_option("profiling", 0 if args.no_profile else 1)
+    e.set_option("profile_every", args.profile_every)  # CUDA-event pairs around every k-th step's kernels only
     e.reset_timers()
     s0 = e.stats()
     sampler = ClockSampler(local)
@@ -207,18 +210,36 @@ def main():
     # positions (what the viewer reads back, reference src/md/mod.rs:843-852) into pinned memory.
     e2e = None
     if not args.no_e2e:
+        # per step: mc_step(dt, 1, ext) with the step's external forces in pinned HOST memory (H2D inside), then
+        # mc_snapshot_begin hands the new positions to a pinned HOST buffer (D2H inside, double-buffered so that
+        # the copy of step s overlaps the kernels of step s+1 -- the Snapshot queue of the reference,
+        # src/md/mod.rs:118-152); mc_snapshot_wait(s-1) before buffer reuse, all copies drained before the clock stops.
+        # A decomposed rank moves its own share: the full ext-force array in, its owned atoms + ids out.
+        cap = n if world == 1 else int(3 * (n // world + n // (2 * world) + 4096))
         ext = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
-        pos = torch.empty((n, 4), dtype=torch.float32).pin_memory()
-        ext_p, pos_p = C.c_void_p(ext.data_ptr()), C.c_void_p(pos.data_ptr())
-        for _ in range(3):
+        pos = [torch.empty((cap, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+        ids = [torch.empty((cap,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        ext_p = C.c_void_p(ext.data_ptr())
+        n_out = C.c_int64(0)
+        d2h = 0
+
+        def one(k):
+            nonlocal d2h
             e.step_raw(DT_PS, 1, ext_p)
-            e.get_positions_into(pos_p)
-        ke = min(K, 200)
+            e._chk(e._L.mc_snapshot_begin(e._h, C.c_void_p(pos[k & 1].data_ptr()),
+                                          C.c_void_p(ids[k & 1].data_ptr()) if world > 1 else None, C.byref(n_out)))
+            d2h = int(n_out.value) * (16 + (4 if world > 1 else 0))
+            if k > 0:
+                e._chk(e._L.mc_snapshot_wait(e._h))
+        for k in range(4):
+            one(k)
+        e._chk(e._L.mc_snapshot_wait(e._h))
+        ke = min(K, 300)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(ke):
-            e.step_raw(DT_PS, 1, ext_p)
-            e.get_positions_into(pos_p)
+        for k in range(ke):
+            one(k)
+        e._chk(e._L.mc_snapshot_wait(e._h))
         barrier()
         te = time.perf_counter() - t0
         if world > 1:
@@ -226,8 +247,9 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             te = float(tt.item())
         e2e = {"value": ns_per_day(ke, te), "unit": UNIT, "h2d_bytes_per_step": int(ext.numel() * 4),
-               "d2h_bytes_per_step": int(pos.numel() * 4), "steps": ke, "ms_per_step": te / ke * 1e3,
-               "api": "mc_step(ctx, dt, 1, ext_forces) + mc_get_positions(ctx, out), pinned host buffers"}
+               "d2h_bytes_per_step": d2h, "steps": ke, "ms_per_step": te / ke * 1e3,
+               "api": "mc_step(ctx, dt, 1, ext_forces) + mc_snapshot_begin(ctx, out, ids) / mc_snapshot_wait(ctx), pinned host "
+                      "buffers; bytes are per rank"}
 
     # ---- roofline of the dominant kernel (pair force), live CUDA-event average over the timed region
     pair_ms = (s1["pair_ms_sum"] - 0.0) / max(s1["pair_launches_timed"], 1)
@@ -244,14 +266,29 @@ def main():
                 "traffic": traffic, "kernel": "pair_force_kernel", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": pair_ms,
                 "launches_timed": s1["pair_launches_timed"],
-                "share_of_step": pair_ms * s1["pair_launches_timed"] / ms if ms > 0 else None,
-                "build_ms_avg": s1["build_ms_sum"] / max(s1["builds_timed"], 1),
+                "launches_in_timed_region": K, "share_of_step": pair_ms * K / ms if ms > 0 else None,
+                "rebuild_ms_avg": s1["build_ms_sum"] / max(s1["n_rebuilds"] - s0["n_rebuilds"], 1),
                 "integrate_ms_avg": s1["integrate_ms_sum"] / max(s1["integrate_launches_timed"], 1),
                 "halo_ms_avg": s1["halo_ms_sum"] / max(s1["halos_timed"], 1) if world > 1 else None,
                 "rank0_atoms_owned": int(s1["n_atoms"]), "rank0_ghosts": int(s1["n_ghosts"]),
+
                 "list_violations": int(s1["n_list_violations"])}
 
     cpu = None
+    per_rank = None
+    if world > 1:
+        # what every rank measured (CUDA events on its own stream): in the fused halo the waits for the
+        # neighbours sit inside kick_drift (ack) and the boundary rows' pair kernel (ready)
+        k_int, frac = e.schedule()
+        mine = torch.tensor([pair_ms, roofline["integrate_ms_avg"], roofline["rebuild_ms_avg"], float(s1["n_atoms"]),
+                             float(k_int), frac], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu().numpy()
+        per_rank = {"pair_ms": [round(float(v), 5) for v in allr[:, 0]], "integrate_ms": [round(float(v), 5) for v in allr[:, 1]],
+                    "rebuild_ms": [round(float(v), 4) for v in allr[:, 2]], "atoms": [int(v) for v in allr[:, 3]],
+                    "rebuild_interval": int(allr[0, 4]), "last_disp_over_half_skin": round(float(allr[0, 5]), 3)}
+    roofline["per_rank"] = per_rank
     if rank == 0 and world == 1 and not args.no_cpu:
         cb = cpu_arm(args.cpu_side, 100, 5)
         cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -266,6 +303,8 @@ def main():
                            "atoms": n, "l2_policy": "inputs larger than L2: list+positions = "
                                                     f"{(4 * p_full + 16 * n) / 1e6:.0f} MB per step vs 126 MB L2",
                            "parallelism": f"slab-dd{world}" if world > 1 else "single-gpu",
+                           "halo": (("fused peer-memory push in kick_drift + flag wait in the pair kernel" if e.halo_mode()[0]
+                                     else "nccl send/recv (" + e.halo_mode()[1] + ")") if world > 1 else None),
                            "pair_lanes": args.lanes or 8},
                 "e2e": e2e, "gpu_launches": int(s1["n_kernel_launches"] - s0["n_kernel_launches"]),
                 "rebuilds_in_timed_region": int(s1["n_rebuilds"] - s0["n_rebuilds"]),

@@ -121,7 +121,11 @@ int mc_set_overrides(mc_ctx *ctx, int lj_disabled, int coulomb_disabled);
 
 /* Tuning / instrumentation knobs: "pair_lanes" (4, 8, 16, 32 lanes per list row),
  * "profiling" (0/1: bracket the hot kernels with CUDA events), "rebuild_every" (0 = rebuild on
- * the displacement criterion, k > 0 = every k steps like GROMACS nstlist). */
+ * the displacement criterion, k > 0 = every k steps like GROMACS nstlist), "halo_fused" (decomposed
+ * handles; 1 = peer-memory ghost exchange inside the step kernels (default), 0 = NCCL send / recv),
+ * "dd_migrate" (decomposed handles; 1 = rebuilds exchange boundary layers with the two neighbour ranks only
+ * (default), 0 = all-gather of the whole system), "subcell_sort" (Morton sub-cell code in the sort key),
+ * "profile_every" (k: inside mc_step only every k-th step's kernels are bracketed with events). */
 int mc_set_option(mc_ctx *ctx, const char *name, double value);
 
 /* Replace positions (and optionally velocities) of the existing atoms, original order. */
@@ -153,6 +157,16 @@ int mc_get_velocities(mc_ctx *ctx, mc_float4 *out);
 int mc_get_forces(mc_ctx *ctx, mc_float4 *out);
 int mc_get_energy(mc_ctx *ctx, mc_energy *out);
 int mc_get_stats(mc_ctx *ctx, mc_stats *out);
+
+/* Asynchronous snapshot hand-off (the Snapshot queue of src/md/mod.rs:118-152): mc_snapshot_begin
+ * stages the current positions on the device and starts their copy to `out_positions` on a second
+ * stream, then returns; the caller may issue further mc_step calls at once.  mc_snapshot_wait blocks
+ * until the OLDEST outstanding snapshot has landed (at most two may be in flight; host buffers should
+ * be page-locked for the copy to overlap).  Single GPU: n_global entries in original order, out_ids
+ * may be NULL.  Decomposed handle: the atoms this rank owns, *n_out of them, with their original
+ * ids in out_ids (both buffers must hold the rank's capacity, see mc_comm_counts). */
+int mc_snapshot_begin(mc_ctx *ctx, mc_float4 *out_positions, int32_t *out_ids, int64_t *n_out);
+int mc_snapshot_wait(mc_ctx *ctx);
 
 /* Verlet list as CSR in original ids, rows ascending.  start: n+1 entries.  Two-call protocol:
  * idx == NULL or cap too small -> start[] is still filled, *total set, MC_E_CAPACITY returned
@@ -192,6 +206,19 @@ int mc_comm_init(mc_ctx *ctx, const uint8_t id[128], int rank, int n_ranks);
  * global cell grid, kz0, kz1 owned z layers [kz0, kz1), ghost layer from prev, ghost layer from
  * next, next rank}.  r_list = max(rc_lj, rc_q) + skin. */
 int mc_dd_plan(const float box_ext[3], float r_list, int rank, int n_ranks, int32_t out[8]);
+/* How the per-step ghost refresh runs: *fused = 1 when the neighbours' position arrays are mapped into
+ * this process (cudaIpc over NVLink) and the step kernels exchange ghosts themselves -- kick_drift
+ * stores its boundary layers into the neighbours' ghost blocks and raises their flags, the pair
+ * kernel of the boundary rows waits on them; 0 = ncclSend / ncclRecv between the two kernels (option
+ * "halo_fused" = 0, or the mapping failed: `why` then holds the reason).  Valid after the first build. */
+int mc_comm_halo_mode(mc_ctx *ctx, int *fused, char *why, int why_cap);
+/* Rebuild schedule of a decomposed run.  Every rank must rebuild at the same step, so the decision cannot
+ * be the local displacement flag: option "rebuild_every" = k > 0 fixes the interval; 0 (default) adapts
+ * it at every build from the largest displacement any rank saw in the interval that just ended (the
+ * number travels with the build's all-gathered layout table, so all ranks derive the same interval), aiming
+ * at 85 % of skin/2.  *interval = steps between builds now in force, *last_disp_frac = that largest
+ * displacement / (skin/2); mc_stats.n_list_violations counts intervals that overshot. */
+int mc_comm_schedule(mc_ctx *ctx, int *interval, double *last_disp_frac);
 /* Number of atoms this rank currently owns / holds as ghosts. */
 int mc_comm_counts(mc_ctx *ctx, int64_t *n_owned, int64_t *n_ghost);
 /* Gather global arrays (original ids, length n_global) -- valid on every rank. */

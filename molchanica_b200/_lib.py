@@ -12,7 +12,8 @@ import re
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmolchanica_md.so")
+# MOLCHANICA_MD_LIB points the harness at another build of the same library (A/B kernel experiments)
+LIB_PATH = os.environ.get("MOLCHANICA_MD_LIB") or os.path.join(_HERE, "libmolchanica_md.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "molchanica_md.h")
 
 MC_OK = 0
@@ -105,5 +106,9 @@ def lib():
     L.mc_comm_init.argtypes = [vp, vp, i32, i32]
     L.mc_comm_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.mc_dd_plan.argtypes = [vp, f32, i32, i32, vp]
+    L.mc_snapshot_begin.argtypes = [vp, vp, vp, C.POINTER(i64)]
+    L.mc_snapshot_wait.argtypes = [vp]
+    L.mc_comm_schedule.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_double)]
+    L.mc_comm_halo_mode.argtypes = [vp, C.POINTER(i32), C.c_char_p, i32]
     _LIB = L
     return L

@@ -29,7 +29,20 @@ struct GridParams {
     int kz_off;        // global z layer of local layer 0
     int ncz_global;    // global number of z layers (== nc[2] unless decomposed)
     int row_l0, row_l1;  // local z layers [row_l0, row_l1) carry list rows (the others are ghost layers)
+    int sub_bits;      // low bits of the sort key: Morton code of the atom's sub-cell (4 x 4 x 4 per cell), so that
+                       // atoms that are close in space are close in memory and a row's gathers share cache lines
 };
+
+#define MC_SUB_BITS 6
+
+// Morton code (2 bits per axis) of the fractional position f in [0,1)^3 inside a cell.
+__host__ __device__ inline uint32_t mc_subcell_code(float fx, float fy, float fz) {
+    const int sx = fx < 0.f ? 0 : (fx >= 1.f ? 3 : (int)(fx * 4.f));
+    const int sy = fy < 0.f ? 0 : (fy >= 1.f ? 3 : (int)(fy * 4.f));
+    const int sz = fz < 0.f ? 0 : (fz >= 1.f ? 3 : (int)(fz * 4.f));
+    auto part = [](int v) { return (uint32_t)(((v & 2) << 2) | (v & 1)); };
+    return part(sx) | (part(sy) << 1) | (part(sz) << 2);
+}
 
 // Nonbonded parameters passed by value to the pair kernels.
 struct NbParams {

@@ -111,6 +111,11 @@ extern "C" int mc_destroy(mc_ctx *c) {
         cudaEventDestroy(c->ev_step_a); cudaEventDestroy(c->ev_step_b);
         cudaEventDestroy(c->ev_flag[0]); cudaEventDestroy(c->ev_flag[1]);
     }
+    if (c->st_copy) {
+        cudaStreamSynchronize(c->st_copy);
+        for (int b = 0; b < 2; ++b) { cudaEventDestroy(c->ev_snap_staged[b]); cudaEventDestroy(c->ev_snap_done[b]); }
+        cudaStreamDestroy(c->st_copy);
+    }
     c->free_all();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaStreamDestroy(c->st);
@@ -321,6 +326,17 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         c->use_tile = value != 0.0;
     } else if (k == "profiling") {
         c->profiling = value != 0.0;
+    } else if (k == "profile_every") {
+        c->prof_every = std::max(1, (int)value);
+    } else if (k == "subcell_sort") {
+        c->subcell_sort = value != 0.0;
+        c->grid_dirty = true;
+        c->list_valid = false;
+    } else if (k == "dd_migrate") {
+        MC_REQUIRE(c, c->comm != nullptr, "mc_set_option: dd_migrate needs a communicator");
+        comm_set_migrate(c, value != 0.0);
+    } else if (k == "halo_fused") {
+        c->halo_fused = value != 0.0;
     } else if (k == "rebuild_every") {
         c->rebuild_every = (int)value;
     } else {
@@ -361,6 +377,7 @@ static int setup_grid(mc_ctx *c) {
         g.ncz_global = g.nc[2];
         g.row_l0 = 0;
         g.row_l1 = g.nc[2];
+        g.sub_bits = (c->subcell_sort && ncell <= (1ll << (32 - MC_SUB_BITS - 1))) ? MC_SUB_BITS : 0;
         c->ncell_cap = (size_t)ncell;
         c->h_grid = g;
         MC_CUDA(c, cudaMemcpyAsync(c->grid.p, &c->h_grid, sizeof(GridParams), cudaMemcpyHostToDevice, c->st));
@@ -372,7 +389,7 @@ static int setup_grid(mc_ctx *c) {
     MC_CUDA(c, c->cell_start.ensure(c->ncell_cap + 2));
     int bits = 1;
     while (((size_t)1 << bits) < c->ncell_cap) ++bits;
-    c->key_bits = bits;
+    c->key_bits = bits + (c->periodic ? c->h_grid.sub_bits : MC_SUB_BITS);
     c->grid_dirty = false;
     return MC_OK;
 }
@@ -510,7 +527,7 @@ static NbParams make_params(const mc_ctx *c) {
     return p;
 }
 
-int engine_launch_forces(mc_ctx *c, bool want_energy) {
+int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs) {
     PairLaunch L;
     L.n_rows = (int)c->n_rows_sorted();
     L.row0 = (int)c->row0;
@@ -527,8 +544,15 @@ int engine_launch_forces(mc_ctx *c, bool want_energy) {
     L.multi = c->n_types > 1;
     L.lanes = c->pair_lanes;
     L.force = c->force.p;
-    {
-        TimedRegion tr(c, c->pair_acc);
+    if (hs) {
+        TimedRegion tr(c, c->pair_acc, true);
+        L.n_interior = hs->last_begin - hs->n_first;
+        L.n_first = hs->n_first;
+        L.wait = hs->wait;
+        launch_pair_force(L, c->st, &c->launches);
+        tr.stop();
+    } else {
+        TimedRegion tr(c, c->pair_acc, true);
         launch_pair_force(L, c->st, &c->launches);
         tr.stop();
     }
@@ -555,6 +579,7 @@ static int ensure_ready(mc_ctx *c, const char *who) {
 extern "C" int mc_compute_forces(mc_ctx *c) {
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);
+    c->prof_now = true;
     int rc = ensure_ready(c, "mc_compute_forces");
     if (rc != MC_OK) return rc;
     if (c->comm_active && (rc = comm_halo_positions(c)) != MC_OK) return rc;
@@ -566,10 +591,23 @@ extern "C" int mc_compute_forces(mc_ctx *c) {
 
 // ---- velocity Verlet -----------------------------------------------------------------------------------
 
+// Spin on a pinned host word until kick_drift's last block has published the expected step tag.
+static int wait_flag_tag(mc_ctx *c, volatile int *word, int tag) {
+    for (long spins = 0;; ++spins) {
+        if ((*word >> 2) == tag) return MC_OK;
+        if ((spins & 0xfffff) == 0xfffff) {  // every ~1M polls: has the stream died?
+            cudaError_t e = cudaStreamQuery(c->st);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return fail(c, MC_E_CUDA, std::string("mc_step: ") + cudaGetErrorString(e));
+            if (e == cudaSuccess && (*word >> 2) != tag) return fail(c, MC_E_CUDA, "mc_step: rebuild flag never published");
+        }
+    }
+}
+
 extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces) {
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);
     MC_REQUIRE(c, n_steps >= 0 && dt > 0.f, "mc_step: n_steps >= 0 and dt > 0 required");
+    c->prof_now = true;
     int rc = ensure_ready(c, "mc_step");
     if (rc != MC_OK) return rc;
     cudaStream_t st = c->st;
@@ -589,9 +627,12 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     // flag travels to pinned host memory asynchronously, and the host acts on the flag of the
     // PREVIOUS step while the GPU is already busy -- no per-step stream synchronisation.
     const float max_disp = 0.5f * c->skin;
-    if (c->comm_active && c->rebuild_every <= 0) c->rebuild_every = 20;  // decomposed runs rebuild on a fixed schedule
+    // decomposed runs rebuild on a schedule every rank derives from the same numbers (no per-step agreement)
     const bool pipelined = !c->comm_active && c->rebuild_every <= 0 && !c->sync_rebuild;
-    const float lookahead = pipelined ? 2.5f : 0.f;
+    // the host acts on the flag of step s-1 before the pair kernel of step s: the stale list is last used one
+    // drift after the flag could first have been raised, so one drift of margin is needed; 1.5 leaves room
+    // for the change of velocity within that step
+    const float lookahead = pipelined ? 1.5f : 0.f;
     int *h_flag = reinterpret_cast<int *>(c->h_pinned) + 8;  // two slots
     if (!c->ev_step_a) {
         MC_CUDA(c, cudaEventCreate(&c->ev_step_a)); MC_CUDA(c, cudaEventCreate(&c->ev_step_b));
@@ -600,24 +641,41 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     }
     MC_CUDA(c, cudaEventRecord(c->ev_step_a, st));
     bool have_prev = false, skip_prev = false;
+    int tag[2] = {0, 0};
+    const bool fused_halo = c->comm_active && comm_peer_direct(c) && c->halo_fused;
     for (int s = 0; s < n_steps; ++s) {
+        HaloSplit split{};
+        c->prof_now = c->prof_every <= 1 || (s % c->prof_every) == 0;
         {
-            TimedRegion tr(c, c->integ_acc);
+            TimedRegion tr(c, c->integ_acc, true);
             const size_t r0 = (size_t)c->row0;
-            launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, d_ext,
-                              c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, s == 0 ? 0.5f * dt : dt, dt,
-                              max_disp, lookahead, c->rebuild_flag.p, st, &c->launches);
+            if (fused_halo) {
+                HaloPush push{};
+                comm_step_descriptors(c, c->steps_since_build + 1 >= comm_interval(c), &push, &split);
+                launch_kick_drift_halo((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0,
+                                       d_ext, c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0,
+                                       s == 0 ? 0.5f * dt : dt, dt, max_disp, c->rebuild_flag.p, push, st, &c->launches);
+            } else {
+                if (pipelined) tag[s & 1] = (++c->flag_tag) & 0x1fffffff;
+                launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, d_ext,
+                                  c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, s == 0 ? 0.5f * dt : dt, dt,
+                                  max_disp, lookahead, c->rebuild_flag.p, st, &c->launches,
+                                  pipelined ? reinterpret_cast<uint32_t *>(c->rebuild_flag.p + 2) : nullptr,
+                                  pipelined ? h_flag + (s & 1) : nullptr, tag[s & 1]);
+            }
             tr.stop();
         }
         c->steps_since_build++;
         bool rebuild = false;
-        if (c->rebuild_every > 0) {
+        if (c->comm_active) {
+            rebuild = c->steps_since_build >= comm_interval(c);
+        } else if (c->rebuild_every > 0) {
             rebuild = c->steps_since_build >= c->rebuild_every;
         } else if (pipelined) {
-            MC_CUDA(c, cudaMemcpyAsync(h_flag + (s & 1), c->rebuild_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            MC_CUDA(c, cudaEventRecord(c->ev_flag[s & 1], st));
+            // kick_drift publishes {tag, flag} into pinned host memory itself; nothing is queued between it and the
+            // pair kernel.  The word of the PREVIOUS step was written one pair kernel ago.
             if (have_prev && !skip_prev) {
-                MC_CUDA(c, cudaEventSynchronize(c->ev_flag[(s - 1) & 1]));  // completed one kernel ago
+                if ((rc = wait_flag_tag(c, h_flag + ((s - 1) & 1), tag[(s - 1) & 1])) != MC_OK) return rc;
                 rebuild = (h_flag[(s - 1) & 1] & 1) != 0;
                 if (h_flag[(s - 1) & 1] & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
             }
@@ -633,10 +691,10 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         if (rebuild) {
             rc = c->comm_active ? comm_rebuild(c) : engine_build_list(c);
             if (rc != MC_OK) return rc;
-        } else if (c->comm_active && (rc = comm_halo_positions(c)) != MC_OK) {
+        } else if (c->comm_active && !fused_halo && (rc = comm_halo_positions(c)) != MC_OK) {
             return rc;
         }
-        if ((rc = engine_launch_forces(c, false)) != MC_OK) return rc;
+        if ((rc = engine_launch_forces(c, false, fused_halo && !rebuild ? &split : nullptr)) != MC_OK) return rc;
         c->n_steps++;
     }
     if (n_steps > 0) {
@@ -647,6 +705,7 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
                           c->rebuild_flag.p, st, &c->launches);
         tr.stop();
     }
+    c->prof_now = true;
     MC_CUDA(c, cudaEventRecord(c->ev_step_b, st));
     MC_CUDA(c, cudaGetLastError());
     MC_CUDA(c, cudaStreamSynchronize(st));
@@ -654,15 +713,19 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     MC_CUDA(c, cudaEventElapsedTime(&ms, c->ev_step_a, c->ev_step_b));
     c->last_step_ms = ms;
     // the flag of the last drift has not been acted upon: make the next evaluation rebuild first
-    if (pipelined && n_steps > 0 && !skip_prev && h_flag[(n_steps - 1) & 1] != 0) c->list_valid = false;
+    if (pipelined && n_steps > 0 && !skip_prev && (h_flag[(n_steps - 1) & 1] & 3) != 0) c->list_valid = false;
     if (pipelined && n_steps > 0 && (h_flag[(n_steps - 1) & 1] & 2))
         return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
-    if (c->rebuild_every > 0 && n_steps > 0) {
+    if ((c->rebuild_every > 0 || c->comm_active) && n_steps > 0) {
         // fixed schedule: the displacement flag is only a safety net -- an atom that moved more than skin/2
         // between two builds means rebuild_every is too large for this system
-        MC_CUDA(c, cudaMemcpy(h_flag, c->rebuild_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+        MC_CUDA(c, cudaMemcpy(h_flag, c->rebuild_flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+        if (h_flag[1] & MC_HALO_ERR_TIMEOUT)
+            return fail(c, MC_E_COMM, "mc_step: a neighbour rank did not signal its halo push within 2 s (peer died or ranks out of step)");
         if (*h_flag & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
-        if (*h_flag != 0) { c->n_list_violations++; c->list_valid = false; }
+        // a decomposed rank only reports the violation: invalidating the list on one rank alone would
+        // make it enter the collective rebuild on its own
+        if (*h_flag != 0) { c->n_list_violations++; if (!c->comm_active) c->list_valid = false; }
     }
     c->collect_timings();
     return MC_OK;
@@ -701,6 +764,65 @@ extern "C" int mc_get_forces(mc_ctx *c, mc_float4 *out) {
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->forces_valid, "mc_get_forces: no force evaluation since the last change; call mc_compute_forces");
     return read_sorted_to_orig(c, c->force.p, out);
+}
+
+// ---- asynchronous snapshot hand-off --------------------------------------------------
+// The reference queues Snapshot{atom_posits, ...} objects while the integrator keeps going
+// (src/md/mod.rs:118-152 flush_snapshot_queues, md/trajectory.rs:160-204).  Here: the positions are
+// copied into one of two device staging buffers on the compute stream (a gather into original order on
+// a single GPU; the owned block + its original ids on a decomposed rank), and a second stream moves
+// the staging buffer to the caller's host buffer while the next steps already run.
+
+extern "C" int mc_snapshot_begin(mc_ctx *c, mc_float4 *out_positions, int32_t *out_ids, int64_t *n_out) {
+    if (!c || !out_positions) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, !c->comm_active || out_ids, "mc_snapshot_begin: a decomposed handle returns its owned atoms and needs out_ids");
+    if (!c->st_copy) {
+        MC_CUDA(c, cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_snap_staged[b], cudaEventDisableTiming));
+            MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_snap_done[b], cudaEventDisableTiming));
+        }
+    }
+    const int k = c->snap_k;
+    c->snap_k ^= 1;
+    const int64_t rows = c->n_rows_sorted();
+    const int64_t n = c->comm_active ? rows : c->n_global;
+    if (n_out) *n_out = n;
+    if (n == 0) return MC_OK;
+    // the copy that last used this staging buffer must have drained before it is overwritten
+    if (c->snap_pending[k]) MC_CUDA(c, cudaStreamWaitEvent(c->st, c->ev_snap_done[k], 0));
+    MC_CUDA(c, c->snap_stage[k].ensure((size_t)n));
+    if (c->comm_active) {
+        MC_CUDA(c, c->snap_ids[k].ensure((size_t)n));
+        MC_CUDA(c, cudaMemcpyAsync(c->snap_stage[k].p, c->xyzq[c->cur].p + c->row0, sizeof(float4) * n, cudaMemcpyDeviceToDevice, c->st));
+        MC_CUDA(c, cudaMemcpyAsync(c->snap_ids[k].p, c->orig[c->cur].p + c->row0, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->st));
+    } else {
+        launch_gather_to_orig((int)rows, c->xyzq[c->cur].p, c->orig[c->cur].p, c->snap_stage[k].p, c->st, &c->launches);
+    }
+    MC_CUDA(c, cudaEventRecord(c->ev_snap_staged[k], c->st));
+    MC_CUDA(c, cudaStreamWaitEvent(c->st_copy, c->ev_snap_staged[k], 0));
+    MC_CUDA(c, cudaMemcpyAsync(out_positions, c->snap_stage[k].p, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->st_copy));
+    if (c->comm_active) MC_CUDA(c, cudaMemcpyAsync(out_ids, c->snap_ids[k].p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->st_copy));
+    MC_CUDA(c, cudaEventRecord(c->ev_snap_done[k], c->st_copy));
+    c->snap_pending[k] = true;
+    return MC_OK;
+}
+
+extern "C" int mc_snapshot_wait(mc_ctx *c) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    if (!c->st_copy) return MC_OK;
+    // the oldest outstanding snapshot is the one in the buffer the next begin would use
+    for (int t = 0; t < 2; ++t) {
+        const int k = c->snap_k ^ t;
+        if (c->snap_pending[k]) {
+            MC_CUDA(c, cudaEventSynchronize(c->ev_snap_done[k]));
+            c->snap_pending[k] = false;
+            return MC_OK;
+        }
+    }
+    return MC_OK;
 }
 
 extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
@@ -796,6 +918,7 @@ extern "C" int mc_time_kernels(mc_ctx *c, int reps, int flush_l2) {
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);
     MC_REQUIRE(c, reps > 0, "mc_time_kernels: reps > 0 required");
+    c->prof_now = true;
     int rc = ensure_ready(c, "mc_time_kernels");
     if (rc != MC_OK) return rc;
     const bool prof = c->profiling;

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "halo_sync.cuh"
 
 template <typename T>
 struct DevBuf {
@@ -75,6 +76,9 @@ struct mc_ctx {
     int rebuild_every = 0;
     int steps_since_build = 0;
     bool profiling = false;
+    int prof_every = 1;     // option "profile_every": inside mc_step only every k-th step's kernels are bracketed
+    bool prof_now = true;   // (event pairs between back-to-back kernels cost ~10 us per step on a 0.2 ms step)
+    bool subcell_sort = false;  // Morton sub-cell code in the low sort-key bits (option "subcell_sort")
     bool use_tile = true;      // TMA-staged tile sweep for the list build (neighbor_tile.cu)
     uint32_t tile_cap = 1024;  // tile capacity in atoms, grows on demand
 
@@ -84,6 +88,7 @@ struct mc_ctx {
     TimeAcc pair_acc, build_acc, integ_acc, halo_acc, dock_acc;
     double last_pair_ms = 0, last_dock_ms = 0, last_step_ms = 0;
     cudaEvent_t ev_step_a = nullptr, ev_step_b = nullptr, ev_flag[2] = {nullptr, nullptr};
+    int flag_tag = 0;           // tag of the last published rebuild-flag word (kick_drift -> pinned host memory)
     bool sync_rebuild = false;  // poll the displacement flag synchronously every step (debug / comparison)
 
     // device arrays
@@ -101,6 +106,14 @@ struct mc_ctx {
     DevBuf<float4> d_rec, d_lig;
     DevBuf<uint32_t> d_rec_meta, d_lig_meta;
 
+    // asynchronous snapshots (mc_snapshot_begin / mc_snapshot_wait): double-buffered staging + a copy stream
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_snap_staged[2] = {nullptr, nullptr}, ev_snap_done[2] = {nullptr, nullptr};
+    DevBuf<float4> snap_stage[2];
+    DevBuf<int> snap_ids[2];
+    int snap_k = 0;
+    bool snap_pending[2] = {false, false};
+
     // event timing
     std::vector<EventPair> ev_pool;
     struct Pending { int ev; TimeAcc *acc; };
@@ -109,6 +122,7 @@ struct mc_ctx {
 
     // domain decomposition
     bool comm_active = false;
+    bool halo_fused = true;  // option "halo_fused": peer-memory halo inside the step kernels (else NCCL send / recv)
     CommState *comm = nullptr;
 
     int64_t n_rows_sorted() const { return n_rows; }
@@ -141,6 +155,7 @@ struct mc_ctx {
         ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); d_poses.release(); d_scores.release();
         grid.release(); red_partial.release(); red_out.release(); d_rec.release(); d_lig.release();
         d_rec_meta.release(); d_lig_meta.release();
+        for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_ids[b].release(); }
     }
 
     // resolve the CUDA-event pairs recorded since the last call (stream must be idle)
@@ -162,8 +177,8 @@ struct TimedRegion {
     mc_ctx *c;
     TimeAcc &acc;
     int ev = -1;
-    TimedRegion(mc_ctx *c_, TimeAcc &a) : c(c_), acc(a) {
-        if (!c->profiling || c->ev_used >= 8192) return;
+    TimedRegion(mc_ctx *c_, TimeAcc &a, bool sampled = false) : c(c_), acc(a) {
+        if (!c->profiling || c->ev_used >= 8192 || (sampled && !c->prof_now)) return;
         if (c->ev_used >= c->ev_pool.size()) {
             EventPair p;
             if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
@@ -184,7 +199,10 @@ struct TimedRegion {
 // engine.cu
 int engine_build_list(mc_ctx *c);
 int engine_build_rows(mc_ctx *c);
-int engine_launch_forces(mc_ctx *c, bool want_energy);
+// hs != nullptr: decomposed step with the peer-memory halo -- interior rows first, then the rows of the
+// first and last owned layer in one launch that waits for the neighbours' pushes
+struct HaloSplit { int n_first, last_begin; HaloWait wait; };
+int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs = nullptr);
 int engine_upload_local(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type, const mc_float4 *vel,
                         const uint8_t *flags, const int *orig_ids, size_t alloc_n);
 
@@ -192,7 +210,13 @@ int engine_upload_local(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint1
 int comm_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *type, const mc_float4 *vel,
                    const uint8_t *flags);
 int comm_rebuild(mc_ctx *c);          // migrate + re-select ghosts + engine_build_list
-int comm_halo_positions(mc_ctx *c);   // per-step ghost position refresh
+int comm_halo_positions(mc_ctx *c);   // per-step ghost position refresh (NCCL send / recv)
+bool comm_peer_direct(const mc_ctx *c);
+void comm_set_migrate(mc_ctx *c, bool on);
+int comm_interval(const mc_ctx *c);  // steps between two builds of a decomposed run  // the fused peer-memory halo is usable on this communicator
+// one decomposed step with the fused halo: advances the epoch and fills the push descriptor of this
+// step's kick_drift (no push when the step ends in a rebuild) and the wait descriptor of its pair kernels
+void comm_step_descriptors(mc_ctx *c, bool rebuild_step, HaloPush *push, HaloSplit *split);
 int comm_agree_flag(mc_ctx *c, bool *flag);
 int comm_allreduce3(mc_ctx *c, double v[3]);
 int comm_allreduce_f4(mc_ctx *c, float4 *buf, int64_t n);  // in-place sum over ranks

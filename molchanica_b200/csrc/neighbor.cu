@@ -98,6 +98,7 @@ __global__ void grid_from_bbox_kernel(const float *__restrict__ bb, float cw_min
     g->ncz_global = nc[2];
     g->row_l0 = 0;
     g->row_l1 = nc[2];
+    g->sub_bits = MC_SUB_BITS;  // max_cells <= 2^22: the key stays within 32 bits
 }
 
 // ---- wrap + cell key --------------------------------------------------------------------------
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) wrap_key_kernel(float4 *__restrict__ xyzq
     const GridParams g = *gp;
     float4 p = xyzq[i];
     float c[3] = {p.x, p.y, p.z};
+    float fr[3];
     int k[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -118,11 +120,14 @@ __global__ void __launch_bounds__(256) wrap_key_kernel(float4 *__restrict__ xyzq
             if (c[a] < g.lo[a]) c[a] += g.ext[a];
             if (c[a] >= g.lo[a] + g.ext[a]) c[a] -= g.ext[a];
         }
-        int kk = (int)floorf((c[a] - g.lo[a]) * g.inv_cw[a]);
+        const float u = (c[a] - g.lo[a]) * g.inv_cw[a];
+        int kk = (int)floorf(u);
         k[a] = min(max(kk, 0), g.nc[a] - 1);
+        fr[a] = u - (float)k[a];
     }
     if (g.periodic) xyzq[i] = make_float4(c[0], c[1], c[2], p.w);
-    keys[i] = (uint32_t)((k[2] * g.nc[1] + k[1]) * g.nc[0] + k[0]);
+    const uint32_t cell = (uint32_t)((k[2] * g.nc[1] + k[1]) * g.nc[0] + k[0]);
+    keys[i] = g.sub_bits ? (cell << MC_SUB_BITS) | mc_subcell_code(fr[0], fr[1], fr[2]) : cell;
     vals[i] = (uint32_t)i;
 }
 
@@ -132,10 +137,10 @@ __global__ void __launch_bounds__(256) reorder_kernel(int n, const uint32_t *__r
                                                        const GridParams *__restrict__ gp, ReorderArrays a) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > n) return;
-    const int ncell = gp->ncell;
-    // cell_start[c] = first sorted slot whose key >= c  (boundary detection on the sorted keys)
-    const int prev = k == 0 ? -1 : (int)skeys[k - 1];
-    const int cur = k == n ? ncell : (int)skeys[k];
+    const int ncell = gp->ncell, sb = gp->sub_bits;
+    // cell_start[c] = first sorted slot whose cell >= c  (boundary detection on the sorted keys)
+    const int prev = k == 0 ? -1 : (int)(skeys[k - 1] >> sb);
+    const int cur = k == n ? ncell : (int)(skeys[k] >> sb);
     for (int c = prev + 1; c <= cur; ++c) a.cell_start[c] = (uint32_t)k;
     if (k == n) return;
     const uint32_t src = svals[k];
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(256) sweep_kernel(int n_rows, const float4 *__
     const float4 pi = xyzq[i];
     // the (local) cell of this slot comes from the sorted keys: on a decomposed rank the local z layer
     // is not a function of the coordinate alone
-    const int cell = (int)cell_of_slot[i];
+    const int cell = (int)(cell_of_slot[i] >> g.sub_bits);
     int ci[3] = {cell % g.nc[0], (cell / g.nc[0]) % g.nc[1], cell / (g.nc[0] * g.nc[1])};
     if (ci[2] < g.row_l0 || ci[2] >= g.row_l1) {  // ghost layer: no row
         if (!FILL && lane == 0) nbr_count[i] = 0;

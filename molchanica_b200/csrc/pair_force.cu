@@ -44,7 +44,7 @@ struct Acc { float fx, fy, fz, e; };
 // One listed pair.  WRAP: apply the minimum image (only rows of atoms in boundary cells need it).
 template <int COUL, bool WRAP, bool ENERGY>
 __device__ __forceinline__ void pair_term(const float4 xi, const float4 xj, const float2 lj, const NbParams &p,
-                                          bool lj_on, Acc &a) {
+                                          const float rc2_lj, Acc &a) {
     float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
     if (WRAP) {
         // rintf(d * inv_ext) == rintf(d / ext) except within rounding of |d| = ext/2, where both
@@ -55,14 +55,26 @@ __device__ __forceinline__ void pair_term(const float4 xi, const float4 xj, cons
     }
     // the oracle's fp32 expression, no fma contraction: both sides mask exactly the same pairs
     const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    // branch-free LJ: the arithmetic runs for every listed pair and the cutoff selects the result (one FSEL
+    // instead of a predicated block that re-materialises its constants); lj_on == false arrives as rc2 < 0
+#ifndef MC_LJ_PREDICATED
+    const float ir2 = rcp_approx(r2);
+    const float s2 = lj.x * ir2;
+    const float s6 = s2 * s2 * s2;
+    const bool in_lj = r2 < rc2_lj;
+    float f = in_lj ? lj.y * s6 * __fmaf_rn(2.f, s6, -1.f) * ir2 : 0.f;
+    float e = 0.f;
+    if (ENERGY) e = in_lj ? lj.y * (1.f / 6.f) * s6 * (s6 - 1.f) : 0.f;
+#else
     float f = 0.f, e = 0.f;
-    if (lj_on && r2 < p.rc2_lj) {
+    if (r2 < rc2_lj) {
         const float ir2 = rcp_approx(r2);
         const float s2 = lj.x * ir2;
         const float s6 = s2 * s2 * s2;
         f = lj.y * s6 * __fmaf_rn(2.f, s6, -1.f) * ir2;
         if (ENERGY) e = lj.y * (1.f / 6.f) * s6 * (s6 - 1.f);
     }
+#endif
     if (COUL != MC_COULOMB_NONE) {
         if (r2 < p.rc2_q) {
             const float qq = xi.w * xj.w;
@@ -93,6 +105,7 @@ __device__ __forceinline__ void row_loop(const float4 xi, const uint32_t *__rest
                                          const float4 *__restrict__ xyzq, const uint16_t *__restrict__ type,
                                          const float2 *row, const NbParams &p, bool lj_on, Acc &a) {
     const float2 lj1 = make_float2(p.sig2, p.eps24);
+    const float rc2_lj = lj_on ? p.rc2_lj : -1.f;
     uint32_t k = sub;
     // two gathers in flight per lane
     for (; k + LANES < cnt; k += 2 * LANES) {
@@ -100,15 +113,15 @@ __device__ __forceinline__ void row_loop(const float4 xi, const uint32_t *__rest
         const float4 x0 = __ldg(xyzq + j0), x1 = __ldg(xyzq + j1);
         float2 l0 = lj1, l1 = lj1;
         if (MULTI) { l0 = row[__ldg(type + j0)]; l1 = row[__ldg(type + j1)]; }
-        pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, lj_on, a);
-        pair_term<COUL, WRAP, ENERGY>(xi, x1, l1, p, lj_on, a);
+        pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, rc2_lj, a);
+        pair_term<COUL, WRAP, ENERGY>(xi, x1, l1, p, rc2_lj, a);
     }
     if (k < cnt) {
         const uint32_t j0 = __ldg(lst + k);
         const float4 x0 = __ldg(xyzq + j0);
         float2 l0 = lj1;
         if (MULTI) l0 = row[__ldg(type + j0)];
-        pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, lj_on, a);
+        pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, rc2_lj, a);
     }
 }
 
@@ -187,8 +200,23 @@ __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, int row0, c
                                                           const uint32_t *__restrict__ nbr_count,
                                                           const uint32_t *__restrict__ nbr_list,
                                                           const float2 *__restrict__ ljtab, const NbParams p,
-                                                          const int lj_on, float4 *__restrict__ force) {
+                                                          const int lj_on, float4 *__restrict__ force,
+                                                          const int n_interior, const int n_first, const HaloWait hw) {
     extern __shared__ float2 s_tab[];
+    constexpr int ROWS_PER_BLOCK = 128 / LANES;
+    if (hw.ready_prev && (int)(blockIdx.x + 1) * ROWS_PER_BLOCK > n_interior) {
+        // Decomposed rank, fused halo (halo_sync.cuh): launch rows are ordered interior first, then the first and
+        // the last owned layer, whose rows gather ghosts that the neighbours' kick_drift kernels store over
+        // NVLink.  Blocks of those rows wait for this epoch's ready flags -- by then the interior rows have
+        // covered the latency -- and then drop this SM's L1 (a gpu-scope fence invalidates it): an interior
+        // block may have pulled in a 32-byte sector that a ghost shares with an owned atom before the push landed.
+        if (threadIdx.x == 0) {
+            halo_spin(hw.ready_prev, hw.want, hw.err);
+            halo_spin(hw.ready_next, hw.want, hw.err);
+            __threadfence();
+        }
+        __syncthreads();
+    }
     if (MULTI) {
         for (int t = threadIdx.x; t < p.n_types * p.n_types; t += blockDim.x) s_tab[t] = ljtab[t];
         __syncthreads();
@@ -196,7 +224,8 @@ __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, int row0, c
     const int sub = threadIdx.x % LANES;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const bool live = r < n_rows;
-    const int i = row0 + r;
+    // r < n_interior: interior row n_first + r; then the first layer's rows 0 .. n_first-1; then the last layer's
+    const int i = row0 + (r < n_interior ? r + n_first : (r < n_interior + n_first ? r - n_interior : r));
     Acc a = {0.f, 0.f, 0.f, 0.f};
     if (UNIFORM) {
         // every lane of the warp enters the loop (dead rows with a zero count)
@@ -324,10 +353,12 @@ void launch_lanes(const PairLaunch &L, cudaStream_t st) {
     do {                                                                                                                \
         if (L.uniform)                                                                                                  \
             pair_force_kernel<LANES, M, C, P, E, true><<<blocks, 128, smem, st>>>(                                      \
-                L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on, L.force); \
+                L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on, L.force, \
+                L.n_interior, L.n_first, L.wait); \
         else                                                                                                            \
             pair_force_kernel<LANES, M, C, P, E, false><<<blocks, 128, smem, st>>>(                                     \
-                L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on, L.force); \
+                L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on, L.force, \
+                L.n_interior, L.n_first, L.wait); \
     } while (0)
 #define MC_PF_E(M, C, P) \
     if (L.energy) MC_PF(M, C, P, true); else MC_PF(M, C, P, false)

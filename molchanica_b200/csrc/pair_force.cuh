@@ -1,6 +1,7 @@
 // pair_force.cuh -- host-side launchers of pair_force.cu
 #pragma once
 #include "common.cuh"
+#include "halo_sync.cuh"
 
 struct PairLaunch {
     int n_rows;
@@ -18,6 +19,11 @@ struct PairLaunch {
     bool energy;  // also accumulate the per-atom energy row sum into force.w
     bool uniform; // warp-uniform row loop with warp-wide skin-shell skipping
     float4 *force;
+    // decomposed rank with the fused halo: launch rows run interior rows first (n_interior of them, slots
+    // row0 + n_first ...), then the first owned layer (n_first rows) and the last one; blocks past the
+    // interior rows wait on the neighbours' ready flags.  Defaults = plain order, no wait.
+    int n_interior = 0, n_first = 0;
+    HaloWait wait{};
 };
 
 int pair_force_max_types();

@@ -158,6 +158,15 @@ class MdEngine:
     def velocities(self):
         return self._get4(self._L.mc_get_velocities)
 
+    def snapshot_begin(self, out_positions, out_ids=None):
+        """mc_snapshot_begin into caller-held (ideally pinned) host arrays; returns the entry count."""
+        n_out = C.c_int64(0)
+        self._chk(self._L.mc_snapshot_begin(self._h, _ptr(out_positions), _ptr(out_ids), C.byref(n_out)))
+        return int(n_out.value)
+
+    def snapshot_wait(self):
+        self._chk(self._L.mc_snapshot_wait(self._h))
+
     def forces(self):
         return self._get4(self._L.mc_get_forces)
 
@@ -165,6 +174,19 @@ class MdEngine:
         e = _lib.McEnergy()
         self._chk(self._L.mc_get_energy(self._h, C.byref(e)))
         return {k: getattr(e, k) for k, _ in e._fields_}
+
+    def halo_mode(self):
+        """(fused, why): 1 when the step kernels exchange ghosts over mapped peer memory, else 0 + the reason."""
+        fused = C.c_int32(0)
+        buf = C.create_string_buffer(256)
+        self._chk(self._L.mc_comm_halo_mode(self._h, C.byref(fused), buf, 256))
+        return int(fused.value), buf.value.decode()
+
+    def schedule(self):
+        """(interval, last_disp_frac) of a decomposed run, see mc_comm_schedule."""
+        k, f = C.c_int32(0), C.c_double(0.0)
+        self._chk(self._L.mc_comm_schedule(self._h, C.byref(k), C.byref(f)))
+        return int(k.value), float(f.value)
 
     def stats(self):
         s = _lib.McStats()

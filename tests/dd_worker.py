@@ -1,5 +1,5 @@
 """One rank of a domain-decomposed run (spawned by tests/test_gpu_multi.py, one process per GPU).
-usage: dd_worker.py <rank> <world> <id_file> <case> <out_npz>"""
+usage: dd_worker.py <rank> <world> <id_file> <case> <out_npz> [fused|nccl] [fixed|adaptive|allgather]"""
 import ctypes as C
 import os
 import sys
@@ -26,6 +26,8 @@ def case_workload(name, world=2):
 
 def main():
     rank, world, id_file, case, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4], sys.argv[5]
+    halo = sys.argv[6] if len(sys.argv) > 6 else "fused"
+    sched = sys.argv[7] if len(sys.argv) > 7 else "fixed"
     w, n_steps = case_workload(case, world)
     e = MdEngine(device=rank)
     uid = np.zeros(128, np.uint8)
@@ -49,7 +51,10 @@ def main():
     e.set_atoms(w["xyzq"], w["type"], w["vel"])
     e.set_exclusions(w.get("excl_start"), w.get("excl_idx"))
     e.set_pairs14(w.get("pairs14"), w.get("scale14_lj", 0.5), w.get("scale14_q", 1 / 1.2))
-    e.set_option("rebuild_every", 5 if case == "lj" else 2)  # the unbonded solvated system has very fast hydrogens
+    e.set_option("halo_fused", 1 if halo == "fused" else 0)
+    # the unbonded solvated system has very fast hydrogens; "adaptive" leaves the interval to the engine
+    e.set_option("rebuild_every", 0 if sched == "adaptive" else (5 if case == "lj" else 2))
+    e.set_option("dd_migrate", 0 if sched == "allgather" else 1)
     e.compute_forces()
     f0 = e.forces()
     en0 = e.energy()
@@ -58,8 +63,16 @@ def main():
     x = e.positions()
     v = e.velocities()
     st = e.stats()
+    fused, why = e.halo_mode()
+    interval, disp_frac = e.schedule()
+    # rank-local asynchronous snapshot: owned atoms + their original ids
+    own, gh = st["n_atoms"], st["n_ghosts"]
+    sp, si = np.zeros((len(w["xyzq"]), 4), np.float32), np.full(len(w["xyzq"]), -1, np.int32)
+    n_snap = e.snapshot_begin(sp, si)
+    e.snapshot_wait()
+    snap_ok = n_snap == own and np.array_equal(sp[:n_snap], x[si[:n_snap]])
     if rank == 0:
-        np.savez(out, f0=f0, x=x, v=v, e_pot=en0["energy_potential_nonbonded"], n_owned=st0["n_atoms"],
+        np.savez(out, fused=fused, why=why, snap_ok=snap_ok, interval=interval, disp_frac=disp_frac, f0=f0, x=x, v=v, e_pot=en0["energy_potential_nonbonded"], n_owned=st0["n_atoms"],
                  n_ghosts=st0["n_ghosts"], rebuilds=st["n_rebuilds"], violations=st["n_list_violations"])
     e.close()
 

@@ -7,6 +7,7 @@ import sys
 import tempfile
 
 import numpy as np
+import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -30,10 +31,14 @@ def test_plan_covers_the_box_once(engine_lib):
     assert engine_lib.mc_dd_plan(small.ctypes.data, 9.5, 0, 2, out.ctypes.data) != 0
 
 
-def test_two_rank_protocol_reproduces_single_process_run(oracle, engine_lib):
+@pytest.mark.parametrize("m", [14, 22])
+def test_two_rank_protocol_reproduces_single_process_run(m, oracle, engine_lib):
+    """m = 14: two cell layers per rank (whole slabs exchanged); m = 22: four per rank (two-layer blocks).
+    The worker also asserts, after every build, that owner and ghost holder keep a layer in the same order."""
     d = tempfile.mkdtemp()
     out = os.path.join(d, "out.npz")
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2", OMP_NUM_THREADS="2")
+    os.environ["DD_M"] = str(m)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29533 + m), WORLD_SIZE="2", OMP_NUM_THREADS="2")
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dd_protocol_worker.py"), out],
                               env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
              for r in range(2)]
@@ -48,3 +53,4 @@ def test_two_rank_protocol_reproduces_single_process_run(oracle, engine_lib):
     dx -= np.rint(dx / w["box_ext"]) * w["box_ext"]
     assert np.abs(dx).max() < 5e-5, np.abs(dx).max()
     assert 0 < int(r["n_owned"]) < len(w["xyzq"]) and int(r["n_ghost"]) > 0
+    assert int(r["migrations"]) == N_STEPS // 3

@@ -23,25 +23,35 @@ def _n_gpus():
         return 0
 
 
-def _run(world, case):
+def _run(world, case, halo="fused", sched="fixed"):
     d = tempfile.mkdtemp()
     idf, out = os.path.join(d, "nccl_id"), os.path.join(d, "out.npz")
-    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dd_worker.py"), str(r), str(world), idf, case, out],
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dd_worker.py"), str(r), str(world), idf, case, out, halo, sched],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
     logs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
     return np.load(out)
 
 
-@pytest.mark.parametrize("case,world", [("lj", 2), ("solv", 2), ("lj", 4), ("lj", 8)])
-def test_decomposed_run_matches_oracle(world, case, oracle):
-    """solv (23.5k atoms, 14 A list radius) has only 4 cell layers along z: 2 ranks at most."""
+@pytest.mark.parametrize("case,world,halo,sched", [
+    ("lj", 2, "fused", "fixed"), ("lj", 2, "nccl", "fixed"), ("lj", 2, "fused", "allgather"), ("lj", 2, "fused", "adaptive"),
+    ("solv", 2, "fused", "fixed"), ("solv", 2, "nccl", "fixed"),
+    ("lj", 4, "fused", "fixed"), ("lj", 4, "fused", "adaptive"), ("lj", 8, "fused", "fixed"), ("lj", 8, "nccl", "fixed")])
+def test_decomposed_run_matches_oracle(world, case, halo, sched, oracle):
+    """solv (23.5k atoms, 14 A list radius) has only 4 cell layers along z: 2 ranks at most.
+    halo = fused: ghosts are stored into the neighbours' arrays by kick_drift over mapped peer memory and
+    the boundary rows' pair kernel waits on the flags (must really be active, not a silent NCCL fallback);
+    halo = nccl: ncclSend / ncclRecv between the two kernels.
+    sched = fixed: rebuild every 5 (2) steps, boundary layers migrate between neighbour ranks only;
+    allgather: rebuilds all-gather the whole system; adaptive: the engine picks the interval from the
+    largest displacement of the previous interval."""
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     sys.path.insert(0, HERE)
     from dd_worker import case_workload
     w, n_steps = case_workload(case, world)
-    r = _run(world, case)
+    r = _run(world, case, halo, sched)
+    assert int(r["fused"]) == (1 if halo == "fused" else 0), str(r["why"])
     nb = oracle.neighbors(w)
     f64, scale, en = oracle.forces(w, nb, precision=64)
     assert force_rel_err(r["f0"], f64, scale).max() < FORCE_RTOL
@@ -50,4 +60,7 @@ def test_decomposed_run_matches_oracle(world, case, oracle):
     ok, worst, sc = trajectory_close(r["x"], ref["xyzq"], w["xyzq"], w["box_ext"])
     assert ok, (worst, sc)
     assert int(r["violations"]) == 0
+    if sched == "adaptive":
+        assert int(r["interval"]) >= 10 and int(r["rebuilds"]) >= 3 and 0.0 < float(r["disp_frac"]) < 1.0
+    assert bool(r["snap_ok"]), "rank-local snapshot differs from the gathered positions"
     assert int(r["n_owned"]) < len(w["xyzq"]) and int(r["n_ghosts"]) > 0

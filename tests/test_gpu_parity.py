@@ -106,6 +106,50 @@ def test_short_trajectory_follows_the_cpu_path(name, Engine, oracle):
     e.close()
 
 
+def test_async_snapshots_match_blocking_reads(Engine):
+    """mc_snapshot_begin / mc_snapshot_wait (the Snapshot queue of reference src/md/mod.rs:118-152): two
+    snapshots in flight while the integrator keeps stepping; each equals the blocking read of its step."""
+    w = W.lj_fluid(m=16)
+    e = Engine.from_workload(w)
+    n = len(w["xyzq"])
+    bufs = [np.zeros((n, 4), np.float32) for _ in range(3)]
+    want = []
+    e.step(w["dt"], 3)
+    want.append(e.positions())
+    assert e.snapshot_begin(bufs[0]) == n
+    e.step(w["dt"], 2)
+    want.append(e.positions())
+    e.snapshot_begin(bufs[1])
+    e.step(w["dt"], 4)
+    e.snapshot_wait()
+    assert np.array_equal(bufs[0], want[0])
+    want.append(e.positions())
+    e.snapshot_begin(bufs[2])
+    e.snapshot_wait()
+    e.snapshot_wait()
+    assert np.array_equal(bufs[1], want[1]) and np.array_equal(bufs[2], want[2])
+    e.close()
+
+
+@pytest.mark.parametrize("opt", [("subcell_sort", 1), ("subcell_sort", 0), ("sync_rebuild", 1), ("rebuild_every", 4)])
+def test_build_and_rebuild_policies_keep_parity(opt, Engine, oracle):
+    """The Morton sub-cell sort key, the host-published displacement flag (default), the synchronous flag
+    read and the fixed rebuild schedule all list the oracle's pairs and follow the oracle's trajectory."""
+    w = W.lj_fluid(m=14, temp_k=400.0)  # hot enough that the displacement criterion fires within 60 steps
+    e = Engine.from_workload(w)
+    e.set_option(*opt)
+    e.build_neighbors()
+    start, idx = e.neighbors()
+    o_start, o_idx = oracle.neighbors(w)
+    assert np.array_equal(start, o_start) and np.array_equal(idx, o_idx)
+    e.step(w["dt"], 60)
+    assert e.stats()["n_rebuilds"] >= 3
+    ref = oracle.md_run(w, 60, precision=64)
+    ok, worst, scale = trajectory_close(e.positions(), ref["xyzq"], w["xyzq"], w["box_ext"])
+    assert ok, (worst, scale)
+    e.close()
+
+
 def test_external_forces_and_static_atoms(Engine, oracle):
     """step(dev, dt, Some(forces)) (reference src/mol_alignment.rs:346) and AtomDynamics.static_."""
     w = W.globule(300, seed=33)
