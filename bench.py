@@ -47,7 +47,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
@@ -110,8 +110,8 @@ def cpu_arm(side, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=1000)   # C4 = 1,000 timed steps after 200 warm-up
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--side", type=int, default=100, help="atoms per box edge (100 -> 1,000,000 atoms)")
     ap.add_argument("--cpu-side", type=int, default=64)
