@@ -192,6 +192,26 @@ int mc_dock_score(mc_ctx *ctx, int64_t n_rec, const mc_float4 *rec_xyzq, const u
                   const uint16_t *lig_type, const uint8_t *lig_hydrophobic, const float lig_anchor[3],
                   int n_rec_types, int n_lig_types, const float *ljtab,
                   int64_t n_poses, const float *poses, float *out);
+/* ---- pose set of the scan -- host side, usable without a GPU -------------------- */
+
+/* make_posits_orientations + init_poses for a rigid ligand (src/docking/legacy/mod.rs:386-500): anchors on a
+ * num_posits^3 grid of cell centres over the cube of half-width site_radius about site_center (x slowest), times
+ * n_lats * n_lons * n_rolls orientations with n_lats = floor((num_orientations/2)^(1/3)), n_lons = n_rolls =
+ * 2 n_lats (find_optimal_pose uses num_posits = 8, num_orientations = 60 -> 512 x 108 poses, :705-706).
+ * out_poses: n x {ax, ay, az, qw, qx, qy, qz}, anchor-major.  out_poses == NULL only reports *n_out. */
+int mc_dock_make_poses(const double site_center[3], double site_radius, int num_posits, int num_orientations,
+                       float *out_poses, int64_t cap, int64_t *n_out);
+int mc_dock_orientation_count(int num_orientations);
+/* find_rec_atoms_near_site (legacy/prep.rs:506-532): receptor atoms within 1.4 x site_radius of the site centre
+ * that are not hetero atoms; out_idx (capacity n_rec) may be NULL to count. */
+int mc_dock_near_site(int64_t n_rec, const mc_float4 *rec_xyzq, const uint8_t *rec_hetero, const double site_center[3],
+                      double site_radius, int32_t *out_idx, int64_t *n_out);
+/* Clash pre-filter of process_poses (legacy/mod.rs:522-573): keep[p] = 0 when a sampled ligand carbon (index % 4 == 0)
+ * of pose p lies within 1.1 x vdw_radius of a sampled receptor carbon (near-site index % 6 == 0).  rec_* describe
+ * the near-site subset in its own order; the ligand is posed exactly as mc_dock_score poses it. */
+int mc_dock_filter_poses(int64_t n_rec, const mc_float4 *rec_xyzq, const uint8_t *rec_is_carbon, int64_t n_lig,
+                         const mc_float4 *lig_xyzq, const uint8_t *lig_is_carbon, const float lig_anchor[3],
+                         float vdw_radius, int64_t n_poses, const float *poses, uint8_t *keep, int64_t *n_kept);
 /* CUDA-event duration of the scan kernel of the last mc_dock_score call (profiling on). */
 double mc_last_dock_kernel_ms(mc_ctx *ctx);
 
