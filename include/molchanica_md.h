@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MC_ABI_VERSION 1
+#define MC_ABI_VERSION 2
 
 #define MC_OK 0
 #define MC_E_INVALID (-1)   /* bad argument / call order                      */
@@ -57,11 +57,14 @@ typedef struct { float x, y, z, w; } mc_float4;
 
 /* SnapshotEnergyData subset (reference src/md/mod.rs:1242-1245, ui/panels/md_viewer.rs:202-256) */
 typedef struct {
-    double energy_potential;            /* = nonbonded here (bonded terms are outside this path) */
+    double energy_potential;            /* nonbonded + bonded                                    */
     double energy_potential_nonbonded;  /* LJ + Coulomb + scaled 1-4, kcal/mol                   */
-    double energy_potential_bonded;     /* always 0: bonded terms are a "next" row   */
+    double energy_potential_bonded;     /* bonds + angles + dihedrals set with mc_set_bonds ...  */
     double energy_kinetic;              /* sum 1/2 m v^2 / 418.4, kcal/mol                       */
     double temperature;                 /* 2 KE / (3 N_mobile k_B), K                            */
+    double energy_bond, energy_angle, energy_dihedral;  /* parts of energy_potential_bonded      */
+    double volume;                      /* A^3 (periodic boxes, else 0)                          */
+    double density;                     /* g/cm^3 from the atoms' masses (periodic boxes)        */
 } mc_energy;
 
 /* Counters for the caller / benchmarks.  The *_ms_sum fields accumulate CUDA-event durations
@@ -112,6 +115,16 @@ int mc_set_exclusions(mc_ctx *ctx, const int32_t *start, const int32_t *idx);
 
 /* Amber 1-4 pairs (pairs[2*m]) evaluated without cutoff, LJ x scale_lj, Coulomb x scale_q. */
 int mc_set_pairs14(mc_ctx *ctx, int64_t m, const int32_t *pairs, float scale_lj, float scale_q);
+
+/* Bonded terms, Amber functional forms, evaluated on the device in the same force evaluation
+ * as the nonbonded terms (single-GPU handles).  Atom ids are the caller's; call after mc_set_atoms (which clears
+ * them); m = 0 clears one kind.  Exclusions / 1-4 pairs that go with the bonds are set separately above.
+ *   bonds:     pairs[2m],   k_r0[2m]       E = k (r - r0)^2                    kcal/mol/A^2, A
+ *   angles:    triples[3m] (vertex second), k_theta0[2m]  E = k (theta - theta0)^2   kcal/mol/rad^2, rad
+ *   dihedrals: quads[4m],   pk_n_phase[3m] E = pk (1 + cos(n phi - phase))     kcal/mol, -, rad (IUPAC phi) */
+int mc_set_bonds(mc_ctx *ctx, int64_t m, const int32_t *pairs, const float *k_r0);
+int mc_set_angles(mc_ctx *ctx, int64_t m, const int32_t *triples, const float *k_theta0);
+int mc_set_dihedrals(mc_ctx *ctx, int64_t m, const int32_t *quads, const float *pk_n_phase);
 
 /* cfg.lj_cutoff / cfg.coulomb_cutoff (ui/panels/md.rs:260-261), Verlet skin, Coulomb form. */
 int mc_set_cutoffs(mc_ctx *ctx, float rc_lj, float rc_q, float skin, int coulomb_mode, float alpha);

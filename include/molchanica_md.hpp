@@ -80,11 +80,15 @@ struct MdSystem {
     std::vector<int32_t> excl_start, excl_idx;  // CSR of excluded partners (1-2, 1-3, 1-4)
     std::vector<int32_t> pairs14;          // 2 x m
     float scale14_lj = 0.5f, scale14_coulomb = 1.0f / 1.2f;
+    // bonded terms, Amber forms (mc_set_bonds / mc_set_angles / mc_set_dihedrals); empty = none
+    std::vector<int32_t> bonds, angles, dihedrals;           // 2 / 3 / 4 atom ids per term
+    std::vector<float> bond_k_r0, angle_k_theta0, dihedral_pk_n_phase;  // 2 / 2 / 3 parameters per term
 };
 
 struct SnapshotEnergyData {  // src/md/mod.rs:1242-1245, ui/panels/md_viewer.rs:202-256
     double energy_potential = 0, energy_potential_nonbonded = 0, energy_potential_bonded = 0;
     double energy_kinetic = 0, temperature = 0;
+    double volume = 0, density = 0;  // A^3, g/cm^3 (periodic boxes)
 };
 
 class MdState {
@@ -119,6 +123,10 @@ class MdState {
         if (!sys.excl_idx.empty()) md.chk(mc_set_exclusions(md.ctx_, sys.excl_start.data(), sys.excl_idx.data()));
         if (!sys.pairs14.empty())
             md.chk(mc_set_pairs14(md.ctx_, (int64_t)sys.pairs14.size() / 2, sys.pairs14.data(), sys.scale14_lj, sys.scale14_coulomb));
+        if (!sys.bonds.empty()) md.chk(mc_set_bonds(md.ctx_, (int64_t)sys.bonds.size() / 2, sys.bonds.data(), sys.bond_k_r0.data()));
+        if (!sys.angles.empty()) md.chk(mc_set_angles(md.ctx_, (int64_t)sys.angles.size() / 3, sys.angles.data(), sys.angle_k_theta0.data()));
+        if (!sys.dihedrals.empty())
+            md.chk(mc_set_dihedrals(md.ctx_, (int64_t)sys.dihedrals.size() / 4, sys.dihedrals.data(), sys.dihedral_pk_n_phase.data()));
         return md;
     }
 
@@ -159,8 +167,19 @@ class MdState {
         s.energy_potential_bonded = e.energy_potential_bonded;
         s.energy_kinetic = e.energy_kinetic;
         s.temperature = e.temperature;
+        s.volume = e.volume;
+        s.density = e.density;
         return s;
     }
+
+    // Snapshot hand-off without stalling the integrator (the queue of src/md/mod.rs:118-152): begin() stages the
+    // current positions on the device and starts the copy into `out` (original atom order; page-locked memory
+    // overlaps with the next steps), wait() blocks until the oldest outstanding snapshot has landed.
+    void snapshot_begin(std::vector<mc_float4> &out) {
+        out.resize(atoms.size());
+        chk(mc_snapshot_begin(ctx_, out.data(), nullptr, nullptr));
+    }
+    void snapshot_wait() { chk(mc_snapshot_wait(ctx_)); }
 
     // Make positions / velocities / forces host-visible on demand (the shrinking-box workflow reads
     // atom.force every chunk, properties/sol_shrinking_box.rs:776-789) -- never per step.

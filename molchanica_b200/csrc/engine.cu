@@ -218,7 +218,13 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
     c->forces_valid = false;
     c->have_excl = false;
     c->have_p14 = false;
+    c->n_bonds = c->n_angles = c->n_dihedrals = 0;
     c->n_pairs_listed = 0;
+    c->total_mass = 0.0;
+    for (int64_t k = 0; k < n; ++k) {
+        const float im = vel_invmass ? vel_invmass[k].w : 1.f;
+        if (im > 0.f) c->total_mass += 1.0 / (double)im;
+    }
     if (c->comm_active) return comm_set_atoms(c, n, xyzq, type, vel_invmass, flags);
     c->n_rows = n;
     if (type)
@@ -280,6 +286,66 @@ extern "C" int mc_set_pairs14(mc_ctx *c, int64_t m, const int32_t *pairs, float 
     MC_CUDA(c, cudaMemcpy(c->p14_start.p, start.data(), start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     MC_CUDA(c, cudaMemcpy(c->p14_idx.p, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     c->have_p14 = true;
+    return MC_OK;
+}
+
+// ---- bonded terms ------------------------------------------------------------------
+// Host layout in, device layout (int2 / int4 + parameter vectors) out; atom ids are the caller's.
+
+template <int W, typename IdxT>
+static int upload_terms(mc_ctx *c, const char *who, int64_t m, const int32_t *ids, DevBuf<IdxT> &d_ids, int *count) {
+    const int64_t n = c->n_global;
+    std::vector<IdxT> h((size_t)std::max<int64_t>(m, 1));
+    for (int64_t k = 0; k < m; ++k) {
+        int v[4] = {0, 0, 0, 0};
+        for (int a = 0; a < W; ++a) {
+            v[a] = ids[W * k + a];
+            MC_REQUIRE(c, v[a] >= 0 && v[a] < n, std::string(who) + ": atom id out of range");
+        }
+        memcpy(&h[(size_t)k], v, sizeof(IdxT));
+    }
+    MC_CUDA(c, d_ids.ensure((size_t)std::max<int64_t>(m, 1)));
+    if (m) MC_CUDA(c, cudaMemcpy(d_ids.p, h.data(), sizeof(IdxT) * (size_t)m, cudaMemcpyHostToDevice));
+    *count = (int)m;
+    c->forces_valid = false;
+    return MC_OK;
+}
+
+extern "C" int mc_set_bonds(mc_ctx *c, int64_t m, const int32_t *pairs, const float *k_r0) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, !c->comm_active, "mc_set_bonds: bonded terms on a decomposed handle are not supported yet");
+    MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || (pairs && k_r0)), "mc_set_bonds: bad arguments");
+    int rc = upload_terms<2, int2>(c, "mc_set_bonds", m, pairs, c->bonds, &c->n_bonds);
+    if (rc != MC_OK) { c->n_bonds = 0; return rc; }
+    MC_CUDA(c, c->bond_kr0.ensure((size_t)std::max<int64_t>(m, 1)));
+    if (m) MC_CUDA(c, cudaMemcpy(c->bond_kr0.p, k_r0, sizeof(float2) * (size_t)m, cudaMemcpyHostToDevice));
+    return MC_OK;
+}
+
+extern "C" int mc_set_angles(mc_ctx *c, int64_t m, const int32_t *triples, const float *k_theta0) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, !c->comm_active, "mc_set_angles: bonded terms on a decomposed handle are not supported yet");
+    MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || (triples && k_theta0)), "mc_set_angles: bad arguments");
+    int rc = upload_terms<3, int4>(c, "mc_set_angles", m, triples, c->angles, &c->n_angles);
+    if (rc != MC_OK) { c->n_angles = 0; return rc; }
+    MC_CUDA(c, c->angle_kt0.ensure((size_t)std::max<int64_t>(m, 1)));
+    if (m) MC_CUDA(c, cudaMemcpy(c->angle_kt0.p, k_theta0, sizeof(float2) * (size_t)m, cudaMemcpyHostToDevice));
+    return MC_OK;
+}
+
+extern "C" int mc_set_dihedrals(mc_ctx *c, int64_t m, const int32_t *quads, const float *pk_n_phase) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, !c->comm_active, "mc_set_dihedrals: bonded terms on a decomposed handle are not supported yet");
+    MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || (quads && pk_n_phase)), "mc_set_dihedrals: bad arguments");
+    int rc = upload_terms<4, int4>(c, "mc_set_dihedrals", m, quads, c->dihedrals, &c->n_dihedrals);
+    if (rc != MC_OK) { c->n_dihedrals = 0; return rc; }
+    std::vector<float4> prm((size_t)std::max<int64_t>(m, 1));
+    for (int64_t k = 0; k < m; ++k) prm[(size_t)k] = make_float4(pk_n_phase[3 * k], pk_n_phase[3 * k + 1], pk_n_phase[3 * k + 2], 0.f);
+    MC_CUDA(c, c->dihedral_prm.ensure(prm.size()));
+    if (m) MC_CUDA(c, cudaMemcpy(c->dihedral_prm.p, prm.data(), sizeof(float4) * (size_t)m, cudaMemcpyHostToDevice));
     return MC_OK;
 }
 
@@ -560,6 +626,15 @@ int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs) {
         launch_pairs14(L.n_rows, L.row0, L.xyzq, L.type, c->orig[c->cur].p, c->slot_of_orig.p, c->p14_start.p, c->p14_idx.p,
                        c->ljtab.p, L.p, c->scale14_lj, c->scale14_q, L.lj_on, (L.coul != MC_COULOMB_NONE) ? 1 : 0,
                        c->force.p, c->st, &c->launches);
+    if (c->n_bonds + c->n_angles + c->n_dihedrals > 0) {
+        BondedTerms t;
+        t.n_bonds = c->n_bonds; t.n_angles = c->n_angles; t.n_dihedrals = c->n_dihedrals;
+        t.bonds = c->bonds.p; t.bond_kr0 = c->bond_kr0.p;
+        t.angles = c->angles.p; t.angle_kt0 = c->angle_kt0.p;
+        t.dihedrals = c->dihedrals.p; t.dihedral_prm = c->dihedral_prm.p;
+        MC_CUDA(c, c->bonded_e.ensure(4));
+        launch_bonded(t, c->slot_of_orig.p, L.xyzq, L.p, c->force.p, c->bonded_e.p, want_energy, c->st, &c->launches);
+    }
     MC_CUDA(c, cudaGetLastError());
     c->forces_valid = true;
     c->forces_have_energy = want_energy;
@@ -845,7 +920,17 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
     memset(out, 0, sizeof(*out));
     out->energy_potential_nonbonded = 0.5 * h[0];  // every pair sits in two rows
     out->energy_potential_bonded = 0.0;
-    out->energy_potential = out->energy_potential_nonbonded;
+    if (c->n_bonds + c->n_angles + c->n_dihedrals > 0) {
+        double hb[3];
+        MC_CUDA(c, cudaMemcpy(hb, c->bonded_e.p, sizeof(hb), cudaMemcpyDeviceToHost));
+        out->energy_bond = hb[0]; out->energy_angle = hb[1]; out->energy_dihedral = hb[2];
+        out->energy_potential_bonded = hb[0] + hb[1] + hb[2];
+    }
+    out->energy_potential = out->energy_potential_nonbonded + out->energy_potential_bonded;
+    if (c->periodic) {
+        out->volume = (double)c->ext[0] * (double)c->ext[1] * (double)c->ext[2];
+        out->density = out->volume > 0.0 ? c->total_mass * 1.66053907 / out->volume : 0.0;  // amu/A^3 -> g/cm^3
+    }
     out->energy_kinetic = h[1] / (double)MC_ACCEL_CONV;
     out->temperature = h[2] > 0 ? 2.0 * out->energy_kinetic / (3.0 * h[2] * MC_KB) : 0.0;
     return MC_OK;

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "halo_sync.cuh"
+#include "bonded.cuh"
 
 template <typename T>
 struct DevBuf {
@@ -106,6 +107,15 @@ struct mc_ctx {
     DevBuf<float4> d_rec, d_lig;
     DevBuf<uint32_t> d_rec_meta, d_lig_meta;
 
+    // bonded terms (bonded.cu), caller's atom ids
+    int n_bonds = 0, n_angles = 0, n_dihedrals = 0;
+    DevBuf<int2> bonds;
+    DevBuf<float2> bond_kr0, angle_kt0;
+    DevBuf<int4> angles, dihedrals;
+    DevBuf<float4> dihedral_prm;
+    DevBuf<double> bonded_e;   // {E_bond, E_angle, E_dihedral} of the last evaluation that asked for energies
+    double total_mass = 0.0;   // amu, from the inverse masses handed to mc_set_atoms (density of the snapshot)
+
     // asynchronous snapshots (mc_snapshot_begin / mc_snapshot_wait): double-buffered staging + a copy stream
     cudaStream_t st_copy = nullptr;
     cudaEvent_t ev_snap_staged[2] = {nullptr, nullptr}, ev_snap_done[2] = {nullptr, nullptr};
@@ -156,6 +166,8 @@ struct mc_ctx {
         grid.release(); red_partial.release(); red_out.release(); d_rec.release(); d_lig.release();
         d_rec_meta.release(); d_lig_meta.release();
         for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_ids[b].release(); }
+        bonds.release(); bond_kr0.release(); angle_kt0.release(); angles.release(); dihedrals.release(); dihedral_prm.release();
+        bonded_e.release();
     }
 
     // resolve the CUDA-event pairs recorded since the last call (stream must be idle)

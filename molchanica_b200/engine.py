@@ -95,6 +95,20 @@ class MdEngine:
         p = None if pairs is None or len(pairs) == 0 else np.ascontiguousarray(pairs, np.int32)
         self._chk(self._L.mc_set_pairs14(self._h, 0 if p is None else len(p), _ptr(p), scale_lj, scale_q))
 
+    def set_bonded(self, bonds=None, bond_kr0=None, angles=None, angle_kt0=None, dihedrals=None, dihedral_prm=None):
+        """mc_set_bonds / mc_set_angles / mc_set_dihedrals (None or empty clears a kind)."""
+        def pair(ids, prm, width):
+            if ids is None or len(ids) == 0:
+                return 0, None, None
+            i = np.ascontiguousarray(ids, np.int32).reshape(-1, width)
+            return len(i), i, np.ascontiguousarray(prm, np.float32)
+        m, i, p = pair(bonds, bond_kr0, 2)
+        self._chk(self._L.mc_set_bonds(self._h, m, _ptr(i), _ptr(p)))
+        m, i, p = pair(angles, angle_kt0, 3)
+        self._chk(self._L.mc_set_angles(self._h, m, _ptr(i), _ptr(p)))
+        m, i, p = pair(dihedrals, dihedral_prm, 4)
+        self._chk(self._L.mc_set_dihedrals(self._h, m, _ptr(i), _ptr(p)))
+
     def set_cutoffs(self, rc_lj, rc_q, skin, coulomb_mode, alpha=0.35):
         self._chk(self._L.mc_set_cutoffs(self._h, rc_lj, rc_q, skin, int(coulomb_mode), alpha))
 
@@ -113,8 +127,9 @@ class MdEngine:
         self._chk(self._L.mc_set_velocities(self._h, _ptr(a)))
 
     @classmethod
-    def from_workload(cls, w, device=0):
-        """Everything MdState::new hands to the engine, from a workloads.py dict."""
+    def from_workload(cls, w, device=0, bonded=False):
+        """Everything MdState::new hands to the engine, from a workloads.py dict (bonded = True: also the
+        bonds / angles / dihedrals the workload carries)."""
         e = cls(device)
         lo = np.asarray(w["box_lo"], np.float32)
         e.set_box(lo, lo + np.asarray(w["box_ext"], np.float32), w["periodic"])
@@ -123,6 +138,9 @@ class MdEngine:
         e.set_atoms(w["xyzq"], w["type"], w["vel"], w.get("flags"))
         e.set_exclusions(w.get("excl_start"), w.get("excl_idx"))
         e.set_pairs14(w.get("pairs14"), w.get("scale14_lj", 0.5), w.get("scale14_q", 1 / 1.2))
+        if bonded:
+            e.set_bonded(w.get("bonds"), w.get("bond_kr0"), w.get("angles"), w.get("angle_kt0"),
+                         w.get("dihedrals"), w.get("dihedral_prm"))
         return e
 
     # -- hot path

@@ -236,6 +236,45 @@ def globule(n_atoms=1231, seed=202, name="C2-globule1231", temp_k=300.0):
     return w
 
 
+def bonded_terms_from_bonds(pos, bonds, seed=0):
+    """Angles and dihedrals of a bond graph with Amber-like parameters: harmonic bonds and angles whose
+    equilibrium values are the current geometry displaced by a few percent (so that forces are non-zero),
+    periodic dihedrals with n in {1, 2, 3} and phase 0 or pi."""
+    rng = np.random.default_rng(9000 + seed)
+    n = len(pos)
+    adj = [[] for _ in range(n)]
+    for i, j in bonds:
+        adj[i].append(j)
+        adj[j].append(i)
+    b = np.array(sorted({(min(i, j), max(i, j)) for i, j in bonds}), np.int32).reshape(-1, 2)
+    r0 = np.linalg.norm(pos[b[:, 0]] - pos[b[:, 1]], axis=1)
+    bk = np.stack([rng.uniform(200, 450, len(b)), r0 * rng.uniform(0.97, 1.03, len(b))], 1).astype(np.float32)
+    ang = np.array(sorted({(min(i, k), j, max(i, k)) for j in range(n) for i in adj[j] for k in adj[j] if i < k}),
+                   np.int32).reshape(-1, 3)
+    va, vb = pos[ang[:, 0]] - pos[ang[:, 1]], pos[ang[:, 2]] - pos[ang[:, 1]]
+    th = np.arccos(np.clip((va * vb).sum(1) / (np.linalg.norm(va, axis=1) * np.linalg.norm(vb, axis=1)), -1, 1))
+    ak = np.stack([rng.uniform(30, 80, len(ang)), th + rng.uniform(-0.08, 0.08, len(ang))], 1).astype(np.float32)
+    dih = set()
+    for j, k in b:
+        for i in adj[j]:
+            for l in adj[k]:
+                if i != k and l != j and i != l:
+                    dih.add((i, int(j), int(k), l))
+    dih = np.array(sorted(dih), np.int32).reshape(-1, 4)
+    dk = np.stack([rng.uniform(0.1, 2.5, len(dih)), rng.integers(1, 4, len(dih)).astype(np.float64),
+                   np.pi * rng.integers(0, 2, len(dih))], 1).astype(np.float32)
+    return dict(bonds=b, bond_kr0=bk, angles=ang, angle_kt0=ak, dihedrals=dih, dihedral_prm=dk)
+
+
+def bonded_globule(n_atoms=400, seed=212):
+    """A C2-like globule that also carries its bonded terms: every bond of the chain graph, every
+    angle and every proper dihedral it implies; nonbonded set-up as C2 (1-2/1-3 exclusions, scaled 1-4)."""
+    w = globule(n_atoms, seed=seed, name=f"bonded-globule{n_atoms}")
+    _, _, bonds = _saw_globule(n_atoms, seed)
+    w.update(bonded_terms_from_bonds(w["xyzq"][:, :3].astype(np.float64), bonds, seed))
+    return w
+
+
 def solvated_c3(seed=303, n_protein=2489, n_water=7023, L=62.23):
     """C3: 2,489-atom globule + 7,023 three-site waters in a 62.23 A cubic PBC box
     (23,558 atoms, the DHFR/JAC stand-in), r_c 12 A, skin 2 A."""

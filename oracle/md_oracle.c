@@ -462,6 +462,91 @@ void orc_bonds(int nb, const int32_t *bonds, const float *kr0, const float *xyzq
     }
 }
 
+/* ---- bonded terms beyond bonds, fp64 ------------------------------------------
+ * Amber functional forms (the reference's force field, README.md:234-241; the evaluating code is in the
+ * un-vendored `dynamics` crate -> parity unpinned, known-answer + finite-difference tests pin the
+ * arithmetic):  angle E = k (theta - theta0)^2, dihedral E = pk (1 + cos(n phi - phase)), IUPAC phi.
+ * Written independently of molchanica_b200/csrc/bonded_terms.h: gradients of theta and phi by the
+ * chain rule on cos(theta) and on atan2, not the GROMACS vector form the device code uses. */
+static void v_sub(const float *x, int i, int j, const float *ext, int periodic, double *d) {
+    for (int a = 0; a < 3; ++a) {
+        double dd = (double)x[4 * i + a] - (double)x[4 * j + a];
+        if (periodic) dd -= rint(dd / (double)ext[a]) * (double)ext[a];
+        d[a] = dd;
+    }
+}
+static void v_cross(const double *a, const double *b, double *c) {
+    c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+static double v_dot(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+/* forces f64: n*3 doubles accumulated; energy3: {bond, angle, dihedral} accumulated */
+void orc_bonded64(int nb, const int32_t *bonds, const float *kr0, int na, const int32_t *angles, const float *kt0,
+                  int nd, const int32_t *dih, const float *prm, const float *xyzq, const float *ext, int periodic,
+                  double *f, double *energy3) {
+    for (int t = 0; t < nb; ++t) {
+        int i = bonds[2 * t], j = bonds[2 * t + 1];
+        double d[3];
+        v_sub(xyzq, i, j, ext, periodic, d);
+        double r = sqrt(v_dot(d, d)), k = kr0[2 * t], r0 = kr0[2 * t + 1];
+        double fr = -2.0 * k * (r - r0) / r;
+        for (int a = 0; a < 3; ++a) { f[3 * i + a] += d[a] * fr; f[3 * j + a] -= d[a] * fr; }
+        energy3[0] += k * (r - r0) * (r - r0);
+    }
+    for (int t = 0; t < na; ++t) {
+        int i = angles[3 * t], j = angles[3 * t + 1], k = angles[3 * t + 2];
+        double a[3], b[3];
+        v_sub(xyzq, i, j, ext, periodic, a);
+        v_sub(xyzq, k, j, ext, periodic, b);
+        double la = sqrt(v_dot(a, a)), lb = sqrt(v_dot(b, b));
+        double c = v_dot(a, b) / (la * lb);
+        if (c > 1.0) c = 1.0;
+        if (c < -1.0) c = -1.0;
+        double th = acos(c), kk = kt0[2 * t], th0 = kt0[2 * t + 1];
+        double dE = 2.0 * kk * (th - th0);            /* dE/dtheta */
+        double s = sqrt(1.0 - c * c);
+        if (s < 1e-9) s = 1e-9;
+        double dth_dc = -1.0 / s;                     /* dtheta/dcos */
+        for (int x = 0; x < 3; ++x) {
+            double dc_da = b[x] / (la * lb) - c * a[x] / (la * la);
+            double dc_db = a[x] / (la * lb) - c * b[x] / (lb * lb);
+            double fi = -dE * dth_dc * dc_da, fk = -dE * dth_dc * dc_db;
+            f[3 * i + x] += fi; f[3 * k + x] += fk; f[3 * j + x] -= fi + fk;
+        }
+        energy3[1] += kk * (th - th0) * (th - th0);
+    }
+    for (int t = 0; t < nd; ++t) {
+        int i = dih[4 * t], j = dih[4 * t + 1], k = dih[4 * t + 2], l = dih[4 * t + 3];
+        double pk = prm[3 * t], per = prm[3 * t + 1], ph = prm[3 * t + 2];
+        /* numerical-free analytic gradient through y = |r_kj| r_ij.n, x = m.n is long; use the textbook
+         * projection form (Blondel & Karplus 1996): F_i = -dE/dphi * (-|G| / |A|^2) A with F = r_i - r_j,
+         * G = r_j - r_k, H = r_l - r_k, A = F x G, B = H x G */
+        double F[3], G[3], H[3], A[3], B[3];
+        v_sub(xyzq, i, j, ext, periodic, F);
+        v_sub(xyzq, j, k, ext, periodic, G);
+        v_sub(xyzq, l, k, ext, periodic, H);
+        v_cross(F, G, A);
+        v_cross(H, G, B);
+        double A2 = v_dot(A, A), B2 = v_dot(B, B), g = sqrt(v_dot(G, G));
+        double cosphi = v_dot(A, B) / sqrt(A2 * B2);
+        double BxA[3];
+        v_cross(B, A, BxA);
+        double sinphi = v_dot(BxA, G) / (sqrt(A2 * B2) * g);
+        double phi = atan2(sinphi, cosphi);
+        double dE = -pk * per * sin(per * phi - ph);  /* dE/dphi */
+        double FG = v_dot(F, G), HG = v_dot(H, G);
+        for (int x = 0; x < 3; ++x) {
+            double dphi_di = -g / A2 * A[x];
+            double dphi_dl = g / B2 * B[x];
+            double dphi_dj = g / A2 * A[x] + FG / (A2 * g) * A[x] - HG / (B2 * g) * B[x];
+            double dphi_dk = -g / B2 * B[x] - FG / (A2 * g) * A[x] + HG / (B2 * g) * B[x];
+            f[3 * i + x] -= dE * dphi_di; f[3 * j + x] -= dE * dphi_dj;
+            f[3 * k + x] -= dE * dphi_dk; f[3 * l + x] -= dE * dphi_dl;
+        }
+        energy3[2] += pk * (1.0 + cos(per * phi - ph));
+    }
+}
+
 /* ---- velocity Verlet -------------------------------------------------------------------- */
 
 /* v += F * inv_mass * (dt/2) * 418.4 ; vel: n*4 (vx,vy,vz,inv_mass); static atoms: inv_mass 0 */

@@ -190,6 +190,33 @@ def md_run(w, n_steps, precision=32, xyzq=None, vel=None, want_energies=False, e
     return dict(xyzq=xyzq, vel=vel, forces=fo, rebuilds=rb, energies=en)
 
 
+def bonded(w, xyzq=None):
+    """fp64 bonded forces (n,3) and energies {bond, angle, dihedral} of the terms a workload carries
+    (keys bonds/bond_kr0, angles/angle_kt0, dihedrals/dihedral_prm; missing kinds count as empty)."""
+    x = np.ascontiguousarray(w["xyzq"] if xyzq is None else xyzq, np.float32)
+    n = len(x)
+
+    def arr(key, dt, width):
+        a = w.get(key)
+        if a is None or len(a) == 0:
+            return None, 0
+        a = np.ascontiguousarray(a, dt).reshape(-1, width)
+        return a, len(a)
+    b, nb = arr("bonds", np.int32, 2)
+    bk, _ = arr("bond_kr0", np.float32, 2)
+    a, na = arr("angles", np.int32, 3)
+    ak, _ = arr("angle_kt0", np.float32, 2)
+    d, nd = arr("dihedrals", np.int32, 4)
+    dk, _ = arr("dihedral_prm", np.float32, 3)
+    f = np.zeros((n, 3), np.float64)
+    e3 = np.zeros(3, np.float64)
+    ext = np.ascontiguousarray(w["box_ext"], np.float32)
+    lib().orc_bonded64(C.c_int(nb), _p(b, C.c_int32), _p(bk, C.c_float), C.c_int(na), _p(a, C.c_int32), _p(ak, C.c_float),
+                       C.c_int(nd), _p(d, C.c_int32), _p(dk, C.c_float), _p(x, C.c_float), _p(ext, C.c_float),
+                       C.c_int(int(w["periodic"])), _p(f, C.c_double), _p(e3, C.c_double))
+    return f, e3
+
+
 def dock_score(d, precision=64, poses=None, with_abs=False):
     """(P,5) f32: score, vdw, hydrophobic, electrostatic, coulomb_e
     [+ (P,3) sums of term magnitudes: vdw, coulomb force, coulomb energy]."""

@@ -12,7 +12,7 @@ def test_library_exports_every_declared_symbol(engine_lib):
     assert len(names) >= 30
     for s in names:
         assert hasattr(engine_lib, s), s
-    assert engine_lib.mc_abi_version() == 1
+    assert engine_lib.mc_abi_version() == 2
 
 
 def test_sass_is_sm100a_only():
