@@ -1,0 +1,64 @@
+"""Runs the on-device bonded-term checks in a process of its own (spawned by tests/test_gpu_bonded.py): bonded.cu
+has not run on hardware yet, and a faulting kernel must not poison the CUDA context of the other GPU tests.
+Prints one JSON line with the measured errors; exit code 0 = every check passed."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from molchanica_b200 import workloads as W  # noqa: E402
+from molchanica_b200.engine import MdEngine  # noqa: E402
+from oracle import oracle_py as O  # noqa: E402
+from util import FORCE_RTOL, trajectory_close  # noqa: E402
+
+
+def main():
+    res = {}
+    # 1. forces and energies of bonds + angles + dihedrals + nonbonded against the fp64 oracle
+    w = W.bonded_globule(400)
+    e = MdEngine.from_workload(w, bonded=True)
+    e.compute_forces()
+    f = e.forces()
+    en = e.energy()
+    nb = O.neighbors(w)
+    f_nb, scale_nb, _ = O.forces(w, nb, precision=64)
+    f_b, e_b = O.bonded(w)
+    want = f_nb[:, :3] + f_b
+    scale = scale_nb + np.abs(f_b).max(1)
+    scale = np.maximum(scale, 1e-3 * scale.max())
+    res["force_err"] = float((np.abs(f[:, :3].astype(np.float64) - want).max(1) / scale).max())
+    res["energy_rel"] = float(np.abs(np.array([en["energy_bond"], en["energy_angle"], en["energy_dihedral"]]) - e_b).max() / e_b.max())
+    res["sum_ok"] = bool(abs(en["energy_potential"] - (en["energy_potential_nonbonded"] + en["energy_potential_bonded"])) < 1e-9)
+    e.close()
+    e = MdEngine.from_workload(w)
+    e.compute_forces()
+    res["no_terms_zero"] = bool(e.energy()["energy_potential_bonded"] == 0.0)
+    # 2. out-of-range ids are an error
+    try:
+        e.set_bonded(np.array([[0, len(w["xyzq"])]], np.int32), np.array([[100.0, 1.0]], np.float32))
+        res["bad_id_rejected"] = False
+    except Exception:
+        res["bad_id_rejected"] = True
+    e.close()
+    # 3. C1: 216 flexible three-site waters, 40 NVE steps against the oracle with the same bonds
+    w = W.water_box_c1()
+    e = MdEngine.from_workload(w)
+    e.set_bonded(w["bonds"], w["bond_kr0"])
+    e.step(w["dt"], 40)
+    ref = O.md_run(w, 40, precision=64, with_bonds=True)
+    ok, worst, sc = trajectory_close(e.positions(), ref["xyzq"], w["xyzq"], w["box_ext"])
+    en = e.energy()
+    res.update(traj_ok=bool(ok), traj_worst=float(worst), density=float(en["density"]), e_bond=float(en["energy_bond"]))
+    e.close()
+    good = (res["force_err"] < 2 * FORCE_RTOL and res["energy_rel"] < 2e-5 and res["sum_ok"] and res["no_terms_zero"] and
+            res["bad_id_rejected"] and res["traj_ok"] and 0.9 < res["density"] < 1.1 and res["e_bond"] > 0)
+    print(json.dumps(res))
+    return 0 if good else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
