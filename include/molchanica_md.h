@@ -126,6 +126,13 @@ int mc_set_bonds(mc_ctx *ctx, int64_t m, const int32_t *pairs, const float *k_r0
 int mc_set_angles(mc_ctx *ctx, int64_t m, const int32_t *triples, const float *k_theta0);
 int mc_set_dihedrals(mc_ctx *ctx, int64_t m, const int32_t *quads, const float *pk_n_phase);
 
+/* Rigid three-site waters (the reference keeps its water rigid with SETTLE, README.md:239):
+ * triples[3m] = (O, H1, H2) atom ids; after every drift of mc_step the molecules are put back onto the
+ * triangle (d_oh, d_oh, d_hh) with the analytic SETTLE and their velocities corrected by the position change
+ * / dt.  Intramolecular pairs must be excluded (mc_set_exclusions); masses are those of mc_set_atoms.
+ * mc_energy.temperature then counts 3 degrees of freedom less per molecule.  Single-GPU handles; m = 0 clears. */
+int mc_set_rigid_waters(mc_ctx *ctx, int64_t m, const int32_t *triples, float d_oh, float d_hh, float m_o, float m_h);
+
 /* cfg.lj_cutoff / cfg.coulomb_cutoff (ui/panels/md.rs:260-261), Verlet skin, Coulomb form. */
 int mc_set_cutoffs(mc_ctx *ctx, float rc_lj, float rc_q, float skin, int coulomb_mode, float alpha);
 

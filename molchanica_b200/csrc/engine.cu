@@ -219,6 +219,7 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
     c->have_excl = false;
     c->have_p14 = false;
     c->n_bonds = c->n_angles = c->n_dihedrals = 0;
+    c->n_waters = 0;
     c->n_pairs_listed = 0;
     c->total_mass = 0.0;
     for (int64_t k = 0; k < n; ++k) {
@@ -346,6 +347,19 @@ extern "C" int mc_set_dihedrals(mc_ctx *c, int64_t m, const int32_t *quads, cons
     for (int64_t k = 0; k < m; ++k) prm[(size_t)k] = make_float4(pk_n_phase[3 * k], pk_n_phase[3 * k + 1], pk_n_phase[3 * k + 2], 0.f);
     MC_CUDA(c, c->dihedral_prm.ensure(prm.size()));
     if (m) MC_CUDA(c, cudaMemcpy(c->dihedral_prm.p, prm.data(), sizeof(float4) * (size_t)m, cudaMemcpyHostToDevice));
+    return MC_OK;
+}
+
+extern "C" int mc_set_rigid_waters(mc_ctx *c, int64_t m, const int32_t *triples, float d_oh, float d_hh, float m_o, float m_h) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, !c->comm_active, "mc_set_rigid_waters: constraints on a decomposed handle are not supported yet");
+    MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || triples), "mc_set_rigid_waters: bad arguments");
+    MC_REQUIRE(c, m == 0 || (d_oh > 0.f && d_hh > 0.f && d_hh < 2.f * d_oh && m_o > 0.f && m_h > 0.f),
+               "mc_set_rigid_waters: need 0 < d_hh < 2 d_oh and positive masses");
+    int rc = upload_terms<3, int4>(c, "mc_set_rigid_waters", m, triples, c->waters, &c->n_waters);
+    if (rc != MC_OK) { c->n_waters = 0; return rc; }
+    c->water_d_oh = d_oh; c->water_d_hh = d_hh; c->water_m_o = m_o; c->water_m_h = m_h;
     return MC_OK;
 }
 
@@ -740,6 +754,9 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
             }
             tr.stop();
         }
+        if (c->n_waters > 0)
+            launch_settle(c->n_waters, c->waters.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vel[c->cur].p, c->water_m_o,
+                          c->water_m_h, c->water_d_oh, c->water_d_hh, make_params(c), dt, st, &c->launches);
         c->steps_since_build++;
         bool rebuild = false;
         if (c->comm_active) {
@@ -932,7 +949,8 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
         out->density = out->volume > 0.0 ? c->total_mass * 1.66053907 / out->volume : 0.0;  // amu/A^3 -> g/cm^3
     }
     out->energy_kinetic = h[1] / (double)MC_ACCEL_CONV;
-    out->temperature = h[2] > 0 ? 2.0 * out->energy_kinetic / (3.0 * h[2] * MC_KB) : 0.0;
+    const double dof = 3.0 * h[2] - 3.0 * (double)c->n_waters;  // each rigid water removes three degrees of freedom
+    out->temperature = dof > 0 ? 2.0 * out->energy_kinetic / (dof * MC_KB) : 0.0;
     return MC_OK;
 }
 

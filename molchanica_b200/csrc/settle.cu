@@ -1,0 +1,64 @@
+// settle.cu -- rigid three-site water on the device: one thread per molecule applies the
+// analytic SETTLE of settle_terms.h to the positions kick_drift has just advanced and corrects the velocities
+// by (x_constrained - x_unconstrained) / dt, the leap-frog form of the constraint (the merged kicks of the
+// step loop make the velocity a half-step one).  The old positions are recovered as x' - v dt, and everything
+// is done relative to the oxygen's old position, so no extra position array is kept and fp32 cancellation
+// stays at the 1e-6 A level; each atom keeps its own periodic image (molecules may straddle the box edge).
+// HBM-bound and tiny: 3 x (16 + 16) B read and written per molecule.
+// STATUS: as bonded.cu -- arithmetic verified on the host against a converged fp64 SHAKE
+// (tests/test_settle_cpu.py), kernel not yet run on hardware (round-1 GPU budget spent).
+#include "settle.cuh"
+#include "settle_terms.h"
+
+namespace {
+
+__global__ void __launch_bounds__(128) settle_kernel(int n_w, const int4 *__restrict__ waters, const int *__restrict__ slot_of_orig,
+                                                      float4 *__restrict__ xyzq, float4 *__restrict__ vel, const SettleParams sp,
+                                                      const NbParams p, float dt) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_w) return;
+    const int4 ids = waters[w];
+    const int so = slot_of_orig[ids.x], s1 = slot_of_orig[ids.y], s2 = slot_of_orig[ids.z];
+    float4 xo = xyzq[so], x1 = xyzq[s1], x2 = xyzq[s2];
+    float4 vo = vel[so], v1 = vel[s1], v2 = vel[s2];
+    const float xo_[3] = {xo.x, xo.y, xo.z}, x1_[3] = {x1.x, x1.y, x1.z}, x2_[3] = {x2.x, x2.y, x2.z};
+    const float vo_[3] = {vo.x, vo.y, vo.z}, v1_[3] = {v1.x, v1.y, v1.z}, v2_[3] = {v2.x, v2.y, v2.z};
+    float b0[3], c0[3], a1[3], b1[3], c1[3], a3[3], b3[3], c3[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        // new relative vectors (minimum image), then back one drift: old H - old O
+        float db = x1_[a] - xo_[a], dc = x2_[a] - xo_[a];
+        if (p.periodic) {
+            db -= rintf(db * p.inv_ext[a]) * p.ext[a];
+            dc -= rintf(dc * p.inv_ext[a]) * p.ext[a];
+        }
+        a1[a] = vo_[a] * dt;
+        b0[a] = db - (v1_[a] - vo_[a]) * dt;
+        c0[a] = dc - (v2_[a] - vo_[a]) * dt;
+        b1[a] = b0[a] + v1_[a] * dt;
+        c1[a] = c0[a] + v2_[a] * dt;
+    }
+    mc_settle(sp, b0, c0, a1, b1, c1, a3, b3, c3);
+    const float inv_dt = 1.f / dt;
+    float da[3], db_[3], dc_[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { da[a] = a3[a] - a1[a]; db_[a] = b3[a] - b1[a]; dc_[a] = c3[a] - c1[a]; }
+    xo.x += da[0]; xo.y += da[1]; xo.z += da[2];
+    x1.x += db_[0]; x1.y += db_[1]; x1.z += db_[2];
+    x2.x += dc_[0]; x2.y += dc_[1]; x2.z += dc_[2];
+    vo.x += da[0] * inv_dt; vo.y += da[1] * inv_dt; vo.z += da[2] * inv_dt;
+    v1.x += db_[0] * inv_dt; v1.y += db_[1] * inv_dt; v1.z += db_[2] * inv_dt;
+    v2.x += dc_[0] * inv_dt; v2.y += dc_[1] * inv_dt; v2.z += dc_[2] * inv_dt;
+    xyzq[so] = xo; xyzq[s1] = x1; xyzq[s2] = x2;
+    vel[so] = vo; vel[s1] = v1; vel[s2] = v2;
+}
+
+}  // namespace
+
+void launch_settle(int n_w, const int4 *waters, const int *slot_of_orig, float4 *xyzq, float4 *vel, float m_o, float m_h,
+                   float d_oh, float d_hh, const NbParams &p, float dt, cudaStream_t st, int64_t *launches) {
+    if (n_w <= 0) return;
+    const SettleParams sp = mc_settle_params(m_o, m_h, d_oh, d_hh);
+    settle_kernel<<<div_up((size_t)n_w, 128), 128, 0, st>>>(n_w, waters, slot_of_orig, xyzq, vel, sp, p, dt);
+    *launches += 1;
+}

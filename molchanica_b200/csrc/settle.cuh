@@ -1,0 +1,7 @@
+// settle.cuh -- host-side launcher of settle.cu
+#pragma once
+#include "common.cuh"
+
+// waters: (O, H1, H2, -) original ids.  Constrains the positions kick_drift advanced by `dt` and corrects the velocities.
+void launch_settle(int n_w, const int4 *waters, const int *slot_of_orig, float4 *xyzq, float4 *vel, float m_o, float m_h,
+                   float d_oh, float d_hh, const NbParams &p, float dt, cudaStream_t st, int64_t *launches);

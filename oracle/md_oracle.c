@@ -583,6 +583,60 @@ double orc_kinetic(int n, const float *vel) {
     return ke / (double)ORC_ACCEL_CONV;
 }
 
+/* ---- rigid three-site water, fp64 SHAKE ------------------------------------------
+ * The reference keeps water rigid with SETTLE (README.md:239; the code is in the un-vendored `dynamics` crate ->
+ * parity unpinned).  The oracle solves the same constraint equations iteratively (SHAKE, Ryckaert et al. 1977,
+ * displacements along the OLD bond vectors, converged to 1e-13) -- an independent route to the positions the
+ * analytic SETTLE of the CUDA path produces.  Set once with orc_set_rigid_waters; orc_md_run then constrains
+ * after every drift and corrects the velocities by the position change / dt (leap-frog form). */
+static int g_nw = 0;
+static const int32_t *g_waters = NULL;
+static double g_doh = 0, g_dhh = 0;
+void orc_set_rigid_waters(int n, const int32_t *triples, float d_oh, float d_hh) {
+    g_nw = n; g_waters = triples; g_doh = d_oh; g_dhh = d_hh;
+}
+
+/* xold / xnew: n*4 floats; constrains xnew in place, adds (x'' - x')/dt to vel */
+void orc_shake_waters(const float *xold, float *xnew, float *vel, const float *ext, int periodic, float dt) {
+    for (int w = 0; w < g_nw; ++w) {
+        const int id[3] = {g_waters[3 * w], g_waters[3 * w + 1], g_waters[3 * w + 2]};
+        double r0[3][3], p[3][3], m[3];
+        for (int k = 0; k < 3; ++k) {
+            m[k] = 1.0 / (double)vel[4 * id[k] + 3];
+            for (int a = 0; a < 3; ++a) {
+                /* everything relative to the old oxygen, minimum image per atom */
+                double d0 = (double)xold[4 * id[k] + a] - (double)xold[4 * id[0] + a];
+                double d1 = (double)xnew[4 * id[k] + a] - (double)xold[4 * id[0] + a];
+                if (periodic) { d0 -= rint(d0 / (double)ext[a]) * (double)ext[a]; d1 -= rint(d1 / (double)ext[a]) * (double)ext[a]; }
+                r0[k][a] = d0; p[k][a] = d1;
+            }
+        }
+        double q[3][3];
+        memcpy(q, p, sizeof(q));
+        const int ci[3] = {0, 0, 1}, cj[3] = {1, 2, 2};
+        const double cd[3] = {g_doh, g_doh, g_dhh};
+        for (int it = 0; it < 1000; ++it) {
+            double worst = 0;
+            for (int c = 0; c < 3; ++c) {
+                int i = ci[c], j = cj[c];
+                double s[3], r[3], ss = 0, sr = 0;
+                for (int a = 0; a < 3; ++a) { s[a] = q[i][a] - q[j][a]; r[a] = r0[i][a] - r0[j][a]; ss += s[a] * s[a]; sr += s[a] * r[a]; }
+                double diff = cd[c] * cd[c] - ss;
+                if (fabs(diff) / (cd[c] * cd[c]) > worst) worst = fabs(diff) / (cd[c] * cd[c]);
+                double g = diff / (2.0 * sr * (1.0 / m[i] + 1.0 / m[j]));
+                for (int a = 0; a < 3; ++a) { q[i][a] += g * r[a] / m[i]; q[j][a] -= g * r[a] / m[j]; }
+            }
+            if (worst < 1e-13) break;
+        }
+        for (int k = 0; k < 3; ++k)
+            for (int a = 0; a < 3; ++a) {
+                double d = q[k][a] - p[k][a];
+                xnew[4 * id[k] + a] = (float)((double)xnew[4 * id[k] + a] + d);
+                vel[4 * id[k] + a] = (float)((double)vel[4 * id[k] + a] + d / (double)dt);
+            }
+    }
+}
+
 /*
  * Whole MD loop on the CPU (the CPU baseline and the C1 plumbing run): n_steps of velocity
  * Verlet with a Verlet list rebuilt when the largest displacement since the last build exceeds
@@ -633,7 +687,10 @@ int orc_md_run(int n, float *xyzq, float *vel, const uint16_t *type, int T, cons
         }
         if (step == n_steps) break;
         orc_kick(n, vel, f, 0.5f * dt);
+        float *xprev = NULL;
+        if (g_nw) { xprev = (float *)malloc(sizeof(float) * 4 * (size_t)n); memcpy(xprev, xyzq, sizeof(float) * 4 * (size_t)n); }
         float worst = orc_drift(n, xyzq, vel, dt, xref);
+        if (g_nw) { orc_shake_waters(xprev, xyzq, vel, ext, periodic, dt); free(xprev); }
         if (worst > 0.25f * skin * skin) need = 1;
     }
     if (forces_out) memcpy(forces_out, f, sizeof(float) * 4 * (size_t)n);

@@ -153,7 +153,7 @@ def forces(w, nbr, xyzq=None, precision=64, lj_on=True, coul_on=True, with_pairs
 
 
 def md_run(w, n_steps, precision=32, xyzq=None, vel=None, want_energies=False, ext_force=None,
-           with_bonds=False):
+           with_bonds=False, rigid_waters=None):
     """n_steps of velocity Verlet on the CPU. Returns dict(xyzq, vel, forces, rebuilds, energies)."""
     xyzq = np.array(w["xyzq"] if xyzq is None else xyzq, np.float32, copy=True)
     vel = np.array(w["vel"] if vel is None else vel, np.float32, copy=True)
@@ -177,7 +177,23 @@ def md_run(w, n_steps, precision=32, xyzq=None, vel=None, want_energies=False, e
     en = np.zeros((n_steps + 1, 4), np.float64) if want_energies else None
     fo = np.zeros((n, 4), np.float32)
     p = nb_params(w)
-    rb = lib().orc_md_run(C.c_int(n), _p(xyzq, C.c_float), _p(vel, C.c_float), _p(typ, C.c_uint16),
+    wt = None
+    if rigid_waters is not None:
+        # (triples, d_oh, d_hh): rigid three-site waters, constrained after every drift (orc_shake_waters)
+        wt = np.ascontiguousarray(rigid_waters[0], np.int32).reshape(-1, 3)
+        lib().orc_set_rigid_waters(C.c_int(len(wt)), _p(wt, C.c_int32), C.c_float(rigid_waters[1]), C.c_float(rigid_waters[2]))
+    try:
+        rb = _md_run_call(n, xyzq, vel, typ, tab, lo, ext, w, p, es, ei, p14, bonds, kr0, ef, n_steps, precision, en, fo)
+    finally:
+        if wt is not None:
+            lib().orc_set_rigid_waters(C.c_int(0), None, C.c_float(0), C.c_float(0))
+    if rb < 0:
+        raise RuntimeError("orc_md_run failed")
+    return dict(xyzq=xyzq, vel=vel, forces=fo, rebuilds=rb, energies=en)
+
+
+def _md_run_call(n, xyzq, vel, typ, tab, lo, ext, w, p, es, ei, p14, bonds, kr0, ef, n_steps, precision, en, fo):
+    return lib().orc_md_run(C.c_int(n), _p(xyzq, C.c_float), _p(vel, C.c_float), _p(typ, C.c_uint16),
                           C.c_int(tab.shape[0]), _p(tab, C.c_float), _p(lo, C.c_float), _p(ext, C.c_float),
                           C.c_int(int(w["periodic"])), C.byref(p), C.c_float(w["skin"]), _p(es, C.c_int32),
                           _p(ei, C.c_int32), C.c_int(0 if p14 is None else len(p14)), _p(p14, C.c_int32),
@@ -185,9 +201,6 @@ def md_run(w, n_steps, precision=32, xyzq=None, vel=None, want_energies=False, e
                           C.c_int(0 if bonds is None else len(bonds)), _p(bonds, C.c_int32), _p(kr0, C.c_float),
                           _p(ef, C.c_float), C.c_float(w["dt"]), C.c_int(n_steps), C.c_int(precision),
                           _p(en, C.c_double), _p(fo, C.c_float))
-    if rb < 0:
-        raise RuntimeError("orc_md_run failed")
-    return dict(xyzq=xyzq, vel=vel, forces=fo, rebuilds=rb, energies=en)
 
 
 def bonded(w, xyzq=None):

@@ -1,0 +1,115 @@
+"""Rigid three-site water without a GPU.  The SETTLE arithmetic the GPU kernel runs
+(molchanica_b200/csrc/settle_terms.h) is compiled for the host into a TEST library and must reproduce a converged
+fp64 SHAKE (same constraint equations, independent algorithm), keep the bond lengths and the centre of mass; the
+oracle's rigid-water MD (fp64 SHAKE inside orc_md_run) must hold the geometry and conserve energy."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from molchanica_b200 import workloads as W
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+D_OH, ANG = 0.9572, np.radians(104.52)
+D_HH = 2 * D_OH * np.sin(ANG / 2)
+M_O, M_H = 15.999, 1.008
+
+
+@pytest.fixture(scope="module")
+def host_math():
+    out = os.path.join(HERE, "cpp", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libsettle_math_host.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so,
+                        os.path.join(HERE, "cpp", "settle_math_host.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return C.CDLL(so)
+
+
+def _rand_waters(n, rng, sigma):
+    base = np.array([[0, 0, 0], [D_OH * np.sin(ANG / 2), D_OH * np.cos(ANG / 2), 0], [-D_OH * np.sin(ANG / 2), D_OH * np.cos(ANG / 2), 0]])
+    x0 = np.zeros((n, 3, 3))
+    for w in range(n):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        a, b, c, d = q
+        R = np.array([[1 - 2 * (c * c + d * d), 2 * (b * c - d * a), 2 * (b * d + c * a)],
+                      [2 * (b * c + d * a), 1 - 2 * (b * b + d * d), 2 * (c * d - b * a)],
+                      [2 * (b * d - c * a), 2 * (c * d + b * a), 1 - 2 * (b * b + c * c)]])
+        x0[w] = base @ R.T + rng.uniform(-30, 30, 3)
+    x0 = x0.astype(np.float32).astype(np.float64)
+    x1 = (x0 + rng.normal(0, sigma, (n, 3, 3))).astype(np.float32).astype(np.float64)
+    return x0, x1
+
+
+def _shake(x0, x1):
+    m = np.array([M_O, M_H, M_H])
+    out = x1.copy()
+    cons = [(0, 1, D_OH), (0, 2, D_OH), (1, 2, D_HH)]
+    for w in range(len(x0)):
+        p = out[w]
+        for _ in range(1000):
+            worst = 0.0
+            for i, j, d in cons:
+                s, r = p[i] - p[j], x0[w, i] - x0[w, j]
+                diff = d * d - s @ s
+                worst = max(worst, abs(diff) / (d * d))
+                g = diff / (2 * (s @ r) * (1 / m[i] + 1 / m[j]))
+                p[i] += g * r / m[i]
+                p[j] -= g * r / m[j]
+            if worst < 1e-14:
+                break
+    return out
+
+
+def _dists(p):
+    return np.stack([np.linalg.norm(p[:, 0] - p[:, 1], axis=1), np.linalg.norm(p[:, 0] - p[:, 2], axis=1),
+                     np.linalg.norm(p[:, 1] - p[:, 2], axis=1)], 1)
+
+
+@pytest.mark.parametrize("sigma", [0.002, 0.03, 0.08])
+def test_settle_reproduces_converged_shake(sigma, host_math):
+    """sigma: rms displacement per coordinate in one step [A]; 0.03 is already far more than a 2 fs step moves a hydrogen."""
+    rng = np.random.default_rng(int(sigma * 1e4))
+    n = 1500
+    x0, x1 = _rand_waters(n, rng, sigma)
+    a0 = np.ascontiguousarray(x0.reshape(n, 9), np.float32)
+    a1 = np.ascontiguousarray(x1.reshape(n, 9), np.float32)
+    out = np.zeros((n, 9), np.float32)
+    host_math.settle_host_eval(C.c_int64(n), a0.ctypes.data_as(C.c_void_p), a1.ctypes.data_as(C.c_void_p), C.c_float(M_O),
+                               C.c_float(M_H), C.c_float(D_OH), C.c_float(D_HH), out.ctypes.data_as(C.c_void_p))
+    o = out.reshape(n, 3, 3).astype(np.float64)
+    ref = _shake(x0, x1)
+    assert np.abs(_dists(ref) - [D_OH, D_OH, D_HH]).max() < 1e-12
+    assert np.abs(_dists(o) - [D_OH, D_OH, D_HH]).max() < 6e-6      # fp32 coordinates of magnitude 30 A: ulp 2e-6
+    assert np.abs(o - ref).max() < 6e-6
+    m = np.array([M_O, M_H, M_H])[None, :, None]
+    assert np.abs((o * m).sum(1) - (x1 * m).sum(1)).max() / (M_O + 2 * M_H) < 4e-6   # centre of mass untouched
+
+
+def test_oracle_rigid_water_md_holds_geometry_and_energy(oracle):
+    w = W.water_box_c1()
+    n = len(w["xyzq"])
+    triples = np.arange(n, dtype=np.int32).reshape(-1, 3)
+    w = dict(w, dt=0.001)
+    # the workload's waters are built with the TIP3P geometry
+    x = w["xyzq"][:, :3].astype(np.float64).reshape(-1, 3, 3)
+    ext = np.asarray(w["box_ext"], np.float64)
+
+    def geom(x):
+        d = lambda a, b: np.linalg.norm((a - b) - np.rint((a - b) / ext) * ext, axis=1)
+        return np.stack([d(x[:, 0], x[:, 1]), d(x[:, 0], x[:, 2]), d(x[:, 1], x[:, 2])], 1)
+    assert np.abs(geom(x) - [D_OH, D_OH, D_HH]).max() < 1e-4
+    r = oracle.md_run(w, 120, precision=64, want_energies=True, rigid_waters=(triples, D_OH, D_HH))
+    x = r["xyzq"][:, :3].astype(np.float64).reshape(-1, 3, 3)
+    assert np.abs(geom(x) - [D_OH, D_OH, D_HH]).max() < 1e-5
+    e = r["energies"]
+    tot = e[:, 0] + e[:, 1] + e[:, 3]
+    # the first constrained step removes the bond-direction components of the Maxwell-Boltzmann velocities; after
+    # that the total energy of the rigid-water NVE run stays put (|E_kin| ~ 390 kcal/mol at 300 K)
+    assert np.abs(tot[20:] - tot[20]).max() < 0.02 * e[20:, 3].mean(), (tot[20], tot[-1], e[20:, 3].mean())
+    # rigid molecules: relative velocity along every bond vanishes at the half step -> at integer steps it is small
+    assert r["rebuilds"] >= 1
