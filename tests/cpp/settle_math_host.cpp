@@ -22,3 +22,35 @@ void settle_host_eval(int64_t n, const float *x0, const float *x1, float m_o, fl
     }
 }
 }
+
+// The body of settle_kernel (molchanica_b200/csrc/settle.cu), line for line, on host arrays: x1 = positions after the
+// unconstrained drift (n x 9), v = velocities (n x 9), ext = periodic box (or NULL).  Updates x1 and v in place.
+extern "C" void settle_host_step(int64_t n, float *x1, float *v, const float *ext, float m_o, float m_h, float d_oh, float d_hh,
+                                 float dt) {
+    const SettleParams sp = mc_settle_params(m_o, m_h, d_oh, d_hh);
+    for (int64_t w = 0; w < n; ++w) {
+        float *xo_ = x1 + 9 * w, *x1_ = xo_ + 3, *x2_ = xo_ + 6;
+        float *vo_ = v + 9 * w, *v1_ = vo_ + 3, *v2_ = vo_ + 6;
+        float b0[3], c0[3], a1[3], b1[3], c1[3], a3[3], b3[3], c3[3];
+        for (int a = 0; a < 3; ++a) {
+            float db = x1_[a] - xo_[a], dc = x2_[a] - xo_[a];
+            if (ext) {
+                const float inv = 1.f / ext[a];
+                db -= rintf(db * inv) * ext[a];
+                dc -= rintf(dc * inv) * ext[a];
+            }
+            a1[a] = vo_[a] * dt;
+            b0[a] = db - (v1_[a] - vo_[a]) * dt;
+            c0[a] = dc - (v2_[a] - vo_[a]) * dt;
+            b1[a] = b0[a] + v1_[a] * dt;
+            c1[a] = c0[a] + v2_[a] * dt;
+        }
+        mc_settle(sp, b0, c0, a1, b1, c1, a3, b3, c3);
+        const float inv_dt = 1.f / dt;
+        for (int a = 0; a < 3; ++a) {
+            const float da = a3[a] - a1[a], db = b3[a] - b1[a], dc = c3[a] - c1[a];
+            xo_[a] += da; x1_[a] += db; x2_[a] += dc;
+            vo_[a] += da * inv_dt; v1_[a] += db * inv_dt; v2_[a] += dc * inv_dt;
+        }
+    }
+}

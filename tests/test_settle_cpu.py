@@ -90,6 +90,40 @@ def test_settle_reproduces_converged_shake(sigma, host_math):
     assert np.abs((o * m).sum(1) - (x1 * m).sum(1)).max() / (M_O + 2 * M_H) < 4e-6   # centre of mass untouched
 
 
+def test_kernel_body_recovers_old_positions_and_corrects_velocities(host_math):
+    """settle_host_step is the body of settle_kernel line for line: it gets only the drifted positions and the
+    velocities (old positions = x' - v dt), works across the periodic boundary, and must land on the SHAKE solution
+    with v'' = v + (x'' - x') / dt."""
+    rng = np.random.default_rng(11)
+    n, dt, L = 1200, 0.002, 25.0
+    x0, _ = _rand_waters(n, rng, 0.0)
+    x0 = (x0 - x0.min()) % L                      # atoms wrapped one by one: molecules straddle the box edge
+    v = rng.normal(0, 6.0, (n, 3, 3))             # A/ps: hot hydrogens, |v dt| ~ 0.012 A
+    x0 = x0.astype(np.float32).astype(np.float64)
+    v32 = v.astype(np.float32)
+    x1 = (x0.astype(np.float32) + v32 * np.float32(dt)).astype(np.float32)
+    # reference: unwrap each molecule about its oxygen, SHAKE in fp64, compare displacements
+    rel = x0 - x0[:, :1]
+    rel -= np.rint(rel / L) * L
+    u0 = x0[:, :1] + rel
+    u1 = u0 + v32.astype(np.float64) * dt
+    ref = _shake(u0, u1)
+    xs, vs = x1.reshape(n, 9).copy(), v32.reshape(n, 9).copy()
+    ext = np.full(3, L, np.float32)
+    host_math.settle_host_step(C.c_int64(n), xs.ctypes.data_as(C.c_void_p), vs.ctypes.data_as(C.c_void_p),
+                               ext.ctypes.data_as(C.c_void_p), C.c_float(M_O), C.c_float(M_H), C.c_float(D_OH), C.c_float(D_HH),
+                               C.c_float(dt))
+    moved = xs.reshape(n, 3, 3).astype(np.float64) - x1.astype(np.float64)
+    assert np.abs(moved - (ref - u1)).max() < 8e-6
+    dv = vs.reshape(n, 3, 3).astype(np.float64) - v32.astype(np.float64)
+    assert np.abs(dv - (ref - u1) / dt).max() < 8e-6 / dt
+    # the constrained velocities have no component along the bonds at the half step: d/dt |r_ij|^2 = 0 to first order
+    xn = xs.reshape(n, 3, 3).astype(np.float64)
+    r01 = xn[:, 0] - xn[:, 1]
+    r01 -= np.rint(r01 / L) * L
+    assert np.abs(np.linalg.norm(r01, axis=1) - D_OH).max() < 8e-6
+
+
 def test_oracle_rigid_water_md_holds_geometry_and_energy(oracle):
     w = W.water_box_c1()
     n = len(w["xyzq"])
