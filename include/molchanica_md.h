@@ -65,6 +65,7 @@ typedef struct {
     double energy_bond, energy_angle, energy_dihedral;  /* parts of energy_potential_bonded      */
     double volume;                      /* A^3 (periodic boxes, else 0)                          */
     double density;                     /* g/cm^3 from the atoms' masses (periodic boxes)        */
+    double energy_pme;                  /* SPME reciprocal + self + excluded-pair correction (part of nonbonded) */
 } mc_energy;
 
 /* Counters for the caller / benchmarks.  The *_ms_sum fields accumulate CUDA-event durations
@@ -125,6 +126,13 @@ int mc_set_pairs14(mc_ctx *ctx, int64_t m, const int32_t *pairs, float scale_lj,
 int mc_set_bonds(mc_ctx *ctx, int64_t m, const int32_t *pairs, const float *k_r0);
 int mc_set_angles(mc_ctx *ctx, int64_t m, const int32_t *triples, const float *k_theta0);
 int mc_set_dihedrals(mc_ctx *ctx, int64_t m, const int32_t *quads, const float *pk_n_phase);
+
+/* SPME reciprocal space (the reference's electrostatics, README.md:240): with coulomb_mode =
+ * MC_COULOMB_ERFC the pair kernel evaluates erfc(alpha r)/r; a k1 x k2 x k3 grid (order-4 B-splines, cuFFT) adds
+ * the reciprocal sum, the self term and the erf(alpha r)/r correction of the excluded pairs to every force
+ * evaluation.  Periodic boxes, single-GPU handles; 0, 0, 0 switches it off.  About one grid point per Angstrom with
+ * alpha = 0.35 gives forces within ~1e-3 of the exact Ewald sum. */
+int mc_set_pme(mc_ctx *ctx, int k1, int k2, int k3);
 
 /* Rigid three-site waters (the reference keeps its water rigid with SETTLE, README.md:239):
  * triples[3m] = (O, H1, H2) atom ids; after every drift of mc_step the molecules are put back onto the

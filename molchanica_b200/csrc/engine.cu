@@ -106,6 +106,7 @@ extern "C" int mc_destroy(mc_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     comm_destroy(c);
+    pme_release(&c->pme);
     for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (c->ev_step_a) {
         cudaEventDestroy(c->ev_step_a); cudaEventDestroy(c->ev_step_b);
@@ -222,6 +223,8 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
     c->n_waters = 0;
     c->n_pairs_listed = 0;
     c->total_mass = 0.0;
+    c->pme.self_q2 = 0.0;
+    for (int64_t k = 0; k < n; ++k) c->pme.self_q2 += (double)xyzq[k].w * (double)xyzq[k].w;
     for (int64_t k = 0; k < n; ++k) {
         const float im = vel_invmass ? vel_invmass[k].w : 1.f;
         if (im > 0.f) c->total_mass += 1.0 / (double)im;
@@ -347,6 +350,18 @@ extern "C" int mc_set_dihedrals(mc_ctx *c, int64_t m, const int32_t *quads, cons
     for (int64_t k = 0; k < m; ++k) prm[(size_t)k] = make_float4(pk_n_phase[3 * k], pk_n_phase[3 * k + 1], pk_n_phase[3 * k + 2], 0.f);
     MC_CUDA(c, c->dihedral_prm.ensure(prm.size()));
     if (m) MC_CUDA(c, cudaMemcpy(c->dihedral_prm.p, prm.data(), sizeof(float4) * (size_t)m, cudaMemcpyHostToDevice));
+    return MC_OK;
+}
+
+extern "C" int mc_set_pme(mc_ctx *c, int k1, int k2, int k3) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, !c->comm_active, "mc_set_pme: reciprocal space on a decomposed handle is not supported yet");
+    MC_REQUIRE(c, (k1 == 0 && k2 == 0 && k3 == 0) || c->periodic, "mc_set_pme: needs a periodic box");
+    const char *msg = "";
+    int rc = pme_configure(&c->pme, k1, k2, k3, c->st, &msg);
+    if (rc != MC_OK) return fail(c, rc, std::string("mc_set_pme: ") + msg);
+    c->forces_valid = false;
     return MC_OK;
 }
 
@@ -649,6 +664,14 @@ int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs) {
         MC_CUDA(c, c->bonded_e.ensure(4));
         launch_bonded(t, c->slot_of_orig.p, L.xyzq, L.p, c->force.p, c->bonded_e.p, want_energy, c->st, &c->launches);
     }
+    if (c->pme.planned && c->periodic && L.coul == MC_COULOMB_ERFC) {
+        const char *msg = "";
+        int rc = pme_launch(&c->pme, (int)c->n, L.xyzq, c->lo, c->ext, c->alpha, c->force.p, want_energy, c->st, &c->launches, &msg);
+        if (rc != MC_OK) return fail(c, rc, std::string("SPME: ") + msg);
+        if (c->have_excl)
+            pme_launch_exclusions(&c->pme, (int)c->n, L.xyzq, c->orig[c->cur].p, c->slot_of_orig.p, c->excl_start.p, c->excl_idx.p, L.p,
+                                  c->force.p, want_energy, c->st, &c->launches);
+    }
     MC_CUDA(c, cudaGetLastError());
     c->forces_valid = true;
     c->forces_have_energy = want_energy;
@@ -942,6 +965,13 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
         MC_CUDA(c, cudaMemcpy(hb, c->bonded_e.p, sizeof(hb), cudaMemcpyDeviceToHost));
         out->energy_bond = hb[0]; out->energy_angle = hb[1]; out->energy_dihedral = hb[2];
         out->energy_potential_bonded = hb[0] + hb[1] + hb[2];
+    }
+    if (c->pme.planned && c->periodic && c->coul_mode == MC_COULOMB_ERFC && !c->coul_disabled) {
+        double hp[2];
+        MC_CUDA(c, cudaMemcpy(hp, c->pme.energy, sizeof(hp), cudaMemcpyDeviceToHost));
+        // reciprocal sum + self term -alpha/sqrt(pi) sum q^2 + erf correction of the excluded pairs
+        out->energy_pme = hp[0] - (double)c->alpha * 0.5641895835477563 * c->pme.self_q2 + (c->have_excl ? hp[1] : 0.0);
+        out->energy_potential_nonbonded += out->energy_pme;
     }
     out->energy_potential = out->energy_potential_nonbonded + out->energy_potential_bonded;
     if (c->periodic) {

@@ -7,6 +7,7 @@
 #include "halo_sync.cuh"
 #include "bonded.cuh"
 #include "settle.cuh"
+#include "pme.cuh"
 
 template <typename T>
 struct DevBuf {
@@ -115,6 +116,7 @@ struct mc_ctx {
     DevBuf<int4> angles, dihedrals;
     DevBuf<float4> dihedral_prm;
     DevBuf<double> bonded_e;   // {E_bond, E_angle, E_dihedral} of the last evaluation that asked for energies
+    PmeState pme;              // SPME reciprocal space (pme.cu); pme.planned == false: off
     int n_waters = 0;          // rigid three-site waters (settle.cu)
     DevBuf<int4> waters;
     float water_m_o = 0, water_m_h = 0, water_d_oh = 0, water_d_hh = 0;

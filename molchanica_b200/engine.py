@@ -109,6 +109,9 @@ class MdEngine:
         m, i, p = pair(dihedrals, dihedral_prm, 4)
         self._chk(self._L.mc_set_dihedrals(self._h, m, _ptr(i), _ptr(p)))
 
+    def set_pme(self, k1, k2, k3):
+        self._chk(self._L.mc_set_pme(self._h, int(k1), int(k2), int(k3)))
+
     def set_rigid_waters(self, triples, d_oh, d_hh, m_o=15.999, m_h=1.008):
         t = None if triples is None or len(triples) == 0 else np.ascontiguousarray(triples, np.int32).reshape(-1, 3)
         self._chk(self._L.mc_set_rigid_waters(self._h, 0 if t is None else len(t), _ptr(t), d_oh, d_hh, m_o, m_h))
