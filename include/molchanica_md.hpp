@@ -83,6 +83,11 @@ struct MdSystem {
     // bonded terms, Amber forms (mc_set_bonds / mc_set_angles / mc_set_dihedrals); empty = none
     std::vector<int32_t> bonds, angles, dihedrals;           // 2 / 3 / 4 atom ids per term
     std::vector<float> bond_k_r0, angle_k_theta0, dihedral_pk_n_phase;  // 2 / 2 / 3 parameters per term
+    // rigid three-site waters (mc_set_rigid_waters): (O, H1, H2) ids; the reference's md.water (sol_shrinking_box.rs:605-613)
+    std::vector<int32_t> rigid_waters;
+    float water_d_oh = 0.9572f, water_d_hh = 1.5139f, water_m_o = 15.999f, water_m_h = 1.008f;
+    // SPME grid (mc_set_pme), 0 = off; used with CoulombMode::EwaldRealSpace
+    int pme_grid[3] = {0, 0, 0};
 };
 
 struct SnapshotEnergyData {  // src/md/mod.rs:1242-1245, ui/panels/md_viewer.rs:202-256
@@ -127,6 +132,10 @@ class MdState {
         if (!sys.angles.empty()) md.chk(mc_set_angles(md.ctx_, (int64_t)sys.angles.size() / 3, sys.angles.data(), sys.angle_k_theta0.data()));
         if (!sys.dihedrals.empty())
             md.chk(mc_set_dihedrals(md.ctx_, (int64_t)sys.dihedrals.size() / 4, sys.dihedrals.data(), sys.dihedral_pk_n_phase.data()));
+        if (!sys.rigid_waters.empty())
+            md.chk(mc_set_rigid_waters(md.ctx_, (int64_t)sys.rigid_waters.size() / 3, sys.rigid_waters.data(), sys.water_d_oh,
+                                       sys.water_d_hh, sys.water_m_o, sys.water_m_h));
+        if (sys.pme_grid[0] > 0) md.chk(mc_set_pme(md.ctx_, sys.pme_grid[0], sys.pme_grid[1], sys.pme_grid[2]));
         return md;
     }
 

@@ -57,7 +57,6 @@ __device__ __forceinline__ void pair_term(const float4 xi, const float4 xj, cons
     const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
     // branch-free LJ: the arithmetic runs for every listed pair and the cutoff selects the result (one FSEL
     // instead of a predicated block that re-materialises its constants); lj_on == false arrives as rc2 < 0
-#ifndef MC_LJ_PREDICATED
     const float ir2 = rcp_approx(r2);
     const float s2 = lj.x * ir2;
     const float s6 = s2 * s2 * s2;
@@ -65,16 +64,6 @@ __device__ __forceinline__ void pair_term(const float4 xi, const float4 xj, cons
     float f = in_lj ? lj.y * s6 * __fmaf_rn(2.f, s6, -1.f) * ir2 : 0.f;
     float e = 0.f;
     if (ENERGY) e = in_lj ? lj.y * (1.f / 6.f) * s6 * (s6 - 1.f) : 0.f;
-#else
-    float f = 0.f, e = 0.f;
-    if (r2 < rc2_lj) {
-        const float ir2 = rcp_approx(r2);
-        const float s2 = lj.x * ir2;
-        const float s6 = s2 * s2 * s2;
-        f = lj.y * s6 * __fmaf_rn(2.f, s6, -1.f) * ir2;
-        if (ENERGY) e = lj.y * (1.f / 6.f) * s6 * (s6 - 1.f);
-    }
-#endif
     if (COUL != MC_COULOMB_NONE) {
         if (r2 < p.rc2_q) {
             const float qq = xi.w * xj.w;
