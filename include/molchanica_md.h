@@ -47,6 +47,9 @@ extern "C" {
 #define MC_COULOMB_PLAIN 1  /* q_i q_j /(r^2 + 1e-6), truncated at rc_q (src/cuda/util.cu:54-63) */
 #define MC_COULOMB_ERFC 2   /* Ewald real-space erfc(alpha r)/r (util.cu:15-18 INV_SQRT_PI)       */
 
+#define MC_THERMOSTAT_NONE 0
+#define MC_THERMOSTAT_LANGEVIN 1  /* Langevin dynamics (one of the reference's thermostats, README.md:238)      */
+
 #define MC_FLAG_STATIC 1u   /* AtomDynamics.static_ : exerts forces, never moves (src/md/mod.rs:843-852) */
 
 typedef struct mc_ctx mc_ctx;
@@ -126,6 +129,12 @@ int mc_set_pairs14(mc_ctx *ctx, int64_t m, const int32_t *pairs, float scale_lj,
 int mc_set_bonds(mc_ctx *ctx, int64_t m, const int32_t *pairs, const float *k_r0);
 int mc_set_angles(mc_ctx *ctx, int64_t m, const int32_t *triples, const float *k_theta0);
 int mc_set_dihedrals(mc_ctx *ctx, int64_t m, const int32_t *quads, const float *pk_n_phase);
+
+/* Thermostat.  MC_THERMOSTAT_LANGEVIN: after the drift (and constraints) of every step the
+ * velocities get the Ornstein-Uhlenbeck update v <- c1 v + sqrt(1 - c1^2) sqrt(kT/m) xi, c1 = exp(-gamma dt)
+ * (splitting B A O B).  The noise is Philox4x32-10 keyed by (seed, atom id, step count since this call): it does
+ * not depend on the engine's internal atom order.  Static atoms are left alone.  Single-GPU handles. */
+int mc_set_thermostat(mc_ctx *ctx, int kind, float temperature_k, float gamma_per_ps, uint64_t seed);
 
 /* SPME reciprocal space (the reference's electrostatics, README.md:240): with coulomb_mode =
  * MC_COULOMB_ERFC the pair kernel evaluates erfc(alpha r)/r; a k1 x k2 x k3 grid (order-4 B-splines, cuFFT) adds

@@ -353,6 +353,19 @@ extern "C" int mc_set_dihedrals(mc_ctx *c, int64_t m, const int32_t *quads, cons
     return MC_OK;
 }
 
+extern "C" int mc_set_thermostat(mc_ctx *c, int kind, float temperature_k, float gamma_per_ps, uint64_t seed) {
+    if (!c) return MC_E_INVALID;
+    MC_REQUIRE(c, kind == MC_THERMOSTAT_NONE || kind == MC_THERMOSTAT_LANGEVIN, "mc_set_thermostat: unknown kind");
+    MC_REQUIRE(c, !c->comm_active || kind == MC_THERMOSTAT_NONE, "mc_set_thermostat: thermostats on a decomposed handle are not supported yet");
+    MC_REQUIRE(c, kind == MC_THERMOSTAT_NONE || (temperature_k >= 0.f && gamma_per_ps >= 0.f), "mc_set_thermostat: negative temperature or friction");
+    c->langevin = kind == MC_THERMOSTAT_LANGEVIN;
+    c->lgv_temperature = temperature_k;
+    c->lgv_gamma = gamma_per_ps;
+    c->lgv_seed = seed;
+    c->lgv_step = 0;
+    return MC_OK;
+}
+
 extern "C" int mc_set_pme(mc_ctx *c, int k1, int k2, int k3) {
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);
@@ -780,6 +793,13 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         if (c->n_waters > 0)
             launch_settle(c->n_waters, c->waters.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vel[c->cur].p, c->water_m_o,
                           c->water_m_h, c->water_d_oh, c->water_d_hh, make_params(c), dt, st, &c->launches);
+        if (c->langevin) {
+            const float c1 = std::exp(-c->lgv_gamma * dt);
+            const size_t r0 = (size_t)c->row0;
+            launch_langevin_ou((int)c->n_rows_sorted(), c->vel[c->cur].p + r0, c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c1,
+                               std::sqrt(std::max(0.f, 1.f - c1 * c1)), (float)MC_KB * c->lgv_temperature, c->lgv_seed, c->lgv_step++,
+                               st, &c->launches);
+        }
         c->steps_since_build++;
         bool rebuild = false;
         if (c->comm_active) {

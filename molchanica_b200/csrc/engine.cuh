@@ -116,6 +116,9 @@ struct mc_ctx {
     DevBuf<int4> angles, dihedrals;
     DevBuf<float4> dihedral_prm;
     DevBuf<double> bonded_e;   // {E_bond, E_angle, E_dihedral} of the last evaluation that asked for energies
+    bool langevin = false;     // Langevin thermostat (integrate.cu langevin_ou_kernel)
+    float lgv_temperature = 300.f, lgv_gamma = 1.f;
+    uint64_t lgv_seed = 0, lgv_step = 0;
     PmeState pme;              // SPME reciprocal space (pme.cu); pme.planned == false: off
     int n_waters = 0;          // rigid three-site waters (settle.cu)
     DevBuf<int4> waters;

@@ -16,6 +16,9 @@ void launch_kick_drift(int n_rows, float4 *xyzq, float4 *vel, const float4 *forc
 void launch_kick_drift_halo(int n_rows, float4 *xyzq, float4 *vel, const float4 *force, const float *ext_force,
                             const int *orig, const uint8_t *flags, const float4 *xref, float kick, float drift,
                             float max_disp, int *rebuild_flag, const HaloPush &hp, cudaStream_t st, int64_t *launches);
+// Langevin O step: v <- c1 v + c2 sqrt(kT/m) xi with Philox noise keyed by (seed, original atom id, step)
+void launch_langevin_ou(int n_rows, float4 *vel, const int *orig, const uint8_t *flags, float c1, float c2, float kT, uint64_t seed,
+                        uint64_t step, cudaStream_t st, int64_t *launches);
 // original-order <-> cell-order copies
 void launch_gather_to_orig(int n, const float4 *sorted, const int *orig, float4 *out, cudaStream_t st, int64_t *launches);
 void launch_scatter_from_orig(int n, const float4 *in_orig, const int *orig, float4 *sorted, int keep_w, cudaStream_t st,

@@ -109,6 +109,10 @@ class MdEngine:
         m, i, p = pair(dihedrals, dihedral_prm, 4)
         self._chk(self._L.mc_set_dihedrals(self._h, m, _ptr(i), _ptr(p)))
 
+    def set_thermostat(self, kind, temperature_k=300.0, gamma_per_ps=1.0, seed=0):
+        """kind: 0 = none, 1 = Langevin (mc_set_thermostat)."""
+        self._chk(self._L.mc_set_thermostat(self._h, int(kind), temperature_k, gamma_per_ps, int(seed)))
+
     def set_pme(self, k1, k2, k3):
         self._chk(self._L.mc_set_pme(self._h, int(k1), int(k2), int(k3)))
 

@@ -637,6 +637,57 @@ void orc_shake_waters(const float *xold, float *xnew, float *vel, const float *e
     }
 }
 
+/* ---- Langevin thermostat, fp64 O step with counter-based noise -------------------------
+ * v <- c1 v + sqrt(1 - c1^2) sqrt(kT/m) xi after the drift (and constraints) of every step.  xi comes from
+ * Philox4x32-10 (Salmon et al., SC'11; this is an implementation of the published algorithm written
+ * independently of molchanica_b200/csrc/langevin_terms.h and pinned by its known-answer vectors) keyed by
+ * (seed, atom id, step), Box-Muller in double on the same 24-bit uniforms the CUDA path uses. */
+static int g_lgv = 0;
+static double g_lgv_kT = 0, g_lgv_gamma = 0;
+static uint64_t g_lgv_seed = 0, g_lgv_step = 0;
+void orc_set_langevin(int on, float temperature_k, float gamma_per_ps, uint64_t seed) {
+    g_lgv = on; g_lgv_kT = 0.0019872041 * (double)temperature_k; g_lgv_gamma = gamma_per_ps; g_lgv_seed = seed; g_lgv_step = 0;
+}
+
+void orc_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]}, k[2] = {key[0], key[1]};
+    for (int round = 0; round < 10; ++round) {
+        uint64_t lo_prod = (uint64_t)c[0] * 0xD2511F53ull, hi_prod = (uint64_t)c[2] * 0xCD9E8D57ull;
+        uint32_t t[4];
+        t[0] = (uint32_t)(hi_prod >> 32) ^ c[1] ^ k[0];
+        t[1] = (uint32_t)(hi_prod & 0xffffffffull);
+        t[2] = (uint32_t)(lo_prod >> 32) ^ c[3] ^ k[1];
+        t[3] = (uint32_t)(lo_prod & 0xffffffffull);
+        memcpy(c, t, sizeof(c));
+        k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+    }
+    memcpy(out, c, 4 * sizeof(uint32_t));
+}
+
+void orc_langevin_normals(uint64_t seed, uint32_t atom, uint64_t step, double *xi) {
+    uint32_t ctr[4] = {atom, (uint32_t)(step & 0xffffffffull), (uint32_t)(step >> 32), 0}, key[2] = {(uint32_t)(seed & 0xffffffffull), (uint32_t)(seed >> 32)}, r[4];
+    orc_philox4x32_10(ctr, key, r);
+    double u[4];
+    for (int j = 0; j < 4; ++j) u[j] = ((double)(r[j] >> 8) + 1.0) / 16777216.0;
+    double ra = sqrt(-2.0 * log(u[0])), rb = sqrt(-2.0 * log(u[2]));
+    xi[0] = ra * cos(6.283185307179586 * u[1]);
+    xi[1] = ra * sin(6.283185307179586 * u[1]);
+    xi[2] = rb * cos(6.283185307179586 * u[3]);
+}
+
+static void orc_langevin_step(int n, float *vel, float dt) {
+    const double c1 = exp(-g_lgv_gamma * (double)dt), c2 = sqrt(1.0 - c1 * c1);
+    for (int i = 0; i < n; ++i) {
+        const double im = vel[4 * i + 3];
+        if (im <= 0) continue;
+        double xi[3];
+        orc_langevin_normals(g_lgv_seed, (uint32_t)i, g_lgv_step, xi);
+        const double s = c2 * sqrt(g_lgv_kT * im * 418.4);
+        for (int a = 0; a < 3; ++a) vel[4 * i + a] = (float)(c1 * (double)vel[4 * i + a] + s * xi[a]);
+    }
+    ++g_lgv_step;
+}
+
 /*
  * Whole MD loop on the CPU (the CPU baseline and the C1 plumbing run): n_steps of velocity
  * Verlet with a Verlet list rebuilt when the largest displacement since the last build exceeds
@@ -691,6 +742,7 @@ int orc_md_run(int n, float *xyzq, float *vel, const uint16_t *type, int T, cons
         if (g_nw) { xprev = (float *)malloc(sizeof(float) * 4 * (size_t)n); memcpy(xprev, xyzq, sizeof(float) * 4 * (size_t)n); }
         float worst = orc_drift(n, xyzq, vel, dt, xref);
         if (g_nw) { orc_shake_waters(xprev, xyzq, vel, ext, periodic, dt); free(xprev); }
+        if (g_lgv) orc_langevin_step(n, vel, dt);
         if (worst > 0.25f * skin * skin) need = 1;
     }
     if (forces_out) memcpy(forces_out, f, sizeof(float) * 4 * (size_t)n);
