@@ -150,6 +150,14 @@ int mc_set_pme(mc_ctx *ctx, int k1, int k2, int k3);
  * mc_energy.temperature then counts 3 degrees of freedom less per molecule.  Single-GPU handles; m = 0 clears. */
 int mc_set_rigid_waters(mc_ctx *ctx, int64_t m, const int32_t *triples, float d_oh, float d_hh, float m_o, float m_h);
 
+/* Virtual sites of four-site water (OPC / TIP4P; the reference's md.water {o, h0, h1, m},
+ * properties/sol_shrinking_box.rs:605-613): quads[4m] = (M, O, H1, H2) atom ids, M = O + a (H1 - O) + b (H2 - O).
+ * M is an atom of the system with inverse mass 0 and MC_FLAG_STATIC (it carries the charge); after every drift
+ * (and SETTLE) of mc_step it is placed again, and after every force evaluation its force is handed to the three
+ * parents (a, b and 1 - a - b) and zeroed.  The caller places M consistently in mc_set_atoms and excludes the
+ * intramolecular pairs.  Single-GPU handles; m = 0 clears. */
+int mc_set_virtual_sites(mc_ctx *ctx, int64_t m, const int32_t *quads, float a, float b);
+
 /* cfg.lj_cutoff / cfg.coulomb_cutoff (ui/panels/md.rs:260-261), Verlet skin, Coulomb form. */
 int mc_set_cutoffs(mc_ctx *ctx, float rc_lj, float rc_q, float skin, int coulomb_mode, float alpha);
 

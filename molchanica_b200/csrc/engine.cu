@@ -221,6 +221,7 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
     c->have_p14 = false;
     c->n_bonds = c->n_angles = c->n_dihedrals = 0;
     c->n_waters = 0;
+    c->n_vsites = 0;
     c->n_pairs_listed = 0;
     c->total_mass = 0.0;
     c->pme.self_q2 = 0.0;
@@ -350,6 +351,17 @@ extern "C" int mc_set_dihedrals(mc_ctx *c, int64_t m, const int32_t *quads, cons
     for (int64_t k = 0; k < m; ++k) prm[(size_t)k] = make_float4(pk_n_phase[3 * k], pk_n_phase[3 * k + 1], pk_n_phase[3 * k + 2], 0.f);
     MC_CUDA(c, c->dihedral_prm.ensure(prm.size()));
     if (m) MC_CUDA(c, cudaMemcpy(c->dihedral_prm.p, prm.data(), sizeof(float4) * (size_t)m, cudaMemcpyHostToDevice));
+    return MC_OK;
+}
+
+extern "C" int mc_set_virtual_sites(mc_ctx *c, int64_t m, const int32_t *quads, float a, float b) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, !c->comm_active, "mc_set_virtual_sites: virtual sites on a decomposed handle are not supported yet");
+    MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || quads), "mc_set_virtual_sites: bad arguments");
+    int rc = upload_terms<4, int4>(c, "mc_set_virtual_sites", m, quads, c->vsites, &c->n_vsites);
+    if (rc != MC_OK) { c->n_vsites = 0; return rc; }
+    c->vsite_a = a; c->vsite_b = b;
     return MC_OK;
 }
 
@@ -685,6 +697,8 @@ int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs) {
             pme_launch_exclusions(&c->pme, (int)c->n, L.xyzq, c->orig[c->cur].p, c->slot_of_orig.p, c->excl_start.p, c->excl_idx.p, L.p,
                                   c->force.p, want_energy, c->st, &c->launches);
     }
+    if (c->n_vsites > 0)
+        launch_vsite_spread(c->n_vsites, c->vsites.p, c->slot_of_orig.p, c->force.p, c->vsite_a, c->vsite_b, c->st, &c->launches);
     MC_CUDA(c, cudaGetLastError());
     c->forces_valid = true;
     c->forces_have_energy = want_energy;
@@ -793,6 +807,9 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         if (c->n_waters > 0)
             launch_settle(c->n_waters, c->waters.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vel[c->cur].p, c->water_m_o,
                           c->water_m_h, c->water_d_oh, c->water_d_hh, make_params(c), dt, st, &c->launches);
+        if (c->n_vsites > 0)
+            launch_vsite_construct(c->n_vsites, c->vsites.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vsite_a, c->vsite_b,
+                                   make_params(c), st, &c->launches);
         if (c->langevin) {
             const float c1 = std::exp(-c->lgv_gamma * dt);
             const size_t r0 = (size_t)c->row0;

@@ -123,6 +123,9 @@ struct mc_ctx {
     int n_waters = 0;          // rigid three-site waters (settle.cu)
     DevBuf<int4> waters;
     float water_m_o = 0, water_m_h = 0, water_d_oh = 0, water_d_hh = 0;
+    int n_vsites = 0;          // virtual sites of four-site water (settle.cu)
+    DevBuf<int4> vsites;
+    float vsite_a = 0, vsite_b = 0;
     double total_mass = 0.0;   // amu, from the inverse masses handed to mc_set_atoms (density of the snapshot)
 
     // asynchronous snapshots (mc_snapshot_begin / mc_snapshot_wait): double-buffered staging + a copy stream
@@ -176,7 +179,7 @@ struct mc_ctx {
         d_rec_meta.release(); d_lig_meta.release();
         for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_ids[b].release(); }
         bonds.release(); bond_kr0.release(); angle_kt0.release(); angles.release(); dihedrals.release(); dihedral_prm.release();
-        bonded_e.release(); waters.release();
+        bonded_e.release(); waters.release(); vsites.release();
     }
 
     // resolve the CUDA-event pairs recorded since the last call (stream must be idle)

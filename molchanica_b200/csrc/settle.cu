@@ -9,6 +9,7 @@
 // (tests/test_settle_cpu.py), kernel not yet run on hardware (round-1 GPU budget spent).
 #include "settle.cuh"
 #include "settle_terms.h"
+#include "vsite_terms.h"
 
 namespace {
 
@@ -53,7 +54,64 @@ __global__ void __launch_bounds__(128) settle_kernel(int n_w, const int4 *__rest
     vel[so] = vo; vel[s1] = v1; vel[s2] = v2;
 }
 
+// Virtual sites (vsite_terms.h): one thread per site.  construct: after the parents have their final positions of
+// the step; spread: after every force of the evaluation has been accumulated, before the next kick.  The site is a
+// static atom to the integrator (inverse mass 0), carries charge / LJ like any atom in the pair kernel.
+__global__ void __launch_bounds__(128) vsite_construct_kernel(int n_v, const int4 *__restrict__ sites, const int *__restrict__ slot_of_orig,
+                                                               float4 *__restrict__ xyzq, float a, float b, const NbParams p) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_v) return;
+    const int4 ids = sites[v];
+    const int sm = slot_of_orig[ids.x], so = slot_of_orig[ids.y], s1 = slot_of_orig[ids.z], s2 = slot_of_orig[ids.w];
+    const float4 xo = xyzq[so], x1 = xyzq[s1], x2 = xyzq[s2];
+    const float o[3] = {xo.x, xo.y, xo.z};
+    float d1[3] = {x1.x - xo.x, x1.y - xo.y, x1.z - xo.z}, d2[3] = {x2.x - xo.x, x2.y - xo.y, x2.z - xo.z}, m[3];
+    if (p.periodic) {
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            d1[x] -= rintf(d1[x] * p.inv_ext[x]) * p.ext[x];
+            d2[x] -= rintf(d2[x] * p.inv_ext[x]) * p.ext[x];
+        }
+    }
+    mc_vsite_position(o, d1, d2, a, b, m);
+    float4 xm = xyzq[sm];
+    xm.x = m[0]; xm.y = m[1]; xm.z = m[2];
+    xyzq[sm] = xm;
+}
+
+__global__ void __launch_bounds__(128) vsite_spread_kernel(int n_v, const int4 *__restrict__ sites, const int *__restrict__ slot_of_orig,
+                                                            float4 *__restrict__ force, float a, float b) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_v) return;
+    const int4 ids = sites[v];
+    const int sm = slot_of_orig[ids.x], so = slot_of_orig[ids.y], s1 = slot_of_orig[ids.z], s2 = slot_of_orig[ids.w];
+    float4 fm4 = force[sm];
+    const float fm[3] = {fm4.x, fm4.y, fm4.z};
+    float fo[3], f1[3], f2[3];
+    mc_vsite_spread(fm, a, b, fo, f1, f2);
+    // every parent belongs to exactly one site: plain read-modify-write
+    float4 t = force[so]; t.x += fo[0]; t.y += fo[1]; t.z += fo[2]; force[so] = t;
+    t = force[s1]; t.x += f1[0]; t.y += f1[1]; t.z += f1[2]; force[s1] = t;
+    t = force[s2]; t.x += f2[0]; t.y += f2[1]; t.z += f2[2]; force[s2] = t;
+    fm4.x = fm4.y = fm4.z = 0.f;   // the energy row sum in .w stays
+    force[sm] = fm4;
+}
+
 }  // namespace
+
+void launch_vsite_construct(int n_v, const int4 *sites, const int *slot_of_orig, float4 *xyzq, float a, float b, const NbParams &p,
+                            cudaStream_t st, int64_t *launches) {
+    if (n_v <= 0) return;
+    vsite_construct_kernel<<<div_up((size_t)n_v, 128), 128, 0, st>>>(n_v, sites, slot_of_orig, xyzq, a, b, p);
+    *launches += 1;
+}
+
+void launch_vsite_spread(int n_v, const int4 *sites, const int *slot_of_orig, float4 *force, float a, float b, cudaStream_t st,
+                         int64_t *launches) {
+    if (n_v <= 0) return;
+    vsite_spread_kernel<<<div_up((size_t)n_v, 128), 128, 0, st>>>(n_v, sites, slot_of_orig, force, a, b);
+    *launches += 1;
+}
 
 void launch_settle(int n_w, const int4 *waters, const int *slot_of_orig, float4 *xyzq, float4 *vel, float m_o, float m_h,
                    float d_oh, float d_hh, const NbParams &p, float dt, cudaStream_t st, int64_t *launches) {

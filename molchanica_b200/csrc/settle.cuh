@@ -5,3 +5,9 @@
 // waters: (O, H1, H2, -) original ids.  Constrains the positions kick_drift advanced by `dt` and corrects the velocities.
 void launch_settle(int n_w, const int4 *waters, const int *slot_of_orig, float4 *xyzq, float4 *vel, float m_o, float m_h,
                    float d_oh, float d_hh, const NbParams &p, float dt, cudaStream_t st, int64_t *launches);
+
+// Virtual sites M = O + a (H1 - O) + b (H2 - O); sites: (M, O, H1, H2) original ids.
+void launch_vsite_construct(int n_v, const int4 *sites, const int *slot_of_orig, float4 *xyzq, float a, float b, const NbParams &p,
+                            cudaStream_t st, int64_t *launches);
+void launch_vsite_spread(int n_v, const int4 *sites, const int *slot_of_orig, float4 *force, float a, float b, cudaStream_t st,
+                         int64_t *launches);

@@ -109,6 +109,10 @@ class MdEngine:
         m, i, p = pair(dihedrals, dihedral_prm, 4)
         self._chk(self._L.mc_set_dihedrals(self._h, m, _ptr(i), _ptr(p)))
 
+    def set_virtual_sites(self, quads, a, b):
+        q = None if quads is None or len(quads) == 0 else np.ascontiguousarray(quads, np.int32).reshape(-1, 4)
+        self._chk(self._L.mc_set_virtual_sites(self._h, 0 if q is None else len(q), _ptr(q), a, b))
+
     def set_thermostat(self, kind, temperature_k=300.0, gamma_per_ps=1.0, seed=0):
         """kind: 0 = none, 1 = Langevin (mc_set_thermostat)."""
         self._chk(self._L.mc_set_thermostat(self._h, int(kind), temperature_k, gamma_per_ps, int(seed)))

@@ -217,6 +217,52 @@ def water_box_c1(seed=101):
     return w
 
 
+OPC = dict(r_oh=0.8724, angle=np.deg2rad(103.6), d_om=0.1594, q_h=0.6791, sigma_o=3.16655, eps_o=0.21280)
+
+
+def water_box_opc(seed=111, m=6, L=18.64):
+    """m^3 four-site OPC waters (O, H, H, M per molecule; the reference's water model, ui/panels/md.rs:393): LJ on O,
+    charges on H and on the massless site M = O + a [(H1 - O) + (H2 - O)]; rigid (SETTLE) + virtual site."""
+    rng = np.random.default_rng(seed)
+    r_oh, ang = OPC["r_oh"], OPC["angle"]
+    a = OPC["d_om"] / (2.0 * r_oh * np.cos(ang / 2))
+    pos, names, charges, masses, bonds = [], [], [], [], []
+    for i in range(m):
+        for j in range(m):
+            for k in range(m):
+                o = (np.array([i, j, k]) + 0.5) * (L / m)
+                g = _water_geometry(rng)
+                # rescale the TIP3P template to the OPC geometry: same plane, OPC bond length and angle
+                h0 = g[1] / np.linalg.norm(g[1])
+                perp = g[2] - (g[2] @ h0) * h0
+                perp /= np.linalg.norm(perp)
+                g1, g2 = r_oh * h0, r_oh * (np.cos(ang) * h0 + np.sin(ang) * perp)
+                base = len(pos)
+                pos.extend([o, o + g1, o + g2, o + a * (g1 + g2)])
+                names += ["OPC_O", "HW", "HW", "HW"]
+                charges += [0.0, OPC["q_h"], OPC["q_h"], -2 * OPC["q_h"]]
+                masses += [15.999, 1.008, 1.008, np.inf]
+                bonds += [(base, base + 1), (base, base + 2), (base + 1, base + 2), (base, base + 3), (base + 1, base + 3), (base + 2, base + 3)]
+    n = len(pos)
+    es, ei, _ = topology_from_bonds(n, bonds)
+    _CLASSES["OPC_O"] = (OPC["sigma_o"] * 2 ** (1 / 6) / 2, OPC["eps_o"], 15.999)
+    w = _pack(np.array(pos), charges, masses, names, ["OPC_O", "HW"],
+              box_lo=np.zeros(3, np.float32), box_ext=np.full(3, L, np.float32), periodic=True,
+              rc_lj=9.0, rc_q=9.0, skin=0.3, coul_mode=2, excl_start=es, excl_idx=ei,
+              pairs14=np.zeros((0, 2), np.int32), dt=0.001, name=f"OPC-water{m ** 3}")
+    flags = np.zeros(n, np.uint8)
+    flags[3::4] = 1                                     # M: static to the integrator
+    w["flags"] = flags
+    idx = np.arange(n, dtype=np.int32).reshape(-1, 4)
+    w["rigid_waters"] = np.ascontiguousarray(idx[:, :3])
+    w["virtual_sites"] = np.ascontiguousarray(idx[:, [3, 0, 1, 2]])
+    w["vsite_ab"] = (float(a), float(a))
+    w["d_oh"], w["d_hh"] = float(r_oh), float(2 * r_oh * np.sin(ang / 2))
+    maxwell_boltzmann(w["vel"], 300.0, seed + 1)
+    w["vel"][3::4, :3] = 0.0
+    return w
+
+
 def globule(n_atoms=1231, seed=202, name="C2-globule1231", temp_k=300.0):
     """C2: protein-like globule in vacuum (non-periodic), Amber-like types, 1-2/1-3 exclusions,
     1-4 scaling, r_c 12 A, skin 2 A, dt 2 fs (reference default, src/prefs/mod.rs:203)."""

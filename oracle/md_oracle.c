@@ -688,6 +688,38 @@ static void orc_langevin_step(int n, float *vel, float dt) {
     ++g_lgv_step;
 }
 
+/* ---- virtual sites of four-site water: M = O + a (H1 - O) + b (H2 - O) ------------------
+ * placed after every drift (+ constraints), its force handed to the parents after every evaluation
+ * (the reference's md.water {o, h0, h1, m}, properties/sol_shrinking_box.rs:605-613; parity unpinned). */
+static int g_nv = 0;
+static const int32_t *g_vsites = NULL;
+static double g_va = 0, g_vb = 0;
+void orc_set_virtual_sites(int n, const int32_t *quads, float a, float b) { g_nv = n; g_vsites = quads; g_va = a; g_vb = b; }
+
+void orc_vsite_construct(float *xyzq, const float *ext, int periodic) {
+    for (int v = 0; v < g_nv; ++v) {
+        const int m = g_vsites[4 * v], o = g_vsites[4 * v + 1], h1 = g_vsites[4 * v + 2], h2 = g_vsites[4 * v + 3];
+        for (int a = 0; a < 3; ++a) {
+            double d1 = (double)xyzq[4 * h1 + a] - (double)xyzq[4 * o + a], d2 = (double)xyzq[4 * h2 + a] - (double)xyzq[4 * o + a];
+            if (periodic) { d1 -= rint(d1 / (double)ext[a]) * (double)ext[a]; d2 -= rint(d2 / (double)ext[a]) * (double)ext[a]; }
+            xyzq[4 * m + a] = (float)((double)xyzq[4 * o + a] + g_va * d1 + g_vb * d2);
+        }
+    }
+}
+
+void orc_vsite_spread(float *f) {
+    for (int v = 0; v < g_nv; ++v) {
+        const int m = g_vsites[4 * v], o = g_vsites[4 * v + 1], h1 = g_vsites[4 * v + 2], h2 = g_vsites[4 * v + 3];
+        for (int a = 0; a < 3; ++a) {
+            const double fm = f[4 * m + a];
+            f[4 * o + a] = (float)((double)f[4 * o + a] + (1.0 - g_va - g_vb) * fm);
+            f[4 * h1 + a] = (float)((double)f[4 * h1 + a] + g_va * fm);
+            f[4 * h2 + a] = (float)((double)f[4 * h2 + a] + g_vb * fm);
+            f[4 * m + a] = 0.f;
+        }
+    }
+}
+
 /*
  * Whole MD loop on the CPU (the CPU baseline and the C1 plumbing run): n_steps of velocity
  * Verlet with a Verlet list rebuilt when the largest displacement since the last build exceeds
@@ -728,6 +760,7 @@ int orc_md_run(int n, float *xyzq, float *vel, const uint16_t *type, int T, cons
         if (npairs14) orc_pairs14(npairs14, pairs14, xyzq, type, T, ljtab, ext, periodic, scale14_lj, scale14_q,
                                   p->lj_on, p->coul_on, f, en, NULL, NULL);
         if (nbonds) orc_bonds(nbonds, bonds, bond_kr0, xyzq, ext, periodic, f, &en[2]);
+        if (g_nv) orc_vsite_spread(f);
         if (ext_force)
             for (int i = 0; i < n; ++i)
                 for (int a = 0; a < 3; ++a) f[4 * i + a] += ext_force[3 * i + a];
@@ -742,6 +775,7 @@ int orc_md_run(int n, float *xyzq, float *vel, const uint16_t *type, int T, cons
         if (g_nw) { xprev = (float *)malloc(sizeof(float) * 4 * (size_t)n); memcpy(xprev, xyzq, sizeof(float) * 4 * (size_t)n); }
         float worst = orc_drift(n, xyzq, vel, dt, xref);
         if (g_nw) { orc_shake_waters(xprev, xyzq, vel, ext, periodic, dt); free(xprev); }
+        if (g_nv) orc_vsite_construct(xyzq, ext, periodic);
         if (g_lgv) orc_langevin_step(n, vel, dt);
         if (worst > 0.25f * skin * skin) need = 1;
     }

@@ -54,3 +54,17 @@ extern "C" void settle_host_step(int64_t n, float *x1, float *v, const float *ex
         }
     }
 }
+
+#include "../../molchanica_b200/csrc/vsite_terms.h"
+// virtual-site arithmetic on host arrays: x n x 12 (O, H1, H2, M), f n x 12
+extern "C" void vsite_host_eval(int64_t n, float *x, float *f, float a, float b) {
+    for (int64_t w = 0; w < n; ++w) {
+        float *o = x + 12 * w, d1[3], d2[3], m[3], fo[3], f1[3], f2[3];
+        for (int k = 0; k < 3; ++k) { d1[k] = o[3 + k] - o[k]; d2[k] = o[6 + k] - o[k]; }
+        mc_vsite_position(o, d1, d2, a, b, m);
+        for (int k = 0; k < 3; ++k) o[9 + k] = m[k];
+        float *ff = f + 12 * w;
+        mc_vsite_spread(ff + 9, a, b, fo, f1, f2);
+        for (int k = 0; k < 3; ++k) { ff[k] += fo[k]; ff[3 + k] += f1[k]; ff[6 + k] += f2[k]; ff[9 + k] = 0.f; }
+    }
+}

@@ -39,7 +39,28 @@ def main():
     res = dict(traj_ok=bool(ok), traj_worst=float(worst), geom_err=float(np.abs(geom - [D_OH, D_OH, D_HH]).max()),
                temperature=float(e.energy()["temperature"]))
     e.close()
-    good = res["traj_ok"] and res["geom_err"] < 2e-5 and 100.0 < res["temperature"] < 600.0
+    # four-site OPC water: SETTLE on (O, H, H) + virtual site M, against the oracle doing the same in fp64
+    w4 = W.water_box_opc(m=5, L=15.6)
+    a, b = w4["vsite_ab"]
+    e = MdEngine.from_workload(w4)
+    e.set_rigid_waters(w4["rigid_waters"], w4["d_oh"], w4["d_hh"], 15.999, 1.008)
+    e.set_virtual_sites(w4["virtual_sites"], a, b)
+    e.step(w4["dt"], 40)
+    x4 = e.positions()
+    ref4 = O.md_run(w4, 40, precision=64, rigid_waters=(w4["rigid_waters"], w4["d_oh"], w4["d_hh"]),
+                    virtual_sites=(w4["virtual_sites"], a, b))
+    ok4, worst4, _ = trajectory_close(x4, ref4["xyzq"], w4["xyzq"], w4["box_ext"])
+    e.compute_forces()
+    f4 = e.forces()
+    e.close()
+    ext4 = np.asarray(w4["box_ext"], np.float64)
+    m4 = x4[:, :3].astype(np.float64).reshape(-1, 4, 3)
+    mi = lambda v: v - np.rint(v / ext4) * ext4
+    msite = np.abs(mi(m4[:, 3] - (m4[:, 0] + a * mi(m4[:, 1] - m4[:, 0]) + b * mi(m4[:, 2] - m4[:, 0])))).max()
+    res.update(opc_traj_ok=bool(ok4), opc_traj_worst=float(worst4), opc_msite_err=float(msite),
+               opc_m_force=float(np.abs(f4[3::4, :3]).max()))
+    good = (res["traj_ok"] and res["geom_err"] < 2e-5 and 100.0 < res["temperature"] < 600.0 and res["opc_traj_ok"] and
+            res["opc_msite_err"] < 5e-6 and res["opc_m_force"] == 0.0)
     print(json.dumps(res))
     return 0 if good else 1
 

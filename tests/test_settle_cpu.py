@@ -147,3 +147,40 @@ def test_oracle_rigid_water_md_holds_geometry_and_energy(oracle):
     assert np.abs(tot[20:] - tot[20]).max() < 0.02 * e[20:, 3].mean(), (tot[20], tot[-1], e[20:, 3].mean())
     # rigid molecules: relative velocity along every bond vanishes at the half step -> at integer steps it is small
     assert r["rebuilds"] >= 1
+
+
+def test_virtual_site_keeps_total_force_and_torque(host_math):
+    rng = np.random.default_rng(4)
+    n, a = 500, 0.14773
+    x0, _ = _rand_waters(n, rng, 0.0)
+    x = np.concatenate([x0, np.zeros((n, 1, 3))], 1).astype(np.float32).reshape(n, 12)
+    f = rng.normal(0, 10, (n, 4, 3)).astype(np.float32).reshape(n, 12)
+    f_in = f.reshape(n, 4, 3).astype(np.float64).copy()
+    host_math.vsite_host_eval(C.c_int64(n), x.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p), C.c_float(a), C.c_float(a))
+    xs, fs = x.reshape(n, 4, 3).astype(np.float64), f.reshape(n, 4, 3).astype(np.float64)
+    # M sits on the bisector, 2 a cos(theta/2) d_OH from the oxygen
+    dm = np.linalg.norm(xs[:, 3] - xs[:, 0], axis=1)
+    assert np.abs(dm - 2 * a * D_OH * np.cos(ANG / 2)).max() < 1e-5
+    assert np.abs(fs[:, 3]).max() == 0.0
+    assert np.abs(fs.sum(1) - f_in.sum(1)).max() < 1e-4                                  # total force
+    tq = lambda ff: np.cross(xs - xs[:, :1], ff).sum(1)                                   # torque about the oxygen
+    assert np.abs(tq(fs) - tq(f_in)).max() < 2e-4
+
+
+def test_oracle_four_site_water_md(oracle):
+    w = W.water_box_opc(m=5, L=15.6)
+    a, b = w["vsite_ab"]
+    r = oracle.md_run(w, 100, precision=64, want_energies=True, rigid_waters=(w["rigid_waters"], w["d_oh"], w["d_hh"]),
+                      virtual_sites=(w["virtual_sites"], a, b))
+    x = r["xyzq"][:, :3].astype(np.float64).reshape(-1, 4, 3)
+    ext = np.asarray(w["box_ext"], np.float64)
+
+    def mi(v):
+        return v - np.rint(v / ext) * ext
+    d1, d2 = mi(x[:, 1] - x[:, 0]), mi(x[:, 2] - x[:, 0])
+    assert np.abs(np.linalg.norm(d1, axis=1) - w["d_oh"]).max() < 1e-5 and np.abs(np.linalg.norm(mi(x[:, 1] - x[:, 2]), axis=1) - w["d_hh"]).max() < 1e-5
+    assert np.abs(mi(x[:, 3] - (x[:, 0] + a * d1 + b * d2))).max() < 2e-6                # M follows its parents
+    assert np.abs(r["vel"][3::4, :3]).max() == 0.0                                        # and is never integrated
+    e = r["energies"]
+    tot = e[:, 0] + e[:, 1] + e[:, 3]
+    assert np.abs(tot[20:] - tot[20]).max() < 0.03 * e[20:, 3].mean(), (tot[20], tot[-1], e[20:, 3].mean())
