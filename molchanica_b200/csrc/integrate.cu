@@ -8,7 +8,6 @@
 #include "common.cuh"
 #include "integrate.cuh"
 #include "halo_sync.cuh"
-#include "langevin_terms.h"
 
 namespace {
 
@@ -128,23 +127,6 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(int n_rows, float4 *__r
     }
 }
 
-// Langevin thermostat, O step (langevin_terms.h): applied after the drift (and the constraints) of a step, before
-// its force evaluation -- the splitting B A O B.  Noise is keyed by the atom's ORIGINAL id and the step counter.
-// STATUS: arithmetic verified on the host (tests/test_langevin_cpu.py), kernel not yet run on hardware.
-__global__ void __launch_bounds__(256) langevin_ou_kernel(int n_rows, float4 *__restrict__ vel, const int *__restrict__ orig,
-                                                           const uint8_t *__restrict__ flags, float c1, float c2, float kT,
-                                                           uint64_t seed, uint64_t step) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rows || (flags[i] & MC_FLAG_STATIC)) return;
-    float4 v = vel[i];
-    if (v.w <= 0.f) return;
-    float xi[3], vv[3] = {v.x, v.y, v.z};
-    mc_langevin_normals(seed, (uint32_t)orig[i], step, xi);
-    mc_langevin_ou(vv, v.w, c1, c2, kT, xi);
-    v.x = vv[0]; v.y = vv[1]; v.z = vv[2];
-    vel[i] = v;
-}
-
 __global__ void gather_to_orig_kernel(int n, const float4 *__restrict__ sorted, const int *__restrict__ orig,
                                       float4 *__restrict__ out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,13 +166,6 @@ void launch_kick_drift_halo(int n_rows, float4 *xyzq, float4 *vel, const float4 
     if (n_rows <= 0) return;
     kick_drift_kernel<true><<<div_up(n_rows, 256), 256, 0, st>>>(n_rows, xyzq, vel, force, ext_force, orig, flags, xref, kick,
                                                                 drift, max_disp, 0.f, rebuild_flag, hp, nullptr, nullptr, 0);
-    *launches += 1;
-}
-
-void launch_langevin_ou(int n_rows, float4 *vel, const int *orig, const uint8_t *flags, float c1, float c2, float kT, uint64_t seed,
-                        uint64_t step, cudaStream_t st, int64_t *launches) {
-    if (n_rows <= 0) return;
-    langevin_ou_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(n_rows, vel, orig, flags, c1, c2, kT, seed, step);
     *launches += 1;
 }
 

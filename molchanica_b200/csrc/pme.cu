@@ -8,7 +8,9 @@
 // 64 grid points per atom -> N x 64 x 4 B of L2 traffic each; the FFTs are HBM-bound for grids beyond L2.
 // STATUS: as bonded.cu -- arithmetic verified on the host (tests/test_pme_cpu.py), kernels not yet run on
 // hardware (round-1 GPU budget spent).
+#ifndef MC_HOST_SHIM
 #include <dlfcn.h>
+#endif
 
 #include <string>
 #include <vector>
@@ -18,6 +20,7 @@
 
 namespace {
 
+#ifndef MC_HOST_SHIM
 struct CufftApi {
     int (*Plan3d)(int *, int, int, int, int) = nullptr;
     int (*ExecR2C)(int, float *, float2 *) = nullptr;
@@ -51,6 +54,8 @@ CufftApi &cufft_api() {
 }
 
 constexpr int CUFFT_R2C_ = 0x2a, CUFFT_C2R_ = 0x2c;
+
+#endif
 
 struct PmeGeom {
     int K[3];
@@ -187,6 +192,7 @@ __global__ void __launch_bounds__(128) pme_excl_kernel(int n, const float4 *__re
 
 }  // namespace
 
+#ifndef MC_HOST_SHIM  // tests/cpp/kernels_host.cpp runs the kernels above on the CPU; cuFFT and launches need nvcc
 void pme_release(PmeState *s) {
     if (s->planned && cufft_api().ok) { cufft_api().Destroy(s->plan_r2c); cufft_api().Destroy(s->plan_c2r); }
     s->planned = false;
@@ -268,3 +274,4 @@ void pme_launch_exclusions(PmeState *s, int n, const float4 *xyzq, const int *or
                                                           s->energy + 1, want_energy ? 1 : 0);
     *launches += 1;
 }
+#endif

@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(128) vsite_spread_kernel(int n_v, const int4 *
 
 }  // namespace
 
+#ifndef MC_HOST_SHIM  // tests/cpp/kernels_host.cpp runs the kernels above on the CPU; launches need nvcc
 void launch_vsite_construct(int n_v, const int4 *sites, const int *slot_of_orig, float4 *xyzq, float a, float b, const NbParams &p,
                             cudaStream_t st, int64_t *launches) {
     if (n_v <= 0) return;
@@ -120,3 +121,4 @@ void launch_settle(int n_w, const int4 *waters, const int *slot_of_orig, float4 
     settle_kernel<<<div_up((size_t)n_w, 128), 128, 0, st>>>(n_w, waters, slot_of_orig, xyzq, vel, sp, p, dt);
     *launches += 1;
 }
+#endif

@@ -1,0 +1,185 @@
+"""The kernel SOURCES of bonded.cu, settle.cu, thermostat.cu and pme.cu, compiled unchanged for the host through
+tests/cpp/shim/cuda_runtime.h and run one thread at a time (tests/cpp/kernels_host.cpp), against the fp64 oracles.
+These device components were written after round 1's GPU budget was spent; this is how their addressing -- slot
+maps in a shuffled cell order, minimum images across the box edge, grid indices, atomics, energy reductions --
+was exercised without a GPU.  (Races between threads and the cuFFT calls are outside what a serial run can show.)"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from molchanica_b200 import workloads as W
+from oracle import pme_oracle as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def K():
+    out = os.path.join(HERE, "cpp", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libkernels_host.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas",
+                        "-I", os.path.join(HERE, "cpp", "shim"), "-o", so, os.path.join(HERE, "cpp", "kernels_host.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return C.CDLL(so)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _shuffle(n, seed):
+    """A cell order that is not the caller's: slot_of_orig and its inverse."""
+    rng = np.random.default_rng(seed)
+    slot_of_orig = rng.permutation(n).astype(np.int32)
+    orig = np.empty(n, np.int32)
+    orig[slot_of_orig] = np.arange(n, dtype=np.int32)
+    return slot_of_orig, orig
+
+
+def _pad4(a, dt):
+    out = np.zeros((len(a), 4), dt)
+    out[:, :a.shape[1]] = a
+    return out
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_bonded_kernel(periodic, K, oracle):
+    w = W.bonded_globule(300, seed=41)
+    n = len(w["xyzq"])
+    if periodic:   # put the globule into a periodic box and wrap every atom on its own: bonds straddle the edge
+        L = 30.0
+        w = dict(w, periodic=True, box_ext=np.full(3, L, np.float32))
+        w["xyzq"] = w["xyzq"].copy()
+        w["xyzq"][:, :3] = np.mod(w["xyzq"][:, :3] - w["xyzq"][:, :3].min(0) + 11.0, L)
+    so, orig = _shuffle(n, 1)
+    x_sorted = np.ascontiguousarray(w["xyzq"][orig])
+    force = np.zeros((n, 4), np.float32)
+    force[:, :3] = 0.25                                      # the kernel ADDS to what the pair kernel left
+    e3 = np.zeros(3, np.float64)
+    ext = np.ascontiguousarray(w["box_ext"], np.float32)
+    K.host_bonded(len(w["bonds"]), _p(np.ascontiguousarray(w["bonds"], np.int32)), _p(np.ascontiguousarray(w["bond_kr0"], np.float32)),
+                  len(w["angles"]), _p(_pad4(w["angles"], np.int32)), _p(np.ascontiguousarray(w["angle_kt0"], np.float32)),
+                  len(w["dihedrals"]), _p(np.ascontiguousarray(w["dihedrals"], np.int32)), _p(_pad4(w["dihedral_prm"], np.float32)),
+                  _p(so), _p(x_sorted), _p(ext), int(periodic), _p(force), _p(e3))
+    f64, e64 = oracle.bonded(w)
+    got = force[so, :3].astype(np.float64) - 0.25             # back in the caller's order
+    assert np.abs(got - f64).max() < 3e-5 * np.abs(f64).max()
+    assert np.allclose(e3, e64, rtol=3e-5)
+    assert np.all(force[:, 3] == 0)
+
+
+def test_settle_and_virtual_site_kernels(K, oracle):
+    w = W.water_box_opc(m=4, L=12.5)
+    n = len(w["xyzq"])
+    ext = np.ascontiguousarray(w["box_ext"], np.float32)
+    a, b = w["vsite_ab"]
+    dt = np.float32(0.002)
+    so, orig = _shuffle(n, 2)
+    x0 = w["xyzq"].copy()
+    x0[:, :3] = np.mod(x0[:, :3], ext)                      # atoms wrapped one by one
+    v = w["vel"].copy()
+    x1 = x0.copy()
+    x1[:, :3] += v[:, :3] * dt                               # the unconstrained drift
+    xs, vs = np.ascontiguousarray(x1[orig]), np.ascontiguousarray(v[orig])
+    waters = _pad4(w["rigid_waters"], np.int32)
+    sites = np.ascontiguousarray(w["virtual_sites"], np.int32)
+    K.host_settle(len(waters), _p(waters), _p(so), _p(xs), _p(vs), C.c_float(15.999), C.c_float(1.008), C.c_float(w["d_oh"]),
+                  C.c_float(w["d_hh"]), _p(ext), 1, C.c_float(dt))
+    K.host_vsite_construct(len(sites), _p(sites), _p(so), _p(xs), C.c_float(a), C.c_float(b), _p(ext), 1)
+    # reference: the oracle's fp64 SHAKE + construction on the same step
+    L = oracle.lib()
+    xr, vr = x1.copy(), v.copy()
+    wt = np.ascontiguousarray(w["rigid_waters"], np.int32)
+    L.orc_set_rigid_waters(C.c_int(len(wt)), _p(wt), C.c_float(w["d_oh"]), C.c_float(w["d_hh"]))
+    L.orc_set_virtual_sites(C.c_int(len(sites)), _p(sites), C.c_float(a), C.c_float(b))
+    try:
+        L.orc_shake_waters(_p(x0), _p(xr), _p(vr), _p(ext), C.c_int(1), C.c_float(dt))
+        L.orc_vsite_construct(_p(xr), _p(ext), C.c_int(1))
+        got_x, got_v = xs[so], vs[so]
+        assert np.abs(got_x[:, :3] - xr[:, :3]).max() < 5e-6
+        assert np.abs(got_v[:, :3] - vr[:, :3]).max() < 5e-6 / dt
+        assert np.array_equal(got_x[:, 3], x0[:, 3]) and np.array_equal(got_v[:, 3], v[:, 3])    # charge and 1/m untouched
+        # force redistribution
+        rng = np.random.default_rng(3)
+        f = rng.normal(0, 8, (n, 4)).astype(np.float32)
+        fs = np.ascontiguousarray(f[orig])
+        K.host_vsite_spread(len(sites), _p(sites), _p(so), _p(fs), C.c_float(a), C.c_float(b))
+        fr = f.copy()
+        L.orc_vsite_spread(_p(fr))
+        assert np.abs(fs[so][:, :3] - fr[:, :3]).max() < 1e-5 and np.array_equal(fs[so][:, 3], f[:, 3])
+    finally:
+        L.orc_set_rigid_waters(C.c_int(0), None, C.c_float(0), C.c_float(0))
+        L.orc_set_virtual_sites(C.c_int(0), None, C.c_float(0), C.c_float(0))
+
+
+def test_langevin_kernel(K, oracle):
+    rng = np.random.default_rng(8)
+    n = 3000
+    so, orig = _shuffle(n, 4)
+    vel = np.concatenate([rng.normal(0, 3, (n, 3)), 1.0 / rng.uniform(1, 40, (n, 1))], 1).astype(np.float32)   # slot order
+    flags = np.zeros(n, np.uint8)
+    flags[::40] = 1
+    v0 = vel.copy()
+    kT, c1 = 0.0019872041 * 310.0, np.exp(-2.0 * 0.002)
+    K.host_langevin(n, _p(vel), _p(orig), _p(flags), C.c_float(c1), C.c_float(np.sqrt(1 - c1 * c1)), C.c_float(kT), C.c_uint64(77), C.c_uint64(12))
+    L = oracle.lib()
+    d = np.zeros(3, np.float64)
+    for s in (0, 1, 40, 999, n - 1):
+        if flags[s]:
+            assert np.array_equal(vel[s], v0[s])
+            continue
+        L.orc_langevin_normals(C.c_uint64(77), C.c_uint32(int(orig[s])), C.c_uint64(12), _p(d))     # keyed by the ORIGINAL id
+        want = c1 * v0[s, :3].astype(np.float64) + np.sqrt(1 - c1 * c1) * np.sqrt(kT * float(v0[s, 3]) * 418.4) * d
+        assert np.abs(vel[s, :3] - want).max() < 1e-5 * max(1.0, np.abs(want).max())
+    assert np.array_equal(vel[:, 3], v0[:, 3])
+
+
+def test_pme_kernels(K):
+    rng = np.random.default_rng(6)
+    n, Lb, alpha = 400, 22.0, 0.35
+    x = rng.uniform(-5, Lb + 5, (n, 3))                       # outside the box too: the wrap is the kernel's job
+    q = rng.normal(0, 0.4, n)
+    q -= q.mean()
+    q[::25] = 0.0                                             # uncharged atoms are skipped
+    xyzq = np.concatenate([x, (q * W.COULOMB_SCALE)[:, None]], 1).astype(np.float32)
+    lo = np.array([0.5, -1.0, 2.0], np.float32)
+    ext = np.array([Lb, Lb + 2, Lb - 1], np.float32)
+    Kd = np.array([24, 27, 20], np.int32)                     # odd and even dimensions
+    grid = np.zeros(tuple(Kd), np.float32)
+    K.host_pme_spread(n, _p(xyzq), _p(Kd), _p(lo), _p(ext), _p(grid))
+    ref_grid = P.spread(xyzq, lo, ext, tuple(Kd))
+    assert np.abs(grid - ref_grid).max() < 3e-6 * np.abs(ref_grid).max()
+    fq = np.fft.rfftn(grid.astype(np.float64)).astype(np.complex64)
+    cg = fq.view(np.float32).reshape(fq.shape + (2,)).copy()
+    e = np.zeros(2, np.float64)
+    K.host_pme_convolve(_p(Kd), _p(cg), _p(ext), C.c_float(alpha), _p(e))
+    bc = P.influence(tuple(Kd), ext, alpha)
+    want = fq.astype(np.complex128) * bc
+    got = cg[..., 0].astype(np.float64) + 1j * cg[..., 1]
+    assert np.abs(got - want).max() < 1e-5 * np.abs(want).max()
+    e_ref, f_ref = P.spme(xyzq, lo, ext, alpha, tuple(Kd))
+    assert abs(e[0] - e_ref) < 2e-5 * abs(e_ref)
+    phi = np.ascontiguousarray((np.fft.irfftn(got, s=tuple(Kd), axes=(0, 1, 2)) * np.prod(Kd)).astype(np.float32))
+    force = np.zeros((n, 4), np.float32)
+    force[:, 3] = 7.0
+    K.host_pme_gather(n, _p(xyzq), _p(Kd), _p(lo), _p(ext), _p(phi), _p(force))
+    assert np.abs(force[:, :3] - f_ref).max() < 2e-5 * np.abs(f_ref).max()
+    assert np.all(force[:, 3] == 7.0) and np.all(force[::25, :3] == 0)
+    # excluded-pair correction in a shuffled order, periodic box
+    w = W.water_box_c1()
+    m = len(w["xyzq"])
+    so, orig = _shuffle(m, 9)
+    xs = np.ascontiguousarray(w["xyzq"][orig])
+    fx = np.zeros((m, 4), np.float32)
+    ee = np.zeros(2, np.float64)
+    es, ei = np.ascontiguousarray(w["excl_start"], np.int32), np.ascontiguousarray(w["excl_idx"], np.int32)
+    wext = np.ascontiguousarray(w["box_ext"], np.float32)
+    K.host_pme_excl(m, _p(xs), _p(orig), _p(so), _p(es), _p(ei), _p(wext), 1, C.c_float(alpha), _p(fx), _p(ee))
+    e_x, f_x = P.excl_correction(w["xyzq"], wext, True, es, ei, alpha)
+    assert abs(ee[0] - e_x) < 2e-5 * abs(e_x) and np.abs(fx[so][:, :3] - f_x).max() < 2e-5 * np.abs(f_x).max()
