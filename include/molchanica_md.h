@@ -49,6 +49,7 @@ extern "C" {
 
 #define MC_THERMOSTAT_NONE 0
 #define MC_THERMOSTAT_LANGEVIN 1  /* Langevin dynamics (one of the reference's thermostats, README.md:238)      */
+#define MC_THERMOSTAT_CSVR 2      /* canonical-sampling velocity rescaling, the reference's default for NVT      */
 
 #define MC_FLAG_STATIC 1u   /* AtomDynamics.static_ : exerts forces, never moves (src/md/mod.rs:843-852) */
 
@@ -133,7 +134,10 @@ int mc_set_dihedrals(mc_ctx *ctx, int64_t m, const int32_t *quads, const float *
 /* Thermostat.  MC_THERMOSTAT_LANGEVIN: after the drift (and constraints) of every step the
  * velocities get the Ornstein-Uhlenbeck update v <- c1 v + sqrt(1 - c1^2) sqrt(kT/m) xi, c1 = exp(-gamma dt)
  * (splitting B A O B).  The noise is Philox4x32-10 keyed by (seed, atom id, step count since this call): it does
- * not depend on the engine's internal atom order.  Static atoms are left alone.  Single-GPU handles. */
+ * not depend on the engine's internal atom order.  Static atoms are left alone.
+ * MC_THERMOSTAT_CSVR (Bussi-Donadio-Parrinello): at the same point of the step all velocities are scaled by one
+ * stochastic factor computed on the device from the kinetic energy; gamma_per_ps is then 1 / tau.  The factor is a
+ * function of (seed, step, kinetic energy) only.  Single-GPU handles. */
 int mc_set_thermostat(mc_ctx *ctx, int kind, float temperature_k, float gamma_per_ps, uint64_t seed);
 
 /* SPME reciprocal space (the reference's electrostatics, README.md:240): with coulomb_mode =

@@ -367,10 +367,11 @@ extern "C" int mc_set_virtual_sites(mc_ctx *c, int64_t m, const int32_t *quads, 
 
 extern "C" int mc_set_thermostat(mc_ctx *c, int kind, float temperature_k, float gamma_per_ps, uint64_t seed) {
     if (!c) return MC_E_INVALID;
-    MC_REQUIRE(c, kind == MC_THERMOSTAT_NONE || kind == MC_THERMOSTAT_LANGEVIN, "mc_set_thermostat: unknown kind");
+    MC_REQUIRE(c, kind == MC_THERMOSTAT_NONE || kind == MC_THERMOSTAT_LANGEVIN || kind == MC_THERMOSTAT_CSVR, "mc_set_thermostat: unknown kind");
     MC_REQUIRE(c, !c->comm_active || kind == MC_THERMOSTAT_NONE, "mc_set_thermostat: thermostats on a decomposed handle are not supported yet");
     MC_REQUIRE(c, kind == MC_THERMOSTAT_NONE || (temperature_k >= 0.f && gamma_per_ps >= 0.f), "mc_set_thermostat: negative temperature or friction");
     c->langevin = kind == MC_THERMOSTAT_LANGEVIN;
+    c->csvr = kind == MC_THERMOSTAT_CSVR;
     c->lgv_temperature = temperature_k;
     c->lgv_gamma = gamma_per_ps;
     c->lgv_seed = seed;
@@ -816,6 +817,18 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
             launch_langevin_ou((int)c->n_rows_sorted(), c->vel[c->cur].p + r0, c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c1,
                                std::sqrt(std::max(0.f, 1.f - c1 * c1)), (float)MC_KB * c->lgv_temperature, c->lgv_seed, c->lgv_step++,
                                st, &c->launches);
+        }
+        if (c->csvr) {
+            // kinetic energy of the half-step velocities (two small reduction launches), then lambda, then the scaling
+            MC_CUDA(c, c->red_partial.ensure((size_t)energy_partial_elems()));
+            MC_CUDA(c, c->red_out.ensure(4));
+            MC_CUDA(c, c->csvr_lambda.ensure(1));
+            const size_t r0 = (size_t)c->row0;
+            launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + r0, c->vel[c->cur].p + r0, c->red_partial.p, c->red_out.p, st,
+                                 &c->launches);
+            launch_csvr((int)c->n_rows_sorted(), c->vel[c->cur].p + r0, c->red_out.p, MC_KB * (double)c->lgv_temperature,
+                        std::exp(-(double)c->lgv_gamma * (double)dt), 3.0 * (double)c->n_waters, c->lgv_seed, c->lgv_step++,
+                        c->csvr_lambda.p, st, &c->launches);
         }
         c->steps_since_build++;
         bool rebuild = false;

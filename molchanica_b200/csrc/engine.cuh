@@ -116,6 +116,8 @@ struct mc_ctx {
     DevBuf<int4> angles, dihedrals;
     DevBuf<float4> dihedral_prm;
     DevBuf<double> bonded_e;   // {E_bond, E_angle, E_dihedral} of the last evaluation that asked for energies
+    bool csvr = false;         // CSVR thermostat (thermostat.cu); lgv_gamma then holds 1 / tau
+    DevBuf<float> csvr_lambda;
     bool langevin = false;     // Langevin thermostat (integrate.cu langevin_ou_kernel)
     float lgv_temperature = 300.f, lgv_gamma = 1.f;
     uint64_t lgv_seed = 0, lgv_step = 0;
@@ -179,7 +181,7 @@ struct mc_ctx {
         d_rec_meta.release(); d_lig_meta.release();
         for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_ids[b].release(); }
         bonds.release(); bond_kr0.release(); angle_kt0.release(); angles.release(); dihedrals.release(); dihedral_prm.release();
-        bonded_e.release(); waters.release(); vsites.release();
+        bonded_e.release(); waters.release(); vsites.release(); csvr_lambda.release();
     }
 
     // resolve the CUDA-event pairs recorded since the last call (stream must be idle)

@@ -2,6 +2,7 @@
 // HBM-bound and tiny: 16 B read + 16 B written per atom, one launch per step when a thermostat is set.
 #include "integrate.cuh"
 #include "langevin_terms.h"
+#include "csvr_terms.h"
 
 namespace {
 
@@ -22,9 +23,37 @@ __global__ void __launch_bounds__(256) langevin_ou_kernel(int n_rows, float4 *__
     vel[i] = v;
 }
 
+// CSVR (csvr_terms.h): one thread turns the kinetic energy that energy_partial / energy_final have just reduced
+// into the velocity scale factor of this step; csvr_scale_kernel applies it.  red3 = {-, sum 1/2 m v^2 in amu A^2/ps^2,
+// mobile atoms}.  STATUS: arithmetic verified on the host (tests/test_csvr_cpu.py), kernels not yet run on hardware.
+__global__ void csvr_lambda_kernel(const double *__restrict__ red3, double kT, double c, double dof_removed, uint64_t seed,
+                                   uint64_t step, float *__restrict__ lambda_out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const double kinetic = red3[1] / 418.4;  // kcal/mol
+    const double nf = 3.0 * red3[2] - dof_removed;
+    *lambda_out = (float)mc_csvr_lambda(kinetic, kT, nf, c, seed, step);
+}
+
+__global__ void __launch_bounds__(256) csvr_scale_kernel(int n_rows, float4 *__restrict__ vel, const float *__restrict__ lambda) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const float l = *lambda;
+    float4 v = vel[i];
+    v.x *= l; v.y *= l; v.z *= l;
+    vel[i] = v;
+}
+
 }  // namespace
 
 #ifndef MC_HOST_SHIM
+void launch_csvr(int n_rows, float4 *vel, const double *red3, double kT, double c, double dof_removed, uint64_t seed, uint64_t step,
+                 float *lambda, cudaStream_t st, int64_t *launches) {
+    if (n_rows <= 0) return;
+    csvr_lambda_kernel<<<1, 32, 0, st>>>(red3, kT, c, dof_removed, seed, step, lambda);
+    csvr_scale_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(n_rows, vel, lambda);
+    *launches += 2;
+}
+
 void launch_langevin_ou(int n_rows, float4 *vel, const int *orig, const uint8_t *flags, float c1, float c2, float kT, uint64_t seed,
                         uint64_t step, cudaStream_t st, int64_t *launches) {
     if (n_rows <= 0) return;

@@ -720,6 +720,75 @@ void orc_vsite_spread(float *f) {
     }
 }
 
+/* ---- CSVR thermostat: Bussi, Donadio & Parrinello, J. Chem. Phys. 126, 014101 (2007) ------
+ * One scale factor per step from the kinetic energy, K' = K + (1-c)(Kbar (R1^2 + S)/Nf - K) + 2 R1 sqrt(K Kbar/Nf (1-c) c).
+ * The draw sequence follows the specification in molchanica_b200/csrc/csvr_terms.h (Philox counter = (draw, step,
+ * 0xC5A1), 53-bit uniforms, Box-Muller, Marsaglia-Tsang gamma) so that both sides get the same factor; the code is
+ * written independently on top of this file's own Philox. */
+static int g_csvr = 0;
+static double g_csvr_kT = 0, g_csvr_inv_tau = 0, g_csvr_dof_removed = 0;
+static uint64_t g_csvr_seed = 0, g_csvr_step = 0;
+void orc_set_csvr(int on, float temperature_k, float inv_tau, uint64_t seed, double dof_removed) {
+    g_csvr = on; g_csvr_kT = 0.0019872041 * (double)temperature_k; g_csvr_inv_tau = inv_tau; g_csvr_seed = seed; g_csvr_step = 0;
+    g_csvr_dof_removed = dof_removed;
+}
+
+typedef struct { uint64_t seed, step; uint32_t draw; } orc_rng;
+static void rng_words(orc_rng *g, uint32_t *r) {
+    uint32_t ctr[4] = {g->draw++, (uint32_t)(g->step & 0xffffffffull), (uint32_t)(g->step >> 32), 0xC5A1u};
+    uint32_t key[2] = {(uint32_t)(g->seed & 0xffffffffull), (uint32_t)(g->seed >> 32)};
+    orc_philox4x32_10(ctr, key, r);
+}
+static double rng_u53(uint32_t hi, uint32_t lo) { return ((double)((((uint64_t)hi) << 21) ^ (uint64_t)(lo >> 11)) + 0.5) / 9007199254740992.0; }
+static void rng_normals(orc_rng *g, double *a, double *b) {
+    uint32_t r[4];
+    rng_words(g, r);
+    double u0 = rng_u53(r[0], r[1]), u1 = rng_u53(r[2], r[3]), rad = sqrt(-2.0 * log(u0));
+    *a = rad * cos(6.283185307179586 * u1); *b = rad * sin(6.283185307179586 * u1);
+}
+static double rng_gamma(orc_rng *g, double k) {
+    double d = k - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
+    for (int trial = 0; trial < 1000; ++trial) {
+        double x, y;
+        rng_normals(g, &x, &y);
+        double t = 1.0 + cc * x;
+        if (t <= 0.0) continue;
+        double v = t * t * t;
+        uint32_t r[4];
+        rng_words(g, r);
+        if (log(rng_u53(r[0], r[1])) < 0.5 * x * x + d - d * v + d * log(v)) return d * v;
+    }
+    return d;
+}
+double orc_csvr_lambda(double kinetic, double kT, double nf, double c, uint64_t seed, uint64_t step) {
+    if (!(kinetic > 0.0) || nf < 1.0) return 1.0;
+    orc_rng g = {seed, step, 0};
+    double r1, y, s = 0.0;
+    rng_normals(&g, &r1, &y);
+    if (nf > 1.0) {
+        if (nf - 1.0 >= 2.0) s = 2.0 * rng_gamma(&g, 0.5 * (nf - 1.0));
+        else { double a, b; rng_normals(&g, &a, &b); s = a * a; }
+    }
+    double kbar = 0.5 * nf * kT;
+    double knew = kinetic + (1.0 - c) * (kbar * (r1 * r1 + s) / nf - kinetic) + 2.0 * r1 * sqrt(kinetic * kbar / nf * (1.0 - c) * c);
+    if (knew < 0.0) knew = 0.0;
+    return sqrt(knew / kinetic);
+}
+
+static void orc_csvr_step(int n, float *vel, float dt) {
+    double ke = 0, mobile = 0;
+    for (int i = 0; i < n; ++i) {
+        if (vel[4 * i + 3] <= 0.f) continue;
+        double m = 1.0 / (double)vel[4 * i + 3];
+        ke += 0.5 * m * ((double)vel[4 * i] * vel[4 * i] + (double)vel[4 * i + 1] * vel[4 * i + 1] + (double)vel[4 * i + 2] * vel[4 * i + 2]);
+        mobile += 1.0;
+    }
+    double lam = orc_csvr_lambda(ke / (double)ORC_ACCEL_CONV, g_csvr_kT, 3.0 * mobile - g_csvr_dof_removed,
+                                 exp(-g_csvr_inv_tau * (double)dt), g_csvr_seed, g_csvr_step++);
+    float l = (float)lam;
+    for (int i = 0; i < n; ++i) { vel[4 * i] *= l; vel[4 * i + 1] *= l; vel[4 * i + 2] *= l; }
+}
+
 /*
  * Whole MD loop on the CPU (the CPU baseline and the C1 plumbing run): n_steps of velocity
  * Verlet with a Verlet list rebuilt when the largest displacement since the last build exceeds
@@ -777,6 +846,7 @@ int orc_md_run(int n, float *xyzq, float *vel, const uint16_t *type, int T, cons
         if (g_nw) { orc_shake_waters(xprev, xyzq, vel, ext, periodic, dt); free(xprev); }
         if (g_nv) orc_vsite_construct(xyzq, ext, periodic);
         if (g_lgv) orc_langevin_step(n, vel, dt);
+        if (g_csvr) orc_csvr_step(n, vel, dt);
         if (worst > 0.25f * skin * skin) need = 1;
     }
     if (forces_out) memcpy(forces_out, f, sizeof(float) * 4 * (size_t)n);

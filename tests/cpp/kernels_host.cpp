@@ -53,6 +53,12 @@ void host_langevin(int n, float4 *vel, const int *orig, const uint8_t *flags, fl
     FOR_THREADS(n + 5) langevin_ou_kernel(n, vel, orig, flags, c1, c2, kT, seed, step);
 }
 
+void host_csvr(int n, float4 *vel, const double *red3, double kT, double c, double dof_removed, uint64_t seed, uint64_t step,
+               float *lambda) {
+    FOR_THREADS(3) csvr_lambda_kernel(red3, kT, c, dof_removed, seed, step, lambda);
+    FOR_THREADS(n + 9) csvr_scale_kernel(n, vel, lambda);
+}
+
 static PmeGeom geom(const int *K, const float *lo, const float *ext) {
     PmeGeom g;
     for (int a = 0; a < 3; ++a) { g.K[a] = K[a]; g.lo[a] = lo[a]; g.inv_ext[a] = 1.0f / ext[a]; g.scale[a] = (float)K[a] / ext[a]; }

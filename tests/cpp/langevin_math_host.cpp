@@ -19,3 +19,8 @@ void lgv_host_ou(int64_t n, float *vel, const int32_t *ids, float c1, float c2, 
     }
 }
 }
+
+#include "../../molchanica_b200/csrc/csvr_terms.h"
+extern "C" double csvr_host_lambda(double kinetic, double kT, double nf, double c, uint64_t seed, uint64_t step) {
+    return mc_csvr_lambda(kinetic, kT, nf, c, seed, step);
+}

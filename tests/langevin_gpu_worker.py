@@ -36,8 +36,19 @@ def main():
         e.compute_forces()
         temps.append(e.energy()["temperature"])
     e.close()
-    res = dict(traj_ok=bool(ok), traj_worst=float(worst), dv=dv, temperature=float(np.mean(temps)))
-    good = res["traj_ok"] and res["dv"] < 5e-3 and abs(res["temperature"] - 120.0) < 12.0
+    # CSVR: the scale factor is a function of (seed, step, kinetic energy) -> same trajectory as the oracle
+    w = W.lj_fluid(m=12)
+    e = MdEngine.from_workload(w)
+    e.set_thermostat(2, 150.0, 20.0, seed=9)
+    e.step(w["dt"], 25)
+    ref = O.md_run(w, 25, precision=64, csvr=(150.0, 20.0, 9))
+    ok2, worst2, _ = trajectory_close(e.positions(), ref["xyzq"], w["xyzq"], w["box_ext"])
+    dv2 = float(np.abs(e.velocities()[:, :3] - ref["vel"][:, :3]).max())
+    e.close()
+    res = dict(traj_ok=bool(ok), traj_worst=float(worst), dv=dv, temperature=float(np.mean(temps)), csvr_traj_ok=bool(ok2),
+               csvr_traj_worst=float(worst2), csvr_dv=dv2)
+    good = (res["traj_ok"] and res["dv"] < 5e-3 and abs(res["temperature"] - 120.0) < 12.0 and res["csvr_traj_ok"] and
+            res["csvr_dv"] < 5e-3)
     print(json.dumps(res))
     return 0 if good else 1
 

@@ -140,6 +140,24 @@ def test_langevin_kernel(K, oracle):
     assert np.array_equal(vel[:, 3], v0[:, 3])
 
 
+def test_csvr_kernels(K, oracle):
+    rng = np.random.default_rng(12)
+    n = 2000
+    vel = np.concatenate([rng.normal(0, 3, (n, 3)), 1.0 / rng.uniform(1, 40, (n, 1))], 1).astype(np.float32)
+    vel[::30, 3] = 0.0
+    vel[::30, :3] = 0.0
+    mob = vel[:, 3] > 0
+    ke_units = float((0.5 * (vel[mob, :3].astype(np.float64) ** 2).sum(1) / vel[mob, 3]).sum())     # amu A^2/ps^2
+    red3 = np.array([0.0, ke_units, float(mob.sum())], np.float64)
+    lam = np.zeros(1, np.float32)
+    v0 = vel.copy()
+    kT, c = 0.0019872041 * 300.0, float(np.exp(-10.0 * 0.002))
+    K.host_csvr(n, _p(vel), _p(red3), C.c_double(kT), C.c_double(c), C.c_double(3.0 * 100), C.c_uint64(21), C.c_uint64(6), _p(lam))
+    want = oracle.lib().orc_csvr_lambda(ke_units / 418.4, kT, 3.0 * mob.sum() - 300.0, c, 21, 6)
+    assert abs(float(lam[0]) - want) < 1e-6 and want != 1.0
+    assert np.allclose(vel[:, :3], v0[:, :3] * lam[0], rtol=1e-6, atol=0) and np.array_equal(vel[:, 3], v0[:, 3])
+
+
 def test_pme_kernels(K):
     rng = np.random.default_rng(6)
     n, Lb, alpha = 400, 22.0, 0.35
