@@ -41,3 +41,23 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|liboracle|oracle_py|oracle\/_build", txt, re.M), os.path.join(dp, f)
+
+
+def test_rust_binding_is_in_step_with_the_header():
+    """bindings/rust/src/lib.rs is generated from include/molchanica_md.h (tools/gen_rust_binding.py): it must be the
+    generator's current output, declare every function of the header, and lay out the two structs like the ctypes
+    mirror the GPU tests drive (same field names, same order)."""
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_rust_binding", os.path.join(root, "tools", "gen_rust_binding.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text = open(os.path.join(root, "bindings", "rust", "src", "lib.rs")).read()
+    assert text == gen.generate(), "run python tools/gen_rust_binding.py"
+    fns = set(re.findall(r"pub fn (mc_[a-z0-9_]+)\(", text))
+    assert fns == set(_lib.declared_symbols())
+    for rust, py in (("McEnergy", _lib.McEnergy), ("McStats", _lib.McStats)):
+        body = re.search(r"pub struct " + rust + r" \{(.*?)\n\}", text, re.S).group(1)
+        assert re.findall(r"pub (\w+):", body) == [n for n, _ in py._fields_]
