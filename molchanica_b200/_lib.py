@@ -25,7 +25,9 @@ FLAG_STATIC = 1
 class McEnergy(C.Structure):
     _fields_ = [("energy_potential", C.c_double), ("energy_potential_nonbonded", C.c_double),
                 ("energy_potential_bonded", C.c_double), ("energy_kinetic", C.c_double),
-                ("temperature", C.c_double)]
+                ("temperature", C.c_double),
+                ("energy_bond", C.c_double), ("energy_angle", C.c_double), ("energy_dihedral", C.c_double),
+                ("volume", C.c_double), ("density", C.c_double), ("energy_pme", C.c_double)]
 
 
 class McStats(C.Structure):
