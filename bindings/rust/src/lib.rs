@@ -77,6 +77,7 @@ extern "C" {
     pub fn mc_destroy(ctx: *mut McCtx) -> c_int;
     pub fn mc_last_error(ctx: *const McCtx) -> *const c_char;
     pub fn mc_abi_version() -> c_int;
+    pub fn mc_struct_sizes(energy_bytes: *mut c_int, stats_bytes: *mut c_int) -> c_int;
     pub fn mc_set_box(ctx: *mut McCtx, lo: *const f32, hi: *const f32, periodic: c_int) -> c_int;
     pub fn mc_set_atoms(ctx: *mut McCtx, n: i64, xyzq: *const McFloat4, type_: *const u16, vel_invmass: *const McFloat4, flags: *const u8) -> c_int;
     pub fn mc_set_lj_table(ctx: *mut McCtx, n_types: c_int, sigma_eps: *const f32) -> c_int;

@@ -98,6 +98,9 @@ int mc_destroy(mc_ctx *ctx);
 /* Message of the last failure on this handle (or of the last failed mc_create when ctx==NULL). */
 const char *mc_last_error(const mc_ctx *ctx);
 int mc_abi_version(void);
+/* sizeof(mc_energy) / sizeof(mc_stats) as this library was compiled: a binding whose struct mirrors differ must not
+ * call mc_get_energy / mc_get_stats (they would write past the caller's buffer). */
+int mc_struct_sizes(int *energy_bytes, int *stats_bytes);
 
 /* ---- system definition (what MdState::new hands over, src/md/mod.rs:641-693) ------------ */
 

@@ -73,6 +73,11 @@ def lib():
     if missing:
         raise RuntimeError(f"{LIB_PATH} does not export {missing}; rebuild it")
     vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
+    se, ss = C.c_int(0), C.c_int(0)
+    L.mc_struct_sizes(C.byref(se), C.byref(ss))
+    if (se.value, ss.value) != (C.sizeof(McEnergy), C.sizeof(McStats)):
+        raise RuntimeError(f"{LIB_PATH}: mc_energy / mc_stats are {se.value} / {ss.value} bytes, the ctypes mirrors "
+                           f"{C.sizeof(McEnergy)} / {C.sizeof(McStats)}: molchanica_b200/_lib.py is out of step with the header")
     L.mc_last_error.restype = C.c_char_p
     L.mc_last_error.argtypes = [vp]
     L.mc_create.argtypes = [i32, C.POINTER(vp)]

@@ -53,6 +53,12 @@ static int fail(mc_ctx *c, int code, const std::string &m) {
 
 extern "C" int mc_abi_version(void) { return MC_ABI_VERSION; }
 
+extern "C" int mc_struct_sizes(int *energy_bytes, int *stats_bytes) {
+    if (energy_bytes) *energy_bytes = (int)sizeof(mc_energy);
+    if (stats_bytes) *stats_bytes = (int)sizeof(mc_stats);
+    return MC_OK;
+}
+
 extern "C" const char *mc_last_error(const mc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 extern "C" int mc_create(int device, mc_ctx **out) {
