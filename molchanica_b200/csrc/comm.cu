@@ -1,24 +1,32 @@
 // comm.cu -- spatial domain decomposition over the GPUs of one box: slabs of whole cell
-// layers along z, one ghost layer on each side, NCCL over NVLink/NVSwitch.
+// layers along z, one ghost layer on each side, one process per GPU.
 //
 // Layout on a rank (cell order, z slowest):   [ ghost layer from prev | owned layers | ghost layer from next ]
 // Because the cell sort is z-major, each of the three parts -- and the first / last OWNED layer that
-// the neighbours need as their ghosts -- is one contiguous block of the position array.  The
-// per-step halo exchange therefore needs no pack / unpack kernels: each rank ncclSend's the two
-// boundary blocks straight out of xyzq and ncclRecv's the two ghost blocks straight into xyzq
-// (0.4-0.9 MB per rank per step on the 1M-atom fluid).  Full (not half) neighbour lists mean every
-// rank computes the forces of its own atoms only: there is no reverse (force) communication.
+// the neighbours need as their ghosts -- is one contiguous block of the position array, ordered
+// identically on the owner and on the ghost holder (see comm_rebuild).  A ghost refresh is therefore a
+// plain block copy with no pack / unpack kernels.  Full (not half) neighbour lists mean every rank
+// computes the forces of its own atoms only: there is no reverse (force) communication.
+//
+// Per-step ghost refresh, two implementations:
+//   fused (default)  the neighbours' position arrays and flag words are mapped into this process with
+//                    cudaIpc at the first build; kick_drift stores its boundary layers straight into the
+//                    neighbours' ghost blocks over NVLink and raises epoch flags, the pair kernel's boundary
+//                    blocks wait on them (halo_sync.cuh, integrate.cu, pair_force.cu).  No call here per step:
+//                    comm_step_descriptors only fills the descriptors the two kernels take.
+//   NCCL             comm_halo_positions: ncclSend / ncclRecv of the four blocks between the two kernels
+//                    (option halo_fused = 0, or the mapping failed on some rank).
 //
 // Positions are kept in the GLOBAL frame and the minimum image is applied to pair differences,
 // exactly as on one GPU (ghosts are never shifted by +-L, which would cost ~1e-5 A of fp32
 // resolution at |z| ~ L), so a decomposed run lists and masks the same pairs as the single-GPU run.
 //
-// Rebuild (every rebuild_every steps): every rank contributes its owned atoms to an ncclAllGather of
-// fixed-capacity blocks (padding marked with id -1), then keeps what falls into its layer range
-// [kz0-1, kz1] by a filter key + the same radix sort / reorder as the single-GPU path.  No count
-// exchange, no host round trip, no migration bookkeeping; 40 MB through NVSwitch every ~20 steps
-// on the 1M-atom system.  (A neighbour-only migration is the obvious next refinement for systems
-// far beyond 1e7 atoms.)
+// Rebuild: the first build all-gathers every rank's atoms in fixed-capacity blocks (padding id -1) and
+// keeps what falls into the rank's layer range [kz0-1, kz1] by a filter key + the same radix sort /
+// reorder as the single-GPU path.  Later builds exchange only the last two / first two owned layers
+// with the ring neighbours (block sizes are known on both sides from the layout record every build
+// all-gathers), laid out [from prev | own | from next] so that the stable sort orders a layer the same
+// way on both sides.  The schedule is derived from all-gathered numbers, identical on every rank.
 #include "nccl_dyn.cuh"
 
 #include <cuda.h>
