@@ -696,7 +696,7 @@ int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs) {
         MC_CUDA(c, c->bonded_e.ensure(4));
         launch_bonded(t, c->slot_of_orig.p, L.xyzq, L.p, c->force.p, c->bonded_e.p, want_energy, c->st, &c->launches);
     }
-    if (c->pme.planned && c->periodic && L.coul == MC_COULOMB_ERFC) {
+    if (c->pme.planned && c->periodic && !c->comm_active && L.coul == MC_COULOMB_ERFC) {
         const char *msg = "";
         int rc = pme_launch(&c->pme, (int)c->n, L.xyzq, c->lo, c->ext, c->alpha, c->force.p, want_energy, c->st, &c->launches, &msg);
         if (rc != MC_OK) return fail(c, rc, std::string("SPME: ") + msg);
@@ -824,7 +824,7 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
                                std::sqrt(std::max(0.f, 1.f - c1 * c1)), (float)MC_KB * c->lgv_temperature, c->lgv_seed, c->lgv_step++,
                                st, &c->launches);
         }
-        if (c->csvr) {
+        if (c->csvr && !c->comm_active) {
             // kinetic energy of the half-step velocities (two small reduction launches), then lambda, then the scaling
             MC_CUDA(c, c->red_partial.ensure((size_t)energy_partial_elems()));
             MC_CUDA(c, c->red_out.ensure(4));
@@ -1022,7 +1022,7 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
         out->energy_bond = hb[0]; out->energy_angle = hb[1]; out->energy_dihedral = hb[2];
         out->energy_potential_bonded = hb[0] + hb[1] + hb[2];
     }
-    if (c->pme.planned && c->periodic && c->coul_mode == MC_COULOMB_ERFC && !c->coul_disabled) {
+    if (c->pme.planned && c->periodic && !c->comm_active && c->coul_mode == MC_COULOMB_ERFC && !c->coul_disabled) {
         double hp[2];
         MC_CUDA(c, cudaMemcpy(hp, c->pme.energy, sizeof(hp), cudaMemcpyDeviceToHost));
         // reciprocal sum + self term -alpha/sqrt(pi) sum q^2 + erf correction of the excluded pairs
