@@ -31,17 +31,20 @@ def test_plan_covers_the_box_once(engine_lib):
     assert engine_lib.mc_dd_plan(small.ctypes.data, 9.5, 0, 2, out.ctypes.data) != 0
 
 
-@pytest.mark.parametrize("m", [14, 22])
-def test_two_rank_protocol_reproduces_single_process_run(m, oracle, engine_lib):
-    """m = 14: two cell layers per rank (whole slabs exchanged); m = 22: four per rank (two-layer blocks).
-    The worker also asserts, after every build, that owner and ghost holder keep a layer in the same order."""
+@pytest.mark.parametrize("m,world", [(14, 2), (22, 2), (22, 4)])
+def test_decomposition_protocol_reproduces_single_process_run(m, world, oracle, engine_lib):
+    """(14, 2): two cell layers per rank, the two ranks exchange whole slabs; (22, 2): four layers per rank, disjoint
+    two-layer blocks to the same peer; (22, 4): a ring of four ranks with two layers each, overlapping blocks to two
+    different peers.  The worker also asserts, after every build, that owner and ghost holder keep a layer in the
+    same order -- the property the zero-copy halo needs."""
     d = tempfile.mkdtemp()
     out = os.path.join(d, "out.npz")
     os.environ["DD_M"] = str(m)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29533 + m), WORLD_SIZE="2", OMP_NUM_THREADS="2")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29533 + m + 100 * world), WORLD_SIZE=str(world),
+               OMP_NUM_THREADS="2")
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dd_protocol_worker.py"), out],
                               env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-             for r in range(2)]
+             for r in range(world)]
     logs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
     r = np.load(out)
