@@ -89,6 +89,7 @@ extern "C" {
     pub fn mc_set_thermostat(ctx: *mut McCtx, kind: c_int, temperature_k: f32, gamma_per_ps: f32, seed: u64) -> c_int;
     pub fn mc_set_pme(ctx: *mut McCtx, k1: c_int, k2: c_int, k3: c_int) -> c_int;
     pub fn mc_set_rigid_waters(ctx: *mut McCtx, m: i64, triples: *const i32, d_oh: f32, d_hh: f32, m_o: f32, m_h: f32) -> c_int;
+    pub fn mc_set_hbond_constraints(ctx: *mut McCtx, m: i64, clusters: *const i32, lengths: *const f32) -> c_int;
     pub fn mc_set_virtual_sites(ctx: *mut McCtx, m: i64, quads: *const i32, a: f32, b: f32) -> c_int;
     pub fn mc_set_cutoffs(ctx: *mut McCtx, rc_lj: f32, rc_q: f32, skin: f32, coulomb_mode: c_int, alpha: f32) -> c_int;
     pub fn mc_set_overrides(ctx: *mut McCtx, lj_disabled: c_int, coulomb_disabled: c_int) -> c_int;

@@ -157,6 +157,14 @@ int mc_set_pme(mc_ctx *ctx, int k1, int k2, int k3);
  * mc_energy.temperature then counts 3 degrees of freedom less per molecule.  Single-GPU handles; m = 0 clears. */
 int mc_set_rigid_waters(mc_ctx *ctx, int64_t m, const int32_t *triples, float d_oh, float d_hh, float m_o, float m_h);
 
+/* Constraints on bonds to hydrogen (SHAKE; the reference's "hydrogen constraints" at 2 fs, ui/panels/md.rs:362-371):
+ * clusters[4m] = (heavy atom, h1, h2, h3) with -1 for unused hydrogen slots, lengths[3m] the constrained distances;
+ * no atom may appear in two clusters (one thread owns a cluster).
+ * Applied after every drift like mc_set_rigid_waters (which handles water); a cluster that does not converge in 64
+ * sweeps makes mc_step return MC_E_INVALID.  mc_energy.temperature counts one degree of freedom less per constraint.
+ * Single-GPU handles; m = 0 clears. */
+int mc_set_hbond_constraints(mc_ctx *ctx, int64_t m, const int32_t *clusters, const float *lengths);
+
 /* Virtual sites of four-site water (OPC / TIP4P; the reference's md.water {o, h0, h1, m},
  * properties/sol_shrinking_box.rs:605-613): quads[4m] = (M, O, H1, H2) atom ids, M = O + a (H1 - O) + b (H2 - O).
  * M is an atom of the system with inverse mass 0 and MC_FLAG_STATIC (it carries the charge); after every drift

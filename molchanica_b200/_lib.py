@@ -90,6 +90,7 @@ def lib():
     L.mc_set_bonds.argtypes = [vp, i64, vp, vp]
     L.mc_set_angles.argtypes = [vp, i64, vp, vp]
     L.mc_set_dihedrals.argtypes = [vp, i64, vp, vp]
+    L.mc_set_hbond_constraints.argtypes = [vp, i64, vp, vp]
     L.mc_set_virtual_sites.argtypes = [vp, i64, vp, f32, f32]
     L.mc_set_thermostat.argtypes = [vp, i32, f32, f32, C.c_uint64]
     L.mc_set_pme.argtypes = [vp, i32, i32, i32]

@@ -228,6 +228,7 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
     c->n_bonds = c->n_angles = c->n_dihedrals = 0;
     c->n_waters = 0;
     c->n_vsites = 0;
+    c->n_hclusters = c->n_hconstraints = 0;
     c->n_pairs_listed = 0;
     c->total_mass = 0.0;
     c->pme.self_q2 = 0.0;
@@ -357,6 +358,45 @@ extern "C" int mc_set_dihedrals(mc_ctx *c, int64_t m, const int32_t *quads, cons
     for (int64_t k = 0; k < m; ++k) prm[(size_t)k] = make_float4(pk_n_phase[3 * k], pk_n_phase[3 * k + 1], pk_n_phase[3 * k + 2], 0.f);
     MC_CUDA(c, c->dihedral_prm.ensure(prm.size()));
     if (m) MC_CUDA(c, cudaMemcpy(c->dihedral_prm.p, prm.data(), sizeof(float4) * (size_t)m, cudaMemcpyHostToDevice));
+    return MC_OK;
+}
+
+extern "C" int mc_set_hbond_constraints(mc_ctx *c, int64_t m, const int32_t *clusters, const float *lengths) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, !c->comm_active, "mc_set_hbond_constraints: constraints on a decomposed handle are not supported yet");
+    MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || (clusters && lengths)), "mc_set_hbond_constraints: bad arguments");
+    const int64_t n = c->n_global;
+    std::vector<int4> h((size_t)std::max<int64_t>(m, 1));
+    std::vector<uint8_t> seen((size_t)std::max<int64_t>(n, 1), 0);  // one thread owns a cluster: no atom may be in two
+    int n_con = 0;
+    for (int64_t k = 0; k < m; ++k) {
+        const int32_t *q = clusters + 4 * k;
+        for (int a = 0; a < 4; ++a) {
+            if (q[a] < 0 || q[a] >= n) continue;  // range errors are reported below
+            MC_REQUIRE(c, !seen[(size_t)q[a]], "mc_set_hbond_constraints: an atom appears in two clusters");
+            seen[(size_t)q[a]] = 1;
+        }
+        MC_REQUIRE(c, q[0] >= 0 && q[0] < n, "mc_set_hbond_constraints: heavy atom id out of range");
+        for (int a = 1; a < 4; ++a) {
+            MC_REQUIRE(c, q[a] >= -1 && q[a] < n && q[a] != q[0], "mc_set_hbond_constraints: hydrogen id out of range");
+            if (q[a] >= 0) {
+                MC_REQUIRE(c, lengths[3 * k + a - 1] > 0.f, "mc_set_hbond_constraints: constrained length must be positive");
+                ++n_con;
+            }
+        }
+        h[(size_t)k] = make_int4(q[0], q[1], q[2], q[3]);
+    }
+    MC_CUDA(c, c->hclusters.ensure(h.size()));
+    MC_CUDA(c, c->hdist.ensure((size_t)std::max<int64_t>(3 * m, 1)));
+    MC_CUDA(c, c->shake_fail.ensure(1));
+    MC_CUDA(c, cudaMemset(c->shake_fail.p, 0, sizeof(int)));
+    if (m) {
+        MC_CUDA(c, cudaMemcpy(c->hclusters.p, h.data(), sizeof(int4) * (size_t)m, cudaMemcpyHostToDevice));
+        MC_CUDA(c, cudaMemcpy(c->hdist.p, lengths, sizeof(float) * 3 * (size_t)m, cudaMemcpyHostToDevice));
+    }
+    c->n_hclusters = (int)m;
+    c->n_hconstraints = n_con;
     return MC_OK;
 }
 
@@ -814,6 +854,9 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         if (c->n_waters > 0)
             launch_settle(c->n_waters, c->waters.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vel[c->cur].p, c->water_m_o,
                           c->water_m_h, c->water_d_oh, c->water_d_hh, make_params(c), dt, st, &c->launches);
+        if (c->n_hclusters > 0)
+            launch_shake_h(c->n_hclusters, c->hclusters.p, c->hdist.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vel[c->cur].p,
+                           make_params(c), dt, c->shake_tol, c->shake_fail.p, st, &c->launches);
         if (c->n_vsites > 0)
             launch_vsite_construct(c->n_vsites, c->vsites.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vsite_a, c->vsite_b,
                                    make_params(c), st, &c->launches);
@@ -833,7 +876,7 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
             launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + r0, c->vel[c->cur].p + r0, c->red_partial.p, c->red_out.p, st,
                                  &c->launches);
             launch_csvr((int)c->n_rows_sorted(), c->vel[c->cur].p + r0, c->red_out.p, MC_KB * (double)c->lgv_temperature,
-                        std::exp(-(double)c->lgv_gamma * (double)dt), 3.0 * (double)c->n_waters, c->lgv_seed, c->lgv_step++,
+                        std::exp(-(double)c->lgv_gamma * (double)dt), 3.0 * (double)c->n_waters + (double)c->n_hconstraints, c->lgv_seed, c->lgv_step++,
                         c->csvr_lambda.p, st, &c->launches);
         }
         c->steps_since_build++;
@@ -897,6 +940,14 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         // a decomposed rank only reports the violation: invalidating the list on one rank alone would
         // make it enter the collective rebuild on its own
         if (*h_flag != 0) { c->n_list_violations++; if (!c->comm_active) c->list_valid = false; }
+    }
+    if (c->n_hclusters > 0 && n_steps > 0) {
+        int bad = 0;
+        MC_CUDA(c, cudaMemcpy(&bad, c->shake_fail.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bad) {
+            MC_CUDA(c, cudaMemset(c->shake_fail.p, 0, sizeof(int)));
+            return fail(c, MC_E_INVALID, "mc_step: SHAKE did not converge for " + std::to_string(bad) + " hydrogen-bond cluster steps (time step too long?)");
+        }
     }
     c->collect_timings();
     return MC_OK;
@@ -1035,7 +1086,8 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
         out->density = out->volume > 0.0 ? c->total_mass * 1.66053907 / out->volume : 0.0;  // amu/A^3 -> g/cm^3
     }
     out->energy_kinetic = h[1] / (double)MC_ACCEL_CONV;
-    const double dof = 3.0 * h[2] - 3.0 * (double)c->n_waters;  // each rigid water removes three degrees of freedom
+    // each rigid water removes three degrees of freedom, each constrained bond one
+    const double dof = 3.0 * h[2] - 3.0 * (double)c->n_waters - (double)c->n_hconstraints;
     out->temperature = dof > 0 ? 2.0 * out->energy_kinetic / (dof * MC_KB) : 0.0;
     return MC_OK;
 }

@@ -125,6 +125,11 @@ struct mc_ctx {
     int n_waters = 0;          // rigid three-site waters (settle.cu)
     DevBuf<int4> waters;
     float water_m_o = 0, water_m_h = 0, water_d_oh = 0, water_d_hh = 0;
+    int n_hclusters = 0, n_hconstraints = 0;   // SHAKE clusters of bonds to hydrogen (settle.cu)
+    DevBuf<int4> hclusters;
+    DevBuf<float> hdist;
+    DevBuf<int> shake_fail;
+    float shake_tol = 1e-6f;
     int n_vsites = 0;          // virtual sites of four-site water (settle.cu)
     DevBuf<int4> vsites;
     float vsite_a = 0, vsite_b = 0;
@@ -182,6 +187,7 @@ struct mc_ctx {
         for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_ids[b].release(); }
         bonds.release(); bond_kr0.release(); angle_kt0.release(); angles.release(); dihedrals.release(); dihedral_prm.release();
         bonded_e.release(); waters.release(); vsites.release(); csvr_lambda.release();
+        hclusters.release(); hdist.release(); shake_fail.release();
     }
 
     // resolve the CUDA-event pairs recorded since the last call (stream must be idle)

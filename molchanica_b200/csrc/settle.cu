@@ -10,6 +10,7 @@
 #include "settle.cuh"
 #include "settle_terms.h"
 #include "vsite_terms.h"
+#include "shake_terms.h"
 
 namespace {
 
@@ -52,6 +53,64 @@ __global__ void __launch_bounds__(128) settle_kernel(int n_w, const int4 *__rest
     v2.x += dc_[0] * inv_dt; v2.y += dc_[1] * inv_dt; v2.z += dc_[2] * inv_dt;
     xyzq[so] = xo; xyzq[s1] = x1; xyzq[s2] = x2;
     vel[so] = vo; vel[s1] = v1; vel[s2] = v2;
+}
+
+// Bonds to hydrogen (shake_terms.h): one thread per heavy atom with its <= 3 hydrogens, same bookkeeping as settle_kernel
+// (old positions = x' - v dt, everything relative to the heavy atom's old position, velocities corrected by the
+// position change / dt).  clusters: (heavy, h1, h2, h3) original ids, -1 = no such hydrogen; dist: 3 lengths per cluster.
+__global__ void __launch_bounds__(128) shake_h_kernel(int n_c, const int4 *__restrict__ clusters, const float *__restrict__ dist,
+                                                       const int *__restrict__ slot_of_orig, float4 *__restrict__ xyzq,
+                                                       float4 *__restrict__ vel, const NbParams p, float dt, float tol,
+                                                       int *__restrict__ not_converged) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_c) return;
+    const int4 ids = clusters[c];
+    const int hid[3] = {ids.y, ids.z, ids.w};
+    const int s0 = slot_of_orig[ids.x];
+    float4 x0 = xyzq[s0], v0 = vel[s0];
+    int sh[MC_SHAKE_MAX_H], nh = 0;
+    float4 xh[MC_SHAKE_MAX_H], vh[MC_SHAKE_MAX_H];
+    float r0[MC_SHAKE_MAX_H][3], pp[MC_SHAKE_MAX_H][3], q1[MC_SHAKE_MAX_H][3], inv_m[MC_SHAKE_MAX_H], d[MC_SHAKE_MAX_H];
+#pragma unroll
+    for (int k = 0; k < MC_SHAKE_MAX_H; ++k) {
+        if (hid[k] < 0) continue;
+        sh[nh] = slot_of_orig[hid[k]];
+        xh[nh] = xyzq[sh[nh]];
+        vh[nh] = vel[sh[nh]];
+        inv_m[nh] = vh[nh].w;
+        d[nh] = dist[3 * c + k];
+        ++nh;
+    }
+    const float x0_[3] = {x0.x, x0.y, x0.z}, v0_[3] = {v0.x, v0.y, v0.z};
+    float p0[3], a1[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { a1[a] = v0_[a] * dt; p0[a] = a1[a]; }
+    for (int k = 0; k < nh; ++k) {
+        const float xk[3] = {xh[k].x, xh[k].y, xh[k].z}, vk[3] = {vh[k].x, vh[k].y, vh[k].z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float db = xk[a] - x0_[a];
+            if (p.periodic) db -= rintf(db * p.inv_ext[a]) * p.ext[a];
+            r0[k][a] = db - (vk[a] - v0_[a]) * dt;   // old heavy -> hydrogen vector
+            q1[k][a] = r0[k][a] + vk[a] * dt;        // unconstrained new hydrogen, relative to the old heavy atom
+            pp[k][a] = q1[k][a];
+        }
+    }
+    const int sweeps = mc_shake_cluster(nh, r0, p0, pp, v0.w, inv_m, d, tol, 64);
+    if (sweeps > 64) atomicAdd(not_converged, 1);
+    const float inv_dt = 1.f / dt;
+    {
+        const float da[3] = {p0[0] - a1[0], p0[1] - a1[1], p0[2] - a1[2]};
+        x0.x += da[0]; x0.y += da[1]; x0.z += da[2];
+        v0.x += da[0] * inv_dt; v0.y += da[1] * inv_dt; v0.z += da[2] * inv_dt;
+        xyzq[s0] = x0; vel[s0] = v0;
+    }
+    for (int k = 0; k < nh; ++k) {
+        const float dk[3] = {pp[k][0] - q1[k][0], pp[k][1] - q1[k][1], pp[k][2] - q1[k][2]};
+        xh[k].x += dk[0]; xh[k].y += dk[1]; xh[k].z += dk[2];
+        vh[k].x += dk[0] * inv_dt; vh[k].y += dk[1] * inv_dt; vh[k].z += dk[2] * inv_dt;
+        xyzq[sh[k]] = xh[k]; vel[sh[k]] = vh[k];
+    }
 }
 
 // Virtual sites (vsite_terms.h): one thread per site.  construct: after the parents have their final positions of
@@ -111,6 +170,13 @@ void launch_vsite_spread(int n_v, const int4 *sites, const int *slot_of_orig, fl
                          int64_t *launches) {
     if (n_v <= 0) return;
     vsite_spread_kernel<<<div_up((size_t)n_v, 128), 128, 0, st>>>(n_v, sites, slot_of_orig, force, a, b);
+    *launches += 1;
+}
+
+void launch_shake_h(int n_c, const int4 *clusters, const float *dist, const int *slot_of_orig, float4 *xyzq, float4 *vel,
+                    const NbParams &p, float dt, float tol, int *not_converged, cudaStream_t st, int64_t *launches) {
+    if (n_c <= 0) return;
+    shake_h_kernel<<<div_up((size_t)n_c, 128), 128, 0, st>>>(n_c, clusters, dist, slot_of_orig, xyzq, vel, p, dt, tol, not_converged);
     *launches += 1;
 }
 

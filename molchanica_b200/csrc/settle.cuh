@@ -11,3 +11,8 @@ void launch_vsite_construct(int n_v, const int4 *sites, const int *slot_of_orig,
                             cudaStream_t st, int64_t *launches);
 void launch_vsite_spread(int n_v, const int4 *sites, const int *slot_of_orig, float4 *force, float a, float b, cudaStream_t st,
                          int64_t *launches);
+
+// SHAKE for bonds to hydrogen: clusters (heavy, h1, h2, h3) original ids (-1 = unused), dist 3 lengths per cluster;
+// *not_converged (device) counts clusters that needed more than 64 sweeps.
+void launch_shake_h(int n_c, const int4 *clusters, const float *dist, const int *slot_of_orig, float4 *xyzq, float4 *vel,
+                    const NbParams &p, float dt, float tol, int *not_converged, cudaStream_t st, int64_t *launches);

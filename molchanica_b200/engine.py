@@ -109,6 +109,15 @@ class MdEngine:
         m, i, p = pair(dihedrals, dihedral_prm, 4)
         self._chk(self._L.mc_set_dihedrals(self._h, m, _ptr(i), _ptr(p)))
 
+    def set_hbond_constraints(self, clusters, lengths):
+        """clusters (m, 4): heavy atom + up to three hydrogens (-1 = unused); lengths (m, 3)."""
+        if clusters is None or len(clusters) == 0:
+            self._chk(self._L.mc_set_hbond_constraints(self._h, 0, None, None))
+            return
+        q = np.ascontiguousarray(clusters, np.int32).reshape(-1, 4)
+        d = np.ascontiguousarray(lengths, np.float32).reshape(-1, 3)
+        self._chk(self._L.mc_set_hbond_constraints(self._h, len(q), _ptr(q), _ptr(d)))
+
     def set_virtual_sites(self, quads, a, b):
         q = None if quads is None or len(quads) == 0 else np.ascontiguousarray(quads, np.int32).reshape(-1, 4)
         self._chk(self._L.mc_set_virtual_sites(self._h, 0 if q is None else len(q), _ptr(q), a, b))

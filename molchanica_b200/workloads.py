@@ -312,12 +312,34 @@ def bonded_terms_from_bonds(pos, bonds, seed=0):
     return dict(bonds=b, bond_kr0=bk, angles=ang, angle_kt0=ak, dihedrals=dih, dihedral_prm=dk)
 
 
+def hbond_clusters(names, bonds, bond_kr0):
+    """Heavy atoms with their (at most three) bonded hydrogens and the bonds' equilibrium lengths: the constraint set
+    of mc_set_hbond_constraints.  Returns (clusters (m, 4) with -1 padding, lengths (m, 3))."""
+    r0 = {(int(i), int(j)): float(k[1]) for (i, j), k in zip(bonds, bond_kr0)}
+    per = {}
+    for (i, j) in r0:
+        hi, hj = names[i].startswith("H"), names[j].startswith("H")
+        if hi == hj:
+            continue
+        heavy, h = (j, i) if hi else (i, j)
+        per.setdefault(heavy, []).append((h, r0[(i, j)]))
+    clusters, lengths = [], []
+    for heavy in sorted(per):
+        hs = sorted(per[heavy])
+        assert len(hs) <= 3, "a heavy atom carries at most three constrained hydrogens (one thread owns the whole cluster)"
+        clusters.append([heavy] + [h for h, _ in hs] + [-1] * (3 - len(hs)))
+        lengths.append([d for _, d in hs] + [1.0] * (3 - len(hs)))
+    return np.array(clusters, np.int32).reshape(-1, 4), np.array(lengths, np.float32).reshape(-1, 3)
+
+
 def bonded_globule(n_atoms=400, seed=212):
     """A C2-like globule that also carries its bonded terms: every bond of the chain graph, every
     angle and every proper dihedral it implies; nonbonded set-up as C2 (1-2/1-3 exclusions, scaled 1-4)."""
     w = globule(n_atoms, seed=seed, name=f"bonded-globule{n_atoms}")
-    _, _, bonds = _saw_globule(n_atoms, seed)
+    _, names, bonds = _saw_globule(n_atoms, seed)
     w.update(bonded_terms_from_bonds(w["xyzq"][:, :3].astype(np.float64), bonds, seed))
+    w["names"] = list(names)
+    w["hbond_clusters"], w["hbond_lengths"] = hbond_clusters(names, w["bonds"], w["bond_kr0"])
     return w
 
 

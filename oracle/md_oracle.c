@@ -688,6 +688,63 @@ static void orc_langevin_step(int n, float *vel, float dt) {
     ++g_lgv_step;
 }
 
+/* ---- SHAKE for bonds to hydrogen, fp64 ------------------------------------------------------
+ * Clusters (heavy, h1, h2, h3; -1 = unused) with one length per hydrogen; the reference constrains bonds to hydrogen
+ * at 2 fs (ui/panels/md.rs:362-371; code in the un-vendored `dynamics` crate -> parity unpinned).  Same equations as
+ * molchanica_b200/csrc/shake_terms.h, solved here in double, sweeping the constraints in the opposite order and to
+ * 1e-13: the fixed point does not depend on the sweep order. */
+static int g_nhc = 0;
+static const int32_t *g_hclusters = NULL;
+static const float *g_hdist = NULL;
+void orc_set_hbond_constraints(int n, const int32_t *clusters, const float *lengths) { g_nhc = n; g_hclusters = clusters; g_hdist = lengths; }
+
+void orc_shake_h(const float *xold, float *xnew, float *vel, const float *ext, int periodic, float dt) {
+    for (int c = 0; c < g_nhc; ++c) {
+        const int hv = g_hclusters[4 * c];
+        int hid[3], nh = 0;
+        double dl[3];
+        for (int k = 0; k < 3; ++k)
+            if (g_hclusters[4 * c + 1 + k] >= 0) { hid[nh] = g_hclusters[4 * c + 1 + k]; dl[nh] = g_hdist[3 * c + k]; ++nh; }
+        double r0[3][3], p[3][3], q[3][3], p0[3], q0[3], im0 = vel[4 * hv + 3], im[3];
+        for (int a = 0; a < 3; ++a) {
+            double d = (double)xnew[4 * hv + a] - (double)xold[4 * hv + a];
+            if (periodic) d -= rint(d / (double)ext[a]) * (double)ext[a];
+            p0[a] = q0[a] = d;
+        }
+        for (int k = 0; k < nh; ++k) {
+            im[k] = vel[4 * hid[k] + 3];
+            for (int a = 0; a < 3; ++a) {
+                double d0 = (double)xold[4 * hid[k] + a] - (double)xold[4 * hv + a], d1 = (double)xnew[4 * hid[k] + a] - (double)xold[4 * hv + a];
+                if (periodic) { d0 -= rint(d0 / (double)ext[a]) * (double)ext[a]; d1 -= rint(d1 / (double)ext[a]) * (double)ext[a]; }
+                r0[k][a] = d0; p[k][a] = q[k][a] = d1;
+            }
+        }
+        for (int it = 0; it < 2000; ++it) {
+            double worst = 0;
+            for (int k = nh - 1; k >= 0; --k) {
+                double s[3], ss = 0, sr = 0;
+                for (int a = 0; a < 3; ++a) { s[a] = p[k][a] - p0[a]; ss += s[a] * s[a]; sr += s[a] * r0[k][a]; }
+                double diff = dl[k] * dl[k] - ss;
+                if (fabs(diff) / (dl[k] * dl[k]) > worst) worst = fabs(diff) / (dl[k] * dl[k]);
+                double g = diff / (2.0 * sr * (im0 + im[k]));
+                for (int a = 0; a < 3; ++a) { p[k][a] += g * r0[k][a] * im[k]; p0[a] -= g * r0[k][a] * im0; }
+            }
+            if (worst < 1e-13) break;
+        }
+        for (int a = 0; a < 3; ++a) {
+            double d = p0[a] - q0[a];
+            xnew[4 * hv + a] = (float)((double)xnew[4 * hv + a] + d);
+            vel[4 * hv + a] = (float)((double)vel[4 * hv + a] + d / (double)dt);
+        }
+        for (int k = 0; k < nh; ++k)
+            for (int a = 0; a < 3; ++a) {
+                double d = p[k][a] - q[k][a];
+                xnew[4 * hid[k] + a] = (float)((double)xnew[4 * hid[k] + a] + d);
+                vel[4 * hid[k] + a] = (float)((double)vel[4 * hid[k] + a] + d / (double)dt);
+            }
+    }
+}
+
 /* ---- virtual sites of four-site water: M = O + a (H1 - O) + b (H2 - O) ------------------
  * placed after every drift (+ constraints), its force handed to the parents after every evaluation
  * (the reference's md.water {o, h0, h1, m}, properties/sol_shrinking_box.rs:605-613; parity unpinned). */
@@ -841,9 +898,11 @@ int orc_md_run(int n, float *xyzq, float *vel, const uint16_t *type, int T, cons
         if (step == n_steps) break;
         orc_kick(n, vel, f, 0.5f * dt);
         float *xprev = NULL;
-        if (g_nw) { xprev = (float *)malloc(sizeof(float) * 4 * (size_t)n); memcpy(xprev, xyzq, sizeof(float) * 4 * (size_t)n); }
+        if (g_nw || g_nhc) { xprev = (float *)malloc(sizeof(float) * 4 * (size_t)n); memcpy(xprev, xyzq, sizeof(float) * 4 * (size_t)n); }
         float worst = orc_drift(n, xyzq, vel, dt, xref);
-        if (g_nw) { orc_shake_waters(xprev, xyzq, vel, ext, periodic, dt); free(xprev); }
+        if (g_nw) orc_shake_waters(xprev, xyzq, vel, ext, periodic, dt);
+        if (g_nhc) orc_shake_h(xprev, xyzq, vel, ext, periodic, dt);
+        free(xprev);
         if (g_nv) orc_vsite_construct(xyzq, ext, periodic);
         if (g_lgv) orc_langevin_step(n, vel, dt);
         if (g_csvr) orc_csvr_step(n, vel, dt);

@@ -155,7 +155,7 @@ def forces(w, nbr, xyzq=None, precision=64, lj_on=True, coul_on=True, with_pairs
 
 
 def md_run(w, n_steps, precision=32, xyzq=None, vel=None, want_energies=False, ext_force=None,
-           with_bonds=False, rigid_waters=None, langevin=None, virtual_sites=None, csvr=None):
+           with_bonds=False, rigid_waters=None, langevin=None, virtual_sites=None, csvr=None, hbond_constraints=None):
     """n_steps of velocity Verlet on the CPU. Returns dict(xyzq, vel, forces, rebuilds, energies)."""
     xyzq = np.array(w["xyzq"] if xyzq is None else xyzq, np.float32, copy=True)
     vel = np.array(w["vel"] if vel is None else vel, np.float32, copy=True)
@@ -189,6 +189,12 @@ def md_run(w, n_steps, precision=32, xyzq=None, vel=None, want_energies=False, e
         # (quads (M, O, H1, H2), a, b): M placed after every drift, its force handed to the parents
         vs = np.ascontiguousarray(virtual_sites[0], np.int32).reshape(-1, 4)
         lib().orc_set_virtual_sites(C.c_int(len(vs)), _p(vs, C.c_int32), C.c_float(virtual_sites[1]), C.c_float(virtual_sites[2]))
+    hc = hd = None
+    if hbond_constraints is not None:
+        # (clusters (m, 4) heavy + up to three hydrogens with -1 for unused, lengths (m, 3)): SHAKE after every drift
+        hc = np.ascontiguousarray(hbond_constraints[0], np.int32).reshape(-1, 4)
+        hd = np.ascontiguousarray(hbond_constraints[1], np.float32).reshape(-1, 3)
+        lib().orc_set_hbond_constraints(C.c_int(len(hc)), _p(hc, C.c_int32), _p(hd, C.c_float))
     if csvr is not None:
         # (temperature_K, 1/tau [1/ps], seed, degrees of freedom removed by constraints): one scale factor per step
         lib().orc_set_csvr(C.c_int(1), C.c_float(csvr[0]), C.c_float(csvr[1]), C.c_uint64(int(csvr[2])), C.c_double(csvr[3] if len(csvr) > 3 else 0.0))
@@ -198,6 +204,8 @@ def md_run(w, n_steps, precision=32, xyzq=None, vel=None, want_energies=False, e
     try:
         rb = _md_run_call(n, xyzq, vel, typ, tab, lo, ext, w, p, es, ei, p14, bonds, kr0, ef, n_steps, precision, en, fo)
     finally:
+        if hc is not None:
+            lib().orc_set_hbond_constraints(C.c_int(0), None, None)
         if csvr is not None:
             lib().orc_set_csvr(C.c_int(0), C.c_float(0), C.c_float(0), C.c_uint64(0), C.c_double(0))
         if vs is not None:

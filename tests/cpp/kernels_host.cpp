@@ -40,6 +40,13 @@ void host_settle(int n_w, const int4 *waters, const int *slot_of_orig, float4 *x
     FOR_THREADS(n_w + 3) settle_kernel(n_w, waters, slot_of_orig, xyzq, vel, sp, nb(ext, periodic, 0.f), dt);
 }
 
+int host_shake_h(int n_c, const int4 *clusters, const float *dist, const int *slot_of_orig, float4 *xyzq, float4 *vel, const float *ext,
+                 int periodic, float dt, float tol) {
+    int bad = 0;
+    FOR_THREADS(n_c + 3) shake_h_kernel(n_c, clusters, dist, slot_of_orig, xyzq, vel, nb(ext, periodic, 0.f), dt, tol, &bad);
+    return bad;
+}
+
 void host_vsite_construct(int n_v, const int4 *sites, const int *slot_of_orig, float4 *xyzq, float a, float b, const float *ext,
                           int periodic) {
     FOR_THREADS(n_v + 3) vsite_construct_kernel(n_v, sites, slot_of_orig, xyzq, a, b, nb(ext, periodic, 0.f));

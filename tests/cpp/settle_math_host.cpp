@@ -68,3 +68,25 @@ extern "C" void vsite_host_eval(int64_t n, float *x, float *f, float a, float b)
         for (int k = 0; k < 3; ++k) { ff[k] += fo[k]; ff[3 + k] += f1[k]; ff[6 + k] += f2[k]; ff[9 + k] = 0.f; }
     }
 }
+
+#include "../../molchanica_b200/csrc/shake_terms.h"
+// SHAKE arithmetic of one cluster per row: x0 / x1 n x 12 (heavy, h1, h2, h3; unused hydrogens ignored via nh[i]), out n x 12
+extern "C" int shake_host_eval(int64_t n, const int32_t *nh, const float *x0, const float *x1, const float *inv_m /* n x 4 */,
+                               const float *d /* n x 3 */, float tol, float *out) {
+    int worst = 0;
+    for (int64_t c = 0; c < n; ++c) {
+        const float *o = x0 + 12 * c, *q = x1 + 12 * c;
+        float r0[3][3], p[3][3], p0[3], im[3], dd[3];
+        for (int a = 0; a < 3; ++a) p0[a] = q[a] - o[a];
+        for (int k = 0; k < nh[c]; ++k) {
+            im[k] = inv_m[4 * c + 1 + k]; dd[k] = d[3 * c + k];
+            for (int a = 0; a < 3; ++a) { r0[k][a] = o[3 + 3 * k + a] - o[a]; p[k][a] = q[3 + 3 * k + a] - o[a]; }
+        }
+        const int it = mc_shake_cluster(nh[c], r0, p0, p, inv_m[4 * c], im, dd, tol, 64);
+        if (it > worst) worst = it;
+        for (int a = 0; a < 3; ++a) out[12 * c + a] = o[a] + p0[a];
+        for (int k = 0; k < 3; ++k)
+            for (int a = 0; a < 3; ++a) out[12 * c + 3 + 3 * k + a] = k < nh[c] ? o[a] + p[k][a] : q[3 + 3 * k + a];
+    }
+    return worst;
+}

@@ -32,6 +32,7 @@ static const shim_dim3 threadIdx = {0, 0, 0}, blockDim = {1, 1, 1};
 
 static inline float atomicAdd(float *a, float v) { float o = *a; *a += v; return o; }
 static inline double atomicAdd(double *a, double v) { double o = *a; *a += v; return o; }
+static inline int atomicAdd(int *a, int v) { int o = *a; *a += v; return o; }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T, int) { return T(0); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 

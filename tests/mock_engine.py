@@ -23,12 +23,13 @@ class MockEngine:
         self.with_bonds = True
     def set_rigid_waters(self, t, doh, dhh, mo=15.999, mh=1.008): self.rigid = (t, doh, dhh)
     def set_virtual_sites(self, q, a, b): self.vs = (q, a, b)
+    def set_hbond_constraints(self, c, l): self.hc = (c, l)
     def set_thermostat(self, kind, T, g, seed=0):
         self.lgv = (T, g, seed) if kind == 1 else None; self.csvr = (T, g, seed) if kind == 2 else None
     def set_pme(self, *K): self.pme = K
     def _w(self): return dict(self.w, xyzq=self.x, vel=self.v)
     def step(self, dt, n):
-        r = O.md_run(dict(self._w(), dt=dt), n, precision=32, with_bonds=getattr(self, "with_bonds", False), rigid_waters=self.rigid,
+        r = O.md_run(dict(self._w(), dt=dt), n, precision=32, with_bonds=getattr(self, "with_bonds", False), rigid_waters=self.rigid, hbond_constraints=getattr(self, "hc", None),
                      virtual_sites=self.vs, langevin=self.lgv, csvr=self.csvr)
         self.x, self.v = r["xyzq"], r["vel"]
     def compute_forces(self): pass

@@ -62,10 +62,28 @@ def main():
     m4 = x4[:, :3].astype(np.float64).reshape(-1, 4, 3)
     mi = lambda v: v - np.rint(v / ext4) * ext4
     msite = np.abs(mi(m4[:, 3] - (m4[:, 0] + a * mi(m4[:, 1] - m4[:, 0]) + b * mi(m4[:, 2] - m4[:, 0])))).max()
+    # bonds to hydrogen by SHAKE: C1 water with its O-H bonds as (O, H, H) clusters, the H-H spring kept
+    wc = dict(W.water_box_c1(), dt=0.001)
+    idx = np.arange(len(wc["xyzq"]), dtype=np.int32).reshape(-1, 3)
+    clusters = np.concatenate([idx, np.full((len(idx), 1), -1, np.int32)], 1)
+    lengths = np.tile(np.array([[D_OH, D_OH, 1.0]], np.float32), (len(idx), 1))
+    e = MdEngine.from_workload(wc)
+    e.set_bonded(wc["bonds"], wc["bond_kr0"])
+    e.set_hbond_constraints(clusters, lengths)
+    e.step(wc["dt"], 40)
+    xc = e.positions()
+    e.close()
+    refc = O.md_run(wc, 40, precision=64, with_bonds=True, hbond_constraints=(clusters, lengths))
+    okc, worstc, _ = trajectory_close(xc, refc["xyzq"], wc["xyzq"], wc["box_ext"])
+    mc = xc[:, :3].astype(np.float64).reshape(-1, 3, 3)
+    extc = np.asarray(wc["box_ext"], np.float64)
+    dc = lambda a, b: np.linalg.norm((a - b) - np.rint((a - b) / extc) * extc, axis=1)
+    res.update(shake_traj_ok=bool(okc), shake_traj_worst=float(worstc),
+               shake_len_err=float(max(np.abs(dc(mc[:, 0], mc[:, 1]) - D_OH).max(), np.abs(dc(mc[:, 0], mc[:, 2]) - D_OH).max())))
     res.update(opc_traj_ok=bool(ok4), opc_traj_worst=float(worst4), opc_msite_err=float(msite),
                opc_m_force=float(np.abs(f4[3::4, :3]).max()))
     good = (res["traj_ok"] and res["geom_err"] < 2e-5 and abs(res["temperature"] - res["temperature_ref"]) < 0.03 * res["temperature_ref"] and res["opc_traj_ok"] and
-            res["opc_msite_err"] < 5e-6 and res["opc_m_force"] == 0.0)
+            res["opc_msite_err"] < 5e-6 and res["opc_m_force"] == 0.0 and res["shake_traj_ok"] and res["shake_len_err"] < 2e-5)
     print(json.dumps(res))
     return 0 if good else 1
 

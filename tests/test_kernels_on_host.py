@@ -118,6 +118,39 @@ def test_settle_and_virtual_site_kernels(K, oracle):
         L.orc_set_virtual_sites(C.c_int(0), None, C.c_float(0), C.c_float(0))
 
 
+def test_shake_h_kernel(K, oracle):
+    """Bonds to hydrogen in a periodic box, shuffled slots: the kernel (old positions from x' - v dt) against the oracle's
+    fp64 SHAKE that is given the true old positions."""
+    w = W.water_box_c1()
+    n = len(w["xyzq"])
+    ext = np.ascontiguousarray(w["box_ext"], np.float32)
+    dt = np.float32(0.001)
+    idx = np.arange(n, dtype=np.int32).reshape(-1, 3)
+    clusters = np.ascontiguousarray(np.concatenate([idx, np.full((len(idx), 1), -1, np.int32)], 1))
+    clusters[::2, 2] = -1                                     # every other cluster constrains one bond only
+    lengths = np.tile(np.array([[0.9572, 0.9572, 1.0]], np.float32), (len(idx), 1))
+    so, orig = _shuffle(n, 5)
+    x0 = w["xyzq"].copy()
+    x0[:, :3] = np.mod(x0[:, :3], ext)
+    v = w["vel"].copy()
+    x1 = x0.copy()
+    x1[:, :3] += v[:, :3] * dt
+    xs, vs = np.ascontiguousarray(x1[orig]), np.ascontiguousarray(v[orig])
+    bad = K.host_shake_h(len(clusters), _p(clusters), _p(lengths), _p(so), _p(xs), _p(vs), _p(ext), 1, C.c_float(dt), C.c_float(1e-6))
+    assert bad == 0
+    L = oracle.lib()
+    xr, vr = x1.copy(), v.copy()
+    L.orc_set_hbond_constraints(C.c_int(len(clusters)), _p(clusters), _p(lengths))
+    try:
+        L.orc_shake_h(_p(x0), _p(xr), _p(vr), _p(ext), C.c_int(1), C.c_float(dt))
+    finally:
+        L.orc_set_hbond_constraints(C.c_int(0), None, None)
+    assert np.abs(xs[so][:, :3] - xr[:, :3]).max() < 6e-6
+    assert np.abs(vs[so][:, :3] - vr[:, :3]).max() < 6e-6 / dt
+    moved = np.abs(xs[so][:, :3] - x1[:, :3]).max(1) > 0
+    assert moved[clusters[1::2, 2]].all() and not moved[idx[::2, 2]].any()       # unconstrained hydrogens are left alone
+
+
 def test_langevin_kernel(K, oracle):
     rng = np.random.default_rng(8)
     n = 3000

@@ -184,3 +184,81 @@ def test_oracle_four_site_water_md(oracle):
     e = r["energies"]
     tot = e[:, 0] + e[:, 1] + e[:, 3]
     assert np.abs(tot[20:] - tot[20]).max() < 0.03 * e[20:, 3].mean(), (tot[20], tot[-1], e[20:, 3].mean())
+
+
+def test_hydrogen_bond_shake_header_and_oracle(host_math, oracle):
+    """Clusters of a heavy atom with 1-3 hydrogens: the device arithmetic (shake_terms.h, Gauss-Seidel in fp32 to 1e-6)
+    and the oracle (fp64, opposite sweep order, 1e-13) land on the same constrained positions; lengths hold; the
+    centre of mass of every cluster is untouched."""
+    rng = np.random.default_rng(21)
+    n = 900
+    nh = rng.integers(1, 4, n).astype(np.int32)
+    m_heavy = rng.choice([12.011, 14.007, 15.999], n)
+    inv_m = np.zeros((n, 4), np.float32)
+    inv_m[:, 0] = 1.0 / m_heavy
+    inv_m[:, 1:] = 1.0 / 1.008
+    d = rng.uniform(0.95, 1.12, (n, 3)).astype(np.float32)
+    x0 = np.zeros((n, 4, 3))
+    x0[:, 0] = rng.uniform(-25, 25, (n, 3))
+    for k in range(3):
+        u = rng.normal(size=(n, 3))
+        u /= np.linalg.norm(u, axis=1, keepdims=True)
+        x0[:, 1 + k] = x0[:, 0] + u * d[:, k:k + 1]
+    x0 = x0.astype(np.float32).astype(np.float64)
+    x1 = (x0 + rng.normal(0, 0.03, x0.shape)).astype(np.float32).astype(np.float64)
+    out = np.zeros((n, 12), np.float32)
+    a0, a1 = np.ascontiguousarray(x0.reshape(n, 12), np.float32), np.ascontiguousarray(x1.reshape(n, 12), np.float32)
+    sweeps = host_math.shake_host_eval(C.c_int64(n), nh.ctypes.data_as(C.c_void_p), a0.ctypes.data_as(C.c_void_p),
+                                       a1.ctypes.data_as(C.c_void_p), inv_m.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                                       C.c_float(1e-6), out.ctypes.data_as(C.c_void_p))
+    assert 1 < sweeps <= 64
+    o = out.reshape(n, 4, 3).astype(np.float64)
+    # the oracle on the same clusters, laid out as a 4n-atom system
+    xo = np.zeros((4 * n, 4), np.float32)
+    xn = np.zeros((4 * n, 4), np.float32)
+    vel = np.zeros((4 * n, 4), np.float32)
+    xo[:, :3], xn[:, :3] = x0.reshape(-1, 3), x1.reshape(-1, 3)
+    vel[:, 3] = inv_m.reshape(-1)
+    clusters = np.arange(4 * n, dtype=np.int32).reshape(n, 4)
+    for k in range(3):
+        clusters[nh <= k, 1 + k] = -1
+    L = oracle.lib()
+    L.orc_set_hbond_constraints(C.c_int(n), clusters.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p))
+    try:
+        L.orc_shake_h(xo.ctypes.data_as(C.c_void_p), xn.ctypes.data_as(C.c_void_p), vel.ctypes.data_as(C.c_void_p), None, C.c_int(0),
+                      C.c_float(0.002))
+    finally:
+        L.orc_set_hbond_constraints(C.c_int(0), None, None)
+    ref = xn[:, :3].astype(np.float64).reshape(n, 4, 3)
+    mass = 1.0 / inv_m.astype(np.float64)
+    for k in range(3):
+        live = nh > k
+        assert np.abs(np.linalg.norm(o[live, 1 + k] - o[live, 0], axis=1) - d[live, k]).max() < 6e-6
+        assert np.abs(o[live, 1 + k] - ref[live, 1 + k]).max() < 8e-6
+        assert np.array_equal(out.reshape(n, 4, 3)[~live, 1 + k], a1.reshape(n, 4, 3)[~live, 1 + k])   # unused slots untouched
+        mass[~live, 1 + k] = 0.0
+    assert np.abs(o[:, 0] - ref[:, 0]).max() < 8e-6
+    com = lambda p: (p * mass[:, :, None]).sum(1) / mass.sum(1)[:, None]
+    assert np.abs(com(o) - com(x1)).max() < 5e-6
+    # the velocity correction of the oracle is the position change over dt
+    assert np.allclose(vel[:, :3].reshape(n, 4, 3)[:, 0], (ref[:, 0] - x1[:, 0]) / 0.002, atol=2e-3)
+
+
+def test_oracle_md_with_hydrogen_constraints(oracle):
+    """C1 water with its two O-H bonds constrained as one (O, H, H) cluster and the H-H spring kept (a flexible angle):
+    1 fs steps, the constrained lengths hold and the total energy stays put once the first step has removed the
+    bond-direction velocities."""
+    w = dict(W.water_box_c1(), dt=0.001)
+    n = len(w["xyzq"])
+    idx = np.arange(n, dtype=np.int32).reshape(-1, 3)
+    clusters = np.concatenate([idx, np.full((len(idx), 1), -1, np.int32)], 1)
+    lengths = np.tile(np.array([[D_OH, D_OH, 1.0]], np.float32), (len(idx), 1))
+    r = oracle.md_run(w, 120, precision=64, want_energies=True, with_bonds=True, hbond_constraints=(clusters, lengths))
+    x = r["xyzq"][:, :3].astype(np.float64).reshape(-1, 3, 3)
+    ext = np.asarray(w["box_ext"], np.float64)
+    d = lambda a, b: np.linalg.norm((a - b) - np.rint((a - b) / ext) * ext, axis=1)
+    assert np.abs(d(x[:, 0], x[:, 1]) - D_OH).max() < 1e-5 and np.abs(d(x[:, 0], x[:, 2]) - D_OH).max() < 1e-5
+    assert np.abs(d(x[:, 1], x[:, 2]) - D_HH).max() > 1e-3          # the angle is free
+    e = r["energies"]
+    tot = e[:, 0] + e[:, 1] + e[:, 2] + e[:, 3]
+    assert np.abs(tot[20:] - tot[20]).max() < 0.02 * e[20:, 3].mean(), (tot[20], tot[-1], e[20:, 3].mean())
