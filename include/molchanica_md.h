@@ -217,6 +217,12 @@ int mc_get_velocities(mc_ctx *ctx, mc_float4 *out);
 int mc_get_forces(mc_ctx *ctx, mc_float4 *out);
 int mc_get_energy(mc_ctx *ctx, mc_energy *out);
 int mc_get_stats(mc_ctx *ctx, mc_stats *out);
+/* SnapshotEnergyData.energy_potential_between_mols (src/md/mod.rs:1242-1245): mol_id[n] assigns every atom to a molecule;
+ * mc_get_energy_between_mols sums the nonbonded pair energies (LJ + the Coulomb form in force, within the cutoffs)
+ * over the listed pairs whose atoms belong to different molecules.  On demand, not on the step path; excluded
+ * pairs and the reciprocal part of SPME are not in it.  Single-GPU handles; NULL clears the ids. */
+int mc_set_molecule_ids(mc_ctx *ctx, const uint16_t *mol_id);
+int mc_get_energy_between_mols(mc_ctx *ctx, double *out);
 
 /* Asynchronous snapshot hand-off (the Snapshot queue of src/md/mod.rs:118-152): mc_snapshot_begin
  * stages the current positions on the device and starts their copy to `out_positions` on a second

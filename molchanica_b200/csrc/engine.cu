@@ -229,6 +229,7 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
     c->n_waters = 0;
     c->n_vsites = 0;
     c->n_hclusters = c->n_hconstraints = 0;
+    c->have_mols = false;
     c->n_pairs_listed = 0;
     c->total_mass = 0.0;
     c->pme.self_q2 = 0.0;
@@ -1089,6 +1090,32 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
     // each rigid water removes three degrees of freedom, each constrained bond one
     const double dof = 3.0 * h[2] - 3.0 * (double)c->n_waters - (double)c->n_hconstraints;
     out->temperature = dof > 0 ? 2.0 * out->energy_kinetic / (dof * MC_KB) : 0.0;
+    return MC_OK;
+}
+
+extern "C" int mc_set_molecule_ids(mc_ctx *c, const uint16_t *mol_id) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, !c->comm_active, "mc_set_molecule_ids: not available on a decomposed handle yet");
+    if (!mol_id) { c->have_mols = false; return MC_OK; }
+    MC_CUDA(c, c->mol_of_orig.ensure((size_t)std::max<int64_t>(c->n_global, 1)));
+    if (c->n_global) MC_CUDA(c, cudaMemcpy(c->mol_of_orig.p, mol_id, sizeof(uint16_t) * (size_t)c->n_global, cudaMemcpyHostToDevice));
+    c->have_mols = true;
+    return MC_OK;
+}
+
+extern "C" int mc_get_energy_between_mols(mc_ctx *c, double *out) {
+    if (!c || !out) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, c->have_mols, "mc_get_energy_between_mols: call mc_set_molecule_ids first");
+    int rc = ensure_ready(c, "mc_get_energy_between_mols");
+    if (rc != MC_OK) return rc;
+    MC_CUDA(c, c->red_out.ensure(4));
+    launch_between_mols((int)c->n_rows_sorted(), (int)c->row0, c->xyzq[c->cur].p, c->type[c->cur].p, c->orig[c->cur].p, c->mol_of_orig.p,
+                        c->nbr_start.p, c->nbr_count.p, c->nbr_list.p, c->ljtab.p, make_params(c), c->lj_disabled ? 0 : 1,
+                        c->coul_disabled ? MC_COULOMB_NONE : c->coul_mode, c->red_out.p + 3, c->st, &c->launches);
+    MC_CUDA(c, cudaMemcpyAsync(out, c->red_out.p + 3, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
     return MC_OK;
 }
 

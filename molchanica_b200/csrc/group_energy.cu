@@ -1,0 +1,57 @@
+// group_energy.cu -- interaction energy between molecules on demand (SnapshotEnergyData.energy_potential_between_mols,
+// reference src/md/mod.rs:1242-1245): the sum of the nonbonded pair energies over the listed pairs whose atoms carry
+// different molecule ids.  One thread per list row, the row's partners gathered like the force kernel does; the
+// cutoff decision uses the same fp32 r^2 expression.  Runs only when mc_get_energy_between_mols is called.
+// STATUS: arithmetic and kernel source verified on the host (tests/test_kernels_on_host.py), not yet run on hardware.
+#include "group_energy.cuh"
+#include "pair_energy_terms.h"
+
+namespace {
+
+__global__ void __launch_bounds__(128) between_mols_kernel(int n_rows, int row0, const float4 *__restrict__ xyzq,
+                                                            const uint16_t *__restrict__ type, const int *__restrict__ orig,
+                                                            const uint16_t *__restrict__ mol_of_orig,
+                                                            const uint32_t *__restrict__ nbr_start, const uint32_t *__restrict__ nbr_count,
+                                                            const uint32_t *__restrict__ nbr_list, const float2 *__restrict__ ljtab,
+                                                            const NbParams p, int lj_on, int coul_mode, double *__restrict__ energy) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    float e = 0.f;
+    if (r < n_rows) {
+        const int i = row0 + r;
+        const float4 xi = xyzq[i];
+        const int ti = type[i];
+        const uint16_t mi = mol_of_orig[orig[i]];
+        const uint32_t s = nbr_start[i], cnt = nbr_count[i];
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const uint32_t j = nbr_list[s + k];
+            if (mol_of_orig[orig[j]] == mi) continue;
+            const float4 xj = xyzq[j];
+            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            if (p.periodic) {
+                dx = __fmaf_rn(-rintf(dx * p.inv_ext[0]), p.ext[0], dx);
+                dy = __fmaf_rn(-rintf(dy * p.inv_ext[1]), p.ext[1], dy);
+                dz = __fmaf_rn(-rintf(dz * p.inv_ext[2]), p.ext[2], dz);
+            }
+            const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            const float2 lj = ljtab[ti * p.n_types + type[j]];
+            e += mc_pair_energy(r2, lj.x, lj.y, xi.w * xj.w, p.rc2_lj, p.rc2_q, lj_on, coul_mode, p.alpha);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) e += __shfl_xor_sync(MC_FULL_MASK, e, d);
+    if ((threadIdx.x & 31) == 0 && e != 0.f) atomicAdd(energy, 0.5 * (double)e);  // every pair sits in two rows
+}
+
+}  // namespace
+
+#ifndef MC_HOST_SHIM
+void launch_between_mols(int n_rows, int row0, const float4 *xyzq, const uint16_t *type, const int *orig, const uint16_t *mol_of_orig,
+                         const uint32_t *nbr_start, const uint32_t *nbr_count, const uint32_t *nbr_list, const float2 *ljtab,
+                         const NbParams &p, int lj_on, int coul_mode, double *energy, cudaStream_t st, int64_t *launches) {
+    cudaMemsetAsync(energy, 0, sizeof(double), st);
+    if (n_rows <= 0) return;
+    between_mols_kernel<<<div_up((size_t)n_rows, 128), 128, 0, st>>>(n_rows, row0, xyzq, type, orig, mol_of_orig, nbr_start, nbr_count,
+                                                                     nbr_list, ljtab, p, lj_on, coul_mode, energy);
+    *launches += 1;
+}
+#endif

@@ -109,6 +109,15 @@ class MdEngine:
         m, i, p = pair(dihedrals, dihedral_prm, 4)
         self._chk(self._L.mc_set_dihedrals(self._h, m, _ptr(i), _ptr(p)))
 
+    def energy_between_mols(self, mol_id):
+        """mc_set_molecule_ids + mc_get_energy_between_mols: nonbonded energy between atoms of different molecules."""
+        m = np.ascontiguousarray(mol_id, np.uint16)
+        assert len(m) == self.n
+        self._chk(self._L.mc_set_molecule_ids(self._h, _ptr(m)))
+        out = C.c_double(0.0)
+        self._chk(self._L.mc_get_energy_between_mols(self._h, C.byref(out)))
+        return float(out.value)
+
     def set_hbond_constraints(self, clusters, lengths):
         """clusters (m, 4): heavy atom + up to three hydrogens (-1 = unused); lengths (m, 3)."""
         if clusters is None or len(clusters) == 0:

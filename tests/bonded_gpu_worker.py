@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from molchanica_b200 import workloads as W  # noqa: E402
 from molchanica_b200.engine import MdEngine  # noqa: E402
 from oracle import oracle_py as O  # noqa: E402
-from util import FORCE_RTOL, trajectory_close  # noqa: E402
+from util import FORCE_RTOL, between_mols_reference, trajectory_close  # noqa: E402
 
 
 def main():
@@ -54,7 +54,18 @@ def main():
     en = e.energy()
     res.update(traj_ok=bool(ok), traj_worst=float(worst), density=float(en["density"]), e_bond=float(en["energy_bond"]))
     e.close()
-    good = (res["force_err"] < 2 * FORCE_RTOL and res["energy_rel"] < 2e-5 and res["sum_ok"] and res["no_terms_zero"] and
+    # 4. interaction energy between molecules (protein against every water), on demand
+    ws = W.solvated_c3(n_protein=300, n_water=500, L=30.0)
+    mol = np.zeros(len(ws["xyzq"]), np.uint16)
+    mol[300:] = 1 + (np.arange(len(mol) - 300) // 3).astype(np.uint16)
+    e = MdEngine.from_workload(ws)
+    e.compute_forces()
+    e_between = e.energy_between_mols(mol)
+    e.close()
+    s_, i_ = O.neighbors(ws)
+    want_b = between_mols_reference(ws, mol, s_, i_)
+    res["between_rel"] = float(abs(e_between - want_b) / max(abs(want_b), 1.0))
+    good = (res["between_rel"] < 2e-5 and res["force_err"] < 2 * FORCE_RTOL and res["energy_rel"] < 2e-5 and res["sum_ok"] and res["no_terms_zero"] and
             res["bad_id_rejected"] and res["traj_ok"] and 0.9 < res["density"] < 1.1 and res["e_bond"] > 0)
     print(json.dumps(res))
     return 0 if good else 1

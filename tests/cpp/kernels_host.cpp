@@ -9,6 +9,7 @@
 #include "../../molchanica_b200/csrc/settle.cu"
 #include "../../molchanica_b200/csrc/thermostat.cu"
 #include "../../molchanica_b200/csrc/pme.cu"
+#include "../../molchanica_b200/csrc/group_energy.cu"
 
 #define FOR_THREADS(n) gridDim.x = (unsigned)(n); for (blockIdx.x = 0; blockIdx.x < (unsigned)(n); ++blockIdx.x)
 
@@ -64,6 +65,17 @@ void host_csvr(int n, float4 *vel, const double *red3, double kT, double c, doub
                float *lambda) {
     FOR_THREADS(3) csvr_lambda_kernel(red3, kT, c, dof_removed, seed, step, lambda);
     FOR_THREADS(n + 9) csvr_scale_kernel(n, vel, lambda);
+}
+
+double host_between_mols(int n, const float4 *xyzq, const uint16_t *type, const int *orig, const uint16_t *mol_of_orig,
+                         const uint32_t *nbr_start, const uint32_t *nbr_count, const uint32_t *nbr_list, const float2 *ljtab, int n_types,
+                         const float *ext, int periodic, float rc_lj, float rc_q, int lj_on, int coul_mode, float alpha) {
+    NbParams p = nb(ext, periodic, alpha);
+    p.rc2_lj = rc_lj * rc_lj; p.rc2_q = rc_q * rc_q; p.n_types = n_types;
+    double e = 0.0;
+    FOR_THREADS(((n + 127) / 128) * 128) between_mols_kernel(n, 0, xyzq, type, orig, mol_of_orig, nbr_start, nbr_count, nbr_list, ljtab, p,
+                                                             lj_on, coul_mode, &e);
+    return e;
 }
 
 static PmeGeom geom(const int *K, const float *lo, const float *ext) {

@@ -35,6 +35,9 @@ static inline double atomicAdd(double *a, double v) { double o = *a; *a += v; re
 static inline int atomicAdd(int *a, int v) { int o = *a; *a += v; return o; }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T, int) { return T(0); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
 
 typedef void *cudaStream_t;
 typedef int cudaError_t;

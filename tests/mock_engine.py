@@ -62,4 +62,8 @@ class MockEngine:
         ke = 0.5 * (m[:, None] * self.v[:, :3].astype(np.float64) ** 2).sum() / 418.4
         nm = int((self.v[:, 3] > 0).sum()); nw = 0 if self.rigid is None else len(self.rigid[0])
         return float(2 * ke / ((3 * nm - 3 * nw) * 0.0019872041))
+    def energy_between_mols(self, mol):
+        from util import between_mols_reference
+        w = self._w(); s_, i_ = O.neighbors(w)
+        return between_mols_reference(w, np.asarray(mol), s_, i_)
     def close(self): pass

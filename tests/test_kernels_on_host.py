@@ -151,6 +151,35 @@ def test_shake_h_kernel(K, oracle):
     assert moved[clusters[1::2, 2]].all() and not moved[idx[::2, 2]].any()       # unconstrained hydrogens are left alone
 
 
+@pytest.mark.parametrize("coul_mode", [1, 2])
+def test_between_molecules_energy_kernel(coul_mode, K, oracle):
+    """energy_potential_between_mols: protein globule (molecule 0) against every water (molecules 1..): the kernel on the
+    engine's kind of list (rows in a shuffled slot order) against a direct fp64 sum over the oracle's neighbour list."""
+    w = W.solvated_c3(n_protein=300, n_water=500, L=30.0)
+    w = dict(w, coul_mode=coul_mode)
+    n = len(w["xyzq"])
+    mol = np.zeros(n, np.uint16)
+    mol[300:] = 1 + (np.arange(n - 300) // 3).astype(np.uint16)
+    start, idx = oracle.neighbors(w)
+    so, orig = _shuffle(n, 13)
+    xs = np.ascontiguousarray(w["xyzq"][orig])
+    ts = np.ascontiguousarray(w["type"][orig].astype(np.uint16))
+    counts = (start[1:] - start[:-1])[orig].astype(np.uint32)
+    nstart = np.zeros(n, np.uint32)
+    nstart[1:] = np.cumsum(counts)[:-1]
+    nlist = np.concatenate([so[idx[start[o]:start[o + 1]]] for o in orig]).astype(np.uint32)
+    tab = np.ascontiguousarray(w["ljtab"], np.float32)                      # (T, T, 2): sigma, eps
+    T = tab.shape[0]
+    dev_tab = np.stack([tab[..., 0] ** 2, 24.0 * tab[..., 1]], -1).astype(np.float32)
+    ext = np.ascontiguousarray(w["box_ext"], np.float32)
+    K.host_between_mols.restype = C.c_double
+    got = K.host_between_mols(n, _p(xs), _p(ts), _p(orig), _p(mol), _p(nstart), _p(counts), _p(nlist), _p(dev_tab), T, _p(ext), 1,
+                              C.c_float(w["rc_lj"]), C.c_float(w["rc_q"]), 1, coul_mode, C.c_float(0.35))
+    from util import between_mols_reference
+    want = between_mols_reference(w, mol, start, idx)
+    assert want != 0.0 and abs(got - want) < 2e-5 * max(abs(want), 1.0), (got, want)
+
+
 def test_langevin_kernel(K, oracle):
     rng = np.random.default_rng(8)
     n = 3000

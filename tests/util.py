@@ -56,3 +56,37 @@ def trajectory_close(x_test, x_truth, x0, ext=None, rtol=2e-4):
     scale = max(1.0, float(np.abs(disp).max()))
     err = np.abs(dx).max(1)
     return bool(np.quantile(err, 0.99) < rtol * scale and err.max() < 100 * rtol * scale), float(err.max()), scale
+
+
+def between_mols_reference(w, mol, start, idx, alpha=0.35):
+    """fp64 sum of the nonbonded pair energies over the listed pairs whose atoms carry different molecule ids
+    (SnapshotEnergyData.energy_potential_between_mols): LJ within rc_lj, plain or erfc Coulomb within rc_q."""
+    from math import erfc
+    x = w["xyzq"][:, :3].astype(np.float64)
+    q = w["xyzq"][:, 3].astype(np.float64)
+    tab = np.asarray(w["ljtab"], np.float64)
+    typ = np.asarray(w["type"])
+    L = np.asarray(w["box_ext"], np.float64)
+    total = 0.0
+    for i in range(len(x)):
+        js = idx[start[i]:start[i + 1]]
+        js = js[(js > i) & (mol[js] != mol[i])]
+        if len(js) == 0:
+            continue
+        d = x[i] - x[js]
+        if w["periodic"]:
+            d -= np.rint(d / L) * L
+        r2 = (d * d).sum(1)
+        sig, eps = tab[typ[i], typ[js], 0], tab[typ[i], typ[js], 1]
+        s6 = (sig * sig / r2) ** 3
+        e = np.where(r2 < w["rc_lj"] ** 2, 4 * eps * s6 * (s6 - 1), 0.0)
+        r = np.sqrt(r2)
+        if w["coul_mode"] == 1:
+            ec = q[i] * q[js] / r
+        elif w["coul_mode"] == 2:
+            ec = q[i] * q[js] * np.array([erfc(alpha * v) for v in r]) / r
+        else:
+            ec = np.zeros_like(r)
+        e = e + np.where(r2 < w["rc_q"] ** 2, ec, 0.0)
+        total += float(e.sum())
+    return total
