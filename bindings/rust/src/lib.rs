@@ -88,6 +88,7 @@ extern "C" {
     pub fn mc_set_dihedrals(ctx: *mut McCtx, m: i64, quads: *const i32, pk_n_phase: *const f32) -> c_int;
     pub fn mc_set_thermostat(ctx: *mut McCtx, kind: c_int, temperature_k: f32, gamma_per_ps: f32, seed: u64) -> c_int;
     pub fn mc_set_pme(ctx: *mut McCtx, k1: c_int, k2: c_int, k3: c_int) -> c_int;
+    pub fn mc_pme_suggest(rc: f32, tol: f32, box_ext: *const f32, alpha: *mut f32, grid: *mut i32) -> c_int;
     pub fn mc_set_rigid_waters(ctx: *mut McCtx, m: i64, triples: *const i32, d_oh: f32, d_hh: f32, m_o: f32, m_h: f32) -> c_int;
     pub fn mc_set_hbond_constraints(ctx: *mut McCtx, m: i64, clusters: *const i32, lengths: *const f32) -> c_int;
     pub fn mc_set_virtual_sites(ctx: *mut McCtx, m: i64, quads: *const i32, a: f32, b: f32) -> c_int;

@@ -149,6 +149,9 @@ int mc_set_thermostat(mc_ctx *ctx, int kind, float temperature_k, float gamma_pe
  * evaluation.  Periodic boxes, single-GPU handles; 0, 0, 0 switches it off.  About one grid point per Angstrom with
  * alpha = 0.35 gives forces within ~1e-3 of the exact Ewald sum. */
 int mc_set_pme(mc_ctx *ctx, int k1, int k2, int k3);
+/* Host-only helper (no GPU needed): the Ewald alpha with erfc(alpha rc) / rc <= tol and a grid K_a >= 2 alpha L_a /
+ * (3 tol^(1/5)) rounded up to a product of 2, 3, 5, 7 -- what a caller would pass to mc_set_cutoffs / mc_set_pme. */
+int mc_pme_suggest(float rc, float tol, const float box_ext[3], float *alpha, int32_t grid[3]);
 
 /* Rigid three-site waters (the reference keeps its water rigid with SETTLE, README.md:239):
  * triples[3m] = (O, H1, H2) atom ids; after every drift of mc_step the molecules are put back onto the

@@ -96,6 +96,7 @@ def lib():
     L.mc_set_virtual_sites.argtypes = [vp, i64, vp, f32, f32]
     L.mc_set_thermostat.argtypes = [vp, i32, f32, f32, C.c_uint64]
     L.mc_set_pme.argtypes = [vp, i32, i32, i32]
+    L.mc_pme_suggest.argtypes = [f32, f32, vp, C.POINTER(f32), vp]
     L.mc_set_rigid_waters.argtypes = [vp, i64, vp, f32, f32, f32, f32]
     L.mc_set_cutoffs.argtypes = [vp, f32, f32, f32, i32, f32]
     L.mc_set_overrides.argtypes = [vp, i32, i32]

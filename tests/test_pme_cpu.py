@@ -128,3 +128,26 @@ def test_excluded_pair_correction(host_math):
     f2 = np.zeros((2, 3), np.float32)
     e2 = host_math.pme_host_excl(C.c_int64(2), _p(two), _p(ext), 0, _p(es2), _p(ei2), C.c_float(0.35), _p(f2))
     assert abs(e2 + erf(0.7) / 2.0) < 1e-6 and f2[0, 0] == -f2[1, 0]
+
+
+def test_parameter_suggestion_meets_its_tolerance(engine_lib):
+    """mc_pme_suggest (host only): the suggested alpha bounds the real-space tail, the grid is FFT friendly, and SPME with
+    these parameters is as accurate as asked for against the exact reciprocal sum."""
+    from math import erfc
+    xyzq, ext = _charged_box(n=250, L=22.0, seed=3)
+    alpha, grid = C.c_float(0), np.zeros(3, np.int32)
+    for rc, tol in ((9.0, 1e-4), (12.0, 5e-4), (8.0, 1e-5)):
+        assert engine_lib.mc_pme_suggest(rc, tol, _p(ext), C.byref(alpha), _p(grid)) == 0
+        a = float(alpha.value)
+        assert erfc(a * rc) / rc <= tol * 1.0001 and erfc(0.98 * a * rc) / rc > tol
+        for k in grid:
+            m = int(k)
+            for pr in (2, 3, 5, 7):
+                while m % pr == 0:
+                    m //= pr
+            assert m == 1 and k >= 8
+    assert engine_lib.mc_pme_suggest(9.0, 1e-4, _p(ext), C.byref(alpha), _p(grid)) == 0
+    e_ex, f_ex = P.ewald_recip_exact(xyzq, ext, float(alpha.value), kmax=10)
+    e, f = P.spme(xyzq, np.zeros(3, np.float32), ext, float(alpha.value), tuple(int(k) for k in grid))
+    assert np.abs(f - f_ex).max() < 2e-3 * np.abs(f_ex).max() and abs(e - e_ex) < 1e-3 * abs(e_ex)
+    assert engine_lib.mc_pme_suggest(-1.0, 1e-4, _p(ext), C.byref(alpha), _p(grid)) != 0
