@@ -101,6 +101,7 @@ extern "C" {
     pub fn mc_compute_forces(ctx: *mut McCtx) -> c_int;
     pub fn mc_step(ctx: *mut McCtx, dt: f32, n_steps: c_int, ext_forces: *const f32) -> c_int;
     pub fn mc_last_step_ms(ctx: *mut McCtx) -> f64;
+    pub fn mc_minimize_energy(ctx: *mut McCtx, max_iters: c_int, iters_accepted: *mut c_int, e_initial: *mut f64, e_final: *mut f64) -> c_int;
     pub fn mc_get_positions(ctx: *mut McCtx, out: *mut McFloat4) -> c_int;
     pub fn mc_get_velocities(ctx: *mut McCtx, out: *mut McFloat4) -> c_int;
     pub fn mc_get_forces(ctx: *mut McCtx, out: *mut McFloat4) -> c_int;

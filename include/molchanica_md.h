@@ -214,6 +214,13 @@ int mc_step(mc_ctx *ctx, float dt, int n_steps, const float *ext_forces);
  * steps (kernels, rebuilds and any idle gaps between them). */
 double mc_last_step_ms(mc_ctx *ctx);
 
+/* md.minimize_energy(dev, max_iters, None) (ui/mol_editor.rs:375, mol_alignment.rs:356, properties/sol_shrinking_box.rs:962):
+ * steepest descent along F/m with an adaptive step (accepted moves lengthen it by 1.2, rejected ones are undone and
+ * halve it), at most max_iters trial moves, list rebuilt on the same displacement criterion as mc_step.  Velocities
+ * are preserved.  Returns the number of accepted moves and the potential energy before / after.  Single-GPU handles,
+ * no constraints set. */
+int mc_minimize_energy(mc_ctx *ctx, int max_iters, int *iters_accepted, double *e_initial, double *e_final);
+
 /* ---- read-back (caller-allocated, original atom order) ---------------------------------- */
 int mc_get_positions(mc_ctx *ctx, mc_float4 *out);
 int mc_get_velocities(mc_ctx *ctx, mc_float4 *out);

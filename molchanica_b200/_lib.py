@@ -106,6 +106,7 @@ def lib():
     L.mc_build_neighbors.argtypes = [vp]
     L.mc_compute_forces.argtypes = [vp]
     L.mc_step.argtypes = [vp, f32, i32, vp]
+    L.mc_minimize_energy.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for f in ("mc_get_positions", "mc_get_velocities", "mc_get_forces", "mc_get_positions_global", "mc_get_forces_global"):
         getattr(L, f).argtypes = [vp, vp]
     L.mc_get_energy.argtypes = [vp, C.POINTER(McEnergy)]

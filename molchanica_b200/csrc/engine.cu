@@ -956,6 +956,74 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
 
 extern "C" double mc_last_step_ms(mc_ctx *c) { return c ? c->last_step_ms : 0.0; }
 
+// ---- energy minimisation -----------------------------------------------------------------------------------
+// md.minimize_energy(dev, max_iters, None) (reference ui/mol_editor.rs:375, mol_alignment.rs:356,
+// properties/sol_shrinking_box.rs:962): steepest descent with an adaptive step, built from the step path's own
+// kernels -- velocities are zeroed, one kick + drift of length tau moves every atom along F/m (a quenched MD step:
+// dx = 418.4 F/m tau^2), the displacement flag triggers list rebuilds exactly as in mc_step, and the move is kept
+// when the potential energy went down (tau x 1.2) or undone from a copy in original order (tau x 0.5).
+// STATUS: host logic written after round 1's GPU budget was spent; not yet run on hardware.
+extern "C" int mc_minimize_energy(mc_ctx *c, int max_iters, int *iters_accepted, double *e_initial, double *e_final) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, max_iters >= 0, "mc_minimize_energy: max_iters >= 0 required");
+    MC_REQUIRE(c, !c->comm_active, "mc_minimize_energy: not available on a decomposed handle yet");
+    MC_REQUIRE(c, c->n_waters == 0 && c->n_hclusters == 0, "mc_minimize_energy: constraints are not applied by the minimiser; clear them first");
+    int rc = mc_compute_forces(c);
+    if (rc != MC_OK) return rc;
+    mc_energy en;
+    if ((rc = mc_get_energy(c, &en)) != MC_OK) return rc;
+    double e_cur = en.energy_potential;
+    if (e_initial) *e_initial = e_cur;
+    const int n = (int)c->n;
+    cudaStream_t st = c->st;
+    MC_CUDA(c, c->min_x.ensure((size_t)std::max(n, 1)));
+    MC_CUDA(c, c->min_v.ensure((size_t)std::max(n, 1)));
+    launch_gather_to_orig(n, c->vel[c->cur].p, c->orig[c->cur].p, c->min_v.p, st, &c->launches);
+    float tau = 0.001f;  // ps
+    int accepted = 0, small = 0;
+    int *h_flag = reinterpret_cast<int *>(c->h_pinned) + 8;
+    for (int it = 0; it < max_iters && n > 0; ++it) {
+        launch_gather_to_orig(n, c->xyzq[c->cur].p, c->orig[c->cur].p, c->min_x.p, st, &c->launches);
+        launch_zero_velocities(n, c->vel[c->cur].p, st, &c->launches);
+        launch_kick_drift(n, c->xyzq[c->cur].p, c->vel[c->cur].p, c->force.p, nullptr, c->orig[c->cur].p, c->flags[c->cur].p, c->xref.p,
+                          tau, tau, 0.5f * c->skin, 0.f, c->rebuild_flag.p, st, &c->launches);
+        MC_CUDA(c, cudaMemcpyAsync(h_flag, c->rebuild_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MC_CUDA(c, cudaStreamSynchronize(st));
+        const bool blew_up = (*h_flag & 2) != 0;
+        if (*h_flag & 1) c->list_valid = false;
+        c->forces_valid = false;
+        double e_try = 0.0;
+        if (!blew_up) {
+            if ((rc = mc_compute_forces(c)) != MC_OK) return rc;
+            if ((rc = mc_get_energy(c, &en)) != MC_OK) return rc;
+            e_try = en.energy_potential;
+        }
+        if (!blew_up && e_try <= e_cur) {
+            small = (e_cur - e_try) <= 1e-9 * std::max(1.0, std::fabs(e_cur)) ? small + 1 : 0;
+            e_cur = e_try;
+            ++accepted;
+            tau = std::min(tau * 1.2f, 0.02f);
+            if (small >= 3) break;  // converged: three accepted moves in a row changed nothing
+        } else {
+            // undo: positions back from the copy in original order (the list may have been rebuilt meanwhile, so
+            // slots are looked up afresh), list rebuilt, forces of the restored positions re-evaluated
+            launch_scatter_from_orig(n, c->min_x.p, c->orig[c->cur].p, c->xyzq[c->cur].p, 0, st, &c->launches);
+            MC_CUDA(c, cudaMemsetAsync(c->rebuild_flag.p, 0, sizeof(int), st));
+            c->list_valid = false;
+            c->forces_valid = false;
+            if ((rc = mc_compute_forces(c)) != MC_OK) return rc;
+            tau *= 0.5f;
+            if (tau < 1e-7f) break;
+        }
+    }
+    launch_scatter_from_orig(n, c->min_v.p, c->orig[c->cur].p, c->vel[c->cur].p, 0, st, &c->launches);
+    MC_CUDA(c, cudaStreamSynchronize(st));
+    if (iters_accepted) *iters_accepted = accepted;
+    if (e_final) *e_final = e_cur;
+    return MC_OK;
+}
+
 // ---- read-back -------------------------------------------------------------------------------------------
 
 static int read_sorted_to_orig(mc_ctx *c, const float4 *sorted, mc_float4 *out) {

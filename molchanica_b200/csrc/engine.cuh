@@ -117,6 +117,7 @@ struct mc_ctx {
     DevBuf<int4> angles, dihedrals;
     DevBuf<float4> dihedral_prm;
     DevBuf<double> bonded_e;   // {E_bond, E_angle, E_dihedral} of the last evaluation that asked for energies
+    DevBuf<float4> min_x, min_v;   // energy minimiser: positions / velocities saved in original order
     bool have_mols = false;    // molecule ids for energy_potential_between_mols (group_energy.cu)
     DevBuf<uint16_t> mol_of_orig;
     bool csvr = false;         // CSVR thermostat (thermostat.cu); lgv_gamma then holds 1 / tau
@@ -190,7 +191,7 @@ struct mc_ctx {
         for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_ids[b].release(); }
         bonds.release(); bond_kr0.release(); angle_kt0.release(); angles.release(); dihedrals.release(); dihedral_prm.release();
         bonded_e.release(); waters.release(); vsites.release(); csvr_lambda.release();
-        hclusters.release(); hdist.release(); shake_fail.release(); mol_of_orig.release();
+        hclusters.release(); hdist.release(); shake_fail.release(); mol_of_orig.release(); min_x.release(); min_v.release();
     }
 
     // resolve the CUDA-event pairs recorded since the last call (stream must be idle)

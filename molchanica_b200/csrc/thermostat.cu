@@ -43,9 +43,24 @@ __global__ void __launch_bounds__(256) csvr_scale_kernel(int n_rows, float4 *__r
     vel[i] = v;
 }
 
+// velocities to zero, inverse masses kept: the quench between two steps of the energy minimiser (engine.cu)
+__global__ void __launch_bounds__(256) zero_velocities_kernel(int n_rows, float4 *__restrict__ vel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    float4 v = vel[i];
+    v.x = v.y = v.z = 0.f;
+    vel[i] = v;
+}
+
 }  // namespace
 
 #ifndef MC_HOST_SHIM
+void launch_zero_velocities(int n_rows, float4 *vel, cudaStream_t st, int64_t *launches) {
+    if (n_rows <= 0) return;
+    zero_velocities_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(n_rows, vel);
+    *launches += 1;
+}
+
 void launch_csvr(int n_rows, float4 *vel, const double *red3, double kT, double c, double dof_removed, uint64_t seed, uint64_t step,
                  float *lambda, cudaStream_t st, int64_t *launches) {
     if (n_rows <= 0) return;

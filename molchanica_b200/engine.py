@@ -187,6 +187,12 @@ class MdEngine:
         ef = None if ext_forces is None else np.ascontiguousarray(ext_forces, np.float32)
         self._chk(self._L.mc_step(self._h, dt, int(n_steps), _ptr(ef)))
 
+    def minimize_energy(self, max_iters):
+        """mc_minimize_energy: (accepted moves, potential energy before, after)."""
+        k, e0, e1 = C.c_int32(0), C.c_double(0.0), C.c_double(0.0)
+        self._chk(self._L.mc_minimize_energy(self._h, int(max_iters), C.byref(k), C.byref(e0), C.byref(e1)))
+        return int(k.value), float(e0.value), float(e1.value)
+
     def last_step_ms(self):
         return self._L.mc_last_step_ms(self._h)
 

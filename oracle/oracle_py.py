@@ -230,6 +230,48 @@ def _md_run_call(n, xyzq, vel, typ, tab, lo, ext, w, p, es, ei, p14, bonds, kr0,
                           _p(en, C.c_double), _p(fo, C.c_float))
 
 
+def minimize(w, max_iters):
+    """The steepest-descent minimiser of mc_minimize_energy in fp64 (quenched MD moves dx = 418.4 F/m tau^2, tau x 1.2 on an
+    accepted move, undone and tau x 0.5 on a rejected one, stop after three accepted moves without change).  The list
+    is rebuilt at every trial.  Returns dict(xyzq, accepted, e_initial, e_final, energies)."""
+    x = np.array(w["xyzq"], np.float32, copy=True)
+    inv_m = w["vel"][:, 3].astype(np.float64)
+    if w.get("flags") is not None:
+        inv_m = np.where(np.asarray(w["flags"]) & 1, 0.0, inv_m)
+
+    def evaluate(xx):
+        ww = dict(w, xyzq=xx)
+        f, _, en = forces(ww, neighbors(ww), precision=64)
+        e = float(en.sum())
+        if w.get("pairs14") is not None and len(w["pairs14"]):
+            raise NotImplementedError("oracle minimiser: 1-4 pairs not wired")
+        if w.get("bonds") is not None and w.get("_min_bonded"):
+            fb, eb = bonded(ww)
+            f = f.copy()
+            f[:, :3] += fb
+            e += float(eb.sum())
+        return e, f[:, :3].astype(np.float64)
+    e_cur, f = evaluate(x)
+    e0, tau, accepted, small, hist = e_cur, 0.001, 0, 0, [e_cur]
+    for _ in range(max_iters):
+        xt = x.copy()
+        xt[:, :3] = (x[:, :3].astype(np.float64) + 418.4 * f * inv_m[:, None] * tau * tau).astype(np.float32)
+        e_try, f_try = evaluate(xt)
+        if e_try <= e_cur:
+            small = small + 1 if (e_cur - e_try) <= 1e-9 * max(1.0, abs(e_cur)) else 0
+            x, f, e_cur = xt, f_try, e_try
+            accepted += 1
+            hist.append(e_cur)
+            tau = min(tau * 1.2, 0.02)
+            if small >= 3:
+                break
+        else:
+            tau *= 0.5
+            if tau < 1e-7:
+                break
+    return dict(xyzq=x, accepted=accepted, e_initial=e0, e_final=e_cur, energies=np.array(hist))
+
+
 def bonded(w, xyzq=None):
     """fp64 bonded forces (n,3) and energies {bond, angle, dihedral} of the terms a workload carries
     (keys bonds/bond_kr0, angles/angle_kt0, dihedrals/dihedral_prm; missing kinds count as empty)."""

@@ -65,7 +65,20 @@ def main():
     s_, i_ = O.neighbors(ws)
     want_b = between_mols_reference(ws, mol, s_, i_)
     res["between_rel"] = float(abs(e_between - want_b) / max(abs(want_b), 1.0))
-    good = (res["between_rel"] < 2e-5 and res["force_err"] < 2 * FORCE_RTOL and res["energy_rel"] < 2e-5 and res["sum_ok"] and res["no_terms_zero"] and
+    # 5. mc_minimize_energy against the fp64 restatement of the same minimiser: energies go down, velocities survive
+    wm = W.lj_fluid(m=8, temp_k=50.0)
+    e = MdEngine.from_workload(wm)
+    v_before = e.velocities()
+    acc, e0, e1 = e.minimize_energy(40)
+    v_after = e.velocities()
+    x_after = e.positions()
+    e.close()
+    rm = O.minimize(dict(wm, pairs14=None), 40)
+    res.update(min_accepted=acc, min_e0=e0, min_e1=e1, min_ref_e1=float(rm["e_final"]),
+               min_vel_kept=bool(np.array_equal(v_before, v_after)), min_moved=float(np.abs(x_after[:, :3] - wm["xyzq"][:, :3]).max()))
+    min_ok = (acc >= 10 and e1 < e0 and abs(e0 - rm["e_initial"]) < 1e-4 * abs(e0) and
+              abs(e1 - rm["e_final"]) < 0.02 * abs(rm["e_initial"] - rm["e_final"]) + 1e-4 * abs(e1) and res["min_vel_kept"])
+    good = (min_ok and res["between_rel"] < 2e-5 and res["force_err"] < 2 * FORCE_RTOL and res["energy_rel"] < 2e-5 and res["sum_ok"] and res["no_terms_zero"] and
             res["bad_id_rejected"] and res["traj_ok"] and 0.9 < res["density"] < 1.1 and res["e_bond"] > 0)
     print(json.dumps(res))
     return 0 if good else 1

@@ -61,6 +61,8 @@ void host_langevin(int n, float4 *vel, const int *orig, const uint8_t *flags, fl
     FOR_THREADS(n + 5) langevin_ou_kernel(n, vel, orig, flags, c1, c2, kT, seed, step);
 }
 
+void host_zero_velocities(int n, float4 *vel) { FOR_THREADS(n + 11) zero_velocities_kernel(n, vel); }
+
 void host_csvr(int n, float4 *vel, const double *red3, double kT, double c, double dof_removed, uint64_t seed, uint64_t step,
                float *lambda) {
     FOR_THREADS(3) csvr_lambda_kernel(red3, kT, c, dof_removed, seed, step, lambda);

@@ -62,6 +62,10 @@ class MockEngine:
         ke = 0.5 * (m[:, None] * self.v[:, :3].astype(np.float64) ** 2).sum() / 418.4
         nm = int((self.v[:, 3] > 0).sum()); nw = 0 if self.rigid is None else len(self.rigid[0])
         return float(2 * ke / ((3 * nm - 3 * nw) * 0.0019872041))
+    def minimize_energy(self, max_iters):
+        r = O.minimize(dict(self._w(), pairs14=None), max_iters)
+        self.x = r["xyzq"]
+        return r["accepted"], r["e_initial"], r["e_final"]
     def energy_between_mols(self, mol):
         from util import between_mols_reference
         w = self._w(); s_, i_ = O.neighbors(w)

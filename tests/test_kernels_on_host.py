@@ -202,6 +202,14 @@ def test_langevin_kernel(K, oracle):
     assert np.array_equal(vel[:, 3], v0[:, 3])
 
 
+def test_zero_velocities_kernel(K):
+    rng = np.random.default_rng(1)
+    v = rng.normal(size=(777, 4)).astype(np.float32)
+    w0 = v[:, 3].copy()
+    K.host_zero_velocities(777, _p(v))
+    assert np.all(v[:, :3] == 0) and np.array_equal(v[:, 3], w0)
+
+
 def test_csvr_kernels(K, oracle):
     rng = np.random.default_rng(12)
     n = 2000
