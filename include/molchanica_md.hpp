@@ -165,6 +165,14 @@ class MdState {
 
     void rebuild_spatial_caches(const ComputationDevice &) { chk(mc_build_neighbors(ctx_)); }
 
+    // md.minimize_energy(dev, max_iters, None) (ui/mol_editor.rs:375): returns the number of accepted descent moves
+    int minimize_energy(const ComputationDevice &, int max_iters) {
+        int accepted = 0;
+        double e0 = 0, e1 = 0;
+        chk(mc_minimize_energy(ctx_, max_iters, &accepted, &e0, &e1));
+        return accepted;
+    }
+
     // compute_energy_snapshot: one force / energy evaluation on the current positions (src/md/mod.rs:1036)
     SnapshotEnergyData energy_snapshot(const ComputationDevice &) {
         chk(mc_compute_forces(ctx_));
