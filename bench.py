@@ -65,6 +65,16 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        note = None
+        if not self.rows:
+            # the sampler produced nothing (interval refused, process too slow to start): one query right after the region
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=20).stdout
+                self.rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+                note = "sampler returned nothing; single query right after the timed region"
+            except Exception:
+                pass
         sm, mx, reasons = [], None, set()
         for r in self.rows:
             try:
@@ -75,8 +85,10 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def measured_peak():
