@@ -312,7 +312,7 @@ int mc_comm_halo_mode(mc_ctx *ctx, int *fused, char *why, int why_cap);
  * be the local displacement flag: option "rebuild_every" = k > 0 fixes the interval; 0 (default) adapts
  * it at every build from the largest displacement any rank saw in the interval that just ended (the
  * number travels with the build's all-gathered layout table, so all ranks derive the same interval), aiming
- * at 85 % of skin/2.  *interval = steps between builds now in force, *last_disp_frac = that largest
+ * at 75 % of skin/2.  *interval = steps between builds now in force, *last_disp_frac = that largest
  * displacement / (skin/2); mc_stats.n_list_violations counts intervals that overshot. */
 int mc_comm_schedule(mc_ctx *ctx, int *interval, double *last_disp_frac);
 /* Number of atoms this rank currently owns / holds as ghosts. */
