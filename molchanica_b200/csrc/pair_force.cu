@@ -27,6 +27,7 @@
 
 namespace {
 
+#ifndef MC_HOST_SHIM
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -38,6 +39,10 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+#else  // tests/cpp/pair_kernel_host.cpp runs this file's kernels on the CPU: no PTX there
+inline float rcp_approx(float x) { return 1.0f / x; }
+inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
+#endif
 
 struct Acc { float fx, fy, fz, e; };
 
@@ -333,6 +338,7 @@ __global__ void energy_final_kernel(const double *__restrict__ partial, int nb, 
     }
 }
 
+#ifndef MC_HOST_SHIM
 template <int LANES>
 void launch_lanes(const PairLaunch &L, cudaStream_t st) {
     const int rows_per_block = 128 / LANES;
@@ -364,8 +370,11 @@ void launch_lanes(const PairLaunch &L, cudaStream_t st) {
 #undef MC_PF
 }
 
+#endif  // MC_HOST_SHIM
+
 }  // namespace
 
+#ifndef MC_HOST_SHIM
 int pair_force_max_types() { return 160; }  // 160^2 * 8 B = 200 KB of the 227 KB shared memory
 
 cudaError_t pair_force_prepare() {
@@ -418,3 +427,4 @@ void launch_energy_reduce(int n_rows, const float4 *force, const float4 *vel, do
     energy_final_kernel<<<1, 32, 0, st>>>(partial, nb, out3);
     *launches += 2;
 }
+#endif  // MC_HOST_SHIM
