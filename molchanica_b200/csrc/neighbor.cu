@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(128) sort_rows_kernel(int n, const uint32_t *_
 
 }  // namespace
 
+#ifndef MC_HOST_SHIM  // tests/cpp/neighbor_kernels_host.cpp runs the kernels above on the CPU; launches need nvcc
 void launch_bbox(const float4 *xyzq, int n, float *bb, float cw_min, int max_cells, GridParams *g, cudaStream_t st,
                  int64_t *launches) {
     bbox_init_kernel<<<1, 32, 0, st>>>(bb);
@@ -364,3 +365,4 @@ void launch_export_rows(int n, const int *orig, const uint32_t *nbr_count, const
     sort_rows_kernel<<<div_up(n, 4), 128, 0, st>>>(n, start_orig, rows);
     *launches += 3;
 }
+#endif  // MC_HOST_SHIM

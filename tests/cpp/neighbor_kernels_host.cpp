@@ -1,0 +1,87 @@
+// Test infrastructure: the cell-list kernels of neighbor.cu (wrap + cell key, reorder + cell starts + interior flag,
+// the 27-cell sweep with its exact accept test, the vacuum bounding-box grid) compiled unchanged for the host through
+// tests/cpp/shim_mt/cuda_runtime.h and chained the way engine.cu chains them; the radix sort and the prefix scan in
+// between are std::stable_sort and a host loop.  tests/test_neighbor_kernels_on_host.py holds the resulting Verlet
+// list to the oracle's, index for index.  (The production list build, tile_build.cu, is TMA / mbarrier PTX and cannot be
+// run this way; it shares the accept arithmetic with the sweep below and is compared with the oracle on the GPU.)
+#define MC_HOST_SHIM 1
+#define MC_SHIM_SHARED_STATIC 1
+#include "shim_mt/cuda_runtime.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+#include "../../molchanica_b200/csrc/neighbor.cu"
+
+extern "C" {
+
+// xyzq: n x 4 (original order).  Returns the number of list entries; fills (all in CELL order, capacity given by the caller):
+// orig_out[n], flags_out[n], xyzq_sorted[n x 4], nbr_count[n], nbr_start[n] (rows padded to 8), nbr_list[cap].
+// n_cells_out[3] reports the grid.  -1: capacity too small.
+long host_neighbor_list(int n, const float4 *xyzq_in, const float *lo, const float *ext, int periodic, float r_list,
+                        const int32_t *excl_start, const int32_t *excl_idx, int *orig_out, uint8_t *flags_out, float4 *xyzq_sorted,
+                        uint32_t *nbr_count, uint32_t *nbr_start, uint32_t *nbr_list, long cap, int *n_cells_out) {
+    std::vector<float4> x(xyzq_in, xyzq_in + n), xo(n), xref(n), vin(n, float4{0, 0, 0, 1}), vout(n);
+    std::vector<uint16_t> tin(n, 0), tout(n);
+    std::vector<uint8_t> fin(n, 0);
+    std::vector<int> oin(n), slot_of_orig(n);
+    std::iota(oin.begin(), oin.end(), 0);
+    GridParams g;
+    memset(&g, 0, sizeof(g));
+    const double cw_min = (double)r_list * 1.001 + 1e-3;  // engine.cu setup_grid
+    size_t ncell_cap;
+    if (periodic) {
+        long long ncell = 1;
+        for (int a = 0; a < 3; ++a) {
+            int m = (int)std::floor((double)ext[a] / cw_min);
+            m = std::max(1, std::min(m, 1024));
+            g.nc[a] = m; g.lo[a] = lo[a]; g.ext[a] = ext[a];
+            g.inv_ext[a] = 1.0f / ext[a];
+            g.inv_cw[a] = (float)((double)m / (double)ext[a]);
+            ncell *= m;
+        }
+        g.ncell = (int)ncell; g.periodic = 1; g.z_ring = 1; g.kz_off = 0; g.ncz_global = g.nc[2]; g.row_l0 = 0; g.row_l1 = g.nc[2];
+        g.sub_bits = 0;
+        ncell_cap = (size_t)ncell;
+    } else {
+        ncell_cap = std::max<size_t>(4096, std::min<size_t>((size_t)n, (size_t)1 << 22));
+        float bb[8];
+        shim_launch(1, 32, [&] { bbox_init_kernel(bb); });
+        shim_launch(std::min<unsigned>((n + 255) / 256, 1184u), 256, [&] { bbox_kernel(x.data(), n, bb); });
+        shim_launch(1, 32, [&] { grid_from_bbox_kernel(bb, (float)cw_min, (int)ncell_cap, &g); });
+        g.sub_bits = 0;  // the harness sorts on the plain cell id
+    }
+    std::vector<uint32_t> keys(n), vals(n), cell_start(ncell_cap + 2, 0);
+    shim_launch((n + 255) / 256, 256, [&] { wrap_key_kernel(x.data(), n, &g, keys.data(), vals.data()); });
+    std::vector<uint32_t> perm(n);
+    std::iota(perm.begin(), perm.end(), 0u);
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<uint32_t> skeys(n), svals(n);
+    for (int k = 0; k < n; ++k) { skeys[k] = keys[perm[k]]; svals[k] = vals[perm[k]]; }
+    ReorderArrays ra;
+    ra.xyzq_in = x.data(); ra.xyzq_out = xo.data(); ra.xref = xref.data();
+    ra.vel_in = vin.data(); ra.vel_out = vout.data();
+    ra.type_in = tin.data(); ra.type_out = tout.data();
+    ra.flags_in = fin.data(); ra.flags_out = flags_out;
+    ra.orig_in = oin.data(); ra.orig_out = orig_out; ra.slot_of_orig = slot_of_orig.data();
+    ra.cell_start = cell_start.data();
+    ra.mark_interior = 1;
+    shim_launch((n + 1 + 255) / 256, 256, [&] { reorder_kernel(n, skeys.data(), svals.data(), &g, ra); });
+    const float rl2 = r_list * r_list;
+    const unsigned blocks = (unsigned)(((size_t)n * 32 + 255) / 256);
+    shim_launch(blocks, 256, [&] {
+        sweep_kernel<false>(n, xo.data(), cell_start.data(), &g, rl2, skeys.data(), orig_out, excl_start, excl_idx, nbr_count, nullptr, nullptr);
+    });
+    uint64_t total = 0;
+    for (int i = 0; i < n; ++i) { nbr_start[i] = (uint32_t)total; total += (nbr_count[i] + 7u) & ~7u; }
+    if ((long)total > cap) return -1;
+    shim_launch(blocks, 256, [&] {
+        sweep_kernel<true>(n, xo.data(), cell_start.data(), &g, rl2, skeys.data(), orig_out, excl_start, excl_idx, nbr_count, nbr_start, nbr_list);
+    });
+    memcpy(xyzq_sorted, xo.data(), sizeof(float4) * (size_t)n);
+    for (int a = 0; a < 3; ++a) n_cells_out[a] = g.nc[a];
+    return (long)total;
+}
+}

@@ -25,7 +25,11 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__ __restrict
-#define __shared__
+#ifdef MC_SHIM_SHARED_STATIC
+#define __shared__ static   // statically sized shared arrays: one copy for the process = for the one block that runs
+#else
+#define __shared__          // kernels with `extern __shared__`: the harness defines the array under the kernel's name
+#endif
 
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
@@ -69,8 +73,12 @@ template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d) {
     return lane >= d ? got : v;
 }
 static inline unsigned __ballot_sync(unsigned, int pred) {
+    const unsigned t = threadIdx.x, w = t >> 5;
+    shim_block->xchg[t] = pred ? 1u : 0u;
+    shim_block->warp_bar[w]->arrive_and_wait();
     unsigned m = 0;
-    for (int l = 0; l < 32; ++l) m |= (shim_exchange(pred ? 1u : 0u, l) & 1u) << l;  // 32 exchanges: slow but simple
+    for (unsigned l = 0; l < 32 && (w << 5 | l) < blockDim.x; ++l) m |= (unsigned)(shim_block->xchg[w << 5 | l] & 1u) << l;
+    shim_block->warp_bar[w]->arrive_and_wait();
     return m;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
@@ -92,6 +100,19 @@ static inline int atomicOr(int *a, int v) { return std::atomic_ref<int>(*a).fetc
 static inline unsigned atomicAdd(unsigned *a, unsigned v) { return std::atomic_ref<unsigned>(*a).fetch_add(v); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline void __syncwarp(unsigned = 0xffffffffu) { shim_block->warp_bar[threadIdx.x >> 5]->arrive_and_wait(); }
+static inline int atomicMin(int *a, int v) { std::atomic_ref<int> r(*a); int o = r.load(); while (o > v && !r.compare_exchange_weak(o, v)) {} return o; }
+static inline int atomicMax(int *a, int v) { std::atomic_ref<int> r(*a); int o = r.load(); while (o < v && !r.compare_exchange_weak(o, v)) {} return o; }
+static inline unsigned atomicMin(unsigned *a, unsigned v) { std::atomic_ref<unsigned> r(*a); unsigned o = r.load(); while (o > v && !r.compare_exchange_weak(o, v)) {} return o; }
+static inline unsigned atomicMax(unsigned *a, unsigned v) { std::atomic_ref<unsigned> r(*a); unsigned o = r.load(); while (o < v && !r.compare_exchange_weak(o, v)) {} return o; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 #define __expf(x) expf(x)
