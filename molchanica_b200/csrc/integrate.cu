@@ -149,6 +149,7 @@ __global__ void l2_flush_kernel(float4 *buf, size_t n) {
 
 }  // namespace
 
+#ifndef MC_HOST_SHIM  // tests/cpp/integrate_kernels_host.cpp runs the kernels above on the CPU; launches need nvcc
 void launch_kick_drift(int n_rows, float4 *xyzq, float4 *vel, const float4 *force, const float *ext_force,
                        const int *orig, const uint8_t *flags, const float4 *xref, float kick, float drift,
                        float max_disp, float lookahead, int *rebuild_flag, cudaStream_t st, int64_t *launches,
@@ -186,3 +187,4 @@ void launch_l2_flush(float4 *buf, size_t n_float4, cudaStream_t st, int64_t *lau
     l2_flush_kernel<<<1184, 256, 0, st>>>(buf, n_float4);
     *launches += 1;
 }
+#endif  // MC_HOST_SHIM
