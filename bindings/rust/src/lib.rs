@@ -120,6 +120,7 @@ extern "C" {
     pub fn mc_dock_orientation_count(num_orientations: c_int) -> c_int;
     pub fn mc_dock_near_site(n_rec: i64, rec_xyzq: *const McFloat4, rec_hetero: *const u8, site_center: *const f64, site_radius: f64, out_idx: *mut i32, n_out: *mut i64) -> c_int;
     pub fn mc_dock_filter_poses(n_rec: i64, rec_xyzq: *const McFloat4, rec_is_carbon: *const u8, n_lig: i64, lig_xyzq: *const McFloat4, lig_is_carbon: *const u8, lig_anchor: *const f32, vdw_radius: f32, n_poses: i64, poses: *const f32, keep: *mut u8, n_kept: *mut i64) -> c_int;
+    pub fn mc_dock_filter_poses_gpu(ctx: *mut McCtx, n_rec: i64, rec_xyzq: *const McFloat4, rec_is_carbon: *const u8, n_lig: i64, lig_xyzq: *const McFloat4, lig_is_carbon: *const u8, lig_anchor: *const f32, vdw_radius: f32, n_poses: i64, poses: *const f32, keep: *mut u8, n_kept: *mut i64) -> c_int;
     pub fn mc_last_dock_kernel_ms(ctx: *mut McCtx) -> f64;
     pub fn mc_comm_unique_id(id: *mut u8) -> c_int;
     pub fn mc_comm_init(ctx: *mut McCtx, id: *const u8, rank: c_int, n_ranks: c_int) -> c_int;

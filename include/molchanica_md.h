@@ -288,6 +288,11 @@ int mc_dock_near_site(int64_t n_rec, const mc_float4 *rec_xyzq, const uint8_t *r
 int mc_dock_filter_poses(int64_t n_rec, const mc_float4 *rec_xyzq, const uint8_t *rec_is_carbon, int64_t n_lig,
                          const mc_float4 *lig_xyzq, const uint8_t *lig_is_carbon, const float lig_anchor[3],
                          float vdw_radius, int64_t n_poses, const float *poses, uint8_t *keep, int64_t *n_kept);
+/* The same filter on the device (one thread per pose; at most 64 sampled ligand carbons): identical arguments and
+ * result, for pose sets where the serial host loop would cost more than the scoring kernel itself. */
+int mc_dock_filter_poses_gpu(mc_ctx *ctx, int64_t n_rec, const mc_float4 *rec_xyzq, const uint8_t *rec_is_carbon, int64_t n_lig,
+                             const mc_float4 *lig_xyzq, const uint8_t *lig_is_carbon, const float lig_anchor[3],
+                             float vdw_radius, int64_t n_poses, const float *poses, uint8_t *keep, int64_t *n_kept);
 /* CUDA-event duration of the scan kernel of the last mc_dock_score call (profiling on). */
 double mc_last_dock_kernel_ms(mc_ctx *ctx);
 

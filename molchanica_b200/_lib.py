@@ -125,6 +125,7 @@ def lib():
     L.mc_dock_orientation_count.argtypes = [i32]
     L.mc_dock_near_site.argtypes = [i64, vp, vp, vp, C.c_double, vp, C.POINTER(i64)]
     L.mc_dock_filter_poses.argtypes = [i64, vp, vp, i64, vp, vp, vp, f32, i64, vp, vp, C.POINTER(i64)]
+    L.mc_dock_filter_poses_gpu.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, f32, i64, vp, vp, C.POINTER(i64)]
     L.mc_comm_unique_id.argtypes = [vp]
     L.mc_comm_init.argtypes = [vp, vp, i32, i32]
     L.mc_comm_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]

@@ -9,3 +9,8 @@ void launch_dock_score(int n_rec, const float4 *rec, const uint32_t *rec_meta, i
                        cudaStream_t st, int64_t *launches);
 size_t dock_smem_bytes(int n_lig, int n_rec_types, int n_lig_types);
 cudaError_t dock_prepare();
+
+// dock_filter.cu: keep[p] = 0 when a sampled ligand carbon of pose p comes within `limit` of a sampled receptor carbon
+int dock_filter_max_lig();
+void launch_dock_filter(int n_rs, const float4 *rec_sample, int n_ls, const float4 *lig_sample, float3 anchor0, float limit, int n_poses,
+                        const float *poses, uint8_t *keep, cudaStream_t st, int64_t *launches);

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/molchanica_md.h"
+#include "pose_terms.h"
 
 namespace {
 
@@ -137,18 +138,10 @@ extern "C" int mc_dock_filter_poses(int64_t n_rec, const mc_float4 *rec_xyzq, co
     int64_t kept = 0;
     for (int64_t p = 0; p < n_poses; ++p) {
         const float *ps = poses + 7 * p;
-        double qw = ps[3], qx = ps[4], qy = ps[5], qz = ps[6];
-        const double qn = std::sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
-        qw /= qn; qx /= qn; qy /= qn; qz /= qn;
+        const PoseQuat q = mc_pose_quat(ps);
         for (size_t a = 0; a < ls.size(); ++a) {
             const mc_float4 &l = lig_xyzq[ls[a]];
-            const double vx = (double)l.x - (double)lig_anchor[0], vy = (double)l.y - (double)lig_anchor[1],
-                         vz = (double)l.z - (double)lig_anchor[2];
-            const double cx = qy * vz - qz * vy, cy = qz * vx - qx * vz, cz = qx * vy - qy * vx;
-            const double dx = qy * cz - qz * cy, dy = qz * cx - qx * cz, dz = qx * cy - qy * cx;
-            lp[3 * a] = (float)(vx + 2.0 * (qw * cx + dx) + (double)ps[0]);
-            lp[3 * a + 1] = (float)(vy + 2.0 * (qw * cy + dy) + (double)ps[1]);
-            lp[3 * a + 2] = (float)(vz + 2.0 * (qw * cz + dz) + (double)ps[2]);
+            mc_pose_point(q, ps, l.x, l.y, l.z, lig_anchor[0], lig_anchor[1], lig_anchor[2], &lp[3 * a]);
         }
         bool clash = false;
         for (size_t r = 0; r < rs.size() && !clash; ++r) {

@@ -1332,4 +1332,40 @@ extern "C" int mc_dock_score(mc_ctx *c, int64_t n_rec, const mc_float4 *rec_xyzq
     return MC_OK;
 }
 
+// The clash pre-filter on the device (dock_filter.cu); same arguments and result as the host-only mc_dock_filter_poses.
+extern "C" int mc_dock_filter_poses_gpu(mc_ctx *c, int64_t n_rec, const mc_float4 *rec_xyzq, const uint8_t *rec_is_carbon, int64_t n_lig,
+                                        const mc_float4 *lig_xyzq, const uint8_t *lig_is_carbon, const float lig_anchor[3], float vdw_radius,
+                                        int64_t n_poses, const float *poses, uint8_t *keep, int64_t *n_kept) {
+    if (!c) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, rec_xyzq && rec_is_carbon && lig_xyzq && lig_is_carbon && lig_anchor && n_rec >= 0 && n_lig >= 0 && n_poses >= 0 &&
+                      (n_poses == 0 || (poses && keep)),
+               "mc_dock_filter_poses_gpu: NULL or negative argument");
+    std::vector<float4> rs, ls;
+    for (int64_t i = 0; i < n_rec; ++i)
+        if (rec_is_carbon[i] && i % 6 == 0) rs.push_back(make_float4(rec_xyzq[i].x, rec_xyzq[i].y, rec_xyzq[i].z, 0.f));
+    for (int64_t i = 0; i < n_lig; ++i)
+        if (lig_is_carbon[i] && i % 4 == 0) ls.push_back(make_float4(lig_xyzq[i].x, lig_xyzq[i].y, lig_xyzq[i].z, 0.f));
+    MC_REQUIRE(c, (int)ls.size() <= dock_filter_max_lig(), "mc_dock_filter_poses_gpu: more than " + std::to_string(dock_filter_max_lig()) +
+                                                              " sampled ligand carbons");
+    if (n_poses == 0) { if (n_kept) *n_kept = 0; return MC_OK; }
+    cudaStream_t st = c->st;
+    MC_CUDA(c, c->d_rec_s.ensure(std::max<size_t>(rs.size(), 1))); MC_CUDA(c, c->d_lig_s.ensure(std::max<size_t>(ls.size(), 1)));
+    MC_CUDA(c, c->d_poses.ensure((size_t)7 * n_poses)); MC_CUDA(c, c->d_keep.ensure((size_t)n_poses));
+    if (!rs.empty()) MC_CUDA(c, cudaMemcpyAsync(c->d_rec_s.p, rs.data(), rs.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    if (!ls.empty()) MC_CUDA(c, cudaMemcpyAsync(c->d_lig_s.p, ls.data(), ls.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    MC_CUDA(c, cudaMemcpyAsync(c->d_poses.p, poses, sizeof(float) * 7 * n_poses, cudaMemcpyHostToDevice, st));
+    launch_dock_filter((int)rs.size(), c->d_rec_s.p, (int)ls.size(), c->d_lig_s.p, make_float3(lig_anchor[0], lig_anchor[1], lig_anchor[2]),
+                       vdw_radius * 1.1f, (int)n_poses, c->d_poses.p, c->d_keep.p, st, &c->launches);
+    MC_CUDA(c, cudaGetLastError());
+    MC_CUDA(c, cudaMemcpyAsync(keep, c->d_keep.p, (size_t)n_poses, cudaMemcpyDeviceToHost, st));
+    MC_CUDA(c, cudaStreamSynchronize(st));
+    if (n_kept) {
+        int64_t k = 0;
+        for (int64_t p = 0; p < n_poses; ++p) k += keep[p] ? 1 : 0;
+        *n_kept = k;
+    }
+    return MC_OK;
+}
+
 extern "C" double mc_last_dock_kernel_ms(mc_ctx *c) { return c ? c->last_dock_ms : 0.0; }

@@ -107,7 +107,8 @@ struct mc_ctx {
     DevBuf<float> bbox, ext_force, d_poses, d_scores;
     DevBuf<GridParams> grid;
     DevBuf<double> red_partial, red_out;
-    DevBuf<float4> d_rec, d_lig;
+    DevBuf<float4> d_rec, d_lig, d_rec_s, d_lig_s;
+    DevBuf<uint8_t> d_keep;
     DevBuf<uint32_t> d_rec_meta, d_lig_meta;
 
     // bonded terms (bonded.cu), caller's atom ids
@@ -187,7 +188,7 @@ struct mc_ctx {
         excl_start.release(); excl_idx.release(); p14_start.release(); p14_idx.release();
         ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); d_poses.release(); d_scores.release();
         grid.release(); red_partial.release(); red_out.release(); d_rec.release(); d_lig.release();
-        d_rec_meta.release(); d_lig_meta.release();
+        d_rec_meta.release(); d_lig_meta.release(); d_rec_s.release(); d_lig_s.release(); d_keep.release();
         for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_ids[b].release(); }
         bonds.release(); bond_kr0.release(); angle_kt0.release(); angles.release(); dihedrals.release(); dihedral_prm.release();
         bonded_e.release(); waters.release(); vsites.release(); csvr_lambda.release();

@@ -232,6 +232,34 @@ class MdEngine:
         self._chk(self._L.mc_get_energy(self._h, C.byref(e)))
         return {k: getattr(e, k) for k, _ in e._fields_}
 
+    # -- docking pose set
+    def dock_make_poses(self, site_center, site_radius, num_posits=8, num_orientations=60):
+        c = np.ascontiguousarray(site_center, np.float64)
+        n = C.c_int64(0)
+        self._chk(self._L.mc_dock_make_poses(_ptr(c), float(site_radius), int(num_posits), int(num_orientations), None, 0, C.byref(n)))
+        out = np.zeros((n.value, 7), np.float32)
+        self._chk(self._L.mc_dock_make_poses(_ptr(c), float(site_radius), int(num_posits), int(num_orientations), _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def dock_filter_poses(self, rec_near, rec_is_carbon, lig, lig_is_carbon, lig_anchor, poses, vdw_radius=1.7, gpu=True):
+        """keep mask of the clash pre-filter: on the device (mc_dock_filter_poses_gpu) or with the host twin."""
+        rec = _f4(rec_near)
+        lg = _f4(lig)
+        rc_ = np.ascontiguousarray(rec_is_carbon, np.uint8)
+        lc_ = np.ascontiguousarray(lig_is_carbon, np.uint8)
+        an = np.ascontiguousarray(lig_anchor, np.float32)
+        ps = np.ascontiguousarray(poses, np.float32)
+        keep = np.zeros(len(ps), np.uint8)
+        kept = C.c_int64(0)
+        if gpu:
+            self._chk(self._L.mc_dock_filter_poses_gpu(self._h, len(rec), _ptr(rec), _ptr(rc_), len(lg), _ptr(lg), _ptr(lc_), _ptr(an),
+                                                       vdw_radius, len(ps), _ptr(ps), _ptr(keep), C.byref(kept)))
+        else:
+            rc = self._L.mc_dock_filter_poses(len(rec), _ptr(rec), _ptr(rc_), len(lg), _ptr(lg), _ptr(lc_), _ptr(an), vdw_radius, len(ps),
+                                              _ptr(ps), _ptr(keep), C.byref(kept))
+            assert rc == 0
+        return keep
+
     def halo_mode(self):
         """(fused, why): 1 when the step kernels exchange ghosts over mapped peer memory, else 0 + the reason."""
         fused = C.c_int32(0)

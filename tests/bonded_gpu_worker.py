@@ -78,7 +78,17 @@ def main():
                min_vel_kept=bool(np.array_equal(v_before, v_after)), min_moved=float(np.abs(x_after[:, :3] - wm["xyzq"][:, :3]).max()))
     min_ok = (acc >= 10 and e1 < e0 and abs(e0 - rm["e_initial"]) < 1e-4 * abs(e0) and
               abs(e1 - rm["e_final"]) < 0.02 * abs(rm["e_initial"] - rm["e_final"]) + 1e-4 * abs(e1) and res["min_vel_kept"])
-    good = (min_ok and res["between_rel"] < 2e-5 and res["force_err"] < 2 * FORCE_RTOL and res["energy_rel"] < 2e-5 and res["sum_ok"] and res["no_terms_zero"] and
+    # 6. the clash pre-filter of the docking scan on the device against its host twin
+    d = W.docking_c5(n_rec=1500, n_lig=24, n_poses=64, seeds=(515, 516, 517))
+    e = MdEngine(0)
+    site = d["rec"][:, :3].astype(np.float64).mean(0) + np.array([6.0, 0.0, 0.0])
+    poses = e.dock_make_poses(site, 8.0, 4, 60)
+    k_gpu = e.dock_filter_poses(d["rec"], d["rec_hphob"], d["lig"], d["lig_hphob"], d["lig_anchor"], poses, gpu=True)
+    k_cpu = e.dock_filter_poses(d["rec"], d["rec_hphob"], d["lig"], d["lig_hphob"], d["lig_anchor"], poses, gpu=False)
+    e.close()
+    res["filter_equal"] = bool(np.array_equal(k_gpu, k_cpu))
+    res["filter_kept"] = int(k_gpu.sum())
+    good = (res["filter_equal"] and 0 < res["filter_kept"] < len(poses) and min_ok and res["between_rel"] < 2e-5 and res["force_err"] < 2 * FORCE_RTOL and res["energy_rel"] < 2e-5 and res["sum_ok"] and res["no_terms_zero"] and
             res["bad_id_rejected"] and res["traj_ok"] and 0.9 < res["density"] < 1.1 and res["e_bond"] > 0)
     print(json.dumps(res))
     return 0 if good else 1

@@ -10,6 +10,7 @@
 #include "../../molchanica_b200/csrc/thermostat.cu"
 #include "../../molchanica_b200/csrc/pme.cu"
 #include "../../molchanica_b200/csrc/group_energy.cu"
+#include "../../molchanica_b200/csrc/dock_filter.cu"
 
 #define FOR_THREADS(n) gridDim.x = (unsigned)(n); for (blockIdx.x = 0; blockIdx.x < (unsigned)(n); ++blockIdx.x)
 
@@ -59,6 +60,12 @@ void host_vsite_spread(int n_v, const int4 *sites, const int *slot_of_orig, floa
 
 void host_langevin(int n, float4 *vel, const int *orig, const uint8_t *flags, float c1, float c2, float kT, uint64_t seed, uint64_t step) {
     FOR_THREADS(n + 5) langevin_ou_kernel(n, vel, orig, flags, c1, c2, kT, seed, step);
+}
+
+void host_dock_filter(int n_rs, const float4 *rec_sample, int n_ls, const float4 *lig_sample, const float *anchor, float limit, int n_poses,
+                      const float *poses, uint8_t *keep) {
+    FOR_THREADS(((n_poses + 127) / 128) * 128)
+    dock_filter_kernel(n_rs, rec_sample, n_ls, lig_sample, make_float3(anchor[0], anchor[1], anchor[2]), limit, n_poses, poses, keep);
 }
 
 void host_zero_velocities(int n, float4 *vel) { FOR_THREADS(n + 11) zero_velocities_kernel(n, vel); }

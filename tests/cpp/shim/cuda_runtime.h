@@ -20,7 +20,9 @@
 #define __restrict__ __restrict
 
 struct float2 { float x, y; };
+struct float3 { float x, y, z; };
 struct float4 { float x, y, z, w; };
+static inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 struct shim_dim3 { unsigned x, y, z; };

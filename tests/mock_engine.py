@@ -10,7 +10,21 @@ from oracle import oracle_py as O
 from oracle import pme_oracle as P
 
 class MockEngine:
-    def __init__(self, w):
+    def __init__(self, w=0):
+        if not isinstance(w, dict):  # MdEngine(device): a bare handle, as the docking helpers use it
+            w = dict(xyzq=np.zeros((1, 4), np.float32), vel=np.zeros((1, 4), np.float32))
+        self._init(w)
+
+    def dock_make_poses(self, site, radius, n_pos=8, n_or=60):
+        from oracle import dock_poses as DP
+        return DP.make_poses(site, radius, n_pos, n_or)
+
+    def dock_filter_poses(self, rec, rec_c, lig, lig_c, anchor, poses, vdw_radius=1.7, gpu=True):
+        from oracle import dock_poses as DP
+        return DP.filter_poses(np.asarray(rec), np.asarray(rec_c), np.asarray(lig), np.asarray(lig_c), np.asarray(anchor, np.float32), poses,
+                               vdw_radius)
+
+    def _init(self, w):
         self.w = dict(w); self.x = np.array(w["xyzq"], np.float32); self.v = np.array(w["vel"], np.float32)
         self.bonded = None; self.rigid = None; self.vs = None; self.lgv = None; self.csvr = None; self.pme = None
     @classmethod

@@ -202,6 +202,28 @@ def test_langevin_kernel(K, oracle):
     assert np.array_equal(vel[:, 3], v0[:, 3])
 
 
+def test_dock_filter_kernel(K, engine_lib):
+    """The device clash filter against its host twin (mc_dock_filter_poses, same pose_terms.h) and the numpy restatement."""
+    from oracle import dock_poses as DP
+    d = W.docking_c5(n_rec=1500, n_lig=24, n_poses=64, seeds=(515, 516, 517))
+    rec, lig = d["rec"], d["lig"]
+    site = rec[:, :3].astype(np.float64).mean(0) + np.array([6.0, 0.0, 0.0])
+    near_idx = DP.near_site(rec, None, site, 8.0)
+    near, near_c = np.ascontiguousarray(rec[near_idx]), np.ascontiguousarray(d["rec_hphob"][near_idx])
+    poses = DP.make_poses(site, 8.0, 4, 60)
+    anchor = np.ascontiguousarray(d["lig_anchor"], np.float32)
+    rs = np.ascontiguousarray(np.array([[*near[i, :3], 0.0] for i in range(len(near)) if near_c[i] and i % 6 == 0], np.float32))
+    ls = np.ascontiguousarray(np.array([[*lig[i, :3], 0.0] for i in range(len(lig)) if d["lig_hphob"][i] and i % 4 == 0], np.float32))
+    keep = np.full(len(poses), 7, np.uint8)
+    K.host_dock_filter(len(rs), _p(rs), len(ls), _p(ls), _p(anchor), C.c_float(np.float32(1.7) * np.float32(1.1)), len(poses), _p(poses), _p(keep))
+    twin = np.zeros(len(poses), np.uint8)
+    kept = C.c_int64(0)
+    assert engine_lib.mc_dock_filter_poses(len(near), _p(near), _p(near_c), len(lig), _p(lig), _p(d["lig_hphob"]), _p(anchor), 1.7, len(poses),
+                                           _p(poses), _p(twin), C.byref(kept)) == 0
+    assert np.array_equal(keep, twin) and np.array_equal(keep, DP.filter_poses(near, near_c, lig, d["lig_hphob"], anchor, poses, 1.7))
+    assert 0 < int(keep.sum()) < len(keep)
+
+
 def test_zero_velocities_kernel(K):
     rng = np.random.default_rng(1)
     v = rng.normal(size=(777, 4)).astype(np.float32)
