@@ -6,6 +6,13 @@
 
 #include "../../include/molchanica_md.h"
 
+// Dynamic shared memory of a kernel.  The host stand-ins of tests/cpp/ (MC_HOST_SHIM) map it onto a process-wide buffer.
+#ifndef MC_HOST_SHIM
+#define MC_DYN_SHARED(T, name) extern __shared__ T name[]
+#else
+#define MC_DYN_SHARED(T, name) T *name = reinterpret_cast<T *>(shim_dyn_smem)
+#endif
+
 #define MC_WARP 32
 #define MC_FULL_MASK 0xffffffffu
 #define MC_ACCEL_CONV 418.4f       // kcal/mol/A/amu -> A/ps^2

@@ -22,6 +22,7 @@ namespace {
 constexpr int DOCK_THREADS = 128;
 constexpr float HYDROPHOBIC_CUTOFF = 4.25f;
 
+#ifndef MC_HOST_SHIM
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -32,6 +33,10 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+#else  // tests/cpp/dock_kernel_host.cpp runs this file's kernel on the CPU: no PTX there
+inline float rcp_approx(float x) { return 1.0f / x; }
+inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
+#endif
 
 __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, const float4 *__restrict__ rec,
                                                                    const uint32_t *__restrict__ rec_meta, int n_lig,
@@ -41,7 +46,7 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
                                                                    const float2 *__restrict__ ljtab,
                                                                    const float *__restrict__ poses,
                                                                    float *__restrict__ out) {
-    extern __shared__ float4 smem[];
+    MC_DYN_SHARED(float4, smem);
     float4 *lp = smem;                                             // n_lig posed atoms (x, y, z, q)
     uint32_t *lmeta = reinterpret_cast<uint32_t *>(lp + n_lig);    // n_lig meta words
     float2 *tab = reinterpret_cast<float2 *>(lmeta + ((n_lig + 3) & ~3));  // T_rec * T_lig
@@ -129,6 +134,7 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
 
 }  // namespace
 
+#ifndef MC_HOST_SHIM
 size_t dock_smem_bytes(int n_lig, int n_rec_types, int n_lig_types) {
     return sizeof(float4) * n_lig + sizeof(uint32_t) * ((n_lig + 3) & ~3) + sizeof(float2) * n_rec_types * n_lig_types;
 }
@@ -146,3 +152,4 @@ void launch_dock_score(int n_rec, const float4 *rec, const uint32_t *rec_meta, i
         n_rec, rec, rec_meta, n_lig, lig, lig_meta, lig_anchor, n_rec_types, n_lig_types, ljtab, poses, out);
     *launches += 1;
 }
+#endif  // MC_HOST_SHIM

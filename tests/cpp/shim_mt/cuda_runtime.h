@@ -32,7 +32,9 @@
 #endif
 
 struct float2 { float x, y; };
+struct float3 { float x, y, z; };
 struct float4 { float x, y, z, w; };
+static inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 struct shim_dim3 { unsigned x, y, z; };
@@ -101,6 +103,11 @@ static inline unsigned atomicAdd(unsigned *a, unsigned v) { return std::atomic_r
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+alignas(16) static unsigned char shim_dyn_smem[256 * 1024];  // MC_DYN_SHARED(T, name) of common.cuh points here
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
