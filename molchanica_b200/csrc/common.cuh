@@ -13,6 +13,13 @@
 #define MC_DYN_SHARED(T, name) T *name = reinterpret_cast<T *>(shim_dyn_smem)
 #endif
 
+// Kernel launch.  Host drivers written with it run unchanged over the stand-ins (one block at a time on OS threads).
+#ifndef MC_HOST_SHIM
+#define MC_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#else
+#define MC_LAUNCH(kernel, grid, block, smem, stream, ...) shim_launch((grid), (block), [&] { kernel(__VA_ARGS__); })
+#endif
+
 #define MC_WARP 32
 #define MC_FULL_MASK 0xffffffffu
 #define MC_ACCEL_CONV 418.4f       // kcal/mol/A/amu -> A/ps^2

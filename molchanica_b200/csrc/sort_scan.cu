@@ -206,11 +206,11 @@ void exclusive_scan_u32(const uint32_t *in, uint32_t *out, size_t n, int align8,
         cudaMemsetAsync(out, 0, sizeof(uint32_t), st);
         return;
     }
-    if (align8) scan_reduce_kernel<true><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, scratch);
-    else scan_reduce_kernel<false><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, scratch);
-    scan_spine_kernel<<<1, 1024, 0, st>>>(scratch, nb, out + n);
-    if (align8) scan_down_kernel<true><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, scratch);
-    else scan_down_kernel<false><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, scratch);
+    if (align8) MC_LAUNCH(scan_reduce_kernel<true>, (unsigned)nb, SCAN_THREADS, 0, st, in, n, scratch);
+    else MC_LAUNCH(scan_reduce_kernel<false>, (unsigned)nb, SCAN_THREADS, 0, st, in, n, scratch);
+    MC_LAUNCH(scan_spine_kernel, 1, 1024, 0, st, scratch, nb, out + n);
+    if (align8) MC_LAUNCH(scan_down_kernel<true>, (unsigned)nb, SCAN_THREADS, 0, st, in, out, n, scratch);
+    else MC_LAUNCH(scan_down_kernel<false>, (unsigned)nb, SCAN_THREADS, 0, st, in, out, n, scratch);
     if (launches) *launches += 3;
 }
 
@@ -231,10 +231,10 @@ int radix_sort_pairs(uint32_t *keys[2], uint32_t *vals[2], size_t n, int bits, u
     const unsigned blocks = div_up(nw, RS_WARPS);
     int cur = 0;
     for (int shift = 0; shift < bits; shift += RS_BITS) {
-        radix_hist_kernel<<<blocks, RS_WARPS * 32, 0, st>>>(keys[cur], n, shift, hist, nw);
+        MC_LAUNCH(radix_hist_kernel, blocks, RS_WARPS * 32, 0, st, keys[cur], n, shift, hist, nw);
         exclusive_scan_u32(hist, hist, table, 0, scan_scratch, st, launches);
-        radix_scatter_kernel<<<blocks, RS_WARPS * 32, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
-                                                               shift, hist, nw);
+        MC_LAUNCH(radix_scatter_kernel, blocks, RS_WARPS * 32, 0, st, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift,
+                  hist, nw);
         if (launches) *launches += 2;
         cur ^= 1;
     }

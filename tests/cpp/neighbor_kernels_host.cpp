@@ -1,7 +1,7 @@
 // Test infrastructure: the cell-list kernels of neighbor.cu (wrap + cell key, reorder + cell starts + interior flag,
 // the 27-cell sweep with its exact accept test, the vacuum bounding-box grid) compiled unchanged for the host through
-// tests/cpp/shim_mt/cuda_runtime.h and chained the way engine.cu chains them; the radix sort and the prefix scan in
-// between are std::stable_sort and a host loop.  tests/test_neighbor_kernels_on_host.py holds the resulting Verlet
+// tests/cpp/shim_mt/cuda_runtime.h and chained the way engine.cu chains them; with the radix sort and the prefix
+// scan of sort_scan.cu (kernels and host drivers) in between, exactly the sequence of engine_build_list up to the list sweep.  tests/test_neighbor_kernels_on_host.py holds the resulting Verlet
 // list to the oracle's, index for index.  (The production list build, tile_build.cu, is TMA / mbarrier PTX and cannot be
 // run this way; it shares the accept arithmetic with the sweep below and is compared with the oracle on the GPU.)
 #define MC_HOST_SHIM 1
@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../molchanica_b200/csrc/neighbor.cu"
+#include "../../molchanica_b200/csrc/sort_scan.cu"
 
 extern "C" {
 
@@ -55,11 +56,14 @@ long host_neighbor_list(int n, const float4 *xyzq_in, const float *lo, const flo
     }
     std::vector<uint32_t> keys(n), vals(n), cell_start(ncell_cap + 2, 0);
     shim_launch((n + 255) / 256, 256, [&] { wrap_key_kernel(x.data(), n, &g, keys.data(), vals.data()); });
-    std::vector<uint32_t> perm(n);
-    std::iota(perm.begin(), perm.end(), 0u);
-    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
-    std::vector<uint32_t> skeys(n), svals(n);
-    for (int k = 0; k < n; ++k) { skeys[k] = keys[perm[k]]; svals[k] = vals[perm[k]]; }
+    // the device radix sort, host driver included, with the key width engine.cu's setup_grid derives
+    int bits = 1;
+    while (((size_t)1 << bits) < ncell_cap) ++bits;
+    if (!periodic) bits += MC_SUB_BITS;
+    std::vector<uint32_t> keys1(n), vals1(n), scratch(std::max(radix_scratch_elems((size_t)n), scan_scratch_elems((size_t)n + 1)) + 64);
+    uint32_t *kk[2] = {keys.data(), keys1.data()}, *vv[2] = {vals.data(), vals1.data()};
+    const int which = radix_sort_pairs(kk, vv, (size_t)n, bits, scratch.data(), nullptr, nullptr);
+    std::vector<uint32_t> &skeys = which ? keys1 : keys, &svals = which ? vals1 : vals;
     ReorderArrays ra;
     ra.xyzq_in = x.data(); ra.xyzq_out = xo.data(); ra.xref = xref.data();
     ra.vel_in = vin.data(); ra.vel_out = vout.data();
@@ -74,8 +78,11 @@ long host_neighbor_list(int n, const float4 *xyzq_in, const float *lo, const flo
     shim_launch(blocks, 256, [&] {
         sweep_kernel<false>(n, xo.data(), cell_start.data(), &g, rl2, skeys.data(), orig_out, excl_start, excl_idx, nbr_count, nullptr, nullptr);
     });
-    uint64_t total = 0;
-    for (int i = 0; i < n; ++i) { nbr_start[i] = (uint32_t)total; total += (nbr_count[i] + 7u) & ~7u; }
+    // row starts: the device scan with rows padded to 8 entries (nbr_start has n + 1 slots; the total lands in the last)
+    std::vector<uint32_t> starts(n + 1);
+    exclusive_scan_u32(nbr_count, starts.data(), (size_t)n, 1, scratch.data(), nullptr, nullptr);
+    memcpy(nbr_start, starts.data(), sizeof(uint32_t) * (size_t)n);
+    const uint64_t total = starts[n];
     if ((long)total > cap) return -1;
     shim_launch(blocks, 256, [&] {
         sweep_kernel<true>(n, xo.data(), cell_start.data(), &g, rl2, skeys.data(), orig_out, excl_start, excl_idx, nbr_count, nbr_start, nbr_list);

@@ -37,6 +37,8 @@ struct float4 { float x, y, z, w; };
 static inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 struct shim_dim3 { unsigned x, y, z; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
@@ -86,6 +88,32 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 
 #include <atomic>
+// Rendezvous of the lanes named in `mask` only (the callers sit inside a divergent branch, so the 32-wide warp barrier
+// cannot be used): a counting barrier whose size is popc(mask), one per warp.
+struct ShimMaskBar { std::atomic<unsigned> count{0}, gen{0}; };
+static ShimMaskBar shim_mask_bar[32];
+static inline void shim_mask_wait(unsigned w, unsigned n) {
+    ShimMaskBar &b = shim_mask_bar[w];
+    const unsigned g = b.gen.load();
+    if (b.count.fetch_add(1) + 1 == n) {
+        b.count.store(0);
+        b.gen.fetch_add(1);
+    } else {
+        while (b.gen.load() == g) std::this_thread::yield();
+    }
+}
+static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
+    const unsigned t = threadIdx.x, w = t >> 5, n = (unsigned)__builtin_popcount(mask);
+    shim_block->xchg[t] = v;
+    shim_mask_wait(w, n);
+    unsigned m = 0;
+    for (unsigned l = 0; l < 32; ++l)
+        if ((mask >> l & 1u) && (unsigned)shim_block->xchg[w << 5 | l] == v) m |= 1u << l;
+    shim_mask_wait(w, n);
+    return m;
+}
+
+#include <atomic>
 static inline float atomicAdd(float *a, float v) {
     std::atomic_ref<float> r(*a);
     float o = r.load();
@@ -130,6 +158,7 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 
 typedef void *cudaStream_t;
 typedef int cudaError_t;
+static inline int cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 enum { cudaSuccess = 0 };
 struct cudaFuncAttributes {};
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
