@@ -9,8 +9,10 @@
 // Dynamic shared memory of a kernel.  The host stand-ins of tests/cpp/ (MC_HOST_SHIM) map it onto a process-wide buffer.
 #ifndef MC_HOST_SHIM
 #define MC_DYN_SHARED(T, name) extern __shared__ T name[]
+#define MC_DYN_SHARED_ALIGNED(T, name, A) extern __shared__ __align__(A) T name[]
 #else
 #define MC_DYN_SHARED(T, name) T *name = reinterpret_cast<T *>(shim_dyn_smem)
+#define MC_DYN_SHARED_ALIGNED(T, name, A) T *name = reinterpret_cast<T *>(shim_dyn_smem)
 #endif
 
 // Kernel launch.  Host drivers written with it run unchanged over the stand-ins (one block at a time on OS threads).

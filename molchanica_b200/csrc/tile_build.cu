@@ -46,6 +46,7 @@ __device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+#ifndef MC_HOST_SHIM
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -78,6 +79,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+
+// barrier 1: the consumer warps only (the producer never joins it)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TILE_WARPS * 32) : "memory"); }
+#else
+// tests/cpp/tile_build_host.cpp: the same six operations on OS threads (shim_mt/mbarrier.h)
+inline void mbar_init(uint64_t *bar, uint32_t count) { shim_mbar_init(bar, count); }
+inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { shim_mbar_arrive(bar, bytes); }
+inline void mbar_arrive(uint64_t *bar) { shim_mbar_arrive(bar, 0); }
+inline void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { shim_bulk_copy(dst, src, bytes, bar); }
+inline void mbar_wait(uint64_t *bar, uint32_t parity) { shim_mbar_wait(bar, parity); }
+inline void consumer_sync() { shim_named_barrier(1, TILE_WARPS * 32); }
+#endif
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t *total) {
     uint32_t inc = v;
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, 3) tile_build_kernel(
     const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx, uint32_t *__restrict__ nbr_count,
     uint32_t *__restrict__ nbr_start, uint32_t *__restrict__ nbr_list, uint32_t list_cap, uint32_t tile_cap, int split,
     int n_stages /* 1 or 2 tiles in flight */, uint32_t *__restrict__ ctl /* [0] work counter, [1] list cursor, [2] max tile atoms seen, [3] tile overflow */) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MC_DYN_SHARED_ALIGNED(unsigned char, smem_raw, 128);
     // per stage: tile_cap float4 positions, then tile_cap slot ids
     const size_t stage_bytes = (size_t)tile_cap * (sizeof(float4) + sizeof(uint32_t));
     __shared__ __align__(8) uint64_t full_bar[TILE_STAGES], empty_bar[TILE_STAGES];
@@ -441,7 +454,7 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, 3) tile_build_kernel(
 #pragma unroll
                     for (int k = 0; k < TILE_A; ++k) s_len[pp][cw + k * TILE_WARPS] = k < na ? ((R.len[k] + 7u) & ~7u) : 0u;
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(TILE_WARPS * 32) : "memory");
+                consumer_sync();
                 if (cw == 0) {
                     uint32_t tot;
                     const uint32_t off = warp_excl_scan(s_len[pp][lane], lane, &tot);
@@ -451,7 +464,7 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, 3) tile_build_kernel(
                     s_off[pp][lane] = b0 + off;
                     if (lane == 0) s_fits[pp] = ((uint64_t)b0 + tot <= (uint64_t)list_cap) ? 1 : 0;
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(TILE_WARPS * 32) : "memory");
+                consumer_sync();
                 uint32_t row[TILE_A];
 #pragma unroll
                 for (int k = 0; k < TILE_A; ++k) {
@@ -501,8 +514,7 @@ void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const f
     if (per_sm < 1) per_sm = 1;
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, (long long)n_sms * per_sm));
     cudaMemsetAsync(ctl, 0, 4 * sizeof(uint32_t), st);
-    tile_build_kernel<<<grid, (TILE_WARPS + 1) * 32, smem, st>>>(n_rows, xyzq, cell_start, g, rl2, rc2_inner, orig, excl_start,
-                                                                 excl_idx, nbr_count, nbr_start, nbr_list, list_cap, tile_cap,
-                                                                 split, n_stages, ctl);
+    MC_LAUNCH(tile_build_kernel, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, cell_start, g, rl2, rc2_inner, orig, excl_start,
+              excl_idx, nbr_count, nbr_start, nbr_list, list_cap, tile_cap, split, n_stages, ctl);
     *launches += 1;
 }

@@ -2,8 +2,9 @@
 // the 27-cell sweep with its exact accept test, the vacuum bounding-box grid) compiled unchanged for the host through
 // tests/cpp/shim_mt/cuda_runtime.h and chained the way engine.cu chains them; with the radix sort and the prefix
 // scan of sort_scan.cu (kernels and host drivers) in between, exactly the sequence of engine_build_list up to the list sweep.  tests/test_neighbor_kernels_on_host.py holds the resulting Verlet
-// list to the oracle's, index for index.  (The production list build, tile_build.cu, is TMA / mbarrier PTX and cannot be
-// run this way; it shares the accept arithmetic with the sweep below and is compared with the oracle on the GPU.)
+// list to the oracle's, index for index.  With use_tile the rows come from
+// the production list build instead (tile_build.cu through tests/cpp/tile_build_host.cpp), driven by the adaptive loop of
+// engine_build_rows.
 #define MC_HOST_SHIM 1
 #define MC_SHIM_SHARED_STATIC 1
 #include "shim_mt/cuda_runtime.h"
@@ -15,6 +16,7 @@
 
 #include "../../molchanica_b200/csrc/neighbor.cu"
 #include "../../molchanica_b200/csrc/sort_scan.cu"
+#include "../../molchanica_b200/csrc/neighbor.cuh"  // launch_tile_build: tests/cpp/tile_build_host.cpp
 
 extern "C" {
 
@@ -23,7 +25,8 @@ extern "C" {
 // n_cells_out[3] reports the grid.  -1: capacity too small.
 long host_neighbor_list(int n, const float4 *xyzq_in, const float *lo, const float *ext, int periodic, float r_list,
                         const int32_t *excl_start, const int32_t *excl_idx, int *orig_out, uint8_t *flags_out, float4 *xyzq_sorted,
-                        uint32_t *nbr_count, uint32_t *nbr_start, uint32_t *nbr_list, long cap, int *n_cells_out) {
+                        uint32_t *nbr_count, uint32_t *nbr_start, uint32_t *nbr_list, long cap, int *n_cells_out,
+                        int use_tile, float rc_inner, int tile_cap0, int list_cap0, int split, int n_sms, int *tile_stats) {
     std::vector<float4> x(xyzq_in, xyzq_in + n), xo(n), xref(n), vin(n, float4{0, 0, 0, 1}), vout(n);
     std::vector<uint16_t> tin(n, 0), tout(n);
     std::vector<uint8_t> fin(n, 0);
@@ -74,6 +77,36 @@ long host_neighbor_list(int n, const float4 *xyzq_in, const float *lo, const flo
     ra.mark_interior = 1;
     shim_launch((n + 1 + 255) / 256, 256, [&] { reorder_kernel(n, skeys.data(), svals.data(), &g, ra); });
     const float rl2 = r_list * r_list;
+    if (use_tile) {
+        // engine_build_rows: the single-pass build with tile and list capacities that adapt on demand.
+        // tile_stats: [0] launches, [1] final tile capacity, [2] largest neighbourhood seen, [3] final list capacity
+        uint32_t ctl[4];
+        uint32_t tile_cap = (uint32_t)tile_cap0;
+        std::vector<uint32_t> list((size_t)list_cap0);
+        memset(nbr_count, 0, sizeof(uint32_t) * (size_t)n);
+        int64_t launches = 0;
+        size_t total = 0;
+        for (;;) {
+            launch_tile_build(n, periodic ? g.ncell : (int)ncell_cap, split, n_sms, xo.data(), cell_start.data(), &g, rl2, rc_inner * rc_inner,
+                              orig_out, excl_start, excl_idx, nbr_count, nbr_start, list.data(), (uint32_t)list.size(), tile_cap, ctl, nullptr,
+                              &launches);
+            if (ctl[3] != 0) {
+                uint32_t need = (ctl[2] + ctl[2] / 4 + 127u) & ~31u;
+                if (need > tile_sweep_max_atoms() && ((ctl[2] + 127u) & ~31u) <= tile_sweep_max_atoms()) need = tile_sweep_max_atoms();
+                if (need <= tile_sweep_max_atoms()) { tile_cap = need; continue; }
+                return -2;  // too dense for the tile path
+            }
+            total = ctl[1];
+            if (total > list.size()) { list.assign(total + total / 8 + 1024, 0u); continue; }
+            break;
+        }
+        tile_stats[0] = (int)launches; tile_stats[1] = (int)tile_cap; tile_stats[2] = (int)ctl[2]; tile_stats[3] = (int)list.size();
+        if ((long)total > cap) return -1;
+        memcpy(nbr_list, list.data(), sizeof(uint32_t) * total);
+        memcpy(xyzq_sorted, xo.data(), sizeof(float4) * (size_t)n);
+        for (int a = 0; a < 3; ++a) n_cells_out[a] = g.nc[a];
+        return (long)total;
+    }
     const unsigned blocks = (unsigned)(((size_t)n * 32 + 255) / 256);
     shim_launch(blocks, 256, [&] {
         sweep_kernel<false>(n, xo.data(), cell_start.data(), &g, rl2, skeys.data(), orig_out, excl_start, excl_idx, nbr_count, nullptr, nullptr);

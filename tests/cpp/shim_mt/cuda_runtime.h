@@ -25,6 +25,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__ __restrict
+#define __align__(n) __attribute__((aligned(n)))
 #ifdef MC_SHIM_SHARED_STATIC
 #define __shared__ static   // statically sized shared arrays: one copy for the process = for the one block that runs
 #else
@@ -135,7 +136,7 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
-alignas(16) static unsigned char shim_dyn_smem[256 * 1024];  // MC_DYN_SHARED(T, name) of common.cuh points here
+alignas(128) static unsigned char shim_dyn_smem[256 * 1024];  // MC_DYN_SHARED(T, name) of common.cuh points here
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
@@ -163,6 +164,7 @@ enum { cudaSuccess = 0 };
 struct cudaFuncAttributes {};
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return cudaSuccess; }
 
 // Runs `body` (a call of the kernel with its arguments bound) for every thread of every block, one block at a time.
 static inline void shim_launch(unsigned blocks, unsigned threads, const std::function<void()> &body) {
