@@ -134,6 +134,11 @@ def main():
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     args = ap.parse_args()
+    if os.environ.get("MOLCHANICA_MD_LIB") and not os.environ.get("MOLCHANICA_BENCH_ALLOW_LIB_OVERRIDE"):
+        # the host build of tests/cpp/host_lib/ is a checker, never a thing to be measured; an nvcc-built A/B variant has
+        # to be asked for explicitly
+        raise SystemExit("bench.py measures molchanica_b200/libmolchanica_md.so; unset MOLCHANICA_MD_LIB "
+                         "(or set MOLCHANICA_BENCH_ALLOW_LIB_OVERRIDE=1 for an nvcc-built A/B variant)")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

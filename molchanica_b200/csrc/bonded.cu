@@ -94,13 +94,13 @@ __global__ void __launch_bounds__(128) bonded_kernel(BondedTerms t, const int *_
 
 }  // namespace
 
-#ifndef MC_HOST_SHIM  // tests/cpp/kernels_host.cpp runs the kernels above on the CPU; launches need nvcc
+#ifdef MC_HAVE_LAUNCH  // the serial stand-in of tests/cpp/shim/ has no launcher
 void launch_bonded(const BondedTerms &t, const int *slot_of_orig, const float4 *xyzq, const NbParams &p, float4 *force,
                    double *energy3, bool want_energy, cudaStream_t st, int64_t *launches) {
     const int n = t.n_bonds + t.n_angles + t.n_dihedrals;
     if (n <= 0) return;
     if (want_energy) cudaMemsetAsync(energy3, 0, 3 * sizeof(double), st);
-    bonded_kernel<<<div_up((size_t)n, 128), 128, 0, st>>>(t, slot_of_orig, xyzq, p, force, energy3, want_energy ? 1 : 0);
+    MC_LAUNCH(bonded_kernel, div_up((size_t)n, 128), 128, 0, st, t, slot_of_orig, xyzq, p, force, energy3, want_energy ? 1 : 0);
     *launches += 1;
 }
 #endif

@@ -15,6 +15,13 @@
 #define MC_DYN_SHARED_ALIGNED(T, name, A) T *name = reinterpret_cast<T *>(shim_dyn_smem)
 #endif
 
+// MC_HOST_SHIM: the file is being compiled by g++ over one of the cuda_runtime.h stand-ins of tests/cpp/ (no PTX).
+// MC_HOST_LAUNCH: that stand-in can also run launches and the host runtime (tests/cpp/shim_fiber/), so the launchers and
+// engine.cu are compiled as well.
+#if !defined(MC_HOST_SHIM) || defined(MC_HOST_LAUNCH)
+#define MC_HAVE_LAUNCH 1
+#endif
+
 // Kernel launch.  Host drivers written with it run unchanged over the stand-ins (one block at a time on OS threads).
 #ifndef MC_HOST_SHIM
 #define MC_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)

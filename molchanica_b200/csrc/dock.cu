@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
 
 }  // namespace
 
-#ifndef MC_HOST_SHIM
+#ifdef MC_HAVE_LAUNCH  // the stand-ins of tests/cpp/shim/ and shim_mt/ have no launcher; shim_fiber/ has
 size_t dock_smem_bytes(int n_lig, int n_rec_types, int n_lig_types) {
     return sizeof(float4) * n_lig + sizeof(uint32_t) * ((n_lig + 3) & ~3) + sizeof(float2) * n_rec_types * n_lig_types;
 }
@@ -148,7 +148,7 @@ void launch_dock_score(int n_rec, const float4 *rec, const uint32_t *rec_meta, i
                        const float2 *ljtab, int n_poses, const float *poses, float *out, cudaStream_t st,
                        int64_t *launches) {
     if (n_poses <= 0) return;
-    dock_score_kernel<<<n_poses, DOCK_THREADS, dock_smem_bytes(n_lig, n_rec_types, n_lig_types), st>>>(
+    MC_LAUNCH(dock_score_kernel, n_poses, DOCK_THREADS, dock_smem_bytes(n_lig, n_rec_types, n_lig_types), st, 
         n_rec, rec, rec_meta, n_lig, lig, lig_meta, lig_anchor, n_rec_types, n_lig_types, ljtab, poses, out);
     *launches += 1;
 }

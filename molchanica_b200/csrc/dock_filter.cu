@@ -41,11 +41,11 @@ __global__ void __launch_bounds__(128) dock_filter_kernel(int n_rs, const float4
 
 int dock_filter_max_lig() { return DOCK_FILTER_MAX_LIG; }
 
-#ifndef MC_HOST_SHIM
+#ifdef MC_HAVE_LAUNCH  // the stand-ins of tests/cpp/shim/ and shim_mt/ have no launcher; shim_fiber/ has
 void launch_dock_filter(int n_rs, const float4 *rec_sample, int n_ls, const float4 *lig_sample, float3 anchor0, float limit, int n_poses,
                         const float *poses, uint8_t *keep, cudaStream_t st, int64_t *launches) {
     if (n_poses <= 0) return;
-    dock_filter_kernel<<<div_up((size_t)n_poses, 128), 128, 0, st>>>(n_rs, rec_sample, n_ls, lig_sample, anchor0, limit, n_poses, poses, keep);
+    MC_LAUNCH(dock_filter_kernel, div_up((size_t)n_poses, 128), 128, 0, st, n_rs, rec_sample, n_ls, lig_sample, anchor0, limit, n_poses, poses, keep);
     *launches += 1;
 }
 #endif

@@ -44,13 +44,13 @@ __global__ void __launch_bounds__(128) between_mols_kernel(int n_rows, int row0,
 
 }  // namespace
 
-#ifndef MC_HOST_SHIM
+#ifdef MC_HAVE_LAUNCH  // the stand-ins of tests/cpp/shim/ and shim_mt/ have no launcher; shim_fiber/ has
 void launch_between_mols(int n_rows, int row0, const float4 *xyzq, const uint16_t *type, const int *orig, const uint16_t *mol_of_orig,
                          const uint32_t *nbr_start, const uint32_t *nbr_count, const uint32_t *nbr_list, const float2 *ljtab,
                          const NbParams &p, int lj_on, int coul_mode, double *energy, cudaStream_t st, int64_t *launches) {
     cudaMemsetAsync(energy, 0, sizeof(double), st);
     if (n_rows <= 0) return;
-    between_mols_kernel<<<div_up((size_t)n_rows, 128), 128, 0, st>>>(n_rows, row0, xyzq, type, orig, mol_of_orig, nbr_start, nbr_count,
+    MC_LAUNCH(between_mols_kernel, div_up((size_t)n_rows, 128), 128, 0, st, n_rows, row0, xyzq, type, orig, mol_of_orig, nbr_start, nbr_count,
                                                                      nbr_list, ljtab, p, lj_on, coul_mode, energy);
     *launches += 1;
 }

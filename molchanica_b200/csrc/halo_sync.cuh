@@ -73,4 +73,15 @@ static __device__ __noinline__ void halo_spin(const uint32_t *flag, uint32_t wan
         __nanosleep(40);
     }
 }
+#elif defined(MC_HOST_LAUNCH)
+// host build of tests/cpp/host_lib/: a single process has no peers, the fused-halo kernels are compiled but never launched
+#include <atomic>
+static inline uint32_t halo_ld_acquire_sys(const uint32_t *p) { return std::atomic_ref<const uint32_t>(*p).load(std::memory_order_acquire); }
+static inline void halo_st_release_sys(uint32_t *p, uint32_t v) { std::atomic_ref<uint32_t>(*p).store(v, std::memory_order_release); }
+static inline void halo_spin(const uint32_t *flag, uint32_t want, int *err) {
+    for (long k = 0; (int)(halo_ld_acquire_sys(flag) - want) < 0; ++k) {
+        if (k > 100000000L) { atomicOr(err, MC_HALO_ERR_TIMEOUT); return; }
+        __nanosleep(40);
+    }
+}
 #endif

@@ -149,13 +149,13 @@ __global__ void l2_flush_kernel(float4 *buf, size_t n) {
 
 }  // namespace
 
-#ifndef MC_HOST_SHIM  // tests/cpp/integrate_kernels_host.cpp runs the kernels above on the CPU; launches need nvcc
+#ifdef MC_HAVE_LAUNCH  // the stand-ins of tests/cpp/shim/ and shim_mt/ have no launcher; shim_fiber/ has
 void launch_kick_drift(int n_rows, float4 *xyzq, float4 *vel, const float4 *force, const float *ext_force,
                        const int *orig, const uint8_t *flags, const float4 *xref, float kick, float drift,
                        float max_disp, float lookahead, int *rebuild_flag, cudaStream_t st, int64_t *launches,
                        uint32_t *done_counter, int *host_flag, int step_tag) {
     if (n_rows <= 0) return;
-    kick_drift_kernel<false><<<div_up(n_rows, 256), 256, 0, st>>>(n_rows, xyzq, vel, force, ext_force, orig, flags, xref, kick,
+    MC_LAUNCH(kick_drift_kernel<false>, div_up(n_rows, 256), 256, 0, st, n_rows, xyzq, vel, force, ext_force, orig, flags, xref, kick,
                                                                  drift, max_disp, lookahead, rebuild_flag, HaloPush{},
                                                                  done_counter, host_flag, step_tag);
     *launches += 1;
@@ -165,26 +165,26 @@ void launch_kick_drift_halo(int n_rows, float4 *xyzq, float4 *vel, const float4 
                             const int *orig, const uint8_t *flags, const float4 *xref, float kick, float drift,
                             float max_disp, int *rebuild_flag, const HaloPush &hp, cudaStream_t st, int64_t *launches) {
     if (n_rows <= 0) return;
-    kick_drift_kernel<true><<<div_up(n_rows, 256), 256, 0, st>>>(n_rows, xyzq, vel, force, ext_force, orig, flags, xref, kick,
+    MC_LAUNCH(kick_drift_kernel<true>, div_up(n_rows, 256), 256, 0, st, n_rows, xyzq, vel, force, ext_force, orig, flags, xref, kick,
                                                                 drift, max_disp, 0.f, rebuild_flag, hp, nullptr, nullptr, 0);
     *launches += 1;
 }
 
 void launch_gather_to_orig(int n, const float4 *sorted, const int *orig, float4 *out, cudaStream_t st, int64_t *launches) {
     if (n <= 0) return;
-    gather_to_orig_kernel<<<div_up(n, 256), 256, 0, st>>>(n, sorted, orig, out);
+    MC_LAUNCH(gather_to_orig_kernel, div_up(n, 256), 256, 0, st, n, sorted, orig, out);
     *launches += 1;
 }
 
 void launch_scatter_from_orig(int n, const float4 *in_orig, const int *orig, float4 *sorted, int keep_w, cudaStream_t st,
                               int64_t *launches) {
     if (n <= 0) return;
-    scatter_from_orig_kernel<<<div_up(n, 256), 256, 0, st>>>(n, in_orig, orig, sorted, keep_w);
+    MC_LAUNCH(scatter_from_orig_kernel, div_up(n, 256), 256, 0, st, n, in_orig, orig, sorted, keep_w);
     *launches += 1;
 }
 
 void launch_l2_flush(float4 *buf, size_t n_float4, cudaStream_t st, int64_t *launches) {
-    l2_flush_kernel<<<1184, 256, 0, st>>>(buf, n_float4);
+    MC_LAUNCH(l2_flush_kernel, 1184, 256, 0, st, buf, n_float4);
     *launches += 1;
 }
 #endif  // MC_HOST_SHIM

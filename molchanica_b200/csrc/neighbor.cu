@@ -322,24 +322,24 @@ __global__ void __launch_bounds__(128) sort_rows_kernel(int n, const uint32_t *_
 
 }  // namespace
 
-#ifndef MC_HOST_SHIM  // tests/cpp/neighbor_kernels_host.cpp runs the kernels above on the CPU; launches need nvcc
+#ifdef MC_HAVE_LAUNCH  // the stand-ins of tests/cpp/shim/ and shim_mt/ have no launcher; shim_fiber/ has
 void launch_bbox(const float4 *xyzq, int n, float *bb, float cw_min, int max_cells, GridParams *g, cudaStream_t st,
                  int64_t *launches) {
-    bbox_init_kernel<<<1, 32, 0, st>>>(bb);
-    bbox_kernel<<<min(div_up(n, 256), 1184u), 256, 0, st>>>(xyzq, n, bb);
-    grid_from_bbox_kernel<<<1, 32, 0, st>>>(bb, cw_min, max_cells, g);
+    MC_LAUNCH(bbox_init_kernel, 1, 32, 0, st, bb);
+    MC_LAUNCH(bbox_kernel, min(div_up(n, 256), 1184u), 256, 0, st, xyzq, n, bb);
+    MC_LAUNCH(grid_from_bbox_kernel, 1, 32, 0, st, bb, cw_min, max_cells, g);
     *launches += 3;
 }
 
 void launch_wrap_key(float4 *xyzq, int n, const GridParams *g, uint32_t *keys, uint32_t *vals, cudaStream_t st,
                      int64_t *launches) {
-    wrap_key_kernel<<<div_up(n, 256), 256, 0, st>>>(xyzq, n, g, keys, vals);
+    MC_LAUNCH(wrap_key_kernel, div_up(n, 256), 256, 0, st, xyzq, n, g, keys, vals);
     *launches += 1;
 }
 
 void launch_reorder(int n, const uint32_t *skeys, const uint32_t *svals, const GridParams *g, const ReorderArrays &a,
                     cudaStream_t st, int64_t *launches) {
-    reorder_kernel<<<div_up((size_t)n + 1, 256), 256, 0, st>>>(n, skeys, svals, g, a);
+    MC_LAUNCH(reorder_kernel, div_up((size_t)n + 1, 256), 256, 0, st, n, skeys, svals, g, a);
     *launches += 1;
 }
 
@@ -348,10 +348,10 @@ void launch_sweep(bool fill, int n_rows, const float4 *xyzq, const uint32_t *cel
                   const uint32_t *nbr_start, uint32_t *nbr_list, cudaStream_t st, int64_t *launches) {
     const unsigned blocks = div_up((size_t)n_rows * 32, 256);
     if (fill)
-        sweep_kernel<true><<<blocks, 256, 0, st>>>(n_rows, xyzq, cell_start, g, rl2, cell_of_slot, orig, excl_start, excl_idx, nbr_count,
+        MC_LAUNCH(sweep_kernel<true>, blocks, 256, 0, st, n_rows, xyzq, cell_start, g, rl2, cell_of_slot, orig, excl_start, excl_idx, nbr_count,
                                                    nbr_start, nbr_list);
     else
-        sweep_kernel<false><<<blocks, 256, 0, st>>>(n_rows, xyzq, cell_start, g, rl2, cell_of_slot, orig, excl_start, excl_idx, nbr_count,
+        MC_LAUNCH(sweep_kernel<false>, blocks, 256, 0, st, n_rows, xyzq, cell_start, g, rl2, cell_of_slot, orig, excl_start, excl_idx, nbr_count,
                                                     nbr_start, nbr_list);
     *launches += 1;
 }
@@ -359,10 +359,10 @@ void launch_sweep(bool fill, int n_rows, const float4 *xyzq, const uint32_t *cel
 void launch_export_rows(int n, const int *orig, const uint32_t *nbr_count, const uint32_t *nbr_start,
                         const uint32_t *nbr_list, uint32_t *cnt_orig, uint32_t *start_orig, uint32_t *rows,
                         uint32_t *scan_scratch, cudaStream_t st, int64_t *launches) {
-    count_by_orig_kernel<<<div_up(n, 256), 256, 0, st>>>(n, orig, nbr_count, cnt_orig);
+    MC_LAUNCH(count_by_orig_kernel, div_up(n, 256), 256, 0, st, n, orig, nbr_count, cnt_orig);
     exclusive_scan_u32(cnt_orig, start_orig, n, 0, scan_scratch, st, launches);
-    translate_rows_kernel<<<div_up((size_t)n * 32, 256), 256, 0, st>>>(n, orig, nbr_count, nbr_start, nbr_list, start_orig, rows);
-    sort_rows_kernel<<<div_up(n, 4), 128, 0, st>>>(n, start_orig, rows);
+    MC_LAUNCH(translate_rows_kernel, div_up((size_t)n * 32, 256), 256, 0, st, n, orig, nbr_count, nbr_start, nbr_list, start_orig, rows);
+    MC_LAUNCH(sort_rows_kernel, div_up(n, 4), 128, 0, st, n, start_orig, rows);
     *launches += 3;
 }
 #endif  // MC_HOST_SHIM

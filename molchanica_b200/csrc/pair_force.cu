@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, int row0, c
                                                           const float2 *__restrict__ ljtab, const NbParams p,
                                                           const int lj_on, float4 *__restrict__ force,
                                                           const int n_interior, const int n_first, const HaloWait hw) {
-    extern __shared__ float2 s_tab[];
+    MC_DYN_SHARED(float2, s_tab);
     constexpr int ROWS_PER_BLOCK = 128 / LANES;
     if (hw.ready_prev && (int)(blockIdx.x + 1) * ROWS_PER_BLOCK > n_interior) {
         // Decomposed rank, fused halo (halo_sync.cuh): launch rows are ordered interior first, then the first and
@@ -338,7 +338,7 @@ __global__ void energy_final_kernel(const double *__restrict__ partial, int nb, 
     }
 }
 
-#ifndef MC_HOST_SHIM
+#ifdef MC_HAVE_LAUNCH  // the stand-ins of tests/cpp/shim/ and shim_mt/ have no launcher; shim_fiber/ has
 template <int LANES>
 void launch_lanes(const PairLaunch &L, cudaStream_t st) {
     const int rows_per_block = 128 / LANES;
@@ -346,14 +346,9 @@ void launch_lanes(const PairLaunch &L, cudaStream_t st) {
     const size_t smem = L.multi ? sizeof(float2) * L.p.n_types * L.p.n_types : 0;
 #define MC_PF(M, C, P, E)                                                                                               \
     do {                                                                                                                \
-        if (L.uniform)                                                                                                  \
-            pair_force_kernel<LANES, M, C, P, E, true><<<blocks, 128, smem, st>>>(                                      \
-                L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on, L.force, \
-                L.n_interior, L.n_first, L.wait); \
-        else                                                                                                            \
-            pair_force_kernel<LANES, M, C, P, E, false><<<blocks, 128, smem, st>>>(                                     \
-                L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on, L.force, \
-                L.n_interior, L.n_first, L.wait); \
+        auto kern = L.uniform ? pair_force_kernel<LANES, M, C, P, E, true> : pair_force_kernel<LANES, M, C, P, E, false>;       \
+        MC_LAUNCH(kern, blocks, 128, smem, st, L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, \
+                  L.ljtab, L.p, L.lj_on, L.force, L.n_interior, L.n_first, L.wait);                                     \
     } while (0)
 #define MC_PF_E(M, C, P) \
     if (L.energy) MC_PF(M, C, P, true); else MC_PF(M, C, P, false)
@@ -374,7 +369,7 @@ void launch_lanes(const PairLaunch &L, cudaStream_t st) {
 
 }  // namespace
 
-#ifndef MC_HOST_SHIM
+#ifdef MC_HAVE_LAUNCH  // the stand-ins of tests/cpp/shim/ and shim_mt/ have no launcher; shim_fiber/ has
 int pair_force_max_types() { return 160; }  // 160^2 * 8 B = 200 KB of the 227 KB shared memory
 
 cudaError_t pair_force_prepare() {
@@ -412,7 +407,7 @@ void launch_pairs14(int n_rows, int row0, const float4 *xyzq, const uint16_t *ty
                     float scale_lj, float scale_q, int lj_on, int coul_on, float4 *force, cudaStream_t st,
                     int64_t *launches) {
     if (n_rows <= 0) return;
-    pairs14_kernel<<<div_up(n_rows, 128), 128, 0, st>>>(n_rows, row0, xyzq, type, orig, slot_of_orig, p14_start, p14_idx, ljtab,
+    MC_LAUNCH(pairs14_kernel, div_up(n_rows, 128), 128, 0, st, n_rows, row0, xyzq, type, orig, slot_of_orig, p14_start, p14_idx, ljtab,
                                                        p, scale_lj, scale_q, lj_on, coul_on, force);
     *launches += 1;
 }
@@ -423,8 +418,8 @@ void launch_energy_reduce(int n_rows, const float4 *force, const float4 *vel, do
                           cudaStream_t st, int64_t *launches) {
     int nb = (int)div_up(n_rows > 0 ? n_rows : 1, 256);
     if (nb > RED_BLOCKS) nb = RED_BLOCKS;
-    energy_partial_kernel<<<nb, 256, 0, st>>>(n_rows, force, vel, partial);
-    energy_final_kernel<<<1, 32, 0, st>>>(partial, nb, out3);
+    MC_LAUNCH(energy_partial_kernel, nb, 256, 0, st, n_rows, force, vel, partial);
+    MC_LAUNCH(energy_final_kernel, 1, 32, 0, st, partial, nb, out3);
     *launches += 2;
 }
 #endif  // MC_HOST_SHIM

@@ -8,8 +8,10 @@
 // 64 grid points per atom -> N x 64 x 4 B of L2 traffic each; the FFTs are HBM-bound for grids beyond L2.
 // STATUS: as bonded.cu -- arithmetic verified on the host (tests/test_pme_cpu.py), kernels not yet run on
 // hardware (round-1 GPU budget spent).
-#ifndef MC_HOST_SHIM
+#include "common.cuh"
+#ifdef MC_HAVE_LAUNCH
 #include <dlfcn.h>
+#include <stdlib.h>
 #endif
 
 #include <string>
@@ -20,7 +22,7 @@
 
 namespace {
 
-#ifndef MC_HOST_SHIM
+#ifdef MC_HAVE_LAUNCH  // the serial stand-in of tests/cpp/shim/ compiles the kernels only
 struct CufftApi {
     int (*Plan3d)(int *, int, int, int, int) = nullptr;
     int (*ExecR2C)(int, float *, float2 *) = nullptr;
@@ -35,9 +37,12 @@ CufftApi &cufft_api() {
     static CufftApi api;
     if (api.ok || !api.err.empty()) return api;
     void *h = nullptr;
-    for (const char *name : {"libcufft.so.11", "libcufft.so.12", "libcufft.so"}) {
+    // MOLCHANICA_CUFFT_LIB names the library explicitly (a non-default install; the host build of tests/cpp/host_lib/
+    // points it at a plain-DFT stand-in with the same five entry points)
+    const char *forced = getenv("MOLCHANICA_CUFFT_LIB");
+    for (const char *name : {forced ? forced : "libcufft.so.11", "libcufft.so.12", "libcufft.so"}) {
         h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-        if (h) break;
+        if (h || forced) break;
     }
     if (!h) { api.err = std::string("cannot load libcufft: ") + dlerror(); return api; }
 #define MC_SYM(field, name)                                                \
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(128) pme_excl_kernel(int n, const float4 *__re
 
 }  // namespace
 
-#ifndef MC_HOST_SHIM  // tests/cpp/kernels_host.cpp runs the kernels above on the CPU; cuFFT and launches need nvcc
+#ifdef MC_HAVE_LAUNCH  // the serial stand-in of tests/cpp/shim/ has no launcher
 void pme_release(PmeState *s) {
     if (s->planned && cufft_api().ok) { cufft_api().Destroy(s->plan_r2c); cufft_api().Destroy(s->plan_c2r); }
     s->planned = false;
@@ -252,16 +257,16 @@ int pme_launch(PmeState *s, int n, const float4 *xyzq, const float lo[3], const 
     const size_t nreal = (size_t)s->K[0] * s->K[1] * s->K[2];
     cudaMemsetAsync(s->grid, 0, nreal * sizeof(float), st);
     if (want_energy) cudaMemsetAsync(s->energy, 0, 2 * sizeof(double), st);
-    pme_spread_kernel<<<div_up((size_t)n, 128), 128, 0, st>>>(n, xyzq, g, s->grid);
+    MC_LAUNCH(pme_spread_kernel, div_up((size_t)n, 128), 128, 0, st, n, xyzq, g, s->grid);
     CufftApi &api = cufft_api();
     if (api.ExecR2C(s->plan_r2c, s->grid, s->cgrid) != 0) { *msg = "cufftExecR2C failed"; return MC_E_CUDA; }
     const double vol = (double)ext[0] * ext[1] * ext[2];
     const float pi = 3.14159265358979f;
-    pme_convolve_kernel<<<592, 256, 0, st>>>(s->K[0], s->K[1], s->K[2], s->cgrid, s->bmod[0], s->bmod[1], s->bmod[2], g.inv_ext[0],
+    MC_LAUNCH(pme_convolve_kernel, 592, 256, 0, st, s->K[0], s->K[1], s->K[2], s->cgrid, s->bmod[0], s->bmod[1], s->bmod[2], g.inv_ext[0],
                                             g.inv_ext[1], g.inv_ext[2], (float)(1.0 / (3.14159265358979323846 * vol)),
                                             pi * pi / (alpha * alpha), s->energy, want_energy ? 1 : 0);
     if (api.ExecC2R(s->plan_c2r, s->cgrid, s->grid) != 0) { *msg = "cufftExecC2R failed"; return MC_E_CUDA; }
-    pme_gather_kernel<<<div_up((size_t)n, 128), 128, 0, st>>>(n, xyzq, g, s->grid, force);
+    MC_LAUNCH(pme_gather_kernel, div_up((size_t)n, 128), 128, 0, st, n, xyzq, g, s->grid, force);
     *launches += 3;
     return MC_OK;
 }
@@ -270,7 +275,7 @@ void pme_launch_exclusions(PmeState *s, int n, const float4 *xyzq, const int *or
                            const int32_t *excl_start, const int32_t *excl_idx, const NbParams &p, float4 *force,
                            bool want_energy, cudaStream_t st, int64_t *launches) {
     if (!s->planned || n <= 0 || !excl_start) return;
-    pme_excl_kernel<<<div_up((size_t)n, 128), 128, 0, st>>>(n, xyzq, orig, slot_of_orig, excl_start, excl_idx, p, force,
+    MC_LAUNCH(pme_excl_kernel, div_up((size_t)n, 128), 128, 0, st, n, xyzq, orig, slot_of_orig, excl_start, excl_idx, p, force,
                                                           s->energy + 1, want_energy ? 1 : 0);
     *launches += 1;
 }

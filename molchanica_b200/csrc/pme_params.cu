@@ -4,6 +4,7 @@
 //   K_a:   >= 2 alpha L_a / (3 tol^(1/5))  (the OpenMM / Essmann rule of thumb for order-4..5 splines),
 //          rounded up to a product of 2, 3, 5 and 7 so that the FFT stays fast, at least 8
 #include <cmath>
+#include <initializer_list>
 
 #include "../../include/molchanica_md.h"
 

@@ -158,25 +158,25 @@ __global__ void __launch_bounds__(128) vsite_spread_kernel(int n_v, const int4 *
 
 }  // namespace
 
-#ifndef MC_HOST_SHIM  // tests/cpp/kernels_host.cpp runs the kernels above on the CPU; launches need nvcc
+#ifdef MC_HAVE_LAUNCH  // the serial stand-in of tests/cpp/shim/ has no launcher
 void launch_vsite_construct(int n_v, const int4 *sites, const int *slot_of_orig, float4 *xyzq, float a, float b, const NbParams &p,
                             cudaStream_t st, int64_t *launches) {
     if (n_v <= 0) return;
-    vsite_construct_kernel<<<div_up((size_t)n_v, 128), 128, 0, st>>>(n_v, sites, slot_of_orig, xyzq, a, b, p);
+    MC_LAUNCH(vsite_construct_kernel, div_up((size_t)n_v, 128), 128, 0, st, n_v, sites, slot_of_orig, xyzq, a, b, p);
     *launches += 1;
 }
 
 void launch_vsite_spread(int n_v, const int4 *sites, const int *slot_of_orig, float4 *force, float a, float b, cudaStream_t st,
                          int64_t *launches) {
     if (n_v <= 0) return;
-    vsite_spread_kernel<<<div_up((size_t)n_v, 128), 128, 0, st>>>(n_v, sites, slot_of_orig, force, a, b);
+    MC_LAUNCH(vsite_spread_kernel, div_up((size_t)n_v, 128), 128, 0, st, n_v, sites, slot_of_orig, force, a, b);
     *launches += 1;
 }
 
 void launch_shake_h(int n_c, const int4 *clusters, const float *dist, const int *slot_of_orig, float4 *xyzq, float4 *vel,
                     const NbParams &p, float dt, float tol, int *not_converged, cudaStream_t st, int64_t *launches) {
     if (n_c <= 0) return;
-    shake_h_kernel<<<div_up((size_t)n_c, 128), 128, 0, st>>>(n_c, clusters, dist, slot_of_orig, xyzq, vel, p, dt, tol, not_converged);
+    MC_LAUNCH(shake_h_kernel, div_up((size_t)n_c, 128), 128, 0, st, n_c, clusters, dist, slot_of_orig, xyzq, vel, p, dt, tol, not_converged);
     *launches += 1;
 }
 
@@ -184,7 +184,7 @@ void launch_settle(int n_w, const int4 *waters, const int *slot_of_orig, float4 
                    float d_oh, float d_hh, const NbParams &p, float dt, cudaStream_t st, int64_t *launches) {
     if (n_w <= 0) return;
     const SettleParams sp = mc_settle_params(m_o, m_h, d_oh, d_hh);
-    settle_kernel<<<div_up((size_t)n_w, 128), 128, 0, st>>>(n_w, waters, slot_of_orig, xyzq, vel, sp, p, dt);
+    MC_LAUNCH(settle_kernel, div_up((size_t)n_w, 128), 128, 0, st, n_w, waters, slot_of_orig, xyzq, vel, sp, p, dt);
     *launches += 1;
 }
 #endif

@@ -54,25 +54,25 @@ __global__ void __launch_bounds__(256) zero_velocities_kernel(int n_rows, float4
 
 }  // namespace
 
-#ifndef MC_HOST_SHIM
+#ifdef MC_HAVE_LAUNCH  // the stand-ins of tests/cpp/shim/ and shim_mt/ have no launcher; shim_fiber/ has
 void launch_zero_velocities(int n_rows, float4 *vel, cudaStream_t st, int64_t *launches) {
     if (n_rows <= 0) return;
-    zero_velocities_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(n_rows, vel);
+    MC_LAUNCH(zero_velocities_kernel, div_up(n_rows, 256), 256, 0, st, n_rows, vel);
     *launches += 1;
 }
 
 void launch_csvr(int n_rows, float4 *vel, const double *red3, double kT, double c, double dof_removed, uint64_t seed, uint64_t step,
                  float *lambda, cudaStream_t st, int64_t *launches) {
     if (n_rows <= 0) return;
-    csvr_lambda_kernel<<<1, 32, 0, st>>>(red3, kT, c, dof_removed, seed, step, lambda);
-    csvr_scale_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(n_rows, vel, lambda);
+    MC_LAUNCH(csvr_lambda_kernel, 1, 32, 0, st, red3, kT, c, dof_removed, seed, step, lambda);
+    MC_LAUNCH(csvr_scale_kernel, div_up(n_rows, 256), 256, 0, st, n_rows, vel, lambda);
     *launches += 2;
 }
 
 void launch_langevin_ou(int n_rows, float4 *vel, const int *orig, const uint8_t *flags, float c1, float c2, float kT, uint64_t seed,
                         uint64_t step, cudaStream_t st, int64_t *launches) {
     if (n_rows <= 0) return;
-    langevin_ou_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(n_rows, vel, orig, flags, c1, c2, kT, seed, step);
+    MC_LAUNCH(langevin_ou_kernel, div_up(n_rows, 256), 256, 0, st, n_rows, vel, orig, flags, c1, c2, kT, seed, step);
     *launches += 1;
 }
 

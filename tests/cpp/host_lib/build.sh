@@ -1,0 +1,32 @@
+#!/bin/bash
+# Test infrastructure: builds the WHOLE library for the host (no GPU, no nvcc): every .cu of molchanica_b200/csrc except
+# comm.cu is compiled by g++ over tests/cpp/shim_fiber/cuda_runtime.h, linked with the fiber runtime and the comm stub
+# into tests/cpp/_build/libmolchanica_md_host.so; a plain-DFT stand-in for cuFFT goes next to it.
+# MOLCHANICA_MD_LIB=<that .so> makes molchanica_b200/_lib.py load it (tests/test_library_on_host.py).
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(cd "$HERE/../../.." && pwd)"
+OUT="$ROOT/tests/cpp/_build"
+OBJ="$OUT/host_lib_obj"
+CXX=/usr/bin/g++; [ -x "$CXX" ] || CXX=g++
+mkdir -p "$OBJ"
+FLAGS="-O1 -g -std=c++20 -pthread -fPIC -ffp-contract=off -Wno-unknown-pragmas -Wno-attributes -DMC_HOST_SHIM=1 -I$ROOT/tests/cpp/shim_fiber"
+SRCS="sort_scan neighbor tile_build pair_force integrate thermostat dock dock_filter dock_poses bonded settle pme pme_params group_energy engine"
+pids=()
+for s in $SRCS; do
+  src="$ROOT/molchanica_b200/csrc/$s.cu"
+  if [ ! -f "$OBJ/$s.o" ] || [ -n "$(find "$ROOT/molchanica_b200/csrc" "$ROOT/tests/cpp/shim_fiber" "$ROOT/include" -newer "$OBJ/$s.o" -type f | head -1)" ]; then
+    $CXX $FLAGS -x c++ -c "$src" -o "$OBJ/$s.o" &
+    pids+=($!)
+  fi
+done
+$CXX $FLAGS -c "$ROOT/tests/cpp/shim_fiber/runtime.cpp" -o "$OBJ/runtime.o" &
+pids+=($!)
+$CXX $FLAGS -c "$HERE/comm_stub.cpp" -o "$OBJ/comm_stub.o" &
+pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+objs=""
+for s in $SRCS runtime comm_stub; do objs="$objs $OBJ/$s.o"; done
+$CXX -shared -pthread -o "$OUT/libmolchanica_md_host.so" $objs -ldl
+$CXX -O2 -std=c++17 -fPIC -shared -o "$OUT/libcufft_standin.so" "$HERE/cufft_standin.cpp"
+echo "$OUT/libmolchanica_md_host.so"

@@ -9,7 +9,7 @@
 static inline void __threadfence() {}
 static void halo_spin(const uint32_t *, uint32_t, int *) {}
 
-namespace { float2 s_tab[160 * 160]; }  // the kernel's dynamic shared memory
+
 
 #include "../../molchanica_b200/csrc/pair_force.cu"
 

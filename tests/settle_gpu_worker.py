@@ -45,7 +45,7 @@ def main():
                temperature=float(e.energy()["temperature"]), temperature_ref=float(t_ref))
     e.close()
     # four-site OPC water: SETTLE on (O, H, H) + virtual site M, against the oracle doing the same in fp64
-    w4 = W.water_box_opc(m=5, L=15.6)
+    w4 = W.water_box_opc()  # 216 molecules, L = 18.64: r_c + skin = 9.3 < L / 2
     a, b = w4["vsite_ab"]
     e = MdEngine.from_workload(w4)
     e.set_rigid_waters(w4["rigid_waters"], w4["d_oh"], w4["d_hh"], 15.999, 1.008)

@@ -1,0 +1,67 @@
+"""The WHOLE library on the CPU.  tests/cpp/host_lib/build.sh compiles every .cu of molchanica_b200/csrc except comm.cu
+with g++ over tests/cpp/shim_fiber/cuda_runtime.h (threads of a block = fibers, warp collectives / __syncthreads /
+mbarrier + bulk copy emulated, cudaMalloc = host memory poisoned with 0xFF) into libmolchanica_md_host.so; with
+MOLCHANICA_MD_LIB pointing at it the GPU parity tests run unchanged -- same Python harness, same C ABI, same engine.cu
+orchestration, same kernel sources, same oracle, same tolerances -- on a machine without a GPU.
+
+This is test infrastructure (a checker of the product's sources), not a CPU fallback: the product library still refuses to
+create a handle without a B200, and nothing outside tests/ knows the host build exists.  It does not replace the -m gpu
+run: timing, the compiled SASS, memory-model races, cuFFT and the multi-GPU path are only seen on hardware.
+
+The full GPU files also pass this way (test_gpu_parity.py incl. the 1,000,000-atom case: ~5 min); here a subset that fits
+the CPU suite: everything small, one 23,558-atom case, the docking scan, and the four worker scripts of the components
+that were written after the round-1 GPU budget was spent (bonded terms + minimiser + between-molecules energy + clash
+filter, SETTLE / SHAKE / virtual sites, SPME over a plain-DFT stand-in for cuFFT, Langevin / CSVR)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def host_env():
+    r = subprocess.run(["bash", os.path.join(HERE, "cpp", "host_lib", "build.sh")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    so = os.path.join(HERE, "cpp", "_build", "libmolchanica_md_host.so")
+    assert os.path.exists(so)
+    return dict(os.environ, MOLCHANICA_MD_LIB=so, MOLCHANICA_CUFFT_LIB=os.path.join(HERE, "cpp", "_build", "libcufft_standin.so"))
+
+
+def test_gpu_parity_tests_pass_on_the_host_build(host_env):
+    slow = "c4 or lane_width or variants or solv23558 or full_size"
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k", f"not ({slow})",
+                        os.path.join(HERE, "test_gpu_parity.py"), os.path.join(HERE, "test_gpu_dock.py")],
+                       capture_output=True, text=True, cwd=ROOT, env=host_env, timeout=1500)
+    tail = r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout and "skipped" not in r.stdout, tail
+    n_passed = int(r.stdout.rsplit(" passed", 1)[0].split()[-1])
+    assert n_passed >= 18, tail
+
+
+@pytest.mark.parametrize("worker", ["bonded", "settle", "pme", "langevin"])
+def test_components_not_yet_run_on_hardware_pass_on_the_host_build(worker, host_env):
+    """The exact checks tests/test_gpu_{bonded,settle,pme,langevin}.py will make on the first GPU of round 2 (there they are
+    xfail, non-strict, until hardware has confirmed them); here they must pass."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, f"{worker}_gpu_worker.py")], capture_output=True, text=True, cwd=ROOT,
+                       env=host_env, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert isinstance(res, dict) and res
+
+
+def test_product_library_still_refuses_without_a_gpu():
+    """No CPU fallback in the product: the nvcc-built library must fail loudly here."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    env = {k: v for k, v in os.environ.items() if k != "MOLCHANICA_MD_LIB"}
+    code = ("from molchanica_b200.engine import MdEngine, McError\n"
+            "try:\n    MdEngine()\n    print('CREATED')\nexcept McError as e:\n    print('REFUSED', e)\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=env, timeout=300)
+    assert "REFUSED" in r.stdout and "no CPU fallback" in r.stdout, r.stdout + r.stderr
