@@ -227,7 +227,9 @@ def main():
     # positions (what the viewer reads back, reference src/md/mod.rs:843-852) into pinned memory.
     e2e = None
     if not args.no_e2e:
-        # per step: mc_step(dt, 1, ext) with the step's external forces in pinned HOST memory (H2D inside), then
+        # per step: mc_step(dt, 1, ext) with the step's external forces in pinned HOST memory (H2D inside; on a single GPU
+        # the upload runs on its own stream under the force evaluation the previous call left open -- engine.cu,
+        # option defer_tail, invisible through the ABI: tests/test_gpu_parity.py::test_pipelined_external_forces...), then
         # mc_snapshot_begin hands the new positions to a pinned HOST buffer (D2H inside, double-buffered so that
         # the copy of step s overlaps the kernels of step s+1 -- the Snapshot queue of the reference,
         # src/md/mod.rs:118-152); mc_snapshot_wait(s-1) before buffer reuse, all copies drained before the clock stops.

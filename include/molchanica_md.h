@@ -188,7 +188,11 @@ int mc_set_overrides(mc_ctx *ctx, int lj_disabled, int coulomb_disabled);
  * handles; 1 = peer-memory ghost exchange inside the step kernels (default), 0 = NCCL send / recv),
  * "dd_migrate" (decomposed handles; 1 = rebuilds exchange boundary layers with the two neighbour ranks only
  * (default), 0 = all-gather of the whole system), "subcell_sort" (Morton sub-cell code in the sort key),
- * "profile_every" (k: inside mc_step only every k-th step's kernels are bracketed with events). */
+ * "profile_every" (k: inside mc_step only every k-th step's kernels are bracketed with events),
+ * "defer_tail" (1 (default): a single-GPU mc_step with ext_forces returns after its last drift and finishes that
+ * step -- force evaluation, second half kick -- under the upload of the next call's array, or as soon as anything
+ * but positions is asked for; results are the same, only the time at which the work is done moves; 0 = finish
+ * every step inside its own call). */
 int mc_set_option(mc_ctx *ctx, const char *name, double value);
 
 /* Replace positions (and optionally velocities) of the existing atoms, original order. */

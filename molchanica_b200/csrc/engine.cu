@@ -49,6 +49,15 @@ static int fail(mc_ctx *c, int code, const std::string &m) {
     return code;
 }
 
+// see engine_flush_tail
+#define MC_FLUSH(c)                                   \
+    do {                                              \
+        if ((c)->tail_pending) {                      \
+            const int rc_flush_ = engine_flush_tail(c); \
+            if (rc_flush_ != MC_OK) return rc_flush_; \
+        }                                             \
+    } while (0)
+
 // ---- lifetime ------------------------------------------------------------------------------------
 
 extern "C" int mc_abi_version(void) { return MC_ABI_VERSION; }
@@ -118,6 +127,7 @@ extern "C" int mc_destroy(mc_ctx *c) {
         cudaEventDestroy(c->ev_step_a); cudaEventDestroy(c->ev_step_b);
         cudaEventDestroy(c->ev_flag[0]); cudaEventDestroy(c->ev_flag[1]);
     }
+    if (c->st_up) { cudaStreamSynchronize(c->st_up); cudaEventDestroy(c->ev_up); cudaStreamDestroy(c->st_up); }
     if (c->st_copy) {
         cudaStreamSynchronize(c->st_copy);
         for (int b = 0; b < 2; ++b) { cudaEventDestroy(c->ev_snap_staged[b]); cudaEventDestroy(c->ev_snap_done[b]); }
@@ -134,6 +144,7 @@ extern "C" int mc_destroy(mc_ctx *c) {
 
 extern "C" int mc_set_box(mc_ctx *c, const float lo[3], const float hi[3], int periodic) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     MC_REQUIRE(c, lo && hi, "mc_set_box: NULL bounds");
     for (int a = 0; a < 3; ++a) {
         MC_REQUIRE(c, !periodic || hi[a] > lo[a], "mc_set_box: periodic box needs hi > lo on every axis");
@@ -149,6 +160,7 @@ extern "C" int mc_set_box(mc_ctx *c, const float lo[3], const float hi[3], int p
 
 extern "C" int mc_set_cutoffs(mc_ctx *c, float rc_lj, float rc_q, float skin, int coulomb_mode, float alpha) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     MC_REQUIRE(c, rc_lj > 0.f && rc_q > 0.f && skin >= 0.f, "mc_set_cutoffs: cutoffs must be positive, skin >= 0");
     MC_REQUIRE(c, coulomb_mode >= MC_COULOMB_NONE && coulomb_mode <= MC_COULOMB_ERFC, "mc_set_cutoffs: bad coulomb_mode");
     c->rc_lj = rc_lj; c->rc_q = rc_q; c->skin = skin; c->coul_mode = coulomb_mode; c->alpha = alpha;
@@ -160,6 +172,7 @@ extern "C" int mc_set_cutoffs(mc_ctx *c, float rc_lj, float rc_q, float skin, in
 
 extern "C" int mc_set_overrides(mc_ctx *c, int lj_disabled, int coulomb_disabled) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     c->lj_disabled = lj_disabled != 0;
     c->coul_disabled = coulomb_disabled != 0;
     c->forces_valid = false;
@@ -168,6 +181,7 @@ extern "C" int mc_set_overrides(mc_ctx *c, int lj_disabled, int coulomb_disabled
 
 extern "C" int mc_set_lj_table(mc_ctx *c, int n_types, const float *sigma_eps) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     MC_REQUIRE(c, n_types >= 1 && n_types <= pair_force_max_types() && sigma_eps,
                "mc_set_lj_table: 1 <= n_types <= " + std::to_string(pair_force_max_types()) + " and a table are required");
     cudaSetDevice(c->device);
@@ -221,6 +235,7 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
     MC_REQUIRE(c, n == 0 || xyzq, "mc_set_atoms: xyzq is NULL");
     cudaSetDevice(c->device);
     c->n_global = n;
+    c->tail_pending = false;  // a new system: nothing of the old one is left to finish
     c->list_valid = false;
     c->forces_valid = false;
     c->have_excl = false;
@@ -258,6 +273,7 @@ int engine_upload_local(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint1
 
 extern "C" int mc_set_exclusions(mc_ctx *c, const int32_t *start, const int32_t *idx) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     c->list_valid = false;
     c->forces_valid = false;
@@ -274,6 +290,7 @@ extern "C" int mc_set_exclusions(mc_ctx *c, const int32_t *start, const int32_t 
 
 extern "C" int mc_set_pairs14(mc_ctx *c, int64_t m, const int32_t *pairs, float scale_lj, float scale_q) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     c->forces_valid = false;
     c->scale14_lj = scale_lj;
@@ -326,6 +343,7 @@ static int upload_terms(mc_ctx *c, const char *who, int64_t m, const int32_t *id
 
 extern "C" int mc_set_bonds(mc_ctx *c, int64_t m, const int32_t *pairs, const float *k_r0) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active, "mc_set_bonds: bonded terms on a decomposed handle are not supported yet");
     MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || (pairs && k_r0)), "mc_set_bonds: bad arguments");
@@ -338,6 +356,7 @@ extern "C" int mc_set_bonds(mc_ctx *c, int64_t m, const int32_t *pairs, const fl
 
 extern "C" int mc_set_angles(mc_ctx *c, int64_t m, const int32_t *triples, const float *k_theta0) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active, "mc_set_angles: bonded terms on a decomposed handle are not supported yet");
     MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || (triples && k_theta0)), "mc_set_angles: bad arguments");
@@ -350,6 +369,7 @@ extern "C" int mc_set_angles(mc_ctx *c, int64_t m, const int32_t *triples, const
 
 extern "C" int mc_set_dihedrals(mc_ctx *c, int64_t m, const int32_t *quads, const float *pk_n_phase) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active, "mc_set_dihedrals: bonded terms on a decomposed handle are not supported yet");
     MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || (quads && pk_n_phase)), "mc_set_dihedrals: bad arguments");
@@ -364,6 +384,7 @@ extern "C" int mc_set_dihedrals(mc_ctx *c, int64_t m, const int32_t *quads, cons
 
 extern "C" int mc_set_hbond_constraints(mc_ctx *c, int64_t m, const int32_t *clusters, const float *lengths) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active, "mc_set_hbond_constraints: constraints on a decomposed handle are not supported yet");
     MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || (clusters && lengths)), "mc_set_hbond_constraints: bad arguments");
@@ -403,6 +424,7 @@ extern "C" int mc_set_hbond_constraints(mc_ctx *c, int64_t m, const int32_t *clu
 
 extern "C" int mc_set_virtual_sites(mc_ctx *c, int64_t m, const int32_t *quads, float a, float b) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active, "mc_set_virtual_sites: virtual sites on a decomposed handle are not supported yet");
     MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || quads), "mc_set_virtual_sites: bad arguments");
@@ -414,6 +436,7 @@ extern "C" int mc_set_virtual_sites(mc_ctx *c, int64_t m, const int32_t *quads, 
 
 extern "C" int mc_set_thermostat(mc_ctx *c, int kind, float temperature_k, float gamma_per_ps, uint64_t seed) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     MC_REQUIRE(c, kind == MC_THERMOSTAT_NONE || kind == MC_THERMOSTAT_LANGEVIN || kind == MC_THERMOSTAT_CSVR, "mc_set_thermostat: unknown kind");
     MC_REQUIRE(c, !c->comm_active || kind == MC_THERMOSTAT_NONE, "mc_set_thermostat: thermostats on a decomposed handle are not supported yet");
     MC_REQUIRE(c, kind == MC_THERMOSTAT_NONE || (temperature_k >= 0.f && gamma_per_ps >= 0.f), "mc_set_thermostat: negative temperature or friction");
@@ -428,6 +451,7 @@ extern "C" int mc_set_thermostat(mc_ctx *c, int kind, float temperature_k, float
 
 extern "C" int mc_set_pme(mc_ctx *c, int k1, int k2, int k3) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active, "mc_set_pme: reciprocal space on a decomposed handle is not supported yet");
     MC_REQUIRE(c, (k1 == 0 && k2 == 0 && k3 == 0) || c->periodic, "mc_set_pme: needs a periodic box");
@@ -440,6 +464,7 @@ extern "C" int mc_set_pme(mc_ctx *c, int k1, int k2, int k3) {
 
 extern "C" int mc_set_rigid_waters(mc_ctx *c, int64_t m, const int32_t *triples, float d_oh, float d_hh, float m_o, float m_h) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active, "mc_set_rigid_waters: constraints on a decomposed handle are not supported yet");
     MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || triples), "mc_set_rigid_waters: bad arguments");
@@ -453,6 +478,7 @@ extern "C" int mc_set_rigid_waters(mc_ctx *c, int64_t m, const int32_t *triples,
 
 extern "C" int mc_set_positions(mc_ctx *c, const mc_float4 *xyzq) {
     if (!c || !xyzq) return MC_E_INVALID;
+    MC_FLUSH(c);
     MC_REQUIRE(c, !c->comm_active, "mc_set_positions: not available on a decomposed handle; use mc_set_atoms");
     cudaSetDevice(c->device);
     const int64_t n = c->n;
@@ -468,6 +494,7 @@ extern "C" int mc_set_positions(mc_ctx *c, const mc_float4 *xyzq) {
 
 extern "C" int mc_set_velocities(mc_ctx *c, const mc_float4 *vel) {
     if (!c || !vel) return MC_E_INVALID;
+    MC_FLUSH(c);
     MC_REQUIRE(c, !c->comm_active, "mc_set_velocities: not available on a decomposed handle; use mc_set_atoms");
     cudaSetDevice(c->device);
     const int64_t n = c->n;
@@ -481,6 +508,7 @@ extern "C" int mc_set_velocities(mc_ctx *c, const mc_float4 *vel) {
 
 extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
     if (!c || !name) return MC_E_INVALID;
+    MC_FLUSH(c);
     const std::string k(name);
     if (k == "pair_lanes") {
         const int v = (int)value;
@@ -507,6 +535,8 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         c->halo_fused = value != 0.0;
     } else if (k == "rebuild_every") {
         c->rebuild_every = (int)value;
+    } else if (k == "defer_tail") {
+        c->defer_tail = value != 0.0;
     } else {
         return fail(c, MC_E_INVALID, "mc_set_option: unknown option '" + k + "'");
     }
@@ -660,6 +690,7 @@ int engine_build_rows(mc_ctx *c) {
 
 extern "C" int mc_build_neighbors(mc_ctx *c) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->rc_lj > 0.f, "mc_build_neighbors: call mc_set_cutoffs first");
     MC_REQUIRE(c, c->n_types > 0, "mc_build_neighbors: call mc_set_lj_table first");
@@ -763,9 +794,27 @@ static int ensure_ready(mc_ctx *c, const char *who) {
     return MC_OK;
 }
 
+// mc_step with external forces may return with the last step's force evaluation and second half kick still open
+// (see there).  Every entry point that observes or changes anything but positions closes them first.
+int engine_flush_tail(mc_ctx *c) {
+    if (!c->tail_pending) return MC_OK;
+    cudaSetDevice(c->device);
+    int rc = ensure_ready(c, "mc_step (deferred half kick)");
+    if (rc != MC_OK) return rc;
+    if (!c->forces_valid && (rc = engine_launch_forces(c, false)) != MC_OK) return rc;
+    const size_t r0 = (size_t)c->row0;
+    launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, c->tail_ext,
+                      c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, 0.5f * c->tail_dt, 0.f, 0.f, 0.f,
+                      c->rebuild_flag.p, c->st, &c->launches);
+    c->tail_pending = false;
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
+    return MC_OK;
+}
+
 extern "C" int mc_compute_forces(mc_ctx *c) {
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);
+    MC_FLUSH(c);
     c->prof_now = true;
     int rc = ensure_ready(c, "mc_compute_forces");
     if (rc != MC_OK) return rc;
@@ -795,27 +844,62 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     cudaSetDevice(c->device);
     MC_REQUIRE(c, n_steps >= 0 && dt > 0.f, "mc_step: n_steps >= 0 and dt > 0 required");
     c->prof_now = true;
+    cudaStream_t st = c->st;
+    // decomposed runs rebuild on a schedule every rank derives from the same numbers (no per-step agreement)
+    const bool pipelined = !c->comm_active && c->rebuild_every <= 0 && !c->sync_rebuild;
+    // External forces are the one per-call input of a step (MdState::step(dev, dt, Some(forces)), reference
+    // src/mol_alignment.rs:346).  Their upload must not sit in front of the kernels: it goes to a stream of its own
+    // (alternating device buffers), and the call returns after the LAST DRIFT -- the positions the caller reads back --
+    // leaving that step's force evaluation and second half kick open (`tail_pending`).  The next call starts its
+    // upload, runs the open force evaluation meanwhile (it does not depend on the new array), closes the half kick
+    // with the PREVIOUS array and only then waits for the upload.  Everything that observes more than positions
+    // closes the tail first (engine_flush_tail), so the deferral is invisible through the ABI.
+    const bool defer = c->defer_tail && ext_forces != nullptr && pipelined && n_steps > 0;
+    struct UploadGuard {  // whatever path leaves this function, the caller's array is no longer being read
+        cudaStream_t s = nullptr;
+        ~UploadGuard() { if (s) cudaStreamSynchronize(s); }
+    } upload_guard;
+    const float *d_ext = nullptr;
+    bool wait_upload = false;
+    if (ext_forces) {
+        DevBuf<float> &buf = c->ext_k ? c->ext_force2 : c->ext_force;
+        c->ext_k ^= 1;
+        MC_CUDA(c, buf.ensure((size_t)3 * c->n_global));
+        if (defer) {
+            if (!c->st_up) {
+                MC_CUDA(c, cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking));
+                MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+            }
+            upload_guard.s = c->st_up;
+            MC_CUDA(c, cudaMemcpyAsync(buf.p, ext_forces, sizeof(float) * 3 * c->n_global, cudaMemcpyHostToDevice, c->st_up));
+            MC_CUDA(c, cudaEventRecord(c->ev_up, c->st_up));
+            wait_upload = true;
+        } else {
+            MC_CUDA(c, cudaMemcpyAsync(buf.p, ext_forces, sizeof(float) * 3 * c->n_global, cudaMemcpyHostToDevice, st));
+        }
+        d_ext = buf.p;
+    }
     int rc = ensure_ready(c, "mc_step");
     if (rc != MC_OK) return rc;
-    cudaStream_t st = c->st;
-    const float *d_ext = nullptr;
-    if (ext_forces) {
-        MC_CUDA(c, c->ext_force.ensure((size_t)3 * c->n_global));
-        MC_CUDA(c, cudaMemcpyAsync(c->ext_force.p, ext_forces, sizeof(float) * 3 * c->n_global, cudaMemcpyHostToDevice, st));
-        d_ext = c->ext_force.p;
-    }
     if (!c->forces_valid) {
         if (c->comm_active && (rc = comm_halo_positions(c)) != MC_OK) return rc;
         if ((rc = engine_launch_forces(c, false)) != MC_OK) return rc;
     }
+    if (c->tail_pending) {
+        // second half kick of the step the previous call left open, with THAT call's external forces
+        const size_t r0 = (size_t)c->row0;
+        launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, c->tail_ext,
+                          c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, 0.5f * c->tail_dt, 0.f, 0.f, 0.f,
+                          c->rebuild_flag.p, st, &c->launches);
+        c->tail_pending = false;
+    }
+    if (wait_upload) MC_CUDA(c, cudaStreamWaitEvent(st, c->ev_up, 0));
     // Velocity Verlet, two kernels per step: [kick + drift] and [pair forces].  The second half
     // kick of step s and the first half kick of step s+1 are one full kick in the same launch.
     // The rebuild decision is pipelined: kick_drift raises the flag with a look-ahead margin, the
     // flag travels to pinned host memory asynchronously, and the host acts on the flag of the
     // PREVIOUS step while the GPU is already busy -- no per-step stream synchronisation.
     const float max_disp = 0.5f * c->skin;
-    // decomposed runs rebuild on a schedule every rank derives from the same numbers (no per-step agreement)
-    const bool pipelined = !c->comm_active && c->rebuild_every <= 0 && !c->sync_rebuild;
     // the host acts on the flag of step s-1 before the pair kernel of step s: the stale list is last used one
     // drift after the flag could first have been raised, so one drift of margin is needed; 1.5 leaves room
     // for the change of velocity within that step
@@ -881,6 +965,15 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
                         c->csvr_lambda.p, st, &c->launches);
         }
         c->steps_since_build++;
+        if (defer && s == n_steps - 1) {
+            // last step of a pipelined call: stop after the drift.  Its flag word is read after the final
+            // synchronisation below (no rebuild has happened since it was written, so it is never stale).
+            have_prev = true;
+            skip_prev = false;
+            c->forces_valid = false;
+            c->n_steps++;
+            break;
+        }
         bool rebuild = false;
         if (c->comm_active) {
             rebuild = c->steps_since_build >= comm_interval(c);
@@ -912,7 +1005,11 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         if ((rc = engine_launch_forces(c, false, fused_halo && !rebuild ? &split : nullptr)) != MC_OK) return rc;
         c->n_steps++;
     }
-    if (n_steps > 0) {
+    if (defer) {
+        c->tail_pending = true;
+        c->tail_dt = dt;
+        c->tail_ext = d_ext;
+    } else if (n_steps > 0) {
         TimedRegion tr(c, c->integ_acc);
         const size_t r0 = (size_t)c->row0;
         launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, d_ext,
@@ -965,6 +1062,7 @@ extern "C" double mc_last_step_ms(mc_ctx *c) { return c ? c->last_step_ms : 0.0;
 // STATUS: host logic written after round 1's GPU budget was spent; not yet run on hardware.
 extern "C" int mc_minimize_energy(mc_ctx *c, int max_iters, int *iters_accepted, double *e_initial, double *e_final) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, max_iters >= 0, "mc_minimize_energy: max_iters >= 0 required");
     MC_REQUIRE(c, !c->comm_active, "mc_minimize_energy: not available on a decomposed handle yet");
@@ -1046,12 +1144,14 @@ extern "C" int mc_get_positions(mc_ctx *c, mc_float4 *out) {
 
 extern "C" int mc_get_velocities(mc_ctx *c, mc_float4 *out) {
     if (!c || !out) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     return read_sorted_to_orig(c, c->vel[c->cur].p, out);
 }
 
 extern "C" int mc_get_forces(mc_ctx *c, mc_float4 *out) {
     if (!c || !out) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->forces_valid, "mc_get_forces: no force evaluation since the last change; call mc_compute_forces");
     return read_sorted_to_orig(c, c->force.p, out);
@@ -1118,6 +1218,7 @@ extern "C" int mc_snapshot_wait(mc_ctx *c) {
 
 extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
     if (!c || !out) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->forces_valid, "mc_get_energy: no force evaluation since the last change; call mc_compute_forces");
     if (!c->forces_have_energy) {
@@ -1174,6 +1275,7 @@ extern "C" int mc_set_molecule_ids(mc_ctx *c, const uint16_t *mol_id) {
 
 extern "C" int mc_get_energy_between_mols(mc_ctx *c, double *out) {
     if (!c || !out) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->have_mols, "mc_get_energy_between_mols: call mc_set_molecule_ids first");
     int rc = ensure_ready(c, "mc_get_energy_between_mols");
@@ -1226,6 +1328,7 @@ extern "C" int mc_reset_timers(mc_ctx *c) {
 
 extern "C" int mc_get_neighbors(mc_ctx *c, int64_t *start, int32_t *idx, int64_t cap, int64_t *total) {
     if (!c || !start || !total) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active, "mc_get_neighbors: single-GPU handles only");
     MC_REQUIRE(c, c->list_valid, "mc_get_neighbors: no current list; call mc_build_neighbors");
@@ -1252,6 +1355,7 @@ extern "C" int mc_get_neighbors(mc_ctx *c, int64_t *start, int32_t *idx, int64_t
 
 extern "C" int mc_time_kernels(mc_ctx *c, int reps, int flush_l2) {
     if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, reps > 0, "mc_time_kernels: reps > 0 required");
     c->prof_now = true;

@@ -140,6 +140,17 @@ struct mc_ctx {
     float vsite_a = 0, vsite_b = 0;
     double total_mass = 0.0;   // amu, from the inverse masses handed to mc_set_atoms (density of the snapshot)
 
+    // pipelined external forces (engine.cu, mc_step): the caller's array is uploaded on a stream of its own while the
+    // force evaluation the previous call left open runs; that call's second half kick is applied once both are there
+    bool defer_tail = true;      // option "defer_tail"
+    bool tail_pending = false;   // positions are one step ahead of forces / velocities (half kick outstanding)
+    float tail_dt = 0.f;
+    const float *tail_ext = nullptr;  // external forces of the outstanding half kick (device, one of the two buffers)
+    DevBuf<float> ext_force2;
+    int ext_k = 0;
+    cudaStream_t st_up = nullptr;
+    cudaEvent_t ev_up = nullptr;
+
     // asynchronous snapshots (mc_snapshot_begin / mc_snapshot_wait): double-buffered staging + a copy stream
     cudaStream_t st_copy = nullptr;
     cudaEvent_t ev_snap_staged[2] = {nullptr, nullptr}, ev_snap_done[2] = {nullptr, nullptr};
@@ -186,7 +197,7 @@ struct mc_ctx {
         scratch.release(); cell_start.release(); nbr_count.release(); nbr_start.release(); nbr_list.release();
         cnt_orig.release(); start_orig.release(); export_rows.release(); tile_need.release();
         excl_start.release(); excl_idx.release(); p14_start.release(); p14_idx.release();
-        ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); d_poses.release(); d_scores.release();
+        ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); ext_force2.release(); d_poses.release(); d_scores.release();
         grid.release(); red_partial.release(); red_out.release(); d_rec.release(); d_lig.release();
         d_rec_meta.release(); d_lig_meta.release(); d_rec_s.release(); d_lig_s.release(); d_keep.release();
         for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_ids[b].release(); }
@@ -235,6 +246,7 @@ struct TimedRegion {
 
 // engine.cu
 int engine_build_list(mc_ctx *c);
+int engine_flush_tail(mc_ctx *c);  // closes the half kick mc_step left open (pipelined external forces)
 int engine_build_rows(mc_ctx *c);
 // hs != nullptr: decomposed step with the peer-memory halo -- interior rows first, then the rows of the
 // first and last owned layer in one launch that waits for the neighbours' pushes

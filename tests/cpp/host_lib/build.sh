@@ -8,9 +8,17 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 ROOT="$(cd "$HERE/../../.." && pwd)"
 OUT="$ROOT/tests/cpp/_build"
 OBJ="$OUT/host_lib_obj"
+NAME=libmolchanica_md_host
+SAN=""
+if [ "$1" = "--asan" ]; then
+  # AddressSanitizer build: "device" memory is heap memory, so every out-of-bounds access of a kernel or of engine.cu is
+  # reported (the compute-sanitizer memcheck of this stand-in).  Load with LD_PRELOAD=$(g++ -print-file-name=libasan.so)
+  # ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0
+  OBJ="$OUT/host_lib_obj_asan"; NAME=libmolchanica_md_host_asan; SAN="-fsanitize=address -fno-omit-frame-pointer"
+fi
 CXX=/usr/bin/g++; [ -x "$CXX" ] || CXX=g++
 mkdir -p "$OBJ"
-FLAGS="-O1 -g -std=c++20 -pthread -fPIC -ffp-contract=off -Wno-unknown-pragmas -Wno-attributes -DMC_HOST_SHIM=1 -I$ROOT/tests/cpp/shim_fiber"
+FLAGS="-O1 -g -std=c++20 -pthread -fPIC -ffp-contract=off -Wno-unknown-pragmas -Wno-attributes -DMC_HOST_SHIM=1 -I$ROOT/tests/cpp/shim_fiber $SAN"
 SRCS="sort_scan neighbor tile_build pair_force integrate thermostat dock dock_filter dock_poses bonded settle pme pme_params group_energy engine"
 pids=()
 for s in $SRCS; do
@@ -27,6 +35,6 @@ pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 objs=""
 for s in $SRCS runtime comm_stub; do objs="$objs $OBJ/$s.o"; done
-$CXX -shared -pthread -o "$OUT/libmolchanica_md_host.so" $objs -ldl
+$CXX -shared -pthread $SAN -o "$OUT/$NAME.so" $objs -ldl
 $CXX -O2 -std=c++17 -fPIC -shared -o "$OUT/libcufft_standin.so" "$HERE/cufft_standin.cpp"
-echo "$OUT/libmolchanica_md_host.so"
+echo "$OUT/$NAME.so"

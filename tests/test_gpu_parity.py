@@ -172,6 +172,75 @@ def test_external_forces_and_static_atoms(Engine, oracle):
     e.close()
 
 
+def _run_with_changing_ext(Engine, w, defer, n_calls, steps_per_call, poke):
+    """One mc_step(dt, k, ext) per call with a different array every call, positions read back after every call (as the
+    reference's alignment loop does, src/mol_alignment.rs:318-353).  `poke` = observers / setters thrown in on the way."""
+    n = len(w["xyzq"])
+    e = Engine.from_workload(w)
+    e.set_option("defer_tail", 1 if defer else 0)
+    rng = np.random.default_rng(77)
+    seen = []
+    for k in range(n_calls):
+        ext = np.zeros((n, 3), np.float32)
+        ext[k % 7::7] = rng.normal(0, 3.0, ext[k % 7::7].shape)
+        e.step(w["dt"], steps_per_call, ext_forces=ext)
+        ext[:] = np.nan                               # the array may be reused the moment the call returns
+        seen.append(e.positions())
+        if poke and k == 3:
+            seen.append(e.velocities())               # observer in the middle: closes the open half kick
+        if poke and k == 6:
+            seen.append(e.energy()["energy_kinetic"])
+        if poke and k == 9:
+            v = e.velocities()
+            v[:, :3] *= 0.5
+            e.set_velocities(v)                       # setter in the middle: must see, then replace, the finished velocities
+        if poke and k == 12:
+            e.step(w["dt"], 2)                        # a call without external forces in between
+    out = dict(x=e.positions(), v=e.velocities(), f=e.forces(), en=e.energy(), seen=seen, rebuilds=e.stats()["n_rebuilds"],
+               steps=e.stats()["n_steps"])
+    e.close()
+    return out
+
+
+@pytest.mark.parametrize("steps_per_call,poke,skin", [(1, False, 0.35), (1, True, 0.35), (3, True, 0.35), (1, True, 1.5), (3, False, 1.5)])
+def test_pipelined_external_forces_are_invisible_through_the_abi(steps_per_call, poke, skin, Engine, oracle):
+    """mc_step with external forces returns after the last drift and finishes that step (force evaluation + second half
+    kick) under the upload of the next call's array (engine.cu, `defer_tail`).  Through the ABI that must be invisible:
+    bit-identical positions, velocities, forces and energies with the option off, whatever is called in between, as long
+    as no rebuild falls into the run (a rebuild changes the summation order of a row; with the option on, both half kicks
+    around it use the forces of the NEW list, with it off the first uses the old one: a last-bit difference); and the
+    trajectory is the oracle's."""
+    w = dict(W.lj_fluid(m=12), skin=skin)             # small skin: rebuilds fall inside the run
+    maxwell = np.random.default_rng(3).normal(0, 1.0, (len(w["xyzq"]), 3)).astype(np.float32)
+    w["vel"] = w["vel"].copy()
+    w["vel"][:, :3] += 2.0 * maxwell * w["vel"][:, 3:4] ** 0.5
+    a = _run_with_changing_ext(Engine, w, True, 16, steps_per_call, poke)
+    b = _run_with_changing_ext(Engine, w, False, 16, steps_per_call, poke)
+    assert a["steps"] == b["steps"]
+    if skin < 1.0:
+        assert a["rebuilds"] >= 2 or poke            # (the halved velocities of the poked run may avoid the second one)
+        same = lambda u, v: np.allclose(u, v, rtol=2e-5, atol=2e-5)
+    else:
+        assert a["rebuilds"] == 1
+        same = np.array_equal
+    for u, v in zip(a["seen"], b["seen"]):
+        assert same(np.asarray(u), np.asarray(v))
+    assert same(a["x"], b["x"]) and same(a["v"], b["v"]) and same(a["f"], b["f"])
+    assert all(same(np.float64(a["en"][k]), np.float64(b["en"][k])) for k in a["en"])
+    if not poke:
+        # against the oracle: the same arrays, call by call
+        n = len(w["xyzq"])
+        rng = np.random.default_rng(77)
+        cur = dict(w)
+        for k in range(16):
+            ext = np.zeros((n, 3), np.float32)
+            ext[k % 7::7] = rng.normal(0, 3.0, ext[k % 7::7].shape)
+            r = oracle.md_run(cur, steps_per_call, precision=64, ext_force=ext)
+            cur = dict(cur, xyzq=r["xyzq"], vel=r["vel"])
+        ok, worst, scale = trajectory_close(a["x"], cur["xyzq"], w["xyzq"], w["box_ext"])
+        assert ok, (worst, scale)
+
+
 def test_nve_energy_and_momentum_on_lj_fluid(Engine):
     w = W.lj_fluid(m=16)
     e = Engine.from_workload(w)
