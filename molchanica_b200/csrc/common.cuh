@@ -29,6 +29,8 @@
 #define MC_LAUNCH(kernel, grid, block, smem, stream, ...) shim_launch((grid), (block), [&] { kernel(__VA_ARGS__); })
 #endif
 
+#define MC_COMMA ,  // for kernel names with several template arguments inside MC_LAUNCH
+
 #define MC_WARP 32
 #define MC_FULL_MASK 0xffffffffu
 #define MC_ACCEL_CONV 418.4f       // kcal/mol/A/amu -> A/ps^2

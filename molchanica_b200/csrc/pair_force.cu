@@ -346,9 +346,14 @@ void launch_lanes(const PairLaunch &L, cudaStream_t st) {
     const size_t smem = L.multi ? sizeof(float2) * L.p.n_types * L.p.n_types : 0;
 #define MC_PF(M, C, P, E)                                                                                               \
     do {                                                                                                                \
-        auto kern = L.uniform ? pair_force_kernel<LANES, M, C, P, E, true> : pair_force_kernel<LANES, M, C, P, E, false>;       \
-        MC_LAUNCH(kern, blocks, 128, smem, st, L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, \
-                  L.ljtab, L.p, L.lj_on, L.force, L.n_interior, L.n_first, L.wait);                                     \
+        if (L.uniform)                                                                                                  \
+            MC_LAUNCH(pair_force_kernel<LANES MC_COMMA M MC_COMMA C MC_COMMA P MC_COMMA E MC_COMMA true>, blocks, 128, smem, st, \
+                      L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on,   \
+                      L.force, L.n_interior, L.n_first, L.wait);                                                        \
+        else                                                                                                            \
+            MC_LAUNCH(pair_force_kernel<LANES MC_COMMA M MC_COMMA C MC_COMMA P MC_COMMA E MC_COMMA false>, blocks, 128, smem, st, \
+                      L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on,   \
+                      L.force, L.n_interior, L.n_first, L.wait);                                                        \
     } while (0)
 #define MC_PF_E(M, C, P) \
     if (L.energy) MC_PF(M, C, P, true); else MC_PF(M, C, P, false)
