@@ -107,6 +107,7 @@ extern "C" {
     pub fn mc_get_forces(ctx: *mut McCtx, out: *mut McFloat4) -> c_int;
     pub fn mc_get_energy(ctx: *mut McCtx, out: *mut McEnergy) -> c_int;
     pub fn mc_get_stats(ctx: *mut McCtx, out: *mut McStats) -> c_int;
+    pub fn mc_get_pressure(ctx: *mut McCtx, pressure_bar: *mut f64, virial: *mut f64) -> c_int;
     pub fn mc_set_molecule_ids(ctx: *mut McCtx, mol_id: *const u16) -> c_int;
     pub fn mc_get_energy_between_mols(ctx: *mut McCtx, out: *mut f64) -> c_int;
     pub fn mc_snapshot_begin(ctx: *mut McCtx, out_positions: *mut McFloat4, out_ids: *mut i32, n_out: *mut i64) -> c_int;

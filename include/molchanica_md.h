@@ -231,6 +231,13 @@ int mc_get_velocities(mc_ctx *ctx, mc_float4 *out);
 int mc_get_forces(mc_ctx *ctx, mc_float4 *out);
 int mc_get_energy(mc_ctx *ctx, mc_energy *out);
 int mc_get_stats(mc_ctx *ctx, mc_stats *out);
+/* SnapshotEnergyData.pressure (reference ui/panels/md_viewer.rs:202-256): P = (2 KE + W) / 3V in bar and the virial
+ * W = sum r_ij . f_ij in kcal/mol over nonbonded pairs inside the cutoffs, scaled 1-4 pairs, bonded terms and the SPME
+ * reciprocal sum with its excluded-pair correction.  One extra pass over the neighbour list, on demand only.
+ * Periodic, single-GPU handles without constraints (the constraint virial is not implemented: MC_E_INVALID).
+ * Either output may be NULL. */
+int mc_get_pressure(mc_ctx *ctx, double *pressure_bar, double *virial);
+
 /* SnapshotEnergyData.energy_potential_between_mols (src/md/mod.rs:1242-1245): mol_id[n] assigns every atom to a molecule;
  * mc_get_energy_between_mols sums the nonbonded pair energies (LJ + the Coulomb form in force, within the cutoffs)
  * over the listed pairs whose atoms belong to different molecules.  On demand, not on the step path; excluded

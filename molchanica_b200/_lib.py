@@ -92,6 +92,7 @@ def lib():
     L.mc_set_dihedrals.argtypes = [vp, i64, vp, vp]
     L.mc_set_molecule_ids.argtypes = [vp, vp]
     L.mc_get_energy_between_mols.argtypes = [vp, C.POINTER(C.c_double)]
+    L.mc_get_pressure.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mc_set_hbond_constraints.argtypes = [vp, i64, vp, vp]
     L.mc_set_virtual_sites.argtypes = [vp, i64, vp, f32, f32]
     L.mc_set_thermostat.argtypes = [vp, i32, f32, f32, C.c_uint64]

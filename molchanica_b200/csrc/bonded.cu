@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128) bonded_kernel(BondedTerms t, const int *_
                                                       float4 *__restrict__ force, double *__restrict__ energy3,
                                                       int want_energy) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    float e = 0.f;
+    float e = 0.f, w = 0.f;  // energy and sum_a (r_a - r_ref) . f_a of this thread's term (its share of the virial)
     int kind = -1;
     if (tid < t.n_bonds) {
         kind = 0;
@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(128) bonded_kernel(BondedTerms t, const int *_
         float d[3] = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z}, fi[3];
         min_image3(d, p);
         e = mc_bond_term(d, kr.x, kr.y, fi);
+        w = d[0] * fi[0] + d[1] * fi[1] + d[2] * fi[2];
         const float fj[3] = {-fi[0], -fi[1], -fi[2]};
         add_force(force, si, fi);
         add_force(force, sj, fj);
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(128) bonded_kernel(BondedTerms t, const int *_
         min_image3(a, p);
         min_image3(b, p);
         e = mc_angle_term(a, b, kt.x, kt.y, fi, fk);
+        w = a[0] * fi[0] + a[1] * fi[1] + a[2] * fi[2] + b[0] * fk[0] + b[1] * fk[1] + b[2] * fk[2];  // zero up to rounding
         const float fj[3] = {-(fi[0] + fk[0]), -(fi[1] + fk[1]), -(fi[2] + fk[2])};
         add_force(force, si, fi);
         add_force(force, sj, fj);
@@ -75,6 +77,9 @@ __global__ void __launch_bounds__(128) bonded_kernel(BondedTerms t, const int *_
         min_image3(rkj, p);
         min_image3(rkl, p);
         e = mc_dihedral_term(rij, rkj, rkl, prm.x, prm.y, prm.z, fi, fj, fk, fl);
+        // relative to atom j: r_i - r_j = rij, r_k - r_j = rkj, r_l - r_j = rkj - rkl (zero up to rounding as well)
+        w = rij[0] * fi[0] + rij[1] * fi[1] + rij[2] * fi[2] + rkj[0] * fk[0] + rkj[1] * fk[1] + rkj[2] * fk[2] +
+            (rkj[0] - rkl[0]) * fl[0] + (rkj[1] - rkl[1]) * fl[1] + (rkj[2] - rkl[2]) * fl[2];
         add_force(force, si, fi);
         add_force(force, sj, fj);
         add_force(force, sk, fk);
@@ -89,6 +94,9 @@ __global__ void __launch_bounds__(128) bonded_kernel(BondedTerms t, const int *_
             for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(MC_FULL_MASK, v, d);
             if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(energy3 + k, (double)v);
         }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(MC_FULL_MASK, w, d);
+        if ((threadIdx.x & 31) == 0 && w != 0.f) atomicAdd(energy3 + 3, (double)w);  // [3]: virial of the bonded terms
     }
 }
 
@@ -99,7 +107,7 @@ void launch_bonded(const BondedTerms &t, const int *slot_of_orig, const float4 *
                    double *energy3, bool want_energy, cudaStream_t st, int64_t *launches) {
     const int n = t.n_bonds + t.n_angles + t.n_dihedrals;
     if (n <= 0) return;
-    if (want_energy) cudaMemsetAsync(energy3, 0, 3 * sizeof(double), st);
+    if (want_energy) cudaMemsetAsync(energy3, 0, 4 * sizeof(double), st);
     MC_LAUNCH(bonded_kernel, div_up((size_t)n, 128), 128, 0, st, t, slot_of_orig, xyzq, p, force, energy3, want_energy ? 1 : 0);
     *launches += 1;
 }

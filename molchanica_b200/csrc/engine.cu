@@ -1262,6 +1262,53 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
     return MC_OK;
 }
 
+// SnapshotEnergyData.pressure (reference ui/panels/md_viewer.rs:202-256; the barostat's input, ui/panels/md.rs:517-556):
+// P = (2 KE + W) / 3V with the virial W = sum r_ij . f_ij of the nonbonded pairs (one extra pass over the list, on
+// demand only), the scaled 1-4 pairs, the bonded terms and, with SPME, the reciprocal sum and its excluded-pair
+// correction (accumulated next to the energies of the last force evaluation).  bar = kcal/mol/A^3 x 69476.95.
+extern "C" int mc_get_pressure(mc_ctx *c, double *pressure_bar, double *virial) {
+    if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, c->periodic, "mc_get_pressure: needs a periodic box");
+    MC_REQUIRE(c, !c->comm_active, "mc_get_pressure: not available on a decomposed handle yet");
+    MC_REQUIRE(c, c->n_waters == 0 && c->n_hclusters == 0,
+               "mc_get_pressure: the virial of the constraint forces (rigid water, bonds to hydrogen) is not implemented");
+    int rc = ensure_ready(c, "mc_get_pressure");
+    if (rc != MC_OK) return rc;
+    if (!c->forces_valid || !c->forces_have_energy) {
+        if ((rc = engine_launch_forces(c, true)) != MC_OK) return rc;
+    }
+    MC_CUDA(c, c->red_partial.ensure((size_t)energy_partial_elems()));
+    MC_CUDA(c, c->red_out.ensure(4));
+    launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + c->row0, c->vel[c->cur].p + c->row0, c->red_partial.p, c->red_out.p, c->st,
+                         &c->launches);
+    const int coul = c->coul_disabled ? MC_COULOMB_NONE : c->coul_mode;
+    launch_virial((int)c->n_rows_sorted(), (int)c->row0, c->xyzq[c->cur].p, c->type[c->cur].p, c->orig[c->cur].p, c->slot_of_orig.p,
+                  c->nbr_start.p, c->nbr_count.p, c->nbr_list.p, c->have_p14 ? c->p14_start.p : nullptr, c->have_p14 ? c->p14_idx.p : nullptr,
+                  c->ljtab.p, make_params(c), c->lj_disabled ? 0 : 1, coul, c->scale14_lj, c->scale14_q, c->red_out.p + 3, c->st,
+                  &c->launches);
+    double h[4];
+    MC_CUDA(c, cudaMemcpyAsync(h, c->red_out.p, sizeof(h), cudaMemcpyDeviceToHost, c->st));
+    MC_CUDA(c, cudaStreamSynchronize(c->st));
+    double w = h[3];
+    if (c->n_bonds + c->n_angles + c->n_dihedrals > 0) {
+        double hb[4];
+        MC_CUDA(c, cudaMemcpy(hb, c->bonded_e.p, sizeof(hb), cudaMemcpyDeviceToHost));
+        w += hb[3];
+    }
+    if (c->pme.planned && coul == MC_COULOMB_ERFC) {
+        double hp[4];
+        MC_CUDA(c, cudaMemcpy(hp, c->pme.energy, sizeof(hp), cudaMemcpyDeviceToHost));
+        w += hp[2] + (c->have_excl ? hp[3] : 0.0);  // the self term does not depend on the volume
+    }
+    const double vol = (double)c->ext[0] * (double)c->ext[1] * (double)c->ext[2];
+    const double ke = h[1] / (double)MC_ACCEL_CONV;
+    if (virial) *virial = w;
+    if (pressure_bar) *pressure_bar = (2.0 * ke + w) / (3.0 * vol) * 69476.95;
+    return MC_OK;
+}
+
 extern "C" int mc_set_molecule_ids(mc_ctx *c, const uint16_t *mol_id) {
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);

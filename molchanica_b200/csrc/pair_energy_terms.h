@@ -26,3 +26,21 @@ MC_PE_HD float mc_pair_energy(float r2, float sig2, float eps24, float qq, float
     }
     return e;
 }
+
+// r_ij . f_ij of the same pair (the pair's contribution to the virial W = sum_{i<j} r_ij . f_ij, pressure =
+// (2 KE + W) / 3V; SnapshotEnergyData.pressure, reference ui/panels/md_viewer.rs:202-256):
+//   LJ       24 eps (2 (sigma/r)^12 - (sigma/r)^6)
+//   Coulomb  plain: q_i q_j / r;  Ewald real space: q_i q_j (erfc(alpha r)/r + 2 alpha/sqrt(pi) exp(-alpha^2 r^2))
+MC_PE_HD float mc_pair_virial(float r2, float sig2, float eps24, float qq, float rc2_lj, float rc2_q, int lj_on, int coul_mode,
+                              float alpha) {
+    float w = 0.f;
+    if (lj_on && r2 < rc2_lj) {
+        const float s2 = sig2 / r2, s6 = s2 * s2 * s2;
+        w += eps24 * s6 * (2.f * s6 - 1.f);
+    }
+    if (coul_mode != 0 && r2 < rc2_q) {
+        const float r = sqrtf(r2);
+        w += coul_mode == 1 ? qq / r : qq * (erfcf(alpha * r) / r + 1.1283791670955126f * alpha * expf(-alpha * alpha * r2));
+    }
+    return w;
+}

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) pme_convolve_kernel(int K1, int K2, int K
                                                             int want_energy) {
     const int K3h = K3 / 2 + 1;
     const size_t total = (size_t)K1 * K2 * K3h;
-    float e = 0.f;
+    float e = 0.f, w = 0.f;
     const float inv_ext[3] = {inv_e0, inv_e1, inv_e2};
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int i3 = (int)(idx % K3h);
@@ -111,7 +111,9 @@ __global__ void __launch_bounds__(256) pme_convolve_kernel(int K1, int K2, int K
         const float bc = mc_pme_influence(i1, i2, i3, K1, K2, K3, inv_ext, inv_vol_pi, pi2_over_alpha2, bm1[i1], bm2[i2], bm3[i3]);
         float2 v = cgrid[idx];
         const float mult = (i3 == 0 || (K3 % 2 == 0 && i3 == K3 / 2)) ? 1.f : 2.f;
-        e += 0.5f * mult * bc * (v.x * v.x + v.y * v.y);
+        const float em = 0.5f * mult * bc * (v.x * v.x + v.y * v.y);
+        e += em;
+        if (want_energy) w += em * (1.f - 2.f * pi2_over_alpha2 * mc_pme_msq(i1, i2, i3, K1, K2, K3, inv_ext));
         v.x *= bc; v.y *= bc;
         cgrid[idx] = v;
     }
@@ -119,6 +121,9 @@ __global__ void __launch_bounds__(256) pme_convolve_kernel(int K1, int K2, int K
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) e += __shfl_xor_sync(MC_FULL_MASK, e, d);
         if ((threadIdx.x & 31) == 0 && e != 0.f) atomicAdd(energy, (double)e);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(MC_FULL_MASK, w, d);
+        if ((threadIdx.x & 31) == 0 && w != 0.f) atomicAdd(energy + 2, (double)w);  // energy[2]: reciprocal-space virial
     }
 }
 
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(128) pme_excl_kernel(int n, const float4 *__re
                                                         const int32_t *__restrict__ excl_idx, const NbParams p,
                                                         float4 *__restrict__ force, double *__restrict__ energy, int want_energy) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    float e = 0.f;
+    float e = 0.f, w = 0.f;
     if (k < n) {
         const int oi = orig[k];
         const int e0 = excl_start[oi], e1 = excl_start[oi + 1];
@@ -181,6 +186,7 @@ __global__ void __launch_bounds__(128) pme_excl_kernel(int n, const float4 *__re
                     for (int a = 0; a < 3; ++a) d[a] -= rintf(d[a] * p.inv_ext[a]) * p.ext[a];
                 }
                 e += 0.5f * mc_pme_excl_term(d, xi.w * xj.w, p.alpha, f);
+                w += 0.5f * (d[0] * f[0] + d[1] * f[1] + d[2] * f[2]);
                 fx += f[0]; fy += f[1]; fz += f[2];
             }
             float4 f4 = force[k];
@@ -192,6 +198,9 @@ __global__ void __launch_bounds__(128) pme_excl_kernel(int n, const float4 *__re
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) e += __shfl_xor_sync(MC_FULL_MASK, e, d);
         if ((threadIdx.x & 31) == 0 && e != 0.f) atomicAdd(energy, (double)e);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(MC_FULL_MASK, w, d);
+        if ((threadIdx.x & 31) == 0 && w != 0.f) atomicAdd(energy + 2, (double)w);  // (s->energy + 1) + 2: virial of the correction
     }
 }
 
@@ -217,7 +226,7 @@ int pme_configure(PmeState *s, int k1, int k2, int k3, cudaStream_t st, const ch
     if (!api.ok) { *msg = api.err.c_str(); return MC_E_CUDA; }
     const size_t nreal = (size_t)k1 * k2 * k3, ncplx = (size_t)k1 * k2 * (k3 / 2 + 1);
     if (cudaMalloc(&s->grid, nreal * sizeof(float)) != cudaSuccess || cudaMalloc(&s->cgrid, ncplx * sizeof(float2)) != cudaSuccess ||
-        cudaMalloc(&s->energy, 2 * sizeof(double)) != cudaSuccess) {
+        cudaMalloc(&s->energy, 4 * sizeof(double)) != cudaSuccess) {
         pme_release(s);
         *msg = "PME grid allocation failed";
         return MC_E_CUDA;
@@ -256,7 +265,7 @@ int pme_launch(PmeState *s, int n, const float4 *xyzq, const float lo[3], const 
     }
     const size_t nreal = (size_t)s->K[0] * s->K[1] * s->K[2];
     cudaMemsetAsync(s->grid, 0, nreal * sizeof(float), st);
-    if (want_energy) cudaMemsetAsync(s->energy, 0, 2 * sizeof(double), st);
+    if (want_energy) cudaMemsetAsync(s->energy, 0, 4 * sizeof(double), st);
     MC_LAUNCH(pme_spread_kernel, div_up((size_t)n, 128), 128, 0, st, n, xyzq, g, s->grid);
     CufftApi &api = cufft_api();
     if (api.ExecR2C(s->plan_r2c, s->grid, s->cgrid) != 0) { *msg = "cufftExecR2C failed"; return MC_E_CUDA; }

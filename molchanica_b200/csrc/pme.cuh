@@ -9,7 +9,7 @@ struct PmeState {
     float *grid = nullptr;        // K1 x K2 x K3 real charge grid / convolved potential
     float2 *cgrid = nullptr;      // K1 x K2 x (K3/2+1)
     float *bmod[3] = {nullptr, nullptr, nullptr};
-    double *energy = nullptr;     // device: {E_recip, E_exclusion_correction}
+    double *energy = nullptr;     // device: {E_recip, E_exclusion_correction, W_recip, W_exclusion_correction} (W: virial)
     double self_q2 = 0.0;         // sum q_i^2 (host)
 };
 

@@ -63,6 +63,14 @@ MC_PME_HD float mc_pme_influence(int i1, int i2, int i3, int K1, int K2, int K3,
     return expf(-pi2_over_alpha2 * msq) * inv_vol_pi / (msq * bm1 * bm2 * bm3);
 }
 
+// |m|^2 of the same reciprocal vector (for the virial: W_rec = sum_m E(m) (1 - 2 pi^2 m^2 / alpha^2), the trace of the
+// tensor of Essmann et al. eq. 2.7 = -dE_rec/d(lambda) under a uniform scaling of box and positions)
+MC_PME_HD float mc_pme_msq(int i1, int i2, int i3, int K1, int K2, int K3, const float inv_ext[3]) {
+    const int m1 = i1 > K1 / 2 ? i1 - K1 : i1, m2 = i2 > K2 / 2 ? i2 - K2 : i2, m3 = i3 > K3 / 2 ? i3 - K3 : i3;
+    const float h1 = (float)m1 * inv_ext[0], h2 = (float)m2 * inv_ext[1], h3 = (float)m3 * inv_ext[2];
+    return h1 * h1 + h2 * h2 + h3 * h3;
+}
+
 // Correction for one excluded (or 1-4) pair: the reciprocal sum contains the full erf(alpha r)/r interaction of
 // every pair; excluded pairs must not have it.  d = r_i - r_j.  Returns the energy -qq erf(ar)/r and writes the
 // force on i.

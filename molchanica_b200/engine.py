@@ -118,6 +118,12 @@ class MdEngine:
         self._chk(self._L.mc_get_energy_between_mols(self._h, C.byref(out)))
         return float(out.value)
 
+    def pressure(self):
+        """mc_get_pressure: (pressure in bar, virial in kcal/mol)."""
+        p, w = C.c_double(0.0), C.c_double(0.0)
+        self._chk(self._L.mc_get_pressure(self._h, C.byref(p), C.byref(w)))
+        return p.value, w.value
+
     def set_hbond_constraints(self, clusters, lengths):
         """clusters (m, 4): heavy atom + up to three hydrogens (-1 = unused); lengths (m, 3)."""
         if clusters is None or len(clusters) == 0:

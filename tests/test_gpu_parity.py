@@ -241,6 +241,90 @@ def test_pipelined_external_forces_are_invisible_through_the_abi(steps_per_call,
         assert ok, (worst, scale)
 
 
+def _pair_virial64(w, nbr, coul_mode):
+    """fp64 virial sum_{i<j} r_ij . f_ij of the listed pairs inside the cutoffs, written out in numpy independently of the
+    device code: LJ 24 eps (2 s^12 - s^6); Coulomb qq/r (plain) or qq (erfc(ar)/r + 2a/sqrt(pi) exp(-a^2 r^2)) (Ewald real space)."""
+    from scipy.special import erfc
+    start, idx = nbr
+    x = np.asarray(w["xyzq"], np.float64)
+    ext = np.asarray(w["box_ext"], np.float64)
+    i = np.repeat(np.arange(len(x)), np.diff(start))
+    d = x[i, :3] - x[idx, :3]
+    if w["periodic"]:
+        d -= ext * np.rint(d / ext)
+    r2 = (d * d).sum(1)
+    tab = np.asarray(w["ljtab"], np.float64)
+    t = np.asarray(w["type"])
+    sig, eps = tab[t[i], t[idx], 0], tab[t[i], t[idx], 1]
+    s6 = (sig * sig / r2) ** 3
+    wl = np.where(r2 < float(np.float32(w["rc_lj"])) ** 2, 24.0 * eps * s6 * (2.0 * s6 - 1.0), 0.0)
+    qq = x[i, 3] * x[idx, 3]
+    r = np.sqrt(r2)
+    a = float(w.get("alpha", 0.35))
+    wq = qq / r if coul_mode == 1 else qq * (erfc(a * r) / r + 2.0 * a / np.sqrt(np.pi) * np.exp(-a * a * r2))
+    wq = np.where((r2 < float(np.float32(w["rc_q"])) ** 2) & (coul_mode != 0), wq, 0.0)
+    return 0.5 * float(wl.sum() + wq.sum())
+
+
+def test_pressure_of_an_lj_fluid(Engine, oracle):
+    """mc_get_pressure (SnapshotEnergyData.pressure): virial of the listed pairs against the fp64 sum, P = (2 KE + W) / 3V."""
+    w = W.lj_fluid(m=12)
+    e = Engine.from_workload(w)
+    e.step(w["dt"], 20)                                 # off the lattice
+    x, v = e.positions(), e.velocities()
+    p_bar, vir = e.pressure()
+    e.close()
+    ws = dict(w, xyzq=x)
+    w64 = _pair_virial64(ws, oracle.neighbors(ws), 0)
+    assert abs(vir - w64) < 2e-5 * abs(w64), (vir, w64)
+    ke = 0.5 * float(((v[:, :3].astype(np.float64) ** 2).sum(1) / v[:, 3]).sum()) / 418.4
+    vol = float(np.prod(np.asarray(w["box_ext"], np.float64)))
+    assert abs(p_bar - (2 * ke + w64) / (3 * vol) * 69476.95) < 2e-5 * (abs(p_bar) + 2 * ke / (3 * vol) * 69476.95)
+    # sanity of the magnitude: liquid argon near its triple point sits within a few hundred bar of zero
+    assert abs(p_bar) < 2000.0
+
+
+@pytest.mark.parametrize("coul_mode", [1, 2])
+def test_pressure_with_charges_bonds_and_exclusions(coul_mode, Engine, oracle):
+    """Flexible water (harmonic O-H / H-H bonds, intramolecular pairs excluded): pair virial (LJ + plain or Ewald real-space
+    Coulomb) + bonded virial; the bonded part against -dU/d(lambda) of the oracle's bonded energy under a uniform scaling."""
+    w = dict(W.water_box_c1(), coul_mode=coul_mode, alpha=0.35)
+    e = Engine.from_workload(w)
+    e.set_bonded(w["bonds"], w["bond_kr0"])
+    e.step(0.0005, 10)
+    x = e.positions()
+    _, vir = e.pressure()
+    e.close()
+    ws = dict(w, xyzq=x)
+    w_pair = _pair_virial64(ws, oracle.neighbors(ws), coul_mode)
+
+    def u(lam):
+        xs = np.array(x, np.float64)
+        xs[:, :3] *= lam
+        return float(np.sum(oracle.bonded(dict(ws, xyzq=xs.astype(np.float32), box_ext=np.asarray(w["box_ext"], np.float64) * lam))[1]))
+    h = 1e-3
+    w_bond = -(u(1 + h) - u(1 - h)) / (2 * h)
+    assert abs(w_bond) > 1.0
+    scale = abs(w_pair) + abs(w_bond)
+    assert abs(vir - (w_pair + w_bond)) < 5e-4 * scale, (vir, w_pair, w_bond)
+
+
+def test_pressure_refuses_what_it_cannot_do(Engine):
+    from molchanica_b200.engine import McError
+    w = W.globule(200, seed=3)                          # vacuum: no volume
+    e = Engine.from_workload(w)
+    with pytest.raises(McError, match="periodic"):
+        e.pressure()
+    e.close()
+    w = W.water_box_c1()
+    e = Engine.from_workload(w)
+    n = len(w["xyzq"])
+    e.set_rigid_waters(np.arange(n, dtype=np.int32).reshape(-1, 3), 0.9572, 1.5139)
+    with pytest.raises(McError, match="constraint"):
+        e.pressure()
+    e.close()
+
+
 def test_nve_energy_and_momentum_on_lj_fluid(Engine):
     w = W.lj_fluid(m=16)
     e = Engine.from_workload(w)

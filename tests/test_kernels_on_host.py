@@ -61,7 +61,7 @@ def test_bonded_kernel(periodic, K, oracle):
     x_sorted = np.ascontiguousarray(w["xyzq"][orig])
     force = np.zeros((n, 4), np.float32)
     force[:, :3] = 0.25                                      # the kernel ADDS to what the pair kernel left
-    e3 = np.zeros(3, np.float64)
+    e3 = np.zeros(4, np.float64)   # bond, angle, dihedral energies + virial
     ext = np.ascontiguousarray(w["box_ext"], np.float32)
     K.host_bonded(len(w["bonds"]), _p(np.ascontiguousarray(w["bonds"], np.int32)), _p(np.ascontiguousarray(w["bond_kr0"], np.float32)),
                   len(w["angles"]), _p(_pad4(w["angles"], np.int32)), _p(np.ascontiguousarray(w["angle_kt0"], np.float32)),
@@ -70,7 +70,18 @@ def test_bonded_kernel(periodic, K, oracle):
     f64, e64 = oracle.bonded(w)
     got = force[so, :3].astype(np.float64) - 0.25             # back in the caller's order
     assert np.abs(got - f64).max() < 3e-5 * np.abs(f64).max()
-    assert np.allclose(e3, e64, rtol=3e-5)
+    assert np.allclose(e3[:3], e64, rtol=3e-5)
+    # e3[3], the bonded virial sum_a (r_a - r_ref) . f_a, against -dU/d(lambda) of the oracle's energy under a uniform
+    # scaling of positions and box (only the bonds contribute: angles and dihedrals are scale invariant)
+
+    def u(lam):
+        x = np.array(w["xyzq"], np.float64)
+        x[:, :3] *= lam
+        ws = dict(w, xyzq=x.astype(np.float32), box_ext=np.asarray(w["box_ext"], np.float64) * lam)
+        return float(np.sum(oracle.bonded(ws)[1]))
+    h = 2e-3
+    w_fd = -(u(1 + h) - u(1 - h)) / (2 * h)
+    assert abs(e3[3] - w_fd) < 2e-3 * abs(w_fd), (e3[3], w_fd)
     assert np.all(force[:, 3] == 0)
 
 
@@ -267,7 +278,7 @@ def test_pme_kernels(K):
     assert np.abs(grid - ref_grid).max() < 3e-6 * np.abs(ref_grid).max()
     fq = np.fft.rfftn(grid.astype(np.float64)).astype(np.complex64)
     cg = fq.view(np.float32).reshape(fq.shape + (2,)).copy()
-    e = np.zeros(2, np.float64)
+    e = np.zeros(4, np.float64)   # energy, -, virial, -
     K.host_pme_convolve(_p(Kd), _p(cg), _p(ext), C.c_float(alpha), _p(e))
     bc = P.influence(tuple(Kd), ext, alpha)
     want = fq.astype(np.complex128) * bc
@@ -287,7 +298,7 @@ def test_pme_kernels(K):
     so, orig = _shuffle(m, 9)
     xs = np.ascontiguousarray(w["xyzq"][orig])
     fx = np.zeros((m, 4), np.float32)
-    ee = np.zeros(2, np.float64)
+    ee = np.zeros(4, np.float64)
     es, ei = np.ascontiguousarray(w["excl_start"], np.int32), np.ascontiguousarray(w["excl_idx"], np.int32)
     wext = np.ascontiguousarray(w["box_ext"], np.float32)
     K.host_pme_excl(m, _p(xs), _p(orig), _p(so), _p(es), _p(ei), _p(wext), 1, C.c_float(alpha), _p(fx), _p(ee))
