@@ -234,7 +234,8 @@ int mc_get_stats(mc_ctx *ctx, mc_stats *out);
 /* SnapshotEnergyData.pressure (reference ui/panels/md_viewer.rs:202-256): P = (2 KE + W) / 3V in bar and the virial
  * W = sum r_ij . f_ij in kcal/mol over nonbonded pairs inside the cutoffs, scaled 1-4 pairs, bonded terms and the SPME
  * reciprocal sum with its excluded-pair correction.  One extra pass over the neighbour list, on demand only.
- * Periodic, single-GPU handles without constraints (the constraint virial is not implemented: MC_E_INVALID).
+ * Periodic, single-GPU handles.  With rigid waters / constrained bonds the virial of the constraint forces of the LAST
+ * step is included (mass x constraint displacement / dt^2 on the old positions), so at least one step must have been taken.
  * Either output may be NULL. */
 int mc_get_pressure(mc_ctx *ctx, double *pressure_bar, double *virial);
 

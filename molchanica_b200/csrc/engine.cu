@@ -236,6 +236,7 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
     cudaSetDevice(c->device);
     c->n_global = n;
     c->tail_pending = false;  // a new system: nothing of the old one is left to finish
+    c->cons_virial_valid = false;
     c->list_valid = false;
     c->forces_valid = false;
     c->have_excl = false;
@@ -936,12 +937,18 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
             }
             tr.stop();
         }
+        if (c->n_waters > 0 || c->n_hclusters > 0) {
+            // virial of this step's constraint forces (mc_get_pressure): one fp64 atomic per warp inside the kernels
+            MC_CUDA(c, c->cons_virial.ensure(1));
+            MC_CUDA(c, cudaMemsetAsync(c->cons_virial.p, 0, sizeof(double), st));
+            c->cons_virial_valid = true;
+        }
         if (c->n_waters > 0)
             launch_settle(c->n_waters, c->waters.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vel[c->cur].p, c->water_m_o,
-                          c->water_m_h, c->water_d_oh, c->water_d_hh, make_params(c), dt, st, &c->launches);
+                          c->water_m_h, c->water_d_oh, c->water_d_hh, make_params(c), dt, c->cons_virial.p, st, &c->launches);
         if (c->n_hclusters > 0)
             launch_shake_h(c->n_hclusters, c->hclusters.p, c->hdist.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vel[c->cur].p,
-                           make_params(c), dt, c->shake_tol, c->shake_fail.p, st, &c->launches);
+                           make_params(c), dt, c->shake_tol, c->shake_fail.p, c->cons_virial.p, st, &c->launches);
         if (c->n_vsites > 0)
             launch_vsite_construct(c->n_vsites, c->vsites.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vsite_a, c->vsite_b,
                                    make_params(c), st, &c->launches);
@@ -1272,8 +1279,9 @@ extern "C" int mc_get_pressure(mc_ctx *c, double *pressure_bar, double *virial) 
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->periodic, "mc_get_pressure: needs a periodic box");
     MC_REQUIRE(c, !c->comm_active, "mc_get_pressure: not available on a decomposed handle yet");
-    MC_REQUIRE(c, c->n_waters == 0 && c->n_hclusters == 0,
-               "mc_get_pressure: the virial of the constraint forces (rigid water, bonds to hydrogen) is not implemented");
+    const bool constrained = c->n_waters > 0 || c->n_hclusters > 0;
+    MC_REQUIRE(c, !constrained || c->cons_virial_valid,
+               "mc_get_pressure: the virial of the constraint forces is that of the last step; take a step first");
     int rc = ensure_ready(c, "mc_get_pressure");
     if (rc != MC_OK) return rc;
     if (!c->forces_valid || !c->forces_have_energy) {
@@ -1301,6 +1309,12 @@ extern "C" int mc_get_pressure(mc_ctx *c, double *pressure_bar, double *virial) 
         double hp[4];
         MC_CUDA(c, cudaMemcpy(hp, c->pme.energy, sizeof(hp), cudaMemcpyDeviceToHost));
         w += hp[2] + (c->have_excl ? hp[3] : 0.0);  // the self term does not depend on the volume
+    }
+    if (constrained) {
+        // constraint forces of the last step (SETTLE / SHAKE displacement x mass / dt^2 on the old positions)
+        double hc = 0.0;
+        MC_CUDA(c, cudaMemcpy(&hc, c->cons_virial.p, sizeof(hc), cudaMemcpyDeviceToHost));
+        w += hc;
     }
     const double vol = (double)c->ext[0] * (double)c->ext[1] * (double)c->ext[2];
     const double ke = h[1] / (double)MC_ACCEL_CONV;

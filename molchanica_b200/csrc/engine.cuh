@@ -117,6 +117,8 @@ struct mc_ctx {
     DevBuf<float2> bond_kr0, angle_kt0;
     DevBuf<int4> angles, dihedrals;
     DevBuf<float4> dihedral_prm;
+    DevBuf<double> cons_virial;   // virial of the constraint forces of the last step (settle.cu)
+    bool cons_virial_valid = false;
     DevBuf<double> bonded_e;   // {E_bond, E_angle, E_dihedral} of the last evaluation that asked for energies
     DevBuf<float4> min_x, min_v;   // energy minimiser: positions / velocities saved in original order
     bool have_mols = false;    // molecule ids for energy_potential_between_mols (group_energy.cu)
@@ -202,7 +204,7 @@ struct mc_ctx {
         d_rec_meta.release(); d_lig_meta.release(); d_rec_s.release(); d_lig_s.release(); d_keep.release();
         for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_ids[b].release(); }
         bonds.release(); bond_kr0.release(); angle_kt0.release(); angles.release(); dihedrals.release(); dihedral_prm.release();
-        bonded_e.release(); waters.release(); vsites.release(); csvr_lambda.release();
+        bonded_e.release(); cons_virial.release(); waters.release(); vsites.release(); csvr_lambda.release();
         hclusters.release(); hdist.release(); shake_fail.release(); mol_of_orig.release(); min_x.release(); min_v.release();
     }
 

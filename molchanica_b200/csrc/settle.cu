@@ -14,11 +14,18 @@
 
 namespace {
 
-__global__ void __launch_bounds__(128) settle_kernel(int n_w, const int4 *__restrict__ waters, const int *__restrict__ slot_of_orig,
-                                                      float4 *__restrict__ xyzq, float4 *__restrict__ vel, const SettleParams sp,
-                                                      const NbParams p, float dt) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_w) return;
+// Adds a thread's share of the constraint virial to *virial (one fp64 atomic per warp).  The constraint force that
+// moved atom i by delta_i within this step is m_i delta_i / dt^2 (kick-drift form); its virial is taken with the OLD
+// positions relative to the molecule's first atom (the constraint forces of a molecule sum to zero), in kcal/mol.
+__device__ __forceinline__ void add_constraint_virial(float wc, double *__restrict__ virial) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) wc += __shfl_xor_sync(MC_FULL_MASK, wc, d);
+    if ((threadIdx.x & 31) == 0 && wc != 0.f) atomicAdd(virial, (double)wc);
+}
+
+__device__ __forceinline__ float settle_one(int w, const int4 *__restrict__ waters, const int *__restrict__ slot_of_orig,
+                                            float4 *__restrict__ xyzq, float4 *__restrict__ vel, const SettleParams &sp,
+                                            const NbParams &p, float dt) {
     const int4 ids = waters[w];
     const int so = slot_of_orig[ids.x], s1 = slot_of_orig[ids.y], s2 = slot_of_orig[ids.z];
     float4 xo = xyzq[so], x1 = xyzq[s1], x2 = xyzq[s2];
@@ -53,17 +60,26 @@ __global__ void __launch_bounds__(128) settle_kernel(int n_w, const int4 *__rest
     v2.x += dc_[0] * inv_dt; v2.y += dc_[1] * inv_dt; v2.z += dc_[2] * inv_dt;
     xyzq[so] = xo; xyzq[s1] = x1; xyzq[s2] = x2;
     vel[so] = vo; vel[s1] = v1; vel[s2] = v2;
+    // oxygen: old relative position 0, no contribution
+    return sp.m_h * (db_[0] * b0[0] + db_[1] * b0[1] + db_[2] * b0[2] + dc_[0] * c0[0] + dc_[1] * c0[1] + dc_[2] * c0[2]) * inv_dt * inv_dt *
+           (1.f / (float)MC_ACCEL_CONV);
+}
+
+__global__ void __launch_bounds__(128) settle_kernel(int n_w, const int4 *__restrict__ waters, const int *__restrict__ slot_of_orig,
+                                                      float4 *__restrict__ xyzq, float4 *__restrict__ vel, const SettleParams sp,
+                                                      const NbParams p, float dt, double *__restrict__ virial) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const float wc = w < n_w ? settle_one(w, waters, slot_of_orig, xyzq, vel, sp, p, dt) : 0.f;
+    if (virial) add_constraint_virial(wc, virial);
 }
 
 // Bonds to hydrogen (shake_terms.h): one thread per heavy atom with its <= 3 hydrogens, same bookkeeping as settle_kernel
 // (old positions = x' - v dt, everything relative to the heavy atom's old position, velocities corrected by the
 // position change / dt).  clusters: (heavy, h1, h2, h3) original ids, -1 = no such hydrogen; dist: 3 lengths per cluster.
-__global__ void __launch_bounds__(128) shake_h_kernel(int n_c, const int4 *__restrict__ clusters, const float *__restrict__ dist,
-                                                       const int *__restrict__ slot_of_orig, float4 *__restrict__ xyzq,
-                                                       float4 *__restrict__ vel, const NbParams p, float dt, float tol,
-                                                       int *__restrict__ not_converged) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_c) return;
+__device__ __forceinline__ float shake_h_one(int c, const int4 *__restrict__ clusters, const float *__restrict__ dist,
+                                             const int *__restrict__ slot_of_orig, float4 *__restrict__ xyzq,
+                                             float4 *__restrict__ vel, const NbParams &p, float dt, float tol,
+                                             int *__restrict__ not_converged) {
     const int4 ids = clusters[c];
     const int hid[3] = {ids.y, ids.z, ids.w};
     const int s0 = slot_of_orig[ids.x];
@@ -105,12 +121,24 @@ __global__ void __launch_bounds__(128) shake_h_kernel(int n_c, const int4 *__res
         v0.x += da[0] * inv_dt; v0.y += da[1] * inv_dt; v0.z += da[2] * inv_dt;
         xyzq[s0] = x0; vel[s0] = v0;
     }
+    float wc = 0.f;  // heavy atom: old relative position 0
     for (int k = 0; k < nh; ++k) {
         const float dk[3] = {pp[k][0] - q1[k][0], pp[k][1] - q1[k][1], pp[k][2] - q1[k][2]};
         xh[k].x += dk[0]; xh[k].y += dk[1]; xh[k].z += dk[2];
         vh[k].x += dk[0] * inv_dt; vh[k].y += dk[1] * inv_dt; vh[k].z += dk[2] * inv_dt;
         xyzq[sh[k]] = xh[k]; vel[sh[k]] = vh[k];
+        wc += (dk[0] * r0[k][0] + dk[1] * r0[k][1] + dk[2] * r0[k][2]) / inv_m[k];
     }
+    return wc * inv_dt * inv_dt * (1.f / (float)MC_ACCEL_CONV);
+}
+
+__global__ void __launch_bounds__(128) shake_h_kernel(int n_c, const int4 *__restrict__ clusters, const float *__restrict__ dist,
+                                                       const int *__restrict__ slot_of_orig, float4 *__restrict__ xyzq,
+                                                       float4 *__restrict__ vel, const NbParams p, float dt, float tol,
+                                                       int *__restrict__ not_converged, double *__restrict__ virial) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const float wc = c < n_c ? shake_h_one(c, clusters, dist, slot_of_orig, xyzq, vel, p, dt, tol, not_converged) : 0.f;
+    if (virial) add_constraint_virial(wc, virial);
 }
 
 // Virtual sites (vsite_terms.h): one thread per site.  construct: after the parents have their final positions of
@@ -174,17 +202,18 @@ void launch_vsite_spread(int n_v, const int4 *sites, const int *slot_of_orig, fl
 }
 
 void launch_shake_h(int n_c, const int4 *clusters, const float *dist, const int *slot_of_orig, float4 *xyzq, float4 *vel,
-                    const NbParams &p, float dt, float tol, int *not_converged, cudaStream_t st, int64_t *launches) {
+                    const NbParams &p, float dt, float tol, int *not_converged, double *virial, cudaStream_t st, int64_t *launches) {
     if (n_c <= 0) return;
-    MC_LAUNCH(shake_h_kernel, div_up((size_t)n_c, 128), 128, 0, st, n_c, clusters, dist, slot_of_orig, xyzq, vel, p, dt, tol, not_converged);
+    MC_LAUNCH(shake_h_kernel, div_up((size_t)n_c, 128), 128, 0, st, n_c, clusters, dist, slot_of_orig, xyzq, vel, p, dt, tol, not_converged,
+              virial);
     *launches += 1;
 }
 
 void launch_settle(int n_w, const int4 *waters, const int *slot_of_orig, float4 *xyzq, float4 *vel, float m_o, float m_h,
-                   float d_oh, float d_hh, const NbParams &p, float dt, cudaStream_t st, int64_t *launches) {
+                   float d_oh, float d_hh, const NbParams &p, float dt, double *virial, cudaStream_t st, int64_t *launches) {
     if (n_w <= 0) return;
     const SettleParams sp = mc_settle_params(m_o, m_h, d_oh, d_hh);
-    MC_LAUNCH(settle_kernel, div_up((size_t)n_w, 128), 128, 0, st, n_w, waters, slot_of_orig, xyzq, vel, sp, p, dt);
+    MC_LAUNCH(settle_kernel, div_up((size_t)n_w, 128), 128, 0, st, n_w, waters, slot_of_orig, xyzq, vel, sp, p, dt, virial);
     *launches += 1;
 }
 #endif

@@ -39,13 +39,13 @@ void host_bonded(int n_bonds, const int2 *bonds, const float2 *kr0, int n_angles
 void host_settle(int n_w, const int4 *waters, const int *slot_of_orig, float4 *xyzq, float4 *vel, float m_o, float m_h, float d_oh,
                  float d_hh, const float *ext, int periodic, float dt) {
     const SettleParams sp = mc_settle_params(m_o, m_h, d_oh, d_hh);
-    FOR_THREADS(n_w + 3) settle_kernel(n_w, waters, slot_of_orig, xyzq, vel, sp, nb(ext, periodic, 0.f), dt);
+    FOR_THREADS(n_w + 3) settle_kernel(n_w, waters, slot_of_orig, xyzq, vel, sp, nb(ext, periodic, 0.f), dt, nullptr);
 }
 
 int host_shake_h(int n_c, const int4 *clusters, const float *dist, const int *slot_of_orig, float4 *xyzq, float4 *vel, const float *ext,
                  int periodic, float dt, float tol) {
     int bad = 0;
-    FOR_THREADS(n_c + 3) shake_h_kernel(n_c, clusters, dist, slot_of_orig, xyzq, vel, nb(ext, periodic, 0.f), dt, tol, &bad);
+    FOR_THREADS(n_c + 3) shake_h_kernel(n_c, clusters, dist, slot_of_orig, xyzq, vel, nb(ext, periodic, 0.f), dt, tol, &bad, nullptr);
     return bad;
 }
 

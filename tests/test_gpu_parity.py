@@ -309,6 +309,53 @@ def test_pressure_with_charges_bonds_and_exclusions(coul_mode, Engine, oracle):
     assert abs(vir - (w_pair + w_bond)) < 5e-4 * scale, (vir, w_pair, w_bond)
 
 
+def _free_rotors(w, seed):
+    """Random thermal velocities for the atoms of a workload whose interactions are switched off."""
+    rng = np.random.default_rng(seed)
+    v = w["vel"].copy()
+    v[:, :3] = rng.normal(0, 1.0, (len(v), 3)) * np.sqrt(0.0019872041 * 300.0 * 418.4 * v[:, 3:4])
+    return v
+
+
+@pytest.mark.parametrize("kind", ["settle", "shake"])
+def test_constraint_virial_of_free_rigid_rotors(kind, Engine):
+    """Known answer for the constraint part of mc_get_pressure: molecules that do not interact at all.  The only forces are
+    the constraint forces that keep a rotating rigid body together (centripetal: W_c = -2 KE_rot), so 2 KE + W must be
+    twice the kinetic energy of the centres of mass -- the ideal-gas pressure of N molecules, not of 3 N atoms."""
+    w = W.water_box_c1()
+    n = len(w["xyzq"])
+    if kind == "shake":                                   # rigid O-H diatomics: drop the second hydrogen
+        keep = np.arange(n).reshape(-1, 3)[:, :2].ravel()
+        w = dict(w, xyzq=w["xyzq"][keep], vel=w["vel"][keep], type=w["type"][keep], excl_start=None, excl_idx=None)
+        n, per = len(keep), 2
+    else:
+        w = dict(w, excl_start=None, excl_idx=None)
+        per = 3
+    w["vel"] = _free_rotors(w, 12)
+    dt = 0.00025
+    e = Engine.from_workload(w)
+    e.set_overrides(lj_disabled=True, coulomb_disabled=True)
+    ids = np.arange(n, dtype=np.int32).reshape(-1, per)
+    if kind == "settle":
+        e.set_rigid_waters(ids, 0.9572, 1.5139)
+    else:
+        e.set_hbond_constraints(np.concatenate([ids, np.full((len(ids), 2), -1, np.int32)], 1),
+                                np.tile(np.array([[0.9572, 1.0, 1.0]], np.float32), (len(ids), 1)))
+    e.step(dt, 40)                                        # the first steps project the random velocities onto the rigid motion
+    v = e.velocities().astype(np.float64)
+    p_bar, vir = e.pressure()
+    e.close()
+    m = 1.0 / v[:, 3]
+    ke = 0.5 * (m * (v[:, :3] ** 2).sum(1)).sum() / 418.4
+    mm = m.reshape(-1, per)
+    vcom = (mm[:, :, None] * v[:, :3].reshape(-1, per, 3)).sum(1) / mm.sum(1)[:, None]
+    ke_com = 0.5 * (mm.sum(1) * (vcom ** 2).sum(1)).sum() / 418.4
+    assert ke_com < 0.75 * ke                             # there is rotational energy to take out
+    assert abs((2 * ke + vir) - 2 * ke_com) < 0.01 * 2 * ke, (ke, ke_com, vir)
+    vol = float(np.prod(np.asarray(w["box_ext"], np.float64)))
+    assert abs(p_bar - (2 * ke + vir) / (3 * vol) * 69476.95) < 1e-6 * abs(p_bar)
+
+
 def test_pressure_refuses_what_it_cannot_do(Engine):
     from molchanica_b200.engine import McError
     w = W.globule(200, seed=3)                          # vacuum: no volume
@@ -320,7 +367,7 @@ def test_pressure_refuses_what_it_cannot_do(Engine):
     e = Engine.from_workload(w)
     n = len(w["xyzq"])
     e.set_rigid_waters(np.arange(n, dtype=np.int32).reshape(-1, 3), 0.9572, 1.5139)
-    with pytest.raises(McError, match="constraint"):
+    with pytest.raises(McError, match="take a step first"):   # the constraint virial is that of the last step
         e.pressure()
     e.close()
 
