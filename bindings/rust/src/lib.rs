@@ -19,6 +19,9 @@ pub const MC_THERMOSTAT_NONE: c_int = 0;
 pub const MC_THERMOSTAT_LANGEVIN: c_int = 1;
 pub const MC_THERMOSTAT_CSVR: c_int = 2;
 pub const MC_FLAG_STATIC: u8 = 1;
+pub const MC_BAROSTAT_NONE: c_int = 0;
+pub const MC_BAROSTAT_BERENDSEN: c_int = 1;
+pub const MC_BAROSTAT_CRESCALE: c_int = 2;
 
 #[repr(C)]
 pub struct McCtx {
@@ -108,6 +111,8 @@ extern "C" {
     pub fn mc_get_energy(ctx: *mut McCtx, out: *mut McEnergy) -> c_int;
     pub fn mc_get_stats(ctx: *mut McCtx, out: *mut McStats) -> c_int;
     pub fn mc_get_pressure(ctx: *mut McCtx, pressure_bar: *mut f64, virial: *mut f64) -> c_int;
+    pub fn mc_set_barostat(ctx: *mut McCtx, kind: c_int, pressure_bar: f32, tau_ps: f32, compressibility_per_bar: f32, every_n_steps: c_int, seed: u64) -> c_int;
+    pub fn mc_get_box(ctx: *mut McCtx, lo: *mut f32, hi: *mut f32) -> c_int;
     pub fn mc_set_molecule_ids(ctx: *mut McCtx, mol_id: *const u16) -> c_int;
     pub fn mc_get_energy_between_mols(ctx: *mut McCtx, out: *mut f64) -> c_int;
     pub fn mc_snapshot_begin(ctx: *mut McCtx, out_positions: *mut McFloat4, out_ids: *mut i32, n_out: *mut i64) -> c_int;

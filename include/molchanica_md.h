@@ -239,6 +239,21 @@ int mc_get_stats(mc_ctx *ctx, mc_stats *out);
  * Either output may be NULL. */
 int mc_get_pressure(mc_ctx *ctx, double *pressure_bar, double *virial);
 
+/* MdConfig.barostat_cfg = BarostatCfg{pressure_target [bar], tau [ps]} (reference ui/panels/md.rs:517-556,
+ * properties/crystal.rs:312, water_sol.rs:146).  Every every_n_steps steps the instantaneous pressure is measured and
+ * box + coordinates are scaled about the origin: MC_BAROSTAT_BERENDSEN (weak coupling) or MC_BAROSTAT_CRESCALE
+ * (stochastic cell rescaling, Bernetti & Bussi 2020, samples NPT together with a canonical thermostat -- call
+ * mc_set_thermostat first, its temperature sets the noise; velocities are scaled by 1/mu).  compressibility_per_bar:
+ * isothermal compressibility (water 4.5e-5).  The `dynamics` crate's own barostat algorithm is not in the reference
+ * tree [EXTERNAL]; both kinds relax the box towards pressure_target with time constant tau.  Periodic single-GPU
+ * handles; mc_get_box reports the current box. */
+#define MC_BAROSTAT_NONE 0
+#define MC_BAROSTAT_BERENDSEN 1
+#define MC_BAROSTAT_CRESCALE 2
+int mc_set_barostat(mc_ctx *ctx, int kind, float pressure_bar, float tau_ps, float compressibility_per_bar, int every_n_steps,
+                    uint64_t seed);
+int mc_get_box(mc_ctx *ctx, float lo[3], float hi[3]);
+
 /* SnapshotEnergyData.energy_potential_between_mols (src/md/mod.rs:1242-1245): mol_id[n] assigns every atom to a molecule;
  * mc_get_energy_between_mols sums the nonbonded pair energies (LJ + the Coulomb form in force, within the cutoffs)
  * over the listed pairs whose atoms belong to different molecules.  On demand, not on the step path; excluded

@@ -93,6 +93,8 @@ def lib():
     L.mc_set_molecule_ids.argtypes = [vp, vp]
     L.mc_get_energy_between_mols.argtypes = [vp, C.POINTER(C.c_double)]
     L.mc_get_pressure.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.mc_set_barostat.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_uint64]
+    L.mc_get_box.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.mc_set_hbond_constraints.argtypes = [vp, i64, vp, vp]
     L.mc_set_virtual_sites.argtypes = [vp, i64, vp, f32, f32]
     L.mc_set_thermostat.argtypes = [vp, i32, f32, f32, C.c_uint64]

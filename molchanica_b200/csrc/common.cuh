@@ -37,6 +37,7 @@
 #define MC_SOFTENING_SQ 0.000001f  // reference src/cuda/util.cu:9-10
 #define MC_INV_SQRT_PI 0.5641895835477563f  // util.cu:15-18
 #define MC_KB 0.0019872041         // kcal/mol/K
+#define MC_BAR_PER_KCAL_MOL_A3 69476.95  // 1 kcal/mol/A^3 in bar
 #define MC_FLAG_INTERIOR 0x80u      // engine-internal flag bit: atom sits in a cell whose 27-cell stencil never wraps
 
 // Device-resident description of the cell grid; written by the host (periodic box) or by

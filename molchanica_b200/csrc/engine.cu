@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "csvr_terms.h"
 #include "dock.cuh"
 #include "engine.cuh"
 #include "integrate.cuh"
@@ -840,6 +841,8 @@ static int wait_flag_tag(mc_ctx *c, volatile int *word, int tag) {
     }
 }
 
+static int apply_barostat(mc_ctx *c, float dt);
+
 extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces) {
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);
@@ -855,7 +858,8 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     // upload, runs the open force evaluation meanwhile (it does not depend on the new array), closes the half kick
     // with the PREVIOUS array and only then waits for the upload.  Everything that observes more than positions
     // closes the tail first (engine_flush_tail), so the deferral is invisible through the ABI.
-    const bool defer = c->defer_tail && ext_forces != nullptr && pipelined && n_steps > 0;
+    const bool baro = c->baro_kind != MC_BAROSTAT_NONE && c->periodic && !c->comm_active;
+    const bool defer = c->defer_tail && ext_forces != nullptr && pipelined && n_steps > 0 && !baro;
     struct UploadGuard {  // whatever path leaves this function, the caller's array is no longer being read
         cudaStream_t s = nullptr;
         ~UploadGuard() { if (s) cudaStreamSynchronize(s); }
@@ -1009,7 +1013,13 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         } else if (c->comm_active && !fused_halo && (rc = comm_halo_positions(c)) != MC_OK) {
             return rc;
         }
-        if ((rc = engine_launch_forces(c, false, fused_halo && !rebuild ? &split : nullptr)) != MC_OK) return rc;
+        const bool baro_now = baro && (c->n_steps + 1) % c->baro_every == 0;
+        if ((rc = engine_launch_forces(c, baro_now, fused_halo && !rebuild ? &split : nullptr)) != MC_OK) return rc;
+        if (baro_now) {
+            // pressure of the positions just reached -> scale box and coordinates -> rebuild -> forces of the scaled system
+            if ((rc = apply_barostat(c, dt)) != MC_OK) return rc;
+            skip_prev = true;  // the flag word of this step refers to the reference positions of the old list
+        }
         c->n_steps++;
     }
     if (defer) {
@@ -1273,20 +1283,9 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
 // P = (2 KE + W) / 3V with the virial W = sum r_ij . f_ij of the nonbonded pairs (one extra pass over the list, on
 // demand only), the scaled 1-4 pairs, the bonded terms and, with SPME, the reciprocal sum and its excluded-pair
 // correction (accumulated next to the energies of the last force evaluation).  bar = kcal/mol/A^3 x 69476.95.
-extern "C" int mc_get_pressure(mc_ctx *c, double *pressure_bar, double *virial) {
-    if (!c) return MC_E_INVALID;
-    MC_FLUSH(c);
-    cudaSetDevice(c->device);
-    MC_REQUIRE(c, c->periodic, "mc_get_pressure: needs a periodic box");
-    MC_REQUIRE(c, !c->comm_active, "mc_get_pressure: not available on a decomposed handle yet");
+// forces of the current positions must be valid and evaluated with energies (bonded / SPME virials sit next to them)
+static int compute_pressure(mc_ctx *c, double *pressure_bar, double *virial) {
     const bool constrained = c->n_waters > 0 || c->n_hclusters > 0;
-    MC_REQUIRE(c, !constrained || c->cons_virial_valid,
-               "mc_get_pressure: the virial of the constraint forces is that of the last step; take a step first");
-    int rc = ensure_ready(c, "mc_get_pressure");
-    if (rc != MC_OK) return rc;
-    if (!c->forces_valid || !c->forces_have_energy) {
-        if ((rc = engine_launch_forces(c, true)) != MC_OK) return rc;
-    }
     MC_CUDA(c, c->red_partial.ensure((size_t)energy_partial_elems()));
     MC_CUDA(c, c->red_out.ensure(4));
     launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + c->row0, c->vel[c->cur].p + c->row0, c->red_partial.p, c->red_out.p, c->st,
@@ -1319,7 +1318,84 @@ extern "C" int mc_get_pressure(mc_ctx *c, double *pressure_bar, double *virial) 
     const double vol = (double)c->ext[0] * (double)c->ext[1] * (double)c->ext[2];
     const double ke = h[1] / (double)MC_ACCEL_CONV;
     if (virial) *virial = w;
-    if (pressure_bar) *pressure_bar = (2.0 * ke + w) / (3.0 * vol) * 69476.95;
+    if (pressure_bar) *pressure_bar = (2.0 * ke + w) / (3.0 * vol) * MC_BAR_PER_KCAL_MOL_A3;
+    return MC_OK;
+}
+
+extern "C" int mc_get_pressure(mc_ctx *c, double *pressure_bar, double *virial) {
+    if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
+    cudaSetDevice(c->device);
+    MC_REQUIRE(c, c->periodic, "mc_get_pressure: needs a periodic box");
+    MC_REQUIRE(c, !c->comm_active, "mc_get_pressure: not available on a decomposed handle yet");
+    MC_REQUIRE(c, !(c->n_waters > 0 || c->n_hclusters > 0) || c->cons_virial_valid,
+               "mc_get_pressure: the virial of the constraint forces is that of the last step; take a step first");
+    int rc = ensure_ready(c, "mc_get_pressure");
+    if (rc != MC_OK) return rc;
+    if (!c->forces_valid || !c->forces_have_energy) {
+        if ((rc = engine_launch_forces(c, true)) != MC_OK) return rc;
+    }
+    return compute_pressure(c, pressure_bar, virial);
+}
+
+// Barostat (MdConfig.barostat_cfg = BarostatCfg{pressure_target [bar], tau [ps]}, reference ui/panels/md.rs:517-556,
+// properties/crystal.rs:312): every `every` steps the instantaneous pressure P of the positions just reached is
+// measured and box + coordinates are scaled by mu about the origin.
+//   Berendsen (weak coupling):       mu^3 = 1 - beta (every dt / tau) (P0 - P)
+//   stochastic cell rescaling (Bernetti & Bussi, J. Chem. Phys. 153, 114107 (2020); the canonical companion of CSVR):
+//     d(ln V) = -(beta / tau) (P0 - P) Dt + sqrt(2 kT beta Dt / (V tau)) xi,   mu = exp(d(ln V) / 3),  v <- v / mu
+// beta = isothermal compressibility (1/bar).  The list is rebuilt and the forces re-evaluated on the scaled system.
+static int apply_barostat(mc_ctx *c, float dt) {
+    double p = 0.0;
+    int rc = compute_pressure(c, &p, nullptr);
+    if (rc != MC_OK) return rc;
+    const double Dt = (double)dt * c->baro_every, vol = (double)c->ext[0] * c->ext[1] * c->ext[2];
+    double dlnv = -(double)c->baro_beta * (Dt / (double)c->baro_tau) * ((double)c->baro_p0 - p);
+    double nu = 1.0;
+    if (c->baro_kind == MC_BAROSTAT_CRESCALE) {
+        CsvrRng g{c->baro_seed ^ 0xB4A05747ull, c->baro_draws++, 0};
+        double xi, unused;
+        mc_csvr_normal_pair(g, &xi, &unused);
+        const double kT = MC_KB * (double)c->lgv_temperature;
+        dlnv += std::sqrt(2.0 * kT * MC_BAR_PER_KCAL_MOL_A3 * (double)c->baro_beta * Dt / (vol * (double)c->baro_tau)) * xi;
+    }
+    dlnv = std::max(-0.03, std::min(0.03, dlnv));  // a runaway pressure must not fold the box in one go
+    const double mu = c->baro_kind == MC_BAROSTAT_CRESCALE ? std::exp(dlnv / 3.0) : std::cbrt(1.0 + dlnv);
+    if (c->baro_kind == MC_BAROSTAT_CRESCALE) nu = 1.0 / mu;
+    c->baro_last_p = p;
+    c->baro_last_mu = mu;
+    launch_scale_coords((int)c->n, c->xyzq[c->cur].p, c->xref.p, c->vel[c->cur].p, (float)mu, (float)nu, c->st, &c->launches);
+    for (int a = 0; a < 3; ++a) {
+        c->lo[a] = (float)((double)c->lo[a] * mu);
+        c->ext[a] = (float)((double)c->ext[a] * mu);
+    }
+    c->grid_dirty = true;
+    c->list_valid = false;
+    c->forces_valid = false;
+    if ((rc = engine_build_list(c)) != MC_OK) return rc;
+    return engine_launch_forces(c, false);
+}
+
+extern "C" int mc_set_barostat(mc_ctx *c, int kind, float pressure_bar, float tau_ps, float compressibility_per_bar, int every_n_steps,
+                               uint64_t seed) {
+    if (!c) return MC_E_INVALID;
+    MC_FLUSH(c);
+    MC_REQUIRE(c, kind == MC_BAROSTAT_NONE || kind == MC_BAROSTAT_BERENDSEN || kind == MC_BAROSTAT_CRESCALE, "mc_set_barostat: unknown kind");
+    if (kind != MC_BAROSTAT_NONE) {
+        MC_REQUIRE(c, !c->comm_active, "mc_set_barostat: not available on a decomposed handle yet");
+        MC_REQUIRE(c, tau_ps > 0.f && compressibility_per_bar > 0.f && every_n_steps >= 1, "mc_set_barostat: tau, compressibility and interval must be positive");
+        MC_REQUIRE(c, kind != MC_BAROSTAT_CRESCALE || c->langevin || c->csvr,
+                   "mc_set_barostat: stochastic cell rescaling takes its temperature from the thermostat; call mc_set_thermostat first");
+    }
+    c->baro_kind = kind;
+    c->baro_p0 = pressure_bar; c->baro_tau = tau_ps; c->baro_beta = compressibility_per_bar; c->baro_every = every_n_steps;
+    c->baro_seed = seed; c->baro_draws = 0;
+    return MC_OK;
+}
+
+extern "C" int mc_get_box(mc_ctx *c, float lo[3], float hi[3]) {
+    if (!c || !lo || !hi) return MC_E_INVALID;
+    for (int a = 0; a < 3; ++a) { lo[a] = c->lo[a]; hi[a] = c->lo[a] + c->ext[a]; }
     return MC_OK;
 }
 

@@ -117,6 +117,11 @@ struct mc_ctx {
     DevBuf<float2> bond_kr0, angle_kt0;
     DevBuf<int4> angles, dihedrals;
     DevBuf<float4> dihedral_prm;
+    // barostat (mc_set_barostat): every baro_every steps the box and all coordinates are scaled towards the target pressure
+    int baro_kind = 0, baro_every = 10;
+    float baro_p0 = 1.f, baro_tau = 5.f, baro_beta = 4.5e-5f;
+    uint64_t baro_seed = 0, baro_draws = 0;
+    double baro_last_p = 0.0, baro_last_mu = 1.0;
     DevBuf<double> cons_virial;   // virial of the constraint forces of the last step (settle.cu)
     bool cons_virial_valid = false;
     DevBuf<double> bonded_e;   // {E_bond, E_angle, E_dihedral} of the last evaluation that asked for energies

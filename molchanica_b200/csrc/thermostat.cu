@@ -52,12 +52,35 @@ __global__ void __launch_bounds__(256) zero_velocities_kernel(int n_rows, float4
     vel[i] = v;
 }
 
+// barostat (engine.cu): positions and the displacement reference scaled about the origin by mu, velocities by nu
+// (1 for Berendsen, 1 / mu for stochastic cell rescaling); charges / inverse masses in .w untouched
+__global__ void __launch_bounds__(256) scale_coords_kernel(int n, float4 *__restrict__ xyzq, float4 *__restrict__ xref,
+                                                            float4 *__restrict__ vel, float mu, float nu) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 x = xyzq[i], r = xref[i];
+    x.x *= mu; x.y *= mu; x.z *= mu;
+    r.x *= mu; r.y *= mu; r.z *= mu;
+    xyzq[i] = x; xref[i] = r;
+    if (nu != 1.f) {
+        float4 v = vel[i];
+        v.x *= nu; v.y *= nu; v.z *= nu;
+        vel[i] = v;
+    }
+}
+
 }  // namespace
 
 #ifdef MC_HAVE_LAUNCH  // the stand-ins of tests/cpp/shim/ and shim_mt/ have no launcher; shim_fiber/ has
 void launch_zero_velocities(int n_rows, float4 *vel, cudaStream_t st, int64_t *launches) {
     if (n_rows <= 0) return;
     MC_LAUNCH(zero_velocities_kernel, div_up(n_rows, 256), 256, 0, st, n_rows, vel);
+    *launches += 1;
+}
+
+void launch_scale_coords(int n, float4 *xyzq, float4 *xref, float4 *vel, float mu, float nu, cudaStream_t st, int64_t *launches) {
+    if (n <= 0) return;
+    MC_LAUNCH(scale_coords_kernel, div_up(n, 256), 256, 0, st, n, xyzq, xref, vel, mu, nu);
     *launches += 1;
 }
 

@@ -124,6 +124,16 @@ class MdEngine:
         self._chk(self._L.mc_get_pressure(self._h, C.byref(p), C.byref(w)))
         return p.value, w.value
 
+    def set_barostat(self, kind, pressure_bar=1.0, tau_ps=5.0, compressibility_per_bar=4.5e-5, every=10, seed=0):
+        """mc_set_barostat: kind 0 none, 1 Berendsen, 2 stochastic cell rescaling."""
+        self._chk(self._L.mc_set_barostat(self._h, int(kind), float(pressure_bar), float(tau_ps), float(compressibility_per_bar), int(every),
+                                          int(seed)))
+
+    def box(self):
+        lo, hi = (C.c_float * 3)(), (C.c_float * 3)()
+        self._chk(self._L.mc_get_box(self._h, lo, hi))
+        return np.array(lo[:], np.float32), np.array(hi[:], np.float32)
+
     def set_hbond_constraints(self, clusters, lengths):
         """clusters (m, 4): heavy atom + up to three hydrogens (-1 = unused); lengths (m, 3)."""
         if clusters is None or len(clusters) == 0:
