@@ -189,6 +189,8 @@ int mc_set_overrides(mc_ctx *ctx, int lj_disabled, int coulomb_disabled);
  * "dd_migrate" (decomposed handles; 1 = rebuilds exchange boundary layers with the two neighbour ranks only
  * (default), 0 = all-gather of the whole system), "subcell_sort" (Morton sub-cell code in the sort key),
  * "profile_every" (k: inside mc_step only every k-th step's kernels are bracketed with events),
+ * "zero_com_drift" (k: remove the velocity of the centre of mass of the mobile atoms every k steps, MdConfig.zero_com_drift
+ * of the reference; 0 = never (default)),
  * "defer_tail" (1 (default): a single-GPU mc_step with ext_forces returns after its last drift and finishes that
  * step -- force evaluation, second half kick -- under the upload of the next call's array, or as soon as anything
  * but positions is asked for; results are the same, only the time at which the work is done moves; 0 = finish
@@ -269,6 +271,9 @@ int mc_get_energy_between_mols(mc_ctx *ctx, double *out);
  * may be NULL.  Decomposed handle: the atoms this rank owns, *n_out of them, with their original
  * ids in out_ids (both buffers must hold the rank's capacity, see mc_comm_counts). */
 int mc_snapshot_begin(mc_ctx *ctx, mc_float4 *out_positions, int32_t *out_ids, int64_t *n_out);
+/* The same with velocities ({vx, vy, vz, 1/m}; Snapshot.atom_velocities, src/md/trajectory.rs:160-204).  Velocities are
+ * only final once the step a pipelined mc_step may have left open is closed, so this call finishes it first. */
+int mc_snapshot_begin_pv(mc_ctx *ctx, mc_float4 *out_positions, mc_float4 *out_velocities, int32_t *out_ids, int64_t *n_out);
 int mc_snapshot_wait(mc_ctx *ctx);
 
 /* Verlet list as CSR in original ids, rows ascending.  start: n+1 entries.  Two-call protocol:

@@ -53,7 +53,24 @@ struct MdOverrides {
 
 enum class CoulombMode : int { None = MC_COULOMB_NONE, PlainCutoff = MC_COULOMB_PLAIN, EwaldRealSpace = MC_COULOMB_ERFC };
 
+// dynamics::BarostatCfg{pressure_target, tau} (ui/panels/md.rs:517-556, properties/crystal.rs:312)
+struct BarostatCfg {
+    float pressure_target = 1.0f;        // bar
+    float tau = 5.0f;                    // ps ("5ps is a good default", ui/panels/md.rs:544)
+    float compressibility = 4.5e-5f;     // 1/bar (water)
+    int every_n_steps = 10;
+    bool stochastic = true;              // stochastic cell rescaling (needs a thermostat); false = Berendsen
+};
+
 struct MdConfig {
+    // Integrator::VerletVelocity{thermostat: Some(tau)} + temp_target (properties/crystal.rs:306-311): CSVR with time
+    // constant tau; 0 = no thermostat (NVE)
+    float thermostat_tau = 0.0f;   // ps
+    float temp_target = 300.0f;    // K
+    uint64_t seed = 0;
+    bool zero_com_drift = false;   // properties/crystal.rs:310
+    bool has_barostat = false;     // barostat_cfg: Option<BarostatCfg>
+    BarostatCfg barostat_cfg;
     float coulomb_cutoff = 12.0f;  // A, ui/panels/md.rs:260
     float lj_cutoff = 12.0f;       // A, ui/panels/md.rs:261
     float skin = 2.0f;             // A, Verlet skin
@@ -94,6 +111,7 @@ struct SnapshotEnergyData {  // src/md/mod.rs:1242-1245, ui/panels/md_viewer.rs:
     double energy_potential = 0, energy_potential_nonbonded = 0, energy_potential_bonded = 0;
     double energy_kinetic = 0, temperature = 0;
     double volume = 0, density = 0;  // A^3, g/cm^3 (periodic boxes)
+    double pressure = 0;             // bar (periodic boxes; 0 when it cannot be evaluated yet)
 };
 
 class MdState {
@@ -136,6 +154,14 @@ class MdState {
             md.chk(mc_set_rigid_waters(md.ctx_, (int64_t)sys.rigid_waters.size() / 3, sys.rigid_waters.data(), sys.water_d_oh,
                                        sys.water_d_hh, sys.water_m_o, sys.water_m_h));
         if (sys.pme_grid[0] > 0) md.chk(mc_set_pme(md.ctx_, sys.pme_grid[0], sys.pme_grid[1], sys.pme_grid[2]));
+        if (cfg.thermostat_tau > 0.0f)
+            md.chk(mc_set_thermostat(md.ctx_, MC_THERMOSTAT_CSVR, cfg.temp_target, 1.0f / cfg.thermostat_tau, cfg.seed));
+        if (cfg.zero_com_drift) md.chk(mc_set_option(md.ctx_, "zero_com_drift", 100.0));
+        if (cfg.has_barostat) {
+            const BarostatCfg &b = cfg.barostat_cfg;
+            md.chk(mc_set_barostat(md.ctx_, b.stochastic && cfg.thermostat_tau > 0.0f ? MC_BAROSTAT_CRESCALE : MC_BAROSTAT_BERENDSEN,
+                                   b.pressure_target, b.tau, b.compressibility, b.every_n_steps, cfg.seed));
+        }
         return md;
     }
 
@@ -186,6 +212,8 @@ class MdState {
         s.temperature = e.temperature;
         s.volume = e.volume;
         s.density = e.density;
+        double p = 0.0;
+        if (cell.periodic && mc_get_pressure(ctx_, &p, nullptr) == MC_OK) s.pressure = p;
         return s;
     }
 
@@ -196,7 +224,22 @@ class MdState {
         out.resize(atoms.size());
         chk(mc_snapshot_begin(ctx_, out.data(), nullptr, nullptr));
     }
+    void snapshot_begin(std::vector<mc_float4> &out, std::vector<mc_float4> &out_vel) {  // + Snapshot.atom_velocities
+        out.resize(atoms.size());
+        out_vel.resize(atoms.size());
+        chk(mc_snapshot_begin_pv(ctx_, out.data(), out_vel.data(), nullptr, nullptr));
+    }
     void snapshot_wait() { chk(mc_snapshot_wait(ctx_)); }
+
+    // the box after barostat scaling (md.cell, properties/crystal.rs:633)
+    SimBox current_box() {
+        float lo[3], hi[3];
+        chk(mc_get_box(ctx_, lo, hi));
+        SimBox b = cell;
+        b.bounds_low = {lo[0], lo[1], lo[2]};
+        b.bounds_high = {hi[0], hi[1], hi[2]};
+        return b;
+    }
 
     // Make positions / velocities / forces host-visible on demand (the shrinking-box workflow reads
     // atom.force every chunk, properties/sol_shrinking_box.rs:776-789) -- never per step.

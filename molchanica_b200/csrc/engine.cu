@@ -537,6 +537,9 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         c->halo_fused = value != 0.0;
     } else if (k == "rebuild_every") {
         c->rebuild_every = (int)value;
+    } else if (k == "zero_com_drift") {
+        MC_REQUIRE(c, value >= 0.0 && !c->comm_active, "mc_set_option: zero_com_drift = k >= 0 steps, single-GPU handles");
+        c->com_every = (int)value;
     } else if (k == "defer_tail") {
         c->defer_tail = value != 0.0;
     } else {
@@ -956,6 +959,11 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         if (c->n_vsites > 0)
             launch_vsite_construct(c->n_vsites, c->vsites.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vsite_a, c->vsite_b,
                                    make_params(c), st, &c->launches);
+        if (c->com_every > 0 && !c->comm_active && (c->n_steps + 1) % c->com_every == 0) {
+            MC_CUDA(c, c->com_partial.ensure((size_t)com_partial_elems()));
+            const size_t r0 = (size_t)c->row0;
+            launch_remove_com((int)c->n_rows_sorted(), c->vel[c->cur].p + r0, c->flags[c->cur].p + r0, c->com_partial.p, st, &c->launches);
+        }
         if (c->langevin) {
             const float c1 = std::exp(-c->lgv_gamma * dt);
             const size_t r0 = (size_t)c->row0;
@@ -1181,8 +1189,9 @@ extern "C" int mc_get_forces(mc_ctx *c, mc_float4 *out) {
 // a single GPU; the owned block + its original ids on a decomposed rank), and a second stream moves
 // the staging buffer to the caller's host buffer while the next steps already run.
 
-extern "C" int mc_snapshot_begin(mc_ctx *c, mc_float4 *out_positions, int32_t *out_ids, int64_t *n_out) {
+static int snapshot_begin_impl(mc_ctx *c, mc_float4 *out_positions, mc_float4 *out_velocities, int32_t *out_ids, int64_t *n_out) {
     if (!c || !out_positions) return MC_E_INVALID;
+    if (out_velocities) MC_FLUSH(c);  // velocities are only final once the step mc_step may have left open is closed
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active || out_ids, "mc_snapshot_begin: a decomposed handle returns its owned atoms and needs out_ids");
     if (!c->st_copy) {
@@ -1208,13 +1217,32 @@ extern "C" int mc_snapshot_begin(mc_ctx *c, mc_float4 *out_positions, int32_t *o
     } else {
         launch_gather_to_orig((int)rows, c->xyzq[c->cur].p, c->orig[c->cur].p, c->snap_stage[k].p, c->st, &c->launches);
     }
+    if (out_velocities) {
+        MC_CUDA(c, c->snap_stage_v[k].ensure((size_t)n));
+        if (c->comm_active)
+            MC_CUDA(c, cudaMemcpyAsync(c->snap_stage_v[k].p, c->vel[c->cur].p + c->row0, sizeof(float4) * n, cudaMemcpyDeviceToDevice, c->st));
+        else
+            launch_gather_to_orig((int)rows, c->vel[c->cur].p, c->orig[c->cur].p, c->snap_stage_v[k].p, c->st, &c->launches);
+    }
     MC_CUDA(c, cudaEventRecord(c->ev_snap_staged[k], c->st));
     MC_CUDA(c, cudaStreamWaitEvent(c->st_copy, c->ev_snap_staged[k], 0));
     MC_CUDA(c, cudaMemcpyAsync(out_positions, c->snap_stage[k].p, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->st_copy));
+    if (out_velocities)
+        MC_CUDA(c, cudaMemcpyAsync(out_velocities, c->snap_stage_v[k].p, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->st_copy));
     if (c->comm_active) MC_CUDA(c, cudaMemcpyAsync(out_ids, c->snap_ids[k].p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->st_copy));
     MC_CUDA(c, cudaEventRecord(c->ev_snap_done[k], c->st_copy));
     c->snap_pending[k] = true;
     return MC_OK;
+}
+
+extern "C" int mc_snapshot_begin(mc_ctx *c, mc_float4 *out_positions, int32_t *out_ids, int64_t *n_out) {
+    return snapshot_begin_impl(c, out_positions, nullptr, out_ids, n_out);
+}
+
+// Snapshot{atom_posits, atom_velocities, ..} (reference src/md/trajectory.rs:160-204): positions AND velocities
+extern "C" int mc_snapshot_begin_pv(mc_ctx *c, mc_float4 *out_positions, mc_float4 *out_velocities, int32_t *out_ids, int64_t *n_out) {
+    if (!out_velocities) return MC_E_INVALID;
+    return snapshot_begin_impl(c, out_positions, out_velocities, out_ids, n_out);
 }
 
 extern "C" int mc_snapshot_wait(mc_ctx *c) {

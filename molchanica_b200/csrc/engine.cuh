@@ -122,6 +122,8 @@ struct mc_ctx {
     float baro_p0 = 1.f, baro_tau = 5.f, baro_beta = 4.5e-5f;
     uint64_t baro_seed = 0, baro_draws = 0;
     double baro_last_p = 0.0, baro_last_mu = 1.0;
+    int com_every = 0;            // option "zero_com_drift": remove the centre-of-mass velocity every k steps (0 = never)
+    DevBuf<double> com_partial;
     DevBuf<double> cons_virial;   // virial of the constraint forces of the last step (settle.cu)
     bool cons_virial_valid = false;
     DevBuf<double> bonded_e;   // {E_bond, E_angle, E_dihedral} of the last evaluation that asked for energies
@@ -161,7 +163,7 @@ struct mc_ctx {
     // asynchronous snapshots (mc_snapshot_begin / mc_snapshot_wait): double-buffered staging + a copy stream
     cudaStream_t st_copy = nullptr;
     cudaEvent_t ev_snap_staged[2] = {nullptr, nullptr}, ev_snap_done[2] = {nullptr, nullptr};
-    DevBuf<float4> snap_stage[2];
+    DevBuf<float4> snap_stage[2], snap_stage_v[2];
     DevBuf<int> snap_ids[2];
     int snap_k = 0;
     bool snap_pending[2] = {false, false};
@@ -207,9 +209,9 @@ struct mc_ctx {
         ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); ext_force2.release(); d_poses.release(); d_scores.release();
         grid.release(); red_partial.release(); red_out.release(); d_rec.release(); d_lig.release();
         d_rec_meta.release(); d_lig_meta.release(); d_rec_s.release(); d_lig_s.release(); d_keep.release();
-        for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_ids[b].release(); }
+        for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_stage_v[b].release(); snap_ids[b].release(); }
         bonds.release(); bond_kr0.release(); angle_kt0.release(); angles.release(); dihedrals.release(); dihedral_prm.release();
-        bonded_e.release(); cons_virial.release(); waters.release(); vsites.release(); csvr_lambda.release();
+        bonded_e.release(); cons_virial.release(); com_partial.release(); waters.release(); vsites.release(); csvr_lambda.release();
         hclusters.release(); hdist.release(); shake_fail.release(); mol_of_orig.release(); min_x.release(); min_v.release();
     }
 

@@ -23,6 +23,8 @@ void launch_langevin_ou(int n_rows, float4 *vel, const int *orig, const uint8_t 
 void launch_csvr(int n_rows, float4 *vel, const double *red3, double kT, double c, double dof_removed, uint64_t seed, uint64_t step,
                  float *lambda, cudaStream_t st, int64_t *launches);
 void launch_zero_velocities(int n_rows, float4 *vel, cudaStream_t st, int64_t *launches);
+int com_partial_elems();
+void launch_remove_com(int n_rows, float4 *vel, const uint8_t *flags, double *partial, cudaStream_t st, int64_t *launches);
 void launch_scale_coords(int n, float4 *xyzq, float4 *xref, float4 *vel, float mu, float nu, cudaStream_t st, int64_t *launches);
 // original-order <-> cell-order copies
 void launch_gather_to_orig(int n, const float4 *sorted, const int *orig, float4 *out, cudaStream_t st, int64_t *launches);

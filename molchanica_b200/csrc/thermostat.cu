@@ -52,6 +52,55 @@ __global__ void __launch_bounds__(256) zero_velocities_kernel(int n_rows, float4
     vel[i] = v;
 }
 
+// MdConfig.zero_com_drift (reference properties/crystal.rs:310, water_sol.rs:144): remove the velocity of the centre of
+// mass of the mobile atoms.  Two launches: per-block partial sums {sum m v, sum m} in fp64, then every block sums the
+// (<= COM_BLOCKS) partials itself -- same order in every block, so all threads subtract the same vector -- and subtracts.
+constexpr int COM_BLOCKS = 296;  // 2 x 148 SMs
+
+__global__ void __launch_bounds__(256) com_partial_kernel(int n_rows, const float4 *__restrict__ vel, const uint8_t *__restrict__ flags,
+                                                           double *__restrict__ partial) {
+    double p[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
+        const float4 v = vel[i];
+        if (v.w > 0.f && !(flags[i] & MC_FLAG_STATIC)) {
+            const double m = 1.0 / (double)v.w;
+            p[0] += m * v.x; p[1] += m * v.y; p[2] += m * v.z; p[3] += m;
+        }
+    }
+    __shared__ double sh[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) p[k] += __shfl_xor_sync(MC_FULL_MASK, p[k], d);
+        if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = p[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+        partial[4 * blockIdx.x + threadIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) com_remove_kernel(int n_rows, float4 *__restrict__ vel, const uint8_t *__restrict__ flags,
+                                                          const double *__restrict__ partial, int n_partial) {
+    __shared__ float vcom[3];
+    if (threadIdx.x == 0) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int b = 0; b < n_partial; ++b)
+            for (int k = 0; k < 4; ++k) t[k] += partial[4 * b + k];
+        for (int k = 0; k < 3; ++k) vcom[k] = t[3] > 0.0 ? (float)(t[k] / t[3]) : 0.f;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    float4 v = vel[i];
+    if (v.w > 0.f && !(flags[i] & MC_FLAG_STATIC)) {
+        v.x -= vcom[0]; v.y -= vcom[1]; v.z -= vcom[2];
+        vel[i] = v;
+    }
+}
+
 // barostat (engine.cu): positions and the displacement reference scaled about the origin by mu, velocities by nu
 // (1 for Berendsen, 1 / mu for stochastic cell rescaling); charges / inverse masses in .w untouched
 __global__ void __launch_bounds__(256) scale_coords_kernel(int n, float4 *__restrict__ xyzq, float4 *__restrict__ xref,
@@ -76,6 +125,16 @@ void launch_zero_velocities(int n_rows, float4 *vel, cudaStream_t st, int64_t *l
     if (n_rows <= 0) return;
     MC_LAUNCH(zero_velocities_kernel, div_up(n_rows, 256), 256, 0, st, n_rows, vel);
     *launches += 1;
+}
+
+int com_partial_elems() { return 4 * COM_BLOCKS; }
+
+void launch_remove_com(int n_rows, float4 *vel, const uint8_t *flags, double *partial, cudaStream_t st, int64_t *launches) {
+    if (n_rows <= 0) return;
+    const int nb = (int)min(div_up(n_rows, 256), (unsigned)COM_BLOCKS);
+    MC_LAUNCH(com_partial_kernel, nb, 256, 0, st, n_rows, vel, flags, partial);
+    MC_LAUNCH(com_remove_kernel, div_up(n_rows, 256), 256, 0, st, n_rows, vel, flags, partial, nb);
+    *launches += 2;
 }
 
 void launch_scale_coords(int n, float4 *xyzq, float4 *xref, float4 *vel, float mu, float nu, cudaStream_t st, int64_t *launches) {

@@ -237,6 +237,12 @@ class MdEngine:
         self._chk(self._L.mc_snapshot_begin(self._h, _ptr(out_positions), _ptr(out_ids), C.byref(n_out)))
         return int(n_out.value)
 
+    def snapshot_begin_pv(self, out_positions, out_velocities, out_ids=None):
+        """mc_snapshot_begin_pv: positions and velocities."""
+        n_out = C.c_int64(0)
+        self._chk(self._L.mc_snapshot_begin_pv(self._h, _ptr(out_positions), _ptr(out_velocities), _ptr(out_ids), C.byref(n_out)))
+        return int(n_out.value)
+
     def snapshot_wait(self):
         self._chk(self._L.mc_snapshot_wait(self._h))
 

@@ -52,6 +52,47 @@ int main() {
             if (!(md.atoms[1].posit.x - md.atoms[0].posit.x > sigma)) return fail("separation", md.atoms[1].posit.x - md.atoms[0].posit.x, sigma);
             if (std::fabs(md.atoms[0].vel.x + md.atoms[1].vel.x) > 1e-5) return fail("momentum", md.atoms[0].vel.x + md.atoms[1].vel.x, 0.0);
         }
+        // NPT the way properties/crystal.rs:306-316 configures it: thermostat + zero_com_drift + barostat, on a small
+        // periodic argon lattice; the box must shrink towards a target far above the starting pressure
+        {
+            MdConfig npt = cfg;
+            const int m = 6;
+            const float a = 3.6f, L = a * m;
+            npt.lj_cutoff = npt.coulomb_cutoff = 8.5f;
+            npt.skin = 0.5f;
+            npt.sim_box.periodic = true;
+            npt.sim_box.bounds_low = {0, 0, 0};
+            npt.sim_box.bounds_high = {L, L, L};
+            npt.thermostat_tau = 0.1f;
+            npt.temp_target = 90.0f;
+            npt.zero_com_drift = true;
+            npt.has_barostat = true;
+            npt.barostat_cfg.pressure_target = 20000.0f;
+            npt.barostat_cfg.tau = 0.5f;
+            npt.barostat_cfg.compressibility = 1e-4f;
+            MdSystem lat;
+            lat.n_lj_types = 1;
+            lat.lj_sigma_eps = {sigma, eps};
+            for (int i = 0; i < m; ++i)
+                for (int j = 0; j < m; ++j)
+                    for (int k = 0; k < m; ++k) {
+                        AtomDynamics at;
+                        at.mass = 39.948f;
+                        at.posit = {(i + 0.5f) * a + 0.01f * ((i * 7 + j * 3 + k) % 5), (j + 0.5f) * a, (k + 0.5f) * a};
+                        at.vel = {0.5f * ((i + j) % 3 - 1), 0.5f * ((j + k) % 3 - 1), 0.5f * ((k + i) % 3 - 1)};
+                        lat.atoms.push_back(at);
+                    }
+            MdState md = MdState::create(dev, npt, lat);
+            md.step(dev, 0.002f, std::nullopt, 100);
+            const SimBox b = md.current_box();
+            if (!(b.bounds_high.x < L - 1e-3f)) return fail("barostat shrinks the box", b.bounds_high.x, L);
+            SnapshotEnergyData e = md.energy_snapshot(dev);
+            if (!(e.pressure != 0.0 && std::isfinite(e.pressure))) return fail("pressure", e.pressure, 1.0);
+            std::vector<mc_float4> px, pv;
+            md.snapshot_begin(px, pv);
+            md.snapshot_wait();
+            if (px.size() != lat.atoms.size() || !(pv[0].w > 0.f)) return fail("snapshot with velocities", (double)px.size(), (double)lat.atoms.size());
+        }
         // error behaviour: a bad configuration surfaces as ParamError, never as a crash or a fallback
         bool threw = false;
         try {

@@ -128,6 +128,14 @@ def test_async_snapshots_match_blocking_reads(Engine):
     e.snapshot_wait()
     e.snapshot_wait()
     assert np.array_equal(bufs[1], want[1]) and np.array_equal(bufs[2], want[2])
+    # positions + velocities (Snapshot.atom_velocities), also right after a pipelined call with external forces
+    ext = np.zeros((n, 3), np.float32)
+    ext[::5, 1] = 2.0
+    e.step(w["dt"], 2, ext_forces=ext)
+    px, pv = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
+    assert e.snapshot_begin_pv(px, pv) == n
+    e.snapshot_wait()
+    assert np.array_equal(px, e.positions()) and np.array_equal(pv, e.velocities())
     e.close()
 
 
@@ -419,6 +427,30 @@ def test_npt_of_rigid_water_with_stochastic_cell_rescaling(Engine):
     d = lambda a, b: np.linalg.norm((a - b) - np.rint((a - b) / ext) * ext, axis=1)
     # coordinates were scaled (bond lengths with them) at most once since the last SETTLE: rigid to 1e-3 A
     assert np.abs(d(m[:, 0], m[:, 1]) - 0.9572).max() < 2e-3 and np.abs(d(m[:, 1], m[:, 2]) - 1.5139).max() < 3e-3
+
+
+def test_zero_com_drift_removes_the_net_momentum_of_the_mobile_atoms(Engine):
+    """MdConfig.zero_com_drift (reference properties/crystal.rs:310): option zero_com_drift = k."""
+    w = W.lj_fluid(m=12)
+    w["vel"] = w["vel"].copy()
+    w["vel"][:, 0] += 1.5                                   # the whole fluid drifts along x
+    flags = np.zeros(len(w["xyzq"]), np.uint8)
+    flags[::50] = 1                                         # static atoms: neither counted nor touched
+    w["flags"] = flags
+    mom = lambda v: ((v[:, :3] / v[:, 3:4]).astype(np.float64))[flags == 0].sum(0)
+    e = Engine.from_workload(w)
+    e.step(w["dt"], 4)
+    p_free = mom(e.velocities())
+    e.close()
+    e = Engine.from_workload(w)
+    e.set_option("zero_com_drift", 2)
+    e.step(w["dt"], 4)
+    v = e.velocities()
+    e.close()
+    assert abs(p_free[0]) > 1e4                            # without the option the drift stays
+    assert np.abs(mom(v)).max() < 2e-4 * abs(p_free[0])    # with it the mobile atoms are at rest as a whole (forces between
+    #                                                        mobile and static atoms feed a little back within two steps)
+    assert np.array_equal(v[flags == 1], w["vel"][flags == 1])
 
 
 def test_pressure_refuses_what_it_cannot_do(Engine):

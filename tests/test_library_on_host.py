@@ -55,6 +55,17 @@ def test_components_not_yet_run_on_hardware_pass_on_the_host_build(worker, host_
     assert isinstance(res, dict) and res
 
 
+def test_cpp_host_mirror_runs_on_the_host_build(host_env, tmp_path):
+    """include/molchanica_md.hpp (the C++ mirror of the reference's MdState interface) driven by tests/cpp/host_mirror_smoke.cpp,
+    its libmolchanica_md.so resolved to the host build: known two-body answers, stepping, NPT configuration, snapshots."""
+    import __graft_entry__ as g
+    g.build_cpp_host()
+    os.symlink(host_env["MOLCHANICA_MD_LIB"], tmp_path / "libmolchanica_md.so")
+    env = dict(host_env, LD_LIBRARY_PATH=str(tmp_path) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([os.path.join(HERE, "cpp", "_build", "host_mirror_smoke")], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "host mirror ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_product_library_still_refuses_without_a_gpu():
     """No CPU fallback in the product: the nvcc-built library must fail loudly here."""
     import torch
