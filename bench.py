@@ -324,7 +324,7 @@ def main():
                            "parallelism": f"slab-dd{world}" if world > 1 else "single-gpu",
                            "halo": (("fused peer-memory push in kick_drift + flag wait in the pair kernel" if e.halo_mode()[0]
                                      else "nccl send/recv (" + e.halo_mode()[1] + ")") if world > 1 else None),
-                           "pair_lanes": args.lanes or 8},
+                           "pair_lanes": args.lanes or 8, "engine_options": args.opt or None},
                 "e2e": e2e, "gpu_launches": int(s1["n_kernel_launches"] - s0["n_kernel_launches"]),
                 "rebuilds_in_timed_region": int(s1["n_rebuilds"] - s0["n_rebuilds"]),
                 "wall_ms_per_step": wall / K * 1e3, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
