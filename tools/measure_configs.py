@@ -114,4 +114,20 @@ try:  # OPC water box: SETTLE + virtual sites + SPME + Langevin, the reference's
     e.close()
 except Exception as ex:  # noqa: BLE001
     out["OPC_water"] = dict(error=str(ex))
+try:  # the same box as NPT: CSVR + stochastic cell rescaling + drift removal (properties/crystal.rs:306-316)
+    w = W.water_box_opc(m=12, L=37.3)
+    e = MdEngine.from_workload(w)
+    e.set_rigid_waters(w["rigid_waters"], w["d_oh"], w["d_hh"])
+    e.set_virtual_sites(w["virtual_sites"], *w["vsite_ab"])
+    e.set_pme(40, 40, 40)
+    e.set_thermostat(2, 300.0, 10.0, seed=1)
+    e.set_option("zero_com_drift", 100)
+    e.set_barostat(2, 1.0, tau_ps=1.0, every=10, seed=3)
+    rate = _timed_steps(e, 0.002, 1000)
+    lo, hi = e.box()
+    out["OPC_water_NPT"] = dict(atoms=len(w["xyzq"]), steps_per_s=rate, pressure_bar=e.pressure()[0], volume=float(np.prod(hi - lo)),
+                                energy=e.energy())
+    e.close()
+except Exception as ex:  # noqa: BLE001
+    out["OPC_water_NPT"] = dict(error=str(ex))
 print(json.dumps(out))
