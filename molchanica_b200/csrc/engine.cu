@@ -850,6 +850,10 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);
     MC_REQUIRE(c, n_steps >= 0 && dt > 0.f, "mc_step: n_steps >= 0 and dt > 0 required");
+    if (!c->comm_active && c->n_global == 0) {  // an empty system steps trivially (no block would publish the rebuild flag)
+        c->n_steps += n_steps;
+        return MC_OK;
+    }
     c->prof_now = true;
     cudaStream_t st = c->st;
     // decomposed runs rebuild on a schedule every rank derives from the same numbers (no per-step agreement)

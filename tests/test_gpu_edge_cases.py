@@ -1,0 +1,146 @@
+"""Edge cases of the hot path through the C ABI (empty and tiny systems, atoms on box faces and far outside the box, pairs
+exactly at the cutoff, empty cells, one overfull cell, degenerate calls).  Same bars as tests/test_gpu_parity.py.
+Needs a B200 (or the host build of tests/test_library_on_host.py)."""
+import numpy as np
+import pytest
+
+from molchanica_b200 import workloads as W
+from util import FORCE_RTOL, force_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Engine():
+    from molchanica_b200.engine import MdEngine
+    return MdEngine
+
+
+def _argon(xyz, L, periodic=True, rc=8.5125, skin=1.0):
+    """An argon system from bare coordinates, in the workload format of molchanica_b200/workloads.py."""
+    base = W.lj_fluid(m=3)
+    n = len(xyz)
+    x = np.zeros((n, 4), np.float32)
+    x[:, :3] = xyz
+    v = np.zeros((n, 4), np.float32)
+    v[:, 3] = base["vel"][0, 3]
+    return dict(base, xyzq=x, vel=v, type=np.zeros(n, np.uint16), flags=np.zeros(n, np.uint8), box_lo=np.zeros(3, np.float32),
+                box_ext=np.full(3, L, np.float32), periodic=periodic, rc_lj=rc, rc_q=rc, skin=skin, excl_start=None, excl_idx=None,
+                pairs14=np.zeros((0, 2), np.int32))
+
+
+def _check_list_and_forces(Engine, oracle, w):
+    e = Engine.from_workload(w)
+    e.build_neighbors()
+    start, idx = e.neighbors()
+    o_start, o_idx = oracle.neighbors(w)
+    assert np.array_equal(start, o_start) and np.array_equal(idx, o_idx)
+    e.compute_forces()
+    f = e.forces()
+    f64, sumabs, _ = oracle.forces(w, (o_start, o_idx), precision=64)
+    if len(o_idx):
+        assert force_rel_err(f, f64, sumabs).max() < FORCE_RTOL
+    else:
+        assert not f[:, :3].any()
+    st = e.stats()
+    e.close()
+    return st, start, idx
+
+
+def test_empty_system(Engine):
+    w = _argon(np.zeros((0, 3), np.float32), 40.0)
+    e = Engine.from_workload(w)
+    e.build_neighbors()
+    start, idx = e.neighbors()
+    assert len(idx) == 0 and list(start) == [0]
+    e.compute_forces()
+    e.step(0.002, 3)
+    assert e.positions().shape == (0, 4) and e.energy()["energy_potential"] == 0.0
+    e.close()
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_one_and_two_atoms(periodic, Engine, oracle):
+    w = _argon(np.array([[5.0, 5.0, 5.0]], np.float32), 40.0, periodic)
+    st, start, idx = _check_list_and_forces(Engine, oracle, w)
+    assert len(idx) == 0
+    # two atoms across the periodic seam (or 4 A apart in vacuum): one pair, equal and opposite forces
+    xyz = np.array([[0.5, 20.0, 20.0], [36.5 if periodic else 4.5, 20.0, 20.0]], np.float32)
+    w = _argon(xyz, 40.0, periodic)
+    e = Engine.from_workload(w)
+    e.compute_forces()
+    f = e.forces()
+    e.close()
+    assert np.abs(f[0, :3] + f[1, :3]).max() < 1e-6 and abs(f[0, 0]) > 1e-4
+    _check_list_and_forces(Engine, oracle, w)
+
+
+def test_pair_exactly_at_the_list_radius_and_at_the_cutoff(Engine, oracle):
+    """r^2 < r_list^2 decides membership, r^2 < rc^2 the force: a pair AT either radius is out, one ulp inside is in --
+    on both sides of the comparison (fp32, no FMA) the engine and the oracle must agree."""
+    rc, skin = np.float32(8.5125), np.float32(1.0)
+    rl = rc + skin
+    for d in (rl, np.nextafter(rl, np.float32(0)), np.nextafter(rl, np.float32(100)), rc, np.nextafter(rc, np.float32(0))):
+        xyz = np.array([[10.0, 10.0, 10.0], [10.0 + d, 10.0, 10.0]], np.float32)
+        _check_list_and_forces(Engine, oracle, _argon(xyz, 60.0))
+
+
+def test_atoms_on_the_faces_and_far_outside_the_box(Engine, oracle):
+    """x = lo and x = hi exactly, negative coordinates, atoms several box lengths away: wrapped into the box, listed as the
+    oracle lists them."""
+    rng = np.random.default_rng(4)
+    L = 30.0
+    xyz = rng.uniform(0, L, (600, 3)).astype(np.float32)
+    xyz[:40, 0] = 0.0
+    xyz[40:80, 1] = L
+    xyz[80:120, 2] = np.nextafter(np.float32(L), np.float32(0))
+    xyz[120:160] -= np.float32(L)
+    xyz[160:200] += np.float32(3 * L)
+    xyz[200:220, 0] = np.float32(-0.0)
+    w = _argon(xyz, L, rc=6.0, skin=1.0)
+    _check_list_and_forces(Engine, oracle, w)
+    e = Engine.from_workload(w)
+    e.build_neighbors()
+    x = e.positions()
+    e.close()
+    assert np.all(x[:, :3] >= 0) and np.all(x[:, :3] < L)
+
+
+def test_mostly_empty_cells_and_one_overfull_cell(Engine, oracle):
+    """A few atoms in a large box (almost every cell empty) and a droplet of 1500 atoms inside ONE cell of a large box: the
+    tile of that cell's neighbourhood outgrows the initial shared-memory tile and the list capacity, both grow on demand."""
+    rng = np.random.default_rng(6)
+    sparse = rng.uniform(0, 120.0, (50, 3)).astype(np.float32)
+    st, _, _ = _check_list_and_forces(Engine, oracle, _argon(sparse, 120.0))
+    assert np.prod(st["n_cells"]) > 1000
+    # droplet: 1500 atoms on a jittered lattice of spacing 0.9 A... too dense for LJ forces to be finite in fp32 at 1e-5,
+    # so the list is checked with the engine's and oracle's indices only
+    g = np.stack(np.meshgrid(*[np.arange(12)] * 3, indexing="ij"), -1).reshape(-1, 3)[:1500].astype(np.float32)
+    drop = 50.0 + 0.75 * g + rng.uniform(-0.1, 0.1, (1500, 3)).astype(np.float32)
+    w = _argon(np.concatenate([drop, sparse]), 120.0)
+    e = Engine.from_workload(w)
+    e.build_neighbors()
+    start, idx = e.neighbors()
+    e.close()
+    o_start, o_idx = oracle.neighbors(w)
+    assert np.array_equal(start, o_start) and np.array_equal(idx, o_idx)
+    assert (np.diff(start)[:1500] > 1000).all()              # every droplet atom lists (almost) the whole droplet
+
+
+def test_degenerate_calls(Engine):
+    from molchanica_b200.engine import McError
+    w = W.lj_fluid(m=6)
+    e = Engine.from_workload(w)
+    x0 = e.positions()
+    e.step(w["dt"], 0)                                       # zero steps: nothing moves, nothing breaks
+    assert np.array_equal(e.positions(), x0)
+    with pytest.raises(McError):
+        e.step(-1.0, 1)
+    with pytest.raises(McError):
+        e.step(w["dt"], -3)
+    with pytest.raises(McError):
+        e.set_option("no_such_option", 1)
+    with pytest.raises(McError):
+        e.set_cutoffs(30.0, 30.0, 1.0, 0)                   # cutoff + skin beyond half the box
+        e.build_neighbors()
+    e.close()
