@@ -144,3 +144,20 @@ def test_degenerate_calls(Engine):
         e.set_cutoffs(30.0, 30.0, 1.0, 0)                   # cutoff + skin beyond half the box
         e.build_neighbors()
     e.close()
+
+
+def test_docking_scan_edge_cases(Engine, oracle):
+    """No poses, a one-atom ligand, a ligand beyond the shared-memory tile, an empty receptor."""
+    from molchanica_b200.engine import McError
+    d = W.docking_c5(n_rec=300, n_lig=10, n_poses=8, seeds=(1, 2, 3))
+    e = Engine()
+    assert e.dock_score(d, poses=np.zeros((0, 7), np.float32)).shape == (0, 5)
+    d1 = dict(d, lig=d["lig"][:1], lig_type=d["lig_type"][:1], lig_hphob=d["lig_hphob"][:1])
+    s = e.dock_score(d1)
+    ref, ref_abs = oracle.dock_score(d1, precision=64, with_abs=True)
+    assert np.all(np.abs(s[:, 1] - ref[:, 1]) <= 1e-5 * ref_abs[:, 0] + 1e-6)
+    with pytest.raises(McError, match="shared-memory"):
+        e.dock_score(W.docking_c5(n_rec=300, n_lig=20000, n_poses=2, seeds=(1, 2, 3)))
+    with pytest.raises(McError):
+        e.dock_score(dict(d, rec=d["rec"][:0], rec_type=d["rec_type"][:0], rec_hphob=d["rec_hphob"][:0]))
+    e.close()
