@@ -36,7 +36,7 @@ def test_gpu_parity_tests_pass_on_the_host_build(host_env):
     slow = "c4 or lane_width or variants or solv23558 or full_size"
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k", f"not ({slow})",
                         os.path.join(HERE, "test_gpu_parity.py"), os.path.join(HERE, "test_gpu_dock.py"),
-                        os.path.join(HERE, "test_gpu_edge_cases.py")],
+                        os.path.join(HERE, "newpaths_md.py"), os.path.join(HERE, "newpaths_edge_cases.py")],
                        capture_output=True, text=True, cwd=ROOT, env=host_env, timeout=1500)
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
