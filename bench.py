@@ -250,25 +250,39 @@ def main():
             d2h = int(n_out.value) * (16 + (4 if world > 1 else 0))
             if k > 0:
                 e._chk(e._L.mc_snapshot_wait(e._h))
-        for k in range(4):
-            one(k)
-        e._chk(e._L.mc_snapshot_wait(e._h))
-        ke = min(K, 300)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(ke):
-            one(k)
-        e._chk(e._L.mc_snapshot_wait(e._h))
-        barrier()
-        te = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([te], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            te = float(tt.item())
-        e2e = {"value": ns_per_day(ke, te), "unit": UNIT, "h2d_bytes_per_step": int(ext.numel() * 4),
-               "d2h_bytes_per_step": d2h, "steps": ke, "ms_per_step": te / ke * 1e3,
-               "api": "mc_step(ctx, dt, 1, ext_forces) + mc_snapshot_begin(ctx, out, ids) / mc_snapshot_wait(ctx), pinned host "
-                      "buffers; bytes are per rank"}
+        def run_leg():
+            for k in range(4):
+                one(k)
+            e._chk(e._L.mc_snapshot_wait(e._h))
+            ke = min(K, 300)
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(ke):
+                one(k)
+            e._chk(e._L.mc_snapshot_wait(e._h))
+            barrier()
+            te = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([te], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                te = float(tt.item())
+            return {"value": ns_per_day(ke, te), "unit": UNIT, "h2d_bytes_per_step": int(ext.numel() * 4),
+                    "d2h_bytes_per_step": d2h, "steps": ke, "ms_per_step": te / ke * 1e3,
+                    "api": "mc_step(ctx, dt, 1, ext_forces) + mc_snapshot_begin(ctx, out, ids) / mc_snapshot_wait(ctx), pinned host "
+                           "buffers; bytes are per rank"}
+        try:
+            e2e = run_leg()
+        except Exception as ex:  # noqa: BLE001
+            if world > 1:
+                raise
+            # the pipelined upload of a single-GPU handle (option defer_tail) was written after this round's last hardware
+            # run: should it fail here, the line still carries the path that WAS measured, and says so
+            try:
+                e.set_option("defer_tail", 0)
+                e2e = run_leg()
+                e2e["note"] = f"pipelined upload failed ({ex}); measured with defer_tail = 0"
+            except Exception as ex2:  # noqa: BLE001
+                e2e = {"value": None, "unit": UNIT, "error": f"{ex}; then {ex2}"}
 
     # ---- roofline of the dominant kernel (pair force), live CUDA-event average over the timed region
     pair_ms = (s1["pair_ms_sum"] - 0.0) / max(s1["pair_launches_timed"], 1)
