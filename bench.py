@@ -229,7 +229,7 @@ def main():
     if not args.no_e2e:
         # per step: mc_step(dt, 1, ext) with the step's external forces in pinned HOST memory (H2D inside; on a single GPU
         # the upload runs on its own stream under the force evaluation the previous call left open -- engine.cu,
-        # option defer_tail, invisible through the ABI: tests/test_gpu_parity.py::test_pipelined_external_forces...), then
+        # option defer_tail, invisible through the ABI: tests/newpaths_md.py::test_pipelined_external_forces...), then
         # mc_snapshot_begin hands the new positions to a pinned HOST buffer (D2H inside, double-buffered so that
         # the copy of step s overlaps the kernels of step s+1 -- the Snapshot queue of the reference,
         # src/md/mod.rs:118-152); mc_snapshot_wait(s-1) before buffer reuse, all copies drained before the clock stops.
@@ -271,7 +271,11 @@ def main():
                     "api": "mc_step(ctx, dt, 1, ext_forces) + mc_snapshot_begin(ctx, out, ids) / mc_snapshot_wait(ctx), pinned host "
                            "buffers; bytes are per rank"}
         try:
+            if world == 1:
+                e.set_option("defer_tail", 0 if any(o.startswith("defer_tail=0") for o in args.opt) else 1)
             e2e = run_leg()
+            if world == 1:
+                e2e["api"] += "; option defer_tail = " + ("0" if any(o.startswith("defer_tail=0") for o in args.opt) else "1 (pipelined upload)")
         except Exception as ex:  # noqa: BLE001
             if world > 1:
                 raise

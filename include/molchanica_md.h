@@ -191,10 +191,10 @@ int mc_set_overrides(mc_ctx *ctx, int lj_disabled, int coulomb_disabled);
  * "profile_every" (k: inside mc_step only every k-th step's kernels are bracketed with events),
  * "zero_com_drift" (k: remove the velocity of the centre of mass of the mobile atoms every k steps, MdConfig.zero_com_drift
  * of the reference; 0 = never (default)),
- * "defer_tail" (1 (default): a single-GPU mc_step with ext_forces returns after its last drift and finishes that
+ * "defer_tail" (1: a single-GPU mc_step with ext_forces returns after its last drift and finishes that
  * step -- force evaluation, second half kick -- under the upload of the next call's array, or as soon as anything
- * but positions is asked for; results are the same, only the time at which the work is done moves; 0 = finish
- * every step inside its own call). */
+ * but positions is asked for; results are the same, only the time at which the work is done moves; 0 (default until
+ * the path has been confirmed on hardware) = finish every step inside its own call). */
 int mc_set_option(mc_ctx *ctx, const char *name, double value);
 
 /* Replace positions (and optionally velocities) of the existing atoms, original order. */
