@@ -44,21 +44,24 @@ __global__ void __launch_bounds__(128) between_mols_kernel(int n_rows, int row0,
 
 // Virial of the nonbonded terms on demand (mc_get_pressure): W = sum_{i<j} r_ij . f_ij over the listed pairs inside the
 // cutoffs plus the scaled 1-4 pairs, with the forms of pair_force.cu (same fp32 r^2 expression for the cutoff decision).
-// One thread per row; every pair sits in two rows, hence the factor 1/2.
+// Eight lanes per row like the force kernel (consecutive lanes read consecutive list entries); every pair sits in two
+// rows, hence the factor 1/2.
+constexpr int VIR_LANES = 8;
 __global__ void __launch_bounds__(128) virial_kernel(int n_rows, int row0, const float4 *__restrict__ xyzq, const uint16_t *__restrict__ type,
                                                       const int *__restrict__ orig, const int *__restrict__ slot_of_orig,
                                                       const uint32_t *__restrict__ nbr_start, const uint32_t *__restrict__ nbr_count,
                                                       const uint32_t *__restrict__ nbr_list, const int32_t *__restrict__ p14_start,
                                                       const int32_t *__restrict__ p14_idx, const float2 *__restrict__ ljtab, const NbParams p,
                                                       int lj_on, int coul_mode, float scale_lj, float scale_q, double *__restrict__ virial) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = gt / VIR_LANES, lane = gt % VIR_LANES;
     float w = 0.f;
     if (r < n_rows) {
         const int i = row0 + r;
         const float4 xi = xyzq[i];
         const int ti = type[i];
         const uint32_t s = nbr_start[i], cnt = nbr_count[i];
-        for (uint32_t k = 0; k < cnt; ++k) {
+        for (uint32_t k = lane; k < cnt; k += VIR_LANES) {
             const uint32_t j = nbr_list[s + k];
             const float4 xj = xyzq[j];
             float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(128) virial_kernel(int n_rows, int row0, const
             const float2 lj = ljtab[ti * p.n_types + type[j]];
             w += mc_pair_virial(r2, lj.x, lj.y, xi.w * xj.w, p.rc2_lj, p.rc2_q, lj_on, coul_mode, p.alpha);
         }
-        if (p14_start) {  // Amber 1-4 rows: no cutoff, LJ x scale_lj, plain Coulomb x scale_q (pairs14_kernel)
+        if (p14_start && lane == 0) {  // Amber 1-4 rows: no cutoff, LJ x scale_lj, plain Coulomb x scale_q (pairs14_kernel)
             const int oi = orig[i];
             for (int e = p14_start[oi]; e < p14_start[oi + 1]; ++e) {
                 const int j = slot_of_orig[p14_idx[e]];
@@ -115,7 +118,7 @@ void launch_virial(int n_rows, int row0, const float4 *xyzq, const uint16_t *typ
                    double *virial, cudaStream_t st, int64_t *launches) {
     cudaMemsetAsync(virial, 0, sizeof(double), st);
     if (n_rows <= 0) return;
-    MC_LAUNCH(virial_kernel, div_up((size_t)n_rows, 128), 128, 0, st, n_rows, row0, xyzq, type, orig, slot_of_orig, nbr_start, nbr_count,
+    MC_LAUNCH(virial_kernel, div_up((size_t)n_rows * VIR_LANES, 128), 128, 0, st, n_rows, row0, xyzq, type, orig, slot_of_orig, nbr_start, nbr_count,
               nbr_list, p14_start, p14_idx, ljtab, p, lj_on, coul_mode, scale_lj, scale_q, virial);
     *launches += 1;
 }
