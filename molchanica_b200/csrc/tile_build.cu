@@ -286,7 +286,12 @@ __device__ __forceinline__ void rows_phase2(const float4 *tile, const uint32_t *
     }
 }
 
-__global__ void __launch_bounds__((TILE_WARPS + 1) * 32, 3) tile_build_kernel(
+// Minimum resident CTAs per SM the register allocation is held to: 3 -> 72 registers and 296 B of spill stores, 2 -> 96
+// registers and 40 B (ptxas -v, sm_100a).  Which one is faster is a measurement: -DMC_TILE_MIN_BLOCKS=2 builds the variant.
+#ifndef MC_TILE_MIN_BLOCKS
+#define MC_TILE_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) tile_build_kernel(
     int n_rows, const float4 *__restrict__ xyzq, const uint32_t *__restrict__ cell_start,
     const GridParams *__restrict__ gp, float rl2, float rc2_inner, const int *__restrict__ orig,
     const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx, uint32_t *__restrict__ nbr_count,
