@@ -582,7 +582,7 @@ int comm_rebuild(mc_ctx *c) {
         const size_t off_next = whole ? (cs->rank == 0 ? n_own : 0) : from_prev + n_own;
         const size_t off_prev = 0;
         MC_CUDAC(c, cs->g_xyzq.ensure(n_all)); MC_CUDAC(c, cs->g_vel.ensure(n_all)); MC_CUDAC(c, cs->g_meta.ensure(n_all));
-        dd_pack_kernel<<<div_up(n_own, 256), 256, 0, st>>>((int)n_own, (int)n_own, c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0,
+        MC_LAUNCH(dd_pack_kernel, div_up(n_own, 256), 256, 0, st, (int)n_own, (int)n_own, c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0,
                                                           c->orig[c->cur].p + r0, c->type[c->cur].p + r0, c->flags[c->cur].p + r0,
                                                           cs->g_xyzq.p + off_own, cs->g_vel.p + off_own, cs->g_meta.p + off_own);
         c->launches += 1;
@@ -616,7 +616,7 @@ int comm_rebuild(mc_ctx *c) {
         n_all = cap * (size_t)cs->n;
         MC_CUDAC(c, cs->s_xyzq.ensure(cap)); MC_CUDAC(c, cs->s_vel.ensure(cap)); MC_CUDAC(c, cs->s_meta.ensure(cap));
         MC_CUDAC(c, cs->g_xyzq.ensure(n_all)); MC_CUDAC(c, cs->g_vel.ensure(n_all)); MC_CUDAC(c, cs->g_meta.ensure(n_all));
-        dd_pack_kernel<<<div_up(cap, 256), 256, 0, st>>>((int)c->n_rows, (int)cap, c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0,
+        MC_LAUNCH(dd_pack_kernel, div_up(cap, 256), 256, 0, st, (int)c->n_rows, (int)cap, c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0,
                                                          c->orig[c->cur].p + r0, c->type[c->cur].p + r0, c->flags[c->cur].p + r0,
                                                          cs->s_xyzq.p, cs->s_vel.p, cs->s_meta.p);
         c->launches += 1;
@@ -630,19 +630,19 @@ int comm_rebuild(mc_ctx *c) {
     MC_CUDAC(c, c->keys[0].ensure(n_all)); MC_CUDAC(c, c->keys[1].ensure(n_all));
     MC_CUDAC(c, c->vals[0].ensure(n_all)); MC_CUDAC(c, c->vals[1].ensure(n_all));
     MC_CUDAC(c, c->scratch.ensure(std::max(radix_scratch_elems(n_all), scan_scratch_elems(n_all + 1)) + 64));
-    dd_key_kernel<<<div_up(n_all, 256), 256, 0, st>>>((int)n_all, cs->g_xyzq.p, cs->g_meta.p, c->grid.p, c->keys[0].p, c->vals[0].p);
+    MC_LAUNCH(dd_key_kernel, div_up(n_all, 256), 256, 0, st, (int)n_all, cs->g_xyzq.p, cs->g_meta.p, c->grid.p, c->keys[0].p, c->vals[0].p);
     c->launches += 1;
     uint32_t *kk[2] = {c->keys[0].p, c->keys[1].p}, *vv[2] = {c->vals[0].p, c->vals[1].p};
     const int which = radix_sort_pairs(kk, vv, n_all, c->key_bits, c->scratch.p, st, &c->launches);
     MC_CUDAC(c, cudaMemsetAsync(c->slot_of_orig.p, 0xff, sizeof(int) * (size_t)c->n_global, st));
     const int nx = c->cur ^ 1;
     const float r_list = std::max(c->rc_lj, c->rc_q) + c->skin;
-    dd_reorder_kernel<<<div_up(n_all + 1, 256), 256, 0, st>>>(
+    MC_LAUNCH(dd_reorder_kernel, div_up(n_all + 1, 256), 256, 0, st, 
         (int)n_all, kk[which], vv[which], c->grid.p, cs->g_xyzq.p, cs->g_vel.p, cs->g_meta.p, c->skin < 0.5f * r_list ? 1 : 0,
         c->xyzq[nx].p, c->xref.p, c->vel[nx].p, c->type[nx].p, c->flags[nx].p, c->orig[nx].p, c->slot_of_orig.p,
         c->cell_start.p, (uint32_t)cs->local_cap);
     const int plane = c->h_grid.nc[0] * c->h_grid.nc[1];
-    dd_layer_offsets_kernel<<<1, 32, 0, st>>>(c->cell_start.p, plane, c->h_grid.nc[2], (uint32_t)nx, c->rebuild_flag.p + 3, cs->d_layer.p);
+    MC_LAUNCH(dd_layer_offsets_kernel, 1, 32, 0, st, c->cell_start.p, plane, c->h_grid.nc[2], (uint32_t)nx, c->rebuild_flag.p + 3, cs->d_layer.p);
     c->launches += 2;
     // every rank's record travels with this rank's: the fused halo and the next migration need the neighbours'
     // block offsets (one 64-byte all-gather per rebuild)

@@ -4,6 +4,7 @@
 #pragma once
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -25,9 +26,12 @@ struct NcclApi {
 inline NcclApi &nccl_api() {
     static NcclApi api;
     if (api.ok || !api.err.empty()) return api;
-    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // an NCCL this process already loaded
-    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    // MOLCHANICA_NCCL_LIB names the library explicitly (the host build of tests/cpp/host_lib/ points it at a
+    // shared-memory stand-in with the same ten entry points)
+    const char *forced = getenv("MOLCHANICA_NCCL_LIB");
+    void *h = forced ? dlopen(forced, RTLD_NOW | RTLD_GLOBAL) : dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // else: an NCCL this process already loaded
+    if (!h && !forced) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h && !forced) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!h) { api.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return api; }
 #define MC_SYM(field, name)                                                              \
     api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name));                   \

@@ -1,7 +1,7 @@
 #!/bin/bash
-# Test infrastructure: builds the WHOLE library for the host (no GPU, no nvcc): every .cu of molchanica_b200/csrc except
-# comm.cu is compiled by g++ over tests/cpp/shim_fiber/cuda_runtime.h, linked with the fiber runtime and the comm stub
-# into tests/cpp/_build/libmolchanica_md_host.so; a plain-DFT stand-in for cuFFT goes next to it.
+# Test infrastructure: builds the WHOLE library for the host (no GPU, no nvcc): every .cu of molchanica_b200/csrc is
+# compiled by g++ over tests/cpp/shim_fiber/cuda_runtime.h and linked with the fiber runtime into
+# tests/cpp/_build/libmolchanica_md_host.so; a plain-DFT stand-in for cuFFT and a shared-memory stand-in for NCCL go next to it.
 # MOLCHANICA_MD_LIB=<that .so> makes molchanica_b200/_lib.py load it (tests/test_library_on_host.py).
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -19,7 +19,7 @@ fi
 CXX=/usr/bin/g++; [ -x "$CXX" ] || CXX=g++
 mkdir -p "$OBJ"
 FLAGS="-O1 -g -std=c++20 -pthread -fPIC -ffp-contract=off -Wno-unknown-pragmas -Wno-attributes -DMC_HOST_SHIM=1 -I$ROOT/tests/cpp/shim_fiber $SAN"
-SRCS="sort_scan neighbor tile_build pair_force integrate thermostat dock dock_filter dock_poses bonded settle pme pme_params group_energy engine"
+SRCS="sort_scan neighbor tile_build pair_force integrate thermostat dock dock_filter dock_poses bonded settle pme pme_params group_energy engine comm"
 pids=()
 for s in $SRCS; do
   src="$ROOT/molchanica_b200/csrc/$s.cu"
@@ -30,11 +30,10 @@ for s in $SRCS; do
 done
 $CXX $FLAGS -c "$ROOT/tests/cpp/shim_fiber/runtime.cpp" -o "$OBJ/runtime.o" &
 pids+=($!)
-$CXX $FLAGS -c "$HERE/comm_stub.cpp" -o "$OBJ/comm_stub.o" &
-pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 objs=""
-for s in $SRCS runtime comm_stub; do objs="$objs $OBJ/$s.o"; done
+for s in $SRCS runtime; do objs="$objs $OBJ/$s.o"; done
 $CXX -shared -pthread $SAN -o "$OUT/$NAME.so" $objs -ldl
 $CXX -O2 -std=c++17 -fPIC -shared -o "$OUT/libcufft_standin.so" "$HERE/cufft_standin.cpp"
+$CXX -O2 -std=c++20 -fPIC -shared -pthread -o "$OUT/libnccl_standin.so" "$HERE/nccl_standin.cpp" -lrt
 echo "$OUT/$NAME.so"

@@ -255,6 +255,19 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return cudaSuccess; }
 
+// ---- no peer memory on the host stand-in: every rank is its own process with its own heap
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1, cudaEnableDefault = 0, cudaErrorNotSupported = 801 };
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+static inline cudaError_t cudaGetDriverEntryPoint(const char *, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *q = nullptr) {
+    *fn = nullptr;
+    if (q) *q = cudaDriverEntryPointSymbolNotFound;
+    return cudaErrorNotSupported;
+}
+
 // ---- mbarrier / bulk copy / named barrier (tile_build.cu), cooperative versions ---------------------------------------------------
 void shim_mbar_init(uint64_t *bar, uint32_t count);
 void shim_mbar_arrive(uint64_t *bar, uint32_t tx_bytes);

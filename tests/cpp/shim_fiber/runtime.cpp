@@ -393,9 +393,9 @@ cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind)
 cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { if (bytes) memmove(dst, src, bytes); return cudaSuccess; }
 cudaError_t cudaMemset(void *p, int v, size_t bytes) { if (bytes) memset(p, v, bytes); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *p, int v, size_t bytes, cudaStream_t) { if (bytes) memset(p, v, bytes); return cudaSuccess; }
-cudaError_t cudaSetDevice(int dev) { return dev == 0 ? cudaSuccess : (g_last_error = cudaErrorInvalidValue); }
+cudaError_t cudaSetDevice(int dev) { return dev >= 0 && dev < 8 ? cudaSuccess : (g_last_error = cudaErrorInvalidValue); }  // ranks of a decomposed run name devices 0..7
 cudaError_t cudaGetDevice(int *dev) { *dev = 0; return cudaSuccess; }
-cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int *n) { *n = 8; return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     memset(p, 0, sizeof(*p));
     snprintf(p->name, sizeof(p->name), "host stand-in (tests/cpp/shim_fiber)");
@@ -415,6 +415,7 @@ const char *cudaGetErrorString(cudaError_t e) {
         case cudaErrorMemoryAllocation: return "out of memory";
         case cudaErrorInvalidValue: return "invalid argument";
         case cudaErrorNotReady: return "device not ready";
+        case 801: return "operation not supported (host stand-in)";
         default: return "unknown error (host stand-in)";
     }
 }

@@ -1,4 +1,4 @@
-"""The WHOLE library on the CPU.  tests/cpp/host_lib/build.sh compiles every .cu of molchanica_b200/csrc except comm.cu
+"""The WHOLE library on the CPU.  tests/cpp/host_lib/build.sh compiles every .cu of molchanica_b200/csrc
 with g++ over tests/cpp/shim_fiber/cuda_runtime.h (threads of a block = fibers, warp collectives / __syncthreads /
 mbarrier + bulk copy emulated, cudaMalloc = host memory poisoned with 0xFF) into libmolchanica_md_host.so; with
 MOLCHANICA_MD_LIB pointing at it the GPU parity tests run unchanged -- same Python harness, same C ABI, same engine.cu
@@ -54,6 +54,41 @@ def test_components_not_yet_run_on_hardware_pass_on_the_host_build(worker, host_
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
     assert isinstance(res, dict) and res
+
+
+@pytest.mark.parametrize("case,world,sched", [("lj", 2, "fixed"), ("lj", 2, "allgather"), ("lj", 4, "fixed"), ("lj", 4, "adaptive")])
+def test_decomposed_run_on_the_host_build(case, world, sched, host_env, oracle):
+    """The multi-GPU path too: one PROCESS per rank as on the GPUs (tests/dd_worker.py, unchanged), comm.cu compiled for the
+    host, NCCL replaced by a shared-memory stand-in behind the same dlopen (tests/cpp/host_lib/nccl_standin.cpp).  Slab
+    decomposition, ghost selection, neighbour-only migration and all-gather rebuilds, the per-step ghost refresh with
+    ncclSend / ncclRecv, rank-local snapshots: same checks as tests/test_gpu_multi.py.  (Peer memory does not exist between
+    host processes: the fused halo is only seen on hardware; its flag protocol is model-checked in test_halo_protocol_model.py.)"""
+    import tempfile
+
+    import numpy as np
+    sys.path.insert(0, HERE)
+    from dd_worker import case_workload
+    from util import FORCE_RTOL, energy_close, force_rel_err, trajectory_close
+    env = dict(host_env, MOLCHANICA_NCCL_LIB=os.path.join(HERE, "cpp", "_build", "libnccl_standin.so"), MC_SHIM_THREADS="2")
+    d = tempfile.mkdtemp()
+    idf, out = os.path.join(d, "nccl_id"), os.path.join(d, "out.npz")
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dd_worker.py"), str(r), str(world), idf, case, out, "nccl", sched],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT) for r in range(world)]
+    logs = [p.communicate(timeout=900)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    r = np.load(out)
+    w, n_steps = case_workload(case, world)
+    assert int(r["fused"]) == 0
+    nb = oracle.neighbors(w)
+    f64, scale, en = oracle.forces(w, nb, precision=64)
+    assert force_rel_err(r["f0"], f64, scale).max() < FORCE_RTOL
+    assert energy_close(float(r["e_pot"]), en.sum(), f64[:, 3])
+    ref = oracle.md_run(w, n_steps, precision=64)
+    ok, worst, sc = trajectory_close(r["x"], ref["xyzq"], w["xyzq"], w["box_ext"])
+    assert ok, (worst, sc)
+    assert int(r["violations"]) == 0 and bool(r["snap_ok"])
+    assert int(r["n_owned"]) < len(w["xyzq"]) and int(r["n_ghosts"]) > 0
+    assert int(r["rebuilds"]) >= 2
 
 
 def test_cpp_host_mirror_runs_on_the_host_build(host_env, tmp_path):
