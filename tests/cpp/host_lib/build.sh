@@ -33,7 +33,7 @@ pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 objs=""
 for s in $SRCS runtime; do objs="$objs $OBJ/$s.o"; done
-$CXX -shared -pthread $SAN -o "$OUT/$NAME.so" $objs -ldl
+$CXX -shared -pthread $SAN -o "$OUT/$NAME.so" $objs -ldl -lrt
 $CXX -O2 -std=c++17 -fPIC -shared -o "$OUT/libcufft_standin.so" "$HERE/cufft_standin.cpp"
 $CXX -O2 -std=c++20 -fPIC -shared -pthread -o "$OUT/libnccl_standin.so" "$HERE/nccl_standin.cpp" -lrt
 echo "$OUT/$NAME.so"

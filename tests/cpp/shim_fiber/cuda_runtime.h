@@ -16,6 +16,7 @@
  */
 #pragma once
 #include <math.h>
+#include <sched.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -204,7 +205,7 @@ static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline long long max(long long a, long long b) { return a > b ? a : b; }
 static inline size_t min(size_t a, size_t b) { return a < b ? a : b; }
 static inline size_t max(size_t a, size_t b) { return a > b ? a : b; }
-static inline void __nanosleep(unsigned) { shim_yield_block(); }
+static inline void __nanosleep(unsigned) { shim_yield_block(); sched_yield(); }  // a spin on memory another warp, block or PROCESS writes
 
 // ---- host runtime (runtime.cpp) -------------------------------------------------------------------------------------------
 typedef int cudaError_t;
@@ -255,18 +256,16 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return cudaSuccess; }
 
-// ---- no peer memory on the host stand-in: every rank is its own process with its own heap
+// ---- peer memory between the processes of a decomposed host run (runtime.cpp): with MC_SHIM_SHARED_HEAP=1 "device"
+// memory comes from a shared-memory arena per process, an IPC handle names (process, offset), opening it maps the
+// exporter's arena.  Without the variable the calls fail and comm.cu falls back to the NCCL halo.
 struct cudaIpcMemHandle_t { char reserved[64]; };
 enum { cudaIpcMemLazyEnablePeerAccess = 1, cudaEnableDefault = 0, cudaErrorNotSupported = 801 };
 enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
-static inline cudaError_t cudaGetDriverEntryPoint(const char *, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *q = nullptr) {
-    *fn = nullptr;
-    if (q) *q = cudaDriverEntryPointSymbolNotFound;
-    return cudaErrorNotSupported;
-}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *base);
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags);
+cudaError_t cudaIpcCloseMemHandle(void *p);
+cudaError_t cudaGetDriverEntryPoint(const char *name, void **fn, unsigned long long flags, cudaDriverEntryPointQueryResult *q = nullptr);
 
 // ---- mbarrier / bulk copy / named barrier (tile_build.cu), cooperative versions ---------------------------------------------------
 void shim_mbar_init(uint64_t *bar, uint32_t count);

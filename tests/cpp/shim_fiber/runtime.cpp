@@ -7,8 +7,11 @@
 // warp resumes one lane past the lane that left it, so no lane starves.  A thread that exits counts as arrived at every
 // barrier it no longer reaches.  The blocks of a launch are handed out to a small pool of OS threads.
 #include "cuda_runtime.h"
+#include "cuda.h"
 
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <condition_variable>
@@ -379,16 +382,118 @@ void shim_mbar_wait(uint64_t *bar, uint32_t parity) {
 struct ShimStream { int id; };
 struct ShimEvent { std::chrono::steady_clock::time_point t; bool recorded = false; };
 
+// ---- "device" memory.  Default: the process heap.  MC_SHIM_SHARED_HEAP=1 (decomposed runs, one process per rank): a
+// shared-memory arena per process (bump allocator, nothing is returned before exit), so that a neighbour rank can map it
+// and the peer-memory halo of comm.cu / halo_sync.cuh -- stores into the neighbour's arrays, flag words, spins -- runs
+// between host processes the way it runs over NVLink.
+namespace {
+constexpr size_t ARENA_BYTES = (size_t)4 << 30;  // virtual; pages exist once touched
+struct Arena {
+    char *base = nullptr;
+    size_t used = 0;
+    char name[64] = {0};
+    std::mutex mu;
+    std::map<uintptr_t, size_t> allocs;            // base address -> size
+    std::map<int, char *> peers;                   // pid -> where that process's arena is mapped here
+};
+Arena &arena() { static Arena *a = new Arena(); return *a; }
+bool shared_heap() { static const bool on = getenv("MC_SHIM_SHARED_HEAP") && atoi(getenv("MC_SHIM_SHARED_HEAP")) != 0; return on; }
+void arena_unlink() { if (arena().name[0]) shm_unlink(arena().name); }
+bool arena_init() {
+    Arena &a = arena();
+    if (a.base) return true;
+    snprintf(a.name, sizeof(a.name), "/mc_shim_heap_%d", (int)getpid());
+    shm_unlink(a.name);
+    const int fd = shm_open(a.name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)ARENA_BYTES) != 0) return false;
+    void *m = mmap(nullptr, ARENA_BYTES, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_NORESERVE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return false;
+    a.base = static_cast<char *>(m);
+    atexit(arena_unlink);
+    return true;
+}
+struct IpcHandle { uint32_t magic; int pid; uint64_t offset; };
+CUresult shim_mem_get_address_range(CUdeviceptr *base, size_t *size, CUdeviceptr p) {
+    Arena &a = arena();
+    std::lock_guard<std::mutex> lk(a.mu);
+    auto it = a.allocs.upper_bound((uintptr_t)p);
+    if (it == a.allocs.begin()) return 1;
+    --it;
+    if ((uintptr_t)p >= it->first + it->second) return 1;
+    *base = it->first;
+    *size = it->second;
+    return CUDA_SUCCESS;
+}
+}  // namespace
+
 cudaError_t shim_malloc(void **p, size_t bytes) {
     if (bytes == 0) bytes = 16;
+    bytes = (bytes + 255) & ~(size_t)255;
     void *q = nullptr;
-    if (posix_memalign(&q, 256, (bytes + 255) & ~(size_t)255) != 0) { *p = nullptr; return g_last_error = cudaErrorMemoryAllocation; }
+    if (shared_heap()) {
+        Arena &a = arena();
+        std::lock_guard<std::mutex> lk(a.mu);
+        if (!arena_init() || a.used + bytes > ARENA_BYTES) { *p = nullptr; return g_last_error = cudaErrorMemoryAllocation; }
+        q = a.base + a.used;
+        a.used += bytes;
+        a.allocs[(uintptr_t)q] = bytes;
+    } else if (posix_memalign(&q, 256, bytes) != 0) {
+        *p = nullptr;
+        return g_last_error = cudaErrorMemoryAllocation;
+    }
     memset(q, 0xFF, bytes);
     *p = q;
     return cudaSuccess;
 }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
-cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void *p) {
+    if (!shared_heap()) free(p);  // the arena only grows: short test runs
+    return cudaSuccess;
+}
+cudaError_t cudaFreeHost(void *p) { return cudaFree(p); }
+
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *base) {
+    if (!shared_heap()) return cudaErrorNotSupported;
+    Arena &a = arena();
+    std::lock_guard<std::mutex> lk(a.mu);
+    if (!a.allocs.count((uintptr_t)base)) return g_last_error = cudaErrorInvalidValue;
+    memset(h, 0, sizeof(*h));
+    const IpcHandle v{0x4D43u, (int)getpid(), (uint64_t)(static_cast<char *>(base) - a.base)};
+    memcpy(h->reserved, &v, sizeof(v));
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+    if (!shared_heap()) return cudaErrorNotSupported;
+    IpcHandle v;
+    memcpy(&v, h.reserved, sizeof(v));
+    if (v.magic != 0x4D43u) return g_last_error = cudaErrorInvalidValue;
+    Arena &a = arena();
+    std::lock_guard<std::mutex> lk(a.mu);
+    char *&map = a.peers[v.pid];
+    if (!map) {
+        char name[64];
+        snprintf(name, sizeof(name), "/mc_shim_heap_%d", v.pid);
+        const int fd = shm_open(name, O_RDWR, 0600);
+        if (fd < 0) return g_last_error = cudaErrorInvalidValue;
+        void *m = mmap(nullptr, ARENA_BYTES, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_NORESERVE, fd, 0);
+        close(fd);
+        if (m == MAP_FAILED) return g_last_error = cudaErrorMemoryAllocation;
+        map = static_cast<char *>(m);
+    }
+    *p = map + v.offset;
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }  // mappings of a peer's arena stay until exit
+cudaError_t cudaGetDriverEntryPoint(const char *name, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *q) {
+    if (shared_heap() && strcmp(name, "cuMemGetAddressRange") == 0) {
+        *fn = reinterpret_cast<void *>(&shim_mem_get_address_range);
+        if (q) *q = cudaDriverEntryPointSuccess;
+        return cudaSuccess;
+    }
+    *fn = nullptr;
+    if (q) *q = cudaDriverEntryPointSymbolNotFound;
+    return cudaErrorNotSupported;
+}
 cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind) { if (bytes) memmove(dst, src, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { if (bytes) memmove(dst, src, bytes); return cudaSuccess; }
 cudaError_t cudaMemset(void *p, int v, size_t bytes) { if (bytes) memset(p, v, bytes); return cudaSuccess; }

@@ -56,29 +56,35 @@ def test_components_not_yet_run_on_hardware_pass_on_the_host_build(worker, host_
     assert isinstance(res, dict) and res
 
 
-@pytest.mark.parametrize("case,world,sched", [("lj", 2, "fixed"), ("lj", 2, "allgather"), ("lj", 4, "fixed"), ("lj", 4, "adaptive")])
-def test_decomposed_run_on_the_host_build(case, world, sched, host_env, oracle):
+@pytest.mark.parametrize("case,world,halo,sched", [("lj", 2, "nccl", "fixed"), ("lj", 2, "nccl", "allgather"), ("lj", 4, "nccl", "fixed"),
+                                                   ("lj", 2, "fused", "fixed"), ("lj", 2, "fused", "adaptive"), ("lj", 4, "fused", "fixed"),
+                                                   ("lj", 4, "fused", "adaptive")])
+def test_decomposed_run_on_the_host_build(case, world, halo, sched, host_env, oracle):
     """The multi-GPU path too: one PROCESS per rank as on the GPUs (tests/dd_worker.py, unchanged), comm.cu compiled for the
     host, NCCL replaced by a shared-memory stand-in behind the same dlopen (tests/cpp/host_lib/nccl_standin.cpp).  Slab
     decomposition, ghost selection, neighbour-only migration and all-gather rebuilds, the per-step ghost refresh with
-    ncclSend / ncclRecv, rank-local snapshots: same checks as tests/test_gpu_multi.py.  (Peer memory does not exist between
-    host processes: the fused halo is only seen on hardware; its flag protocol is model-checked in test_halo_protocol_model.py.)"""
+    ncclSend / ncclRecv, rank-local snapshots: same checks as tests/test_gpu_multi.py.
+    halo = fused: with MC_SHIM_SHARED_HEAP=1 the stand-in's "device" memory is a shared-memory arena per process and the
+    cudaIpc calls map a neighbour's arena, so the peer-memory halo itself runs between the host processes: kick_drift<true>
+    stores its boundary layers into the neighbour's arrays and raises the epoch flags, the boundary blocks of the pair kernel
+    spin on them (halo_sync.cuh), the adaptive interval follows the all-gathered largest displacement."""
     import tempfile
 
     import numpy as np
     sys.path.insert(0, HERE)
     from dd_worker import case_workload
     from util import FORCE_RTOL, energy_close, force_rel_err, trajectory_close
-    env = dict(host_env, MOLCHANICA_NCCL_LIB=os.path.join(HERE, "cpp", "_build", "libnccl_standin.so"), MC_SHIM_THREADS="2")
+    env = dict(host_env, MOLCHANICA_NCCL_LIB=os.path.join(HERE, "cpp", "_build", "libnccl_standin.so"), MC_SHIM_THREADS="2",
+               MC_SHIM_SHARED_HEAP="1" if halo == "fused" else "0")
     d = tempfile.mkdtemp()
     idf, out = os.path.join(d, "nccl_id"), os.path.join(d, "out.npz")
-    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dd_worker.py"), str(r), str(world), idf, case, out, "nccl", sched],
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dd_worker.py"), str(r), str(world), idf, case, out, halo, sched],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT) for r in range(world)]
     logs = [p.communicate(timeout=900)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
     r = np.load(out)
     w, n_steps = case_workload(case, world)
-    assert int(r["fused"]) == 0
+    assert int(r["fused"]) == (1 if halo == "fused" else 0), str(r["why"])
     nb = oracle.neighbors(w)
     f64, scale, en = oracle.forces(w, nb, precision=64)
     assert force_rel_err(r["f0"], f64, scale).max() < FORCE_RTOL
@@ -89,6 +95,8 @@ def test_decomposed_run_on_the_host_build(case, world, sched, host_env, oracle):
     assert int(r["violations"]) == 0 and bool(r["snap_ok"])
     assert int(r["n_owned"]) < len(w["xyzq"]) and int(r["n_ghosts"]) > 0
     assert int(r["rebuilds"]) >= 2
+    if sched == "adaptive":
+        assert int(r["interval"]) >= 10 and int(r["rebuilds"]) >= 3 and 0.0 < float(r["disp_frac"]) < 1.0
 
 
 def test_cpp_host_mirror_runs_on_the_host_build(host_env, tmp_path):
