@@ -3,6 +3,7 @@
 // __graft_entry__.build(), run on the GPU box by tests/test_gpu_cpp_host.py.
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 
 #include "molchanica_md.hpp"
 
@@ -13,7 +14,10 @@ static int fail(const char *what, double got, double want) {
     return 1;
 }
 
-int main() {
+// --npt adds the part written after the last hardware run of round 1 (thermostat + barostat + drift removal, pressure,
+// snapshots with velocities): tests/test_library_on_host.py runs it against the host build, tests/newpaths_md.py on a GPU.
+int main(int argc, char **argv) {
+    const bool with_npt = argc > 1 && std::strcmp(argv[1], "--npt") == 0;
     ComputationDevice dev{0};
     try {
         // two argon atoms at the LJ minimum: E = -eps, F = 0; then at r = sigma: E = 0, |F| = 24 eps / sigma
@@ -54,7 +58,7 @@ int main() {
         }
         // NPT the way properties/crystal.rs:306-316 configures it: thermostat + zero_com_drift + barostat, on a small
         // periodic argon lattice; the box must shrink towards a target far above the starting pressure
-        {
+        if (with_npt) {
             MdConfig npt = cfg;
             const int m = 6;
             const float a = 3.6f, L = a * m;

@@ -321,3 +321,22 @@ def test_pressure_refuses_what_it_cannot_do(Engine):
     with pytest.raises(McError, match="take a step first"):   # the constraint virial is that of the last step
         e.pressure()
     e.close()
+
+
+def test_cpp_host_mirror_npt_configuration():
+    """include/molchanica_md.hpp configured the way properties/crystal.rs:306-316 configures `dynamics` (thermostat, drift
+    removal, barostat), pressure in the energy snapshot, snapshots with velocities: tests/cpp/host_mirror_smoke.cpp --npt
+    against whichever library this process uses."""
+    import os
+    import subprocess
+    import tempfile
+
+    import __graft_entry__ as g
+    from molchanica_b200 import _lib
+    g.build_cpp_host()
+    here = os.path.dirname(os.path.abspath(__file__))
+    d = tempfile.mkdtemp()
+    os.symlink(_lib.LIB_PATH, os.path.join(d, "libmolchanica_md.so"))
+    env = dict(os.environ, LD_LIBRARY_PATH=d + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([os.path.join(here, "cpp", "_build", "host_mirror_smoke"), "--npt"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "host mirror ok" in r.stdout, r.stdout + r.stderr

@@ -106,7 +106,7 @@ def test_cpp_host_mirror_runs_on_the_host_build(host_env, tmp_path):
     g.build_cpp_host()
     os.symlink(host_env["MOLCHANICA_MD_LIB"], tmp_path / "libmolchanica_md.so")
     env = dict(host_env, LD_LIBRARY_PATH=str(tmp_path) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-    r = subprocess.run([os.path.join(HERE, "cpp", "_build", "host_mirror_smoke")], capture_output=True, text=True, env=env, timeout=300)
+    r = subprocess.run([os.path.join(HERE, "cpp", "_build", "host_mirror_smoke"), "--npt"], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "host mirror ok" in r.stdout, r.stdout + r.stderr
 
 
