@@ -21,6 +21,11 @@ def case_workload(name, world=2):
         w = W.solvated_c3()
         w["coul_mode"] = 2  # continuous at the cutoff: trajectories are comparable
         return w, 6
+    if name == "ljx":
+        # fuzzing hook (tests/test_library_on_host.py, manual sweeps): DD_M atoms per edge, DD_TEMP K, DD_SKIN A, DD_STEPS
+        w = W.lj_fluid(m=int(os.environ.get("DD_M", "24")), temp_k=float(os.environ.get("DD_TEMP", "86.3")))
+        w["skin"] = float(os.environ.get("DD_SKIN", w["skin"]))
+        return w, int(os.environ.get("DD_STEPS", "30"))
     raise ValueError(name)
 
 
@@ -53,7 +58,7 @@ def main():
     e.set_pairs14(w.get("pairs14"), w.get("scale14_lj", 0.5), w.get("scale14_q", 1 / 1.2))
     e.set_option("halo_fused", 1 if halo == "fused" else 0)
     # the unbonded solvated system has very fast hydrogens; "adaptive" leaves the interval to the engine
-    e.set_option("rebuild_every", 0 if sched == "adaptive" else (5 if case == "lj" else 2))
+    e.set_option("rebuild_every", 0 if sched == "adaptive" else int(os.environ.get("DD_EVERY", "5")) if case in ("lj", "ljx") else 2)
     e.set_option("dd_migrate", 0 if sched == "allgather" else 1)
     e.compute_forces()
     f0 = e.forces()
