@@ -225,3 +225,34 @@ def test_random_boxes_cutoffs_and_grids(seed, Engine, oracle):
         assert err[rmin >= 2.0].max(initial=0.0) < FORCE_RTOL, seed
         assert err.max() < 2e-4, seed
     e.close()
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("MC_FUZZ_SEEDS", "6"))))
+def test_the_list_never_misses_an_interacting_pair(seed, Engine, oracle):
+    """The pipelined rebuild decision (flag raised with a look-ahead, acted upon one step late) under hot fluids, thin skins
+    and calls of random length: whenever the caller looks, every pair inside the force cutoff is in the list the engine
+    is using -- the property the displacement criterion exists for."""
+    rng = np.random.default_rng(500 + seed)
+    w = W.lj_fluid(m=int(rng.integers(9, 13)), temp_k=float(rng.choice([150.0, 400.0, 900.0, 1500.0])))
+    w["skin"] = float(rng.choice([0.3, 0.5, 1.0]))
+    e = Engine.from_workload(w)
+    n = len(w["xyzq"])
+    from molchanica_b200.engine import McError
+    checked = 0
+    for _ in range(14):
+        e.step(w["dt"], int(rng.integers(1, 18)))
+        try:
+            start, idx = e.neighbors()                    # the list the last force evaluation used
+        except McError as ex:                             # the engine has just flagged it itself: nothing stale can be in use
+            assert "no current list" in str(ex)
+            e.build_neighbors()
+            continue
+        checked += 1
+        x = e.positions()
+        ws = dict(w, xyzq=x, skin=0.0)
+        c_start, c_idx = oracle.neighbors(ws)             # pairs inside the force cutoff right now
+        have = set(zip(np.repeat(np.arange(n), np.diff(start)).tolist(), idx.tolist()))
+        need = set(zip(np.repeat(np.arange(n), np.diff(c_start)).tolist(), c_idx.tolist()))
+        assert not (need - have), (seed, len(need - have))
+    assert e.stats()["n_rebuilds"] >= 3 and checked >= 4
+    e.close()
