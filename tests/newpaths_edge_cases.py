@@ -256,3 +256,55 @@ def test_the_list_never_misses_an_interacting_pair(seed, Engine, oracle):
         assert not (need - have), (seed, len(need - have))
     assert e.stats()["n_rebuilds"] >= 3 and checked >= 4
     e.close()
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("MC_FUZZ_SEEDS", "2"))))
+def test_features_in_random_combination_follow_the_oracle(seed, Engine, oracle):
+    """Static atoms, external forces that change from call to call, exclusions + scaled 1-4 pairs, plain and Ewald real-space Coulomb,
+    vacuum and periodic systems, calls of random length, the pipelined upload on or off -- drawn at random together; the
+    trajectory and the final forces are the oracle's."""
+    from util import trajectory_close
+    rng = np.random.default_rng(900 + seed)
+    if rng.integers(0, 2):
+        w = dict(W.globule(int(rng.integers(150, 500)), seed=int(rng.integers(0, 1000))))
+    else:
+        w = dict(W.water_box_c1())
+        w["dt"] = 0.0005
+    w["coul_mode"] = int(rng.choice([1, 2])) if w["periodic"] else 1
+    n = len(w["xyzq"])
+    flags = (rng.uniform(0, 1, n) < rng.choice([0.0, 0.03, 0.1])).astype(np.uint8)
+    w["flags"] = flags
+    w["vel"] = w["vel"].copy()
+    w["vel"][flags == 1, :3] = 0.0
+    e = Engine.from_workload(w)
+    bonded = bool(w["periodic"])                             # the water box is flexible water: harmonic O-H / H-H bonds keep it together
+    if bonded:
+        e.set_bonded(w["bonds"], w["bond_kr0"])
+    e.set_option("defer_tail", int(rng.integers(0, 2)))
+    vel_o = w["vel"].copy()
+    vel_o[flags == 1, 3] = 0.0                               # the oracle knows static atoms as atoms of infinite mass
+    cur = dict(w, vel=vel_o)
+    total = 0
+    for _ in range(int(rng.integers(2, 6))):
+        k = int(rng.integers(1, 9))
+        ext = None
+        if rng.integers(0, 3):
+            ext = np.zeros((n, 3), np.float32)
+            sel = rng.uniform(0, 1, n) < 0.2
+            ext[sel] = rng.normal(0, 4.0, (int(sel.sum()), 3))
+        e.step(w["dt"], k, ext_forces=ext)
+        r = oracle.md_run(cur, k, precision=64, ext_force=ext, with_bonds=bonded)
+        cur = dict(cur, xyzq=r["xyzq"], vel=r["vel"])
+        total += k
+    x = e.positions()
+    x0 = np.asarray(w["xyzq"], np.float32)[:, :3]
+    if np.abs(cur["xyzq"][:, :3] - x0).max() > 3.0:
+        # a random pull on an unbonded chain now and then throws atoms out at km/s: chaos, no trajectory to compare --
+        # the engine must have seen the same explosion, not a different physics
+        assert np.abs(x[:, :3] - x0).max() > 1.0, seed
+        e.close()
+        return
+    ok, worst, scale = trajectory_close(x, cur["xyzq"], w["xyzq"], w["box_ext"] if w["periodic"] else None)
+    assert ok, (seed, worst, scale)
+    assert np.array_equal(x[flags == 1], np.asarray(w["xyzq"], np.float32)[flags == 1])
+    e.close()
