@@ -308,3 +308,20 @@ def test_features_in_random_combination_follow_the_oracle(seed, Engine, oracle):
     assert ok, (seed, worst, scale)
     assert np.array_equal(x[flags == 1], np.asarray(w["xyzq"], np.float32)[flags == 1])
     e.close()
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("MC_FUZZ_SEEDS", "8"))))
+def test_docking_scan_random_sizes(seed, Engine, oracle):
+    """Receptor / ligand / pose counts that are not multiples of anything (1 .. 1200 receptor atoms, 1 .. 60 ligand atoms,
+    1 .. 40 poses): per-pose terms against the fp64 oracle at the bars of tests/test_gpu_dock.py."""
+    rng = np.random.default_rng(300 + seed)
+    d = W.docking_c5(n_rec=int(rng.integers(1, 1200)), n_lig=int(rng.integers(1, 60)), n_poses=int(rng.integers(1, 40)),
+                     seeds=(int(rng.integers(0, 999)), int(rng.integers(0, 999)), int(rng.integers(0, 999))))
+    e = Engine()
+    got = e.dock_score(d)
+    e.close()
+    ref, ref_abs = oracle.dock_score(d, precision=64, with_abs=True)
+    assert np.all(np.abs(got[:, 1] - ref[:, 1]) <= 1e-5 * ref_abs[:, 0] + 1e-6)
+    assert np.all(np.abs(got[:, 2] - ref[:, 2]) <= 1e-5 * np.abs(ref[:, 2]) + 1e-5)
+    assert np.all(np.abs(got[:, 3] - ref[:, 3]) <= 1e-5 * ref_abs[:, 1] + 1e-6)
+    assert np.all(np.abs(got[:, 4] - ref[:, 4]) <= 1e-5 * ref_abs[:, 2] + 1e-6)
