@@ -98,13 +98,22 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_arm(side, steps, warmup):
-    """The CPU path (oracle port, OpenMP over all host cores) on a bounded sample: the same
-    fluid at the same density in a side^3-atom box; ns/day is reported for the 1M-atom system by
-    scaling with atoms (the work per atom is identical)."""
+    """The CPU path (oracle port, OpenMP over all host cores) on the SAME workload: side = 100 is the full
+    1,000,000-atom C4 fluid; the sample is bounded in STEPS, not in atoms.  A smaller side (--cpu-side) runs the same
+    fluid at the same density in a side^3-atom box and scales by atoms (the work per atom is identical); the line says
+    which.  torchrun exports OMP_NUM_THREADS=1: the thread count is set explicitly to the cores this process may use."""
     from molchanica_b200 import workloads as W
     from oracle import oracle_py as O
     O.lib()
+    O.set_num_threads(host_cores())
     w = W.lj_fluid(m=side)
     n = len(w["xyzq"])
     st = O.md_run(w, warmup, precision=32)
@@ -113,10 +122,89 @@ def cpu_arm(side, steps, warmup):
     dt = time.perf_counter() - t0
     v_sample = ns_per_day(steps, dt)
     v_1m = v_sample * n / 1.0e6
-    return dict(value=v_1m, unit=UNIT, cores=O.num_threads(), kind="port",
-                sample=f"{n}-atom box of the same LJ fluid (side {side}), {steps} steps incl. list rebuilds, "
-                       f"{dt:.2f} s; scaled by atoms to 1M",
+    full = n == 1000000
+    return dict(value=v_1m, unit=UNIT, cores=O.num_threads(), kind="port", same_config=full,
+                sample=(f"the full {n}-atom C4 fluid, {steps} steps incl. list rebuilds after {warmup} warm-up steps, {dt:.2f} s"
+                        if full else
+                        f"{n}-atom box of the same LJ fluid (side {side}), {steps} steps incl. list rebuilds, {dt:.2f} s; "
+                        f"scaled by atoms to 1M"),
                 seconds=dt, steps=steps)
+
+
+def secondary_configs(peak_gbs):
+    """BASELINE.json configs 2, 3 and 5 on this GPU (one small block each, a few seconds in total): C2 steps/s in
+    batches of 10 like the GUI (reference src/md/mod.rs:45), C3 pair-force and list-build kernels individually,
+    C5 pose-energy scan in pair evaluations per second against the FP32 issue ceiling."""
+    from molchanica_b200 import workloads as W
+    from molchanica_b200.engine import MdEngine
+    out = {}
+    try:
+        w = W.globule(temp_k=100.0)
+        e = MdEngine.from_workload(w)
+        dt_run = 0.0002  # the synthetic globule has no bonded terms: a short step keeps it intact; cost per step is dt-independent
+        e.step(dt_run, 200)
+        s0 = e.stats()
+        t0 = time.perf_counter()
+        for _ in range(1000):
+            e.step(dt_run, 10)
+        el = time.perf_counter() - t0
+        s1 = e.stats()
+        out["C2"] = {"workload": f"{len(w['xyzq'])}-atom globule in vacuum, 10,000 steps in mc_step batches of 10", "steps_per_s": 10000 / el,
+                     "us_per_step": el / 10000 * 1e6, "ns_per_day_at_2fs": ns_per_day(10000, el),
+                     "launches_per_step": (s1["n_kernel_launches"] - s0["n_kernel_launches"]) / 10000.0,
+                     "rebuilds": int(s1["n_rebuilds"] - s0["n_rebuilds"])}
+        e.close()
+    except Exception as ex:  # noqa: BLE001
+        out["C2"] = {"error": str(ex)}
+    try:
+        w = W.solvated_c3()
+        e = MdEngine.from_workload(w)
+        e.set_option("profiling", 1)
+        for _ in range(3):
+            e.build_neighbors()
+        e.reset_timers()
+        for _ in range(10):
+            e.build_neighbors()
+        sb = e.stats()
+        pair_ms = e.time_pair_kernel(reps=50, flush_l2=True)
+        n, p = len(w["xyzq"]), sb["n_pairs_listed"]
+        alg = 32.0 * n + 20.0 * p
+        build_ms = sb["build_ms_sum"] / 10.0  # ten builds; each one is bracketed in two parts (sort + reorder, rows)
+        out["C3"] = {"workload": f"{n} atoms solvated, rc 12 A + 2 A skin, {p} list entries", "pair_kernel_ms": pair_ms,
+                     "pair_algorithmic_GBs": alg / pair_ms / 1e6, "pair_frac_of_measured_hbm": alg / pair_ms / 1e6 / peak_gbs,
+                     "list_build_ms": build_ms, "list_build_algorithmic_GBs": (120.0 * n + 4.0 * p) / max(build_ms, 1e-9) / 1e6,
+                     "builds_timed": int(sb["builds_timed"])}
+        e.close()
+    except Exception as ex:  # noqa: BLE001
+        out["C3"] = {"error": str(ex)}
+    try:
+        d = W.docking_c5()
+        e = MdEngine()
+        e.set_option("profiling", 1)
+        e.dock_score(d)
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            e.dock_score(d)
+        wall = (time.perf_counter() - t0) / reps
+        kms = e.last_dock_kernel_ms()
+        pairs = len(d["poses"]) * len(d["rec"]) * len(d["lig"])
+        # ceiling: 128 FP32 lanes/clk/SM x 148 SMs x max SM clock / issue slots per pair (counted in the SASS of the
+        # inner loop, tools/sass_count.sh -> profiles/dock_sass_r2.txt)
+        slots = DOCK_ISSUE_SLOTS_PER_PAIR
+        ceil = 128.0 * 148 * 1.965e9 / slots
+        out["C5"] = {"workload": f"{len(d['poses'])} poses x {len(d['rec'])} receptor x {len(d['lig'])} ligand atoms", "pair_evals": pairs,
+                     "kernel_ms": kms, "pair_evals_per_s": pairs / (kms * 1e-3), "e2e_ms_host_buffers": wall * 1e3,
+                     "poses_per_s_e2e": len(d["poses"]) / wall,
+                     "roofline": {"bound": "fp32 issue", "achieved": pairs / (kms * 1e-3), "peak": ceil, "unit": "pair-evals/s",
+                                  "frac": pairs / (kms * 1e-3) / ceil, "issue_slots_per_pair": slots}}
+        e.close()
+    except Exception as ex:  # noqa: BLE001
+        out["C5"] = {"error": str(ex)}
+    return out
+
+
+DOCK_ISSUE_SLOTS_PER_PAIR = 24.0  # inner loop of dock_score_kernel, see profiles/dock_sass_r2.txt
 
 
 def main():
@@ -126,9 +214,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--side", type=int, default=100, help="atoms per box edge (100 -> 1,000,000 atoms)")
-    ap.add_argument("--cpu-side", type=int, default=64)
+    ap.add_argument("--cpu-side", type=int, default=100, help="box edge of the CPU arm (100 = the full workload)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiler runs)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C2 / C3 / C5 blocks (profiler runs)")
+    ap.add_argument("--no-steady", action="store_true", help="skip the long steady-state window (profiler runs)")
     ap.add_argument("--no-profile", action="store_true", help="experiment: no CUDA events around the kernels")
     ap.add_argument("--profile-every", type=int, default=8)
     ap.add_argument("--lanes", type=int, default=0)
@@ -148,12 +238,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb = cpu_arm(args.cpu_side, min(K, 200), min(W_, 10))
+        ks, ws = min(K, 100), min(W_, 10)
+        cb = cpu_arm(args.cpu_side, ks, ws)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": cb["steps"], "warmup": min(W_, 10), "ms_per_step": cb["seconds"] / cb["steps"] * 1e3,
+                "steps": cb["steps"], "warmup": ws, "ms_per_step": cb["seconds"] / cb["steps"] * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "C4 1M-atom LJ fluid (argon, rho*=0.8442, rc=2.5 sigma, skin 1 A, dt 2 fs), "
-                                       "CPU restatement on a bounded sample"},
+                                       "CPU restatement of the path (oracle/md_oracle.c, OpenMP), " +
+                                       ("full size" if cb["same_config"] else "bounded sample scaled by atoms"),
+                           "same_config": cb["same_config"]},
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -197,8 +290,55 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident, CUDA events on the engine's stream around all K steps ----------
+    def all_max(x):
+        if world == 1:
+            return float(x)
+        tt = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def all_min_int(x):
+        if world == 1:
+            return int(x)
+        tt = torch.tensor([x], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+        return int(tt.item())
+
+    # ---- warm-up.  W steps as asked, then -- still untimed -- on until the run is in its steady state: at least three
+    # list rebuilds behind it (the first one is the initial all-gather build of a decomposed run, the second the first
+    # neighbour-only migration, whose NCCL channels are set up on first use; the adaptive interval of a decomposed run
+    # needs two builds to climb from its cautious start).  One step per call, so that the spacing of the rebuilds is seen.
     e.step(DT_PS, W_)
+    warm_total = W_
+    rebuild_at = []
+    nb_prev = e.stats()["n_rebuilds"]
+    since = None  # steps since the last observed rebuild
+    for _ in range(600):
+        if len(rebuild_at) >= 3:
+            break
+        e.step(DT_PS, 1)
+        warm_total += 1
+        nb = e.stats()["n_rebuilds"]
+        if since is not None:
+            since += 1
+        if nb != nb_prev:
+            rebuild_at.append(warm_total)
+            nb_prev = nb
+            since = 0
+    interval = e.schedule()[0] if world > 1 else (rebuild_at[-1] - rebuild_at[-2] if len(rebuild_at) >= 2 else 0)
+    interval = all_min_int(interval)
+    # A window shorter than the rebuild interval would otherwise be timed with or without a rebuild by accident of
+    # its phase (round 1: none).  Place it so that one rebuild falls inside: conservative (1 per K instead of 1 per
+    # interval), never flattering.  Every rank takes the same number of steps (decomposed runs are in lock-step).
+    align = 0
+    if since is not None and 0 < K < interval:
+        align = max(0, interval - max(K // 2, 1) - 1 - since)
+        align = all_min_int(align)
+        if align:
+            e.step(DT_PS, align)
+            warm_total += align
+
+    # ---- value: device-resident, CUDA events on the engine's stream around all K steps ----------
     e.set_option("profiling", 0 if args.no_profile else 1)
     e.set_option("profile_every", args.profile_every)  # CUDA-event pairs around every k-th step's kernels only
     e.reset_timers()
@@ -211,15 +351,26 @@ def main():
     e.step(DT_PS, K)
     barrier()
     wall = time.perf_counter() - t0
-    ms = e.last_step_ms()
-    clocks = sampler.stop() if rank == 0 else None
+    ms = all_max(e.last_step_ms())
     s1 = e.stats()
-    e.set_option("profiling", 0)
-    if world > 1:
-        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
     value = ns_per_day(K, ms * 1e-3)
+
+    # ---- steady state: the same measurement over a window of ~10 rebuild intervals (what a long run sees)
+    steady = None
+    if not args.no_steady:
+        ks = int(min(max(10 * max(interval, 1), 200), 400))
+        barrier()
+        e.step(DT_PS, ks)
+        barrier()
+        ms_s = all_max(e.last_step_ms())
+        s2 = e.stats()
+        steady = {"value": ns_per_day(ks, ms_s * 1e-3), "unit": UNIT, "steps": ks, "ms_per_step": ms_s / ks,
+                  "rebuilds": int(s2["n_rebuilds"] - s1["n_rebuilds"]),
+                  "rebuild_interval_steps": ks / max(int(s2["n_rebuilds"] - s1["n_rebuilds"]), 1)}
+    else:
+        s2 = s1
+    clocks = sampler.stop() if rank == 0 else None
+    e.set_option("profiling", 0)
 
     # ---- e2e: host buffers through the C ABI, one call per step, H2D + D2H inside the timing ----
     # per step: H2D of the step's external forces (the Some(forces) argument of MdState::step,
@@ -227,13 +378,14 @@ def main():
     # positions (what the viewer reads back, reference src/md/mod.rs:843-852) into pinned memory.
     e2e = None
     if not args.no_e2e:
-        # per step: mc_step(dt, 1, ext) with the step's external forces in pinned HOST memory (H2D inside; on a single GPU
-        # the upload runs on its own stream under the force evaluation the previous call left open -- engine.cu,
-        # option defer_tail, invisible through the ABI: tests/newpaths_md.py::test_pipelined_external_forces...), then
+        # per step: mc_step(dt, 1, ext) with the step's external forces in pinned HOST memory (H2D inside, on its own
+        # stream under the force evaluation the previous call left open -- engine.cu, option defer_tail, invisible
+        # through the ABI: tests/test_gpu_parity.py::test_pipelined_external_forces...), then
         # mc_snapshot_begin hands the new positions to a pinned HOST buffer (D2H inside, double-buffered so that
         # the copy of step s overlaps the kernels of step s+1 -- the Snapshot queue of the reference,
         # src/md/mod.rs:118-152); mc_snapshot_wait(s-1) before buffer reuse, all copies drained before the clock stops.
-        # A decomposed rank moves its own share: the full ext-force array in, its owned atoms + ids out.
+        # A decomposed rank moves its own share: the rows of the caller's external-force array that belong to the atoms
+        # it owns (gathered by the engine from the pinned array, see mc_step) in, its owned atoms + ids out.
         cap = n if world == 1 else int(3 * (n // world + n // (2 * world) + 4096))
         ext = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
         pos = [torch.empty((cap, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -250,66 +402,69 @@ def main():
             d2h = int(n_out.value) * (16 + (4 if world > 1 else 0))
             if k > 0:
                 e._chk(e._L.mc_snapshot_wait(e._h))
+
         def run_leg():
             for k in range(4):
                 one(k)
             e._chk(e._L.mc_snapshot_wait(e._h))
-            ke = min(K, 300)
+            ke = min(max(K, 100), 300)
+            sa = e.stats()
             barrier()
             t0 = time.perf_counter()
             for k in range(ke):
                 one(k)
             e._chk(e._L.mc_snapshot_wait(e._h))
             barrier()
-            te = time.perf_counter() - t0
-            if world > 1:
-                tt = torch.tensor([te], device="cuda", dtype=torch.float64)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                te = float(tt.item())
-            return {"value": ns_per_day(ke, te), "unit": UNIT, "h2d_bytes_per_step": int(ext.numel() * 4),
+            te = all_max(time.perf_counter() - t0)
+            sb = e.stats()
+            return {"value": ns_per_day(ke, te), "unit": UNIT, "h2d_bytes_per_step": int(e.ext_upload_bytes()),
                     "d2h_bytes_per_step": d2h, "steps": ke, "ms_per_step": te / ke * 1e3,
+                    "rebuilds": int(sb["n_rebuilds"] - sa["n_rebuilds"]),
                     "api": "mc_step(ctx, dt, 1, ext_forces) + mc_snapshot_begin(ctx, out, ids) / mc_snapshot_wait(ctx), pinned host "
                            "buffers; bytes are per rank"}
-        try:
-            if world == 1:
-                e.set_option("defer_tail", 0 if any(o.startswith("defer_tail=0") for o in args.opt) else 1)
-            e2e = run_leg()
-            if world == 1:
-                e2e["api"] += "; option defer_tail = " + ("0" if any(o.startswith("defer_tail=0") for o in args.opt) else "1 (pipelined upload)")
-        except Exception as ex:  # noqa: BLE001
-            if world > 1:
-                raise
-            # the pipelined upload of a single-GPU handle (option defer_tail) was written after this round's last hardware
-            # run: should it fail here, the line still carries the path that WAS measured, and says so
-            try:
-                e.set_option("defer_tail", 0)
-                e2e = run_leg()
-                e2e["note"] = f"pipelined upload failed ({ex}); measured with defer_tail = 0"
-            except Exception as ex2:  # noqa: BLE001
-                e2e = {"value": None, "unit": UNIT, "error": f"{ex}; then {ex2}"}
+        e.set_option("defer_tail", 0 if any(o.startswith("defer_tail=0") for o in args.opt) else 1)
+        e2e = run_leg()
+        e2e["api"] += "; option defer_tail = " + ("0" if any(o.startswith("defer_tail=0") for o in args.opt) else "1 (pipelined upload)")
 
-    # ---- roofline of the dominant kernel (pair force), live CUDA-event average over the timed region
-    pair_ms = (s1["pair_ms_sum"] - 0.0) / max(s1["pair_launches_timed"], 1)
-    p_full = s1["n_pairs_listed"]
-    n_rows = s1["n_atoms"]
+    # ---- roofline of the dominant kernel (pair force), live CUDA-event average over the timed regions
+    pair_ms = s2["pair_ms_sum"] / max(s2["pair_launches_timed"], 1)
+    p_full = s2["n_pairs_listed"]
+    n_rows = s2["n_atoms"]
     alg_bytes = 32.0 * n_rows + 20.0 * p_full
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
-    traffic = None
+    traffic = limiter = traffic_src = None
     tp = os.path.join(ROOT, "profiles", "pair_force_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic = tj.get("dram_bytes_per_launch")
+        limiter = tj.get("limiter")
+        traffic_src = tj.get("source")
+    n_rb = max(s2["n_rebuilds"] - s0["n_rebuilds"], 1)
+    rebuild_ms = s2["build_ms_sum"] / n_rb
+    build_alg = 120.0 * n_rows + 4.0 * p_full
+    # `frac` follows SURVEY 8d literally: ALGORITHMIC bytes (32 N + 20 P: every listed pair counted as a 16-byte gather + a
+    # 4-byte index) over the kernel time.  It can exceed 1: the gathers are served on chip (shared-memory tile / L1), DRAM
+    # only carries the index stream and one pass over the positions.  `dram_frac` is the physical one: measured DRAM bytes
+    # per launch (ncu) over the live kernel time against the same peak.
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "pair_force_kernel", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "pair_force", "peak_source": peak_src,
+                "dram_frac": (traffic / (pair_ms * 1e-3) / 1e9 / peak) if (traffic and pair_ms > 0 and world == 1) else None,
+                "limiter": limiter, "traffic_source": traffic_src,
+                "frac_note": "frac = algorithmic bytes (SURVEY 8d: 32 N + 20 P_full) / kernel time / peak; it is not a DRAM "
+                             "utilisation (gathers hit on-chip memory) -- dram_frac is",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": pair_ms,
-                "launches_timed": s1["pair_launches_timed"],
+                "launches_timed": s2["pair_launches_timed"],
                 "launches_in_timed_region": K, "share_of_step": pair_ms * K / ms if ms > 0 else None,
-                "rebuild_ms_avg": s1["build_ms_sum"] / max(s1["n_rebuilds"] - s0["n_rebuilds"], 1),
-                "integrate_ms_avg": s1["integrate_ms_sum"] / max(s1["integrate_launches_timed"], 1),
-                "halo_ms_avg": s1["halo_ms_sum"] / max(s1["halos_timed"], 1) if world > 1 else None,
-                "rank0_atoms_owned": int(s1["n_atoms"]), "rank0_ghosts": int(s1["n_ghosts"]),
-
-                "list_violations": int(s1["n_list_violations"])}
+                "rebuild": {"ms": rebuild_ms, "kernel": "sort + reorder + tile_build", "algorithmic_bytes": build_alg,
+                            "achieved": build_alg / (rebuild_ms * 1e-3) / 1e9 if rebuild_ms > 0 else None, "unit": "GB/s",
+                            "frac": build_alg / (rebuild_ms * 1e-3) / 1e9 / peak if rebuild_ms > 0 else None,
+                            "interval_steps": steady["rebuild_interval_steps"] if steady else interval},
+                "rebuild_ms_avg": rebuild_ms,
+                "integrate_ms_avg": s2["integrate_ms_sum"] / max(s2["integrate_launches_timed"], 1),
+                "halo_ms_avg": s2["halo_ms_sum"] / max(s2["halos_timed"], 1) if world > 1 else None,
+                "rank0_atoms_owned": int(s2["n_atoms"]), "rank0_ghosts": int(s2["n_ghosts"]),
+                "list_violations": int(s2["n_list_violations"])}
 
     cpu = None
     per_rank = None
@@ -317,7 +472,7 @@ def main():
         # what every rank measured (CUDA events on its own stream): in the fused halo the waits for the
         # neighbours sit inside kick_drift (ack) and the boundary rows' pair kernel (ready)
         k_int, frac = e.schedule()
-        mine = torch.tensor([pair_ms, roofline["integrate_ms_avg"], roofline["rebuild_ms_avg"], float(s1["n_atoms"]),
+        mine = torch.tensor([pair_ms, roofline["integrate_ms_avg"], roofline["rebuild_ms_avg"], float(s2["n_atoms"]),
                              float(k_int), frac], device="cuda", dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
@@ -326,9 +481,16 @@ def main():
                     "rebuild_ms": [round(float(v), 4) for v in allr[:, 2]], "atoms": [int(v) for v in allr[:, 3]],
                     "rebuild_interval": int(allr[0, 4]), "last_disp_over_half_skin": round(float(allr[0, 5]), 3)}
     roofline["per_rank"] = per_rank
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cb = cpu_arm(args.cpu_side, 100, 5)
-        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    halo = (("fused peer-memory push in kick_drift + flag wait in the pair kernel" if e.halo_mode()[0]
+             else "nccl send/recv (" + e.halo_mode()[1] + ")") if world > 1 else None)
+    e.close()
+    secondary = None
+    if rank == 0 and world == 1:
+        if not args.no_cpu:
+            cb = cpu_arm(args.cpu_side, 40, 5)
+            cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "same_config")}
+        if not args.no_secondary:
+            secondary = secondary_configs(peak)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
@@ -338,17 +500,19 @@ def main():
                                        f"dt 2 fs, PBC {w['box_ext'][0]:.1f} A), velocity Verlet, Verlet list rebuilt on "
                                        f"displacement > skin/2",
                            "atoms": n, "l2_policy": "inputs larger than L2: list+positions = "
-                                                    f"{(4 * p_full + 16 * n) / 1e6:.0f} MB per step vs 126 MB L2",
+                                                    f"{(s2['list_bytes'] + 16 * n) / 1e6:.0f} MB per step vs 126 MB L2",
                            "parallelism": f"slab-dd{world}" if world > 1 else "single-gpu",
-                           "halo": (("fused peer-memory push in kick_drift + flag wait in the pair kernel" if e.halo_mode()[0]
-                                     else "nccl send/recv (" + e.halo_mode()[1] + ")") if world > 1 else None),
-                           "pair_lanes": args.lanes or 8, "engine_options": args.opt or None},
+                           "halo": halo,
+                           "pair_lanes": args.lanes or 8, "engine_options": args.opt or None,
+                           "warmup_steps_run": warm_total,
+                           "window": (f"{K} timed steps placed so that one list rebuild falls inside (interval {interval} steps)"
+                                      if align or (0 < K < interval) else f"{K} consecutive steps, rebuilds as they come")},
+                "value_steady": steady,
                 "e2e": e2e, "gpu_launches": int(s1["n_kernel_launches"] - s0["n_kernel_launches"]),
                 "rebuilds_in_timed_region": int(s1["n_rebuilds"] - s0["n_rebuilds"]),
-                "wall_ms_per_step": wall / K * 1e3, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-                "loaded_library": _lib.LIB_PATH}
+                "wall_ms_per_step": wall / K * 1e3, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
+                "clocks": clocks, "loaded_library": _lib.LIB_PATH}
         print(json.dumps(line))
-    e.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -12,6 +12,7 @@ pub const MC_E_CUDA: c_int = -2;
 pub const MC_E_NODEVICE: c_int = -3;
 pub const MC_E_CAPACITY: c_int = -4;
 pub const MC_E_COMM: c_int = -5;
+pub const MC_W_STALE_LIST: c_int = 1;
 pub const MC_COULOMB_NONE: c_int = 0;
 pub const MC_COULOMB_PLAIN: c_int = 1;
 pub const MC_COULOMB_ERFC: c_int = 2;
@@ -72,6 +73,8 @@ pub struct McStats {
     pub halo_ms_sum: f64,
     pub halos_timed: i64,
     pub n_list_violations: i64,
+    pub list_bytes: i64,
+    pub ext_upload_bytes: i64,
 }
 
 #[link(name = "molchanica_md")]
@@ -141,8 +144,8 @@ extern "C" {
 
 /// Maps a status code to the error text `build_dynamics` propagates as `ParamError` (reference src/md/mod.rs:651).
 pub fn check(ctx: *const McCtx, rc: c_int) -> Result<(), String> {
-    if rc == MC_OK {
-        return Ok(());
+    if rc >= MC_OK {
+        return Ok(()); // positive codes are warnings (MC_W_STALE_LIST): the call completed, mc_last_error has the text
     }
     let msg = unsafe { std::ffi::CStr::from_ptr(mc_last_error(ctx)) };
     Err(format!("molchanica_md error {}: {}", rc, msg.to_string_lossy()))

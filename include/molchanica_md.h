@@ -14,7 +14,7 @@
  *   - plain pointers and sizes only; the caller owns every host buffer; the library copies in
  *     `mc_set_*`, owns all device memory until `mc_destroy`, and fills caller-allocated buffers
  *     in `mc_get_*` (the ownership model of clone_htod / clone_dtoh, src/reflection.rs:146-214)
- *   - every function returns 0 on success, a negative MC_E_* code otherwise; the message is
+ *   - every function returns 0 on success, a negative MC_E_* code on failure (a positive MC_W_* code is a warning); the message is
  *     available from mc_last_error(); nothing throws or aborts across the ABI
  *   - there is NO CPU fallback: without a usable CUDA device mc_create fails (the reference
  *     degrades to ComputationDevice::Cpu, src/util.rs:1065-1070; BASELINE.json forbids that here)
@@ -42,6 +42,9 @@ extern "C" {
 #define MC_E_NODEVICE (-3)  /* no usable sm_100 device -- there is no fallback */
 #define MC_E_CAPACITY (-4)  /* caller buffer too small                         */
 #define MC_E_COMM (-5)      /* NCCL / peer-exchange error                      */
+#define MC_W_STALE_LIST 1   /* warning (the call completed): an atom moved more than skin/2 between two list builds of a
+                             * fixed / decomposed rebuild schedule, so pairs inside the cutoff may have been missing from the
+                             * forces of the last steps; the list is rebuilt before the next evaluation (all ranks agree) */
 
 #define MC_COULOMB_NONE 0   /* q ignored                                                  */
 #define MC_COULOMB_PLAIN 1  /* q_i q_j /(r^2 + 1e-6), truncated at rc_q (src/cuda/util.cu:54-63) */
@@ -87,6 +90,8 @@ typedef struct {
     double  integrate_ms_sum; int64_t integrate_launches_timed;
     double  halo_ms_sum;      int64_t halos_timed;
     int64_t n_list_violations;   /* fixed-schedule rebuilds only: times an atom outran skin/2 between builds */
+    int64_t list_bytes;          /* bytes of the neighbour-list index stream one force evaluation reads (rows incl. padding) */
+    int64_t ext_upload_bytes;    /* host-to-device bytes the last mc_step moved for its external forces (this rank) */
 } mc_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------- */

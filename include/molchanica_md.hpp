@@ -268,7 +268,7 @@ class MdState {
     }
     void chk(int rc) { chk(rc, ctx_); }
     void chk(int rc, mc_ctx *c) {
-        if (rc != MC_OK) throw ParamError(rc, mc_last_error(c));
+        if (rc < MC_OK) throw ParamError(rc, mc_last_error(c));  // positive codes (MC_W_*) are warnings: the call completed
     }
 };
 

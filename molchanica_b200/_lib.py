@@ -37,7 +37,8 @@ class McStats(C.Structure):
                 ("pair_ms_sum", C.c_double), ("pair_launches_timed", C.c_int64),
                 ("build_ms_sum", C.c_double), ("builds_timed", C.c_int64),
                 ("integrate_ms_sum", C.c_double), ("integrate_launches_timed", C.c_int64),
-                ("halo_ms_sum", C.c_double), ("halos_timed", C.c_int64), ("n_list_violations", C.c_int64)]
+                ("halo_ms_sum", C.c_double), ("halos_timed", C.c_int64), ("n_list_violations", C.c_int64),
+                ("list_bytes", C.c_int64), ("ext_upload_bytes", C.c_int64)]
 
 
 def declared_symbols():

@@ -70,6 +70,8 @@ struct CommState {
     PeerMap prev_map, next_map;
     bool have_table = false;                // h_layer_all describes the build the local arrays are in
     bool dd_migrate = true;                 // rebuilds exchange boundary layers with the two neighbours only
+    bool preconnected = false;              // the ring's point-to-point channels have been set up (first build)
+    DevBuf<float4> pre_buf;                 // scratch of that warm-up exchange
     int interval = 10;                      // adaptive rebuild interval (option rebuild_every = 0)
     double last_disp_frac = 0.0;            // largest displacement of the last interval / (skin/2)
     uint32_t epoch = 1;                     // the first step runs at epoch 2: its acks are real signals
@@ -265,7 +267,7 @@ void comm_destroy(mc_ctx *c) {
     if (!c->comm) return;
     CommState *cs = c->comm;
     peer_close(cs);
-    cs->flags.release(); cs->d_exp.release(); cs->d_exp_all.release(); cs->d_layer_all.release();
+    cs->flags.release(); cs->d_exp.release(); cs->d_exp_all.release(); cs->d_layer_all.release(); cs->pre_buf.release();
     if (cs->h_layer_all) cudaFreeHost(cs->h_layer_all);
     if (cs->comm) nccl_api().CommDestroy(cs->comm);
     cs->s_xyzq.release(); cs->s_vel.release(); cs->g_xyzq.release(); cs->g_vel.release();
@@ -625,6 +627,23 @@ int comm_rebuild(mc_ctx *c) {
         MC_NCCL(c, nccl_api().AllGather(cs->s_vel.p, cs->g_vel.p, cap * 4, ncclFloat, cs->comm, st));
         MC_NCCL(c, nccl_api().AllGather(cs->s_meta.p, cs->g_meta.p, cap * 2, ncclInt32, cs->comm, st));
         MC_NCCL(c, nccl_api().GroupEnd());
+        if (!cs->preconnected && cs->dd_migrate) {
+            // NCCL connects its point-to-point channels lazily, at the first ncclSend / ncclRecv between two ranks --
+            // tens of milliseconds that would otherwise land in the first neighbour-only migration, i.e. in the middle of
+            // a run (round 1: a 27 ms stall ten steps in).  Pay for it here, with the message shape of a migration
+            // (three sends + three receives per neighbour, ~1 MB each so that every channel a real block uses is up).
+            const size_t m = 1u << 16;
+            MC_CUDAC(c, cs->pre_buf.ensure(4 * m));
+            MC_CUDAC(c, cudaMemsetAsync(cs->pre_buf.p, 0, sizeof(float4) * 2 * m, st));
+            float4 *sb[2] = {cs->pre_buf.p, cs->pre_buf.p + m}, *rb[2] = {cs->pre_buf.p + 2 * m, cs->pre_buf.p + 3 * m};
+            MC_NCCL(c, nccl_api().GroupStart());
+            for (int k = 0; k < 3; ++k) MC_NCCL(c, nccl_api().Send(sb[0], m * 4, ncclFloat, prev, cs->comm, st));
+            for (int k = 0; k < 3; ++k) MC_NCCL(c, nccl_api().Send(sb[1], m * 4, ncclFloat, next, cs->comm, st));
+            for (int k = 0; k < 3; ++k) MC_NCCL(c, nccl_api().Recv(rb[0], m * 4, ncclFloat, next, cs->comm, st));
+            for (int k = 0; k < 3; ++k) MC_NCCL(c, nccl_api().Recv(rb[1], m * 4, ncclFloat, prev, cs->comm, st));
+            MC_NCCL(c, nccl_api().GroupEnd());
+            cs->preconnected = true;
+        }
     }
     cs->have_table = false;
     MC_CUDAC(c, c->keys[0].ensure(n_all)); MC_CUDAC(c, c->keys[1].ensure(n_all));
@@ -678,10 +697,13 @@ int comm_rebuild(mc_ctx *c) {
             cs->last_disp_frac = frac;
             // the fastest atom moves ballistically over one interval: aim at 75 % of skin/2 (the largest displacement of
             // an interval fluctuates by 10-20 % from one interval to the next, more on small systems: replayed on oracle
-            // trajectories in tests/test_rebuild_flag_model.py, 85 % overshoots now and then, 75 % does not), grow by <= 25 %
-            double want = frac > 1e-6 ? 0.75 * steps_in_interval / frac : 1.25 * steps_in_interval + 1;
-            want = std::min(want, 1.25 * steps_in_interval + 1.0);
+            // trajectories in tests/test_rebuild_flag_model.py, 85 % overshoots now and then, 75 % does not), at most double
+            // (the extrapolation is linear in time, an upper bound for anything slower than ballistic motion: doubling is safe)
+            double want = frac > 1e-6 ? 0.75 * steps_in_interval / frac : 2.0 * steps_in_interval + 1;
+            want = std::min(want, 2.0 * steps_in_interval + 1.0);
             cs->interval = (int)std::max(4.0, std::min(200.0, std::floor(want)));
+            // every rank reads the same table: an atom that outran skin/2 anywhere is counted everywhere
+            if (frac > 1.0) c->n_list_violations++;
         }
     }
     cs->have_table = true;
@@ -738,6 +760,22 @@ int comm_agree_flag(mc_ctx *c, bool *flag) {
     MC_CUDAC(c, cudaStreamSynchronize(c->st));
     *flag = out != 0;
     return MC_OK;
+}
+
+// max over ranks of the two flag words behind the step kernels {displacement / non-finite bits, halo error bits},
+// delivered to pinned host memory; no synchronisation here -- the caller's one cudaStreamSynchronize covers it
+int comm_reduce_flags_async(mc_ctx *c, const int *d_flags2, int *h_out2) {
+    CommState *cs = c->comm;
+    MC_CUDAC(c, cs->d_red.ensure(4));
+    int *d = reinterpret_cast<int *>(cs->d_red.p);
+    MC_CUDAC(c, cudaMemcpyAsync(d, d_flags2, 2 * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
+    MC_NCCL(c, nccl_api().AllReduce(d, d, 2, ncclInt32, ncclMax, cs->comm, c->st));
+    MC_CUDAC(c, cudaMemcpyAsync(h_out2, d, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    return MC_OK;
+}
+
+void comm_shrink_interval(mc_ctx *c) {
+    if (c->comm) c->comm->interval = std::max(4, c->comm->interval / 2);
 }
 
 int comm_allreduce3(mc_ctx *c, double v[3]) {

@@ -1048,6 +1048,18 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     }
     c->prof_now = true;
     MC_CUDA(c, cudaEventRecord(c->ev_step_b, st));
+    // Fixed schedules (rebuild_every > 0, decomposed runs): the displacement flag is the safety net.  It rides behind the
+    // last kernel -- on a decomposed handle as the maximum over all ranks (one 8-byte all-reduce per CALL, not per step),
+    // so that every rank takes the same decision -- and is read after the one synchronisation of this call.
+    int *h_agree = reinterpret_cast<int *>(c->h_pinned) + 12;
+    const bool check_flag = (c->rebuild_every > 0 || c->comm_active) && n_steps > 0;
+    if (check_flag) {
+        if (c->comm_active) {
+            if ((rc = comm_reduce_flags_async(c, c->rebuild_flag.p, h_agree)) != MC_OK) return rc;
+        } else {
+            MC_CUDA(c, cudaMemcpyAsync(h_agree, c->rebuild_flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        }
+    }
     MC_CUDA(c, cudaGetLastError());
     MC_CUDA(c, cudaStreamSynchronize(st));
     float ms = 0.f;
@@ -1057,16 +1069,21 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     if (pipelined && n_steps > 0 && !skip_prev && (h_flag[(n_steps - 1) & 1] & 3) != 0) c->list_valid = false;
     if (pipelined && n_steps > 0 && (h_flag[(n_steps - 1) & 1] & 2))
         return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
-    if ((c->rebuild_every > 0 || c->comm_active) && n_steps > 0) {
-        // fixed schedule: the displacement flag is only a safety net -- an atom that moved more than skin/2
-        // between two builds means rebuild_every is too large for this system
-        MC_CUDA(c, cudaMemcpy(h_flag, c->rebuild_flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
-        if (h_flag[1] & MC_HALO_ERR_TIMEOUT)
+    bool stale_list = false;
+    if (check_flag) {
+        if (h_agree[1] & MC_HALO_ERR_TIMEOUT)
             return fail(c, MC_E_COMM, "mc_step: a neighbour rank did not signal its halo push within 2 s (peer died or ranks out of step)");
-        if (*h_flag & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
-        // a decomposed rank only reports the violation: invalidating the list on one rank alone would
-        // make it enter the collective rebuild on its own
-        if (*h_flag != 0) { c->n_list_violations++; if (!c->comm_active) c->list_valid = false; }
+        if (h_agree[0] & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
+        // An atom moved more than skin/2 between two builds: the schedule was too long for this system (sudden heating, a
+        // caller-chosen rebuild_every).  The list is rebuilt before the next evaluation -- on every rank of a decomposed
+        // run, which all see the same reduced flag -- the adaptive interval is halved, and the caller is told
+        // (MC_W_STALE_LIST: pairs inside the cutoff may have been missing from the last steps' forces).
+        if (h_agree[0] != 0) {
+            c->n_list_violations++;
+            c->list_valid = false;
+            stale_list = true;
+            if (c->comm_active) comm_shrink_interval(c);
+        }
     }
     if (c->n_hclusters > 0 && n_steps > 0) {
         int bad = 0;
@@ -1077,6 +1094,10 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         }
     }
     c->collect_timings();
+    if (stale_list) {
+        c->err = "mc_step: an atom moved more than skin/2 between two list builds; the list is rebuilt before the next evaluation";
+        return MC_W_STALE_LIST;
+    }
     return MC_OK;
 }
 
@@ -1486,6 +1507,8 @@ extern "C" int mc_get_stats(mc_ctx *c, mc_stats *out) {
     out->integrate_ms_sum = c->integ_acc.ms; out->integrate_launches_timed = c->integ_acc.count;
     out->halo_ms_sum = c->halo_acc.ms; out->halos_timed = c->halo_acc.count;
     out->n_list_violations = c->n_list_violations;
+    out->list_bytes = c->n_padded_entries * (int64_t)sizeof(uint32_t);
+    out->ext_upload_bytes = c->ext_upload_bytes;
     return MC_OK;
 }
 

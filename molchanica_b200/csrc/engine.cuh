@@ -88,6 +88,7 @@ struct mc_ctx {
 
     // counters
     int64_t n_list_violations = 0;
+    int64_t ext_upload_bytes = 0;  // H2D bytes of the last mc_step's external forces
     int64_t launches = 0, n_rebuilds = 0, n_steps = 0, n_pairs_listed = 0, n_padded_entries = 0;
     TimeAcc pair_acc, build_acc, integ_acc, halo_acc, dock_acc;
     double last_pair_ms = 0, last_dock_ms = 0, last_step_ms = 0;
@@ -276,6 +277,8 @@ int comm_interval(const mc_ctx *c);  // steps between two builds of a decomposed
 // step's kick_drift (no push when the step ends in a rebuild) and the wait descriptor of its pair kernels
 void comm_step_descriptors(mc_ctx *c, bool rebuild_step, HaloPush *push, HaloSplit *split);
 int comm_agree_flag(mc_ctx *c, bool *flag);
+int comm_reduce_flags_async(mc_ctx *c, const int *d_flags2, int *h_out2);
+void comm_shrink_interval(mc_ctx *c);
 int comm_allreduce3(mc_ctx *c, double v[3]);
 int comm_allreduce_f4(mc_ctx *c, float4 *buf, int64_t n);  // in-place sum over ranks
 void comm_destroy(mc_ctx *c);

@@ -46,11 +46,14 @@ class MdEngine:
             raise McError(rc, self._L.mc_last_error(None).decode())
         self._h = h
         self.n = 0
+        self.warnings = []
 
     # -- plumbing
     def _chk(self, rc):
-        if rc != 0:
+        if rc < 0:
             raise McError(rc, self._L.mc_last_error(self._h).decode())
+        if rc > 0:  # MC_W_*: the call completed; keep the warning for whoever wants to look
+            self.warnings.append((rc, self._L.mc_last_error(self._h).decode()))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -301,6 +304,10 @@ class MdEngine:
         d = {k: getattr(s, k) for k, _ in s._fields_}
         d["n_cells"] = list(s.n_cells)
         return d
+
+    def ext_upload_bytes(self):
+        """host-to-device bytes the last mc_step moved for its external forces on this rank"""
+        return self.stats()["ext_upload_bytes"]
 
     def reset_timers(self):
         self._chk(self._L.mc_reset_timers(self._h))

@@ -44,6 +44,20 @@ def test_dock_scan_matches_golden():
     e.close()
 
 
+def test_dock_scan_full_size_matches_oracle_on_sampled_poses():
+    """C5 at full size (10k poses x 5k receptor x 40 ligand atoms): 600 poses drawn from the scan are held to the fp64
+    oracle -- scored inside the full 10k-pose launch, so the launch geometry is the headline one."""
+    from molchanica_b200.engine import MdEngine
+    from oracle import oracle_py as O
+    d = W.docking_c5()
+    e = MdEngine()
+    s = e.dock_score(d)
+    pick = np.sort(np.random.default_rng(11).choice(len(d["poses"]), 600, replace=False))
+    ref, ref_abs = O.dock_score(d, precision=64, poses=d["poses"][pick], with_abs=True)
+    _check(s[pick], ref, ref_abs)
+    e.close()
+
+
 def test_dock_scan_full_size_is_invariant_under_pose_order():
     """C5 at full size (10k poses x 5k receptor atoms): a permutation of the poses permutes the
     scores (each pose is an independent unit of work)."""

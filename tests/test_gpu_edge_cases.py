@@ -1,7 +1,7 @@
 """Edge cases of the hot path through the C ABI (empty and tiny systems, atoms on box faces and far outside the box, pairs
-exactly at the cutoff, empty cells, one overfull cell, degenerate calls).  Same bars as tests/test_gpu_parity.py.
-Written after the last hardware run of round 1: like tests/newpaths_md.py it is not collected by name but run by
-tests/test_library_on_host.py (host build) and, on a GPU box, by tests/test_gpu_new_paths.py in a process of its own."""
+exactly at the cutoff, empty cells, one overfull cell, degenerate calls) and the randomised sweeps (MC_FUZZ_SEEDS).  Same
+bars as tests/test_gpu_parity.py.  Confirmed on hardware at the end of round 1; tests/test_library_on_host.py also runs
+this file against the host build of the library."""
 import numpy as np
 import pytest
 

@@ -1,8 +1,6 @@
-"""Paths added AFTER the last hardware run of round 1 (the GPU budget was spent): the pipelined external-force upload,
-pressure / virial, constraint virial, barostats, drift removal, snapshots with velocities.  They pass against the host build
-of the library (tests/test_library_on_host.py runs this file there); on a GPU box they are run by tests/test_gpu_new_paths.py
-in a process of their own, so that a fault in a never-run kernel cannot poison the CUDA context of the validated tests.
-Not collected by name (no test_ prefix): always run through one of those two."""
+"""MD paths beside the plain NVE step, through the C ABI on the GPU: the pipelined external-force upload, pressure /
+virial, constraint virial, barostats, drift removal, snapshots with velocities.  First run on hardware by the driver at
+the end of round 1 (all passed); tests/test_library_on_host.py also runs this file against the host build of the library."""
 import numpy as np
 import pytest
 

@@ -61,6 +61,6 @@ def test_decomposed_run_matches_oracle(world, case, halo, sched, oracle):
     assert ok, (worst, sc)
     assert int(r["violations"]) == 0
     if sched == "adaptive":
-        assert int(r["interval"]) >= 10 and int(r["rebuilds"]) >= 3 and 0.0 < float(r["disp_frac"]) < 1.0
+        assert int(r["interval"]) >= 10 and int(r["rebuilds"]) >= 2 and 0.0 < float(r["disp_frac"]) < 1.0
     assert bool(r["snap_ok"]), "rank-local snapshot differs from the gathered positions"
     assert int(r["n_owned"]) < len(w["xyzq"]) and int(r["n_ghosts"]) > 0

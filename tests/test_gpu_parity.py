@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from molchanica_b200 import workloads as W
-from util import FORCE_RTOL, energy_close, force_rel_err, numpy_row, trajectory_close
+from util import FORCE_RTOL, FORCE_RTOL_NET, energy_close, force_rel_err, numpy_row, trajectory_close
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "md_small.npz")
@@ -45,6 +45,9 @@ def test_neighbour_list_bit_exact_and_forces(name, Engine, oracle):
     f64, sumabs, en = oracle.forces(w, (o_start, o_idx), precision=64)
     err = force_rel_err(f, f64, sumabs)
     assert err.max() < FORCE_RTOL, f"max force error {err.max():.3e} at atom {err.argmax()}"
+    _, sumnet, _ = oracle.forces(w, (o_start, o_idx), precision=64, scale="net")
+    err_net = force_rel_err(f, f64, sumnet)
+    assert err_net.max() < FORCE_RTOL_NET, f"max force error on the net-pair scale {err_net.max():.3e} at atom {err_net.argmax()}"
     assert energy_close(e.energy()["energy_potential_nonbonded"], en.sum(), f64[:, 3])
     # per-atom energy rows
     assert np.abs(f[:, 3] - f64[:, 3]).max() < 1e-5 * max(1.0, float(np.abs(f64[:, 3]).max()))
@@ -231,6 +234,36 @@ def test_full_size_c4_properties(Engine):
     f = e.forces().astype(np.float64)
     assert np.abs(f[:, :3].sum(0)).max() < 1e-6 * np.abs(f[:, :3]).sum()
     assert abs(e.energy()["energy_potential_nonbonded"] - 0.5 * f[:, 3].sum()) < 1e-6 * abs(f[:, 3].sum())
+    e.close()
+
+
+def test_full_size_c4_matches_the_oracle(Engine, oracle):
+    """BASELINE config 4 at full size against the oracle itself, ALL atoms: the 80,000,000-entry Verlet list bit-exact
+    with the oracle's cell-list build, forces of every atom within 1e-5 of the fp64 sum over that list (and 3e-5 on the
+    net-pair scale), the energy, and a 20-step trajectory against the oracle's fp64 path."""
+    w = W.lj_fluid(m=100)
+    n = len(w["xyzq"])
+    e = Engine.from_workload(w)
+    e.build_neighbors()
+    start, idx = e.neighbors()
+    o_start, o_idx = oracle.neighbors(w)
+    assert np.array_equal(start, o_start), "row lengths differ"
+    assert np.array_equal(idx, o_idx), "neighbour indices differ"
+    del start, idx
+    e.compute_forces()
+    f = e.forces()
+    f64, sumabs, en = oracle.forces(w, (o_start, o_idx), precision=64)
+    err = force_rel_err(f, f64, sumabs)
+    assert err.max() < FORCE_RTOL, f"max force error {err.max():.3e} at atom {err.argmax()} of {n}"
+    _, sumnet, _ = oracle.forces(w, (o_start, o_idx), precision=64, scale="net")
+    err_net = force_rel_err(f, f64, sumnet)
+    assert err_net.max() < FORCE_RTOL_NET, f"net-pair scale: {err_net.max():.3e} at atom {err_net.argmax()}"
+    assert energy_close(e.energy()["energy_potential_nonbonded"], en.sum(), f64[:, 3])
+    del o_start, o_idx
+    e.step(w["dt"], 20)
+    ref = oracle.md_run(w, 20, precision=64)
+    ok, worst, scale = trajectory_close(e.positions(), ref["xyzq"], w["xyzq"], w["box_ext"])
+    assert ok, (worst, scale)
     e.close()
 
 

@@ -36,7 +36,7 @@ def test_gpu_parity_tests_pass_on_the_host_build(host_env):
     slow = "c4 or lane_width or variants or solv23558 or full_size"
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k", f"not ({slow})",
                         os.path.join(HERE, "test_gpu_parity.py"), os.path.join(HERE, "test_gpu_dock.py"),
-                        os.path.join(HERE, "newpaths_md.py"), os.path.join(HERE, "newpaths_edge_cases.py")],
+                        os.path.join(HERE, "test_gpu_md_paths.py"), os.path.join(HERE, "test_gpu_edge_cases.py")],
                        capture_output=True, text=True, cwd=ROOT, env=host_env, timeout=1500)
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
@@ -46,9 +46,9 @@ def test_gpu_parity_tests_pass_on_the_host_build(host_env):
 
 
 @pytest.mark.parametrize("worker", ["bonded", "settle", "pme", "langevin"])
-def test_components_not_yet_run_on_hardware_pass_on_the_host_build(worker, host_env):
-    """The exact checks tests/test_gpu_{bonded,settle,pme,langevin}.py will make on the first GPU of round 2 (there they are
-    xfail, non-strict, until hardware has confirmed them); here they must pass."""
+def test_component_workers_pass_on_the_host_build(worker, host_env):
+    """The exact checks tests/test_gpu_{bonded,settle,pme,langevin}.py make on a GPU (the same worker scripts), here against the
+    host build of the library."""
     r = subprocess.run([sys.executable, os.path.join(HERE, f"{worker}_gpu_worker.py")], capture_output=True, text=True, cwd=ROOT,
                        env=host_env, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
@@ -96,7 +96,7 @@ def test_decomposed_run_on_the_host_build(case, world, halo, sched, host_env, or
     assert int(r["n_owned"]) < len(w["xyzq"]) and int(r["n_ghosts"]) > 0
     assert int(r["rebuilds"]) >= 2
     if sched == "adaptive":
-        assert int(r["interval"]) >= 10 and int(r["rebuilds"]) >= 3 and 0.0 < float(r["disp_frac"]) < 1.0
+        assert int(r["interval"]) >= 10 and int(r["rebuilds"]) >= 2 and 0.0 < float(r["disp_frac"]) < 1.0
 
 
 def test_cpp_host_mirror_runs_on_the_host_build(host_env, tmp_path):

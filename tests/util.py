@@ -9,6 +9,10 @@ import numpy as np
 # stricter net-pair scale (scale="net") is reported by tests/report_parity.py for information.
 FORCE_RTOL = 1e-5
 ENERGY_RTOL = 1e-5
+# The stricter scale, asserted next to the bar above so that a regression against it is visible: per atom the sum of the
+# magnitudes of the NET pair forces (oracle.forces scale="net").  fp32 arithmetic sits at 2-4e-6 typical and 1.1e-5 worst
+# on this scale (the reference-form fp32 arithmetic of the oracle itself is at 4e-6), hence 3e-5.
+FORCE_RTOL_NET = 3e-5
 
 
 def force_rel_err(f_test, f_truth, sumabs):

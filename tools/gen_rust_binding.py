@@ -39,8 +39,8 @@ TAIL = """}
 
 /// Maps a status code to the error text `build_dynamics` propagates as `ParamError` (reference src/md/mod.rs:651).
 pub fn check(ctx: *const McCtx, rc: c_int) -> Result<(), String> {
-    if rc == MC_OK {
-        return Ok(());
+    if rc >= MC_OK {
+        return Ok(()); // positive codes are warnings (MC_W_STALE_LIST): the call completed, mc_last_error has the text
     }
     let msg = unsafe { std::ffi::CStr::from_ptr(mc_last_error(ctx)) };
     Err(format!("molchanica_md error {}: {}", rc, msg.to_string_lossy()))

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 TAG=${1:-8f}
 # everything added after the last hardware run in one go first: the parity file (pipelined external forces, pressure,
 # constraint virial, barostat, snapshots with velocities, drift removal) -- these already pass against the host build
-timeout 1200 python -m pytest tests/newpaths_md.py tests/newpaths_edge_cases.py -m gpu -q > gpurun_out/new_paths_$TAG.log 2>&1; echo "new paths rc=$?"; tail -5 gpurun_out/new_paths_$TAG.log
+timeout 1200 python -m pytest tests/test_gpu_md_paths.py tests/test_gpu_edge_cases.py -m gpu -q > gpurun_out/new_paths_$TAG.log 2>&1; echo "new paths rc=$?"; tail -5 gpurun_out/new_paths_$TAG.log
 # the e2e line with and without the pipelined upload (option defer_tail): the A/B that says what it bought
 timeout 600 python bench.py --steps 300 --warmup 50 > gpurun_out/bench_defer_on_$TAG.json 2> gpurun_out/bench_defer_on_$TAG.err; tail -1 gpurun_out/bench_defer_on_$TAG.json
 timeout 600 python bench.py --steps 300 --warmup 50 --no-cpu --opt defer_tail=0 > gpurun_out/bench_defer_off_$TAG.json 2> gpurun_out/bench_defer_off_$TAG.err; tail -1 gpurun_out/bench_defer_off_$TAG.json
