@@ -105,7 +105,7 @@ extern "C" int mc_create(int device, mc_ctx **out) {
     c->l2_bytes = (size_t)prop.l2CacheSize;
     if ((e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = pair_force_prepare()) != cudaSuccess || (e = dock_prepare()) != cudaSuccess ||
-        (e = tile_sweep_prepare()) != cudaSuccess ||
+        (e = tile_sweep_prepare()) != cudaSuccess || (e = pair_tile_prepare()) != cudaSuccess ||
         (e = cudaMallocHost(&c->h_pinned, 256)) != cudaSuccess) {
         g_create_err = std::string("mc_create: ") + cudaGetErrorString(e);
         delete c;
@@ -522,6 +522,10 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         c->sync_rebuild = value != 0.0;
     } else if (k == "tile_sweep") {
         c->use_tile = value != 0.0;
+        c->list_valid = false;
+    } else if (k == "pair_tile") {
+        c->use_pair_tile = value != 0.0;
+        c->list_valid = false;
     } else if (k == "profiling") {
         c->profiling = value != 0.0;
     } else if (k == "profile_every") {
@@ -647,13 +651,19 @@ int engine_build_rows(mc_ctx *c) {
     const int grid_cells = c->periodic ? c->h_grid.ncell : (int)c->ncell_cap;
     const int est_cells = c->periodic ? c->h_grid.ncell : std::max(1, n / 256);
     const int split = std::max(1, std::min(8, (4 * c->n_sms + est_cells - 1) / est_cells));
+    // compact rows (16-bit tile-local indices) for the TMA-staged force kernel whenever its tile + LJ table fit shared memory
+    bool compact = tiled && c->use_pair_tile;
     while (tiled) {
         // single-pass TMA-staged build (tile_build.cu); tile and list capacities adapt on demand
         MC_CUDA(c, c->tile_need.ensure(4));
-        if (!c->nbr_list.p) MC_CUDA(c, c->nbr_list.ensure(1024));
+        if (compact && pair_tile_smem(c->tile_cap, c->n_types, c->n_types > 1, nullptr) == 0) compact = false;
+        if (compact) { if (!c->nbr_list16.p) MC_CUDA(c, c->nbr_list16.ensure(1024)); }
+        else if (!c->nbr_list.p) MC_CUDA(c, c->nbr_list.ensure(1024));
+        const size_t cap_now = compact ? c->nbr_list16.n : c->nbr_list.n;
         launch_tile_build(n_rows, grid_cells, split, c->n_sms, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, rc2_inner,
-                          c->orig[c->cur].p, es, ei, c->nbr_count.p, c->nbr_start.p, c->nbr_list.p,
-                          (uint32_t)std::min<size_t>(c->nbr_list.n, 0xffffffffu), c->tile_cap, c->tile_need.p, st, &c->launches);
+                          c->orig[c->cur].p, es, ei, c->nbr_count.p, c->nbr_start.p,
+                          compact ? static_cast<void *>(c->nbr_list16.p) : static_cast<void *>(c->nbr_list.p), compact,
+                          (uint32_t)std::min<size_t>(cap_now, 0xffffffffu), c->tile_cap, c->tile_need.p, st, &c->launches);
         MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->tile_need.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         MC_CUDA(c, cudaStreamSynchronize(st));
         if (h_ctl[3] != 0) {  // a neighbourhood did not fit the tile
@@ -661,13 +671,17 @@ int engine_build_rows(mc_ctx *c) {
             if (need > tile_sweep_max_atoms() && ((h_ctl[2] + 127u) & ~31u) <= tile_sweep_max_atoms()) need = tile_sweep_max_atoms();
             if (need <= tile_sweep_max_atoms()) { c->tile_cap = need; continue; }
             tiled = c->use_tile = false;  // too dense for shared memory: two-pass global sweep from now on
+            compact = false;
             break;
         }
         total = h_ctl[1];
-        if (total > c->nbr_list.n) {  // the cursor ran past the list: grow it and build again
-            MC_CUDA(c, c->nbr_list.ensure(total + total / 8 + 1024));
+        if (total > cap_now) {  // the cursor ran past the list: grow it and build again
+            if (compact) MC_CUDA(c, c->nbr_list16.ensure(total + total / 8 + 1024));
+            else MC_CUDA(c, c->nbr_list.ensure(total + total / 8 + 1024));
             continue;
         }
+        c->tile_max_m = (h_ctl[2] + 31u) & ~31u;
+        if (compact && pair_tile_smem(c->tile_max_m, c->n_types, c->n_types > 1, nullptr) == 0) { compact = false; continue; }
         break;
     }
     if (!tiled) {
@@ -685,11 +699,23 @@ int engine_build_rows(mc_ctx *c) {
     tr.stop();
     MC_CUDA(c, cudaGetLastError());
     c->n_padded_entries = (int64_t)total;
+    c->list_compact = tiled && compact;
+    c->list32_valid = !c->list_compact;
     c->list_valid = true;
     c->forces_valid = false;
     c->n_rebuilds++;
     c->steps_since_build = 0;
     c->pairs_dirty = true;
+    return MC_OK;
+}
+
+int engine_ensure_list32(mc_ctx *c) {
+    if (c->list32_valid || !c->list_valid) return MC_OK;
+    MC_CUDA(c, c->nbr_list.ensure((size_t)std::max<int64_t>(c->n_padded_entries, 1)));
+    launch_expand_rows(c->periodic ? c->h_grid.ncell : (int)c->ncell_cap, c->cell_start.p, c->grid.p, c->nbr_start.p, c->nbr_count.p,
+                       c->nbr_list16.p, c->nbr_list.p, c->st, &c->launches);
+    MC_CUDA(c, cudaGetLastError());
+    c->list32_valid = true;
     return MC_OK;
 }
 
@@ -748,7 +774,25 @@ int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs) {
     L.multi = c->n_types > 1;
     L.lanes = c->pair_lanes;
     L.force = c->force.p;
-    if (hs) {
+    if (c->list_compact) {
+        // TMA-staged kernel over the compact rows (pair_tile.cu); a decomposed rank hands it the ready flags to wait on
+        PairTileLaunch T;
+        T.grid_cells = c->periodic ? c->h_grid.ncell : (int)c->ncell_cap;
+        T.n_sms = c->n_sms;
+        T.xyzq = L.xyzq; T.type = L.type; T.cell_start = c->cell_start.p; T.grid = c->grid.p;
+        T.nbr_start = L.nbr_start; T.nbr_count = L.nbr_count; T.list16 = c->nbr_list16.p; T.ljtab = L.ljtab;
+        T.p = L.p; T.lj_on = L.lj_on; T.coul = L.coul; T.multi = L.multi; T.energy = L.energy; T.force = L.force;
+        T.tile_cap = c->tile_max_m;
+        if (!c->pair_ctl.p) {
+            MC_CUDA(c, c->pair_ctl.ensure(4));
+            MC_CUDA(c, cudaMemsetAsync(c->pair_ctl.p, 0, 4 * sizeof(uint32_t), c->st));
+        }
+        T.ctl = c->pair_ctl.p;
+        if (hs) T.wait = hs->wait;
+        TimedRegion tr(c, c->pair_acc, true);
+        launch_pair_tile(T, c->st, &c->launches);
+        tr.stop();
+    } else if (hs) {
         TimedRegion tr(c, c->pair_acc, true);
         L.n_interior = hs->last_begin - hs->n_first;
         L.n_first = hs->n_first;
@@ -1344,6 +1388,7 @@ static int compute_pressure(mc_ctx *c, double *pressure_bar, double *virial) {
     launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + c->row0, c->vel[c->cur].p + c->row0, c->red_partial.p, c->red_out.p, c->st,
                          &c->launches);
     const int coul = c->coul_disabled ? MC_COULOMB_NONE : c->coul_mode;
+    { int rc32 = engine_ensure_list32(c); if (rc32 != MC_OK) return rc32; }
     launch_virial((int)c->n_rows_sorted(), (int)c->row0, c->xyzq[c->cur].p, c->type[c->cur].p, c->orig[c->cur].p, c->slot_of_orig.p,
                   c->nbr_start.p, c->nbr_count.p, c->nbr_list.p, c->have_p14 ? c->p14_start.p : nullptr, c->have_p14 ? c->p14_idx.p : nullptr,
                   c->ljtab.p, make_params(c), c->lj_disabled ? 0 : 1, coul, c->scale14_lj, c->scale14_q, c->red_out.p + 3, c->st,
@@ -1471,6 +1516,7 @@ extern "C" int mc_get_energy_between_mols(mc_ctx *c, double *out) {
     int rc = ensure_ready(c, "mc_get_energy_between_mols");
     if (rc != MC_OK) return rc;
     MC_CUDA(c, c->red_out.ensure(4));
+    if ((rc = engine_ensure_list32(c)) != MC_OK) return rc;
     launch_between_mols((int)c->n_rows_sorted(), (int)c->row0, c->xyzq[c->cur].p, c->type[c->cur].p, c->orig[c->cur].p, c->mol_of_orig.p,
                         c->nbr_start.p, c->nbr_count.p, c->nbr_list.p, c->ljtab.p, make_params(c), c->lj_disabled ? 0 : 1,
                         c->coul_disabled ? MC_COULOMB_NONE : c->coul_mode, c->red_out.p + 3, c->st, &c->launches);
@@ -1507,7 +1553,7 @@ extern "C" int mc_get_stats(mc_ctx *c, mc_stats *out) {
     out->integrate_ms_sum = c->integ_acc.ms; out->integrate_launches_timed = c->integ_acc.count;
     out->halo_ms_sum = c->halo_acc.ms; out->halos_timed = c->halo_acc.count;
     out->n_list_violations = c->n_list_violations;
-    out->list_bytes = c->n_padded_entries * (int64_t)sizeof(uint32_t);
+    out->list_bytes = c->n_padded_entries * (int64_t)(c->list_compact ? sizeof(uint16_t) : sizeof(uint32_t));
     out->ext_upload_bytes = c->ext_upload_bytes;
     return MC_OK;
 }
@@ -1530,6 +1576,7 @@ extern "C" int mc_get_neighbors(mc_ctx *c, int64_t *start, int32_t *idx, int64_t
     MC_CUDA(c, c->start_orig.ensure((size_t)n + 1));
     MC_CUDA(c, c->export_rows.ensure((size_t)c->n_padded_entries + 1));
     MC_CUDA(c, c->scratch.ensure(scan_scratch_elems((size_t)n + 1) + 64));
+    { int rc32 = engine_ensure_list32(c); if (rc32 != MC_OK) return rc32; }
     launch_export_rows(n, c->orig[c->cur].p, c->nbr_count.p, c->nbr_start.p, c->nbr_list.p, c->cnt_orig.p,
                        c->start_orig.p, c->export_rows.p, c->scratch.p, c->st, &c->launches);
     std::vector<uint32_t> hs((size_t)n + 1);

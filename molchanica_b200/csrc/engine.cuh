@@ -85,6 +85,10 @@ struct mc_ctx {
     bool subcell_sort = false;  // Morton sub-cell code in the low sort-key bits (option "subcell_sort")
     bool use_tile = true;      // TMA-staged tile sweep for the list build (neighbor_tile.cu)
     uint32_t tile_cap = 1024;  // tile capacity in atoms, grows on demand
+    bool use_pair_tile = true; // option "pair_tile": compact rows (16-bit tile-local indices) + TMA-staged force kernel (pair_tile.cu)
+    bool list_compact = false; // the current list is in compact form (nbr_list16)
+    bool list32_valid = false; // nbr_list holds the current list as global slots (expanded on demand from the compact form)
+    uint32_t tile_max_m = 0;   // largest tile (atoms) of the current build = stage capacity of the force kernel
 
     // counters
     int64_t n_list_violations = 0;
@@ -102,7 +106,8 @@ struct mc_ctx {
     DevBuf<uint8_t> flags[2];
     DevBuf<int> orig[2], slot_of_orig, rebuild_flag;
     DevBuf<uint32_t> keys[2], vals[2], scratch, cell_start, nbr_count, nbr_start, nbr_list;
-    DevBuf<uint32_t> cnt_orig, start_orig, export_rows, tile_need;
+    DevBuf<uint32_t> cnt_orig, start_orig, export_rows, tile_need, pair_ctl;
+    DevBuf<uint16_t> nbr_list16;
     DevBuf<int32_t> excl_start, excl_idx, p14_start, p14_idx;
     DevBuf<float2> ljtab, d_dock_tab;
     DevBuf<float> bbox, ext_force, d_poses, d_scores;
@@ -205,7 +210,7 @@ struct mc_ctx {
         for (int b = 0; b < 2; ++b) { xyzq[b].release(); vel[b].release(); type[b].release(); flags[b].release(); orig[b].release(); keys[b].release(); vals[b].release(); }
         force.release(); xref.release(); stage.release(); flush.release(); slot_of_orig.release(); rebuild_flag.release();
         scratch.release(); cell_start.release(); nbr_count.release(); nbr_start.release(); nbr_list.release();
-        cnt_orig.release(); start_orig.release(); export_rows.release(); tile_need.release();
+        cnt_orig.release(); start_orig.release(); export_rows.release(); tile_need.release(); pair_ctl.release(); nbr_list16.release();
         excl_start.release(); excl_idx.release(); p14_start.release(); p14_idx.release();
         ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); ext_force2.release(); d_poses.release(); d_scores.release();
         grid.release(); red_partial.release(); red_out.release(); d_rec.release(); d_lig.release();
@@ -258,6 +263,7 @@ struct TimedRegion {
 int engine_build_list(mc_ctx *c);
 int engine_flush_tail(mc_ctx *c);  // closes the half kick mc_step left open (pipelined external forces)
 int engine_build_rows(mc_ctx *c);
+int engine_ensure_list32(mc_ctx *c);  // global-slot rows for the consumers off the hot path (expands the compact list once per build)
 // hs != nullptr: decomposed step with the peer-memory halo -- interior rows first, then the rows of the
 // first and last owned layer in one launch that waits for the neighbours' pushes
 struct HaloSplit { int n_first, last_begin; HaloWait wait; };

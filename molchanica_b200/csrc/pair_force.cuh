@@ -36,3 +36,27 @@ void launch_pairs14(int n_rows, int row0, const float4 *xyzq, const uint16_t *ty
 int energy_partial_elems();
 void launch_energy_reduce(int n_rows, const float4 *force, const float4 *vel, double *partial, double *out3,
                           cudaStream_t st, int64_t *launches);
+
+// pair_tile.cu -- the TMA-staged variant: rows of 16-bit tile-local indices (tile_build.cu, compact = true), the cell's
+// 27-cell tile in shared memory.  ctl: 4 zeroed words owned by this launcher (the kernel re-arms them itself).
+struct PairTileLaunch {
+    int grid_cells;   // upper bound of the cells holding rows (the kernel reads the exact grid from `grid`)
+    int n_sms;
+    const float4 *xyzq;
+    const uint16_t *type;
+    const uint32_t *cell_start;
+    const GridParams *grid;
+    const uint32_t *nbr_start, *nbr_count;
+    const uint16_t *list16;
+    const float2 *ljtab;
+    NbParams p;
+    int lj_on, coul;
+    bool multi, energy;
+    float4 *force;
+    uint32_t tile_cap;
+    uint32_t *ctl;
+    HaloWait wait{};
+};
+cudaError_t pair_tile_prepare();
+size_t pair_tile_smem(uint32_t tile_cap, int n_types, bool multi, int *n_stages_out);
+void launch_pair_tile(const PairTileLaunch &L, cudaStream_t st, int64_t *launches);

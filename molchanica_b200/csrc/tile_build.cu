@@ -206,11 +206,13 @@ __device__ __forceinline__ void rows_phase1(const float4 *tile, const uint32_t *
 }
 
 // phase 2: write the rows in tile order; inner entries from the front, skin-shell entries from the back
-template <int NA, int WRAP>
+// IDX = uint32_t: entries are global slots (tile_slot[t]); IDX = uint16_t: entries are the TILE-LOCAL indices t themselves
+// (the compact list pair_tile.cu gathers from its own copy of the tile, laid out by the same tile_plan)
+template <int NA, int WRAP, typename IDX>
 __device__ __forceinline__ void rows_phase2(const float4 *tile, const uint32_t *tile_slot, const StageMeta &M, const GridParams &g,
                                             float rl2, float rc2_inner, const uint32_t (&row)[TILE_A],
                                             const int *__restrict__ orig, const int32_t *__restrict__ excl_idx,
-                                            uint32_t *__restrict__ nbr_list, int lane, RowState &R) {
+                                            IDX *__restrict__ nbr_list, int lane, RowState &R) {
     const bool one_chunk = M.m <= 992u;
     uint32_t run_in[TILE_A], run_out[TILE_A];
 #pragma unroll
@@ -238,7 +240,7 @@ __device__ __forceinline__ void rows_phase2(const float4 *tile, const uint32_t *
             while (mleft) {
                 const int it = __ffs(mleft) - 1;
                 mleft &= mleft - 1u;
-                const uint32_t j = tile_slot[tl + (uint32_t)it];
+                const IDX j = sizeof(IDX) == 2 ? (IDX)(tl + (uint32_t)it) : (IDX)tile_slot[tl + (uint32_t)it];
                 if ((R.inn[k] >> it) & 1u) nbr_list[p_in++] = j;
                 else nbr_list[p_out--] = j;
             }
@@ -252,11 +254,12 @@ __device__ __forceinline__ void rows_phase2(const float4 *tile, const uint32_t *
 #ifndef MC_TILE_MIN_BLOCKS
 #define MC_TILE_MIN_BLOCKS 3
 #endif
+template <typename IDX>
 __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) tile_build_kernel(
     int n_rows, const float4 *__restrict__ xyzq, const uint32_t *__restrict__ cell_start,
     const GridParams *__restrict__ gp, float rl2, float rc2_inner, const int *__restrict__ orig,
     const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx, uint32_t *__restrict__ nbr_count,
-    uint32_t *__restrict__ nbr_start, uint32_t *__restrict__ nbr_list, uint32_t list_cap, uint32_t tile_cap, int split,
+    uint32_t *__restrict__ nbr_start, IDX *__restrict__ nbr_list, uint32_t list_cap, uint32_t tile_cap, int split,
     int n_stages /* 1 or 2 tiles in flight */, uint32_t *__restrict__ ctl /* [0] work counter, [1] list cursor, [2] max tile atoms seen, [3] tile overflow */) {
     MC_DYN_SHARED_ALIGNED(unsigned char, smem_raw, 128);
     // per stage: tile_cap float4 positions, then tile_cap slot ids
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) til
                 const bool fits = s_fits[pp] != 0;  // otherwise the host grows the list and rebuilds
                 pp ^= 1;  // the other buffer serves the next pass: no third barrier needed
                 if (fits && na > 0) {
-#define MC_P2(NA_, W_) rows_phase2<NA_, W_>(tile, tile_slot, M, g, rl2, rc2_inner, row, orig, excl_idx, nbr_list, lane, R)
+#define MC_P2(NA_, W_) rows_phase2<NA_, W_, IDX>(tile, tile_slot, M, g, rl2, rc2_inner, row, orig, excl_idx, nbr_list, lane, R)
 #define MC_P2W(NA_) \
     if (M.wrap == 0) MC_P2(NA_, 0); else if (M.wrap == 1) MC_P2(NA_, 1); else MC_P2(NA_, 2)
                     switch (na_u) { case 1: MC_P2W(1); break; case 2: MC_P2W(2); break; case 3: MC_P2W(3); break; default: MC_P2W(4); break; }
@@ -411,10 +414,52 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) til
     }
 }
 
+// Compact rows (tile-local 16-bit indices) -> rows of global slots, same nbr_start / nbr_count.  Off the hot path: only
+// mc_get_neighbors, the virial and the between-molecules energy read global-slot rows.  One CTA per cell at a time.
+__global__ void __launch_bounds__(128) expand_rows_kernel(const uint32_t *__restrict__ cell_start, const GridParams *__restrict__ gp,
+                                                         const uint32_t *__restrict__ nbr_start, const uint32_t *__restrict__ nbr_count,
+                                                         const uint16_t *__restrict__ list16, uint32_t *__restrict__ list32) {
+    __shared__ TileRange rg[18];
+    const GridParams g = *gp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int c = blockIdx.x; c < g.ncell; c += gridDim.x) {
+        const uint32_t a0 = cell_start[c], a1 = cell_start[c + 1];
+        const int c2 = c / (g.nc[0] * g.nc[1]);
+        if (a0 == a1 || c2 < g.row_l0 || c2 >= g.row_l1) continue;  // block-uniform
+        if (warp == 0) {
+            TilePlan P;
+            tile_plan(g, cell_start, c, a0, lane, P);
+            if (lane < 9) { rg[2 * lane] = P.r0; rg[2 * lane + 1] = P.r1; }
+        }
+        __syncthreads();
+        for (uint32_t i = a0 + (uint32_t)warp; i < a1; i += (uint32_t)n_warps) {
+            const uint32_t s = nbr_start[i], cnt = nbr_count[i];
+            for (uint32_t k = lane; k < cnt; k += 32) {
+                const uint32_t t = list16[s + k];
+                uint32_t slot = 0xffffffffu;
+#pragma unroll 1
+                for (int r = 0; r < 18; ++r)
+                    if (t >= rg[r].off && t < rg[r].off + rg[r].cnt) { slot = rg[r].src + (t - rg[r].off); break; }
+                list32[s + k] = slot;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
+void launch_expand_rows(int grid_cells, const uint32_t *cell_start, const GridParams *g, const uint32_t *nbr_start,
+                        const uint32_t *nbr_count, const uint16_t *list16, uint32_t *list32, cudaStream_t st, int64_t *launches) {
+    const unsigned grid = (unsigned)std::max(1, std::min(grid_cells, 148 * 16));
+    MC_LAUNCH(expand_rows_kernel, grid, 128, 0, st, cell_start, g, nbr_start, nbr_count, list16, list32);
+    *launches += 1;
+}
+
 cudaError_t tile_sweep_prepare() {
-    return cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tile_build_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tile_build_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 // 16 B position + 4 B slot id per staged atom in 200 KB of shared memory; tiles above half of that run
@@ -423,18 +468,23 @@ uint32_t tile_sweep_max_atoms() { return ((200u * 1024u) / 20u) & ~31u; }
 
 void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
                        const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
-                       const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, uint32_t *nbr_list,
+                       const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, void *nbr_list, bool compact,
                        uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches) {
     // persistent: exactly one resident wave of CTAs pulls (cell, slice) items from ctl[0]
     const long long items = (long long)grid_cells * split;
     const int n_stages = (size_t)2 * tile_cap * 20u <= 200u * 1024u ? 2 : 1;
     const size_t smem = (size_t)n_stages * tile_cap * (sizeof(float4) + sizeof(uint32_t));
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_build_kernel, (TILE_WARPS + 1) * 32, smem);
+    if (compact) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_build_kernel<uint16_t>, (TILE_WARPS + 1) * 32, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_build_kernel<uint32_t>, (TILE_WARPS + 1) * 32, smem);
     if (per_sm < 1) per_sm = 1;
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, (long long)n_sms * per_sm));
     cudaMemsetAsync(ctl, 0, 4 * sizeof(uint32_t), st);
-    MC_LAUNCH(tile_build_kernel, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, cell_start, g, rl2, rc2_inner, orig, excl_start,
-              excl_idx, nbr_count, nbr_start, nbr_list, list_cap, tile_cap, split, n_stages, ctl);
+    if (compact)
+        MC_LAUNCH(tile_build_kernel<uint16_t>, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, cell_start, g, rl2, rc2_inner, orig,
+                  excl_start, excl_idx, nbr_count, nbr_start, static_cast<uint16_t *>(nbr_list), list_cap, tile_cap, split, n_stages, ctl);
+    else
+        MC_LAUNCH(tile_build_kernel<uint32_t>, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, cell_start, g, rl2, rc2_inner, orig,
+                  excl_start, excl_idx, nbr_count, nbr_start, static_cast<uint32_t *>(nbr_list), list_cap, tile_cap, split, n_stages, ctl);
     *launches += 1;
 }
