@@ -788,6 +788,17 @@ int comm_allreduce3(mc_ctx *c, double v[3]) {
     return MC_OK;
 }
 
+void comm_rank_size(const mc_ctx *c, int *rank, int *n_ranks) {
+    *rank = c->comm ? c->comm->rank : 0;
+    *n_ranks = c->comm ? c->comm->n : 1;
+}
+
+int comm_allgather_f32_inplace(mc_ctx *c, float *buf, size_t chunk) {
+    CommState *cs = c->comm;
+    MC_NCCL(c, nccl_api().AllGather(buf + (size_t)cs->rank * chunk, buf, chunk, ncclFloat, cs->comm, c->st));
+    return MC_OK;
+}
+
 int comm_allreduce_f4(mc_ctx *c, float4 *buf, int64_t n) {
     CommState *cs = c->comm;
     MC_NCCL(c, nccl_api().AllReduce(buf, buf, (size_t)n * 4, ncclFloat, ncclSum, cs->comm, c->st));

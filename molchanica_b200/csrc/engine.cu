@@ -524,7 +524,7 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         c->use_tile = value != 0.0;
         c->list_valid = false;
     } else if (k == "pair_tile") {
-        c->use_pair_tile = value != 0.0;
+        c->use_pair_tile = value == 0.0 ? 0 : (value == 2.0 ? 2 : 1);
         c->list_valid = false;
     } else if (k == "profiling") {
         c->profiling = value != 0.0;
@@ -652,7 +652,7 @@ int engine_build_rows(mc_ctx *c) {
     const int est_cells = c->periodic ? c->h_grid.ncell : std::max(1, n / 256);
     const int split = std::max(1, std::min(8, (4 * c->n_sms + est_cells - 1) / est_cells));
     // compact rows (16-bit tile-local indices) for the TMA-staged force kernel whenever its tile + LJ table fit shared memory
-    bool compact = tiled && c->use_pair_tile;
+    bool compact = tiled && (c->use_pair_tile == 1 || (c->use_pair_tile == 2 && c->n_rows_sorted() >= 16384));
     while (tiled) {
         // single-pass TMA-staged build (tile_build.cu); tile and list capacities adapt on demand
         MC_CUDA(c, c->tile_need.ensure(4));
@@ -704,6 +704,7 @@ int engine_build_rows(mc_ctx *c) {
     c->list_valid = true;
     c->forces_valid = false;
     c->n_rebuilds++;
+    c->tail_use_split = false;  // a halo descriptor kept for a deferred force evaluation describes the old layout
     c->steps_since_build = 0;
     c->pairs_dirty = true;
     return MC_OK;
@@ -845,17 +846,37 @@ static int ensure_ready(mc_ctx *c, const char *who) {
 
 // mc_step with external forces may return with the last step's force evaluation and second half kick still open
 // (see there).  Every entry point that observes or changes anything but positions closes them first.
-int engine_flush_tail(mc_ctx *c) {
-    if (!c->tail_pending) return MC_OK;
-    cudaSetDevice(c->device);
-    int rc = ensure_ready(c, "mc_step (deferred half kick)");
-    if (rc != MC_OK) return rc;
-    if (!c->forces_valid && (rc = engine_launch_forces(c, false)) != MC_OK) return rc;
+// Closes the step a pipelined mc_step left open: (scheduled rebuild of a decomposed run,) force evaluation of the positions
+// reached, second half kick with THAT call's external forces.  Nothing here synchronises.
+static int close_tail(mc_ctx *c) {
+    int rc;
+    bool fresh_ghosts = false;
+    if (c->tail_rebuild) {
+        if ((rc = comm_rebuild(c)) != MC_OK) return rc;  // every rank of the run is here: same schedule
+        c->tail_rebuild = false;
+        fresh_ghosts = true;
+    } else if ((rc = ensure_ready(c, "mc_step (deferred half kick)")) != MC_OK) {
+        return rc;
+    }
+    if (!c->forces_valid) {
+        const bool use_split = c->tail_use_split && !fresh_ghosts && c->list_valid;
+        if (c->comm_active && !use_split && !fresh_ghosts && (rc = comm_halo_positions(c)) != MC_OK) return rc;
+        if ((rc = engine_launch_forces(c, false, use_split ? &c->tail_split : nullptr)) != MC_OK) return rc;
+    }
+    c->tail_use_split = false;
     const size_t r0 = (size_t)c->row0;
     launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, c->tail_ext,
                       c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, 0.5f * c->tail_dt, 0.f, 0.f, 0.f,
                       c->rebuild_flag.p, c->st, &c->launches);
     c->tail_pending = false;
+    return MC_OK;
+}
+
+int engine_flush_tail(mc_ctx *c) {
+    if (!c->tail_pending) return MC_OK;
+    cudaSetDevice(c->device);
+    int rc = close_tail(c);
+    if (rc != MC_OK) return rc;
     MC_CUDA(c, cudaStreamSynchronize(c->st));
     return MC_OK;
 }
@@ -910,46 +931,59 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     // with the PREVIOUS array and only then waits for the upload.  Everything that observes more than positions
     // closes the tail first (engine_flush_tail), so the deferral is invisible through the ABI.
     const bool baro = c->baro_kind != MC_BAROSTAT_NONE && c->periodic && !c->comm_active;
-    const bool defer = c->defer_tail && ext_forces != nullptr && pipelined && n_steps > 0 && !baro;
+    // (a decomposed run rebuilds on its schedule, known to every rank: nothing to pipeline there, the deferral works as is)
+    const bool defer = c->defer_tail && ext_forces != nullptr && (pipelined || (c->comm_active && !c->sync_rebuild)) && n_steps > 0 && !baro;
     struct UploadGuard {  // whatever path leaves this function, the caller's array is no longer being read
         cudaStream_t s = nullptr;
         ~UploadGuard() { if (s) cudaStreamSynchronize(s); }
     } upload_guard;
     const float *d_ext = nullptr;
     bool wait_upload = false;
+    size_t gather_chunk = 0;  // decomposed: floats per rank of the all-gather that completes the array on every rank
     if (ext_forces) {
         DevBuf<float> &buf = c->ext_k ? c->ext_force2 : c->ext_force;
         c->ext_k ^= 1;
-        MC_CUDA(c, buf.ensure((size_t)3 * c->n_global));
+        // A decomposed rank uploads only ITS 1/N of the caller's array (a contiguous block of original ids) over its own
+        // PCIe link; the blocks are then exchanged over NVLink (one in-place ncclAllGather on the engine stream), so the
+        // host-to-device traffic per rank shrinks with N instead of every rank pulling the whole array.
+        int rank = 0, n_ranks = 1;
+        if (c->comm_active) comm_rank_size(c, &rank, &n_ranks);
+        const size_t total = (size_t)3 * c->n_global;
+        const size_t chunk = c->comm_active ? (total + n_ranks - 1) / n_ranks : total;
+        const size_t lo = std::min(total, (size_t)rank * chunk), cnt = std::min(chunk, total - lo);
+        MC_CUDA(c, buf.ensure(chunk * (size_t)n_ranks));
+        if (c->comm_active) gather_chunk = chunk;
+        c->ext_upload_bytes = (int64_t)(cnt * sizeof(float));
         if (defer) {
             if (!c->st_up) {
                 MC_CUDA(c, cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking));
                 MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
             }
             upload_guard.s = c->st_up;
-            MC_CUDA(c, cudaMemcpyAsync(buf.p, ext_forces, sizeof(float) * 3 * c->n_global, cudaMemcpyHostToDevice, c->st_up));
+            if (cnt) MC_CUDA(c, cudaMemcpyAsync(buf.p + lo, ext_forces + lo, sizeof(float) * cnt, cudaMemcpyHostToDevice, c->st_up));
             MC_CUDA(c, cudaEventRecord(c->ev_up, c->st_up));
             wait_upload = true;
-        } else {
-            MC_CUDA(c, cudaMemcpyAsync(buf.p, ext_forces, sizeof(float) * 3 * c->n_global, cudaMemcpyHostToDevice, st));
+        } else if (cnt) {
+            MC_CUDA(c, cudaMemcpyAsync(buf.p + lo, ext_forces + lo, sizeof(float) * cnt, cudaMemcpyHostToDevice, st));
         }
         d_ext = buf.p;
+    } else {
+        c->ext_upload_bytes = 0;
     }
-    int rc = ensure_ready(c, "mc_step");
-    if (rc != MC_OK) return rc;
-    if (!c->forces_valid) {
-        if (c->comm_active && (rc = comm_halo_positions(c)) != MC_OK) return rc;
-        if ((rc = engine_launch_forces(c, false)) != MC_OK) return rc;
-    }
+    int rc;
     if (c->tail_pending) {
-        // second half kick of the step the previous call left open, with THAT call's external forces
-        const size_t r0 = (size_t)c->row0;
-        launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, c->tail_ext,
-                          c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, 0.5f * c->tail_dt, 0.f, 0.f, 0.f,
-                          c->rebuild_flag.p, st, &c->launches);
-        c->tail_pending = false;
+        // the step the previous call left open: its force evaluation (it does not depend on the new array) runs under the
+        // upload started above, then its second half kick with THAT call's external forces
+        if ((rc = close_tail(c)) != MC_OK) return rc;
+    } else {
+        if ((rc = ensure_ready(c, "mc_step")) != MC_OK) return rc;
+        if (!c->forces_valid) {
+            if (c->comm_active && (rc = comm_halo_positions(c)) != MC_OK) return rc;
+            if ((rc = engine_launch_forces(c, false)) != MC_OK) return rc;
+        }
     }
     if (wait_upload) MC_CUDA(c, cudaStreamWaitEvent(st, c->ev_up, 0));
+    if (gather_chunk && (rc = comm_allgather_f32_inplace(c, const_cast<float *>(d_ext), gather_chunk)) != MC_OK) return rc;
     // Velocity Verlet, two kernels per step: [kick + drift] and [pair forces].  The second half
     // kick of step s and the first half kick of step s+1 are one full kick in the same launch.
     // The rebuild decision is pipelined: kick_drift raises the flag with a look-ahead margin, the
@@ -1035,6 +1069,9 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         if (defer && s == n_steps - 1) {
             // last step of a pipelined call: stop after the drift.  Its flag word is read after the final
             // synchronisation below (no rebuild has happened since it was written, so it is never stale).
+            c->tail_rebuild = c->comm_active && c->steps_since_build >= comm_interval(c);
+            c->tail_use_split = fused_halo && !c->tail_rebuild;
+            c->tail_split = split;
             have_prev = true;
             skip_prev = false;
             c->forces_valid = false;

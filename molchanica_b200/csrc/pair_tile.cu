@@ -45,22 +45,69 @@ struct PtMeta {
 
 // One row: entries k = 2 sub, 2 sub + 1 of every group of 2 LANES entries -- a lane reads its two 16-bit indices as one
 // 32-bit word (8 lanes = one 32-byte sector of the index stream), gathers both atoms from the tile, then does the math.
+// The next word is requested before the current one is used (the index stream comes from HBM / L2, the only long-latency
+// access of the loop).  An odd row length leaves the second entry of the last word as padding: it is gathered from the
+// first entry's slot and masked by a cutoff below zero.
+constexpr int PT_WORDS = 6;  // index words a lane holds in registers: rows up to 2 * LANES * PT_WORDS = 96 entries in one batch
+
 template <bool MULTI, int COUL, bool WRAP, bool ENERGY>
 __device__ __forceinline__ void row_loop_tile(const float4 xi, const uint32_t *__restrict__ lst32, uint32_t cnt, int sub,
                                               const float4 *tile, const uint16_t *ttype, const float2 *row,
                                               const NbParams &p, bool lj_on, Acc &a) {
     const float2 lj1 = make_float2(p.sig2, p.eps24);
     const float rc2_lj = lj_on ? p.rc2_lj : -1.f;
-    for (uint32_t k = 2u * (uint32_t)sub; k < cnt; k += 2u * PT_LANES) {
-        const uint32_t w = __ldg(lst32 + (k >> 1));
-        const uint32_t j0 = w & 0xffffu;
-        const bool has1 = k + 1u < cnt;
-        const uint32_t j1 = has1 ? (w >> 16) : j0;
-        const float4 x0 = tile[j0], x1 = tile[j1];
-        float2 l0 = lj1, l1 = lj1;
-        if (MULTI) { l0 = row[ttype[j0]]; l1 = row[ttype[j1]]; }
-        pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, rc2_lj, a);
-        if (has1) pair_term<COUL, WRAP, ENERGY>(xi, x1, l1, p, rc2_lj, a);
+    const uint32_t nw = (cnt + 1u) >> 1;  // index words of this row
+    // The index stream is the one long-latency access of this kernel (HBM / L2).  All words of a lane are requested in
+    // ONE batch before any of them is used -- one memory round trip per row instead of one per trip of the loop; rows
+    // longer than a batch take another.
+    for (uint32_t w0 = (uint32_t)sub; w0 < nw; w0 += PT_LANES * PT_WORDS) {
+        uint32_t words[PT_WORDS];
+#pragma unroll
+        for (int t = 0; t < PT_WORDS; ++t) {
+            const uint32_t wi = w0 + (uint32_t)t * PT_LANES;
+            words[t] = wi < nw ? __ldg(lst32 + wi) : 0u;
+        }
+        if constexpr (COUL == MC_COULOMB_NONE && !ENERGY) {
+            // packed path: two pairs per instruction (pair_terms.cuh)
+            const float s6c = lj1.x * lj1.x * lj1.x;  // sigma^6
+            float2 c12 = make_float2(2.f * lj1.y * s6c * s6c, 2.f * lj1.y * s6c * s6c), c6n = make_float2(-lj1.y * s6c, -lj1.y * s6c);
+            Acc2 b = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+            for (int t = 0; t < PT_WORDS; ++t) {
+                const uint32_t wi = w0 + (uint32_t)t * PT_LANES;
+                if (wi < nw) {
+                    const uint32_t cur = words[t];
+                    const bool has1 = 2u * wi + 1u < cnt;
+                    const uint32_t j0 = cur & 0xffffu, j1 = has1 ? (cur >> 16) : j0;
+                    const float4 x0 = tile[j0], x1 = tile[j1];
+                    if (MULTI) {
+                        const float2 l0 = row[ttype[j0]], l1 = row[ttype[j1]];  // (c12, -c6) per type pair (staged by the kernel)
+                        c12 = make_float2(l0.x, l1.x);
+                        c6n = make_float2(l0.y, l1.y);
+                    }
+                    pair_term2_lj<WRAP>(xi, x0, x1, c12, c6n, p, rc2_lj, has1 ? rc2_lj : -1.f, b);
+                }
+            }
+            // d was x_j - x_i: flip the sign once
+            a.fx -= b.fx.x + b.fx.y;
+            a.fy -= b.fy.x + b.fy.y;
+            a.fz -= b.fz.x + b.fz.y;
+        } else {
+#pragma unroll
+            for (int t = 0; t < PT_WORDS; ++t) {
+                const uint32_t wi = w0 + (uint32_t)t * PT_LANES;
+                if (wi < nw) {
+                    const uint32_t cur = words[t];
+                    const bool has1 = 2u * wi + 1u < cnt;
+                    const uint32_t j0 = cur & 0xffffu, j1 = has1 ? (cur >> 16) : j0;
+                    const float4 x0 = tile[j0], x1 = tile[j1];
+                    float2 l0 = lj1, l1 = lj1;
+                    if (MULTI) { l0 = row[ttype[j0]]; l1 = row[ttype[j1]]; }
+                    pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, rc2_lj, a);
+                    if (has1) pair_term<COUL, WRAP, ENERGY>(xi, x1, l1, p, rc2_lj, a);
+                }
+            }
+        }
     }
 }
 
@@ -102,7 +149,14 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
         }
     }
     if (MULTI)
-        for (int t = threadIdx.x; t < nt2; t += blockDim.x) s_tab[t] = A.ljtab[t];
+        for (int t = threadIdx.x; t < nt2; t += blockDim.x) {
+            float2 l = A.ljtab[t];  // (sigma^2, 24 eps)
+            if (COUL == MC_COULOMB_NONE && !ENERGY) {  // the packed LJ path takes (48 eps sigma^12, -24 eps sigma^6)
+                const float s6c = l.x * l.x * l.x;
+                l = make_float2(2.f * l.y * s6c * s6c, -l.y * s6c);
+            }
+            s_tab[t] = l;
+        }
     __syncthreads();
 
     // item order: layers that need no ghost first, then the first and the last row layer (decomposed ranks only)

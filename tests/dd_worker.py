@@ -1,5 +1,8 @@
 """One rank of a domain-decomposed run (spawned by tests/test_gpu_multi.py, one process per GPU).
-usage: dd_worker.py <rank> <world> <id_file> <case> <out_npz> [fused|nccl] [fixed|adaptive|allgather]"""
+usage: dd_worker.py <rank> <world> <id_file> <case> <out_npz> [fused|nccl] [fixed|adaptive|allgather]
+DD_EXT=<k>: the steps are taken in calls of k steps, each with its own external-force array (ext_forces_for_call), through
+the pipelined upload (option defer_tail = DD_DEFER, default 1): a decomposed rank uploads its 1/N block of the array and the
+blocks are all-gathered over NCCL."""
 import ctypes as C
 import os
 import sys
@@ -27,6 +30,13 @@ def case_workload(name, world=2):
         w["skin"] = float(os.environ.get("DD_SKIN", w["skin"]))
         return w, int(os.environ.get("DD_STEPS", "30"))
     raise ValueError(name)
+
+
+def ext_forces_for_call(n, k):
+    """external forces of call k: every 7th atom, offset k, seeded -- the same arrays on every rank and in the test"""
+    ext = np.zeros((n, 3), np.float32)
+    ext[k % 7::7] = np.random.default_rng(1000 + k).normal(0, 3.0, ext[k % 7::7].shape)
+    return ext
 
 
 def main():
@@ -64,7 +74,13 @@ def main():
     f0 = e.forces()
     en0 = e.energy()
     st0 = e.stats()
-    e.step(w["dt"], n_steps)
+    per_call = int(os.environ.get("DD_EXT", "0"))
+    if per_call:
+        e.set_option("defer_tail", int(os.environ.get("DD_DEFER", "1")))
+        for k in range(n_steps // per_call):
+            e.step(w["dt"], per_call, ext_forces_for_call(len(w["xyzq"]), k))
+    else:
+        e.step(w["dt"], n_steps)
     x = e.positions()
     v = e.velocities()
     st = e.stats()
@@ -78,7 +94,8 @@ def main():
     snap_ok = n_snap == own and np.array_equal(sp[:n_snap], x[si[:n_snap]])
     if rank == 0:
         np.savez(out, fused=fused, why=why, snap_ok=snap_ok, interval=interval, disp_frac=disp_frac, f0=f0, x=x, v=v, e_pot=en0["energy_potential_nonbonded"], n_owned=st0["n_atoms"],
-                 n_ghosts=st0["n_ghosts"], rebuilds=st["n_rebuilds"], violations=st["n_list_violations"])
+                 n_ghosts=st0["n_ghosts"], rebuilds=st["n_rebuilds"], violations=st["n_list_violations"],
+                 ext_upload_bytes=st["ext_upload_bytes"])
     e.close()
 
 

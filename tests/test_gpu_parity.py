@@ -54,6 +54,49 @@ def test_neighbour_list_bit_exact_and_forces(name, Engine, oracle):
     e.close()
 
 
+@pytest.mark.parametrize("name", ["lj1728", "lj8000", "water648", "glob1231", "solv5100"])
+@pytest.mark.parametrize("erfc", [0, 1])
+def test_tile_kernel_matches_the_oracle(name, erfc, Engine, oracle):
+    """pair_tile.cu (TMA-staged tile, compact rows of 16-bit tile-local indices, packed fp32) forced on for systems below
+    its automatic threshold: periodic and vacuum grids, one and many LJ types, no / plain / erfc Coulomb, exclusions and 1-4
+    pairs, energies, and the expansion of the compact rows back to global indices (mc_get_neighbors) -- same bars as above."""
+    w = W.solvated_c3(n_protein=600, n_water=1500, L=40.0) if name == "solv5100" else _cases()[name]()
+    if erfc:
+        if w["coul_mode"] == 0:
+            pytest.skip("no charges")
+        w = dict(w, coul_mode=2)
+    e = Engine.from_workload(w)
+    e.set_option("pair_tile", 1)
+    e.build_neighbors()
+    st = e.stats()
+    assert st["list_bytes"] < 2.2 * max(st["n_pairs_listed"], 1) + 64 * len(w["xyzq"]), "the compact list is not in use"
+    start, idx = e.neighbors()
+    o_start, o_idx = oracle.neighbors(w)
+    assert np.array_equal(start, o_start) and np.array_equal(idx, o_idx)
+    e.compute_forces()
+    f = e.forces()
+    f64, sumabs, en = oracle.forces(w, (o_start, o_idx), precision=64)
+    err = force_rel_err(f, f64, sumabs)
+    assert err.max() < FORCE_RTOL, f"max force error {err.max():.3e} at atom {err.argmax()}"
+    assert energy_close(e.energy()["energy_potential_nonbonded"], en.sum(), f64[:, 3])
+    assert np.abs(f[:, 3] - f64[:, 3]).max() < 1e-5 * max(1.0, float(np.abs(f64[:, 3]).max()))
+    n_steps = 20 if name.startswith("lj") else 6
+    dt = w["dt"] * (0.05 if name == "solv5100" else 1.0)  # (the unbonded solvated box has free hydrogens: keep them inside the skin)
+    e.step(dt, n_steps)   # the step path runs the instantiation without energies (packed arithmetic for LJ-only systems)
+    ref = oracle.md_run(dict(w, dt=dt), n_steps, precision=64)
+    ok, worst, scale = trajectory_close(e.positions(), ref["xyzq"], w["xyzq"], w["box_ext"] if w["periodic"] else None)
+    assert ok, (worst, scale)
+    # forces of the packed / energy-free instantiation against the gather kernel on the positions just reached
+    e.compute_forces()
+    f_tile = e.forces()
+    e.set_option("pair_tile", 0)
+    e.compute_forces()
+    f_gather = e.forces()
+    scale = np.abs(f_gather[:, :3]).max() + 1e-30
+    assert np.abs(f_tile[:, :3] - f_gather[:, :3]).max() < 2e-5 * scale
+    e.close()
+
+
 @pytest.mark.parametrize("lanes", [4, 8, 16, 32])
 def test_every_lane_width_gives_the_same_forces(lanes, Engine, oracle):
     w = W.solvated_c3()

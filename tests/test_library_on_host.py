@@ -99,6 +99,41 @@ def test_decomposed_run_on_the_host_build(case, world, halo, sched, host_env, or
         assert int(r["interval"]) >= 10 and int(r["rebuilds"]) >= 2 and 0.0 < float(r["disp_frac"]) < 1.0
 
 
+@pytest.mark.parametrize("world,halo,per_call,defer", [(2, "fused", 1, 1), (2, "fused", 3, 1), (4, "fused", 1, 1), (2, "nccl", 1, 1), (2, "fused", 1, 0)])
+def test_decomposed_external_forces_on_the_host_build(world, halo, per_call, defer, host_env, oracle):
+    """mc_step(dt, k, ext) on a decomposed handle: every rank uploads its 1/N block of the caller's array, the blocks are
+    all-gathered over NCCL, and the call returns after its last drift (the open force evaluation, its halo wait and -- when
+    the schedule says so -- its rebuild run at the start of the next call, under that call's upload).  The trajectory must be
+    the oracle's, call by call with the same arrays, in both halo modes, across rebuilds, with the deferral on and off."""
+    import tempfile
+
+    import numpy as np
+    sys.path.insert(0, HERE)
+    from dd_worker import case_workload, ext_forces_for_call
+    from util import trajectory_close
+    env = dict(host_env, MOLCHANICA_NCCL_LIB=os.path.join(HERE, "cpp", "_build", "libnccl_standin.so"), MC_SHIM_THREADS="2",
+               MC_SHIM_SHARED_HEAP="1" if halo == "fused" else "0", DD_EXT=str(per_call), DD_DEFER=str(defer))
+    d = tempfile.mkdtemp()
+    idf, out = os.path.join(d, "nccl_id"), os.path.join(d, "out.npz")
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dd_worker.py"), str(r), str(world), idf, "lj", out, halo, "fixed"],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT) for r in range(world)]
+    logs = [p.communicate(timeout=900)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    r = np.load(out)
+    w, n_steps = case_workload("lj", world)
+    n = len(w["xyzq"])
+    cur = dict(w)
+    for k in range(n_steps // per_call):
+        ref = oracle.md_run(cur, per_call, precision=64, ext_force=ext_forces_for_call(n, k))
+        cur = dict(cur, xyzq=ref["xyzq"], vel=ref["vel"])
+    ok, worst, sc = trajectory_close(r["x"], cur["xyzq"], w["xyzq"], w["box_ext"])
+    assert ok, (worst, sc)
+    verr = np.abs(r["v"][:, :3] - cur["vel"][:, :3]).max(1)
+    assert np.quantile(verr, 0.99) < 2e-4 * max(float(np.abs(cur["vel"][:, :3]).max()), 1.0)
+    assert int(r["violations"]) == 0 and bool(r["snap_ok"]) and int(r["rebuilds"]) >= 3
+    assert int(r["ext_upload_bytes"]) <= 12 * n // world + 64  # this rank moved its block only
+
+
 def test_cpp_host_mirror_runs_on_the_host_build(host_env, tmp_path):
     """include/molchanica_md.hpp (the C++ mirror of the reference's MdState interface) driven by tests/cpp/host_mirror_smoke.cpp,
     its libmolchanica_md.so resolved to the host build: known two-body answers, stepping, NPT configuration, snapshots."""
