@@ -525,6 +525,7 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         c->list_valid = false;
     } else if (k == "pair_tile") {
         c->use_pair_tile = value == 0.0 ? 0 : (value == 2.0 ? 2 : 1);
+        c->pair_tile_fits = true;
         c->list_valid = false;
     } else if (k == "profiling") {
         c->profiling = value != 0.0;
@@ -652,11 +653,10 @@ int engine_build_rows(mc_ctx *c) {
     const int est_cells = c->periodic ? c->h_grid.ncell : std::max(1, n / 256);
     const int split = std::max(1, std::min(8, (4 * c->n_sms + est_cells - 1) / est_cells));
     // compact rows (16-bit tile-local indices) for the TMA-staged force kernel whenever its tile + LJ table fit shared memory
-    bool compact = tiled && (c->use_pair_tile == 1 || (c->use_pair_tile == 2 && c->n_rows_sorted() >= 16384));
+    bool compact = tiled && c->pair_tile_fits && (c->use_pair_tile == 1 || (c->use_pair_tile == 2 && c->n_rows_sorted() >= 16384));
     while (tiled) {
         // single-pass TMA-staged build (tile_build.cu); tile and list capacities adapt on demand
-        MC_CUDA(c, c->tile_need.ensure(4));
-        if (compact && pair_tile_smem(c->tile_cap, c->n_types, c->n_types > 1, nullptr) == 0) compact = false;
+        MC_CUDA(c, c->tile_need.ensure(8));
         if (compact) { if (!c->nbr_list16.p) MC_CUDA(c, c->nbr_list16.ensure(1024)); }
         else if (!c->nbr_list.p) MC_CUDA(c, c->nbr_list.ensure(1024));
         const size_t cap_now = compact ? c->nbr_list16.n : c->nbr_list.n;
@@ -664,7 +664,7 @@ int engine_build_rows(mc_ctx *c) {
                           c->orig[c->cur].p, es, ei, c->nbr_count.p, c->nbr_start.p,
                           compact ? static_cast<void *>(c->nbr_list16.p) : static_cast<void *>(c->nbr_list.p), compact,
                           (uint32_t)std::min<size_t>(cap_now, 0xffffffffu), c->tile_cap, c->tile_need.p, st, &c->launches);
-        MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->tile_need.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->tile_need.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         MC_CUDA(c, cudaStreamSynchronize(st));
         if (h_ctl[3] != 0) {  // a neighbourhood did not fit the tile
             uint32_t need = (h_ctl[2] + h_ctl[2] / 4 + 127u) & ~31u;  // 25 % head-room + NaN padding to whole chunks
@@ -681,7 +681,14 @@ int engine_build_rows(mc_ctx *c) {
             continue;
         }
         c->tile_max_m = (h_ctl[2] + 31u) & ~31u;
-        if (compact && pair_tile_smem(c->tile_max_m, c->n_types, c->n_types > 1, nullptr) == 0) { compact = false; continue; }
+        c->rows_max_entries = h_ctl[4];
+        // the TMA-staged force kernel wants every cell's rows as one block of <= 32 rows next to the tile in shared memory:
+        // a system that is too dense for that (seen only now) is built again with global-slot rows, and stays that way
+        if (compact && (h_ctl[5] > 32u || pair_tile_smem(c->tile_max_m, c->rows_max_entries, c->n_types, c->n_types > 1, nullptr, nullptr) == 0)) {
+            compact = false;
+            c->pair_tile_fits = false;
+            continue;
+        }
         break;
     }
     if (!tiled) {
@@ -784,6 +791,7 @@ int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs) {
         T.nbr_start = L.nbr_start; T.nbr_count = L.nbr_count; T.list16 = c->nbr_list16.p; T.ljtab = L.ljtab;
         T.p = L.p; T.lj_on = L.lj_on; T.coul = L.coul; T.multi = L.multi; T.energy = L.energy; T.force = L.force;
         T.tile_cap = c->tile_max_m;
+        T.rows_max_entries = c->rows_max_entries;
         if (!c->pair_ctl.p) {
             MC_CUDA(c, c->pair_ctl.ensure(4));
             MC_CUDA(c, cudaMemsetAsync(c->pair_ctl.p, 0, 4 * sizeof(uint32_t), c->st));

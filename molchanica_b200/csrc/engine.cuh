@@ -89,9 +89,11 @@ struct mc_ctx {
     int use_pair_tile = 2;     // option "pair_tile": compact rows (16-bit tile-local indices) + TMA-staged force kernel (pair_tile.cu):
                                // 0 off, 1 on, 2 (default) on for systems of >= 16384 atoms (below that the persistent
                                // kernel's fixed cost outweighs it: C2 measured 17.0k steps/s with it, 24.6k without)
+    bool pair_tile_fits = true; // cleared when a build showed the system too dense for pair_tile.cu (cells of > 32 atoms, rows too long)
     bool list_compact = false; // the current list is in compact form (nbr_list16)
     bool list32_valid = false; // nbr_list holds the current list as global slots (expanded on demand from the compact form)
     uint32_t tile_max_m = 0;   // largest tile (atoms) of the current build = stage capacity of the force kernel
+    uint32_t rows_max_entries = 0;  // largest row block (16-bit entries) one 32-atom pass of the build allocated
 
     // counters
     int64_t n_list_violations = 0;

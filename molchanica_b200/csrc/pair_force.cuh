@@ -54,9 +54,10 @@ struct PairTileLaunch {
     bool multi, energy;
     float4 *force;
     uint32_t tile_cap;
+    uint32_t rows_max_entries;  // largest row block of a <= 32-atom cell (the kernel stages such blocks in shared memory when they fit)
     uint32_t *ctl;
     HaloWait wait{};
 };
 cudaError_t pair_tile_prepare();
-size_t pair_tile_smem(uint32_t tile_cap, int n_types, bool multi, int *n_stages_out);
+size_t pair_tile_smem(uint32_t tile_cap, uint32_t rows_max_entries, int n_types, bool multi, int *n_stages_out, uint32_t *rows_cap_out);
 void launch_pair_tile(const PairTileLaunch &L, cudaStream_t st, int64_t *launches);

@@ -28,7 +28,7 @@
 namespace {
 
 #ifndef MC_PT_WARPS
-#define MC_PT_WARPS 8  // consumer warps per CTA
+#define MC_PT_WARPS 7  // consumer warps per CTA (7 + the producer = 256 threads: five CTAs per SM at 48 registers)
 #endif
 #ifndef MC_PT_MIN_BLOCKS
 #define MC_PT_MIN_BLOCKS 5
@@ -44,69 +44,51 @@ struct PtMeta {
 };
 
 // One row: entries k = 2 sub, 2 sub + 1 of every group of 2 LANES entries -- a lane reads its two 16-bit indices as one
-// 32-bit word (8 lanes = one 32-byte sector of the index stream), gathers both atoms from the tile, then does the math.
-// The next word is requested before the current one is used (the index stream comes from HBM / L2, the only long-latency
-// access of the loop).  An odd row length leaves the second entry of the last word as padding: it is gathered from the
-// first entry's slot and masked by a cutoff below zero.
-constexpr int PT_WORDS = 6;  // index words a lane holds in registers: rows up to 2 * LANES * PT_WORDS = 96 entries in one batch
-
+// 32-bit word (8 lanes = 32 consecutive bytes of the index stream), gathers both atoms from the tile, then does the math.
+// The row itself sits in shared memory as well (staged by the producer with the tile): the loop touches no global memory.  An odd row length leaves the second entry of the last word
+// as padding: it is gathered from the first entry's slot and masked by a cutoff below zero.
 template <bool MULTI, int COUL, bool WRAP, bool ENERGY>
-__device__ __forceinline__ void row_loop_tile(const float4 xi, const uint32_t *__restrict__ lst32, uint32_t cnt, int sub,
+__device__ __forceinline__ void row_loop_tile(const float4 xi, const uint32_t *lst32, uint32_t cnt, int sub,
                                               const float4 *tile, const uint16_t *ttype, const float2 *row,
-                                              const NbParams &p, bool lj_on, Acc &a) {
-    const float2 lj1 = make_float2(p.sig2, p.eps24);
-    const float rc2_lj = lj_on ? p.rc2_lj : -1.f;
+                                              const NbParams &p, const float rc2_lj, const float2 c12_1, const float2 c6n_1, Acc &a) {
     const uint32_t nw = (cnt + 1u) >> 1;  // index words of this row
-    // The index stream is the one long-latency access of this kernel (HBM / L2).  All words of a lane are requested in
-    // ONE batch before any of them is used -- one memory round trip per row instead of one per trip of the loop; rows
-    // longer than a batch take another.
-    for (uint32_t w0 = (uint32_t)sub; w0 < nw; w0 += PT_LANES * PT_WORDS) {
-        uint32_t words[PT_WORDS];
-#pragma unroll
-        for (int t = 0; t < PT_WORDS; ++t) {
-            const uint32_t wi = w0 + (uint32_t)t * PT_LANES;
-            words[t] = wi < nw ? __ldg(lst32 + wi) : 0u;
+    uint32_t wi = (uint32_t)sub;
+    uint32_t word = wi < nw ? lst32[wi] : 0u;
+    if constexpr (COUL == MC_COULOMB_NONE && !ENERGY) {
+        // packed path: two pairs per instruction (pair_terms.cuh)
+        float2 c12 = c12_1, c6n = c6n_1;
+        Acc2 b = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        while (wi < nw) {
+            const uint32_t cur = word;
+            const bool has1 = 2u * wi + 1u < cnt;
+            wi += PT_LANES;
+            if (wi < nw) word = lst32[wi];
+            const uint32_t j0 = cur & 0xffffu, j1 = has1 ? (cur >> 16) : j0;
+            const float4 x0 = tile[j0], x1 = tile[j1];
+            if (MULTI) {
+                const float2 l0 = row[ttype[j0]], l1 = row[ttype[j1]];  // (c12, -c6) per type pair (staged by the kernel)
+                c12 = make_float2(l0.x, l1.x);
+                c6n = make_float2(l0.y, l1.y);
+            }
+            pair_term2_lj<WRAP>(xi, x0, x1, c12, c6n, p, rc2_lj, has1 ? rc2_lj : -1.f, b);
         }
-        if constexpr (COUL == MC_COULOMB_NONE && !ENERGY) {
-            // packed path: two pairs per instruction (pair_terms.cuh)
-            const float s6c = lj1.x * lj1.x * lj1.x;  // sigma^6
-            float2 c12 = make_float2(2.f * lj1.y * s6c * s6c, 2.f * lj1.y * s6c * s6c), c6n = make_float2(-lj1.y * s6c, -lj1.y * s6c);
-            Acc2 b = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-            for (int t = 0; t < PT_WORDS; ++t) {
-                const uint32_t wi = w0 + (uint32_t)t * PT_LANES;
-                if (wi < nw) {
-                    const uint32_t cur = words[t];
-                    const bool has1 = 2u * wi + 1u < cnt;
-                    const uint32_t j0 = cur & 0xffffu, j1 = has1 ? (cur >> 16) : j0;
-                    const float4 x0 = tile[j0], x1 = tile[j1];
-                    if (MULTI) {
-                        const float2 l0 = row[ttype[j0]], l1 = row[ttype[j1]];  // (c12, -c6) per type pair (staged by the kernel)
-                        c12 = make_float2(l0.x, l1.x);
-                        c6n = make_float2(l0.y, l1.y);
-                    }
-                    pair_term2_lj<WRAP>(xi, x0, x1, c12, c6n, p, rc2_lj, has1 ? rc2_lj : -1.f, b);
-                }
-            }
-            // d was x_j - x_i: flip the sign once
-            a.fx -= b.fx.x + b.fx.y;
-            a.fy -= b.fy.x + b.fy.y;
-            a.fz -= b.fz.x + b.fz.y;
-        } else {
-#pragma unroll
-            for (int t = 0; t < PT_WORDS; ++t) {
-                const uint32_t wi = w0 + (uint32_t)t * PT_LANES;
-                if (wi < nw) {
-                    const uint32_t cur = words[t];
-                    const bool has1 = 2u * wi + 1u < cnt;
-                    const uint32_t j0 = cur & 0xffffu, j1 = has1 ? (cur >> 16) : j0;
-                    const float4 x0 = tile[j0], x1 = tile[j1];
-                    float2 l0 = lj1, l1 = lj1;
-                    if (MULTI) { l0 = row[ttype[j0]]; l1 = row[ttype[j1]]; }
-                    pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, rc2_lj, a);
-                    if (has1) pair_term<COUL, WRAP, ENERGY>(xi, x1, l1, p, rc2_lj, a);
-                }
-            }
+        // d was x_j - x_i: flip the sign once
+        a.fx -= b.fx.x + b.fx.y;
+        a.fy -= b.fy.x + b.fy.y;
+        a.fz -= b.fz.x + b.fz.y;
+    } else {
+        const float2 lj1 = make_float2(p.sig2, p.eps24);
+        while (wi < nw) {
+            const uint32_t cur = word;
+            const bool has1 = 2u * wi + 1u < cnt;
+            wi += PT_LANES;
+            if (wi < nw) word = lst32[wi];
+            const uint32_t j0 = cur & 0xffffu, j1 = has1 ? (cur >> 16) : j0;
+            const float4 x0 = tile[j0], x1 = tile[j1];
+            float2 l0 = lj1, l1 = lj1;
+            if (MULTI) { l0 = row[ttype[j0]]; l1 = row[ttype[j1]]; }
+            pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, rc2_lj, a);
+            if (has1) pair_term<COUL, WRAP, ENERGY>(xi, x1, l1, p, rc2_lj, a);
         }
     }
 }
@@ -123,6 +105,7 @@ struct PairTileArgs {
     int lj_on;
     float4 *force;
     uint32_t tile_cap;   // atoms per stage (multiple of 32)
+    uint32_t rows_cap;   // 16-bit entries of the row block a stage holds (multiple of 8)
     int n_stages;
     uint32_t *ctl;       // [0] work counter, [1] CTAs that have drained, [3] a tile did not fit (never, if the build fitted)
     HaloWait wait;       // decomposed rank, fused halo: ready flags of this epoch (ready_prev == nullptr: none)
@@ -133,11 +116,15 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
     MC_DYN_SHARED_ALIGNED(unsigned char, smem_raw, 128);
     __shared__ __align__(8) uint64_t full_bar[PT_MAX_STAGES], empty_bar[PT_MAX_STAGES];
     __shared__ PtMeta meta[PT_MAX_STAGES];
-    // dynamic shared memory: [LJ table (MULTI)] then per stage tile_cap float4 positions (+ tile_cap u16 types when MULTI)
+    __shared__ uint32_t row_tab[PT_MAX_STAGES][32];  // per staged row: word offset inside the block << 16 | entries
+    // dynamic shared memory: [LJ table (MULTI)] then per stage: tile_cap float4 positions, rows_cap 16-bit list entries
+    // (the cell's row block), tile_cap u16 types when MULTI
     const int nt2 = MULTI ? A.p.n_types * A.p.n_types : 0;
     float2 *s_tab = reinterpret_cast<float2 *>(smem_raw);
     unsigned char *stage0 = smem_raw + (((size_t)nt2 * sizeof(float2) + 127) & ~(size_t)127);
-    const size_t stage_bytes = (size_t)A.tile_cap * (sizeof(float4) + (MULTI ? sizeof(uint16_t) : 0));
+    const size_t rows_off = (size_t)A.tile_cap * sizeof(float4);
+    const size_t type_off = rows_off + (size_t)A.rows_cap * sizeof(uint16_t);
+    const size_t stage_bytes = (type_off + (MULTI ? (size_t)A.tile_cap * sizeof(uint16_t) : 0) + 15) & ~(size_t)15;
     const int n_stages = A.n_stages;
 
     const GridParams g = *A.gp;
@@ -178,6 +165,7 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
             uint32_t a0 = 0xffffffffu, a1 = 0xffffffffu;
             TilePlan P;
             P.m = 0; P.self_off = 0; P.wrap = 0; P.r0 = P.r1 = TileRange{0u, 0u, 0u};
+            uint32_t blk_src = 0, blk_entries = 0, my_tab = 0;
             if (!done) {
                 int c;
                 bool boundary = false;
@@ -196,6 +184,21 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
                     if (lane == 0) A.ctl[3] = 1u;
                     continue;
                 }
+                // The rows of a cell (<= 32 atoms: the launcher checked the build's maxima) are ONE contiguous block of the list
+                // -- tile_build.cu allocates them with one cursor bump, in atom order.  The block travels with the tile, and
+                // with it an (offset, count) table, so that the consumers never wait for global memory.
+                const uint32_t na = a1 - a0;
+                uint32_t st = 0, cn = 0;
+                if ((uint32_t)lane < na) { st = __ldg(A.nbr_start + a0 + lane); cn = __ldg(A.nbr_count + a0 + lane); }
+                blk_src = __shfl_sync(MC_FULL_MASK, st, 0);
+                const uint32_t end_l = st + ((cn + 7u) & ~7u);
+                blk_entries = __shfl_sync(MC_FULL_MASK, end_l, (int)min(na, 32u) - 1) - blk_src;
+                my_tab = (((st - blk_src) >> 1) << 16) | (cn & 0xffffu);
+                const bool okl = (uint32_t)lane >= na || (st >= blk_src && end_l - blk_src <= A.rows_cap && cn <= 0xffffu);
+                if (!__all_sync(MC_FULL_MASK, okl) || na > 32u || blk_entries > A.rows_cap || (blk_src & 7u) != 0u) {
+                    if (lane == 0) A.ctl[3] = 2u;  // a list this kernel was not built for: reported, never read out of bounds
+                    continue;
+                }
                 if (boundary && !waited) {
                     if (lane == 0) {
                         halo_spin(A.wait.ready_prev, A.wait.want, A.wait.err);
@@ -208,12 +211,14 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
             }
             const int s = (int)(it % (uint32_t)n_stages);
             mbar_wait(&empty_bar[s], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
-            float4 *tile = reinterpret_cast<float4 *>(stage0 + (size_t)s * stage_bytes);
+            unsigned char *stage = stage0 + (size_t)s * stage_bytes;
+            float4 *tile = reinterpret_cast<float4 *>(stage);
             if (lane == 0) {
                 meta[s].m = P.m; meta[s].a0 = a0; meta[s].a1 = a1; meta[s].self_off = P.self_off; meta[s].wrap = P.wrap;
             }
+            row_tab[s][lane] = my_tab;
             if (MULTI && !done) {
-                uint16_t *ttype = reinterpret_cast<uint16_t *>(tile + A.tile_cap);
+                uint16_t *ttype = reinterpret_cast<uint16_t *>(stage + type_off);
                 for (int src_lane = 0; src_lane < 9; ++src_lane) {
                     const uint32_t s0 = __shfl_sync(MC_FULL_MASK, P.r0.src, src_lane), n0 = __shfl_sync(MC_FULL_MASK, P.r0.cnt, src_lane),
                                    o0 = __shfl_sync(MC_FULL_MASK, P.r0.off, src_lane), s1 = __shfl_sync(MC_FULL_MASK, P.r1.src, src_lane),
@@ -223,12 +228,15 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_expect_tx(&full_bar[s], P.m * (uint32_t)sizeof(float4));  // release: meta (+ types) visible
+            if (lane == 0)  // release: meta, row table (+ types) visible
+                mbar_expect_tx(&full_bar[s], P.m * (uint32_t)sizeof(float4) + blk_entries * (uint32_t)sizeof(uint16_t));
             __syncwarp();
             if (lane < 9) {
                 if (P.r0.cnt) tma_bulk_g2s(tile + P.r0.off, A.xyzq + P.r0.src, P.r0.cnt * (uint32_t)sizeof(float4), &full_bar[s]);
                 if (P.r1.cnt) tma_bulk_g2s(tile + P.r1.off, A.xyzq + P.r1.src, P.r1.cnt * (uint32_t)sizeof(float4), &full_bar[s]);
             }
+            if (lane == 9 && blk_entries)
+                tma_bulk_g2s(stage + rows_off, A.list16 + blk_src, blk_entries * (uint32_t)sizeof(uint16_t), &full_bar[s]);
             ++it;
             if (done) break;
         }
@@ -236,27 +244,34 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
         // ===== consumers =====
         const int cw = warp - 1;
         const int sub = lane % PT_LANES, rsub = lane / PT_LANES;
+        const float rc2_lj = A.lj_on ? A.p.rc2_lj : -1.f;
+        const float s6c = A.p.sig2 * A.p.sig2 * A.p.sig2;  // single-type constants of the packed path
+        const float2 c12_1 = make_float2(2.f * A.p.eps24 * s6c * s6c, 2.f * A.p.eps24 * s6c * s6c), c6n_1 = make_float2(-A.p.eps24 * s6c, -A.p.eps24 * s6c);
         for (uint32_t it = 0;; ++it) {
             const int s = (int)(it % (uint32_t)n_stages);
             mbar_wait(&full_bar[s], (it / (uint32_t)n_stages) & 1u);
             const PtMeta M = meta[s];
             if (M.a0 == 0xffffffffu) break;
-            const float4 *tile = reinterpret_cast<const float4 *>(stage0 + (size_t)s * stage_bytes);
-            const uint16_t *ttype = reinterpret_cast<const uint16_t *>(tile + A.tile_cap);
+            const unsigned char *stage = stage0 + (size_t)s * stage_bytes;
+            const float4 *tile = reinterpret_cast<const float4 *>(stage);
+            const uint32_t *rows_s = reinterpret_cast<const uint32_t *>(stage + rows_off);
+            const uint16_t *ttype = reinterpret_cast<const uint16_t *>(stage + type_off);
             const uint32_t na = M.a1 - M.a0;
             const uint32_t nq = (na + PT_RPW - 1) / PT_RPW;
             // row quads are dealt round-robin, rotated by the item number: a ~19-atom cell has 5 quads for 8 warps
             for (uint32_t q = (uint32_t)(cw + (int)(it % PT_WARPS)) % PT_WARPS; q < nq; q += PT_WARPS) {
                 const uint32_t r = q * PT_RPW + (uint32_t)rsub;
                 const bool live = r < na;
-                const uint32_t i = M.a0 + (live ? r : 0u);
+                const uint32_t rr = live ? r : 0u;
+                const uint32_t i = M.a0 + rr;
                 Acc a = {0.f, 0.f, 0.f, 0.f};
-                const float4 xi = tile[M.self_off + (live ? r : 0u)];
-                const uint32_t start = __ldg(A.nbr_start + i), cnt = live ? __ldg(A.nbr_count + i) : 0u;
-                const float2 *row = MULTI ? s_tab + (int)ttype[M.self_off + (live ? r : 0u)] * A.p.n_types : nullptr;
-                const uint32_t *lst32 = reinterpret_cast<const uint32_t *>(A.list16 + start);
-                if (M.wrap) row_loop_tile<MULTI, COUL, true, ENERGY>(xi, lst32, cnt, sub, tile, ttype, row, A.p, A.lj_on != 0, a);
-                else row_loop_tile<MULTI, COUL, false, ENERGY>(xi, lst32, cnt, sub, tile, ttype, row, A.p, A.lj_on != 0, a);
+                const float4 xi = tile[M.self_off + rr];
+                const float2 *row = MULTI ? s_tab + (int)ttype[M.self_off + rr] * A.p.n_types : nullptr;
+                const uint32_t tab = row_tab[s][rr];
+                const uint32_t cnt = live ? (tab & 0xffffu) : 0u;
+                const uint32_t *lst32 = rows_s + (tab >> 16);
+                if (M.wrap) row_loop_tile<MULTI, COUL, true, ENERGY>(xi, lst32, cnt, sub, tile, ttype, row, A.p, rc2_lj, c12_1, c6n_1, a);
+                else row_loop_tile<MULTI, COUL, false, ENERGY>(xi, lst32, cnt, sub, tile, ttype, row, A.p, rc2_lj, c12_1, c6n_1, a);
                 // warp-shuffle partial-force reduction across the lanes of this row
 #pragma unroll
                 for (int d = PT_LANES / 2; d > 0; d >>= 1) {
@@ -308,15 +323,19 @@ cudaError_t pair_tile_prepare() {
     return e;
 }
 
-// Shared memory the kernel needs for this tile capacity / type count; 0 = does not fit (use pair_force.cu)
-size_t pair_tile_smem(uint32_t tile_cap, int n_types, bool multi, int *n_stages_out) {
+// Shared memory the kernel needs; 0 = this system is not for it (use pair_force.cu): the kernel stages, per cell, the
+// 27-cell tile AND the cell's rows, which must be one block of <= 32 rows (max_cell_atoms) -- LJ-fluid-like systems, ~12 KB
+// of tile + ~5 KB of rows.  Dense / long-cutoff systems (hundreds of atoms per cell, rows of a thousand entries) are not.
+size_t pair_tile_smem(uint32_t tile_cap, uint32_t rows_max_entries, int n_types, bool multi, int *n_stages_out, uint32_t *rows_cap_out) {
     const size_t tab = multi ? (((size_t)n_types * n_types * sizeof(float2) + 127) & ~(size_t)127) : 0;
-    const size_t stage = (size_t)tile_cap * (sizeof(float4) + (multi ? sizeof(uint16_t) : 0));
-    const size_t budget = 200u * 1024u;
-    if (tab + stage > budget) return 0;
-    // three tiles in flight when they are small (the copy of item k+2 hides behind two sweeps), else two, else one
-    int ns = stage * 3 + tab <= 48u * 1024u ? 3 : (stage * 2 + tab <= budget ? 2 : 1);
+    const size_t tile_b = (size_t)tile_cap * (sizeof(float4) + (multi ? sizeof(uint16_t) : 0));
+    const uint32_t rows_cap = (rows_max_entries + 7u) & ~7u;
+    const size_t stage = (tile_b + (size_t)rows_cap * 2 + 15) & ~(size_t)15;
+    if (stage > 40u * 1024u || tab + 2 * stage > 200u * 1024u) return 0;
+    // as many stages in flight as keep ~40 KB per CTA (five CTAs per SM), at least two
+    const int ns = stage * 3 + tab <= 40u * 1024u ? 3 : 2;
     if (n_stages_out) *n_stages_out = ns;
+    if (rows_cap_out) *rows_cap_out = rows_cap;
     return tab + (size_t)ns * stage;
 }
 
@@ -326,8 +345,10 @@ void launch_pair_tile(const PairTileLaunch &L, cudaStream_t st, int64_t *launche
     A.nbr_start = L.nbr_start; A.nbr_count = L.nbr_count; A.list16 = L.list16; A.ljtab = L.ljtab;
     A.p = L.p; A.lj_on = L.lj_on; A.force = L.force; A.tile_cap = L.tile_cap; A.ctl = L.ctl; A.wait = L.wait;
     int ns = 1;
-    const size_t smem = pair_tile_smem(L.tile_cap, L.p.n_types, L.multi, &ns);
+    uint32_t rows_cap = 0;
+    const size_t smem = pair_tile_smem(L.tile_cap, L.rows_max_entries, L.p.n_types, L.multi, &ns, &rows_cap);
     A.n_stages = ns;
+    A.rows_cap = rows_cap;
 #define MC_PT_E(M, C) \
     if (L.energy) launch_one<M, C, true>(L, A, smem, st); else launch_one<M, C, false>(L, A, smem, st)
 #define MC_PT_C(M)                                                  \

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) til
     const GridParams *__restrict__ gp, float rl2, float rc2_inner, const int *__restrict__ orig,
     const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx, uint32_t *__restrict__ nbr_count,
     uint32_t *__restrict__ nbr_start, IDX *__restrict__ nbr_list, uint32_t list_cap, uint32_t tile_cap, int split,
-    int n_stages /* 1 or 2 tiles in flight */, uint32_t *__restrict__ ctl /* [0] work counter, [1] list cursor, [2] max tile atoms seen, [3] tile overflow */) {
+    int n_stages /* 1 or 2 tiles in flight */, uint32_t *__restrict__ ctl /* [0] work counter, [1] list cursor, [2] max tile atoms seen, [3] tile overflow, [4] largest row block (entries) of one pass, [5] most atoms in a row cell */) {
     MC_DYN_SHARED_ALIGNED(unsigned char, smem_raw, 128);
     // per stage: tile_cap float4 positions, then tile_cap slot ids
     const size_t stage_bytes = (size_t)tile_cap * (sizeof(float4) + sizeof(uint32_t));
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) til
                 TilePlan P;
                 tile_plan(g, cell_start, c, a0, lane, P);  // tile layout shared with the force kernel (tile_ring.cuh)
                 r0 = P.r0; r1 = P.r1; m = P.m; self_off = P.self_off; wrap = P.wrap;
-                if (lane == 0) atomicMax(ctl + 2, m);
+                if (lane == 0) { atomicMax(ctl + 2, m); if (a1 - a0 > *reinterpret_cast<volatile uint32_t *>(ctl + 5)) atomicMax(ctl + 5, a1 - a0); }
                 if (padded_size(m) > tile_cap) {  // does not fit: the host enlarges the tile (or falls back)
                     if (lane == 0) ctl[3] = 1u;
                     continue;
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) til
                     uint32_t tot;
                     const uint32_t off = warp_excl_scan(s_len[pp][lane], lane, &tot);
                     uint32_t b0 = 0;
-                    if (lane == 0) b0 = atomicAdd(ctl + 1, tot);
+                    if (lane == 0) { b0 = atomicAdd(ctl + 1, tot); if (tot > *reinterpret_cast<volatile uint32_t *>(ctl + 4)) atomicMax(ctl + 4, tot); }
                     b0 = __shfl_sync(MC_FULL_MASK, b0, 0);
                     s_off[pp][lane] = b0 + off;
                     if (lane == 0) s_fits[pp] = ((uint64_t)b0 + tot <= (uint64_t)list_cap) ? 1 : 0;
@@ -479,7 +479,7 @@ void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const f
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_build_kernel<uint32_t>, (TILE_WARPS + 1) * 32, smem);
     if (per_sm < 1) per_sm = 1;
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, (long long)n_sms * per_sm));
-    cudaMemsetAsync(ctl, 0, 4 * sizeof(uint32_t), st);
+    cudaMemsetAsync(ctl, 0, 8 * sizeof(uint32_t), st);
     if (compact)
         MC_LAUNCH(tile_build_kernel<uint16_t>, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, cell_start, g, rl2, rc2_inner, orig,
                   excl_start, excl_idx, nbr_count, nbr_start, static_cast<uint16_t *>(nbr_list), list_cap, tile_cap, split, n_stages, ctl);

@@ -405,6 +405,30 @@ def lj_fluid(m=100, seed=404, seed_v=405, temp_k=86.3, name=None):
     return w
 
 
+def ionic_mixture(m=12, seed=414, coul_mode=1):
+    """A charged three-species LJ mixture at the density and cutoff of the C4 fluid (cells of ~19 atoms, rows of ~80
+    entries): the dilute, short-cutoff regime of the TMA-staged force kernel with several LJ types and Coulomb terms --
+    what a coarse-grained or molten-salt system looks like to the engine.  Test workload (no BASELINE config)."""
+    w = lj_fluid(m=m, seed=seed, seed_v=seed + 1, name=f"ionic-mixture{m ** 3}")
+    n = len(w["xyzq"])
+    rng = np.random.default_rng(seed + 2)
+    typ = rng.integers(0, 3, n).astype(np.uint16)
+    sig = np.array([3.405, 3.0, 3.8], np.float64)
+    eps = np.array([0.2381, 0.15, 0.30], np.float64)
+    tab = np.zeros((3, 3, 2), np.float32)
+    for a in range(3):
+        for b in range(3):
+            tab[a, b] = (0.5 * (sig[a] + sig[b]), np.sqrt(eps[a] * eps[b]))  # Lorentz-Berthelot
+    q = np.where(typ == 1, 0.4, np.where(typ == 2, -0.4, 0.0))
+    q -= q.mean()
+    w["type"] = typ
+    w["ljtab"] = tab
+    w["xyzq"] = w["xyzq"].copy()
+    w["xyzq"][:, 3] = (q * COULOMB_SCALE).astype(np.float32)
+    w["coul_mode"] = coul_mode
+    return w
+
+
 def docking_c5(n_rec=5000, n_lig=40, n_poses=10000, seeds=(505, 506, 507)):
     """C5: receptor globule (R atoms), ligand (L atoms), rigid poses = anchors on an 8^3 grid
     within +-8 A of the site centre (site_radius default 8, reference src/docking/mod.rs:43;

@@ -54,22 +54,20 @@ def test_neighbour_list_bit_exact_and_forces(name, Engine, oracle):
     e.close()
 
 
-@pytest.mark.parametrize("name", ["lj1728", "lj8000", "water648", "glob1231", "solv5100"])
-@pytest.mark.parametrize("erfc", [0, 1])
-def test_tile_kernel_matches_the_oracle(name, erfc, Engine, oracle):
-    """pair_tile.cu (TMA-staged tile, compact rows of 16-bit tile-local indices, packed fp32) forced on for systems below
-    its automatic threshold: periodic and vacuum grids, one and many LJ types, no / plain / erfc Coulomb, exclusions and 1-4
-    pairs, energies, and the expansion of the compact rows back to global indices (mc_get_neighbors) -- same bars as above."""
-    w = W.solvated_c3(n_protein=600, n_water=1500, L=40.0) if name == "solv5100" else _cases()[name]()
-    if erfc:
-        if w["coul_mode"] == 0:
-            pytest.skip("no charges")
-        w = dict(w, coul_mode=2)
+@pytest.mark.parametrize("name", ["lj1728", "lj8000", "ions_plain", "ions_erfc", "ions_nocoul", "water648"])
+def test_tile_kernel_matches_the_oracle(name, Engine, oracle):
+    """pair_tile.cu (TMA-staged tile + row block, compact rows of 16-bit tile-local indices, packed fp32) forced on for
+    systems below its automatic size threshold: one and many LJ types, no / plain / erfc Coulomb, energies, wrapping and
+    interior cells, and the expansion of the compact rows back to global indices (mc_get_neighbors) -- same bars as above.
+    water648 is the counter-example: one cell holds all 648 atoms, the build must notice and fall back to global-slot rows."""
+    w = {"ions_plain": lambda: W.ionic_mixture(12, coul_mode=1), "ions_erfc": lambda: W.ionic_mixture(12, coul_mode=2),
+         "ions_nocoul": lambda: W.ionic_mixture(12, coul_mode=0)}.get(name, _cases().get(name))()
     e = Engine.from_workload(w)
     e.set_option("pair_tile", 1)
     e.build_neighbors()
     st = e.stats()
-    assert st["list_bytes"] < 2.2 * max(st["n_pairs_listed"], 1) + 64 * len(w["xyzq"]), "the compact list is not in use"
+    compact = st["list_bytes"] < 2.2 * max(st["n_pairs_listed"], 1) + 64 * len(w["xyzq"])
+    assert compact == (name != "water648"), "compact rows in use: %s" % compact
     start, idx = e.neighbors()
     o_start, o_idx = oracle.neighbors(w)
     assert np.array_equal(start, o_start) and np.array_equal(idx, o_idx)
@@ -81,9 +79,9 @@ def test_tile_kernel_matches_the_oracle(name, erfc, Engine, oracle):
     assert energy_close(e.energy()["energy_potential_nonbonded"], en.sum(), f64[:, 3])
     assert np.abs(f[:, 3] - f64[:, 3]).max() < 1e-5 * max(1.0, float(np.abs(f64[:, 3]).max()))
     n_steps = 20 if name.startswith("lj") else 6
-    dt = w["dt"] * (0.05 if name == "solv5100" else 1.0)  # (the unbonded solvated box has free hydrogens: keep them inside the skin)
+    dt = w["dt"]
     e.step(dt, n_steps)   # the step path runs the instantiation without energies (packed arithmetic for LJ-only systems)
-    ref = oracle.md_run(dict(w, dt=dt), n_steps, precision=64)
+    ref = oracle.md_run(w, n_steps, precision=64)
     ok, worst, scale = trajectory_close(e.positions(), ref["xyzq"], w["xyzq"], w["box_ext"] if w["periodic"] else None)
     assert ok, (worst, scale)
     # forces of the packed / energy-free instantiation against the gather kernel on the positions just reached
