@@ -653,7 +653,7 @@ int engine_build_rows(mc_ctx *c) {
     const int est_cells = c->periodic ? c->h_grid.ncell : std::max(1, n / 256);
     const int split = std::max(1, std::min(8, (4 * c->n_sms + est_cells - 1) / est_cells));
     // compact rows (16-bit tile-local indices) for the TMA-staged force kernel whenever its tile + LJ table fit shared memory
-    bool compact = tiled && c->pair_tile_fits && (c->use_pair_tile == 1 || (c->use_pair_tile == 2 && c->n_rows_sorted() >= 16384));
+    bool compact = tiled && c->periodic && c->pair_tile_fits && (c->use_pair_tile == 1 || (c->use_pair_tile == 2 && c->n_rows_sorted() >= 16384));
     while (tiled) {
         // single-pass TMA-staged build (tile_build.cu); tile and list capacities adapt on demand
         MC_CUDA(c, c->tile_need.ensure(8));
@@ -688,6 +688,15 @@ int engine_build_rows(mc_ctx *c) {
             compact = false;
             c->pair_tile_fits = false;
             continue;
+        }
+        if (compact) {
+            // per-cell staging records of the force kernel's producer (fixed until the next build)
+            uint32_t rows_cap = 0;
+            pair_tile_smem(c->tile_max_m, c->rows_max_entries, c->n_types, c->n_types > 1, nullptr, &rows_cap);
+            MC_CUDA(c, c->cell_plan.ensure((size_t)c->h_grid.ncell * pair_tile_plan_words()));
+            MC_CUDA(c, c->cell_rowtab.ensure((size_t)c->h_grid.ncell * 32));
+            launch_cell_plan(c->h_grid.ncell, c->cell_start.p, c->grid.p, c->nbr_start.p, c->nbr_count.p, c->tile_max_m, rows_cap,
+                             c->cell_plan.p, c->cell_rowtab.p, c->tile_need.p, st, &c->launches);
         }
         break;
     }
@@ -785,18 +794,14 @@ int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs) {
     if (c->list_compact) {
         // TMA-staged kernel over the compact rows (pair_tile.cu); a decomposed rank hands it the ready flags to wait on
         PairTileLaunch T;
-        T.grid_cells = c->periodic ? c->h_grid.ncell : (int)c->ncell_cap;
+        T.grid_cells = c->h_grid.ncell;
         T.n_sms = c->n_sms;
-        T.xyzq = L.xyzq; T.type = L.type; T.cell_start = c->cell_start.p; T.grid = c->grid.p;
-        T.nbr_start = L.nbr_start; T.nbr_count = L.nbr_count; T.list16 = c->nbr_list16.p; T.ljtab = L.ljtab;
+        T.xyzq = L.xyzq; T.type = L.type; T.grid = c->grid.p;
+        T.plan = c->cell_plan.p; T.rowtab = c->cell_rowtab.p;
+        T.list16 = c->nbr_list16.p; T.ljtab = L.ljtab;
         T.p = L.p; T.lj_on = L.lj_on; T.coul = L.coul; T.multi = L.multi; T.energy = L.energy; T.force = L.force;
         T.tile_cap = c->tile_max_m;
         T.rows_max_entries = c->rows_max_entries;
-        if (!c->pair_ctl.p) {
-            MC_CUDA(c, c->pair_ctl.ensure(4));
-            MC_CUDA(c, cudaMemsetAsync(c->pair_ctl.p, 0, 4 * sizeof(uint32_t), c->st));
-        }
-        T.ctl = c->pair_ctl.p;
         if (hs) T.wait = hs->wait;
         TimedRegion tr(c, c->pair_acc, true);
         launch_pair_tile(T, c->st, &c->launches);

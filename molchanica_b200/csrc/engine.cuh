@@ -111,7 +111,7 @@ struct mc_ctx {
     DevBuf<uint8_t> flags[2];
     DevBuf<int> orig[2], slot_of_orig, rebuild_flag;
     DevBuf<uint32_t> keys[2], vals[2], scratch, cell_start, nbr_count, nbr_start, nbr_list;
-    DevBuf<uint32_t> cnt_orig, start_orig, export_rows, tile_need, pair_ctl;
+    DevBuf<uint32_t> cnt_orig, start_orig, export_rows, tile_need, cell_plan, cell_rowtab;
     DevBuf<uint16_t> nbr_list16;
     DevBuf<int32_t> excl_start, excl_idx, p14_start, p14_idx;
     DevBuf<float2> ljtab, d_dock_tab;
@@ -218,7 +218,7 @@ struct mc_ctx {
         for (int b = 0; b < 2; ++b) { xyzq[b].release(); vel[b].release(); type[b].release(); flags[b].release(); orig[b].release(); keys[b].release(); vals[b].release(); }
         force.release(); xref.release(); stage.release(); flush.release(); slot_of_orig.release(); rebuild_flag.release();
         scratch.release(); cell_start.release(); nbr_count.release(); nbr_start.release(); nbr_list.release();
-        cnt_orig.release(); start_orig.release(); export_rows.release(); tile_need.release(); pair_ctl.release(); nbr_list16.release();
+        cnt_orig.release(); start_orig.release(); export_rows.release(); tile_need.release(); cell_plan.release(); cell_rowtab.release(); nbr_list16.release();
         excl_start.release(); excl_idx.release(); p14_start.release(); p14_idx.release();
         ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); ext_force2.release(); d_poses.release(); d_scores.release();
         grid.release(); red_partial.release(); red_out.release(); d_rec.release(); d_lig.release();

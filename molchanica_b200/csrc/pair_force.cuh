@@ -40,13 +40,12 @@ void launch_energy_reduce(int n_rows, const float4 *force, const float4 *vel, do
 // pair_tile.cu -- the TMA-staged variant: rows of 16-bit tile-local indices (tile_build.cu, compact = true), the cell's
 // 27-cell tile in shared memory.  ctl: 4 zeroed words owned by this launcher (the kernel re-arms them itself).
 struct PairTileLaunch {
-    int grid_cells;   // upper bound of the cells holding rows (the kernel reads the exact grid from `grid`)
+    int grid_cells;   // cells of the (periodic) grid
     int n_sms;
     const float4 *xyzq;
     const uint16_t *type;
-    const uint32_t *cell_start;
     const GridParams *grid;
-    const uint32_t *nbr_start, *nbr_count;
+    const uint32_t *plan, *rowtab;  // launch_cell_plan, once per build
     const uint16_t *list16;
     const float2 *ljtab;
     NbParams p;
@@ -54,10 +53,14 @@ struct PairTileLaunch {
     bool multi, energy;
     float4 *force;
     uint32_t tile_cap;
-    uint32_t rows_max_entries;  // largest row block of a <= 32-atom cell (the kernel stages such blocks in shared memory when they fit)
-    uint32_t *ctl;
+    uint32_t rows_max_entries;  // largest row block of a cell
     HaloWait wait{};
 };
 cudaError_t pair_tile_prepare();
 size_t pair_tile_smem(uint32_t tile_cap, uint32_t rows_max_entries, int n_types, bool multi, int *n_stages_out, uint32_t *rows_cap_out);
 void launch_pair_tile(const PairTileLaunch &L, cudaStream_t st, int64_t *launches);
+// per-build table of everything the force kernel's producer needs per cell (plan: n_cells x pair_tile_plan_words() words,
+// rowtab: n_cells x 32 words); ctl[3] is set to 2 when a cell cannot be staged (> 32 atoms, rows not one block, ...)
+size_t pair_tile_plan_words();
+void launch_cell_plan(int n_cells, const uint32_t *cell_start, const GridParams *g, const uint32_t *nbr_start, const uint32_t *nbr_count,
+                      uint32_t tile_cap, uint32_t rows_cap, uint32_t *plan, uint32_t *rowtab, uint32_t *ctl, cudaStream_t st, int64_t *launches);

@@ -58,6 +58,7 @@ __device__ __forceinline__ void row_loop_tile(const float4 xi, const uint32_t *l
         // packed path: two pairs per instruction (pair_terms.cuh)
         float2 c12 = c12_1, c6n = c6n_1;
         Acc2 b = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll 1
         while (wi < nw) {
             const uint32_t cur = word;
             const bool has1 = 2u * wi + 1u < cnt;
@@ -78,6 +79,7 @@ __device__ __forceinline__ void row_loop_tile(const float4 xi, const uint32_t *l
         a.fz -= b.fz.x + b.fz.y;
     } else {
         const float2 lj1 = make_float2(p.sig2, p.eps24);
+#pragma unroll 1
         while (wi < nw) {
             const uint32_t cur = word;
             const bool has1 = 2u * wi + 1u < cnt;
@@ -93,12 +95,65 @@ __device__ __forceinline__ void row_loop_tile(const float4 xi, const uint32_t *l
     }
 }
 
+#define PT_REC_WORDS 64  // per cell: 18 range sources, 18 range lengths, then the scalars below
+#define PT_REC_M 36
+#define PT_REC_SELF 37
+#define PT_REC_WRAP 38
+#define PT_REC_A0 39
+#define PT_REC_NA 40
+#define PT_REC_BLK_SRC 41
+#define PT_REC_BLK_ENTRIES 42
+#define PT_REC_OK 43
+
+// Everything the producer needs to stage a cell is fixed between two list builds: written once per build, one warp per
+// cell, so that the force kernel's producer does ONE round trip to global memory per item (three independent coalesced
+// loads) instead of a chain of five (work counter, cell bounds, stencil rows, row starts, row lengths).
+//   plan[c]   : the tile layout of tile_ring.cuh (18 ranges in tile order), tile size, own offset, wrap class, the cell's
+//               atoms, and its row block (one contiguous piece of the compact list: tile_build.cu allocates the rows of a
+//               <= 32-atom cell with one cursor bump, in atom order)
+//   rowtab[c] : per atom of the cell, (word offset of its row inside the block) << 16 | row length
+__global__ void __launch_bounds__(128) cell_plan_kernel(const uint32_t *__restrict__ cell_start, const GridParams *__restrict__ gp,
+                                                       const uint32_t *__restrict__ nbr_start, const uint32_t *__restrict__ nbr_count,
+                                                       uint32_t tile_cap, uint32_t rows_cap, uint32_t *__restrict__ plan,
+                                                       uint32_t *__restrict__ rowtab, uint32_t *__restrict__ ctl) {
+    const GridParams g = *gp;
+    const int lane = threadIdx.x & 31;
+    const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (c >= g.ncell) return;
+    uint32_t *rec = plan + (size_t)c * PT_REC_WORDS;
+    const uint32_t a0 = cell_start[c], a1 = cell_start[c + 1];
+    const int c2 = c / (g.nc[0] * g.nc[1]);
+    const uint32_t na = (c2 < g.row_l0 || c2 >= g.row_l1) ? 0u : a1 - a0;  // ghost layers carry no rows
+    if (na == 0) {
+        if (lane == 0) { rec[PT_REC_NA] = 0u; rec[PT_REC_OK] = 1u; }
+        return;
+    }
+    TilePlan P;
+    tile_plan(g, cell_start, c, a0, lane, P);
+    if (lane < 9) {
+        rec[2 * lane] = P.r0.src; rec[2 * lane + 1] = P.r1.src;
+        rec[18 + 2 * lane] = P.r0.cnt; rec[18 + 2 * lane + 1] = P.r1.cnt;
+    }
+    uint32_t st = 0, cn = 0;
+    if ((uint32_t)lane < na) { st = nbr_start[a0 + lane]; cn = nbr_count[a0 + lane]; }
+    const uint32_t blk_src = __shfl_sync(MC_FULL_MASK, st, 0);
+    const uint32_t end_l = st + ((cn + 7u) & ~7u);
+    const uint32_t blk_entries = __shfl_sync(MC_FULL_MASK, end_l, (int)min(na, 32u) - 1) - blk_src;
+    rowtab[(size_t)c * 32 + lane] = (((st - blk_src) >> 1) << 16) | (cn & 0xffffu);
+    const bool okl = (uint32_t)lane >= na || (st >= blk_src && end_l - blk_src <= rows_cap && cn <= 0xffffu);
+    const bool ok = __all_sync(MC_FULL_MASK, okl) && na <= 32u && blk_entries <= rows_cap && (blk_src & 7u) == 0u && P.m <= tile_cap;
+    if (lane == 0) {
+        rec[PT_REC_M] = P.m; rec[PT_REC_SELF] = P.self_off; rec[PT_REC_WRAP] = (uint32_t)P.wrap; rec[PT_REC_A0] = a0;
+        rec[PT_REC_NA] = na; rec[PT_REC_BLK_SRC] = blk_src; rec[PT_REC_BLK_ENTRIES] = blk_entries; rec[PT_REC_OK] = ok ? 1u : 0u;
+        if (!ok) ctl[3] = 2u;  // a list this kernel was not built for: the host falls back before any force launch
+    }
+}
+
 struct PairTileArgs {
     const float4 *xyzq;
     const uint16_t *type;
-    const uint32_t *cell_start;
     const GridParams *gp;
-    const uint32_t *nbr_start, *nbr_count;
+    const uint32_t *plan, *rowtab;   // cell_plan_kernel
     const uint16_t *list16;
     const float2 *ljtab;
     NbParams p;
@@ -107,7 +162,6 @@ struct PairTileArgs {
     uint32_t tile_cap;   // atoms per stage (multiple of 32)
     uint32_t rows_cap;   // 16-bit entries of the row block a stage holds (multiple of 8)
     int n_stages;
-    uint32_t *ctl;       // [0] work counter, [1] CTAs that have drained, [3] a tile did not fit (never, if the build fitted)
     HaloWait wait;       // decomposed rank, fused halo: ready flags of this epoch (ready_prev == nullptr: none)
 };
 
@@ -146,7 +200,8 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
         }
     __syncthreads();
 
-    // item order: layers that need no ghost first, then the first and the last row layer (decomposed ranks only)
+    // item order: layers that need no ghost first, then the first and the last row layer (decomposed ranks only);
+    // items are dealt round-robin over the CTAs (the cost of a cell varies little: static scheduling, no work counter)
     const int plane = g.nc[0] * g.nc[1];
     const int nl = g.row_l1 - g.row_l0;
     const bool halo = A.wait.ready_prev != nullptr;
@@ -157,86 +212,89 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
         // ===== producer =====
         bool waited = !halo;
         uint32_t it = 0;
+        auto cell_of = [&](long long w, bool &boundary) -> int {
+            boundary = false;
+            if (!halo) return g.row_l0 * plane + (int)w;
+            if (w < n_int) return (g.row_l0 + 1) * plane + (int)w;
+            const long long w2 = w - n_int;
+            boundary = true;
+            return w2 < plane ? g.row_l0 * plane + (int)w2 : (g.row_l1 - 1) * plane + (int)(w2 - plane);
+        };
+        // the record of the NEXT item is requested before the current one is staged: the one global round trip of the
+        // producer hides behind the wait for a free stage
+        long long w = blockIdx.x;
+        uint32_t rec_lo = 0, rec_hi = 0, tab = 0;
+        bool boundary = false;
+        if (w < n_items) {
+            const int c = cell_of(w, boundary);
+            rec_lo = __ldg(A.plan + (size_t)c * PT_REC_WORDS + lane);
+            rec_hi = __ldg(A.plan + (size_t)c * PT_REC_WORDS + 32 + lane);
+            tab = __ldg(A.rowtab + (size_t)c * 32 + lane);
+        }
         for (;;) {
-            long long w = 0;
-            if (lane == 0) w = (long long)atomicAdd(A.ctl, 1u);
-            w = __shfl_sync(MC_FULL_MASK, w, 0);
             const bool done = w >= n_items;
-            uint32_t a0 = 0xffffffffu, a1 = 0xffffffffu;
-            TilePlan P;
-            P.m = 0; P.self_off = 0; P.wrap = 0; P.r0 = P.r1 = TileRange{0u, 0u, 0u};
-            uint32_t blk_src = 0, blk_entries = 0, my_tab = 0;
-            if (!done) {
-                int c;
-                bool boundary = false;
-                if (!halo) c = g.row_l0 * plane + (int)w;
-                else if (w < n_int) c = (g.row_l0 + 1) * plane + (int)w;
-                else {
-                    const long long w2 = w - n_int;
-                    c = w2 < plane ? g.row_l0 * plane + (int)w2 : (g.row_l1 - 1) * plane + (int)(w2 - plane);
-                    boundary = true;
+            const uint32_t cur_lo = rec_lo, cur_hi = rec_hi, cur_tab = tab;
+            const bool cur_boundary = boundary;
+            const long long wn = w + gridDim.x;
+            if (!done && wn < n_items) {
+                const int cn = cell_of(wn, boundary);
+                rec_lo = __ldg(A.plan + (size_t)cn * PT_REC_WORDS + lane);
+                rec_hi = __ldg(A.plan + (size_t)cn * PT_REC_WORDS + 32 + lane);
+                tab = __ldg(A.rowtab + (size_t)cn * 32 + lane);
+            }
+            w = wn;
+            // lanes 0..17 own the 18 ranges: source in word l, length in word 18 + l (= lanes 18..31 of rec_lo, 0..3 of rec_hi)
+            const uint32_t src = cur_lo;
+            const uint32_t cnt_a = __shfl_sync(MC_FULL_MASK, cur_lo, (lane + 18) & 31), cnt_b = __shfl_sync(MC_FULL_MASK, cur_hi, (lane + 18) & 31);
+            uint32_t cnt = lane < 14 ? cnt_a : cnt_b;
+            const uint32_t m = __shfl_sync(MC_FULL_MASK, cur_hi, PT_REC_M - 32), self_off = __shfl_sync(MC_FULL_MASK, cur_hi, PT_REC_SELF - 32),
+                           wrap = __shfl_sync(MC_FULL_MASK, cur_hi, PT_REC_WRAP - 32), a0 = __shfl_sync(MC_FULL_MASK, cur_hi, PT_REC_A0 - 32),
+                           na = __shfl_sync(MC_FULL_MASK, cur_hi, PT_REC_NA - 32), blk_src = __shfl_sync(MC_FULL_MASK, cur_hi, PT_REC_BLK_SRC - 32),
+                           blk_entries = __shfl_sync(MC_FULL_MASK, cur_hi, PT_REC_BLK_ENTRIES - 32), ok = __shfl_sync(MC_FULL_MASK, cur_hi, PT_REC_OK - 32);
+            if (!done && (na == 0u || !ok)) continue;  // empty cell / ghost layer (warp-uniform); !ok was reported by cell_plan_kernel
+            if (done || lane >= 18) cnt = 0u;
+            uint32_t inc = cnt;  // exclusive prefix of the range lengths = tile offsets
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(MC_FULL_MASK, inc, d);
+                if (lane >= d) inc += v;
+            }
+            const uint32_t off = inc - cnt;
+            if (!done && cur_boundary && !waited) {
+                if (lane == 0) {
+                    halo_spin(A.wait.ready_prev, A.wait.want, A.wait.err);
+                    halo_spin(A.wait.ready_next, A.wait.want, A.wait.err);
+                    fence_proxy_async();  // the peers' stores (acquired above) before the bulk-copy reads
                 }
-                a0 = A.cell_start[c];
-                a1 = A.cell_start[c + 1];
-                if (a0 == a1) continue;  // empty cell (warp-uniform)
-                tile_plan(g, A.cell_start, c, a0, lane, P);
-                if (P.m > A.tile_cap) {  // cannot happen when the list was built with this layout; never read out of bounds
-                    if (lane == 0) A.ctl[3] = 1u;
-                    continue;
-                }
-                // The rows of a cell (<= 32 atoms: the launcher checked the build's maxima) are ONE contiguous block of the list
-                // -- tile_build.cu allocates them with one cursor bump, in atom order.  The block travels with the tile, and
-                // with it an (offset, count) table, so that the consumers never wait for global memory.
-                const uint32_t na = a1 - a0;
-                uint32_t st = 0, cn = 0;
-                if ((uint32_t)lane < na) { st = __ldg(A.nbr_start + a0 + lane); cn = __ldg(A.nbr_count + a0 + lane); }
-                blk_src = __shfl_sync(MC_FULL_MASK, st, 0);
-                const uint32_t end_l = st + ((cn + 7u) & ~7u);
-                blk_entries = __shfl_sync(MC_FULL_MASK, end_l, (int)min(na, 32u) - 1) - blk_src;
-                my_tab = (((st - blk_src) >> 1) << 16) | (cn & 0xffffu);
-                const bool okl = (uint32_t)lane >= na || (st >= blk_src && end_l - blk_src <= A.rows_cap && cn <= 0xffffu);
-                if (!__all_sync(MC_FULL_MASK, okl) || na > 32u || blk_entries > A.rows_cap || (blk_src & 7u) != 0u) {
-                    if (lane == 0) A.ctl[3] = 2u;  // a list this kernel was not built for: reported, never read out of bounds
-                    continue;
-                }
-                if (boundary && !waited) {
-                    if (lane == 0) {
-                        halo_spin(A.wait.ready_prev, A.wait.want, A.wait.err);
-                        halo_spin(A.wait.ready_next, A.wait.want, A.wait.err);
-                        fence_proxy_async();  // the peers' stores (acquired above) before this thread's bulk-copy reads
-                    }
-                    __syncwarp();
-                    waited = true;
-                }
+                __syncwarp();
+                waited = true;
             }
             const int s = (int)(it % (uint32_t)n_stages);
             mbar_wait(&empty_bar[s], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
             unsigned char *stage = stage0 + (size_t)s * stage_bytes;
             float4 *tile = reinterpret_cast<float4 *>(stage);
             if (lane == 0) {
-                meta[s].m = P.m; meta[s].a0 = a0; meta[s].a1 = a1; meta[s].self_off = P.self_off; meta[s].wrap = P.wrap;
+                meta[s].m = done ? 0u : m; meta[s].a0 = done ? 0xffffffffu : a0; meta[s].a1 = done ? 0xffffffffu : a0 + na;
+                meta[s].self_off = self_off; meta[s].wrap = (int)wrap;
             }
-            row_tab[s][lane] = my_tab;
+            row_tab[s][lane] = cur_tab;
             if (MULTI && !done) {
                 uint16_t *ttype = reinterpret_cast<uint16_t *>(stage + type_off);
-                for (int src_lane = 0; src_lane < 9; ++src_lane) {
-                    const uint32_t s0 = __shfl_sync(MC_FULL_MASK, P.r0.src, src_lane), n0 = __shfl_sync(MC_FULL_MASK, P.r0.cnt, src_lane),
-                                   o0 = __shfl_sync(MC_FULL_MASK, P.r0.off, src_lane), s1 = __shfl_sync(MC_FULL_MASK, P.r1.src, src_lane),
-                                   n1 = __shfl_sync(MC_FULL_MASK, P.r1.cnt, src_lane), o1 = __shfl_sync(MC_FULL_MASK, P.r1.off, src_lane);
+                for (int src_lane = 0; src_lane < 18; ++src_lane) {
+                    const uint32_t s0 = __shfl_sync(MC_FULL_MASK, src, src_lane), n0 = __shfl_sync(MC_FULL_MASK, cnt, src_lane),
+                                   o0 = __shfl_sync(MC_FULL_MASK, off, src_lane);
                     for (uint32_t t = lane; t < n0; t += 32) ttype[o0 + t] = A.type[s0 + t];
-                    for (uint32_t t = lane; t < n1; t += 32) ttype[o1 + t] = A.type[s1 + t];
                 }
             }
             __syncwarp();
             if (lane == 0)  // release: meta, row table (+ types) visible
-                mbar_expect_tx(&full_bar[s], P.m * (uint32_t)sizeof(float4) + blk_entries * (uint32_t)sizeof(uint16_t));
+                mbar_expect_tx(&full_bar[s], done ? 0u : m * (uint32_t)sizeof(float4) + blk_entries * (uint32_t)sizeof(uint16_t));
             __syncwarp();
-            if (lane < 9) {
-                if (P.r0.cnt) tma_bulk_g2s(tile + P.r0.off, A.xyzq + P.r0.src, P.r0.cnt * (uint32_t)sizeof(float4), &full_bar[s]);
-                if (P.r1.cnt) tma_bulk_g2s(tile + P.r1.off, A.xyzq + P.r1.src, P.r1.cnt * (uint32_t)sizeof(float4), &full_bar[s]);
+            if (!done) {
+                if (cnt) tma_bulk_g2s(tile + off, A.xyzq + src, cnt * (uint32_t)sizeof(float4), &full_bar[s]);
+                if (lane == 18 && blk_entries)
+                    tma_bulk_g2s(stage + rows_off, A.list16 + blk_src, blk_entries * (uint32_t)sizeof(uint16_t), &full_bar[s]);
             }
-            if (lane == 9 && blk_entries)
-                tma_bulk_g2s(stage + rows_off, A.list16 + blk_src, blk_entries * (uint32_t)sizeof(uint16_t), &full_bar[s]);
             ++it;
             if (done) break;
         }
@@ -258,7 +316,8 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
             const uint16_t *ttype = reinterpret_cast<const uint16_t *>(stage + type_off);
             const uint32_t na = M.a1 - M.a0;
             const uint32_t nq = (na + PT_RPW - 1) / PT_RPW;
-            // row quads are dealt round-robin, rotated by the item number: a ~19-atom cell has 5 quads for 8 warps
+            // row quads are dealt round-robin, rotated by the item number: a ~19-atom cell has 5 quads for the consumer warps
+#pragma unroll 1
             for (uint32_t q = (uint32_t)(cw + (int)(it % PT_WARPS)) % PT_WARPS; q < nq; q += PT_WARPS) {
                 const uint32_t r = q * PT_RPW + (uint32_t)rsub;
                 const bool live = r < na;
@@ -284,16 +343,6 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
-        }
-        // The last CTA to drain re-arms the work counter for the next launch (no memset between the step kernels).  A
-        // CTA has drained when its consumers have seen the end marker: every atomicAdd on ctl[0] is behind it.
-        if (cw == 0 && lane == 0) {
-            __threadfence();
-            if (atomicAdd(A.ctl + 1, 1u) == gridDim.x - 1) {
-                A.ctl[0] = 0u;
-                A.ctl[1] = 0u;
-                __threadfence();
-            }
         }
     }
 }
@@ -339,11 +388,21 @@ size_t pair_tile_smem(uint32_t tile_cap, uint32_t rows_max_entries, int n_types,
     return tab + (size_t)ns * stage;
 }
 
+void launch_cell_plan(int n_cells, const uint32_t *cell_start, const GridParams *g, const uint32_t *nbr_start, const uint32_t *nbr_count,
+                      uint32_t tile_cap, uint32_t rows_cap, uint32_t *plan, uint32_t *rowtab, uint32_t *ctl, cudaStream_t st, int64_t *launches) {
+    if (n_cells <= 0) return;
+    MC_LAUNCH(cell_plan_kernel, div_up((size_t)n_cells * 32, 128), 128, 0, st, cell_start, g, nbr_start, nbr_count, tile_cap, rows_cap, plan,
+              rowtab, ctl);
+    *launches += 1;
+}
+
+size_t pair_tile_plan_words() { return PT_REC_WORDS; }
+
 void launch_pair_tile(const PairTileLaunch &L, cudaStream_t st, int64_t *launches) {
     PairTileArgs A;
-    A.xyzq = L.xyzq; A.type = L.type; A.cell_start = L.cell_start; A.gp = L.grid;
-    A.nbr_start = L.nbr_start; A.nbr_count = L.nbr_count; A.list16 = L.list16; A.ljtab = L.ljtab;
-    A.p = L.p; A.lj_on = L.lj_on; A.force = L.force; A.tile_cap = L.tile_cap; A.ctl = L.ctl; A.wait = L.wait;
+    A.xyzq = L.xyzq; A.type = L.type; A.gp = L.grid; A.plan = L.plan; A.rowtab = L.rowtab;
+    A.list16 = L.list16; A.ljtab = L.ljtab;
+    A.p = L.p; A.lj_on = L.lj_on; A.force = L.force; A.tile_cap = L.tile_cap; A.wait = L.wait;
     int ns = 1;
     uint32_t rows_cap = 0;
     const size_t smem = pair_tile_smem(L.tile_cap, L.rows_max_entries, L.p.n_types, L.multi, &ns, &rows_cap);
