@@ -86,9 +86,10 @@ struct mc_ctx {
     bool subcell_sort = false;  // Morton sub-cell code in the low sort-key bits (option "subcell_sort")
     bool use_tile = true;      // TMA-staged tile sweep for the list build (neighbor_tile.cu)
     uint32_t tile_cap = 1024;  // tile capacity in atoms, grows on demand
-    int use_pair_tile = 2;     // option "pair_tile": compact rows (16-bit tile-local indices) + TMA-staged force kernel (pair_tile.cu):
-                               // 0 off, 1 on, 2 (default) on for systems of >= 16384 atoms (below that the persistent
-                               // kernel's fixed cost outweighs it: C2 measured 17.0k steps/s with it, 24.6k without)
+    int use_pair_tile = 0;     // option "pair_tile": compact rows (16-bit tile-local indices) + TMA-staged force kernel (pair_tile.cu):
+                               // 0 (default) off, 1 on, 2 on for systems of >= 16384 atoms.  Measured on C4 (profiles/pair_tile_r2_*):
+                               // 0.199 ms against 0.178 ms of the gather kernel -- staging a 27-cell tile per ~19-atom cell is
+                               // latency bound (0.126 ms with the arithmetic removed), so it is an option, not the default
     bool pair_tile_fits = true; // cleared when a build showed the system too dense for pair_tile.cu (cells of > 32 atoms, rows too long)
     bool list_compact = false; // the current list is in compact form (nbr_list16)
     bool list32_valid = false; // nbr_list holds the current list as global slots (expanded on demand from the compact form)

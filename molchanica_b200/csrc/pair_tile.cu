@@ -53,7 +53,8 @@ __device__ __forceinline__ void row_loop_tile(const float4 xi, const uint32_t *l
                                               const NbParams &p, const float rc2_lj, const float2 c12_1, const float2 c6n_1, Acc &a) {
     const uint32_t nw = (cnt + 1u) >> 1;  // index words of this row
     uint32_t wi = (uint32_t)sub;
-    uint32_t word = wi < nw ? lst32[wi] : 0u;
+    const uint32_t *pw = lst32 + sub;
+    uint32_t word = wi < nw ? *pw : 0u;
     if constexpr (COUL == MC_COULOMB_NONE && !ENERGY) {
         // packed path: two pairs per instruction (pair_terms.cuh)
         float2 c12 = c12_1, c6n = c6n_1;
@@ -63,7 +64,8 @@ __device__ __forceinline__ void row_loop_tile(const float4 xi, const uint32_t *l
             const uint32_t cur = word;
             const bool has1 = 2u * wi + 1u < cnt;
             wi += PT_LANES;
-            if (wi < nw) word = lst32[wi];
+            pw += PT_LANES;
+            if (wi < nw) word = *pw;
             const uint32_t j0 = cur & 0xffffu, j1 = has1 ? (cur >> 16) : j0;
             const float4 x0 = tile[j0], x1 = tile[j1];
             if (MULTI) {
@@ -84,7 +86,8 @@ __device__ __forceinline__ void row_loop_tile(const float4 xi, const uint32_t *l
             const uint32_t cur = word;
             const bool has1 = 2u * wi + 1u < cnt;
             wi += PT_LANES;
-            if (wi < nw) word = lst32[wi];
+            pw += PT_LANES;
+            if (wi < nw) word = *pw;
             const uint32_t j0 = cur & 0xffffu, j1 = has1 ? (cur >> 16) : j0;
             const float4 x0 = tile[j0], x1 = tile[j1];
             float2 l0 = lj1, l1 = lj1;
@@ -211,7 +214,8 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
     if (warp == 0) {
         // ===== producer =====
         bool waited = !halo;
-        uint32_t it = 0;
+        int p_stage = 0;
+        uint32_t p_phase = 0u;
         auto cell_of = [&](long long w, bool &boundary) -> int {
             boundary = false;
             if (!halo) return g.row_l0 * plane + (int)w;
@@ -269,8 +273,9 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
                 __syncwarp();
                 waited = true;
             }
-            const int s = (int)(it % (uint32_t)n_stages);
-            mbar_wait(&empty_bar[s], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
+            const int s = p_stage;
+            mbar_wait_parked(&empty_bar[s], p_phase ^ 1u, 20000u);
+            if (++p_stage == n_stages) { p_stage = 0; p_phase ^= 1u; }
             unsigned char *stage = stage0 + (size_t)s * stage_bytes;
             float4 *tile = reinterpret_cast<float4 *>(stage);
             if (lane == 0) {
@@ -287,15 +292,20 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
                 }
             }
             __syncwarp();
+#ifdef MC_PT_EXPERIMENT_ONE_COPY  // (timing experiment: one tile copy per item instead of ~9; the data is wrong on purpose)
+            const uint32_t cnt0 = __shfl_sync(MC_FULL_MASK, cnt, 0);
+            if (lane == 0) mbar_expect_tx(&full_bar[s], done ? 0u : cnt0 * (uint32_t)sizeof(float4) + blk_entries * (uint32_t)sizeof(uint16_t));
+            if (lane != 0) cnt = 0u;
+#else
             if (lane == 0)  // release: meta, row table (+ types) visible
                 mbar_expect_tx(&full_bar[s], done ? 0u : m * (uint32_t)sizeof(float4) + blk_entries * (uint32_t)sizeof(uint16_t));
+#endif
             __syncwarp();
             if (!done) {
                 if (cnt) tma_bulk_g2s(tile + off, A.xyzq + src, cnt * (uint32_t)sizeof(float4), &full_bar[s]);
                 if (lane == 18 && blk_entries)
                     tma_bulk_g2s(stage + rows_off, A.list16 + blk_src, blk_entries * (uint32_t)sizeof(uint16_t), &full_bar[s]);
             }
-            ++it;
             if (done) break;
         }
     } else {
@@ -305,9 +315,10 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
         const float rc2_lj = A.lj_on ? A.p.rc2_lj : -1.f;
         const float s6c = A.p.sig2 * A.p.sig2 * A.p.sig2;  // single-type constants of the packed path
         const float2 c12_1 = make_float2(2.f * A.p.eps24 * s6c * s6c, 2.f * A.p.eps24 * s6c * s6c), c6n_1 = make_float2(-A.p.eps24 * s6c, -A.p.eps24 * s6c);
-        for (uint32_t it = 0;; ++it) {
-            const int s = (int)(it % (uint32_t)n_stages);
-            mbar_wait(&full_bar[s], (it / (uint32_t)n_stages) & 1u);
+        int s = 0;
+        uint32_t phase = 0u, rot = (uint32_t)cw;  // rot: this warp's first quad of the current item (rotates with the items)
+        for (;; ) {
+            mbar_wait_parked(&full_bar[s], phase, 20000u);
             const PtMeta M = meta[s];
             if (M.a0 == 0xffffffffu) break;
             const unsigned char *stage = stage0 + (size_t)s * stage_bytes;
@@ -318,7 +329,7 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
             const uint32_t nq = (na + PT_RPW - 1) / PT_RPW;
             // row quads are dealt round-robin, rotated by the item number: a ~19-atom cell has 5 quads for the consumer warps
 #pragma unroll 1
-            for (uint32_t q = (uint32_t)(cw + (int)(it % PT_WARPS)) % PT_WARPS; q < nq; q += PT_WARPS) {
+            for (uint32_t q = rot; q < nq; q += PT_WARPS) {
                 const uint32_t r = q * PT_RPW + (uint32_t)rsub;
                 const bool live = r < na;
                 const uint32_t rr = live ? r : 0u;
@@ -329,8 +340,12 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
                 const uint32_t tab = row_tab[s][rr];
                 const uint32_t cnt = live ? (tab & 0xffffu) : 0u;
                 const uint32_t *lst32 = rows_s + (tab >> 16);
+#ifndef MC_PT_EXPERIMENT_NO_MATH  // (timing experiment: what the staging pipeline alone costs)
                 if (M.wrap) row_loop_tile<MULTI, COUL, true, ENERGY>(xi, lst32, cnt, sub, tile, ttype, row, A.p, rc2_lj, c12_1, c6n_1, a);
                 else row_loop_tile<MULTI, COUL, false, ENERGY>(xi, lst32, cnt, sub, tile, ttype, row, A.p, rc2_lj, c12_1, c6n_1, a);
+#else
+                a.fx = xi.x + (float)cnt + (float)lst32[sub];
+#endif
                 // warp-shuffle partial-force reduction across the lanes of this row
 #pragma unroll
                 for (int d = PT_LANES / 2; d > 0; d >>= 1) {
@@ -343,6 +358,8 @@ __global__ void __launch_bounds__((PT_WARPS + 1) * 32, MC_PT_MIN_BLOCKS) pair_ti
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (++s == n_stages) { s = 0; phase ^= 1u; }
+            if (++rot == PT_WARPS) rot = 0u;
         }
     }
 }
@@ -381,8 +398,12 @@ size_t pair_tile_smem(uint32_t tile_cap, uint32_t rows_max_entries, int n_types,
     const uint32_t rows_cap = (rows_max_entries + 7u) & ~7u;
     const size_t stage = (tile_b + (size_t)rows_cap * 2 + 15) & ~(size_t)15;
     if (stage > 40u * 1024u || tab + 2 * stage > 200u * 1024u) return 0;
-    // as many stages in flight as keep ~40 KB per CTA (five CTAs per SM), at least two
-    const int ns = stage * 3 + tab <= 40u * 1024u ? 3 : 2;
+    // as many stages in flight as keep ~44 KB per CTA (five CTAs per SM), at least two
+#ifdef MC_PT_EXPERIMENT_STAGES
+    const int ns = MC_PT_EXPERIMENT_STAGES;
+#else
+    const int ns = stage * 4 + tab <= 44u * 1024u ? 4 : (stage * 3 + tab <= 44u * 1024u ? 3 : 2);
+#endif
     if (n_stages_out) *n_stages_out = ns;
     if (rows_cap_out) *rows_cap_out = rows_cap;
     return tab + (size_t)ns * stage;

@@ -53,6 +53,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
+// the same wait with a suspend-time hint: a waiting warp is parked by the hardware for up to `ns` instead of coming back to
+// re-issue the test every few hundred cycles (measured in pair_tile.cu: 7.5 M retries = 13 % of all issued instructions)
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+            : "memory");
+    } while (!ok);
+}
+
 // generic-proxy writes (a peer GPU's stores made visible by an acquire, this warp's own shared-memory stores) ordered
 // before the async-proxy reads of a following bulk copy
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -63,6 +76,7 @@ inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { shim_mbar_arrive(bar
 inline void mbar_arrive(uint64_t *bar) { shim_mbar_arrive(bar, 0); }
 inline void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { shim_bulk_copy(dst, src, bytes, bar); }
 inline void mbar_wait(uint64_t *bar, uint32_t parity) { shim_mbar_wait(bar, parity); }
+inline void mbar_wait_parked(uint64_t *bar, uint32_t parity, uint32_t) { shim_mbar_wait(bar, parity); }
 inline void fence_proxy_async() {}
 #endif
 
