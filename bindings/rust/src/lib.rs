@@ -119,6 +119,7 @@ extern "C" {
     pub fn mc_set_molecule_ids(ctx: *mut McCtx, mol_id: *const u16) -> c_int;
     pub fn mc_get_energy_between_mols(ctx: *mut McCtx, out: *mut f64) -> c_int;
     pub fn mc_snapshot_begin(ctx: *mut McCtx, out_positions: *mut McFloat4, out_ids: *mut i32, n_out: *mut i64) -> c_int;
+    pub fn mc_snapshot_begin_xyz(ctx: *mut McCtx, out_xyz: *mut f32, out_ids: *mut i32, n_out: *mut i64, layout_epoch: *mut i64) -> c_int;
     pub fn mc_snapshot_begin_pv(ctx: *mut McCtx, out_positions: *mut McFloat4, out_velocities: *mut McFloat4, out_ids: *mut i32, n_out: *mut i64) -> c_int;
     pub fn mc_snapshot_wait(ctx: *mut McCtx) -> c_int;
     pub fn mc_get_neighbors(ctx: *mut McCtx, start: *mut i64, idx: *mut i32, cap: i64, total: *mut i64) -> c_int;

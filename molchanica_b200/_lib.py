@@ -136,6 +136,7 @@ def lib():
     L.mc_dd_plan.argtypes = [vp, f32, i32, i32, vp]
     L.mc_snapshot_begin.argtypes = [vp, vp, vp, C.POINTER(i64)]
     L.mc_snapshot_begin_pv.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int64)]
+    L.mc_snapshot_begin_xyz.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]
     L.mc_snapshot_wait.argtypes = [vp]
     L.mc_comm_schedule.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_double)]
     L.mc_comm_halo_mode.argtypes = [vp, C.POINTER(i32), C.c_char_p, i32]

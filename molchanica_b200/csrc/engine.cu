@@ -1354,6 +1354,43 @@ static int snapshot_begin_impl(mc_ctx *c, mc_float4 *out_positions, mc_float4 *o
     return MC_OK;
 }
 
+// Snapshot.atom_posits is a Vec<Vec3F32> (reference src/md/trajectory.rs:160-204): 12 bytes per atom are what the viewer
+// needs per frame -- a quarter less PCIe traffic than the float4 record; and the ids of a decomposed rank only change at a
+// list rebuild, so they travel only when the caller has not yet seen this layout (layout_epoch).
+extern "C" int mc_snapshot_begin_xyz(mc_ctx *c, float *out_xyz, int32_t *out_ids, int64_t *n_out, int64_t *layout_epoch) {
+    if (!c || !out_xyz) return MC_E_INVALID;
+    cudaSetDevice(c->device);
+    if (!c->st_copy) {
+        MC_CUDA(c, cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_snap_staged[b], cudaEventDisableTiming));
+            MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_snap_done[b], cudaEventDisableTiming));
+        }
+    }
+    const int k = c->snap_k;
+    c->snap_k ^= 1;
+    const int64_t rows = c->n_rows_sorted();
+    const int64_t n = c->comm_active ? rows : c->n_global;
+    if (n_out) *n_out = n;
+    if (layout_epoch) *layout_epoch = c->n_rebuilds;
+    if (n == 0) return MC_OK;
+    if (c->snap_pending[k]) MC_CUDA(c, cudaStreamWaitEvent(c->st, c->ev_snap_done[k], 0));
+    MC_CUDA(c, c->snap_stage[k].ensure((size_t)n));  // float4 elements: 3n floats fit
+    float *stage = reinterpret_cast<float *>(c->snap_stage[k].p);
+    launch_pack_xyz((int)rows, c->xyzq[c->cur].p + c->row0, c->comm_active ? nullptr : c->orig[c->cur].p + c->row0, stage, c->st, &c->launches);
+    if (c->comm_active && out_ids) {
+        MC_CUDA(c, c->snap_ids[k].ensure((size_t)n));
+        MC_CUDA(c, cudaMemcpyAsync(c->snap_ids[k].p, c->orig[c->cur].p + c->row0, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->st));
+    }
+    MC_CUDA(c, cudaEventRecord(c->ev_snap_staged[k], c->st));
+    MC_CUDA(c, cudaStreamWaitEvent(c->st_copy, c->ev_snap_staged[k], 0));
+    MC_CUDA(c, cudaMemcpyAsync(out_xyz, stage, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->st_copy));
+    if (c->comm_active && out_ids) MC_CUDA(c, cudaMemcpyAsync(out_ids, c->snap_ids[k].p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->st_copy));
+    MC_CUDA(c, cudaEventRecord(c->ev_snap_done[k], c->st_copy));
+    c->snap_pending[k] = true;
+    return MC_OK;
+}
+
 extern "C" int mc_snapshot_begin(mc_ctx *c, mc_float4 *out_positions, int32_t *out_ids, int64_t *n_out) {
     return snapshot_begin_impl(c, out_positions, nullptr, out_ids, n_out);
 }

@@ -142,6 +142,15 @@ __global__ void scatter_from_orig_kernel(int n, const float4 *__restrict__ in_or
     sorted[k] = v;
 }
 
+// positions as packed float3: in slot order (orig == nullptr: a decomposed rank's owned block) or scattered to the caller's ids
+__global__ void pack_xyz_kernel(int n, const float4 *__restrict__ sorted, const int *__restrict__ orig, float *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 v = sorted[k];
+    const size_t o = 3 * (size_t)(orig ? orig[k] : k);
+    out[o] = v.x; out[o + 1] = v.y; out[o + 2] = v.z;
+}
+
 __global__ void l2_flush_kernel(float4 *buf, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -180,6 +189,12 @@ void launch_scatter_from_orig(int n, const float4 *in_orig, const int *orig, flo
                               int64_t *launches) {
     if (n <= 0) return;
     MC_LAUNCH(scatter_from_orig_kernel, div_up(n, 256), 256, 0, st, n, in_orig, orig, sorted, keep_w);
+    *launches += 1;
+}
+
+void launch_pack_xyz(int n, const float4 *sorted, const int *orig, float *out, cudaStream_t st, int64_t *launches) {
+    if (n <= 0) return;
+    MC_LAUNCH(pack_xyz_kernel, div_up(n, 256), 256, 0, st, n, sorted, orig, out);
     *launches += 1;
 }
 

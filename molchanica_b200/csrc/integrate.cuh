@@ -30,4 +30,5 @@ void launch_scale_coords(int n, float4 *xyzq, float4 *xref, float4 *vel, float m
 void launch_gather_to_orig(int n, const float4 *sorted, const int *orig, float4 *out, cudaStream_t st, int64_t *launches);
 void launch_scatter_from_orig(int n, const float4 *in_orig, const int *orig, float4 *sorted, int keep_w, cudaStream_t st,
                               int64_t *launches);
+void launch_pack_xyz(int n, const float4 *sorted, const int *orig, float *out, cudaStream_t st, int64_t *launches);
 void launch_l2_flush(float4 *buf, size_t n_float4, cudaStream_t st, int64_t *launches);

@@ -246,6 +246,12 @@ class MdEngine:
         self._chk(self._L.mc_snapshot_begin_pv(self._h, _ptr(out_positions), _ptr(out_velocities), _ptr(out_ids), C.byref(n_out)))
         return int(n_out.value)
 
+    def snapshot_begin_xyz(self, out_xyz, out_ids=None):
+        """mc_snapshot_begin_xyz: packed float3 positions; returns (entries, layout epoch)."""
+        n_out, ep = C.c_int64(0), C.c_int64(0)
+        self._chk(self._L.mc_snapshot_begin_xyz(self._h, _ptr(out_xyz), _ptr(out_ids), C.byref(n_out), C.byref(ep)))
+        return int(n_out.value), int(ep.value)
+
     def snapshot_wait(self):
         self._chk(self._L.mc_snapshot_wait(self._h))
 

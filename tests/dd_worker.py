@@ -92,6 +92,15 @@ def main():
     n_snap = e.snapshot_begin(sp, si)
     e.snapshot_wait()
     snap_ok = n_snap == own and np.array_equal(sp[:n_snap], x[si[:n_snap]])
+    # the packed float3 hand-off, ids included and (same layout epoch) without
+    s3, i3 = np.zeros((len(w["xyzq"]), 3), np.float32), np.full(len(w["xyzq"]), -1, np.int32)
+    n3, ep = e.snapshot_begin_xyz(s3, i3)
+    e.snapshot_wait()
+    s3b = np.zeros_like(s3)
+    n3b, ep2 = e.snapshot_begin_xyz(s3b)
+    e.snapshot_wait()
+    snap_ok = snap_ok and n3 == own and n3b == own and ep == ep2 and np.array_equal(i3[:n3], si[:n_snap]) and \
+        np.array_equal(s3[:n3], x[i3[:n3], :3]) and np.array_equal(s3b[:n3], s3[:n3])
     if rank == 0:
         np.savez(out, fused=fused, why=why, snap_ok=snap_ok, interval=interval, disp_frac=disp_frac, f0=f0, x=x, v=v, e_pot=en0["energy_potential_nonbonded"], n_owned=st0["n_atoms"],
                  n_ghosts=st0["n_ghosts"], rebuilds=st["n_rebuilds"], violations=st["n_list_violations"],

@@ -233,6 +233,19 @@ def test_nve_energy_and_momentum_on_lj_fluid(Engine):
     e.close()
 
 
+def test_packed_xyz_snapshot(Engine):
+    """mc_snapshot_begin_xyz: the same hand-off as mc_snapshot_begin, 3 floats per atom in the caller's order."""
+    w = W.lj_fluid(m=12)
+    e = Engine.from_workload(w)
+    e.step(w["dt"], 7)
+    xyz = np.zeros((len(w["xyzq"]), 3), np.float32)
+    n, epoch = e.snapshot_begin_xyz(xyz)
+    e.snapshot_wait()
+    assert n == len(w["xyzq"]) and epoch == e.stats()["n_rebuilds"]
+    assert np.array_equal(xyz, e.positions()[:, :3])
+    e.close()
+
+
 def test_golden_fixtures(Engine):
     g = np.load(GOLD)
     for name in ("lj512", "water648", "glob300"):
