@@ -6,7 +6,10 @@
 // atoms (coalesced float4, L2-resident: the 80 KB receptor is shared by all CTAs) and keeps the
 // six partial sums in registers; a warp-shuffle + shared-memory tree finishes the pose.
 //
-// Bound: FP32 issue + MUFU (rcp/rsqrt), not HBM -- the receptor and table are on chip.
+// Bound: FP32 issue, not HBM -- the receptor and table are on chip.  The inner loop takes TWO ligand atoms per
+// iteration in packed fp32 (f32x2: the posed ligand is kept as (a, a+1) pairs per component, the LJ parameters as pairs
+// per receptor type, so every LDS.64 delivers a packed operand) and ONE MUFU per pair: 1/r from rsqrt, 1/r^2 = (1/r)^2,
+// and the softened 1/(r^2 + 1e-6) = (1/r^2)(1 - 1e-6/r^2 + ...) to first order (exact to 1e-8 for r > 0.1 A).
 //
 //   ligand atom a at pose p : x = anchor_p + R(q_p) (lig_a - lig_anchor)           (:149-158)
 //   vdw          = sum 4 eps ((sigma/r)^12 - (sigma/r)^6)                          (:235-262; lj_V, cuda/util.cu:74-90)
@@ -16,27 +19,12 @@
 //   score        = vdw + (-1.2) n_hbond + hydrophobic + 10 electrostatic, n_hbond = 0 (external crate)
 #include "common.cuh"
 #include "dock.cuh"
+#include "pair_terms.cuh"  // rsqrt_approx, packed fp32 helpers
 
 namespace {
 
 constexpr int DOCK_THREADS = 128;
 constexpr float HYDROPHOBIC_CUTOFF = 4.25f;
-
-#ifndef MC_HOST_SHIM
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float rsqrt_approx(float x) {
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-#else  // tests/cpp/dock_kernel_host.cpp runs this file's kernel on the CPU: no PTX there
-inline float rcp_approx(float x) { return 1.0f / x; }
-inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
-#endif
 
 __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, const float4 *__restrict__ rec,
                                                                    const uint32_t *__restrict__ rec_meta, int n_lig,
@@ -46,10 +34,13 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
                                                                    const float2 *__restrict__ ljtab,
                                                                    const float *__restrict__ poses,
                                                                    float *__restrict__ out) {
-    MC_DYN_SHARED(float4, smem);
-    float4 *lp = smem;                                             // n_lig posed atoms (x, y, z, q)
-    uint32_t *lmeta = reinterpret_cast<uint32_t *>(lp + n_lig);    // n_lig meta words
-    float2 *tab = reinterpret_cast<float2 *>(lmeta + ((n_lig + 3) & ~3));  // T_rec * T_lig
+    MC_DYN_SHARED(float2, smem);
+    // posed ligand as pairs of atoms (a, a+1) per component; an odd count is padded with a far, neutral, sigma = 0 atom
+    const int np = (n_lig + 1) >> 1;
+    float2 *lx2 = smem, *ly2 = lx2 + np, *lz2 = ly2 + np, *lq2 = lz2 + np;
+    float2 *s2tab = lq2 + np;                    // [n_rec_types][np] (sigma^2 of the pair's two atoms)
+    float2 *e4tab = s2tab + n_rec_types * np;    // [n_rec_types][np] (4 eps)
+    uint32_t *lhyd = reinterpret_cast<uint32_t *>(e4tab + n_rec_types * np);  // [np] hydrophobic flags, bit 0 / bit 1
     const int pose = blockIdx.x;
     const float *ps = poses + 7 * (size_t)pose;
     {
@@ -61,7 +52,10 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
         const double qn = sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(qw, qw), __dmul_rn(qx, qx)), __dmul_rn(qy, qy)),
                                          __dmul_rn(qz, qz)));
         qw = __ddiv_rn(qw, qn); qx = __ddiv_rn(qx, qn); qy = __ddiv_rn(qy, qn); qz = __ddiv_rn(qz, qn);
-        for (int a = threadIdx.x; a < n_lig; a += DOCK_THREADS) {
+        float *lxs = reinterpret_cast<float *>(lx2), *lys = reinterpret_cast<float *>(ly2), *lzs = reinterpret_cast<float *>(lz2),
+              *lqs = reinterpret_cast<float *>(lq2);
+        for (int a = threadIdx.x; a < 2 * np; a += DOCK_THREADS) {
+            if (a >= n_lig) { lxs[a] = lys[a] = lzs[a] = 1.0e6f; lqs[a] = 0.f; continue; }
             const float4 l = lig[a];
             const double vx = __dsub_rn((double)l.x, (double)anchor0.x), vy = __dsub_rn((double)l.y, (double)anchor0.y),
                          vz = __dsub_rn((double)l.z, (double)anchor0.z);
@@ -75,41 +69,62 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
             const double ox = __dadd_rn(vx, __dmul_rn(2.0, __dadd_rn(__dmul_rn(qw, cx), dx)));
             const double oy = __dadd_rn(vy, __dmul_rn(2.0, __dadd_rn(__dmul_rn(qw, cy), dy)));
             const double oz = __dadd_rn(vz, __dmul_rn(2.0, __dadd_rn(__dmul_rn(qw, cz), dz)));
-            lp[a] = make_float4((float)__dadd_rn(ox, (double)ps[0]), (float)__dadd_rn(oy, (double)ps[1]),
-                                (float)__dadd_rn(oz, (double)ps[2]), l.w);
-            lmeta[a] = lig_meta[a];
+            lxs[a] = (float)__dadd_rn(ox, (double)ps[0]);
+            lys[a] = (float)__dadd_rn(oy, (double)ps[1]);
+            lzs[a] = (float)__dadd_rn(oz, (double)ps[2]);
+            lqs[a] = l.w;
         }
-        for (int t = threadIdx.x; t < n_rec_types * n_lig_types; t += DOCK_THREADS) tab[t] = ljtab[t];
+        // LJ parameters of every (receptor type, ligand atom) as pairs, hydrophobic flags of the ligand pairs
+        float *s2s = reinterpret_cast<float *>(s2tab), *e4s = reinterpret_cast<float *>(e4tab);
+        for (int t = threadIdx.x; t < n_rec_types * 2 * np; t += DOCK_THREADS) {
+            const int rt = t / (2 * np), a = t - rt * 2 * np;
+            float2 lj = make_float2(0.f, 0.f);
+            if (a < n_lig) lj = ljtab[rt * n_lig_types + (int)(lig_meta[a] & 0xffffu)];
+            s2s[t] = lj.x;
+            e4s[t] = lj.y;
+        }
+        for (int p = threadIdx.x; p < np; p += DOCK_THREADS) {
+            const uint32_t h0 = (lig_meta[2 * p] >> 16) & 1u, h1 = (2 * p + 1 < n_lig) ? ((lig_meta[2 * p + 1] >> 16) & 1u) : 0u;
+            lhyd[p] = h0 | (h1 << 1);
+        }
     }
     __syncthreads();
 
-    float vdw = 0.f, hyd = 0.f, ec = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
+    float hyd = 0.f;
+    float2 vdw2 = make_float2(0.f, 0.f), ec2 = vdw2, fx2 = vdw2, fy2 = vdw2, fz2 = vdw2;
+    const float2 one_n = make_float2(-1.f, -1.f), one = make_float2(1.f, 1.f), soft_n = make_float2(-MC_SOFTENING_SQ, -MC_SOFTENING_SQ);
     for (int r = threadIdx.x; r < n_rec; r += DOCK_THREADS) {
         const float4 xr = __ldg(rec + r);
         const uint32_t mr = __ldg(rec_meta + r);
-        const float2 *row = tab + (mr & 0xffffu) * n_lig_types;
+        const float2 *s2row = s2tab + (mr & 0xffffu) * np, *e4row = e4tab + (mr & 0xffffu) * np;
         const bool hr = (mr >> 16) & 1u;
-#pragma unroll 4
-        for (int a = 0; a < n_lig; ++a) {
-            const float4 xl = lp[a];
-            const uint32_t ml = lmeta[a];
-            const float2 lj = row[ml & 0xffffu];
-            const float dx = xl.x - xr.x, dy = xl.y - xr.y, dz = xl.z - xr.z;
-            const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-            const float ir2 = rcp_approx(r2);
-            const float s2 = lj.x * ir2, s6 = s2 * s2 * s2;
-            vdw = fmaf(lj.y * s6, s6 - 1.f, vdw);
-            const float ir = rsqrt_approx(r2);
-            const float qq = xr.w * xl.w;
-            ec = fmaf(qq, ir, ec);
-            const float fm = qq * ir * rcp_approx(r2 + MC_SOFTENING_SQ);
-            fx = fmaf(dx, fm, fx); fy = fmaf(dy, fm, fy); fz = fmaf(dz, fm, fz);
-            if (hr && ((ml >> 16) & 1u)) {
-                const float rr = r2 * ir;
-                if (rr < HYDROPHOBIC_CUTOFF) hyd += -0.2f * fmaxf(1.0f - rr * (1.0f / HYDROPHOBIC_CUTOFF), 0.f);
+        const float2 nx = make_float2(-xr.x, -xr.x), ny = make_float2(-xr.y, -xr.y), nz = make_float2(-xr.z, -xr.z),
+                     qr = make_float2(xr.w, xr.w);
+#pragma unroll 2
+        for (int p = 0; p < np; ++p) {
+            const float2 dx = mc_add2(lx2[p], nx), dy = mc_add2(ly2[p], ny), dz = mc_add2(lz2[p], nz);
+            const float2 r2 = mc_fma2(dx, dx, mc_fma2(dy, dy, mc_mul2(dz, dz)));
+            const float2 ir = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+            const float2 ir2 = mc_mul2(ir, ir);
+            const float2 s2 = mc_mul2(s2row[p], ir2);
+            const float2 s6 = mc_mul2(mc_mul2(s2, s2), s2);
+            vdw2 = mc_fma2(mc_mul2(e4row[p], s6), mc_add2(s6, one_n), vdw2);
+            const float2 qq = mc_mul2(qr, lq2[p]);
+            ec2 = mc_fma2(qq, ir, ec2);
+            // qq / r / (r^2 + 1e-6) = qq (1/r)^3 (1 - 1e-6 / r^2) to first order
+            const float2 fm = mc_mul2(mc_mul2(qq, mc_mul2(ir, ir2)), mc_fma2(soft_n, ir2, one));
+            fx2 = mc_fma2(dx, fm, fx2); fy2 = mc_fma2(dy, fm, fy2); fz2 = mc_fma2(dz, fm, fz2);
+            if (hr) {
+                const uint32_t lh = lhyd[p];
+                if (lh) {
+                    const float2 rr = mc_mul2(r2, ir);
+                    if ((lh & 1u) && rr.x < HYDROPHOBIC_CUTOFF) hyd += -0.2f * fmaxf(1.0f - rr.x * (1.0f / HYDROPHOBIC_CUTOFF), 0.f);
+                    if ((lh & 2u) && rr.y < HYDROPHOBIC_CUTOFF) hyd += -0.2f * fmaxf(1.0f - rr.y * (1.0f / HYDROPHOBIC_CUTOFF), 0.f);
+                }
             }
         }
     }
+    const float vdw = vdw2.x + vdw2.y, ec = ec2.x + ec2.y, fx = fx2.x + fx2.y, fy = fy2.x + fy2.y, fz = fz2.x + fz2.y;
     float v[6] = {vdw, hyd, ec, fx, fy, fz};
     __shared__ float red[6][DOCK_THREADS / 32];
 #pragma unroll
@@ -136,7 +151,9 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
 
 #ifdef MC_HAVE_LAUNCH  // the stand-ins of tests/cpp/shim/ and shim_mt/ have no launcher; shim_fiber/ has
 size_t dock_smem_bytes(int n_lig, int n_rec_types, int n_lig_types) {
-    return sizeof(float4) * n_lig + sizeof(uint32_t) * ((n_lig + 3) & ~3) + sizeof(float2) * n_rec_types * n_lig_types;
+    (void)n_lig_types;
+    const size_t np = (size_t)(n_lig + 1) / 2;
+    return sizeof(float2) * np * (4 + 2 * (size_t)n_rec_types) + sizeof(uint32_t) * np;
 }
 
 cudaError_t dock_prepare() {

@@ -518,6 +518,7 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         c->pair_lanes = v;
     } else if (k == "pair_uniform") {
         c->pair_uniform = value != 0.0;
+        c->list_valid = false;  // the warp-uniform loop wants rows partitioned inner / skin shell: built on request only
     } else if (k == "sync_rebuild") {
         c->sync_rebuild = value != 0.0;
     } else if (k == "tile_sweep") {
@@ -662,7 +663,7 @@ int engine_build_rows(mc_ctx *c) {
         const size_t cap_now = compact ? c->nbr_list16.n : c->nbr_list.n;
         launch_tile_build(n_rows, grid_cells, split, c->n_sms, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, rc2_inner,
                           c->orig[c->cur].p, es, ei, c->nbr_count.p, c->nbr_start.p,
-                          compact ? static_cast<void *>(c->nbr_list16.p) : static_cast<void *>(c->nbr_list.p), compact,
+                          compact ? static_cast<void *>(c->nbr_list16.p) : static_cast<void *>(c->nbr_list.p), compact, c->pair_uniform,
                           (uint32_t)std::min<size_t>(cap_now, 0xffffffffu), c->tile_cap, c->tile_need.p, st, &c->launches);
         MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->tile_need.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         MC_CUDA(c, cudaStreamSynchronize(st));

@@ -30,10 +30,12 @@ cudaError_t tile_sweep_prepare();
 uint32_t tile_sweep_max_atoms();
 void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
                        const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
-                       const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, void *nbr_list, bool compact,
+                       const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, void *nbr_list, bool compact, bool partition,
                        uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches);
 // compact = true: nbr_list is uint16_t[list_cap], entries are tile-local indices (tile_ring.cuh) -- what pair_tile.cu reads;
 // compact = false: uint32_t[list_cap] global slots.  Rows are padded to 8 entries either way.
+// partition = true: entries inside the force cutoff at build time come first in every row (the warp-uniform pair loop skips
+// the skin shell warp-wide); false (default): plain tile order, cheaper to build.
 // Compact rows -> global-slot rows with the same nbr_start / nbr_count (for the consumers that are not on the hot path)
 void launch_expand_rows(int grid_cells, const uint32_t *cell_start, const GridParams *g, const uint32_t *nbr_start,
                         const uint32_t *nbr_count, const uint16_t *list16, uint32_t *list32, cudaStream_t st, int64_t *launches);

@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "neighbor.cuh"
+#include "pair_terms.cuh"  // packed fp32 helpers
 #include "tile_ring.cuh"
 
 namespace {
@@ -35,15 +36,21 @@ constexpr int TILE_WARPS = 8;   // consumer warps
 constexpr int TILE_STAGES = 2;  // tiles in flight per CTA
 constexpr int TILE_A = 4;       // atoms swept together by one warp
 
+#ifndef MC_HOST_SHIM
+__device__ __forceinline__ uint32_t mc_brev(uint32_t v) { return __brev(v); }
+#else
+inline uint32_t mc_brev(uint32_t v) {
+    uint32_t r = 0;
+    for (int b = 0; b < 32; ++b) r |= ((v >> b) & 1u) << (31 - b);
+    return r;
+}
+#endif
+
 __device__ __forceinline__ float min_image_exact(float d, float ext, float inv_ext) {
     float q = __fmul_rn(d, inv_ext);
     float n = rintf(q);
     if (fabsf(q - n) > 0.4999f) n = rintf(__fdiv_rn(d, ext));
     return __fmaf_rn(-n, ext, d);
-}
-
-__device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
-    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
 #ifndef MC_HOST_SHIM
@@ -87,42 +94,69 @@ __device__ __forceinline__ uint32_t padded_size(uint32_t m) {  // tile entries i
     return full * 992u + (rem ? 32u * chunk_B(rem) : 0u);
 }
 
-// Accept decisions of NA atoms against one chunk: bit `it` of hit[k] / inn[k] (per lane) = candidate
-// t0 + lane*B + it is listed / is inside the force cutoff.  WRAP is warp-uniform: cells whose
-// stencil does not wrap skip the minimum image -- for such a cell every candidate's raw difference
-// either IS the minimum image (|d| <= ext/2, n == 0) or belongs to a pair whose nearest image is
-// beyond the list radius as well, so the decision is unchanged.  Parked atoms and tile padding are
-// NaN: never accepted.
-template <int NA, int WRAP>
+// Accept decisions of NA atoms (NA = 2 or 4: always whole PAIRS of atoms, a missing one is parked on NaN) against one chunk:
+// bit `it` of hit[k] / inn[k] (per lane) = candidate t0 + lane*B + it is listed / is inside the force cutoff.  Two atoms
+// share every instruction of the distance (packed fp32: FADD2 / FMUL2 with the candidate broadcast; the two additions of
+// r^2 stay scalar so that ptxas cannot contract them with the products -- the expression must round exactly like the
+// oracle's ((dx*dx)+(dy*dy))+(dz*dz)).  The decisions are shifted into the masks (2 instructions per test instead of a
+// variable shift + select + or) and bit-reversed once per chunk; the own atom's bit is cleared afterwards instead of being
+// tested per candidate.  WRAP is warp-uniform: cells whose stencil does not wrap skip the minimum image -- for such a cell
+// every candidate's raw difference either IS the minimum image (|d| <= ext/2, n == 0) or belongs to a pair whose nearest
+// image is beyond the list radius as well, so the decision is unchanged.  Parked atoms and tile padding are NaN: never
+// accepted.  PART: also record which hits are inside the force cutoff (rows partitioned inner / skin shell for the
+// warp-uniform pair loop); off by default.
+template <int NA, int WRAP, bool PART>
 __device__ __forceinline__ void sweep_chunk(const float4 *tile, uint32_t t0, uint32_t B, const GridParams &g, float rl2,
                                             float rc2_inner, const float4 (&pi)[TILE_A], const uint32_t (&t_self)[TILE_A],
                                             int lane, uint32_t (&hit)[TILE_A], uint32_t (&inn)[TILE_A]) {
 #pragma unroll
     for (int k = 0; k < NA; ++k) hit[k] = inn[k] = 0u;
     const uint32_t tl = t0 + (uint32_t)lane * B;
-    for (uint32_t it = 0; it < B; ++it) {
-        const uint32_t t = tl + it;
-        const float4 pj = tile[t];
-        const uint32_t bit = 1u << it;
+    float2 px[NA / 2], py[NA / 2], pz[NA / 2];
 #pragma unroll
-        for (int k = 0; k < NA; ++k) {
-            float dx = __fsub_rn(pi[k].x, pj.x), dy = __fsub_rn(pi[k].y, pj.y), dz = __fsub_rn(pi[k].z, pj.z);
+    for (int h = 0; h < NA / 2; ++h) {
+        px[h] = make_float2(pi[2 * h].x, pi[2 * h + 1].x);
+        py[h] = make_float2(pi[2 * h].y, pi[2 * h + 1].y);
+        pz[h] = make_float2(pi[2 * h].z, pi[2 * h + 1].z);
+    }
+    for (uint32_t it = 0; it < B; ++it) {
+        const float4 pj = tile[tl + it];
+        const float2 nx = make_float2(-pj.x, -pj.x), ny = make_float2(-pj.y, -pj.y), nz = make_float2(-pj.z, -pj.z);
+#pragma unroll
+        for (int h = 0; h < NA / 2; ++h) {
+            float2 dx = mc_add2(px[h], nx), dy = mc_add2(py[h], ny), dz = mc_add2(pz[h], nz);
             if (WRAP == 2) {
-                dx = min_image_exact(dx, g.ext[0], g.inv_ext[0]);
-                dy = min_image_exact(dy, g.ext[1], g.inv_ext[1]);
-                dz = min_image_exact(dz, g.ext[2], g.inv_ext[2]);
+                dx.x = min_image_exact(dx.x, g.ext[0], g.inv_ext[0]); dx.y = min_image_exact(dx.y, g.ext[0], g.inv_ext[0]);
+                dy.x = min_image_exact(dy.x, g.ext[1], g.inv_ext[1]); dy.y = min_image_exact(dy.y, g.ext[1], g.inv_ext[1]);
+                dz.x = min_image_exact(dz.x, g.ext[2], g.inv_ext[2]); dz.y = min_image_exact(dz.y, g.ext[2], g.inv_ext[2]);
             } else if (WRAP == 1) {
                 // >= 3 cells per axis: ext >= 3 r_list, so whenever rintf(d * inv_ext) could differ from
                 // rintf(d / ext) (|d| within rounding of ext/2) both images lie beyond 1.4 r_list and the
                 // decision is the same; everywhere else the two agree and d - n*ext is exact
-                dx = __fmaf_rn(-rintf(__fmul_rn(dx, g.inv_ext[0])), g.ext[0], dx);
-                dy = __fmaf_rn(-rintf(__fmul_rn(dy, g.inv_ext[1])), g.ext[1], dy);
-                dz = __fmaf_rn(-rintf(__fmul_rn(dz, g.inv_ext[2])), g.ext[2], dz);
+                const float2 qx = mc_mul2(dx, make_float2(g.inv_ext[0], g.inv_ext[0])), qy = mc_mul2(dy, make_float2(g.inv_ext[1], g.inv_ext[1])),
+                             qz = mc_mul2(dz, make_float2(g.inv_ext[2], g.inv_ext[2]));
+                dx = mc_fma2(make_float2(-rintf(qx.x), -rintf(qx.y)), make_float2(g.ext[0], g.ext[0]), dx);
+                dy = mc_fma2(make_float2(-rintf(qy.x), -rintf(qy.y)), make_float2(g.ext[1], g.ext[1]), dy);
+                dz = mc_fma2(make_float2(-rintf(qz.x), -rintf(qz.y)), make_float2(g.ext[2], g.ext[2]), dz);
             }
-            const float r2 = dist2_exact(dx, dy, dz);
-            if (r2 < rl2 && t != t_self[k]) hit[k] |= bit;
-            if (r2 < rc2_inner) inn[k] |= bit;
+            const float2 sx = mc_mul2(dx, dx), sy = mc_mul2(dy, dy), sz = mc_mul2(dz, dz);
+            const float r2a = __fadd_rn(__fadd_rn(sx.x, sy.x), sz.x), r2b = __fadd_rn(__fadd_rn(sx.y, sy.y), sz.y);
+            hit[2 * h] = (hit[2 * h] << 1) | (r2a < rl2 ? 1u : 0u);
+            hit[2 * h + 1] = (hit[2 * h + 1] << 1) | (r2b < rl2 ? 1u : 0u);
+            if (PART) {
+                inn[2 * h] = (inn[2 * h] << 1) | (r2a < rc2_inner ? 1u : 0u);
+                inn[2 * h + 1] = (inn[2 * h + 1] << 1) | (r2b < rc2_inner ? 1u : 0u);
+            }
         }
+    }
+    // candidate `it` sits in bit B-1-it: reverse, then clear the bit of the atom itself
+    const uint32_t sh = 32u - B;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        hit[k] = mc_brev(hit[k]) >> sh;
+        if (PART) inn[k] = mc_brev(inn[k]) >> sh;
+        const uint32_t ds = t_self[k] - tl;  // (huge when the own atom is not in this lane's entries)
+        if (ds < B) hit[k] &= ~(1u << ds);
     }
 }
 
@@ -157,7 +191,7 @@ struct RowState {
 };
 
 // phase 1: accept decisions and row lengths of the NA atoms of this warp
-template <int NA, int WRAP>
+template <int NA, int WRAP, bool PART>
 __device__ __forceinline__ void rows_phase1(const float4 *tile, const uint32_t *tile_slot, const StageMeta &M, const GridParams &g,
                                             float rl2, float rc2_inner, const uint32_t (&ia)[TILE_A],
                                             const float4 *__restrict__ xyzq, const int *__restrict__ orig,
@@ -172,8 +206,8 @@ __device__ __forceinline__ void rows_phase1(const float4 *tile, const uint32_t *
         R.hit[k] = R.inn[k] = 0u;
         R.len[k] = R.n_inner[k] = 0u;
         if (k < NA && k < na) {
-            R.pi[k] = xyzq[ia[k]];
             R.t_self[k] = M.self_off + (ia[k] - M.a0);
+            R.pi[k] = tile[R.t_self[k]];  // the own cell is part of the staged tile
             if (excl_start) {
                 const int oi = orig[ia[k]];
                 R.ex_lo[k] = excl_start[oi];
@@ -186,20 +220,25 @@ __device__ __forceinline__ void rows_phase1(const float4 *tile, const uint32_t *
     for (int k = 0; k < TILE_A; ++k) n_in[k] = n_out[k] = 0u;
     for (uint32_t t0 = 0; t0 < M.m;) {
         const uint32_t B = chunk_B(M.m - t0);
-        sweep_chunk<NA, WRAP>(tile, t0, B, g, rl2, rc2_inner, R.pi, R.t_self, lane, R.hit, R.inn);
+        sweep_chunk<NA, WRAP, PART>(tile, t0, B, g, rl2, rc2_inner, R.pi, R.t_self, lane, R.hit, R.inn);
         apply_exclusions<NA>(tile_slot, t0 + (uint32_t)lane * B, R.ex_lo, R.ex_hi, orig, excl_idx, R.hit);
 #pragma unroll
         for (int k = 0; k < NA; ++k) {
-            n_in[k] += __popc(R.hit[k] & R.inn[k]);
-            n_out[k] += __popc(R.hit[k] & ~R.inn[k]);
+            if (PART) {
+                n_in[k] += __popc(R.hit[k] & R.inn[k]);
+                n_out[k] += __popc(R.hit[k] & ~R.inn[k]);
+            } else {
+                n_in[k] += __popc(R.hit[k]);
+            }
         }
         t0 += 32u * B;
     }
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
-        uint32_t tot_in, tot_out;
+        uint32_t tot_in, tot_out = 0u;
         R.lane_in[k] = warp_excl_scan(n_in[k], lane, &tot_in);
-        R.lane_out[k] = warp_excl_scan(n_out[k], lane, &tot_out);
+        R.lane_out[k] = 0u;
+        if (PART) R.lane_out[k] = warp_excl_scan(n_out[k], lane, &tot_out);
         R.len[k] = tot_in + tot_out;
         R.n_inner[k] = tot_in;
     }
@@ -208,7 +247,7 @@ __device__ __forceinline__ void rows_phase1(const float4 *tile, const uint32_t *
 // phase 2: write the rows in tile order; inner entries from the front, skin-shell entries from the back
 // IDX = uint32_t: entries are global slots (tile_slot[t]); IDX = uint16_t: entries are the TILE-LOCAL indices t themselves
 // (the compact list pair_tile.cu gathers from its own copy of the tile, laid out by the same tile_plan)
-template <int NA, int WRAP, typename IDX>
+template <int NA, int WRAP, bool PART, typename IDX>
 __device__ __forceinline__ void rows_phase2(const float4 *tile, const uint32_t *tile_slot, const StageMeta &M, const GridParams &g,
                                             float rl2, float rc2_inner, const uint32_t (&row)[TILE_A],
                                             const int *__restrict__ orig, const int32_t *__restrict__ excl_idx,
@@ -221,16 +260,17 @@ __device__ __forceinline__ void rows_phase2(const float4 *tile, const uint32_t *
         const uint32_t B = chunk_B(M.m - t0);
         const uint32_t tl = t0 + (uint32_t)lane * B;
         if (!one_chunk) {
-            sweep_chunk<NA, WRAP>(tile, t0, B, g, rl2, rc2_inner, R.pi, R.t_self, lane, R.hit, R.inn);
+            sweep_chunk<NA, WRAP, PART>(tile, t0, B, g, rl2, rc2_inner, R.pi, R.t_self, lane, R.hit, R.inn);
             apply_exclusions<NA>(tile_slot, tl, R.ex_lo, R.ex_hi, orig, excl_idx, R.hit);
         }
 #pragma unroll
         for (int k = 0; k < NA; ++k) {
             uint32_t li = R.lane_in[k], lo = R.lane_out[k];
             if (!one_chunk) {  // per-chunk lane offsets
-                uint32_t ti, to;
-                li = warp_excl_scan(__popc(R.hit[k] & R.inn[k]), lane, &ti);
-                lo = warp_excl_scan(__popc(R.hit[k] & ~R.inn[k]), lane, &to);
+                uint32_t ti, to = 0u;
+                li = warp_excl_scan(PART ? __popc(R.hit[k] & R.inn[k]) : __popc(R.hit[k]), lane, &ti);
+                lo = 0u;
+                if (PART) lo = warp_excl_scan(__popc(R.hit[k] & ~R.inn[k]), lane, &to);
                 li += run_in[k]; lo += run_out[k];
                 run_in[k] += ti; run_out[k] += to;
             }
@@ -241,7 +281,7 @@ __device__ __forceinline__ void rows_phase2(const float4 *tile, const uint32_t *
                 const int it = __ffs(mleft) - 1;
                 mleft &= mleft - 1u;
                 const IDX j = sizeof(IDX) == 2 ? (IDX)(tl + (uint32_t)it) : (IDX)tile_slot[tl + (uint32_t)it];
-                if ((R.inn[k] >> it) & 1u) nbr_list[p_in++] = j;
+                if (!PART || ((R.inn[k] >> it) & 1u)) nbr_list[p_in++] = j;
                 else nbr_list[p_out--] = j;
             }
         }
@@ -254,7 +294,7 @@ __device__ __forceinline__ void rows_phase2(const float4 *tile, const uint32_t *
 #ifndef MC_TILE_MIN_BLOCKS
 #define MC_TILE_MIN_BLOCKS 3
 #endif
-template <typename IDX>
+template <typename IDX, bool PART>
 __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) tile_build_kernel(
     int n_rows, const float4 *__restrict__ xyzq, const uint32_t *__restrict__ cell_start,
     const GridParams *__restrict__ gp, float rl2, float rc2_inner, const int *__restrict__ orig,
@@ -364,10 +404,11 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) til
                 const uint32_t n_pass = min((uint32_t)(TILE_WARPS * TILE_A), M.a1 - base);
                 const int na_u = (int)((n_pass + TILE_WARPS - 1) / TILE_WARPS);
                 RowState R;
-#define MC_P1(NA_, W_) rows_phase1<NA_, W_>(tile, tile_slot, M, g, rl2, rc2_inner, ia, xyzq, orig, excl_start, excl_idx, lane, na, R)
+#define MC_P1(NA_, W_) rows_phase1<NA_, W_, PART>(tile, tile_slot, M, g, rl2, rc2_inner, ia, xyzq, orig, excl_start, excl_idx, lane, na, R)
 #define MC_P1W(NA_) \
     if (M.wrap == 0) MC_P1(NA_, 0); else if (M.wrap == 1) MC_P1(NA_, 1); else MC_P1(NA_, 2)
-                switch (na_u) { case 1: MC_P1W(1); break; case 2: MC_P1W(2); break; case 3: MC_P1W(3); break; default: MC_P1W(4); break; }
+                // whole pairs of atoms (packed arithmetic): two instantiations per wrap class
+                if (na_u <= 2) { MC_P1W(2); } else { MC_P1W(4); }
 #undef MC_P1W
 #undef MC_P1
                 // ---- row allocation for the whole pass (up to 32 atoms of the cell, in atom order): the padded
@@ -400,10 +441,10 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) til
                 const bool fits = s_fits[pp] != 0;  // otherwise the host grows the list and rebuilds
                 pp ^= 1;  // the other buffer serves the next pass: no third barrier needed
                 if (fits && na > 0) {
-#define MC_P2(NA_, W_) rows_phase2<NA_, W_, IDX>(tile, tile_slot, M, g, rl2, rc2_inner, row, orig, excl_idx, nbr_list, lane, R)
+#define MC_P2(NA_, W_) rows_phase2<NA_, W_, PART, IDX>(tile, tile_slot, M, g, rl2, rc2_inner, row, orig, excl_idx, nbr_list, lane, R)
 #define MC_P2W(NA_) \
     if (M.wrap == 0) MC_P2(NA_, 0); else if (M.wrap == 1) MC_P2(NA_, 1); else MC_P2(NA_, 2)
-                    switch (na_u) { case 1: MC_P2W(1); break; case 2: MC_P2W(2); break; case 3: MC_P2W(3); break; default: MC_P2W(4); break; }
+                    if (na_u <= 2) { MC_P2W(2); } else { MC_P2W(4); }
 #undef MC_P2W
 #undef MC_P2
                 }
@@ -457,34 +498,43 @@ void launch_expand_rows(int grid_cells, const uint32_t *cell_start, const GridPa
 }
 
 cudaError_t tile_sweep_prepare() {
-    cudaError_t e = cudaFuncSetAttribute(tile_build_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tile_build_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaSuccess;
+#define MC_TB_ATTR(I, P) if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_build_kernel<I, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    MC_TB_ATTR(uint32_t, false) MC_TB_ATTR(uint32_t, true) MC_TB_ATTR(uint16_t, false) MC_TB_ATTR(uint16_t, true)
+#undef MC_TB_ATTR
+    return e;
 }
 
 // 16 B position + 4 B slot id per staged atom in 200 KB of shared memory; tiles above half of that run
 // single-buffered (no copy/sweep overlap, but still one L2 read per cell instead of one per atom)
 uint32_t tile_sweep_max_atoms() { return ((200u * 1024u) / 20u) & ~31u; }
 
-void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
-                       const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
-                       const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, void *nbr_list, bool compact,
-                       uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches) {
+template <typename IDX, bool PART>
+static void launch_tile_build_t(int n_rows, long long items, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
+                                const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
+                                const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, IDX *nbr_list, uint32_t list_cap,
+                                uint32_t tile_cap, uint32_t *ctl, cudaStream_t st) {
     // persistent: exactly one resident wave of CTAs pulls (cell, slice) items from ctl[0]
-    const long long items = (long long)grid_cells * split;
     const int n_stages = (size_t)2 * tile_cap * 20u <= 200u * 1024u ? 2 : 1;
     const size_t smem = (size_t)n_stages * tile_cap * (sizeof(float4) + sizeof(uint32_t));
     int per_sm = 1;
-    if (compact) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_build_kernel<uint16_t>, (TILE_WARPS + 1) * 32, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_build_kernel<uint32_t>, (TILE_WARPS + 1) * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_build_kernel<IDX, PART>, (TILE_WARPS + 1) * 32, smem);
     if (per_sm < 1) per_sm = 1;
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, (long long)n_sms * per_sm));
     cudaMemsetAsync(ctl, 0, 8 * sizeof(uint32_t), st);
-    if (compact)
-        MC_LAUNCH(tile_build_kernel<uint16_t>, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, cell_start, g, rl2, rc2_inner, orig,
-                  excl_start, excl_idx, nbr_count, nbr_start, static_cast<uint16_t *>(nbr_list), list_cap, tile_cap, split, n_stages, ctl);
-    else
-        MC_LAUNCH(tile_build_kernel<uint32_t>, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, cell_start, g, rl2, rc2_inner, orig,
-                  excl_start, excl_idx, nbr_count, nbr_start, static_cast<uint32_t *>(nbr_list), list_cap, tile_cap, split, n_stages, ctl);
+    MC_LAUNCH(tile_build_kernel<IDX MC_COMMA PART>, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, cell_start, g, rl2, rc2_inner, orig,
+              excl_start, excl_idx, nbr_count, nbr_start, nbr_list, list_cap, tile_cap, split, n_stages, ctl);
+}
+
+void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
+                       const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
+                       const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, void *nbr_list, bool compact, bool partition,
+                       uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches) {
+    const long long items = (long long)grid_cells * split;
+#define MC_TB_GO(I, P) launch_tile_build_t<I, P>(n_rows, items, split, n_sms, xyzq, cell_start, g, rl2, rc2_inner, orig, excl_start, excl_idx, \
+                                                 nbr_count, nbr_start, static_cast<I *>(nbr_list), list_cap, tile_cap, ctl, st)
+    if (compact) { if (partition) MC_TB_GO(uint16_t, true); else MC_TB_GO(uint16_t, false); }
+    else { if (partition) MC_TB_GO(uint32_t, true); else MC_TB_GO(uint32_t, false); }
+#undef MC_TB_GO
     *launches += 1;
 }

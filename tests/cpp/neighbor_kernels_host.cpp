@@ -80,7 +80,7 @@ long host_neighbor_list(int n, const float4 *xyzq_in, const float *lo, const flo
     if (use_tile) {
         // engine_build_rows: the single-pass build with tile and list capacities that adapt on demand.
         // tile_stats: [0] launches, [1] final tile capacity, [2] largest neighbourhood seen, [3] final list capacity
-        uint32_t ctl[4];
+        uint32_t ctl[8];
         uint32_t tile_cap = (uint32_t)tile_cap0;
         std::vector<uint32_t> list((size_t)list_cap0);
         memset(nbr_count, 0, sizeof(uint32_t) * (size_t)n);
@@ -88,7 +88,7 @@ long host_neighbor_list(int n, const float4 *xyzq_in, const float *lo, const flo
         size_t total = 0;
         for (;;) {
             launch_tile_build(n, periodic ? g.ncell : (int)ncell_cap, split, n_sms, xo.data(), cell_start.data(), &g, rl2, rc_inner * rc_inner,
-                              orig_out, excl_start, excl_idx, nbr_count, nbr_start, list.data(), (uint32_t)list.size(), tile_cap, ctl, nullptr,
+                              orig_out, excl_start, excl_idx, nbr_count, nbr_start, list.data(), false, true, (uint32_t)list.size(), tile_cap, ctl, nullptr,
                               &launches);
             if (ctl[3] != 0) {
                 uint32_t need = (ctl[2] + ctl[2] / 4 + 127u) & ~31u;
