@@ -23,6 +23,7 @@ pub const MC_FLAG_STATIC: u8 = 1;
 pub const MC_BAROSTAT_NONE: c_int = 0;
 pub const MC_BAROSTAT_BERENDSEN: c_int = 1;
 pub const MC_BAROSTAT_CRESCALE: c_int = 2;
+pub const MC_DOCK_MAX_FLEX: c_int = 12;
 
 #[repr(C)]
 pub struct McCtx {
@@ -127,8 +128,11 @@ extern "C" {
     pub fn mc_time_kernels(ctx: *mut McCtx, reps: c_int, flush_l2: c_int) -> c_int;
     pub fn mc_last_pair_kernel_ms(ctx: *mut McCtx) -> f64;
     pub fn mc_dock_score(ctx: *mut McCtx, n_rec: i64, rec_xyzq: *const McFloat4, rec_type: *const u16, rec_hydrophobic: *const u8, n_lig: i64, lig_xyzq: *const McFloat4, lig_type: *const u16, lig_hydrophobic: *const u8, lig_anchor: *const f32, n_rec_types: c_int, n_lig_types: c_int, ljtab: *const f32, n_poses: i64, poses: *const f32, out: *mut f32) -> c_int;
+    pub fn mc_dock_score_flex(ctx: *mut McCtx, n_rec: i64, rec_xyzq: *const McFloat4, rec_type: *const u16, rec_hydrophobic: *const u8, n_lig: i64, lig_xyzq: *const McFloat4, lig_type: *const u16, lig_hydrophobic: *const u8, lig_anchor: *const f32, n_rec_types: c_int, n_lig_types: c_int, ljtab: *const f32, n_flex: c_int, flex_axis: *const i32, flex_mask: *const u8, n_poses: i64, poses: *const f32, out: *mut f32) -> c_int;
     pub fn mc_dock_make_poses(site_center: *const f64, site_radius: f64, num_posits: c_int, num_orientations: c_int, out_poses: *mut f32, cap: i64, n_out: *mut i64) -> c_int;
     pub fn mc_dock_orientation_count(num_orientations: c_int) -> c_int;
+    pub fn mc_dock_make_poses_flex(site_center: *const f64, site_radius: f64, num_posits: c_int, num_orientations: c_int, n_flex_bonds: c_int, angles_per_bond: c_int, out_poses: *mut f32, cap: i64, n_out: *mut i64) -> c_int;
+    pub fn mc_dock_flex_masks(n_lig: i64, n_bonds: i64, bonds: *const i32, n_flex_bonds: c_int, flex_bond_idx: *const i32, axis_out: *mut i32, mask_out: *mut u8) -> c_int;
     pub fn mc_dock_near_site(n_rec: i64, rec_xyzq: *const McFloat4, rec_hetero: *const u8, site_center: *const f64, site_radius: f64, out_idx: *mut i32, n_out: *mut i64) -> c_int;
     pub fn mc_dock_filter_poses(n_rec: i64, rec_xyzq: *const McFloat4, rec_is_carbon: *const u8, n_lig: i64, lig_xyzq: *const McFloat4, lig_is_carbon: *const u8, lig_anchor: *const f32, vdw_radius: f32, n_poses: i64, poses: *const f32, keep: *mut u8, n_kept: *mut i64) -> c_int;
     pub fn mc_dock_filter_poses_gpu(ctx: *mut McCtx, n_rec: i64, rec_xyzq: *const McFloat4, rec_is_carbon: *const u8, n_lig: i64, lig_xyzq: *const McFloat4, lig_is_carbon: *const u8, lig_anchor: *const f32, vdw_radius: f32, n_poses: i64, poses: *const f32, keep: *mut u8, n_kept: *mut i64) -> c_int;

@@ -309,6 +309,14 @@ int mc_dock_score(mc_ctx *ctx, int64_t n_rec, const mc_float4 *rec_xyzq, const u
                   const uint16_t *lig_type, const uint8_t *lig_hydrophobic, const float lig_anchor[3],
                   int n_rec_types, int n_lig_types, const float *ljtab,
                   int64_t n_poses, const float *poses, float *out);
+/* The same scan for a flexible ligand (ConformationType::AssignedTorsions, legacy/mod.rs:140-158): poses carry n_flex torsion
+ * angles behind the 7 rigid numbers (mc_dock_make_poses_flex); before the rigid transform the atoms downstream of flexible
+ * bond f (flex_mask[f * n_lig + a], mc_dock_flex_masks) are rotated by t_f about the axis a0 -> a1 through a1, bond after
+ * bond in the order given (a later axis sees the atoms where the earlier rotations left them), in f64 like the transform. */
+int mc_dock_score_flex(mc_ctx *ctx, int64_t n_rec, const mc_float4 *rec_xyzq, const uint16_t *rec_type, const uint8_t *rec_hydrophobic,
+                       int64_t n_lig, const mc_float4 *lig_xyzq, const uint16_t *lig_type, const uint8_t *lig_hydrophobic,
+                       const float lig_anchor[3], int n_rec_types, int n_lig_types, const float *ljtab, int n_flex,
+                       const int32_t *flex_axis, const uint8_t *flex_mask, int64_t n_poses, const float *poses, float *out);
 /* ---- pose set of the scan -- host side, usable without a GPU -------------------- */
 
 /* make_posits_orientations + init_poses for a rigid ligand (src/docking/legacy/mod.rs:386-500): anchors on a
@@ -319,6 +327,17 @@ int mc_dock_score(mc_ctx *ctx, int64_t n_rec, const mc_float4 *rec_xyzq, const u
 int mc_dock_make_poses(const double site_center[3], double site_radius, int num_posits, int num_orientations,
                        float *out_poses, int64_t cap, int64_t *n_out);
 int mc_dock_orientation_count(int num_orientations);
+/* init_poses with flexible bonds (legacy/mod.rs:453-500, Torsion{bond, dihedral_angle} legacy/prep.rs:405-410): every rigid
+ * pose times the cartesian product of angles_per_bond angles = linspace(0, TAU, angles_per_bond) per flexible bond (first
+ * bond slowest).  out_poses: n x (7 + n_flex_bonds) floats {ax, ay, az, qw, qx, qy, qz, t_0 ..}.  n_flex_bonds <= MC_DOCK_MAX_FLEX. */
+#define MC_DOCK_MAX_FLEX 12
+int mc_dock_make_poses_flex(const double site_center[3], double site_radius, int num_posits, int num_orientations,
+                            int n_flex_bonds, int angles_per_bond, float *out_poses, int64_t cap, int64_t *n_out);
+/* The rotating side of every flexible bond: bonds[2 * n_bonds] atom pairs of the ligand, flex_bond_idx[n_flex_bonds] indices
+ * into it; axis_out[2 f] = {a0, a1}, mask_out[f * n_lig + a] = 1 for the atoms downstream of a1 when the bond is cut.
+ * MC_E_INVALID for a bond inside a ring. */
+int mc_dock_flex_masks(int64_t n_lig, int64_t n_bonds, const int32_t *bonds, int n_flex_bonds, const int32_t *flex_bond_idx,
+                       int32_t *axis_out, uint8_t *mask_out);
 /* find_rec_atoms_near_site (legacy/prep.rs:506-532): receptor atoms within 1.4 x site_radius of the site centre
  * that are not hetero atoms; out_idx (capacity n_rec) may be NULL to count. */
 int mc_dock_near_site(int64_t n_rec, const mc_float4 *rec_xyzq, const uint8_t *rec_hetero, const double site_center[3],

@@ -125,6 +125,9 @@ def lib():
     L.mc_last_dock_kernel_ms.restype = C.c_double
     L.mc_last_dock_kernel_ms.argtypes = [vp]
     L.mc_dock_score.argtypes = [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, vp, i64, vp, vp]
+    L.mc_dock_score_flex.argtypes = [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, vp, i32, vp, vp, i64, vp, vp]
+    L.mc_dock_make_poses_flex.argtypes = [vp, C.c_double, i32, i32, i32, i32, vp, i64, C.POINTER(i64)]
+    L.mc_dock_flex_masks.argtypes = [i64, i64, vp, i32, vp, vp, vp]
     L.mc_dock_make_poses.argtypes = [vp, C.c_double, i32, i32, vp, i64, C.POINTER(i64)]
     L.mc_dock_orientation_count.argtypes = [i32]
     L.mc_dock_near_site.argtypes = [i64, vp, vp, vp, C.c_double, vp, C.POINTER(i64)]

@@ -32,7 +32,9 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
                                                                    const uint32_t *__restrict__ lig_meta, float3 anchor0,
                                                                    int n_rec_types, int n_lig_types,
                                                                    const float2 *__restrict__ ljtab,
-                                                                   const float *__restrict__ poses,
+                                                                   const float *__restrict__ poses, int pose_stride, int n_flex,
+                                                                   const int2 *__restrict__ flex_axis,
+                                                                   const uint8_t *__restrict__ flex_mask,
                                                                    float *__restrict__ out) {
     MC_DYN_SHARED(float2, smem);
     // posed ligand as pairs of atoms (a, a+1) per component; an odd count is padded with a far, neutral, sigma = 0 atom
@@ -42,7 +44,38 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
     float2 *e4tab = s2tab + n_rec_types * np;    // [n_rec_types][np] (4 eps)
     uint32_t *lhyd = reinterpret_cast<uint32_t *>(e4tab + n_rec_types * np);  // [np] hydrophobic flags, bit 0 / bit 1
     const int pose = blockIdx.x;
-    const float *ps = poses + 7 * (size_t)pose;
+    const float *ps = poses + (size_t)pose_stride * (size_t)pose;
+    // flexible ligand: the conformer of this pose in f64 (3 n_lig doubles behind the tables)
+    double *conf = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(lhyd + np) + 7) & ~(uintptr_t)7);
+    if (n_flex > 0) {
+        for (int a = threadIdx.x; a < n_lig; a += DOCK_THREADS) {
+            const float4 l = lig[a];
+            conf[3 * a] = (double)l.x; conf[3 * a + 1] = (double)l.y; conf[3 * a + 2] = (double)l.z;
+        }
+        for (int f = 0; f < n_flex; ++f) {
+            __syncthreads();
+            const int2 ax = flex_axis[f];
+            const double p0x = conf[3 * ax.x], p0y = conf[3 * ax.x + 1], p0z = conf[3 * ax.x + 2];
+            const double p1x = conf[3 * ax.y], p1y = conf[3 * ax.y + 1], p1z = conf[3 * ax.y + 2];
+            __syncthreads();  // every thread has read the axis before anybody moves an atom
+            double ux = p1x - p0x, uy = p1y - p0y, uz = p1z - p0z;
+            const double un = 1.0 / sqrt(ux * ux + uy * uy + uz * uz);
+            ux *= un; uy *= un; uz *= un;
+            double sn, cs;
+            sincos((double)ps[7 + f], &sn, &cs);
+            for (int a = threadIdx.x; a < n_lig; a += DOCK_THREADS) {
+                if (!flex_mask[(size_t)f * n_lig + a]) continue;
+                // Rodrigues: v' = v cos t + (u x v) sin t + u (u . v)(1 - cos t), about the axis through a1
+                const double vx = conf[3 * a] - p1x, vy = conf[3 * a + 1] - p1y, vz = conf[3 * a + 2] - p1z;
+                const double cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+                const double dt = (ux * vx + uy * vy + uz * vz) * (1.0 - cs);
+                conf[3 * a] = p1x + vx * cs + cx * sn + ux * dt;
+                conf[3 * a + 1] = p1y + vy * cs + cy * sn + uy * dt;
+                conf[3 * a + 2] = p1z + vz * cs + cz * sn + uz * dt;
+            }
+        }
+        __syncthreads();
+    }
     {
         // The pose transform runs in f64 and is rounded once to f32, exactly as the reference does
         // (Pose{anchor_posit, orientation} are f64, lig_posits are Vec3F32; legacy/mod.rs:149-158,
@@ -57,8 +90,10 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
         for (int a = threadIdx.x; a < 2 * np; a += DOCK_THREADS) {
             if (a >= n_lig) { lxs[a] = lys[a] = lzs[a] = 1.0e6f; lqs[a] = 0.f; continue; }
             const float4 l = lig[a];
-            const double vx = __dsub_rn((double)l.x, (double)anchor0.x), vy = __dsub_rn((double)l.y, (double)anchor0.y),
-                         vz = __dsub_rn((double)l.z, (double)anchor0.z);
+            const double lx = n_flex > 0 ? conf[3 * a] : (double)l.x, ly = n_flex > 0 ? conf[3 * a + 1] : (double)l.y,
+                         lz = n_flex > 0 ? conf[3 * a + 2] : (double)l.z;
+            const double vx = __dsub_rn(lx, (double)anchor0.x), vy = __dsub_rn(ly, (double)anchor0.y),
+                         vz = __dsub_rn(lz, (double)anchor0.z);
             // v' = v + 2 (w (u x v) + u x (u x v))
             const double cx = __dsub_rn(__dmul_rn(qy, vz), __dmul_rn(qz, vy));
             const double cy = __dsub_rn(__dmul_rn(qz, vx), __dmul_rn(qx, vz));
@@ -153,7 +188,8 @@ __global__ void __launch_bounds__(DOCK_THREADS) dock_score_kernel(int n_rec, con
 size_t dock_smem_bytes(int n_lig, int n_rec_types, int n_lig_types) {
     (void)n_lig_types;
     const size_t np = (size_t)(n_lig + 1) / 2;
-    return sizeof(float2) * np * (4 + 2 * (size_t)n_rec_types) + sizeof(uint32_t) * np;
+    // pairs of ligand atoms, LJ pairs per receptor type, hydrophobic flags, and the f64 conformer of a flexible ligand
+    return sizeof(float2) * np * (4 + 2 * (size_t)n_rec_types) + sizeof(uint32_t) * np + 8 + sizeof(double) * 3 * (size_t)n_lig;
 }
 
 cudaError_t dock_prepare() {
@@ -162,11 +198,12 @@ cudaError_t dock_prepare() {
 
 void launch_dock_score(int n_rec, const float4 *rec, const uint32_t *rec_meta, int n_lig, const float4 *lig,
                        const uint32_t *lig_meta, float3 lig_anchor, int n_rec_types, int n_lig_types,
-                       const float2 *ljtab, int n_poses, const float *poses, float *out, cudaStream_t st,
-                       int64_t *launches) {
+                       const float2 *ljtab, int n_poses, const float *poses, int pose_stride, int n_flex, const int2 *flex_axis,
+                       const uint8_t *flex_mask, float *out, cudaStream_t st, int64_t *launches) {
     if (n_poses <= 0) return;
     MC_LAUNCH(dock_score_kernel, n_poses, DOCK_THREADS, dock_smem_bytes(n_lig, n_rec_types, n_lig_types), st, 
-        n_rec, rec, rec_meta, n_lig, lig, lig_meta, lig_anchor, n_rec_types, n_lig_types, ljtab, poses, out);
+        n_rec, rec, rec_meta, n_lig, lig, lig_meta, lig_anchor, n_rec_types, n_lig_types, ljtab, poses, pose_stride, n_flex, flex_axis,
+        flex_mask, out);
     *launches += 1;
 }
 #endif  // MC_HOST_SHIM

@@ -13,6 +13,7 @@
 // from_unit_vecs(a, b) = normalise(1 + a.b, a x b), from_axis_angle(axis, t) = (cos t/2, axis sin t/2),
 // Hamilton product.  The pose transform is the one dock.cu applies (p = anchor + R(q)(x - x_anchor), f64, rounded
 // once to f32), so the filter sees bit-identical points to the scoring kernel's.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -102,6 +103,86 @@ extern "C" int mc_dock_make_poses(const double site_center[3], double site_radiu
                     o[3] = (float)q.w; o[4] = (float)q.x; o[5] = (float)q.y; o[6] = (float)q.z;
                 }
             }
+    return MC_OK;
+}
+
+// init_poses with flexible bonds (legacy/mod.rs:453-500): every rigid pose (anchor x orientation) times the cartesian
+// product of angles_per_bond dihedral angles per flexible bond, angles = linspace(0, TAU, angles_per_bond) (end points
+// included, as the reference's linspace gives them); the FIRST bond varies slowest, the last fastest (the reference
+// extends every existing combination by all angles of the next bond).  Row: {ax, ay, az, qw, qx, qy, qz, t_0 .. t_{F-1}}.
+extern "C" int mc_dock_make_poses_flex(const double site_center[3], double site_radius, int num_posits, int num_orientations,
+                                       int n_flex_bonds, int angles_per_bond, float *out_poses, int64_t cap, int64_t *n_out) {
+    if (!n_out || n_flex_bonds < 0 || n_flex_bonds > MC_DOCK_MAX_FLEX || (n_flex_bonds > 0 && angles_per_bond < 1)) return MC_E_INVALID;
+    int64_t n_rigid = 0;
+    int rc = mc_dock_make_poses(site_center, site_radius, num_posits, num_orientations, nullptr, 0, &n_rigid);
+    if (rc != MC_OK) return rc;
+    int64_t combos = 1;
+    for (int b = 0; b < n_flex_bonds; ++b) {
+        combos *= angles_per_bond;
+        if (combos > ((int64_t)1 << 40) / std::max<int64_t>(n_rigid, 1)) return MC_E_CAPACITY;
+    }
+    *n_out = n_rigid * combos;
+    if (!out_poses) return MC_OK;
+    if (cap < *n_out) return MC_E_CAPACITY;
+    std::vector<float> rigid((size_t)7 * n_rigid);
+    if ((rc = mc_dock_make_poses(site_center, site_radius, num_posits, num_orientations, rigid.data(), n_rigid, &n_rigid)) != MC_OK) return rc;
+    std::vector<float> angles((size_t)std::max(angles_per_bond, 1));
+    for (int a = 0; a < angles_per_bond; ++a)  // linspace(0., TAU, n): f32, both ends
+        angles[(size_t)a] = angles_per_bond == 1 ? 0.f : (float)a * (TAU_F / (float)(angles_per_bond - 1));
+    const int stride = 7 + n_flex_bonds;
+    for (int64_t r = 0; r < n_rigid; ++r)
+        for (int64_t k = 0; k < combos; ++k) {
+            float *o = out_poses + (size_t)stride * (size_t)(r * combos + k);
+            memcpy(o, rigid.data() + 7 * r, 7 * sizeof(float));
+            int64_t rem = k;
+            for (int b = n_flex_bonds - 1; b >= 0; --b) {  // last bond fastest
+                o[7 + b] = angles[(size_t)(rem % angles_per_bond)];
+                rem /= angles_per_bond;
+            }
+        }
+    return MC_OK;
+}
+
+// The two sides of every flexible bond (the reference's rotate_around_bond, EXTERNAL crate: "divide all atoms into those
+// upstream of this bond and those downstream; rotate all downstream atoms", mol_alignment.rs:114-122): the bond graph is
+// cut at bond (a0, a1), everything still connected to a1 is downstream.  axis_out: {a0, a1} per flexible bond;
+// mask_out[f * n_lig + a] = 1 for downstream atoms (a1 itself lies on the axis and is left out).  A bond inside a ring
+// (a0 reachable from a1 after the cut) cannot rotate: MC_E_INVALID.
+extern "C" int mc_dock_flex_masks(int64_t n_lig, int64_t n_bonds, const int32_t *bonds, int n_flex_bonds, const int32_t *flex_bond_idx,
+                                  int32_t *axis_out, uint8_t *mask_out) {
+    if (n_lig <= 0 || n_bonds < 0 || (n_bonds > 0 && !bonds) || n_flex_bonds < 0 || n_flex_bonds > MC_DOCK_MAX_FLEX ||
+        (n_flex_bonds > 0 && (!flex_bond_idx || !axis_out || !mask_out)))
+        return MC_E_INVALID;
+    std::vector<std::vector<int32_t>> adj((size_t)n_lig);
+    for (int64_t b = 0; b < n_bonds; ++b) {
+        const int32_t u = bonds[2 * b], v = bonds[2 * b + 1];
+        if (u < 0 || v < 0 || u >= n_lig || v >= n_lig || u == v) return MC_E_INVALID;
+        adj[(size_t)u].push_back(v);
+        adj[(size_t)v].push_back(u);
+    }
+    for (int f = 0; f < n_flex_bonds; ++f) {
+        const int32_t bi = flex_bond_idx[f];
+        if (bi < 0 || bi >= n_bonds) return MC_E_INVALID;
+        const int32_t a0 = bonds[2 * bi], a1 = bonds[2 * bi + 1];
+        axis_out[2 * f] = a0;
+        axis_out[2 * f + 1] = a1;
+        uint8_t *m = mask_out + (size_t)f * (size_t)n_lig;
+        memset(m, 0, (size_t)n_lig);
+        std::vector<int32_t> stack{a1};
+        std::vector<uint8_t> seen((size_t)n_lig, 0);
+        seen[(size_t)a1] = 1;
+        while (!stack.empty()) {
+            const int32_t u = stack.back();
+            stack.pop_back();
+            for (int32_t v : adj[(size_t)u]) {
+                if ((u == a1 && v == a0) || seen[(size_t)v]) continue;  // the cut bond
+                if (v == a0) return MC_E_INVALID;                       // ring: a0 reached the other way round
+                seen[(size_t)v] = 1;
+                m[(size_t)v] = 1;
+                stack.push_back(v);
+            }
+        }
+    }
     return MC_OK;
 }
 

@@ -1711,13 +1711,45 @@ extern "C" double mc_last_pair_kernel_ms(mc_ctx *c) { return c ? c->last_pair_ms
 
 // ---- docking scan -------------------------------------------------------------------------------------------
 
+static int dock_score_impl(mc_ctx *c, int64_t n_rec, const mc_float4 *rec_xyzq, const uint16_t *rec_type,
+                           const uint8_t *rec_hydrophobic, int64_t n_lig, const mc_float4 *lig_xyzq,
+                           const uint16_t *lig_type, const uint8_t *lig_hydrophobic, const float lig_anchor[3],
+                           int n_rec_types, int n_lig_types, const float *ljtab, int n_flex, const int32_t *flex_axis,
+                           const uint8_t *flex_mask, int64_t n_poses, const float *poses, float *out);
+
 extern "C" int mc_dock_score(mc_ctx *c, int64_t n_rec, const mc_float4 *rec_xyzq, const uint16_t *rec_type,
                              const uint8_t *rec_hydrophobic, int64_t n_lig, const mc_float4 *lig_xyzq,
                              const uint16_t *lig_type, const uint8_t *lig_hydrophobic, const float lig_anchor[3],
                              int n_rec_types, int n_lig_types, const float *ljtab, int64_t n_poses, const float *poses,
                              float *out) {
+    return dock_score_impl(c, n_rec, rec_xyzq, rec_type, rec_hydrophobic, n_lig, lig_xyzq, lig_type, lig_hydrophobic, lig_anchor,
+                           n_rec_types, n_lig_types, ljtab, 0, nullptr, nullptr, n_poses, poses, out);
+}
+
+extern "C" int mc_dock_score_flex(mc_ctx *c, int64_t n_rec, const mc_float4 *rec_xyzq, const uint16_t *rec_type,
+                                  const uint8_t *rec_hydrophobic, int64_t n_lig, const mc_float4 *lig_xyzq,
+                                  const uint16_t *lig_type, const uint8_t *lig_hydrophobic, const float lig_anchor[3],
+                                  int n_rec_types, int n_lig_types, const float *ljtab, int n_flex, const int32_t *flex_axis,
+                                  const uint8_t *flex_mask, int64_t n_poses, const float *poses, float *out) {
+    if (!c) return MC_E_INVALID;
+    MC_REQUIRE(c, n_flex >= 0 && n_flex <= MC_DOCK_MAX_FLEX && (n_flex == 0 || (flex_axis && flex_mask)),
+               "mc_dock_score_flex: 0 <= n_flex <= MC_DOCK_MAX_FLEX with axis and mask arrays");
+    for (int f = 0; f < n_flex; ++f)
+        MC_REQUIRE(c, flex_axis[2 * f] >= 0 && flex_axis[2 * f] < n_lig && flex_axis[2 * f + 1] >= 0 && flex_axis[2 * f + 1] < n_lig &&
+                          flex_axis[2 * f] != flex_axis[2 * f + 1],
+                   "mc_dock_score_flex: bond atom out of range");
+    return dock_score_impl(c, n_rec, rec_xyzq, rec_type, rec_hydrophobic, n_lig, lig_xyzq, lig_type, lig_hydrophobic, lig_anchor,
+                           n_rec_types, n_lig_types, ljtab, n_flex, flex_axis, flex_mask, n_poses, poses, out);
+}
+
+static int dock_score_impl(mc_ctx *c, int64_t n_rec, const mc_float4 *rec_xyzq, const uint16_t *rec_type,
+                           const uint8_t *rec_hydrophobic, int64_t n_lig, const mc_float4 *lig_xyzq,
+                           const uint16_t *lig_type, const uint8_t *lig_hydrophobic, const float lig_anchor[3],
+                           int n_rec_types, int n_lig_types, const float *ljtab, int n_flex, const int32_t *flex_axis,
+                           const uint8_t *flex_mask, int64_t n_poses, const float *poses, float *out) {
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);
+    const int stride = 7 + n_flex;
     MC_REQUIRE(c, n_rec > 0 && n_lig > 0 && n_poses >= 0 && rec_xyzq && lig_xyzq && rec_type && lig_type && ljtab &&
                       lig_anchor && (n_poses == 0 || (poses && out)),
                "mc_dock_score: NULL or empty argument");
@@ -1740,18 +1772,24 @@ extern "C" int mc_dock_score(mc_ctx *c, int64_t n_rec, const mc_float4 *rec_xyzq
     MC_CUDA(c, c->d_rec.ensure((size_t)n_rec)); MC_CUDA(c, c->d_rec_meta.ensure((size_t)n_rec));
     MC_CUDA(c, c->d_lig.ensure((size_t)n_lig)); MC_CUDA(c, c->d_lig_meta.ensure((size_t)n_lig));
     MC_CUDA(c, c->d_dock_tab.ensure(tab.size()));
-    MC_CUDA(c, c->d_poses.ensure((size_t)7 * n_poses)); MC_CUDA(c, c->d_scores.ensure((size_t)5 * n_poses));
+    MC_CUDA(c, c->d_poses.ensure((size_t)stride * n_poses)); MC_CUDA(c, c->d_scores.ensure((size_t)5 * n_poses));
+    if (n_flex > 0) {
+        MC_CUDA(c, c->d_flex_axis.ensure((size_t)n_flex)); MC_CUDA(c, c->d_keep.ensure((size_t)n_flex * (size_t)n_lig));
+        MC_CUDA(c, cudaMemcpyAsync(c->d_flex_axis.p, flex_axis, sizeof(int2) * (size_t)n_flex, cudaMemcpyHostToDevice, st));
+        MC_CUDA(c, cudaMemcpyAsync(c->d_keep.p, flex_mask, (size_t)n_flex * (size_t)n_lig, cudaMemcpyHostToDevice, st));
+    }
     MC_CUDA(c, cudaMemcpyAsync(c->d_rec.p, rec_xyzq, n_rec * sizeof(float4), cudaMemcpyHostToDevice, st));
     MC_CUDA(c, cudaMemcpyAsync(c->d_rec_meta.p, rm.data(), n_rec * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     MC_CUDA(c, cudaMemcpyAsync(c->d_lig.p, lig_xyzq, n_lig * sizeof(float4), cudaMemcpyHostToDevice, st));
     MC_CUDA(c, cudaMemcpyAsync(c->d_lig_meta.p, lm.data(), n_lig * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     MC_CUDA(c, cudaMemcpyAsync(c->d_dock_tab.p, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
-    MC_CUDA(c, cudaMemcpyAsync(c->d_poses.p, poses, sizeof(float) * 7 * n_poses, cudaMemcpyHostToDevice, st));
+    MC_CUDA(c, cudaMemcpyAsync(c->d_poses.p, poses, sizeof(float) * stride * n_poses, cudaMemcpyHostToDevice, st));
     {
         TimedRegion tr(c, c->dock_acc);
         launch_dock_score((int)n_rec, c->d_rec.p, c->d_rec_meta.p, (int)n_lig, c->d_lig.p, c->d_lig_meta.p,
                           make_float3(lig_anchor[0], lig_anchor[1], lig_anchor[2]), n_rec_types, n_lig_types,
-                          c->d_dock_tab.p, (int)n_poses, c->d_poses.p, c->d_scores.p, st, &c->launches);
+                          c->d_dock_tab.p, (int)n_poses, c->d_poses.p, stride, n_flex, n_flex > 0 ? c->d_flex_axis.p : nullptr,
+                          n_flex > 0 ? c->d_keep.p : nullptr, c->d_scores.p, st, &c->launches);
         tr.stop();
     }
     MC_CUDA(c, cudaGetLastError());

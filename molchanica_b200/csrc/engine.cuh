@@ -121,6 +121,7 @@ struct mc_ctx {
     DevBuf<double> red_partial, red_out;
     DevBuf<float4> d_rec, d_lig, d_rec_s, d_lig_s;
     DevBuf<uint8_t> d_keep;
+    DevBuf<int2> d_flex_axis;
     DevBuf<uint32_t> d_rec_meta, d_lig_meta;
 
     // bonded terms (bonded.cu), caller's atom ids
@@ -223,7 +224,7 @@ struct mc_ctx {
         excl_start.release(); excl_idx.release(); p14_start.release(); p14_idx.release();
         ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); ext_force2.release(); d_poses.release(); d_scores.release();
         grid.release(); red_partial.release(); red_out.release(); d_rec.release(); d_lig.release();
-        d_rec_meta.release(); d_lig_meta.release(); d_rec_s.release(); d_lig_s.release(); d_keep.release();
+        d_rec_meta.release(); d_lig_meta.release(); d_rec_s.release(); d_lig_s.release(); d_keep.release(); d_flex_axis.release();
         for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_stage_v[b].release(); snap_ids[b].release(); }
         bonds.release(); bond_kr0.release(); angle_kt0.release(); angles.release(); dihedrals.release(); dihedral_prm.release();
         bonded_e.release(); cons_virial.release(); com_partial.release(); waters.release(); vsites.release(); csvr_lambda.release();

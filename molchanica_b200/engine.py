@@ -272,6 +272,27 @@ class MdEngine:
         self._chk(self._L.mc_dock_make_poses(_ptr(c), float(site_radius), int(num_posits), int(num_orientations), _ptr(out), n.value, C.byref(n)))
         return out
 
+    def dock_make_poses_flex(self, site_center, site_radius, n_flex_bonds, angles_per_bond, num_posits=8, num_orientations=60):
+        """mc_dock_make_poses_flex: n x (7 + n_flex_bonds) floats."""
+        c = np.ascontiguousarray(site_center, np.float64)
+        n = C.c_int64(0)
+        args = (_ptr(c), float(site_radius), int(num_posits), int(num_orientations), int(n_flex_bonds), int(angles_per_bond))
+        self._chk(self._L.mc_dock_make_poses_flex(*args, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 7 + n_flex_bonds), np.float32)
+        self._chk(self._L.mc_dock_make_poses_flex(*args, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def dock_flex_masks(self, n_lig, bonds, flex_bond_idx):
+        """mc_dock_flex_masks: (axis (F, 2) int32, mask (F, n_lig) uint8)."""
+        b = np.ascontiguousarray(bonds, np.int32).reshape(-1, 2)
+        fi = np.ascontiguousarray(flex_bond_idx, np.int32)
+        axis = np.zeros((len(fi), 2), np.int32)
+        mask = np.zeros((len(fi), n_lig), np.uint8)
+        rc = self._L.mc_dock_flex_masks(int(n_lig), len(b), _ptr(b), len(fi), _ptr(fi), _ptr(axis), _ptr(mask))
+        if rc != 0:
+            raise McError(rc, "mc_dock_flex_masks: bad bond list or a flexible bond inside a ring")
+        return axis, mask
+
     def dock_filter_poses(self, rec_near, rec_is_carbon, lig, lig_is_carbon, lig_anchor, poses, vdw_radius=1.7, gpu=True):
         """keep mask of the clash pre-filter: on the device (mc_dock_filter_poses_gpu) or with the host twin."""
         rec = _f4(rec_near)
@@ -346,6 +367,25 @@ class MdEngine:
         self._chk(self._L.mc_dock_score(self._h, len(rec), _ptr(rec), _ptr(rt), _ptr(rh), len(lig), _ptr(lig), _ptr(lt),
                                         _ptr(lh), _ptr(anchor), tab.shape[0], tab.shape[1], _ptr(tab), len(poses),
                                         _ptr(poses), _ptr(out)))
+        return out
+
+    def dock_score_flex(self, d, poses, flex_axis, flex_mask):
+        """mc_dock_score_flex: poses (P, 7 + F) with F torsion angles; flex_axis (F, 2), flex_mask (F, n_lig)."""
+        poses = np.ascontiguousarray(poses, np.float32)
+        rec, lig = _f4(d["rec"]), _f4(d["lig"])
+        rt = np.ascontiguousarray(d["rec_type"], np.uint16)
+        lt = np.ascontiguousarray(d["lig_type"], np.uint16)
+        rh = np.ascontiguousarray(d["rec_hphob"], np.uint8)
+        lh = np.ascontiguousarray(d["lig_hphob"], np.uint8)
+        anchor = np.ascontiguousarray(d["lig_anchor"], np.float32)
+        tab = np.ascontiguousarray(d["ljtab"], np.float32)
+        ax = np.ascontiguousarray(flex_axis, np.int32).reshape(-1, 2)
+        mk = np.ascontiguousarray(flex_mask, np.uint8).reshape(len(ax), len(lig))
+        assert poses.shape[1] == 7 + len(ax)
+        out = np.empty((len(poses), 5), np.float32)
+        self._chk(self._L.mc_dock_score_flex(self._h, len(rec), _ptr(rec), _ptr(rt), _ptr(rh), len(lig), _ptr(lig), _ptr(lt),
+                                             _ptr(lh), _ptr(anchor), tab.shape[0], tab.shape[1], _ptr(tab), len(ax), _ptr(ax),
+                                             _ptr(mk), len(poses), _ptr(poses), _ptr(out)))
         return out
 
     def last_dock_kernel_ms(self):

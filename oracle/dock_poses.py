@@ -72,6 +72,75 @@ def make_poses(site_center, site_radius, num_posits, num_orientations):
     return poses
 
 
+def make_poses_flex(site_center, site_radius, num_posits, num_orientations, n_flex_bonds, angles_per_bond):
+    """init_poses with flexible bonds (mod.rs:453-500): every rigid pose times the cartesian product of
+    linspace(0, TAU, angles_per_bond) per bond, first bond slowest.  n x (7 + n_flex_bonds) f32."""
+    import itertools
+    rigid = make_poses(site_center, site_radius, num_posits, num_orientations)
+    if n_flex_bonds == 0:
+        return rigid
+    angles = [f32(0.0)] if angles_per_bond == 1 else [f32(a) * (TAU32 / f32(angles_per_bond - 1)) for a in range(angles_per_bond)]
+    combos = np.array(list(itertools.product(angles, repeat=n_flex_bonds)), f32)
+    out = np.zeros((len(rigid) * len(combos), 7 + n_flex_bonds), f32)
+    out[:, :7] = np.repeat(rigid, len(combos), axis=0)
+    out[:, 7:] = np.tile(combos, (len(rigid), 1))
+    return out
+
+
+def flex_masks(n_lig, bonds, flex_bond_idx):
+    """Downstream side of every flexible bond: atoms still connected to a1 when bond (a0, a1) is cut (a1 itself excluded).
+    Returns (axis (F, 2), mask (F, n_lig)); raises ValueError for a bond inside a ring."""
+    bonds = np.asarray(bonds, np.int64).reshape(-1, 2)
+    adj = [[] for _ in range(n_lig)]
+    for u, v in bonds:
+        adj[u].append(v)
+        adj[v].append(u)
+    axis = np.zeros((len(flex_bond_idx), 2), np.int32)
+    mask = np.zeros((len(flex_bond_idx), n_lig), np.uint8)
+    for f, bi in enumerate(flex_bond_idx):
+        a0, a1 = bonds[bi]
+        axis[f] = (a0, a1)
+        seen, todo = {int(a1)}, [int(a1)]
+        while todo:
+            u = todo.pop()
+            for v in adj[u]:
+                if (u == a1 and v == a0) or v in seen:
+                    continue
+                if v == a0:
+                    raise ValueError("flexible bond inside a ring")
+                seen.add(int(v))
+                mask[f, v] = 1
+                todo.append(int(v))
+    return axis, mask
+
+
+def apply_torsions(lig_xyz, axis, mask, angles):
+    """The conformer of one pose in f64: for every flexible bond in order, the downstream atoms are rotated by its angle
+    about the axis a0 -> a1 through a1 (Rodrigues), a later axis seeing the atoms where earlier rotations left them."""
+    x = np.asarray(lig_xyz, np.float64)[:, :3].copy()
+    for (a0, a1), m, t in zip(axis, mask, angles):
+        p1 = x[a1].copy()
+        u = p1 - x[a0]
+        u /= np.sqrt((u * u).sum())
+        c, s = np.cos(float(t)), np.sin(float(t))
+        sel = np.nonzero(m)[0]
+        v = x[sel] - p1
+        x[sel] = p1 + v * c + np.cross(u, v) * s + np.outer((v @ u) * (1.0 - c), u)
+    return x
+
+
+def pose_points_flex(lig_xyz, lig_anchor, pose, axis, mask):
+    """Torsions (f64) then the rigid transform (f64), rounded once to f32."""
+    conf = apply_torsions(lig_xyz[:, :3].astype(f32), axis, mask, pose[7:])
+    q = pose[3:7].astype(np.float64)
+    q = q / np.sqrt(np.sum(q * q))
+    v = conf - np.asarray(lig_anchor, f32).astype(np.float64)
+    qv = q[1:]
+    c = np.cross(qv, v)
+    dd = np.cross(qv, c)
+    return (v + 2.0 * (q[0] * c + dd) + pose[:3].astype(np.float64)).astype(f32)
+
+
 def near_site(rec_xyz, hetero, site_center, site_radius):
     d = np.sqrt(((rec_xyz[:, :3].astype(np.float64) - np.asarray(site_center, np.float64)) ** 2).sum(1))
     ok = d < 1.4 * site_radius

@@ -13,6 +13,6 @@ extern "C" void host_dock_score(int n_rec, const float4 *rec, const uint32_t *re
                                 float *out) {
     shim_launch((unsigned)n_poses, DOCK_THREADS, [&] {
         dock_score_kernel(n_rec, rec, rec_meta, n_lig, lig, lig_meta, make_float3(anchor[0], anchor[1], anchor[2]), n_rec_types, n_lig_types,
-                          ljtab, poses, out);
+                          ljtab, poses, 7, 0, nullptr, nullptr, out);
     });
 }

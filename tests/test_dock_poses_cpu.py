@@ -85,3 +85,48 @@ def test_near_site_and_clash_filter_match_restatement(engine_lib):
     ref = DP.filter_poses(near, near_c, lig, d["lig_hphob"], anchor, poses, 1.7)
     assert np.array_equal(keep, ref)
     assert 0 < kept.value == int(ref.sum()) < len(poses)      # the filter does remove some and keep some
+
+
+def test_flexible_pose_set_and_downstream_masks(engine_lib):
+    """init_poses with flexible bonds (legacy/mod.rs:453-500) and the two sides of a rotatable bond, against the numpy
+    restatement and known answers: pose count = rigid x angles^bonds, first bond slowest, linspace end points 0 and TAU;
+    a chain splits at the bond, a ring bond is refused."""
+    c = np.asarray((1.0, 2.0, 3.0), np.float64)
+    n = C.c_int64(0)
+    assert engine_lib.mc_dock_make_poses_flex(_ptr(c), 6.0, 2, 16, 2, 3, None, 0, C.byref(n)) == 0
+    n_rigid = 8 * engine_lib.mc_dock_orientation_count(16)
+    assert n.value == n_rigid * 9
+    out = np.zeros((n.value, 9), np.float32)
+    assert engine_lib.mc_dock_make_poses_flex(_ptr(c), 6.0, 2, 16, 2, 3, _ptr(out), n.value, C.byref(n)) == 0
+    ref = DP.make_poses_flex(c, 6.0, 2, 16, 2, 3)
+    assert np.array_equal(out, ref)
+    assert np.array_equal(out[:9, 7], np.repeat(np.float32([0.0, np.pi, 2 * np.pi]), 3))    # first bond slowest
+    assert np.array_equal(out[:9, 8], np.tile(np.float32([0.0, np.pi, 2 * np.pi]), 3))
+    assert np.array_equal(out[:9, :7], np.repeat(out[:1, :7], 9, axis=0))
+    # rigid case = mc_dock_make_poses
+    assert engine_lib.mc_dock_make_poses_flex(_ptr(c), 6.0, 2, 16, 0, 0, None, 0, C.byref(n)) == 0 and n.value == n_rigid
+    # a 6-chain with a 3-ring at its end: 0-1-2-3-4-5, 3-5
+    bonds = np.array([[0, 1], [1, 2], [2, 3], [3, 4], [4, 5], [3, 5]], np.int32)
+    flex = np.array([1, 2], np.int32)
+    axis, mask = np.zeros((2, 2), np.int32), np.zeros((2, 6), np.uint8)
+    assert engine_lib.mc_dock_flex_masks(6, len(bonds), _ptr(bonds), 2, _ptr(flex), _ptr(axis), _ptr(mask)) == 0
+    ra, rm = DP.flex_masks(6, bonds, flex)
+    assert np.array_equal(axis, ra) and np.array_equal(mask, rm)
+    assert mask[0].tolist() == [0, 0, 0, 1, 1, 1] and mask[1].tolist() == [0, 0, 0, 0, 1, 1] and axis.tolist() == [[1, 2], [2, 3]]
+    ring = np.array([3], np.int32)   # bond 3-4 lies in the ring 3-4-5
+    assert engine_lib.mc_dock_flex_masks(6, len(bonds), _ptr(bonds), 1, _ptr(ring), _ptr(axis), _ptr(mask)) != 0
+
+
+def test_torsion_restatement_known_answers():
+    """apply_torsions: a half turn about the z axis maps (x, y, z) to (-x, -y, z) for downstream atoms only; bond lengths to
+    the axis atoms are kept; a second torsion acts on the already rotated atoms."""
+    lig = np.array([[0, 0, 0], [0, 0, 1.5], [1.0, 0.5, 2.0], [1.0, 0.5, 3.5], [2.2, 0.5, 3.9]], np.float64)
+    axis, mask = DP.flex_masks(5, [[0, 1], [1, 2], [2, 3], [3, 4]], [0])
+    x = DP.apply_torsions(lig, axis, mask, [np.pi])
+    assert np.allclose(x[:2], lig[:2]) and np.allclose(x[2:, 0], -lig[2:, 0]) and np.allclose(x[2:, 1], -lig[2:, 1]) and np.allclose(x[2:, 2], lig[2:, 2])
+    axis2, mask2 = DP.flex_masks(5, [[0, 1], [1, 2], [2, 3], [3, 4]], [0, 2])
+    y = DP.apply_torsions(lig, axis2, mask2, [0.7, -1.1])
+    d = lambda p, i, j: np.linalg.norm(p[i] - p[j])
+    for i, j in ((0, 1), (1, 2), (2, 3), (3, 4)):
+        assert abs(d(y, i, j) - d(lig, i, j)) < 1e-12
+    assert not np.allclose(y[4], DP.apply_torsions(lig, axis2[:1], mask2[:1], [0.7])[4])

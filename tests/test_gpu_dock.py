@@ -44,6 +44,39 @@ def test_dock_scan_matches_golden():
     e.close()
 
 
+def test_flexible_ligand_scan_matches_oracle():
+    """SURVEY 8a row a8 with torsions (ConformationType::AssignedTorsions, legacy/mod.rs:140-158, :453-500): the pose set of
+    mc_dock_make_poses_flex scored by mc_dock_score_flex against the numpy restatement of the conformer (torsions in f64,
+    then the rigid transform, rounded once) fed to the fp64 oracle pose by pose; the rigid columns of the same call equal
+    mc_dock_score."""
+    from molchanica_b200.engine import MdEngine
+    from oracle import dock_poses as DP
+    from oracle import oracle_py as O
+    d = W.docking_c5(n_rec=800, n_lig=18, n_poses=8, seeds=(545, 546, 547))
+    n_lig = len(d["lig"])
+    bonds = np.array([[i, i + 1] for i in range(n_lig - 1)], np.int32)   # the ligand is a self-avoiding chain
+    e = MdEngine()
+    axis, mask = e.dock_flex_masks(n_lig, bonds, [4, 11])
+    ra, rm = DP.flex_masks(n_lig, bonds, [4, 11])
+    assert np.array_equal(axis, ra) and np.array_equal(mask, rm)
+    site = d["poses"][:, :3].mean(0)
+    poses = e.dock_make_poses_flex(site, 6.0, 2, 3, num_posits=2, num_orientations=16)
+    assert poses.shape == (8 * 32 * 9, 9)
+    s = e.dock_score_flex(d, poses, axis, mask)
+    pick = np.sort(np.random.default_rng(5).choice(len(poses), 48, replace=False))
+    ident = np.array([[0, 0, 0, 1, 0, 0, 0]], np.float32)
+    for p in pick:
+        pts = DP.pose_points_flex(d["lig"], d["lig_anchor"], poses[p], axis, mask)
+        dd = dict(d, lig=np.concatenate([pts, d["lig"][:, 3:4]], 1).astype(np.float32), lig_anchor=np.zeros(3, np.float32))
+        ref, ref_abs = O.dock_score(dd, precision=64, poses=ident, with_abs=True)
+        _check(s[p:p + 1], ref, ref_abs)
+    # zero torsions = the rigid scan
+    rigid = poses[poses[:, 7:].max(1) == 0.0]
+    assert len(rigid) == 8 * 32
+    assert np.array_equal(e.dock_score_flex(d, rigid, axis, mask), e.dock_score(d, poses=rigid[:, :7].copy()))
+    e.close()
+
+
 def test_dock_scan_full_size_matches_oracle_on_sampled_poses():
     """C5 at full size (10k poses x 5k receptor x 40 ligand atoms): 600 poses drawn from the scan are held to the fp64
     oracle -- scored inside the full 10k-pose launch, so the launch geometry is the headline one."""
