@@ -282,6 +282,10 @@ extern "C" int mc_set_exclusions(mc_ctx *c, const int32_t *start, const int32_t 
     if (!start || !idx || start[c->n_global] == 0) { c->have_excl = false; return MC_OK; }
     const int64_t n = c->n_global, m = start[n];
     MC_REQUIRE(c, m >= 0, "mc_set_exclusions: negative total");
+    // the rows are dereferenced on the device (tile_build.cu, pme.cu): a malformed CSR must not get that far
+    MC_REQUIRE(c, start[0] == 0, "mc_set_exclusions: start[0] must be 0");
+    for (int64_t i = 0; i < n; ++i) MC_REQUIRE(c, start[i + 1] >= start[i], "mc_set_exclusions: start[] must be non-decreasing");
+    for (int64_t k = 0; k < m; ++k) MC_REQUIRE(c, idx[k] >= 0 && idx[k] < n, "mc_set_exclusions: partner id out of range");
     MC_CUDA(c, c->excl_start.ensure((size_t)n + 1));
     MC_CUDA(c, c->excl_idx.ensure((size_t)m));
     MC_CUDA(c, cudaMemcpy(c->excl_start.p, start, (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -946,7 +950,11 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     // closes the tail first (engine_flush_tail), so the deferral is invisible through the ABI.
     const bool baro = c->baro_kind != MC_BAROSTAT_NONE && c->periodic && !c->comm_active;
     // (a decomposed run rebuilds on its schedule, known to every rank: nothing to pipeline there, the deferral works as is)
-    const bool defer = c->defer_tail && ext_forces != nullptr && (pipelined || (c->comm_active && !c->sync_rebuild)) && n_steps > 0 && !baro;
+    // Constrained systems (rigid waters, bonds to hydrogen) close every step on its own -- half kick, then the velocity stage
+    // of RATTLE -- instead of merging the closing half kick with the next step's opening one.
+    const bool constrained = c->n_waters > 0 || c->n_hclusters > 0;
+    const bool defer = c->defer_tail && ext_forces != nullptr && (pipelined || (c->comm_active && !c->sync_rebuild)) && n_steps > 0 && !baro &&
+                       !constrained;
     struct UploadGuard {  // whatever path leaves this function, the caller's array is no longer being read
         cudaStream_t s = nullptr;
         ~UploadGuard() { if (s) cudaStreamSynchronize(s); }
@@ -1029,11 +1037,11 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
                 comm_step_descriptors(c, c->steps_since_build + 1 >= comm_interval(c), &push, &split);
                 launch_kick_drift_halo((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0,
                                        d_ext, c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0,
-                                       s == 0 ? 0.5f * dt : dt, dt, max_disp, c->rebuild_flag.p, push, st, &c->launches);
+                                       (s == 0 || constrained) ? 0.5f * dt : dt, dt, max_disp, c->rebuild_flag.p, push, st, &c->launches);
             } else {
                 if (pipelined) tag[s & 1] = (++c->flag_tag) & 0x1fffffff;
                 launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, d_ext,
-                                  c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, s == 0 ? 0.5f * dt : dt, dt,
+                                  c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, (s == 0 || constrained) ? 0.5f * dt : dt, dt,
                                   max_disp, lookahead, c->rebuild_flag.p, st, &c->launches,
                                   pipelined ? reinterpret_cast<uint32_t *>(c->rebuild_flag.p + 2) : nullptr,
                                   pipelined ? h_flag + (s & 1) : nullptr, tag[s & 1]);
@@ -1073,7 +1081,7 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
             MC_CUDA(c, c->red_out.ensure(4));
             MC_CUDA(c, c->csvr_lambda.ensure(1));
             const size_t r0 = (size_t)c->row0;
-            launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + r0, c->vel[c->cur].p + r0, c->red_partial.p, c->red_out.p, st,
+            launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + r0, c->vel[c->cur].p + r0, c->flags[c->cur].p + r0, c->red_partial.p, c->red_out.p, st,
                                  &c->launches);
             launch_csvr((int)c->n_rows_sorted(), c->vel[c->cur].p + r0, c->red_out.p, MC_KB * (double)c->lgv_temperature,
                         std::exp(-(double)c->lgv_gamma * (double)dt), 3.0 * (double)c->n_waters + (double)c->n_hconstraints, c->lgv_seed, c->lgv_step++,
@@ -1127,13 +1135,22 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
             if ((rc = apply_barostat(c, dt)) != MC_OK) return rc;
             skip_prev = true;  // the flag word of this step refers to the reference positions of the old list
         }
+        if (constrained) {
+            // closing half kick of THIS step, then RATTLE's velocity stage on the positions of this step
+            const size_t r0 = (size_t)c->row0;
+            launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, d_ext,
+                              c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, 0.5f * dt, 0.f, 0.f, 0.f,
+                              c->rebuild_flag.p, st, &c->launches);
+            launch_rattle_velocities(c->n_waters, c->waters.p, c->n_hclusters, c->hclusters.p, c->slot_of_orig.p, c->xyzq[c->cur].p,
+                                     c->vel[c->cur].p, make_params(c), st, &c->launches);
+        }
         c->n_steps++;
     }
     if (defer) {
         c->tail_pending = true;
         c->tail_dt = dt;
         c->tail_ext = d_ext;
-    } else if (n_steps > 0) {
+    } else if (n_steps > 0 && !constrained) {
         TimedRegion tr(c, c->integ_acc);
         const size_t r0 = (size_t)c->row0;
         launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, d_ext,
@@ -1430,7 +1447,7 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
     }
     MC_CUDA(c, c->red_partial.ensure((size_t)energy_partial_elems()));
     MC_CUDA(c, c->red_out.ensure(4));
-    launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + c->row0, c->vel[c->cur].p + c->row0, c->red_partial.p, c->red_out.p, c->st,
+    launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + c->row0, c->vel[c->cur].p + c->row0, c->flags[c->cur].p + c->row0, c->red_partial.p, c->red_out.p, c->st,
                          &c->launches);
     double h[3];
     MC_CUDA(c, cudaMemcpyAsync(h, c->red_out.p, sizeof(h), cudaMemcpyDeviceToHost, c->st));
@@ -1459,7 +1476,8 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
     }
     out->energy_kinetic = h[1] / (double)MC_ACCEL_CONV;
     // each rigid water removes three degrees of freedom, each constrained bond one
-    const double dof = 3.0 * h[2] - 3.0 * (double)c->n_waters - (double)c->n_hconstraints;
+    // ... and removing the centre-of-mass drift takes three more
+    const double dof = 3.0 * h[2] - 3.0 * (double)c->n_waters - (double)c->n_hconstraints - (c->com_every > 0 ? 3.0 : 0.0);
     out->temperature = dof > 0 ? 2.0 * out->energy_kinetic / (dof * MC_KB) : 0.0;
     return MC_OK;
 }
@@ -1473,7 +1491,7 @@ static int compute_pressure(mc_ctx *c, double *pressure_bar, double *virial) {
     const bool constrained = c->n_waters > 0 || c->n_hclusters > 0;
     MC_CUDA(c, c->red_partial.ensure((size_t)energy_partial_elems()));
     MC_CUDA(c, c->red_out.ensure(4));
-    launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + c->row0, c->vel[c->cur].p + c->row0, c->red_partial.p, c->red_out.p, c->st,
+    launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + c->row0, c->vel[c->cur].p + c->row0, c->flags[c->cur].p + c->row0, c->red_partial.p, c->red_out.p, c->st,
                          &c->launches);
     const int coul = c->coul_disabled ? MC_COULOMB_NONE : c->coul_mode;
     { int rc32 = engine_ensure_list32(c); if (rc32 != MC_OK) return rc32; }

@@ -236,13 +236,13 @@ __global__ void __launch_bounds__(128) pairs14_kernel(int n_rows, int row0, cons
 // Two-stage deterministic reduction: per-block partials {sum e_i, sum 1/2 m v^2, n_mobile}.
 constexpr int RED_BLOCKS = 592;  // 4 x 148 SMs
 __global__ void __launch_bounds__(256) energy_partial_kernel(int n_rows, const float4 *__restrict__ force,
-                                                              const float4 *__restrict__ vel,
+                                                              const float4 *__restrict__ vel, const uint8_t *__restrict__ flags,
                                                               double *__restrict__ partial) {
     double e = 0.0, ke = 0.0, nm = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
         e += (double)force[i].w;
         const float4 v = vel[i];
-        if (v.w > 0.f) {
+        if (v.w > 0.f && !(flags && (flags[i] & MC_FLAG_STATIC))) {  // a static atom is no degree of freedom, whatever its mass
             ke += 0.5 * ((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z) / (double)v.w;
             nm += 1.0;
         }
@@ -353,11 +353,11 @@ void launch_pairs14(int n_rows, int row0, const float4 *xyzq, const uint16_t *ty
 
 int energy_partial_elems() { return 3 * RED_BLOCKS; }
 
-void launch_energy_reduce(int n_rows, const float4 *force, const float4 *vel, double *partial, double *out3,
+void launch_energy_reduce(int n_rows, const float4 *force, const float4 *vel, const uint8_t *flags, double *partial, double *out3,
                           cudaStream_t st, int64_t *launches) {
     int nb = (int)div_up(n_rows > 0 ? n_rows : 1, 256);
     if (nb > RED_BLOCKS) nb = RED_BLOCKS;
-    MC_LAUNCH(energy_partial_kernel, nb, 256, 0, st, n_rows, force, vel, partial);
+    MC_LAUNCH(energy_partial_kernel, nb, 256, 0, st, n_rows, force, vel, flags, partial);
     MC_LAUNCH(energy_final_kernel, 1, 32, 0, st, partial, nb, out3);
     *launches += 2;
 }

@@ -34,7 +34,7 @@ void launch_pairs14(int n_rows, int row0, const float4 *xyzq, const uint16_t *ty
                     float scale_lj, float scale_q, int lj_on, int coul_on, float4 *force, cudaStream_t st,
                     int64_t *launches);
 int energy_partial_elems();
-void launch_energy_reduce(int n_rows, const float4 *force, const float4 *vel, double *partial, double *out3,
+void launch_energy_reduce(int n_rows, const float4 *force, const float4 *vel, const uint8_t *flags /* may be NULL */, double *partial, double *out3,
                           cudaStream_t st, int64_t *launches);
 
 // pair_tile.cu -- the TMA-staged variant: rows of 16-bit tile-local indices (tile_build.cu, compact = true), the cell's

@@ -5,17 +5,19 @@
 // is done relative to the oxygen's old position, so no extra position array is kept and fp32 cancellation
 // stays at the 1e-6 A level; each atom keeps its own periodic image (molecules may straddle the box edge).
 // HBM-bound and tiny: 3 x (16 + 16) B read and written per molecule.
-// STATUS: as bonded.cu -- arithmetic verified on the host against a converged fp64 SHAKE
-// (tests/test_settle_cpu.py), kernel not yet run on hardware (round-1 GPU budget spent).
+// After the closing half kick of every step the velocity stage of RATTLE (rattle_terms.h) removes the velocity components
+// along the constrained bonds, so that kinetic energy / temperature / pressure read between steps are the constrained
+// system's.  Confirmed on hardware at the end of round 1 (positions) / in round 2 (velocity stage).
 #include "settle.cuh"
 #include "settle_terms.h"
 #include "vsite_terms.h"
 #include "shake_terms.h"
+#include "rattle_terms.h"
 
 namespace {
 
 // Adds a thread's share of the constraint virial to *virial (one fp64 atomic per warp).  The constraint force that
-// moved atom i by delta_i within this step is m_i delta_i / dt^2 (kick-drift form); its virial is taken with the OLD
+// moved atom i by delta_i within this step is 2 m_i delta_i / dt^2 (half kick + drift form); its virial is taken with the OLD
 // positions relative to the molecule's first atom (the constraint forces of a molecule sum to zero), in kcal/mol.
 __device__ __forceinline__ void add_constraint_virial(float wc, double *__restrict__ virial) {
 #pragma unroll
@@ -61,7 +63,9 @@ __device__ __forceinline__ float settle_one(int w, const int4 *__restrict__ wate
     xyzq[so] = xo; xyzq[s1] = x1; xyzq[s2] = x2;
     vel[so] = vo; vel[s1] = v1; vel[s2] = v2;
     // oxygen: old relative position 0, no contribution
-    return sp.m_h * (db_[0] * b0[0] + db_[1] * b0[1] + db_[2] * b0[2] + dc_[0] * c0[0] + dc_[1] * c0[1] + dc_[2] * c0[2]) * inv_dt * inv_dt *
+    // The step is half kick + drift (the closing half kick and RATTLE's velocity stage follow the force evaluation): the
+    // position stage's displacement is that of a constraint force acting through ONE half kick, delta = f_c dt^2 / (2 m).
+    return 2.f * sp.m_h * (db_[0] * b0[0] + db_[1] * b0[1] + db_[2] * b0[2] + dc_[0] * c0[0] + dc_[1] * c0[1] + dc_[2] * c0[2]) * inv_dt * inv_dt *
            (1.f / (float)MC_ACCEL_CONV);
 }
 
@@ -129,7 +133,7 @@ __device__ __forceinline__ float shake_h_one(int c, const int4 *__restrict__ clu
         xyzq[sh[k]] = xh[k]; vel[sh[k]] = vh[k];
         wc += (dk[0] * r0[k][0] + dk[1] * r0[k][1] + dk[2] * r0[k][2]) / inv_m[k];
     }
-    return wc * inv_dt * inv_dt * (1.f / (float)MC_ACCEL_CONV);
+    return 2.f * wc * inv_dt * inv_dt * (1.f / (float)MC_ACCEL_CONV);  // delta = f_c dt^2 / (2 m), see settle_one
 }
 
 __global__ void __launch_bounds__(128) shake_h_kernel(int n_c, const int4 *__restrict__ clusters, const float *__restrict__ dist,
@@ -184,9 +188,81 @@ __global__ void __launch_bounds__(128) vsite_spread_kernel(int n_v, const int4 *
     force[sm] = fm4;
 }
 
+// Velocity stage of RATTLE: one thread per rigid water / per hydrogen cluster (rattle_terms.h).
+__global__ void __launch_bounds__(128) rattle_waters_kernel(int n_w, const int4 *__restrict__ waters, const int *__restrict__ slot_of_orig,
+                                                             const float4 *__restrict__ xyzq, float4 *__restrict__ vel, const NbParams p) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_w) return;
+    const int4 ids = waters[w];
+    const int sl[3] = {slot_of_orig[ids.x], slot_of_orig[ids.y], slot_of_orig[ids.z]};
+    float r[4][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, v[4][3], inv_m[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 vv[3];
+    const float4 x0 = xyzq[sl[0]];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 x = xyzq[sl[k]];
+        vv[k] = vel[sl[k]];
+        float d[3] = {x.x - x0.x, x.y - x0.y, x.z - x0.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (p.periodic) d[a] -= rintf(d[a] * p.inv_ext[a]) * p.ext[a];
+            r[k][a] = d[a];
+        }
+        v[k][0] = vv[k].x; v[k][1] = vv[k].y; v[k][2] = vv[k].z;
+        inv_m[k] = vv[k].w;
+    }
+    v[3][0] = v[3][1] = v[3][2] = 0.f;
+    const int ci[3] = {0, 0, 1}, cj[3] = {1, 2, 2};
+    mc_rattle_velocity<float>(3, ci, cj, r, inv_m, v);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) vel[sl[k]] = make_float4(v[k][0], v[k][1], v[k][2], vv[k].w);
+}
+
+__global__ void __launch_bounds__(128) rattle_h_kernel(int n_c, const int4 *__restrict__ clusters, const int *__restrict__ slot_of_orig,
+                                                        const float4 *__restrict__ xyzq, float4 *__restrict__ vel, const NbParams p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_c) return;
+    const int4 ids = clusters[c];
+    const int id[4] = {ids.x, ids.y, ids.z, ids.w};
+    int sl[4], nat = 0, ci[3] = {0, 0, 0}, cj[3] = {1, 2, 3};
+    float r[4][3], v[4][3], inv_m[4], w4[4];
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 4; ++k) {
+        r[k][0] = r[k][1] = r[k][2] = v[k][0] = v[k][1] = v[k][2] = 0.f;
+        inv_m[k] = 0.f;
+        if (id[k] < 0) continue;
+        sl[nat] = slot_of_orig[id[k]];
+        const float4 x = xyzq[sl[nat]], vv = vel[sl[nat]];
+        if (nat == 0) x0 = x;
+        float d[3] = {x.x - x0.x, x.y - x0.y, x.z - x0.z};
+        for (int a = 0; a < 3; ++a) {
+            if (p.periodic) d[a] -= rintf(d[a] * p.inv_ext[a]) * p.ext[a];
+            r[nat][a] = d[a];
+        }
+        v[nat][0] = vv.x; v[nat][1] = vv.y; v[nat][2] = vv.z;
+        inv_m[nat] = vv.w; w4[nat] = vv.w;
+        ++nat;
+    }
+    if (nat < 2) return;
+    mc_rattle_velocity<float>(nat - 1, ci, cj, r, inv_m, v);
+    for (int k = 0; k < nat; ++k) vel[sl[k]] = make_float4(v[k][0], v[k][1], v[k][2], w4[k]);
+}
+
 }  // namespace
 
 #ifdef MC_HAVE_LAUNCH  // the serial stand-in of tests/cpp/shim/ has no launcher
+void launch_rattle_velocities(int n_w, const int4 *waters, int n_c, const int4 *clusters, const int *slot_of_orig, const float4 *xyzq,
+                              float4 *vel, const NbParams &p, cudaStream_t st, int64_t *launches) {
+    if (n_w > 0) {
+        MC_LAUNCH(rattle_waters_kernel, div_up((size_t)n_w, 128), 128, 0, st, n_w, waters, slot_of_orig, xyzq, vel, p);
+        *launches += 1;
+    }
+    if (n_c > 0) {
+        MC_LAUNCH(rattle_h_kernel, div_up((size_t)n_c, 128), 128, 0, st, n_c, clusters, slot_of_orig, xyzq, vel, p);
+        *launches += 1;
+    }
+}
+
 void launch_vsite_construct(int n_v, const int4 *sites, const int *slot_of_orig, float4 *xyzq, float a, float b, const NbParams &p,
                             cudaStream_t st, int64_t *launches) {
     if (n_v <= 0) return;

@@ -16,3 +16,8 @@ void launch_vsite_spread(int n_v, const int4 *sites, const int *slot_of_orig, fl
 // *not_converged (device) counts clusters that needed more than 64 sweeps.
 void launch_shake_h(int n_c, const int4 *clusters, const float *dist, const int *slot_of_orig, float4 *xyzq, float4 *vel,
                     const NbParams &p, float dt, float tol, int *not_converged, double *virial, cudaStream_t st, int64_t *launches);
+
+// Velocity stage of RATTLE after a closing half kick: removes the velocity components along the constrained bonds of the
+// rigid waters and of the hydrogen clusters (either count may be 0).
+void launch_rattle_velocities(int n_w, const int4 *waters, int n_c, const int4 *clusters, const int *slot_of_orig, const float4 *xyzq,
+                              float4 *vel, const NbParams &p, cudaStream_t st, int64_t *launches);

@@ -692,6 +692,68 @@ static void orc_langevin_step(int n, float *vel, float dt) {
     ++g_lgv_step;
 }
 
+/* ---- velocity stage of RATTLE (Andersen 1983) for the clusters above, fp64: after every closing half kick the velocity
+ * components along the constrained bonds are removed by solving the <= 3 x 3 linear system of the cluster (Gaussian
+ * elimination here; molchanica_b200/csrc/rattle_terms.h uses Cramer's rule in fp32). */
+static void orc_rattle_cluster(int nat, const int *id, int nc, const int *ci, const int *cj, const float *xyzq, float *vel,
+                               const float *ext, int periodic) {
+    double r[4][3], rk[3][3], A[3][4], lam[3];
+    for (int k = 0; k < nat; ++k)
+        for (int a = 0; a < 3; ++a) {
+            double d = (double)xyzq[4 * id[k] + a] - (double)xyzq[4 * id[0] + a];
+            if (periodic) d -= rint(d / (double)ext[a]) * (double)ext[a];
+            r[k][a] = d;
+        }
+    for (int k = 0; k < nc; ++k) {
+        A[k][3] = 0;
+        for (int a = 0; a < 3; ++a) {
+            rk[k][a] = r[ci[k]][a] - r[cj[k]][a];
+            A[k][3] += rk[k][a] * ((double)vel[4 * id[ci[k]] + a] - (double)vel[4 * id[cj[k]] + a]);
+        }
+    }
+    for (int k = 0; k < nc; ++k)
+        for (int l = 0; l < nc; ++l) {
+            double si = (ci[k] == ci[l]) - (ci[k] == cj[l]), sj = (cj[k] == ci[l]) - (cj[k] == cj[l]);
+            A[k][l] = (si * (double)vel[4 * id[ci[k]] + 3] - sj * (double)vel[4 * id[cj[k]] + 3]) *
+                      (rk[l][0] * rk[k][0] + rk[l][1] * rk[k][1] + rk[l][2] * rk[k][2]);
+        }
+    for (int p = 0; p < nc; ++p) {  /* elimination with partial pivoting */
+        int best = p;
+        for (int q = p + 1; q < nc; ++q) if (fabs(A[q][p]) > fabs(A[best][p])) best = q;
+        for (int c = 0; c < 4; ++c) { double t = A[p][c]; A[p][c] = A[best][c]; A[best][c] = t; }
+        for (int q = p + 1; q < nc; ++q) {
+            double f = A[q][p] / A[p][p];
+            for (int c = p; c < 4; ++c) A[q][c] -= f * A[p][c];
+        }
+    }
+    for (int p = nc - 1; p >= 0; --p) {
+        double t = A[p][3];
+        for (int c = p + 1; c < nc; ++c) t -= A[p][c] * lam[c];
+        lam[p] = t / A[p][p];
+    }
+    for (int l = 0; l < nc; ++l)
+        for (int a = 0; a < 3; ++a) {
+            vel[4 * id[ci[l]] + a] = (float)((double)vel[4 * id[ci[l]] + a] - (double)vel[4 * id[ci[l]] + 3] * lam[l] * rk[l][a]);
+            vel[4 * id[cj[l]] + a] = (float)((double)vel[4 * id[cj[l]] + a] + (double)vel[4 * id[cj[l]] + 3] * lam[l] * rk[l][a]);
+        }
+}
+
+static const int32_t *g_hclusters_fwd(void);
+static int g_nhc_fwd(void);
+void orc_rattle_velocities(const float *xyzq, float *vel, const float *ext, int periodic) {
+    const int wi[3] = {0, 0, 1}, wj[3] = {1, 2, 2}, hi[3] = {0, 0, 0}, hj[3] = {1, 2, 3};
+    for (int w = 0; w < g_nw; ++w) {
+        const int id[4] = {g_waters[3 * w], g_waters[3 * w + 1], g_waters[3 * w + 2], 0};
+        orc_rattle_cluster(3, id, 3, wi, wj, xyzq, vel, ext, periodic);
+    }
+    const int32_t *hc = g_hclusters_fwd();
+    for (int c = 0; c < g_nhc_fwd(); ++c) {
+        int id[4], nat = 0;
+        for (int k = 0; k < 4; ++k) if (hc[4 * c + k] >= 0) id[nat++] = hc[4 * c + k];
+        if (nat >= 2) orc_rattle_cluster(nat, id, nat - 1, hi, hj, xyzq, vel, ext, periodic);
+    }
+}
+
 /* ---- SHAKE for bonds to hydrogen, fp64 ------------------------------------------------------
  * Clusters (heavy, h1, h2, h3; -1 = unused) with one length per hydrogen; the reference constrains bonds to hydrogen
  * at 2 fs (ui/panels/md.rs:362-371; code in the un-vendored `dynamics` crate -> parity unpinned).  Same equations as
@@ -701,6 +763,8 @@ static int g_nhc = 0;
 static const int32_t *g_hclusters = NULL;
 static const float *g_hdist = NULL;
 void orc_set_hbond_constraints(int n, const int32_t *clusters, const float *lengths) { g_nhc = n; g_hclusters = clusters; g_hdist = lengths; }
+static const int32_t *g_hclusters_fwd(void) { return g_hclusters; }
+static int g_nhc_fwd(void) { return g_nhc; }
 
 void orc_shake_h(const float *xold, float *xnew, float *vel, const float *ext, int periodic, float dt) {
     for (int c = 0; c < g_nhc; ++c) {
@@ -894,7 +958,10 @@ int orc_md_run(int n, float *xyzq, float *vel, const uint16_t *type, int T, cons
         if (ext_force)
             for (int i = 0; i < n; ++i)
                 for (int a = 0; a < 3; ++a) f[4 * i + a] += ext_force[3 * i + a];
-        if (step > 0) orc_kick(n, vel, f, 0.5f * dt);
+        if (step > 0) {
+            orc_kick(n, vel, f, 0.5f * dt);
+            if (g_nw || g_nhc) orc_rattle_velocities(xyzq, vel, ext, periodic);  /* on-step velocities of the constrained system */
+        }
         if (energies_out) {
             energies_out[4 * step] = en[0]; energies_out[4 * step + 1] = en[1];
             energies_out[4 * step + 2] = en[2]; energies_out[4 * step + 3] = orc_kinetic(n, vel);

@@ -28,6 +28,16 @@ def main():
     n_steps = 60
     e.step(w["dt"], n_steps)
     x = e.positions()
+    # velocity stage of RATTLE (known answer): after mc_step every constrained distance is stationary, d/dt |r_ij| = 0
+    vv = e.velocities()[:, :3].astype(np.float64).reshape(-1, 3, 3)
+    xx = x[:, :3].astype(np.float64).reshape(-1, 3, 3)
+
+    def rdot(i, j):
+        r = xx[:, i] - xx[:, j]
+        r -= np.rint(r / ext) * ext
+        return np.abs((r * (vv[:, i] - vv[:, j])).sum(1)) / np.linalg.norm(r, axis=1)
+    bond_speed = float(max(rdot(0, 1).max(), rdot(0, 2).max(), rdot(1, 2).max()))   # A/ps along constrained bonds
+    v_typ = float(np.sqrt((vv ** 2).sum(-1)).mean())
     ref = O.md_run(w, n_steps, precision=64, rigid_waters=(triples, D_OH, D_HH))
     ok, worst, sc = trajectory_close(x, ref["xyzq"], w["xyzq"], w["box_ext"])
     m = x[:, :3].astype(np.float64).reshape(-1, 3, 3)
@@ -42,7 +52,8 @@ def main():
     t_ref = 2 * ke_ref / ((3 * n - 3 * len(triples)) * 0.0019872041)
     e.compute_forces()
     res = dict(traj_ok=bool(ok), traj_worst=float(worst), geom_err=float(np.abs(geom - [D_OH, D_OH, D_HH]).max()),
-               temperature=float(e.energy()["temperature"]), temperature_ref=float(t_ref))
+               temperature=float(e.energy()["temperature"]), temperature_ref=float(t_ref),
+               bond_speed_over_typical=bond_speed / v_typ)
     e.close()
     # four-site OPC water: SETTLE on (O, H, H) + virtual site M, against the oracle doing the same in fp64
     w4 = W.water_box_opc()  # 216 molecules, L = 18.64: r_c + skin = 9.3 < L / 2
@@ -72,17 +83,22 @@ def main():
     e.set_hbond_constraints(clusters, lengths)
     e.step(wc["dt"], 40)
     xc = e.positions()
+    vc = e.velocities()[:, :3].astype(np.float64).reshape(-1, 3, 3)
     e.close()
     refc = O.md_run(wc, 40, precision=64, with_bonds=True, hbond_constraints=(clusters, lengths))
     okc, worstc, _ = trajectory_close(xc, refc["xyzq"], wc["xyzq"], wc["box_ext"])
     mc = xc[:, :3].astype(np.float64).reshape(-1, 3, 3)
     extc = np.asarray(wc["box_ext"], np.float64)
     dc = lambda a, b: np.linalg.norm((a - b) - np.rint((a - b) / extc) * extc, axis=1)
+    rc_ = lambda i, j: (mc[:, i] - mc[:, j]) - np.rint((mc[:, i] - mc[:, j]) / extc) * extc
+    shake_bond_speed = max(float(np.abs((rc_(0, k) * (vc[:, 0] - vc[:, k])).sum(1) / np.linalg.norm(rc_(0, k), axis=1)).max()) for k in (1, 2))
+    res.update(shake_bond_speed_over_typical=shake_bond_speed / float(np.sqrt((vc ** 2).sum(-1)).mean()))
     res.update(shake_traj_ok=bool(okc), shake_traj_worst=float(worstc),
                shake_len_err=float(max(np.abs(dc(mc[:, 0], mc[:, 1]) - D_OH).max(), np.abs(dc(mc[:, 0], mc[:, 2]) - D_OH).max())))
     res.update(opc_traj_ok=bool(ok4), opc_traj_worst=float(worst4), opc_msite_err=float(msite),
                opc_m_force=float(np.abs(f4[3::4, :3]).max()))
-    good = (res["traj_ok"] and res["geom_err"] < 2e-5 and abs(res["temperature"] - res["temperature_ref"]) < 0.03 * res["temperature_ref"] and res["opc_traj_ok"] and
+    good = (res["traj_ok"] and res["geom_err"] < 2e-5 and abs(res["temperature"] - res["temperature_ref"]) < 0.01 * res["temperature_ref"] and res["opc_traj_ok"] and
+            res["bond_speed_over_typical"] < 2e-5 and res["shake_bond_speed_over_typical"] < 2e-5 and
             res["opc_msite_err"] < 5e-6 and res["opc_m_force"] == 0.0 and res["shake_traj_ok"] and res["shake_len_err"] < 2e-5)
     print(json.dumps(res))
     return 0 if good else 1
