@@ -35,19 +35,23 @@ def ns_per_day(steps, seconds, dt_ps=DT_PS):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (B200_PROFILING.md).  The sampler process is
+    started well before the first timed window (its start-up -- fork, exec, NVML initialisation -- would otherwise steal
+    the launching thread's time inside a 20-step window of a few milliseconds) and its rows carry timestamps; only the
+    rows that fall between mark_begin() and mark_end() are reported."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
@@ -55,7 +59,13 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.rows.append([x.strip() for x in ln.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in ln.split(",")]))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
@@ -66,26 +76,24 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         note = None
-        if not self.rows:
-            # the sampler produced nothing (interval refused, process too slow to start): one query right after the region
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=20).stdout
-                self.rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
-                note = "sampler returned nothing; single query right after the timed region"
-            except Exception:
-                pass
+        lo, hi = self.t_begin or 0.0, (self.t_end or time.time()) + 0.03
+        rows = [r for (t, r) in self.rows if lo <= t <= hi]
+        if not rows and self.rows:
+            # the timed regions were shorter than one sampling interval: the nearest rows around them
+            rows = [r for (t, r) in sorted(self.rows, key=lambda tr: min(abs(tr[0] - lo), abs(tr[0] - hi)))[:3]]
+            note = "timed regions shorter than the sampling interval; nearest samples reported"
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             try:
-                sm.append(float(r[1]))
-                mx = float(r[2])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                sm.append(float(r[2]))
+                mx = float(r[3])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
-        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+               "window": "value + steady-state + end-to-end legs"}
         if note:
             out["note"] = note
         return out
@@ -308,6 +316,9 @@ def main():
     # list rebuilds behind it (the first one is the initial all-gather build of a decomposed run, the second the first
     # neighbour-only migration, whose NCCL channels are set up on first use; the adaptive interval of a decomposed run
     # needs two builds to climb from its cautious start).  One step per call, so that the spacing of the rebuilds is seen.
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     e.step(DT_PS, W_)
     warm_total = W_
     rebuild_at = []
@@ -343,10 +354,8 @@ def main():
     e.set_option("profile_every", args.profile_every)  # CUDA-event pairs around every k-th step's kernels only
     e.reset_timers()
     s0 = e.stats()
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     e.step(DT_PS, K)
     barrier()
@@ -369,7 +378,6 @@ def main():
                   "rebuild_interval_steps": ks / max(int(s2["n_rebuilds"] - s1["n_rebuilds"]), 1)}
     else:
         s2 = s1
-    clocks = sampler.stop() if rank == 0 else None
     e.set_option("profiling", 0)
 
     # ---- e2e: host buffers through the C ABI, one call per step, H2D + D2H inside the timing ----
@@ -435,6 +443,9 @@ def main():
         e.set_option("defer_tail", 0 if any(o.startswith("defer_tail=0") for o in args.opt) else 1)
         e2e = run_leg()
         e2e["api"] += "; option defer_tail = " + ("0" if any(o.startswith("defer_tail=0") for o in args.opt) else "1 (pipelined upload)")
+
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel (pair force), live CUDA-event average over the timed regions
     pair_ms = s2["pair_ms_sum"] / max(s2["pair_launches_timed"], 1)

@@ -10,81 +10,18 @@
 // HBM-bound and tiny next to the pair kernel: 3 x 16 B gathered + 3 x 12 B of atomics per bond.
 // STATUS: written after round 1's GPU budget was spent -- compiled for sm_100a, arithmetic verified on the host,
 // kernel plumbing not yet run on hardware (tests/test_gpu_bonded.py is marked accordingly).
-#include "bonded.cuh"
-#include "bonded_terms.h"
+#include "bonded_device.cuh"
 
 namespace {
-
-__device__ __forceinline__ void min_image3(float d[3], const NbParams &p) {
-    if (p.periodic) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) d[a] -= rintf(d[a] * p.inv_ext[a]) * p.ext[a];
-    }
-}
-
-__device__ __forceinline__ void add_force(float4 *force, int slot, const float f[3]) {
-    atomicAdd(&force[slot].x, f[0]);
-    atomicAdd(&force[slot].y, f[1]);
-    atomicAdd(&force[slot].z, f[2]);
-}
 
 __global__ void __launch_bounds__(128) bonded_kernel(BondedTerms t, const int *__restrict__ slot_of_orig,
                                                       const float4 *__restrict__ xyzq, const NbParams p,
                                                       float4 *__restrict__ force, double *__restrict__ energy3,
                                                       int want_energy) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    float e = 0.f, w = 0.f;  // energy and sum_a (r_a - r_ref) . f_a of this thread's term (its share of the virial)
-    int kind = -1;
-    if (tid < t.n_bonds) {
-        kind = 0;
-        const int2 ij = t.bonds[tid];
-        const float2 kr = t.bond_kr0[tid];
-        const int si = slot_of_orig[ij.x], sj = slot_of_orig[ij.y];
-        const float4 xi = xyzq[si], xj = xyzq[sj];
-        float d[3] = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z}, fi[3];
-        min_image3(d, p);
-        e = mc_bond_term(d, kr.x, kr.y, fi);
-        w = d[0] * fi[0] + d[1] * fi[1] + d[2] * fi[2];
-        const float fj[3] = {-fi[0], -fi[1], -fi[2]};
-        add_force(force, si, fi);
-        add_force(force, sj, fj);
-    } else if (tid < t.n_bonds + t.n_angles) {
-        kind = 1;
-        const int a_ = tid - t.n_bonds;
-        const int4 ijk = t.angles[a_];
-        const float2 kt = t.angle_kt0[a_];
-        const int si = slot_of_orig[ijk.x], sj = slot_of_orig[ijk.y], sk = slot_of_orig[ijk.z];
-        const float4 xi = xyzq[si], xj = xyzq[sj], xk = xyzq[sk];
-        float a[3] = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z}, b[3] = {xk.x - xj.x, xk.y - xj.y, xk.z - xj.z}, fi[3], fk[3];
-        min_image3(a, p);
-        min_image3(b, p);
-        e = mc_angle_term(a, b, kt.x, kt.y, fi, fk);
-        w = a[0] * fi[0] + a[1] * fi[1] + a[2] * fi[2] + b[0] * fk[0] + b[1] * fk[1] + b[2] * fk[2];  // zero up to rounding
-        const float fj[3] = {-(fi[0] + fk[0]), -(fi[1] + fk[1]), -(fi[2] + fk[2])};
-        add_force(force, si, fi);
-        add_force(force, sj, fj);
-        add_force(force, sk, fk);
-    } else if (tid < t.n_bonds + t.n_angles + t.n_dihedrals) {
-        kind = 2;
-        const int d_ = tid - t.n_bonds - t.n_angles;
-        const int4 q = t.dihedrals[d_];
-        const float4 prm = t.dihedral_prm[d_];  // pk, periodicity, phase
-        const int si = slot_of_orig[q.x], sj = slot_of_orig[q.y], sk = slot_of_orig[q.z], sl = slot_of_orig[q.w];
-        const float4 xi = xyzq[si], xj = xyzq[sj], xk = xyzq[sk], xl = xyzq[sl];
-        float rij[3] = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z}, rkj[3] = {xk.x - xj.x, xk.y - xj.y, xk.z - xj.z},
-              rkl[3] = {xk.x - xl.x, xk.y - xl.y, xk.z - xl.z}, fi[3], fj[3], fk[3], fl[3];
-        min_image3(rij, p);
-        min_image3(rkj, p);
-        min_image3(rkl, p);
-        e = mc_dihedral_term(rij, rkj, rkl, prm.x, prm.y, prm.z, fi, fj, fk, fl);
-        // relative to atom j: r_i - r_j = rij, r_k - r_j = rkj, r_l - r_j = rkj - rkl (zero up to rounding as well)
-        w = rij[0] * fi[0] + rij[1] * fi[1] + rij[2] * fi[2] + rkj[0] * fk[0] + rkj[1] * fk[1] + rkj[2] * fk[2] +
-            (rkj[0] - rkl[0]) * fl[0] + (rkj[1] - rkl[1]) * fl[1] + (rkj[2] - rkl[2]) * fl[2];
-        add_force(force, si, fi);
-        add_force(force, sj, fj);
-        add_force(force, sk, fk);
-        add_force(force, sl, fl);
-    }
+    float e, w;  // energy and sum_a (r_a - r_ref) . f_a of this thread's term (its share of the virial)
+    int kind;
+    bonded_term_apply(tid, t, slot_of_orig, xyzq, p, force, e, w, kind);
     if (want_energy) {
         // per-kind energy sums: warp-reduce, one fp64 atomic per warp and kind present in it
 #pragma unroll

@@ -21,6 +21,7 @@
 #include "csvr_terms.h"
 #include "dock.cuh"
 #include "engine.cuh"
+#include "md_fused.cuh"
 #include "integrate.cuh"
 #include "neighbor.cuh"
 #include "pair_force.cuh"
@@ -105,7 +106,7 @@ extern "C" int mc_create(int device, mc_ctx **out) {
     c->l2_bytes = (size_t)prop.l2CacheSize;
     if ((e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = pair_force_prepare()) != cudaSuccess || (e = dock_prepare()) != cudaSuccess ||
-        (e = tile_sweep_prepare()) != cudaSuccess || (e = pair_tile_prepare()) != cudaSuccess ||
+        (e = tile_sweep_prepare()) != cudaSuccess || (e = pair_tile_prepare()) != cudaSuccess || (e = md_fused_prepare()) != cudaSuccess ||
         (e = cudaMallocHost(&c->h_pinned, 256)) != cudaSuccess) {
         g_create_err = std::string("mc_create: ") + cudaGetErrorString(e);
         delete c;
@@ -552,6 +553,8 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         c->com_every = (int)value;
     } else if (k == "defer_tail") {
         c->defer_tail = value != 0.0;
+    } else if (k == "fused_steps") {
+        c->fused_steps = value != 0.0;
     } else {
         return fail(c, MC_E_INVALID, "mc_set_option: unknown option '" + k + "'");
     }
@@ -1006,6 +1009,66 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     }
     if (wait_upload) MC_CUDA(c, cudaStreamWaitEvent(st, c->ev_up, 0));
     if (gather_chunk && (rc = comm_allgather_f32_inplace(c, const_cast<float *>(d_ext), gather_chunk)) != MC_OK) return rc;
+    // Small plain-NVE systems: all n_steps in ONE cooperative launch (md_fused.cu) instead of 2-4 launches + a host poll per
+    // step.  The launch stops after the drift of a step that trips the displacement criterion; list rebuild and force
+    // evaluation happen here, then the remaining steps go out in the next launch.
+    const bool fused = c->fused_steps && !c->comm_active && c->rebuild_every <= 0 && !c->sync_rebuild && !constrained && !baro && !defer &&
+                       !c->langevin && !c->csvr && !c->pme.planned && c->n_vsites == 0 && c->com_every == 0 && n_steps > 0 &&
+                       c->n_global <= md_fused_max_atoms() && !c->profiling && !c->list_compact;
+    if (fused) {
+        int *h_out = reinterpret_cast<int *>(c->h_pinned) + 16;
+        if (!c->ev_step_a) {
+            MC_CUDA(c, cudaEventCreate(&c->ev_step_a)); MC_CUDA(c, cudaEventCreate(&c->ev_step_b));
+            MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_flag[0], cudaEventDisableTiming));
+            MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_flag[1], cudaEventDisableTiming));
+        }
+        MC_CUDA(c, cudaEventRecord(c->ev_step_a, st));
+        int remaining = n_steps;
+        bool first_half = true;
+        while (remaining > 0) {
+            if (c->list_compact) break;  // (never: compact rows are only built for large systems)
+            FusedArgs A;
+            A.n = (int)c->n;
+            A.xyzq = c->xyzq[c->cur].p; A.vel = c->vel[c->cur].p; A.force = c->force.p; A.xref = c->xref.p;
+            A.type = c->type[c->cur].p; A.flags = c->flags[c->cur].p; A.orig = c->orig[c->cur].p; A.slot_of_orig = c->slot_of_orig.p;
+            A.nbr_start = c->nbr_start.p; A.nbr_count = c->nbr_count.p; A.nbr_list = c->nbr_list.p;
+            A.ljtab = c->ljtab.p; A.p = make_params(c); A.lj_on = c->lj_disabled ? 0 : 1;
+            A.p14_start = c->have_p14 ? c->p14_start.p : nullptr; A.p14_idx = c->have_p14 ? c->p14_idx.p : nullptr;
+            A.s14_lj = c->scale14_lj; A.s14_q = c->scale14_q;
+            A.bt.n_bonds = c->n_bonds; A.bt.n_angles = c->n_angles; A.bt.n_dihedrals = c->n_dihedrals;
+            A.bt.bonds = c->bonds.p; A.bt.bond_kr0 = c->bond_kr0.p; A.bt.angles = c->angles.p; A.bt.angle_kt0 = c->angle_kt0.p;
+            A.bt.dihedrals = c->dihedrals.p; A.bt.dihedral_prm = c->dihedral_prm.p;
+            A.ext_force = d_ext; A.dt = dt; A.max_disp = 0.5f * c->skin; A.n_steps = remaining; A.first_half = first_half ? 1 : 0;
+            A.rebuild_flag = c->rebuild_flag.p; A.out = h_out;
+            const int coul = c->coul_disabled ? MC_COULOMB_NONE : c->coul_mode;
+            h_out[0] = -1; h_out[1] = 0;
+            MC_CUDA(c, launch_md_fused(A, c->n_types > 1, coul, c->periodic, c->n_sms, st, &c->launches));
+            MC_CUDA(c, cudaStreamSynchronize(st));
+            const int done = h_out[0], fl = h_out[1];
+            if (done < 0) return fail(c, MC_E_CUDA, "mc_step: the fused step kernel did not report back");
+            if (fl & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
+            c->n_steps += done;
+            c->steps_since_build += done;
+            remaining -= done;
+            if (!(fl & 1)) break;  // all steps taken, closing half kick applied in the kernel; forces belong to the positions
+            // the last drift tripped the displacement criterion: its forces are still those of the previous positions
+            c->forces_valid = false;
+            if ((rc = engine_build_list(c)) != MC_OK) return rc;
+            if ((rc = engine_launch_forces(c, false)) != MC_OK) return rc;
+            first_half = false;
+            if (remaining == 0) {
+                launch_kick_drift((int)c->n, c->xyzq[c->cur].p, c->vel[c->cur].p, c->force.p, d_ext, c->orig[c->cur].p, c->flags[c->cur].p,
+                                  c->xref.p, 0.5f * dt, 0.f, 0.f, 0.f, c->rebuild_flag.p, st, &c->launches);
+            }
+        }
+        c->forces_have_energy = false;
+        MC_CUDA(c, cudaEventRecord(c->ev_step_b, st));
+        MC_CUDA(c, cudaStreamSynchronize(st));
+        float ms_f = 0.f;
+        MC_CUDA(c, cudaEventElapsedTime(&ms_f, c->ev_step_a, c->ev_step_b));
+        c->last_step_ms = ms_f;
+        return MC_OK;
+    }
     // Velocity Verlet, two kernels per step: [kick + drift] and [pair forces].  The second half
     // kick of step s and the first half kick of step s+1 are one full kick in the same launch.
     // The rebuild decision is pipelined: kick_drift raises the flag with a look-ahead margin, the

@@ -164,6 +164,7 @@ struct mc_ctx {
 
     // pipelined external forces (engine.cu, mc_step): the caller's array is uploaded on a stream of its own while the
     // force evaluation the previous call left open runs; that call's second half kick is applied once both are there
+    bool fused_steps = true;     // option "fused_steps": small plain-NVE systems take all steps of a call in one cooperative launch (md_fused.cu)
     bool defer_tail = false;     // option "defer_tail" (off until the path has been confirmed on hardware; bench.py's e2e leg turns it on)
     bool tail_pending = false;   // positions are one step ahead of forces / velocities (half kick outstanding)
     float tail_dt = 0.f;

@@ -19,7 +19,7 @@ fi
 CXX=/usr/bin/g++; [ -x "$CXX" ] || CXX=g++
 mkdir -p "$OBJ"
 FLAGS="-O1 -g -std=c++20 -pthread -fPIC -ffp-contract=off -Wno-unknown-pragmas -Wno-attributes -DMC_HOST_SHIM=1 -I$ROOT/tests/cpp/shim_fiber $SAN"
-SRCS="sort_scan neighbor tile_build pair_force pair_tile integrate thermostat dock dock_filter dock_poses bonded settle pme pme_params group_energy engine comm"
+SRCS="sort_scan neighbor tile_build pair_force pair_tile md_fused integrate thermostat dock dock_filter dock_poses bonded settle pme pme_params group_energy engine comm"
 pids=()
 for s in $SRCS; do
   src="$ROOT/molchanica_b200/csrc/$s.cu"
