@@ -553,6 +553,10 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         c->com_every = (int)value;
     } else if (k == "defer_tail") {
         c->defer_tail = value != 0.0;
+    } else if (k == "build_variant") {
+        MC_REQUIRE(c, value == 1.0 || value == 2.0, "mc_set_option: build_variant is 1 (tile_build_kernel) or 2 (rows_build_kernel)");
+        c->build_variant = (int)value;
+        c->list_valid = false;
     } else if (k == "fused_steps") {
         c->fused_steps = value != 0.0;
     } else {
@@ -671,7 +675,8 @@ int engine_build_rows(mc_ctx *c) {
         launch_tile_build(n_rows, grid_cells, split, c->n_sms, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, rc2_inner,
                           c->orig[c->cur].p, es, ei, c->nbr_count.p, c->nbr_start.p,
                           compact ? static_cast<void *>(c->nbr_list16.p) : static_cast<void *>(c->nbr_list.p), compact, c->pair_uniform,
-                          (uint32_t)std::min<size_t>(cap_now, 0xffffffffu), c->tile_cap, c->tile_need.p, st, &c->launches);
+                          (uint32_t)std::min<size_t>(cap_now, 0xffffffffu), c->tile_cap, c->tile_need.p, st, &c->launches,
+                          c->build_variant, c->row_len_hint);
         MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->tile_need.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         MC_CUDA(c, cudaStreamSynchronize(st));
         if (h_ctl[3] != 0) {  // a neighbourhood did not fit the tile
@@ -690,6 +695,7 @@ int engine_build_rows(mc_ctx *c) {
         }
         c->tile_max_m = (h_ctl[2] + 31u) & ~31u;
         c->rows_max_entries = h_ctl[4];
+        if (h_ctl[6]) c->row_len_hint = h_ctl[6];  // longest row: sizes the row staging of the next build (rows_build_kernel)
         // the TMA-staged force kernel wants every cell's rows as one block of <= 32 rows next to the tile in shared memory:
         // a system that is too dense for that (seen only now) is built again with global-slot rows, and stays that way
         if (compact && (h_ctl[5] > 32u || pair_tile_smem(c->tile_max_m, c->rows_max_entries, c->n_types, c->n_types > 1, nullptr, nullptr) == 0)) {

@@ -86,6 +86,8 @@ struct mc_ctx {
     bool subcell_sort = false;  // Morton sub-cell code in the low sort-key bits (option "subcell_sort")
     bool use_tile = true;      // TMA-staged tile sweep for the list build (neighbor_tile.cu)
     uint32_t tile_cap = 1024;  // tile capacity in atoms, grows on demand
+    int build_variant = 2;     // option "build_variant": 2 = rows_build_kernel (default), 1 = tile_build_kernel (tile_build.cu)
+    uint32_t row_len_hint = 0; // longest row of the last build (0: none yet)
     int use_pair_tile = 0;     // option "pair_tile": compact rows (16-bit tile-local indices) + TMA-staged force kernel (pair_tile.cu):
                                // 0 (default) off, 1 on, 2 on for systems of >= 16384 atoms.  Measured on C4 (profiles/pair_tile_r2_*):
                                // 0.199 ms against 0.178 ms of the gather kernel -- staging a 27-cell tile per ~19-atom cell is

@@ -97,9 +97,13 @@ __global__ void __launch_bounds__(FUSED_THREADS) md_fused_kernel(const FusedArgs
         flag = *reinterpret_cast<volatile int *>(A.rebuild_flag);
         if (flag & 3) break;  // grid-uniform: this step ends after its drift; the host rebuilds / reports
         // ---- pair forces over the Verlet rows (pair_force.cu's layout), the row's 1-4 partners added by its first lane
-        for (int r = tid / FUSED_LANES; r < A.n; r += n_threads / FUSED_LANES) {
+        // (whole warps enter every iteration -- the reduction below shuffles with the full mask; rows past the end are dead lanes)
+        for (int rb = (tid / 32) * (32 / FUSED_LANES); rb < A.n; rb += n_threads / FUSED_LANES) {
+            const int r_raw = rb + (threadIdx.x & 31) / FUSED_LANES;
+            const bool live = r_raw < A.n;
+            const int r = live ? r_raw : A.n - 1;
             const float4 xi = A.xyzq[r];
-            const uint32_t start = __ldg(A.nbr_start + r), cnt = __ldg(A.nbr_count + r);
+            const uint32_t start = __ldg(A.nbr_start + r), cnt = live ? __ldg(A.nbr_count + r) : 0u;
             const int ti = MULTI ? (int)__ldg(A.type + r) : 0;
             const float2 *row = MULTI ? s_tab + ti * A.p.n_types : nullptr;
             const bool wrap = PBC && !(__ldg(A.flags + r) & MC_FLAG_INTERIOR);
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) md_fused_kernel(const FusedArgs
                 a.fy += __shfl_xor_sync(MC_FULL_MASK, a.fy, d);
                 a.fz += __shfl_xor_sync(MC_FULL_MASK, a.fz, d);
             }
-            if (sub == 0) {
+            if (live && sub == 0) {
                 if (A.p14_start) {  // Amber 1-4 rows (pairs14_kernel of pair_force.cu): no cutoff, scaled LJ / Coulomb
                     const int oi = A.orig[r];
                     for (int e = A.p14_start[oi]; e < A.p14_start[oi + 1]; ++e) {

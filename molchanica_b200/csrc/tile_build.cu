@@ -455,6 +455,281 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) til
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// rows_build_kernel -- the default build (global-slot rows, no inner / skin partition).  Same producer, same tile, same
+// accept expression; the consumer side is organised around what the first kernel's profile showed (round 2, ncu: only a
+// third of its 725 M warp instructions were distance tests -- 23 % were per-lane find-first-set write loops running at
+// 5 of 32 lanes, 40 % of its atom slots were parked because the eight warps of a CTA went through a cell in lock-step):
+//   * lanes own CONSECUTIVE candidates (t = 32 b + lane): a block of 32 tile entries is one conflict-free LDS.128 per
+//     lane, the warp-wide accept decision of an atom is one ballot, and tile order is ballot order -- a hit's place in its
+//     row is count_so_far + popc(ballot & lanes_below), no per-lane loop, no prefix scan, no bit reversal;
+//   * a warp sweeps the tile ONCE for a quad of four consecutive atoms of the cell, staging the rows as 16-bit tile
+//     indices in shared memory; when the sweep ends the row lengths are known, the quad's rows are claimed with one
+//     atomicAdd on the list cursor and copied out with coalesced 128-byte stores (slot ids looked up on the way).  A row
+//     longer than the staging space is written by a second sweep straight to its place (dense systems: every row);
+//   * the consumer warps are decoupled: quads are dealt round-robin ACROSS items (the deal continues where the previous
+//     cell stopped), a warp that has no quad in this tile moves on to the next stage of the ring, so nobody is parked and
+//     nobody waits at a CTA barrier; packing pairs the x / y components of ONE atom (FADD2 / FMUL2 on the register pair the
+//     LDS.128 delivers), so any number of atoms per quad is as cheap per atom and nothing is duplicated into pairs.
+// Row content and order are those of tile_build_kernel (ascending tile index); row placement follows completion order.
+constexpr int RB_A = 4;           // atoms per quad
+constexpr int RB_MAX_STAGES = 4;  // tiles in flight per CTA
+
+__device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
+
+// accept decision of one atom (negated position npi = -x_i) against the candidate pj: the oracle's
+// ((dx*dx)+(dy*dy))+(dz*dz) < rl2 on d = x_j - x_i = -(x_i - x_j) (exactly the negative in fp32, and every step below is
+// odd or even in d: the decision is the oracle's bit for bit).  NaN (tile padding, parked atoms) is never accepted.
+template <int WRAP>
+__device__ __forceinline__ bool rb_accept(const float4 pj, const float2 npi_xy, const float npi_z, const GridParams &g, float rl2) {
+    float2 dxy = mc_add2(make_float2(pj.x, pj.y), npi_xy);
+    float dz = __fadd_rn(pj.z, npi_z);
+    if (WRAP == 2) {
+        dxy.x = min_image_exact(dxy.x, g.ext[0], g.inv_ext[0]);
+        dxy.y = min_image_exact(dxy.y, g.ext[1], g.inv_ext[1]);
+        dz = min_image_exact(dz, g.ext[2], g.inv_ext[2]);
+    } else if (WRAP == 1) {  // see sweep_chunk: >= 3 cells per axis, the fast image is the exact one wherever it matters
+        const float2 q = mc_mul2(dxy, make_float2(g.inv_ext[0], g.inv_ext[1]));
+        dxy = mc_fma2(make_float2(-rintf(q.x), -rintf(q.y)), make_float2(g.ext[0], g.ext[1]), dxy);
+        dz = __fmaf_rn(-rintf(__fmul_rn(dz, g.inv_ext[2])), g.ext[2], dz);
+    }
+    const float2 s = mc_mul2(dxy, dxy);
+    const float r2 = __fadd_rn(__fadd_rn(s.x, s.y), __fmul_rn(dz, dz));
+    return r2 < rl2;
+}
+
+struct RbQuad {
+    float2 npxy[RB_A];
+    float npz[RB_A];
+    uint32_t t_self[RB_A];
+    int ex_lo[RB_A], ex_hi[RB_A];
+};
+
+// One pass of a quad over the tile.  MODE 0: stage the rows (16-bit tile indices, the first `stage_cap` entries of each)
+// and count; MODE 1: write the rows flagged in `direct` straight to nbr_list at row[k] (second pass of rows that did not
+// fit the staging space).  cnt[k] = row lengths (warp-uniform).
+template <int WRAP, int MODE>
+__device__ __forceinline__ void rb_sweep(const float4 *tile, const uint32_t *tile_slot, uint32_t m_pad, const GridParams &g, float rl2,
+                                         const RbQuad &Q, bool any_excl, const int *__restrict__ orig, const int32_t *__restrict__ excl_idx,
+                                         uint16_t *stage, uint32_t stage_cap, const uint32_t (&row)[RB_A], uint32_t direct,
+                                         uint32_t *__restrict__ nbr_list, int lane, uint32_t (&cnt)[RB_A]) {
+#pragma unroll
+    for (int k = 0; k < RB_A; ++k) cnt[k] = 0u;
+    const uint32_t lt = lanemask_lt(lane);
+    for (uint32_t t = (uint32_t)lane; t < m_pad; t += 32u) {
+        const float4 pj = tile[t];
+        bool hit[RB_A];
+#pragma unroll
+        for (int k = 0; k < RB_A; ++k) hit[k] = rb_accept<WRAP>(pj, Q.npxy[k], Q.npz[k], g, rl2) && t != Q.t_self[k];
+        if (any_excl) {  // 1-2 / 1-3 / 1-4 partners (original ids) never enter the list; rare: only hits of atoms that carry exclusions pay
+#pragma unroll
+            for (int k = 0; k < RB_A; ++k) {
+                if (hit[k] && Q.ex_hi[k] > Q.ex_lo[k]) {
+                    const int oj = orig[tile_slot[t]];
+                    for (int e = Q.ex_lo[k]; e < Q.ex_hi[k]; ++e)
+                        if (excl_idx[e] == oj) { hit[k] = false; break; }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RB_A; ++k) {
+            const uint32_t mask = __ballot_sync(MC_FULL_MASK, hit[k]);
+            const uint32_t pos = cnt[k] + (uint32_t)__popc(mask & lt);
+            if (MODE == 0) {
+                if (hit[k] && pos < stage_cap) stage[(uint32_t)k * stage_cap + pos] = (uint16_t)t;
+            } else {
+                if (hit[k] && ((direct >> k) & 1u)) nbr_list[row[k] + pos] = tile_slot[t];
+            }
+            cnt[k] += (uint32_t)__popc(mask);
+        }
+    }
+}
+
+template <int WRAP>
+__device__ __forceinline__ void rb_quad(const float4 *tile, const uint32_t *tile_slot, const StageMeta &M, uint32_t m_pad, uint32_t i0,
+                                        int n_rows, const GridParams &g, float rl2, const int *__restrict__ orig,
+                                        const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx, uint16_t *stage,
+                                        uint32_t stage_cap, uint32_t *__restrict__ nbr_count, uint32_t *__restrict__ nbr_start,
+                                        uint32_t *__restrict__ nbr_list, uint32_t list_cap, uint32_t *__restrict__ ctl, int lane) {
+    const float qnan = __int_as_float(0x7fffffff);
+    RbQuad Q;
+    uint32_t valid = 0u;
+    bool any_excl = false;
+#pragma unroll
+    for (int k = 0; k < RB_A; ++k) {
+        const uint32_t i = i0 + (uint32_t)k;
+        Q.npxy[k] = make_float2(qnan, qnan);
+        Q.npz[k] = qnan;
+        Q.t_self[k] = 0xffffffffu;
+        Q.ex_lo[k] = Q.ex_hi[k] = 0;
+        if (i < M.a1 && (int)i < n_rows) {
+            valid |= 1u << k;
+            Q.t_self[k] = M.self_off + (i - M.a0);
+            const float4 p = tile[Q.t_self[k]];  // the own cell is part of the staged tile
+            Q.npxy[k] = make_float2(-p.x, -p.y);
+            Q.npz[k] = -p.z;
+            if (excl_start) {
+                const int oi = orig[i];
+                Q.ex_lo[k] = excl_start[oi];
+                Q.ex_hi[k] = excl_start[oi + 1];
+                any_excl = any_excl || Q.ex_hi[k] > Q.ex_lo[k];
+            }
+        }
+    }
+    if (!valid) return;
+    uint32_t cnt[RB_A], row[RB_A] = {0u, 0u, 0u, 0u};
+    rb_sweep<WRAP, 0>(tile, tile_slot, m_pad, g, rl2, Q, any_excl, orig, excl_idx, stage, stage_cap, row, 0u, nbr_list, lane, cnt);
+    // claim the quad's rows (each padded to 8 entries = whole 32-byte sectors) with one atomicAdd
+    uint32_t tot = 0u, mx = 0u, direct = 0u;
+#pragma unroll
+    for (int k = 0; k < RB_A; ++k) {
+        row[k] = tot;
+        tot += (cnt[k] + 7u) & ~7u;
+        mx = max(mx, cnt[k]);
+        if (cnt[k] > stage_cap) direct |= 1u << k;
+    }
+    uint32_t base = 0u;
+    if (lane == 0) {
+        base = atomicAdd(ctl + 1, tot);
+        if (mx > *reinterpret_cast<volatile uint32_t *>(ctl + 6)) atomicMax(ctl + 6, mx);
+    }
+    base = __shfl_sync(MC_FULL_MASK, base, 0);
+#pragma unroll
+    for (int k = 0; k < RB_A; ++k) {
+        row[k] += base;
+        if (lane == k && ((valid >> k) & 1u)) {
+            nbr_start[i0 + (uint32_t)k] = row[k];
+            nbr_count[i0 + (uint32_t)k] = cnt[k];
+        }
+    }
+    if ((uint64_t)base + tot > (uint64_t)list_cap) return;  // the host grows the list and builds again
+    __syncwarp();  // the staged entries of every lane are visible to the warp
+#pragma unroll
+    for (int k = 0; k < RB_A; ++k) {
+        if ((direct >> k) & 1u) continue;
+        const uint16_t *sk = stage + (uint32_t)k * stage_cap;
+        for (uint32_t e = (uint32_t)lane; e < cnt[k]; e += 32u) nbr_list[row[k] + e] = tile_slot[sk[e]];
+    }
+    if (direct) {
+        uint32_t cnt2[RB_A];
+        rb_sweep<WRAP, 1>(tile, tile_slot, m_pad, g, rl2, Q, any_excl, orig, excl_idx, stage, stage_cap, row, direct, nbr_list, lane, cnt2);
+    }
+    __syncwarp();  // copy-out reads done before the next quad's staging overwrites the space
+}
+
+__global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) rows_build_kernel(
+    int n_rows, const float4 *__restrict__ xyzq, const uint32_t *__restrict__ cell_start, const GridParams *__restrict__ gp, float rl2,
+    const int *__restrict__ orig, const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx,
+    uint32_t *__restrict__ nbr_count, uint32_t *__restrict__ nbr_start, uint32_t *__restrict__ nbr_list, uint32_t list_cap,
+    uint32_t tile_cap, uint32_t stage_cap /* staged entries per row; 0: every row takes two sweeps */, int split, int n_stages,
+    uint32_t *__restrict__ ctl /* as tile_build_kernel; [6] longest row */) {
+    MC_DYN_SHARED_ALIGNED(unsigned char, smem_raw, 128);
+    const size_t stage_bytes = (size_t)tile_cap * (sizeof(float4) + sizeof(uint32_t));
+    __shared__ __align__(8) uint64_t full_bar[RB_MAX_STAGES], empty_bar[RB_MAX_STAGES];
+    __shared__ StageMeta meta[RB_MAX_STAGES];
+
+    const GridParams g = *gp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RB_MAX_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], TILE_WARPS);
+        }
+    }
+    __syncthreads();
+    const long long n_items = (long long)g.ncell * split;
+
+    if (warp == 0) {
+        // ===== producer (as in tile_build_kernel; the tile is padded to whole blocks of 32) =====
+        uint32_t it = 0;
+        for (;;) {
+            long long w = 0;
+            if (lane == 0) w = (long long)atomicAdd(ctl, 1u);
+            w = __shfl_sync(MC_FULL_MASK, w, 0);
+            const bool done = w >= n_items;
+            const int c = done ? 0 : (int)(w / split);
+            uint32_t a0 = 0xffffffffu, a1 = 0xffffffffu, m = 0, self_off = 0;
+            TileRange r0 = {0u, 0u, 0u}, r1 = {0u, 0u, 0u};
+            int wrap = 0;
+            if (!done) {
+                a0 = cell_start[c];
+                a1 = cell_start[c + 1];
+                if (a0 == a1) continue;
+                const int c2 = c / (g.nc[0] * g.nc[1]);
+                if (c2 < g.row_l0 || c2 >= g.row_l1) continue;  // ghost layer: its atoms carry no rows
+                TilePlan P;
+                tile_plan(g, cell_start, c, a0, lane, P);
+                r0 = P.r0; r1 = P.r1; m = P.m; self_off = P.self_off; wrap = P.wrap;
+                if (lane == 0) {
+                    if (m > *reinterpret_cast<volatile uint32_t *>(ctl + 2)) atomicMax(ctl + 2, m);
+                    if (a1 - a0 > *reinterpret_cast<volatile uint32_t *>(ctl + 5)) atomicMax(ctl + 5, a1 - a0);
+                }
+                if (((m + 31u) & ~31u) > tile_cap) {
+                    if (lane == 0) ctl[3] = 1u;
+                    continue;
+                }
+            }
+            const int s = it % n_stages;
+            mbar_wait(&empty_bar[s], ((it / n_stages) & 1) ^ 1);
+            float4 *tile = reinterpret_cast<float4 *>(smem_raw + (size_t)s * stage_bytes);
+            uint32_t *tile_slot = reinterpret_cast<uint32_t *>(tile + tile_cap);
+            if (lane == 0) {
+                meta[s].m = m; meta[s].a0 = a0; meta[s].a1 = a1; meta[s].wrap = wrap; meta[s].self_off = self_off;
+                meta[s].slice = done ? 0u : (uint32_t)(w % split);
+            }
+            for (int src_lane = 0; src_lane < 9; ++src_lane) {
+                const uint32_t s0 = __shfl_sync(MC_FULL_MASK, r0.src, src_lane), n0 = __shfl_sync(MC_FULL_MASK, r0.cnt, src_lane),
+                               o0 = __shfl_sync(MC_FULL_MASK, r0.off, src_lane), s1 = __shfl_sync(MC_FULL_MASK, r1.src, src_lane),
+                               n1 = __shfl_sync(MC_FULL_MASK, r1.cnt, src_lane), o1 = __shfl_sync(MC_FULL_MASK, r1.off, src_lane);
+                for (uint32_t t = lane; t < n0; t += 32) tile_slot[o0 + t] = s0 + t;
+                for (uint32_t t = lane; t < n1; t += 32) tile_slot[o1 + t] = s1 + t;
+            }
+            {
+                const float qnan = __int_as_float(0x7fffffff);
+                const uint32_t pend = (m + 31u) & ~31u;
+                for (uint32_t t = m + lane; t < pend; t += 32) tile[t] = make_float4(qnan, qnan, qnan, 0.f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&full_bar[s], m * (uint32_t)sizeof(float4));
+            __syncwarp();
+            if (lane < 9) {
+                if (r0.cnt) tma_bulk_g2s(tile + r0.off, xyzq + r0.src, r0.cnt * (uint32_t)sizeof(float4), &full_bar[s]);
+                if (r1.cnt) tma_bulk_g2s(tile + r1.off, xyzq + r1.src, r1.cnt * (uint32_t)sizeof(float4), &full_bar[s]);
+            }
+            ++it;
+            if (done) break;
+        }
+    } else {
+        // ===== consumers: decoupled warps, quads dealt round-robin across items =====
+        const int cw = warp - 1;
+        uint16_t *stage = reinterpret_cast<uint16_t *>(smem_raw + (size_t)n_stages * stage_bytes) + (size_t)cw * RB_A * stage_cap;
+        uint32_t rot = 0;  // quads dealt so far (mod TILE_WARPS): the same number on every warp
+        for (uint32_t it = 0;; ++it) {
+            const int s = it % n_stages;
+            mbar_wait(&full_bar[s], (it / n_stages) & 1);
+            const StageMeta M = meta[s];
+            if (M.a0 == 0xffffffffu) break;
+            const float4 *tile = reinterpret_cast<const float4 *>(smem_raw + (size_t)s * stage_bytes);
+            const uint32_t *tile_slot = reinterpret_cast<const uint32_t *>(tile + tile_cap);
+            const uint32_t m_pad = (M.m + 31u) & ~31u;
+            const uint32_t n_at = min(M.a1, (uint32_t)max(n_rows, 0)) > M.a0 ? min(M.a1, (uint32_t)max(n_rows, 0)) - M.a0 : 0u;
+            const uint32_t n_quads_cell = (n_at + RB_A - 1) / RB_A;
+            // this item's quads: q = slice, slice + split, ...
+            const uint32_t nq = n_quads_cell > M.slice ? (n_quads_cell - M.slice + (uint32_t)split - 1u) / (uint32_t)split : 0u;
+            for (uint32_t j = ((uint32_t)cw + TILE_WARPS - rot) % TILE_WARPS; j < nq; j += TILE_WARPS) {
+                const uint32_t i0 = M.a0 + (M.slice + j * (uint32_t)split) * RB_A;
+#define MC_RBQ(W_) rb_quad<W_>(tile, tile_slot, M, m_pad, i0, n_rows, g, rl2, orig, excl_start, excl_idx, stage, stage_cap, nbr_count, \
+                               nbr_start, nbr_list, list_cap, ctl, lane)
+                if (M.wrap == 0) MC_RBQ(0); else if (M.wrap == 1) MC_RBQ(1); else MC_RBQ(2);
+#undef MC_RBQ
+            }
+            rot = (rot + nq) % TILE_WARPS;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+    }
+}
+
 // Compact rows (tile-local 16-bit indices) -> rows of global slots, same nbr_start / nbr_count.  Off the hot path: only
 // mc_get_neighbors, the virial and the between-molecules energy read global-slot rows.  One CTA per cell at a time.
 __global__ void __launch_bounds__(128) expand_rows_kernel(const uint32_t *__restrict__ cell_start, const GridParams *__restrict__ gp,
@@ -502,6 +777,7 @@ cudaError_t tile_sweep_prepare() {
 #define MC_TB_ATTR(I, P) if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_build_kernel<I, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     MC_TB_ATTR(uint32_t, false) MC_TB_ATTR(uint32_t, true) MC_TB_ATTR(uint16_t, false) MC_TB_ATTR(uint16_t, true)
 #undef MC_TB_ATTR
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     return e;
 }
 
@@ -526,11 +802,42 @@ static void launch_tile_build_t(int n_rows, long long items, int split, int n_sm
               excl_start, excl_idx, nbr_count, nbr_start, nbr_list, list_cap, tile_cap, split, n_stages, ctl);
 }
 
+// rows_build_kernel: tiles in flight and staged entries per row from what fits.  Three tiles in flight while the CTA stays
+// small enough for three CTAs per SM, else two, else one; rows are staged when the longest row of the previous build (+ 25 %)
+// fits next to the tiles, otherwise (first build of a system, very dense systems) every row takes the two-sweep path.
+static void launch_rows_build(int n_rows, long long items, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
+                              const GridParams *g, float rl2, const int *orig, const int32_t *excl_start, const int32_t *excl_idx,
+                              uint32_t *nbr_count, uint32_t *nbr_start, uint32_t *nbr_list, uint32_t list_cap, uint32_t tile_cap,
+                              uint32_t row_hint, uint32_t *ctl, cudaStream_t st) {
+    const size_t budget = 200u * 1024u, per_tile = (size_t)tile_cap * 20u;
+    uint32_t stage_cap = row_hint ? ((row_hint + row_hint / 4u + 47u) & ~31u) : 0u;
+    size_t staging = (size_t)TILE_WARPS * RB_A * stage_cap * sizeof(uint16_t);
+    if (per_tile + staging > budget) { stage_cap = 0u; staging = 0; }
+    int n_stages = 1;
+    if (3 * per_tile + staging <= 72u * 1024u) n_stages = 3;
+    else if (2 * per_tile + staging <= budget) n_stages = 2;
+    const size_t smem = (size_t)n_stages * per_tile + staging;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_build_kernel, (TILE_WARPS + 1) * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, (long long)n_sms * per_sm));
+    cudaMemsetAsync(ctl, 0, 8 * sizeof(uint32_t), st);
+    MC_LAUNCH(rows_build_kernel, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, cell_start, g, rl2, orig, excl_start, excl_idx,
+              nbr_count, nbr_start, nbr_list, list_cap, tile_cap, stage_cap, split, n_stages, ctl);
+}
+
 void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
                        const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
                        const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, void *nbr_list, bool compact, bool partition,
-                       uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches) {
+                       uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches, int variant,
+                       uint32_t row_hint) {
     const long long items = (long long)grid_cells * split;
+    if (variant == 2 && !compact && !partition) {
+        launch_rows_build(n_rows, items, split, n_sms, xyzq, cell_start, g, rl2, orig, excl_start, excl_idx, nbr_count, nbr_start,
+                          static_cast<uint32_t *>(nbr_list), list_cap, tile_cap, row_hint, ctl, st);
+        *launches += 1;
+        return;
+    }
 #define MC_TB_GO(I, P) launch_tile_build_t<I, P>(n_rows, items, split, n_sms, xyzq, cell_start, g, rl2, rc2_inner, orig, excl_start, excl_idx, \
                                                  nbr_count, nbr_start, static_cast<I *>(nbr_list), list_cap, tile_cap, ctl, st)
     if (compact) { if (partition) MC_TB_GO(uint16_t, true); else MC_TB_GO(uint16_t, false); }

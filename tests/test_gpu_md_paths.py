@@ -101,6 +101,56 @@ def test_pipelined_external_forces_are_invisible_through_the_abi(steps_per_call,
         assert ok, (worst, scale)
 
 
+@pytest.mark.parametrize("case", ["globule", "bonded_globule", "hot_fluid", "odd_sizes"])
+def test_fused_multi_step_kernel_equals_the_per_launch_path(case, Engine, oracle):
+    """Small plain-NVE systems take all steps of a call in one cooperative launch (md_fused.cu, option fused_steps, the
+    GUI's ten-steps-per-frame path of reference src/md/mod.rs:45,737-749).  Same arithmetic as the per-launch path: with no
+    rebuild inside the run positions, velocities and forces are bit-identical; with rebuilds (the fused kernel uses the
+    synchronous displacement criterion, the per-launch path the look-ahead one: lists are rebuilt at different steps and rows
+    change their summation order) both follow the oracle's trajectory.  System sizes that leave the last warp of the row
+    loop partly empty are part of the sweep (the first hardware run of this kernel hung on exactly that)."""
+    if case == "globule":
+        ws, bonded, n_calls, k = [W.globule()], False, 3, 2  # (atoms without bonds: a few steps, as in test_gpu_parity.py)
+    elif case == "bonded_globule":
+        ws, bonded, n_calls, k = [W.bonded_globule()], True, 3, 4
+    elif case == "hot_fluid":
+        ws, bonded, n_calls, k = [dict(W.lj_fluid(m=12, temp_k=400.0), skin=0.6)], False, 4, 15
+    else:
+        ws, bonded, n_calls, k = [W.globule(n, seed=300 + n) for n in (1, 2, 3, 5, 31, 33, 127, 257)], False, 2, 3
+    for w in ws:
+        n = len(w["xyzq"])
+        runs = []
+        for fused in (1, 0):
+            e = Engine.from_workload(w, bonded=bonded)
+            e.set_option("fused_steps", fused)
+            ext = np.zeros((n, 3), np.float32)
+            ext[::3, 0] = 1.5
+            for c in range(n_calls):
+                e.step(w["dt"], k, ext_forces=ext if c == 1 else None)
+            runs.append(dict(x=e.positions(), v=e.velocities(), f=e.forces(), st=e.stats()))
+            e.close()
+        a, b = runs
+        assert a["st"]["n_steps"] == b["st"]["n_steps"] == n_calls * k
+        # one launch per call (+ what a rebuild inside the call adds) against two and more per step
+        import os
+        if not os.environ.get("MOLCHANICA_MD_LIB"):  # (the host build of the library has no cooperative launch: both runs are per-launch there)
+            assert a["st"]["n_kernel_launches"] <= b["st"]["n_kernel_launches"] - n_calls * (k - 1)  # (list builds are in both counts)
+        if a["st"]["n_rebuilds"] == 1 and b["st"]["n_rebuilds"] == 1:
+            assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["v"], b["v"]) and np.array_equal(a["f"][:, :3], b["f"][:, :3])
+        if case == "hot_fluid":
+            assert a["st"]["n_rebuilds"] >= 3
+        if not bonded and case != "odd_sizes":
+            cur = dict(xyzq=w["xyzq"], vel=w["vel"])  # replay the calls on the oracle (the second one carries external forces)
+            for c in range(n_calls):
+                cur = oracle.md_run(w, k, precision=64, xyzq=cur["xyzq"], vel=cur["vel"], ext_force=ext if c == 1 else None)
+            for r in (a, b):
+                ok, worst, scale = trajectory_close(r["x"], cur["xyzq"], w["xyzq"], w["box_ext"] if w["periodic"] else None)
+                assert ok, (case, worst, scale)
+        else:
+            ok, worst, scale = trajectory_close(a["x"], b["x"], w["xyzq"], w["box_ext"] if w["periodic"] else None)
+            assert ok, (case, n, worst, scale)
+
+
 def _pair_virial64(w, nbr, coul_mode):
     """fp64 virial sum_{i<j} r_ij . f_ij of the listed pairs inside the cutoffs, written out in numpy independently of the
     device code: LJ 24 eps (2 s^12 - s^6); Coulomb qq/r (plain) or qq (erfc(ar)/r + 2a/sqrt(pi) exp(-a^2 r^2)) (Ewald real space)."""
