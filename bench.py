@@ -403,8 +403,12 @@ def main():
         seen_epoch = -1
         d2h = []
 
+        trace = {"step": 0.0, "begin": 0.0, "wait": 0.0, "ids": 0.0} if os.environ.get("MC_E2E_TRACE") else None
+
         def one(k):
             nonlocal seen_epoch
+            if trace is not None:
+                return one_traced(k)
             e.step_raw(DT_PS, 1, ext_p)
             # positions as packed float3 (Snapshot.atom_posits); a decomposed rank's ids only when its layout changed
             e._chk(e._L.mc_snapshot_begin_xyz(e._h, C.c_void_p(pos[k & 1].data_ptr()), None, C.byref(n_out), C.byref(epoch)))
@@ -419,6 +423,27 @@ def main():
             d2h.append(b)
             if k > 0:
                 e._chk(e._L.mc_snapshot_wait(e._h))
+
+        def one_traced(k):  # MC_E2E_TRACE=1: host time of the three calls of a step, summed per rank (stderr)
+            nonlocal seen_epoch
+            t0 = time.perf_counter()
+            e.step_raw(DT_PS, 1, ext_p)
+            t1 = time.perf_counter()
+            e._chk(e._L.mc_snapshot_begin_xyz(e._h, C.c_void_p(pos[k & 1].data_ptr()), None, C.byref(n_out), C.byref(epoch)))
+            t2 = time.perf_counter()
+            b = int(n_out.value) * 12
+            if world > 1 and epoch.value != seen_epoch:
+                e._chk(e._L.mc_snapshot_wait(e._h))
+                e._chk(e._L.mc_snapshot_begin_xyz(e._h, C.c_void_p(pos[k & 1].data_ptr()), C.c_void_p(ids.data_ptr()), C.byref(n_out),
+                                                  C.byref(epoch)))
+                seen_epoch = epoch.value
+                b += int(n_out.value) * 16
+            t3 = time.perf_counter()
+            d2h.append(b)
+            if k > 0:
+                e._chk(e._L.mc_snapshot_wait(e._h))
+            t4 = time.perf_counter()
+            trace["step"] += t1 - t0; trace["begin"] += t2 - t1; trace["ids"] += t3 - t2; trace["wait"] += t4 - t3
 
         def run_leg():
             for k in range(4):
@@ -435,6 +460,9 @@ def main():
             barrier()
             te = all_max(time.perf_counter() - t0)
             sb = e.stats()
+            if trace is not None:
+                print(f"[e2e trace rank {rank}] per step ms: " + ", ".join(f"{k_} {v / (ke + 4) * 1e3:.4f}" for k_, v in trace.items()),
+                      file=sys.stderr, flush=True)
             return {"value": ns_per_day(ke, te), "unit": UNIT, "h2d_bytes_per_step": int(e.ext_upload_bytes()),
                     "d2h_bytes_per_step": int(sum(d2h) / max(len(d2h), 1)), "steps": ke, "ms_per_step": te / ke * 1e3,
                     "rebuilds": int(sb["n_rebuilds"] - sa["n_rebuilds"]),

@@ -50,6 +50,7 @@ struct CommState {
     DevBuf<int2> s_meta, g_meta;            // {original id (-1 = padding), type | flags << 16}
     DevBuf<uint32_t> d_layer;               // 6 slot offsets read back after every rebuild
     DevBuf<double> d_red;
+    DevBuf<int> d_flags_all;                // every rank's flag words (+ this rank's own two behind them)
     // slot offsets of the current build
     uint32_t o_gp = 0, o_own = 0, o_first_end = 0, o_last_begin = 0, o_own_end = 0, o_end = 0;
 
@@ -271,7 +272,7 @@ void comm_destroy(mc_ctx *c) {
     if (cs->h_layer_all) cudaFreeHost(cs->h_layer_all);
     if (cs->comm) nccl_api().CommDestroy(cs->comm);
     cs->s_xyzq.release(); cs->s_vel.release(); cs->g_xyzq.release(); cs->g_vel.release();
-    cs->s_meta.release(); cs->g_meta.release(); cs->d_layer.release(); cs->d_red.release();
+    cs->s_meta.release(); cs->g_meta.release(); cs->d_layer.release(); cs->d_red.release(); cs->d_flags_all.release();
     delete cs;
     c->comm = nullptr;
     c->comm_active = false;
@@ -791,6 +792,22 @@ int comm_allreduce3(mc_ctx *c, double v[3]) {
 void comm_rank_size(const mc_ctx *c, int *rank, int *n_ranks) {
     *rank = c->comm ? c->comm->rank : 0;
     *n_ranks = c->comm ? c->comm->n : 1;
+}
+
+// The external-force blocks of all ranks, and -- in the same NCCL group, i.e. the same launch -- every rank's two flag words
+// {displacement / non-finite bits, halo error bits} as they stand on the stream (those of the previous step's kick_drift).
+// The per-rank words land in pinned host memory h_flags[2 * n_ranks] behind the call's one synchronisation.
+int comm_allgather_ext_and_flags(mc_ctx *c, float *buf, size_t chunk, const int *d_flags2, int *h_flags) {
+    CommState *cs = c->comm;
+    MC_CUDAC(c, cs->d_flags_all.ensure(2 * (size_t)cs->n + 2));
+    int *mine = cs->d_flags_all.p + 2 * (size_t)cs->n;
+    MC_CUDAC(c, cudaMemcpyAsync(mine, d_flags2, 2 * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
+    MC_NCCL(c, nccl_api().GroupStart());
+    MC_NCCL(c, nccl_api().AllGather(buf + (size_t)cs->rank * chunk, buf, chunk, ncclFloat, cs->comm, c->st));
+    MC_NCCL(c, nccl_api().AllGather(mine, cs->d_flags_all.p, 2, ncclInt32, cs->comm, c->st));
+    MC_NCCL(c, nccl_api().GroupEnd());
+    MC_CUDAC(c, cudaMemcpyAsync(h_flags, cs->d_flags_all.p, 2 * sizeof(int) * (size_t)cs->n, cudaMemcpyDeviceToHost, c->st));
+    return MC_OK;
 }
 
 int comm_allgather_f32_inplace(mc_ctx *c, float *buf, size_t chunk) {

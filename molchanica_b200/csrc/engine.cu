@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -52,12 +53,19 @@ static int fail(mc_ctx *c, int code, const std::string &m) {
 }
 
 // see engine_flush_tail
-#define MC_FLUSH(c)                                   \
+#define MC_FLUSH_OBS(c)                               \
     do {                                              \
         if ((c)->tail_pending) {                      \
             const int rc_flush_ = engine_flush_tail(c); \
             if (rc_flush_ != MC_OK) return rc_flush_; \
         }                                             \
+    } while (0)
+// setters (anything that may move, reorder or redefine atoms) also drop the fused kernel's private list; pure observers
+// (MC_FLUSH_OBS) leave it alone -- a list build they trigger reorders the atoms and drops it in engine_build_list
+#define MC_FLUSH(c)                                   \
+    do {                                              \
+        (c)->bl_valid = false;                        \
+        MC_FLUSH_OBS(c);                              \
     } while (0)
 
 // ---- lifetime ------------------------------------------------------------------------------------
@@ -112,6 +120,7 @@ extern "C" int mc_create(int device, mc_ctx **out) {
         delete c;
         return MC_E_CUDA;
     }
+    c->trace_step = getenv("MC_TRACE_STEP") != nullptr;
     const char *ln = getenv("MC_PAIR_LANES");
     if (ln) c->pair_lanes = atoi(ln);
     *out = c;
@@ -122,6 +131,12 @@ extern "C" int mc_destroy(mc_ctx *c) {
     if (!c) return MC_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
+    if (c->trace_step && c->trace_calls > 0) {
+        static const char *nm[8] = {"upload+setup", "close_tail/forces", "wait+allgather", "step loop", "flags", "sync", "after", ""};
+        fprintf(stderr, "[mc_step trace, device %d, %lld calls] ms per call:", c->device, (long long)c->trace_calls);
+        for (int k = 0; k < 7; ++k) fprintf(stderr, " %s %.4f", nm[k], c->trace_t[k] / (double)c->trace_calls * 1e3);
+        fprintf(stderr, "\n");
+    }
     comm_destroy(c);
     pme_release(&c->pme);
     for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -137,6 +152,7 @@ extern "C" int mc_destroy(mc_ctx *c) {
     }
     c->free_all();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_flags_all) cudaFreeHost(c->h_flags_all);
     cudaStreamDestroy(c->st);
     delete c;
     return MC_OK;
@@ -237,6 +253,7 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
     MC_REQUIRE(c, n == 0 || xyzq, "mc_set_atoms: xyzq is NULL");
     cudaSetDevice(c->device);
     c->n_global = n;
+    c->bl_valid = false;
     c->tail_pending = false;  // a new system: nothing of the old one is left to finish
     c->cons_virial_valid = false;
     c->list_valid = false;
@@ -557,6 +574,18 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         MC_REQUIRE(c, value == 1.0 || value == 2.0, "mc_set_option: build_variant is 1 (tile_build_kernel) or 2 (rows_build_kernel)");
         c->build_variant = (int)value;
         c->list_valid = false;
+    } else if (k == "rows_min_blocks") {  // register budget of rows_build_kernel: 3 CTAs per SM (72 registers) or 2 (112)
+        MC_REQUIRE(c, value == 2.0 || value == 3.0, "mc_set_option: rows_min_blocks is 2 or 3");
+        c->rows_min_blocks = (int)value;
+    } else if (k == "row_stage_limit") {  // testing knob: rows longer than this take the two-sweep path of rows_build_kernel
+        MC_REQUIRE(c, value >= 0.0, "mc_set_option: row_stage_limit >= 0 (0 = no limit)");
+        c->row_stage_limit = (uint32_t)value;
+        c->list_valid = false;
+    } else if (k == "fused_lanes") {
+        MC_REQUIRE(c, value == 0.0 || value == 8.0 || value == 16.0 || value == 32.0, "mc_set_option: fused_lanes is 0 (automatic), 8, 16 or 32");
+        c->fused_lanes = (int)value;
+    } else if (k == "fused_brute") {
+        c->fused_brute = value != 0.0;
     } else if (k == "fused_steps") {
         c->fused_steps = value != 0.0;
     } else {
@@ -616,6 +645,7 @@ static int setup_grid(mc_ctx *c) {
 
 int engine_build_list(mc_ctx *c) {
     const int n = (int)c->n;
+    c->bl_valid = false;  // atoms change slots
     cudaStream_t st = c->st;
     if (c->grid_dirty) { int rc = setup_grid(c); if (rc != MC_OK) return rc; }
     if (n == 0) { c->list_valid = true; return MC_OK; }
@@ -672,17 +702,23 @@ int engine_build_rows(mc_ctx *c) {
         if (compact) { if (!c->nbr_list16.p) MC_CUDA(c, c->nbr_list16.ensure(1024)); }
         else if (!c->nbr_list.p) MC_CUDA(c, c->nbr_list.ensure(1024));
         const size_t cap_now = compact ? c->nbr_list16.n : c->nbr_list.n;
+        const bool rows_v2 = c->build_variant == 2 && !compact && !c->pair_uniform;
+        if (rows_v2) MC_CUDA(c, c->rows_plan.ensure(rows_plan_words(grid_cells)));
+        // rows_build_kernel: a tile capacity close to the largest tile of the previous build leaves room for more tiles in flight
+        uint32_t tile_cap_now = c->tile_cap;
+        if (rows_v2 && c->tile_max_m) tile_cap_now = std::min(c->tile_cap, (c->tile_max_m + c->tile_max_m / 8u + 63u) & ~31u);
         launch_tile_build(n_rows, grid_cells, split, c->n_sms, c->xyzq[c->cur].p, c->cell_start.p, c->grid.p, rl2, rc2_inner,
                           c->orig[c->cur].p, es, ei, c->nbr_count.p, c->nbr_start.p,
                           compact ? static_cast<void *>(c->nbr_list16.p) : static_cast<void *>(c->nbr_list.p), compact, c->pair_uniform,
-                          (uint32_t)std::min<size_t>(cap_now, 0xffffffffu), c->tile_cap, c->tile_need.p, st, &c->launches,
-                          c->build_variant, c->row_len_hint);
+                          (uint32_t)std::min<size_t>(cap_now, 0xffffffffu), tile_cap_now, c->tile_need.p, st, &c->launches,
+                          c->build_variant, c->row_stage_limit ? std::min(c->row_len_hint, c->row_stage_limit) : c->row_len_hint,
+                          rows_v2 ? c->rows_plan.p : nullptr, c->rows_min_blocks);
         MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->tile_need.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         MC_CUDA(c, cudaStreamSynchronize(st));
         if (h_ctl[3] != 0) {  // a neighbourhood did not fit the tile
             uint32_t need = (h_ctl[2] + h_ctl[2] / 4 + 127u) & ~31u;  // 25 % head-room + NaN padding to whole chunks
             if (need > tile_sweep_max_atoms() && ((h_ctl[2] + 127u) & ~31u) <= tile_sweep_max_atoms()) need = tile_sweep_max_atoms();
-            if (need <= tile_sweep_max_atoms()) { c->tile_cap = need; continue; }
+            if (need <= tile_sweep_max_atoms()) { c->tile_cap = std::max(c->tile_cap, need); c->tile_max_m = 0; continue; }
             tiled = c->use_tile = false;  // too dense for shared memory: two-pass global sweep from now on
             compact = false;
             break;
@@ -911,7 +947,7 @@ int engine_flush_tail(mc_ctx *c) {
 extern "C" int mc_compute_forces(mc_ctx *c) {
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);
-    MC_FLUSH(c);
+    MC_FLUSH_OBS(c);
     c->prof_now = true;
     int rc = ensure_ready(c, "mc_compute_forces");
     if (rc != MC_OK) return rc;
@@ -948,6 +984,16 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     }
     c->prof_now = true;
     cudaStream_t st = c->st;
+    struct Tr {  // host-side phase clock (MC_TRACE_STEP)
+        mc_ctx *c; bool on; std::chrono::steady_clock::time_point t;
+        void lap(int k) {
+            if (!on) return;
+            const auto now = std::chrono::steady_clock::now();
+            c->trace_t[k] += std::chrono::duration<double>(now - t).count();
+            t = now;
+        }
+    } trc{c, c->trace_step && n_steps == 1 && ext_forces != nullptr /* the per-step calls of an end-to-end loop */, std::chrono::steady_clock::now()};
+    if (trc.on) c->trace_calls++;
     // decomposed runs rebuild on a schedule every rank derives from the same numbers (no per-step agreement)
     const bool pipelined = !c->comm_active && c->rebuild_every <= 0 && !c->sync_rebuild;
     // External forces are the one per-call input of a step (MdState::step(dev, dt, Some(forces)), reference
@@ -1002,10 +1048,27 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         c->ext_upload_bytes = 0;
     }
     int rc;
+    trc.lap(0);
+    // Small plain-NVE systems: all n_steps in ONE cooperative launch (md_fused.cu) instead of 2-4 launches + a host poll per
+    // step.  Up to md_fused_brute_max_atoms() atoms the kernel keeps a private all-pairs Verlet list and rebuilds it inside the
+    // launch: the host's list (sort, cells, tiles) is then not needed for stepping at all.  Larger systems (up to
+    // md_fused_max_atoms()) use the host's rows: the launch stops after the drift of a step that trips the displacement
+    // criterion; list rebuild and force evaluation happen here, then the remaining steps go out in the next launch.
+    const bool fused_ok = c->fused_steps && !c->comm_active && c->rebuild_every <= 0 && !c->sync_rebuild && !constrained && !baro && !defer &&
+                          !c->langevin && !c->csvr && !c->pme.planned && c->n_vsites == 0 && c->com_every == 0 && n_steps > 0 &&
+                          c->n_global <= md_fused_max_atoms() && !c->profiling;
+    const bool brute = fused_ok && c->fused_brute && c->n_global <= md_fused_brute_max_atoms();
+    if (!brute || c->tail_pending) c->bl_valid = false;  // any other path moves the atoms behind the private list's back
     if (c->tail_pending) {
         // the step the previous call left open: its force evaluation (it does not depend on the new array) runs under the
         // upload started above, then its second half kick with THAT call's external forces
         if ((rc = close_tail(c)) != MC_OK) return rc;
+    } else if (brute) {
+        MC_REQUIRE(c, c->rc_lj > 0.f, "mc_step: call mc_set_cutoffs first");
+        MC_REQUIRE(c, c->n_types > 0, "mc_step: call mc_set_lj_table first");
+        if (c->periodic)
+            for (int a = 0; a < 3; ++a)
+                MC_REQUIRE(c, 2.0f * list_radius(c) <= c->ext[a], "mc_step: cutoff + skin exceeds half the periodic box (minimum image would be ambiguous)");
     } else {
         if ((rc = ensure_ready(c, "mc_step")) != MC_OK) return rc;
         if (!c->forces_valid) {
@@ -1013,14 +1076,26 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
             if ((rc = engine_launch_forces(c, false)) != MC_OK) return rc;
         }
     }
+    trc.lap(1);
     if (wait_upload) MC_CUDA(c, cudaStreamWaitEvent(st, c->ev_up, 0));
-    if (gather_chunk && (rc = comm_allgather_f32_inplace(c, const_cast<float *>(d_ext), gather_chunk)) != MC_OK) return rc;
-    // Small plain-NVE systems: all n_steps in ONE cooperative launch (md_fused.cu) instead of 2-4 launches + a host poll per
-    // step.  The launch stops after the drift of a step that trips the displacement criterion; list rebuild and force
-    // evaluation happen here, then the remaining steps go out in the next launch.
-    const bool fused = c->fused_steps && !c->comm_active && c->rebuild_every <= 0 && !c->sync_rebuild && !constrained && !baro && !defer &&
-                       !c->langevin && !c->csvr && !c->pme.planned && c->n_vsites == 0 && c->com_every == 0 && n_steps > 0 &&
-                       c->n_global <= md_fused_max_atoms() && !c->profiling && !c->list_compact;
+    // A pipelined call of a decomposed run ends after its drift: the flags of that drift are agreed upon at the NEXT call, where
+    // they ride with the all-gather of the external forces (same NCCL launch) instead of costing an all-reduce per call.
+    bool flags_arrive = false;
+    int n_ranks_f = 1;
+    if (gather_chunk) {
+        if (defer && c->flags_ride) {
+            int rank_f = 0;
+            comm_rank_size(c, &rank_f, &n_ranks_f);
+            if (!c->h_flags_all) MC_CUDA(c, cudaMallocHost(&c->h_flags_all, sizeof(int) * 2 * 1024));
+            MC_REQUIRE(c, n_ranks_f <= 1024, "mc_step: more than 1024 ranks");
+            if ((rc = comm_allgather_ext_and_flags(c, const_cast<float *>(d_ext), gather_chunk, c->rebuild_flag.p, c->h_flags_all)) != MC_OK) return rc;
+            flags_arrive = true;
+        } else if ((rc = comm_allgather_f32_inplace(c, const_cast<float *>(d_ext), gather_chunk)) != MC_OK) {
+            return rc;
+        }
+    }
+    trc.lap(2);
+    const bool fused = fused_ok && (brute || !c->list_compact);
     if (fused) {
         int *h_out = reinterpret_cast<int *>(c->h_pinned) + 16;
         if (!c->ev_step_a) {
@@ -1032,10 +1107,29 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         int remaining = n_steps;
         bool first_half = true;
         while (remaining > 0) {
-            if (c->list_compact) break;  // (never: compact rows are only built for large systems)
-            FusedArgs A;
+            // (a rebuild inside this loop may have switched to compact rows: the kernel reads global-slot rows)
+            if (!brute && c->list_compact && (rc = engine_ensure_list32(c)) != MC_OK) return rc;
+            FusedArgs A{};
             A.n = (int)c->n;
-            A.xyzq = c->xyzq[c->cur].p; A.vel = c->vel[c->cur].p; A.force = c->force.p; A.xref = c->xref.p;
+            A.brute = brute ? 1 : 0;
+            A.lanes = c->fused_lanes;
+            if (brute) {
+                const uint32_t stride = ((uint32_t)c->n + 7u) & ~7u;
+                MC_CUDA(c, c->bl_list.ensure((size_t)c->n * stride));
+                MC_CUDA(c, c->bl_count.ensure((size_t)c->n));
+                MC_CUDA(c, c->bl_xref.ensure((size_t)c->n));
+                MC_CUDA(c, c->bl_flags.ensure(4));
+                MC_CUDA(c, cudaMemsetAsync(c->bl_flags.p, 0, 4 * sizeof(int), st));
+                A.bl_list = c->bl_list.p; A.bl_count = c->bl_count.p; A.bl_stride = stride; A.bl_xref = c->bl_xref.p;
+                A.bl_flags = reinterpret_cast<int *>(c->bl_flags.p);
+                A.need_forces = c->forces_valid ? 0 : 1;
+                A.bl_keep = (c->bl_valid && c->bl_n == c->n && c->bl_rl2 == list_radius(c) * list_radius(c)) ? 1 : 0;
+                A.rl2 = list_radius(c) * list_radius(c);
+                A.excl_start = c->have_excl ? c->excl_start.p : nullptr;
+                A.excl_idx = c->have_excl ? c->excl_idx.p : nullptr;
+            }
+            A.xyzq = c->xyzq[c->cur].p; A.vel = c->vel[c->cur].p; A.force = c->force.p;
+            A.xref = (!brute || c->list_valid) ? c->xref.p : nullptr;  // (brute: only to tell whether the host's list went stale)
             A.type = c->type[c->cur].p; A.flags = c->flags[c->cur].p; A.orig = c->orig[c->cur].p; A.slot_of_orig = c->slot_of_orig.p;
             A.nbr_start = c->nbr_start.p; A.nbr_count = c->nbr_count.p; A.nbr_list = c->nbr_list.p;
             A.ljtab = c->ljtab.p; A.p = make_params(c); A.lj_on = c->lj_disabled ? 0 : 1;
@@ -1047,15 +1141,38 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
             A.ext_force = d_ext; A.dt = dt; A.max_disp = 0.5f * c->skin; A.n_steps = remaining; A.first_half = first_half ? 1 : 0;
             A.rebuild_flag = c->rebuild_flag.p; A.out = h_out;
             const int coul = c->coul_disabled ? MC_COULOMB_NONE : c->coul_mode;
-            h_out[0] = -1; h_out[1] = 0;
+            h_out[0] = -1; h_out[1] = 0; h_out[2] = 0; h_out[3] = 0;
+            static const bool fused_times = getenv("MC_FUSED_TIMES") != nullptr;
+            if (fused_times) {  // debugging aid: phase time stamps of the launch, printed after it
+                MC_CUDA(c, c->fused_dbg.ensure(64));
+                MC_CUDA(c, cudaMemsetAsync(c->fused_dbg.p, 0, 64 * sizeof(unsigned long long), st));
+                A.dbg = c->fused_dbg.p;
+            }
             MC_CUDA(c, launch_md_fused(A, c->n_types > 1, coul, c->periodic, c->n_sms, st, &c->launches));
             MC_CUDA(c, cudaStreamSynchronize(st));
             const int done = h_out[0], fl = h_out[1];
+            if (fused_times) {
+                unsigned long long h[64];
+                cudaMemcpy(h, c->fused_dbg.p, sizeof(h), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[fused times, ns since launch start]");
+                for (int k = 1; k < 64 && h[k]; ++k) fprintf(stderr, " %llu", h[k] - h[0]);
+                fprintf(stderr, "\n");
+            }
             if (done < 0) return fail(c, MC_E_CUDA, "mc_step: the fused step kernel did not report back");
             if (fl & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
             c->n_steps += done;
             c->steps_since_build += done;
             remaining -= done;
+            if (brute) {
+                // every step taken on the kernel's own list; the host's list only goes stale (rebuilt when somebody needs it)
+                c->n_rebuilds += h_out[3];
+                if (h_out[2]) c->list_valid = false;
+                c->forces_valid = true;
+                c->bl_valid = true;  // (cleared by everything else that moves, reorders or redefines atoms: MC_FLUSH, the builds, the other step paths)
+                c->bl_n = c->n;
+                c->bl_rl2 = list_radius(c) * list_radius(c);
+                break;
+            }
             if (!(fl & 1)) break;  // all steps taken, closing half kick applied in the kernel; forces belong to the positions
             // the last drift tripped the displacement criterion: its forces are still those of the previous positions
             c->forces_valid = false;
@@ -1229,11 +1346,15 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     }
     c->prof_now = true;
     MC_CUDA(c, cudaEventRecord(c->ev_step_b, st));
+    trc.lap(3);
     // Fixed schedules (rebuild_every > 0, decomposed runs): the displacement flag is the safety net.  It rides behind the
     // last kernel -- on a decomposed handle as the maximum over all ranks (one 8-byte all-reduce per CALL, not per step),
     // so that every rank takes the same decision -- and is read after the one synchronisation of this call.
     int *h_agree = reinterpret_cast<int *>(c->h_pinned) + 12;
-    const bool check_flag = (c->rebuild_every > 0 || c->comm_active) && n_steps > 0;
+    // (a pipelined decomposed call with external forces leaves its flags to the next call's all-gather, see above)
+    const bool ride = defer && c->comm_active && gather_chunk != 0;
+    c->flags_ride = ride;
+    const bool check_flag = (c->rebuild_every > 0 || c->comm_active) && n_steps > 0 && !ride;
     if (check_flag) {
         if (c->comm_active) {
             if ((rc = comm_reduce_flags_async(c, c->rebuild_flag.p, h_agree)) != MC_OK) return rc;
@@ -1242,7 +1363,9 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         }
     }
     MC_CUDA(c, cudaGetLastError());
+    trc.lap(4);
     MC_CUDA(c, cudaStreamSynchronize(st));
+    trc.lap(5);
     float ms = 0.f;
     MC_CUDA(c, cudaEventElapsedTime(&ms, c->ev_step_a, c->ev_step_b));
     c->last_step_ms = ms;
@@ -1251,7 +1374,16 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     if (pipelined && n_steps > 0 && (h_flag[(n_steps - 1) & 1] & 2))
         return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
     bool stale_list = false;
-    if (check_flag) {
+    if (flags_arrive) {
+        // the previous call's flags, the same words on every rank: maximum over the ranks, then as below
+        h_agree[0] = h_agree[1] = 0;
+        for (int r = 0; r < n_ranks_f; ++r) {
+            h_agree[0] = std::max(h_agree[0], c->h_flags_all[2 * r]);
+            h_agree[1] |= c->h_flags_all[2 * r + 1];
+        }
+        // (a rebuild between the two calls has cleared the displacement word: nothing to report then)
+    }
+    if (check_flag || flags_arrive) {
         if (h_agree[1] & MC_HALO_ERR_TIMEOUT)
             return fail(c, MC_E_COMM, "mc_step: a neighbour rank did not signal its halo push within 2 s (peer died or ranks out of step)");
         if (h_agree[0] & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
@@ -1375,14 +1507,14 @@ extern "C" int mc_get_positions(mc_ctx *c, mc_float4 *out) {
 
 extern "C" int mc_get_velocities(mc_ctx *c, mc_float4 *out) {
     if (!c || !out) return MC_E_INVALID;
-    MC_FLUSH(c);
+    MC_FLUSH_OBS(c);
     cudaSetDevice(c->device);
     return read_sorted_to_orig(c, c->vel[c->cur].p, out);
 }
 
 extern "C" int mc_get_forces(mc_ctx *c, mc_float4 *out) {
     if (!c || !out) return MC_E_INVALID;
-    MC_FLUSH(c);
+    MC_FLUSH_OBS(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->forces_valid, "mc_get_forces: no force evaluation since the last change; call mc_compute_forces");
     return read_sorted_to_orig(c, c->force.p, out);
@@ -1397,7 +1529,7 @@ extern "C" int mc_get_forces(mc_ctx *c, mc_float4 *out) {
 
 static int snapshot_begin_impl(mc_ctx *c, mc_float4 *out_positions, mc_float4 *out_velocities, int32_t *out_ids, int64_t *n_out) {
     if (!c || !out_positions) return MC_E_INVALID;
-    if (out_velocities) MC_FLUSH(c);  // velocities are only final once the step mc_step may have left open is closed
+    if (out_velocities) MC_FLUSH_OBS(c);  // velocities are only final once the step mc_step may have left open is closed
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active || out_ids, "mc_snapshot_begin: a decomposed handle returns its owned atoms and needs out_ids");
     if (!c->st_copy) {
@@ -1506,7 +1638,7 @@ extern "C" int mc_snapshot_wait(mc_ctx *c) {
 
 extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
     if (!c || !out) return MC_E_INVALID;
-    MC_FLUSH(c);
+    MC_FLUSH_OBS(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->forces_valid, "mc_get_energy: no force evaluation since the last change; call mc_compute_forces");
     if (!c->forces_have_energy) {
@@ -1597,7 +1729,7 @@ static int compute_pressure(mc_ctx *c, double *pressure_bar, double *virial) {
 
 extern "C" int mc_get_pressure(mc_ctx *c, double *pressure_bar, double *virial) {
     if (!c) return MC_E_INVALID;
-    MC_FLUSH(c);
+    MC_FLUSH_OBS(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->periodic, "mc_get_pressure: needs a periodic box");
     MC_REQUIRE(c, !c->comm_active, "mc_get_pressure: not available on a decomposed handle yet");
@@ -1685,7 +1817,7 @@ extern "C" int mc_set_molecule_ids(mc_ctx *c, const uint16_t *mol_id) {
 
 extern "C" int mc_get_energy_between_mols(mc_ctx *c, double *out) {
     if (!c || !out) return MC_E_INVALID;
-    MC_FLUSH(c);
+    MC_FLUSH_OBS(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->have_mols, "mc_get_energy_between_mols: call mc_set_molecule_ids first");
     int rc = ensure_ready(c, "mc_get_energy_between_mols");
@@ -1741,7 +1873,7 @@ extern "C" int mc_reset_timers(mc_ctx *c) {
 
 extern "C" int mc_get_neighbors(mc_ctx *c, int64_t *start, int32_t *idx, int64_t cap, int64_t *total) {
     if (!c || !start || !total) return MC_E_INVALID;
-    MC_FLUSH(c);
+    MC_FLUSH_OBS(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active, "mc_get_neighbors: single-GPU handles only");
     MC_REQUIRE(c, c->list_valid, "mc_get_neighbors: no current list; call mc_build_neighbors");

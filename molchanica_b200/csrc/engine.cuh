@@ -51,6 +51,12 @@ struct mc_ctx {
     cudaStream_t st = nullptr;
     std::string err;
     void *h_pinned = nullptr;
+    int *h_flags_all = nullptr;   // pinned, 2 ints per rank: the flag words that ride with the external-force all-gather of a pipelined decomposed call
+    bool flags_ride = false;      // the previous call was such a call: its flags arrive with this call's all-gather
+    // MC_TRACE_STEP=1: host time spent in the phases of mc_step (seconds, summed; printed by mc_destroy) -- a debugging aid
+    bool trace_step = false;
+    double trace_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t trace_calls = 0;
 
     // system
     int64_t n = 0;         // atoms held locally (owned + ghosts)
@@ -88,6 +94,8 @@ struct mc_ctx {
     uint32_t tile_cap = 1024;  // tile capacity in atoms, grows on demand
     int build_variant = 2;     // option "build_variant": 2 = rows_build_kernel (default), 1 = tile_build_kernel (tile_build.cu)
     uint32_t row_len_hint = 0; // longest row of the last build (0: none yet)
+    int rows_min_blocks = 3;   // option "rows_min_blocks"
+    uint32_t row_stage_limit = 0;  // option "row_stage_limit" (testing): cap on the hint, forces the two-sweep path for longer rows
     int use_pair_tile = 0;     // option "pair_tile": compact rows (16-bit tile-local indices) + TMA-staged force kernel (pair_tile.cu):
                                // 0 (default) off, 1 on, 2 on for systems of >= 16384 atoms.  Measured on C4 (profiles/pair_tile_r2_*):
                                // 0.199 ms against 0.178 ms of the gather kernel -- staging a 27-cell tile per ~19-atom cell is
@@ -114,7 +122,7 @@ struct mc_ctx {
     DevBuf<uint8_t> flags[2];
     DevBuf<int> orig[2], slot_of_orig, rebuild_flag;
     DevBuf<uint32_t> keys[2], vals[2], scratch, cell_start, nbr_count, nbr_start, nbr_list;
-    DevBuf<uint32_t> cnt_orig, start_orig, export_rows, tile_need, cell_plan, cell_rowtab;
+    DevBuf<uint32_t> cnt_orig, start_orig, export_rows, tile_need, cell_plan, cell_rowtab, rows_plan;
     DevBuf<uint16_t> nbr_list16;
     DevBuf<int32_t> excl_start, excl_idx, p14_start, p14_idx;
     DevBuf<float2> ljtab, d_dock_tab;
@@ -166,6 +174,14 @@ struct mc_ctx {
 
     // pipelined external forces (engine.cu, mc_step): the caller's array is uploaded on a stream of its own while the
     // force evaluation the previous call left open runs; that call's second half kick is applied once both are there
+    int fused_lanes = 0;         // option "fused_lanes": lanes per row in the fused kernel's force phase (0 = chosen by the launcher)
+    bool fused_brute = true;     // option "fused_brute": up to md_fused_brute_max_atoms() atoms the fused kernel keeps its own all-pairs list
+    DevBuf<uint32_t> bl_list, bl_count, bl_flags;  // the private list of the fused kernel's brute-force mode
+    DevBuf<float4> bl_xref;
+    DevBuf<unsigned long long> fused_dbg;
+    bool bl_valid = false;       // the private list matches the atoms as they are (positions moved only by the fused kernel since)
+    int64_t bl_n = 0;
+    float bl_rl2 = 0.f;
     bool fused_steps = true;     // option "fused_steps": small plain-NVE systems take all steps of a call in one cooperative launch (md_fused.cu)
     bool defer_tail = false;     // option "defer_tail" (off until the path has been confirmed on hardware; bench.py's e2e leg turns it on)
     bool tail_pending = false;   // positions are one step ahead of forces / velocities (half kick outstanding)
@@ -221,9 +237,10 @@ struct mc_ctx {
 
     void free_all() {
         for (int b = 0; b < 2; ++b) { xyzq[b].release(); vel[b].release(); type[b].release(); flags[b].release(); orig[b].release(); keys[b].release(); vals[b].release(); }
+        fused_dbg.release(); bl_list.release(); bl_count.release(); bl_flags.release(); bl_xref.release();
         force.release(); xref.release(); stage.release(); flush.release(); slot_of_orig.release(); rebuild_flag.release();
         scratch.release(); cell_start.release(); nbr_count.release(); nbr_start.release(); nbr_list.release();
-        cnt_orig.release(); start_orig.release(); export_rows.release(); tile_need.release(); cell_plan.release(); cell_rowtab.release(); nbr_list16.release();
+        cnt_orig.release(); start_orig.release(); export_rows.release(); tile_need.release(); rows_plan.release(); cell_plan.release(); cell_rowtab.release(); nbr_list16.release();
         excl_start.release(); excl_idx.release(); p14_start.release(); p14_idx.release();
         ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); ext_force2.release(); d_poses.release(); d_scores.release();
         grid.release(); red_partial.release(); red_out.release(); d_rec.release(); d_lig.release();
@@ -300,5 +317,6 @@ void comm_shrink_interval(mc_ctx *c);
 int comm_allreduce3(mc_ctx *c, double v[3]);
 int comm_allreduce_f4(mc_ctx *c, float4 *buf, int64_t n);  // in-place sum over ranks
 void comm_rank_size(const mc_ctx *c, int *rank, int *n_ranks);
+int comm_allgather_ext_and_flags(mc_ctx *c, float *buf, size_t chunk, const int *d_flags2, int *h_flags);  // h_flags: pinned, 2 ints per rank
 int comm_allgather_f32_inplace(mc_ctx *c, float *buf, size_t chunk);  // rank r contributes buf[r * chunk .. (r + 1) * chunk)
 void comm_destroy(mc_ctx *c);

@@ -31,9 +31,10 @@ uint32_t tile_sweep_max_atoms();
 void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
                        const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
                        const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, void *nbr_list, bool compact, bool partition,
-                       uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches, int variant = 2,
-                       uint32_t row_hint = 0);
-// variant = 2 (default): global-slot rows without partition are built by rows_build_kernel (ballot compaction, rows staged in
+                       uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches, int variant = 1,
+                       uint32_t row_hint = 0, uint32_t *plan = nullptr, int variant_min_blocks = 3);
+size_t rows_plan_words(int grid_cells);  // size of `plan` (uint32_t), the per-cell staging records of variant 2
+// variant = 2 (the engine's default; needs `plan`): global-slot rows without partition are built by rows_build_kernel (ballot compaction, rows staged in
 // shared memory when row_hint -- the longest row of the previous build, ctl[6] -- says they fit); 1: tile_build_kernel always.
 // compact = true: nbr_list is uint16_t[list_cap], entries are tile-local indices (tile_ring.cuh) -- what pair_tile.cu reads;
 // compact = false: uint32_t[list_cap] global slots.  Rows are padded to 8 entries either way.

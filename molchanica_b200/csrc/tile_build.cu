@@ -477,6 +477,17 @@ constexpr int RB_MAX_STAGES = 4;  // tiles in flight per CTA
 
 __device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
 
+// staging stores through a 32-bit shared-window address (one IADD3 forms base + 2 * rank; a generic pointer costs a 64-bit add)
+#ifndef MC_HOST_SHIM
+typedef uint32_t rb_sptr;
+__device__ __forceinline__ rb_sptr rb_sptr_of(const uint16_t *p) { return smem_u32(p); }
+__device__ __forceinline__ void rb_store16(rb_sptr a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+#else
+typedef uintptr_t rb_sptr;
+inline rb_sptr rb_sptr_of(const uint16_t *p) { return reinterpret_cast<uintptr_t>(p); }
+inline void rb_store16(rb_sptr a, uint16_t v) { *reinterpret_cast<uint16_t *>(a) = v; }
+#endif
+
 // accept decision of one atom (negated position npi = -x_i) against the candidate pj: the oracle's
 // ((dx*dx)+(dy*dy))+(dz*dz) < rl2 on d = x_j - x_i = -(x_i - x_j) (exactly the negative in fp32, and every step below is
 // odd or even in d: the decision is the oracle's bit for bit).  NaN (tile padding, parked atoms) is never accepted.
@@ -507,42 +518,53 @@ struct RbQuad {
 
 // One pass of a quad over the tile.  MODE 0: stage the rows (16-bit tile indices, the first `stage_cap` entries of each)
 // and count; MODE 1: write the rows flagged in `direct` straight to nbr_list at row[k] (second pass of rows that did not
-// fit the staging space).  cnt[k] = row lengths (warp-uniform).
-template <int WRAP, int MODE>
+// fit the staging space).  cnt[k] = row lengths (warp-uniform).  EXCL: some atom of the quad carries exclusions (rare; the
+// common instantiation keeps every decision in a predicate register).
+template <int WRAP, int MODE, bool EXCL>
 __device__ __forceinline__ void rb_sweep(const float4 *tile, const uint32_t *tile_slot, uint32_t m_pad, const GridParams &g, float rl2,
-                                         const RbQuad &Q, bool any_excl, const int *__restrict__ orig, const int32_t *__restrict__ excl_idx,
+                                         const RbQuad &Q, const int *__restrict__ orig, const int32_t *__restrict__ excl_idx,
                                          uint16_t *stage, uint32_t stage_cap, const uint32_t (&row)[RB_A], uint32_t direct,
                                          uint32_t *__restrict__ nbr_list, int lane, uint32_t (&cnt)[RB_A]) {
+    // MODE 0: byte address (shared window) of the next free staging element of row k and the end of its space;
+    // MODE 1: index of the next list entry of row k
+    // (the staged rows are interleaved: element e of row k sits at stage[e * RB_A + k], so one end-of-space bound serves
+    // all rows and the row's offset is an immediate of the store)
+    rb_sptr sp[RB_A];
+    const rb_sptr se = rb_sptr_of(stage) + 2u * RB_A * stage_cap;
+    uint32_t lo[RB_A];
 #pragma unroll
-    for (int k = 0; k < RB_A; ++k) cnt[k] = 0u;
+    for (int k = 0; k < RB_A; ++k) {
+        sp[k] = rb_sptr_of(stage) + 2u * (uint32_t)k;
+        lo[k] = row[k];
+    }
     const uint32_t lt = lanemask_lt(lane);
     for (uint32_t t = (uint32_t)lane; t < m_pad; t += 32u) {
         const float4 pj = tile[t];
-        bool hit[RB_A];
-#pragma unroll
-        for (int k = 0; k < RB_A; ++k) hit[k] = rb_accept<WRAP>(pj, Q.npxy[k], Q.npz[k], g, rl2) && t != Q.t_self[k];
-        if (any_excl) {  // 1-2 / 1-3 / 1-4 partners (original ids) never enter the list; rare: only hits of atoms that carry exclusions pay
-#pragma unroll
-            for (int k = 0; k < RB_A; ++k) {
-                if (hit[k] && Q.ex_hi[k] > Q.ex_lo[k]) {
-                    const int oj = orig[tile_slot[t]];
-                    for (int e = Q.ex_lo[k]; e < Q.ex_hi[k]; ++e)
-                        if (excl_idx[e] == oj) { hit[k] = false; break; }
-                }
-            }
-        }
 #pragma unroll
         for (int k = 0; k < RB_A; ++k) {
-            const uint32_t mask = __ballot_sync(MC_FULL_MASK, hit[k]);
-            const uint32_t pos = cnt[k] + (uint32_t)__popc(mask & lt);
-            if (MODE == 0) {
-                if (hit[k] && pos < stage_cap) stage[(uint32_t)k * stage_cap + pos] = (uint16_t)t;
-            } else {
-                if (hit[k] && ((direct >> k) & 1u)) nbr_list[row[k] + pos] = tile_slot[t];
+            bool hit = rb_accept<WRAP>(pj, Q.npxy[k], Q.npz[k], g, rl2) && t != Q.t_self[k];
+            if (EXCL) {  // 1-2 / 1-3 / 1-4 partners (original ids) never enter the list: only hits of atoms that carry exclusions pay
+                if (hit && Q.ex_hi[k] > Q.ex_lo[k]) {
+                    const int oj = orig[tile_slot[t]];
+                    for (int e = Q.ex_lo[k]; e < Q.ex_hi[k]; ++e)
+                        if (excl_idx[e] == oj) { hit = false; break; }
+                }
             }
-            cnt[k] += (uint32_t)__popc(mask);
+            const uint32_t mask = __ballot_sync(MC_FULL_MASK, hit);
+            const uint32_t below = (uint32_t)__popc(mask & lt), all = (uint32_t)__popc(mask);
+            if (MODE == 0) {
+                const rb_sptr q = sp[k] + 2u * RB_A * below;
+                if (hit && q < se) rb_store16(q, (uint16_t)t);
+                sp[k] += 2u * RB_A * all;
+            } else {
+                if (hit && ((direct >> k) & 1u)) nbr_list[lo[k] + below] = tile_slot[t];
+                lo[k] += all;
+            }
         }
     }
+#pragma unroll
+    for (int k = 0; k < RB_A; ++k)
+        cnt[k] = MODE == 0 ? (uint32_t)((sp[k] - rb_sptr_of(stage)) / (2u * RB_A)) : lo[k] - row[k];
 }
 
 template <int WRAP>
@@ -578,7 +600,8 @@ __device__ __forceinline__ void rb_quad(const float4 *tile, const uint32_t *tile
     }
     if (!valid) return;
     uint32_t cnt[RB_A], row[RB_A] = {0u, 0u, 0u, 0u};
-    rb_sweep<WRAP, 0>(tile, tile_slot, m_pad, g, rl2, Q, any_excl, orig, excl_idx, stage, stage_cap, row, 0u, nbr_list, lane, cnt);
+    if (any_excl) rb_sweep<WRAP, 0, true>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, stage_cap, row, 0u, nbr_list, lane, cnt);
+    else rb_sweep<WRAP, 0, false>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, stage_cap, row, 0u, nbr_list, lane, cnt);
     // claim the quad's rows (each padded to 8 entries = whole 32-byte sectors) with one atomicAdd
     uint32_t tot = 0u, mx = 0u, direct = 0u;
 #pragma unroll
@@ -607,18 +630,82 @@ __device__ __forceinline__ void rb_quad(const float4 *tile, const uint32_t *tile
 #pragma unroll
     for (int k = 0; k < RB_A; ++k) {
         if ((direct >> k) & 1u) continue;
-        const uint16_t *sk = stage + (uint32_t)k * stage_cap;
-        for (uint32_t e = (uint32_t)lane; e < cnt[k]; e += 32u) nbr_list[row[k] + e] = tile_slot[sk[e]];
+        for (uint32_t e = (uint32_t)lane; e < cnt[k]; e += 32u) nbr_list[row[k] + e] = tile_slot[stage[e * RB_A + (uint32_t)k]];
     }
     if (direct) {
         uint32_t cnt2[RB_A];
-        rb_sweep<WRAP, 1>(tile, tile_slot, m_pad, g, rl2, Q, any_excl, orig, excl_idx, stage, stage_cap, row, direct, nbr_list, lane, cnt2);
+        if (any_excl) rb_sweep<WRAP, 1, true>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, stage_cap, row, direct, nbr_list, lane, cnt2);
+        else rb_sweep<WRAP, 1, false>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, stage_cap, row, direct, nbr_list, lane, cnt2);
     }
     __syncwarp();  // copy-out reads done before the next quad's staging overwrites the space
 }
 
-__global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) rows_build_kernel(
-    int n_rows, const float4 *__restrict__ xyzq, const uint32_t *__restrict__ cell_start, const GridParams *__restrict__ gp, float rl2,
+// Per-cell staging record of rows_build_kernel's producer (RB_PLAN_WORDS words, written once per build by
+// rows_plan_kernel): [0] a0 [1] a1 [2] m [3] self_off [4] wrap | skip << 8; then src[18], cnt[18], off[18] of the tile's
+// ranges.  With the record the producer needs ONE round trip to global memory per item instead of three dependent ones
+// (work counter -> cell_start -> stencil rows), and that one is issued an item ahead.
+constexpr int RB_PLAN_WORDS = 64;
+constexpr int RB_PLAN_SRC = 8, RB_PLAN_CNT = 26, RB_PLAN_OFF = 44;
+
+__global__ void __launch_bounds__(256) rows_plan_kernel(const uint32_t *__restrict__ cell_start, const GridParams *__restrict__ gp,
+                                                        uint32_t *__restrict__ plan, uint32_t *__restrict__ ctl) {
+    const GridParams g = *gp;
+    const int lane = threadIdx.x & 31;
+    const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (c >= g.ncell) return;  // warp-uniform
+    const uint32_t a0 = cell_start[c], a1 = cell_start[c + 1];
+    const int c2 = c / (g.nc[0] * g.nc[1]);
+    const bool skip = a0 == a1 || c2 < g.row_l0 || c2 >= g.row_l1;  // empty cell / ghost layer: no rows
+    uint32_t *rec = plan + (size_t)c * RB_PLAN_WORDS;
+    TilePlan P;
+    P.m = 0; P.self_off = 0; P.wrap = 0;
+    P.r0 = TileRange{0u, 0u, 0u}; P.r1 = TileRange{0u, 0u, 0u};
+    if (!skip) tile_plan(g, cell_start, c, a0, lane, P);
+    if (lane < 9) {
+        rec[RB_PLAN_SRC + 2 * lane] = P.r0.src; rec[RB_PLAN_CNT + 2 * lane] = P.r0.cnt; rec[RB_PLAN_OFF + 2 * lane] = P.r0.off;
+        rec[RB_PLAN_SRC + 2 * lane + 1] = P.r1.src; rec[RB_PLAN_CNT + 2 * lane + 1] = P.r1.cnt; rec[RB_PLAN_OFF + 2 * lane + 1] = P.r1.off;
+    }
+    if (lane == 0) {
+        rec[0] = a0; rec[1] = a1; rec[2] = P.m; rec[3] = P.self_off; rec[4] = (uint32_t)P.wrap | (skip ? 0x100u : 0u);
+        if (!skip) {
+            if (P.m > *reinterpret_cast<volatile uint32_t *>(ctl + 2)) atomicMax(ctl + 2, P.m);
+            if (a1 - a0 > *reinterpret_cast<volatile uint32_t *>(ctl + 5)) atomicMax(ctl + 5, a1 - a0);
+        }
+    }
+}
+
+struct RbPlanRegs { uint32_t a0, a1, m, self_off, flags, src, cnt, off; };
+
+__device__ __forceinline__ void rb_load_plan(const uint32_t *__restrict__ plan, int c, int lane, RbPlanRegs &R) {
+    const uint32_t *rec = plan + (size_t)c * RB_PLAN_WORDS;
+    R.a0 = rec[0]; R.a1 = rec[1]; R.m = rec[2]; R.self_off = rec[3]; R.flags = rec[4];
+    const int l = lane < 18 ? lane : 0;
+    R.src = rec[RB_PLAN_SRC + l]; R.cnt = lane < 18 ? rec[RB_PLAN_CNT + l] : 0u; R.off = rec[RB_PLAN_OFF + l];
+}
+
+#ifndef MC_HOST_SHIM
+// mbarrier wait that gives the issue slots away while it waits (a plain try_wait loop measured 15 % of the kernel's issued
+// instructions: consumer warps run ahead of the tiles by design)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+    uint32_t ok, ns = 250u;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(ns);
+        if (ns < 2000u) ns += ns;
+    }
+}
+#else
+inline void mbar_wait_sleep(uint64_t *bar, uint32_t parity) { shim_mbar_wait(bar, parity); }
+#endif
+
+template <int MINB>
+__global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MINB) rows_build_kernel(
+    int n_rows, const float4 *__restrict__ xyzq, const uint32_t *__restrict__ plan, const GridParams *__restrict__ gp, float rl2,
     const int *__restrict__ orig, const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx,
     uint32_t *__restrict__ nbr_count, uint32_t *__restrict__ nbr_start, uint32_t *__restrict__ nbr_list, uint32_t list_cap,
     uint32_t tile_cap, uint32_t stage_cap /* staged entries per row; 0: every row takes two sweeps */, int split, int n_stages,
@@ -640,49 +727,54 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) row
     const long long n_items = (long long)g.ncell * split;
 
     if (warp == 0) {
-        // ===== producer (as in tile_build_kernel; the tile is padded to whole blocks of 32) =====
-        uint32_t it = 0;
+        // ===== producer =====
+        // Items come from the global work counter (cells differ in cost -- the minimum image of boundary cells -- and a
+        // static deal aliases with the grid: 444 CTAs over rows of 37 cells gave every CTA one x coordinate).  Two things
+        // are in flight while an item is staged: the plan record of the next item and the claim of the one after it.
+        int s = 0;
+        uint32_t ph = 1;  // parity to wait for on empty_bar[s] (flips every time the ring wraps)
+        uint32_t pend = 0;
+        if (lane == 0) pend = atomicAdd(ctl, 1u);
+        long long w = (long long)__shfl_sync(MC_FULL_MASK, pend, 0);
+        bool have = w < n_items;
+        RbPlanRegs nx = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        uint32_t slice_nx = 0;
+        if (have) { rb_load_plan(plan, (int)(w / split), lane, nx); slice_nx = (uint32_t)(w % split); }
+        if (lane == 0 && have) pend = atomicAdd(ctl, 1u);
         for (;;) {
-            long long w = 0;
-            if (lane == 0) w = (long long)atomicAdd(ctl, 1u);
-            w = __shfl_sync(MC_FULL_MASK, w, 0);
-            const bool done = w >= n_items;
-            const int c = done ? 0 : (int)(w / split);
-            uint32_t a0 = 0xffffffffu, a1 = 0xffffffffu, m = 0, self_off = 0;
-            TileRange r0 = {0u, 0u, 0u}, r1 = {0u, 0u, 0u};
+            const bool done = !have;
+            const RbPlanRegs cu = nx;
+            const uint32_t slice = slice_nx;
+            if (!done) {
+                w = (long long)__shfl_sync(MC_FULL_MASK, pend, 0);  // the claim issued an item ago
+                have = w < n_items;
+                if (have) { rb_load_plan(plan, (int)(w / split), lane, nx); slice_nx = (uint32_t)(w % split); }
+                if (lane == 0 && have) pend = atomicAdd(ctl, 1u);
+            }
+            uint32_t a0 = 0xffffffffu, a1 = 0xffffffffu, m = 0, self_off = 0, rsrc = 0, rcnt = 0, roff = 0;
             int wrap = 0;
             if (!done) {
-                a0 = cell_start[c];
-                a1 = cell_start[c + 1];
-                if (a0 == a1) continue;
-                const int c2 = c / (g.nc[0] * g.nc[1]);
-                if (c2 < g.row_l0 || c2 >= g.row_l1) continue;  // ghost layer: its atoms carry no rows
-                TilePlan P;
-                tile_plan(g, cell_start, c, a0, lane, P);
-                r0 = P.r0; r1 = P.r1; m = P.m; self_off = P.self_off; wrap = P.wrap;
-                if (lane == 0) {
-                    if (m > *reinterpret_cast<volatile uint32_t *>(ctl + 2)) atomicMax(ctl + 2, m);
-                    if (a1 - a0 > *reinterpret_cast<volatile uint32_t *>(ctl + 5)) atomicMax(ctl + 5, a1 - a0);
-                }
-                if (((m + 31u) & ~31u) > tile_cap) {
+                if (cu.flags & 0x100u) continue;  // empty cell / ghost layer
+                if (((cu.m + 31u) & ~31u) > tile_cap) {  // does not fit: the host enlarges the tile (or falls back)
                     if (lane == 0) ctl[3] = 1u;
                     continue;
                 }
+                a0 = cu.a0; a1 = cu.a1; m = cu.m; self_off = cu.self_off; wrap = (int)(cu.flags & 0xffu);
+                rsrc = cu.src; rcnt = cu.cnt; roff = cu.off;
             }
-            const int s = it % n_stages;
-            mbar_wait(&empty_bar[s], ((it / n_stages) & 1) ^ 1);
+            mbar_wait_sleep(&empty_bar[s], ph);
             float4 *tile = reinterpret_cast<float4 *>(smem_raw + (size_t)s * stage_bytes);
             uint32_t *tile_slot = reinterpret_cast<uint32_t *>(tile + tile_cap);
             if (lane == 0) {
                 meta[s].m = m; meta[s].a0 = a0; meta[s].a1 = a1; meta[s].wrap = wrap; meta[s].self_off = self_off;
-                meta[s].slice = done ? 0u : (uint32_t)(w % split);
+                meta[s].slice = slice;
             }
-            for (int src_lane = 0; src_lane < 9; ++src_lane) {
-                const uint32_t s0 = __shfl_sync(MC_FULL_MASK, r0.src, src_lane), n0 = __shfl_sync(MC_FULL_MASK, r0.cnt, src_lane),
-                               o0 = __shfl_sync(MC_FULL_MASK, r0.off, src_lane), s1 = __shfl_sync(MC_FULL_MASK, r1.src, src_lane),
-                               n1 = __shfl_sync(MC_FULL_MASK, r1.cnt, src_lane), o1 = __shfl_sync(MC_FULL_MASK, r1.off, src_lane);
+            // slot ids of the staged atoms (lanes 0..17 own a range each; every lane helps to write them)
+            for (int src_lane = 0; src_lane < 18; ++src_lane) {
+                const uint32_t n0 = __shfl_sync(MC_FULL_MASK, rcnt, src_lane);
+                if (n0 == 0u) continue;  // warp-uniform
+                const uint32_t s0 = __shfl_sync(MC_FULL_MASK, rsrc, src_lane), o0 = __shfl_sync(MC_FULL_MASK, roff, src_lane);
                 for (uint32_t t = lane; t < n0; t += 32) tile_slot[o0 + t] = s0 + t;
-                for (uint32_t t = lane; t < n1; t += 32) tile_slot[o1 + t] = s1 + t;
             }
             {
                 const float qnan = __int_as_float(0x7fffffff);
@@ -690,13 +782,10 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) row
                 for (uint32_t t = m + lane; t < pend; t += 32) tile[t] = make_float4(qnan, qnan, qnan, 0.f);
             }
             __syncwarp();
-            if (lane == 0) mbar_expect_tx(&full_bar[s], m * (uint32_t)sizeof(float4));
+            if (lane == 0) mbar_expect_tx(&full_bar[s], m * (uint32_t)sizeof(float4));  // release: meta + slots visible
             __syncwarp();
-            if (lane < 9) {
-                if (r0.cnt) tma_bulk_g2s(tile + r0.off, xyzq + r0.src, r0.cnt * (uint32_t)sizeof(float4), &full_bar[s]);
-                if (r1.cnt) tma_bulk_g2s(tile + r1.off, xyzq + r1.src, r1.cnt * (uint32_t)sizeof(float4), &full_bar[s]);
-            }
-            ++it;
+            if (rcnt) tma_bulk_g2s(tile + roff, xyzq + rsrc, rcnt * (uint32_t)sizeof(float4), &full_bar[s]);
+            if (++s == n_stages) { s = 0; ph ^= 1u; }
             if (done) break;
         }
     } else {
@@ -704,31 +793,36 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) row
         const int cw = warp - 1;
         uint16_t *stage = reinterpret_cast<uint16_t *>(smem_raw + (size_t)n_stages * stage_bytes) + (size_t)cw * RB_A * stage_cap;
         uint32_t rot = 0;  // quads dealt so far (mod TILE_WARPS): the same number on every warp
-        for (uint32_t it = 0;; ++it) {
-            const int s = it % n_stages;
-            mbar_wait(&full_bar[s], (it / n_stages) & 1);
+        int s = 0;
+        uint32_t ph = 0;
+        for (;;) {
+            mbar_wait_sleep(&full_bar[s], ph);
             const StageMeta M = meta[s];
             if (M.a0 == 0xffffffffu) break;
             const float4 *tile = reinterpret_cast<const float4 *>(smem_raw + (size_t)s * stage_bytes);
             const uint32_t *tile_slot = reinterpret_cast<const uint32_t *>(tile + tile_cap);
             const uint32_t m_pad = (M.m + 31u) & ~31u;
-            const uint32_t n_at = min(M.a1, (uint32_t)max(n_rows, 0)) > M.a0 ? min(M.a1, (uint32_t)max(n_rows, 0)) - M.a0 : 0u;
+            const uint32_t lim = min(M.a1, (uint32_t)max(n_rows, 0));
+            const uint32_t n_at = lim > M.a0 ? lim - M.a0 : 0u;
             const uint32_t n_quads_cell = (n_at + RB_A - 1) / RB_A;
             // this item's quads: q = slice, slice + split, ...
-            const uint32_t nq = n_quads_cell > M.slice ? (n_quads_cell - M.slice + (uint32_t)split - 1u) / (uint32_t)split : 0u;
-            for (uint32_t j = ((uint32_t)cw + TILE_WARPS - rot) % TILE_WARPS; j < nq; j += TILE_WARPS) {
+            uint32_t nq = n_quads_cell;
+            if (split > 1) nq = n_quads_cell > M.slice ? (n_quads_cell - M.slice + (uint32_t)split - 1u) / (uint32_t)split : 0u;
+            for (uint32_t j = ((uint32_t)cw - rot) & (TILE_WARPS - 1); j < nq; j += TILE_WARPS) {
                 const uint32_t i0 = M.a0 + (M.slice + j * (uint32_t)split) * RB_A;
 #define MC_RBQ(W_) rb_quad<W_>(tile, tile_slot, M, m_pad, i0, n_rows, g, rl2, orig, excl_start, excl_idx, stage, stage_cap, nbr_count, \
                                nbr_start, nbr_list, list_cap, ctl, lane)
                 if (M.wrap == 0) MC_RBQ(0); else if (M.wrap == 1) MC_RBQ(1); else MC_RBQ(2);
 #undef MC_RBQ
             }
-            rot = (rot + nq) % TILE_WARPS;
+            rot = (rot + nq) & (TILE_WARPS - 1);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (++s == n_stages) { s = 0; ph ^= 1u; }
         }
     }
 }
+static_assert((TILE_WARPS & (TILE_WARPS - 1)) == 0, "the quad deal masks with TILE_WARPS - 1");
 
 // Compact rows (tile-local 16-bit indices) -> rows of global slots, same nbr_start / nbr_count.  Off the hot path: only
 // mc_get_neighbors, the virial and the between-molecules energy read global-slot rows.  One CTA per cell at a time.
@@ -777,7 +871,8 @@ cudaError_t tile_sweep_prepare() {
 #define MC_TB_ATTR(I, P) if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_build_kernel<I, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     MC_TB_ATTR(uint32_t, false) MC_TB_ATTR(uint32_t, true) MC_TB_ATTR(uint16_t, false) MC_TB_ATTR(uint16_t, true)
 #undef MC_TB_ATTR
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_build_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_build_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     return e;
 }
 
@@ -805,37 +900,46 @@ static void launch_tile_build_t(int n_rows, long long items, int split, int n_sm
 // rows_build_kernel: tiles in flight and staged entries per row from what fits.  Three tiles in flight while the CTA stays
 // small enough for three CTAs per SM, else two, else one; rows are staged when the longest row of the previous build (+ 25 %)
 // fits next to the tiles, otherwise (first build of a system, very dense systems) every row takes the two-sweep path.
-static void launch_rows_build(int n_rows, long long items, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
+static void launch_rows_build(int n_rows, int grid_cells, long long items, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
                               const GridParams *g, float rl2, const int *orig, const int32_t *excl_start, const int32_t *excl_idx,
                               uint32_t *nbr_count, uint32_t *nbr_start, uint32_t *nbr_list, uint32_t list_cap, uint32_t tile_cap,
-                              uint32_t row_hint, uint32_t *ctl, cudaStream_t st) {
+                              uint32_t row_hint, uint32_t *plan, uint32_t *ctl, cudaStream_t st, int min_blocks) {
     const size_t budget = 200u * 1024u, per_tile = (size_t)tile_cap * 20u;
     uint32_t stage_cap = row_hint ? ((row_hint + row_hint / 4u + 47u) & ~31u) : 0u;
     size_t staging = (size_t)TILE_WARPS * RB_A * stage_cap * sizeof(uint16_t);
     if (per_tile + staging > budget) { stage_cap = 0u; staging = 0; }
     int n_stages = 1;
-    if (3 * per_tile + staging <= 72u * 1024u) n_stages = 3;
+    const size_t per_cta = min_blocks == 2 ? 110u * 1024u : 72u * 1024u;  // shared memory that keeps min_blocks CTAs on an SM
+    if (4 * per_tile + staging <= per_cta) n_stages = 4;
+    else if (3 * per_tile + staging <= per_cta) n_stages = 3;
     else if (2 * per_tile + staging <= budget) n_stages = 2;
     const size_t smem = (size_t)n_stages * per_tile + staging;
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_build_kernel, (TILE_WARPS + 1) * 32, smem);
-    if (per_sm < 1) per_sm = 1;
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, (long long)n_sms * per_sm));
     cudaMemsetAsync(ctl, 0, 8 * sizeof(uint32_t), st);
-    MC_LAUNCH(rows_build_kernel, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, cell_start, g, rl2, orig, excl_start, excl_idx,
-              nbr_count, nbr_start, nbr_list, list_cap, tile_cap, stage_cap, split, n_stages, ctl);
+    MC_LAUNCH(rows_plan_kernel, div_up((size_t)grid_cells * 32, 256), 256, 0, st, cell_start, g, plan, ctl);
+#define MC_RB_GO(MINB_) do { \
+        int per_sm = 1; \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_build_kernel<MINB_>, (TILE_WARPS + 1) * 32, smem); \
+        if (per_sm < 1) per_sm = 1; \
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, (long long)n_sms * per_sm)); \
+        MC_LAUNCH(rows_build_kernel<MINB_>, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, plan, g, rl2, orig, excl_start, excl_idx, \
+                  nbr_count, nbr_start, nbr_list, list_cap, tile_cap, stage_cap, split, n_stages, ctl); \
+    } while (0)
+    if (min_blocks == 2) MC_RB_GO(2); else MC_RB_GO(3);
+#undef MC_RB_GO
 }
+
+size_t rows_plan_words(int grid_cells) { return (size_t)grid_cells * RB_PLAN_WORDS; }
 
 void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
                        const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
                        const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, void *nbr_list, bool compact, bool partition,
                        uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches, int variant,
-                       uint32_t row_hint) {
+                       uint32_t row_hint, uint32_t *plan, int variant_min_blocks) {
     const long long items = (long long)grid_cells * split;
-    if (variant == 2 && !compact && !partition) {
-        launch_rows_build(n_rows, items, split, n_sms, xyzq, cell_start, g, rl2, orig, excl_start, excl_idx, nbr_count, nbr_start,
-                          static_cast<uint32_t *>(nbr_list), list_cap, tile_cap, row_hint, ctl, st);
-        *launches += 1;
+    if (variant == 2 && !compact && !partition && plan) {
+        launch_rows_build(n_rows, grid_cells, items, split, n_sms, xyzq, cell_start, g, rl2, orig, excl_start, excl_idx, nbr_count, nbr_start,
+                          static_cast<uint32_t *>(nbr_list), list_cap, tile_cap, row_hint, plan, ctl, st, variant_min_blocks);
+        *launches += 2;
         return;
     }
 #define MC_TB_GO(I, P) launch_tile_build_t<I, P>(n_rows, items, split, n_sms, xyzq, cell_start, g, rl2, rc2_inner, orig, excl_start, excl_idx, \

@@ -37,6 +37,7 @@ def _run_with_changing_ext(Engine, w, defer, n_calls, steps_per_call, poke):
     reference's alignment loop does, src/mol_alignment.rs:318-353).  `poke` = observers / setters thrown in on the way."""
     n = len(w["xyzq"])
     e = Engine.from_workload(w)
+    e.set_option("fused_steps", 0)  # the per-launch path with and without the deferral is what is compared bit for bit here
     e.set_option("defer_tail", 1 if defer else 0)
     rng = np.random.default_rng(77)
     seen = []
@@ -101,11 +102,11 @@ def test_pipelined_external_forces_are_invisible_through_the_abi(steps_per_call,
         assert ok, (worst, scale)
 
 
-@pytest.mark.parametrize("case", ["globule", "bonded_globule", "hot_fluid", "odd_sizes"])
+@pytest.mark.parametrize("case", ["globule", "bonded_globule", "hot_fluid", "cold_fluid", "odd_sizes"])
 def test_fused_multi_step_kernel_equals_the_per_launch_path(case, Engine, oracle):
-    """Small plain-NVE systems take all steps of a call in one cooperative launch (md_fused.cu, option fused_steps, the
+    """Small plain-NVE systems take all steps of a call in one cooperative launch (md_fused.cu, options fused_steps / fused_brute, the
     GUI's ten-steps-per-frame path of reference src/md/mod.rs:45,737-749).  Same arithmetic as the per-launch path: with no
-    rebuild inside the run positions, velocities and forces are bit-identical; with rebuilds (the fused kernel uses the
+    rebuild inside the run and the same lanes per row positions, velocities and forces are bit-identical; with rebuilds (the fused kernel uses the
     synchronous displacement criterion, the per-launch path the look-ahead one: lists are rebuilt at different steps and rows
     change their summation order) both follow the oracle's trajectory.  System sizes that leave the last warp of the row
     loop partly empty are part of the sweep (the first hardware run of this kernel hung on exactly that)."""
@@ -115,40 +116,50 @@ def test_fused_multi_step_kernel_equals_the_per_launch_path(case, Engine, oracle
         ws, bonded, n_calls, k = [W.bonded_globule()], True, 3, 4
     elif case == "hot_fluid":
         ws, bonded, n_calls, k = [dict(W.lj_fluid(m=12, temp_k=400.0), skin=0.6)], False, 4, 15
+    elif case == "cold_fluid":  # no rebuild inside the run: the host's rows inside the fused kernel give the per-launch path's bits
+        ws, bonded, n_calls, k = [W.lj_fluid(m=10)], False, 3, 10
     else:
         ws, bonded, n_calls, k = [W.globule(n, seed=300 + n) for n in (1, 2, 3, 5, 31, 33, 127, 257)], False, 2, 3
     for w in ws:
         n = len(w["xyzq"])
         runs = []
-        for fused in (1, 0):
+        for fused, brute in ((1, 0), (0, 0), (1, 1)):  # the host's rows inside the fused kernel / per launch / the kernel's own list
             e = Engine.from_workload(w, bonded=bonded)
             e.set_option("fused_steps", fused)
+            e.set_option("fused_brute", brute)
+            if case == "cold_fluid":
+                e.set_option("fused_lanes", 8)  # the lane count of the per-launch pair kernel: same summation order
             ext = np.zeros((n, 3), np.float32)
             ext[::3, 0] = 1.5
             for c in range(n_calls):
                 e.step(w["dt"], k, ext_forces=ext if c == 1 else None)
             runs.append(dict(x=e.positions(), v=e.velocities(), f=e.forces(), st=e.stats()))
             e.close()
-        a, b = runs
-        assert a["st"]["n_steps"] == b["st"]["n_steps"] == n_calls * k
+        a, b, c = runs
+        assert a["st"]["n_steps"] == b["st"]["n_steps"] == c["st"]["n_steps"] == n_calls * k
         # one launch per call (+ what a rebuild inside the call adds) against two and more per step
         import os
         if not os.environ.get("MOLCHANICA_MD_LIB"):  # (the host build of the library has no cooperative launch: both runs are per-launch there)
             assert a["st"]["n_kernel_launches"] <= b["st"]["n_kernel_launches"] - n_calls * (k - 1)  # (list builds are in both counts)
-        if a["st"]["n_rebuilds"] == 1 and b["st"]["n_rebuilds"] == 1:
+            assert c["st"]["n_kernel_launches"] <= n_calls + 4  # one launch per call (+ the reads of positions, velocities, forces), no list build
+        if case == "cold_fluid" and not os.environ.get("MOLCHANICA_MD_LIB"):
+            assert a["st"]["n_rebuilds"] == 1 and b["st"]["n_rebuilds"] == 1
             assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["v"], b["v"]) and np.array_equal(a["f"][:, :3], b["f"][:, :3])
         if case == "hot_fluid":
             assert a["st"]["n_rebuilds"] >= 3
         if not bonded and case != "odd_sizes":
             cur = dict(xyzq=w["xyzq"], vel=w["vel"])  # replay the calls on the oracle (the second one carries external forces)
-            for c in range(n_calls):
-                cur = oracle.md_run(w, k, precision=64, xyzq=cur["xyzq"], vel=cur["vel"], ext_force=ext if c == 1 else None)
-            for r in (a, b):
+            for call in range(n_calls):
+                cur = oracle.md_run(w, k, precision=64, xyzq=cur["xyzq"], vel=cur["vel"], ext_force=ext if call == 1 else None)
+            for r in (a, b, c):
                 ok, worst, scale = trajectory_close(r["x"], cur["xyzq"], w["xyzq"], w["box_ext"] if w["periodic"] else None)
                 assert ok, (case, worst, scale)
         else:
-            ok, worst, scale = trajectory_close(a["x"], b["x"], w["xyzq"], w["box_ext"] if w["periodic"] else None)
-            assert ok, (case, n, worst, scale)
+            for r in (b, c):
+                ok, worst, scale = trajectory_close(a["x"], r["x"], w["xyzq"], w["box_ext"] if w["periodic"] else None)
+                assert ok, (case, n, worst, scale)
+        if case == "hot_fluid" and not os.environ.get("MOLCHANICA_MD_LIB"):
+            assert c["st"]["n_rebuilds"] >= 3  # rebuilt inside the launches
 
 
 def _pair_virial64(w, nbr, coul_mode):
