@@ -399,6 +399,7 @@ def main():
         pos = [torch.empty((cap, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
         ids = torch.empty((cap,), dtype=torch.int32).pin_memory()
         ext_p = C.c_void_p(ext.data_ptr())
+        ids_p = C.c_void_p(ids.data_ptr()) if world > 1 else None
         n_out, epoch = C.c_int64(0), C.c_int64(0)
         seen_epoch = -1
         d2h = []
@@ -410,16 +411,14 @@ def main():
             if trace is not None:
                 return one_traced(k)
             e.step_raw(DT_PS, 1, ext_p)
-            # positions as packed float3 (Snapshot.atom_posits); a decomposed rank's ids only when its layout changed
-            e._chk(e._L.mc_snapshot_begin_xyz(e._h, C.c_void_p(pos[k & 1].data_ptr()), None, C.byref(n_out), C.byref(epoch)))
+            # positions as packed float3 (Snapshot.atom_posits); a decomposed rank's ids travel only when its layout changed
+            # (*layout_epoch is in/out: the epoch whose ids this loop already holds)
+            epoch.value = seen_epoch
+            e._chk(e._L.mc_snapshot_begin_xyz(e._h, C.c_void_p(pos[k & 1].data_ptr()), ids_p, C.byref(n_out), C.byref(epoch)))
             b = int(n_out.value) * 12
             if world > 1 and epoch.value != seen_epoch:
-                # a rebuild happened in this step: fetch the new ids once (the snapshot just begun carries positions only)
-                e._chk(e._L.mc_snapshot_wait(e._h))
-                e._chk(e._L.mc_snapshot_begin_xyz(e._h, C.c_void_p(pos[k & 1].data_ptr()), C.c_void_p(ids.data_ptr()), C.byref(n_out),
-                                                  C.byref(epoch)))
                 seen_epoch = epoch.value
-                b += int(n_out.value) * 16
+                b += int(n_out.value) * 4
             d2h.append(b)
             if k > 0:
                 e._chk(e._L.mc_snapshot_wait(e._h))
@@ -429,15 +428,13 @@ def main():
             t0 = time.perf_counter()
             e.step_raw(DT_PS, 1, ext_p)
             t1 = time.perf_counter()
-            e._chk(e._L.mc_snapshot_begin_xyz(e._h, C.c_void_p(pos[k & 1].data_ptr()), None, C.byref(n_out), C.byref(epoch)))
+            epoch.value = seen_epoch
+            e._chk(e._L.mc_snapshot_begin_xyz(e._h, C.c_void_p(pos[k & 1].data_ptr()), ids_p, C.byref(n_out), C.byref(epoch)))
             t2 = time.perf_counter()
             b = int(n_out.value) * 12
             if world > 1 and epoch.value != seen_epoch:
-                e._chk(e._L.mc_snapshot_wait(e._h))
-                e._chk(e._L.mc_snapshot_begin_xyz(e._h, C.c_void_p(pos[k & 1].data_ptr()), C.c_void_p(ids.data_ptr()), C.byref(n_out),
-                                                  C.byref(epoch)))
                 seen_epoch = epoch.value
-                b += int(n_out.value) * 16
+                b += int(n_out.value) * 4
             t3 = time.perf_counter()
             d2h.append(b)
             if k > 0:

@@ -277,8 +277,9 @@ int mc_get_energy_between_mols(mc_ctx *ctx, double *out);
  * ids in out_ids (both buffers must hold the rank's capacity, see mc_comm_counts). */
 int mc_snapshot_begin(mc_ctx *ctx, mc_float4 *out_positions, int32_t *out_ids, int64_t *n_out);
 /* The same hand-off as packed x, y, z (Snapshot.atom_posits: Vec<Vec3F32>, src/md/trajectory.rs:160-204): 3 floats per atom.
- * *layout_epoch (may be NULL) counts the list builds: the ids a decomposed rank returns only change when it does, so a
- * caller that already holds the ids of this epoch passes out_ids = NULL and saves their copy. */
+ * *layout_epoch (may be NULL) counts the list builds: the ids a decomposed rank returns only change when it does.  It is read
+ * and written: on entry the epoch whose ids the caller already holds (-1: none) -- out_ids is then only filled, and the ids
+ * only travel, when the layout is another one -- on return the epoch of this snapshot.  (NULL: ids whenever out_ids is given.) */
 int mc_snapshot_begin_xyz(mc_ctx *ctx, float *out_xyz, int32_t *out_ids, int64_t *n_out, int64_t *layout_epoch);
 /* The same with velocities ({vx, vy, vz, 1/m}; Snapshot.atom_velocities, src/md/trajectory.rs:160-204).  Velocities are
  * only final once the step a pipelined mc_step may have left open is closed, so this call finishes it first. */

@@ -135,7 +135,10 @@ extern "C" int mc_destroy(mc_ctx *c) {
         static const char *nm[8] = {"upload+setup", "close_tail/forces", "wait+allgather", "step loop", "flags", "sync", "after", ""};
         fprintf(stderr, "[mc_step trace, device %d, %lld calls] ms per call:", c->device, (long long)c->trace_calls);
         for (int k = 0; k < 7; ++k) fprintf(stderr, " %s %.4f", nm[k], c->trace_t[k] / (double)c->trace_calls * 1e3);
-        fprintf(stderr, "\n");
+        fprintf(stderr, " | device ms per call: upload %.4f tail(forces+half kick) %.4f all-gather %.4f kick+drift %.4f\n",
+                c->trace_dev[0] / (double)c->trace_calls, c->trace_dev[1] / (double)c->trace_calls, c->trace_dev[2] / (double)c->trace_calls,
+                c->trace_dev[3] / (double)c->trace_calls);
+        for (int k = 0; k < 8; ++k) if (c->trace_ev[k]) cudaEventDestroy(c->trace_ev[k]);
     }
     comm_destroy(c);
     pme_release(&c->pme);
@@ -145,6 +148,7 @@ extern "C" int mc_destroy(mc_ctx *c) {
         cudaEventDestroy(c->ev_flag[0]); cudaEventDestroy(c->ev_flag[1]);
     }
     if (c->st_up) { cudaStreamSynchronize(c->st_up); cudaEventDestroy(c->ev_up); cudaStreamDestroy(c->st_up); }
+    if (c->ev_drift) cudaEventDestroy(c->ev_drift);
     if (c->st_copy) {
         cudaStreamSynchronize(c->st_copy);
         for (int b = 0; b < 2; ++b) { cudaEventDestroy(c->ev_snap_staged[b]); cudaEventDestroy(c->ev_snap_done[b]); }
@@ -581,6 +585,10 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         MC_REQUIRE(c, value >= 0.0, "mc_set_option: row_stage_limit >= 0 (0 = no limit)");
         c->row_stage_limit = (uint32_t)value;
         c->list_valid = false;
+    } else if (k == "early_tail") {
+        c->early_tail = value != 0.0;
+    } else if (k == "lazy_sync") {
+        c->lazy_sync = value != 0.0;
     } else if (k == "fused_lanes") {
         MC_REQUIRE(c, value == 0.0 || value == 8.0 || value == 16.0 || value == 32.0, "mc_set_option: fused_lanes is 0 (automatic), 8, 16 or 32");
         c->fused_lanes = (int)value;
@@ -771,6 +779,7 @@ int engine_build_rows(mc_ctx *c) {
     c->forces_valid = false;
     c->n_rebuilds++;
     c->tail_use_split = false;  // a halo descriptor kept for a deferred force evaluation describes the old layout
+    c->drift_event_valid = false;  // the atoms sit in other arrays now, written by kernels behind that event
     c->steps_since_build = 0;
     c->pairs_dirty = true;
     return MC_OK;
@@ -911,7 +920,15 @@ static int ensure_ready(mc_ctx *c, const char *who) {
 // (see there).  Every entry point that observes or changes anything but positions closes them first.
 // Closes the step a pipelined mc_step left open: (scheduled rebuild of a decomposed run,) force evaluation of the positions
 // reached, second half kick with THAT call's external forces.  Nothing here synchronises.
-static int close_tail(mc_ctx *c) {
+static int collect_pending_epilogue(mc_ctx *c, int *warn);
+
+// First half of closing the open step: (rebuild when one is due,) force evaluation of the positions reached.  A pipelined call
+// launches it itself right before it returns (option early_tail), so that it runs while the caller is away -- reading the
+// snapshot, preparing the next array -- instead of waiting for the next call to launch it; whoever closes the step finds the
+// forces valid and goes straight to the half kick (and must not rebuild in between: the forces are in the order they were
+// computed in).
+static int tail_forces(mc_ctx *c) {
+    if (c->forces_valid && !c->tail_rebuild) return MC_OK;
     int rc;
     bool fresh_ghosts = false;
     if (c->tail_rebuild) {
@@ -927,6 +944,12 @@ static int close_tail(mc_ctx *c) {
         if ((rc = engine_launch_forces(c, false, use_split ? &c->tail_split : nullptr)) != MC_OK) return rc;
     }
     c->tail_use_split = false;
+    return MC_OK;
+}
+
+static int close_tail(mc_ctx *c) {
+    int rc = tail_forces(c);
+    if (rc != MC_OK) return rc;
     const size_t r0 = (size_t)c->row0;
     launch_kick_drift((int)c->n_rows_sorted(), c->xyzq[c->cur].p + r0, c->vel[c->cur].p + r0, c->force.p + r0, c->tail_ext,
                       c->orig[c->cur].p + r0, c->flags[c->cur].p + r0, c->xref.p + r0, 0.5f * c->tail_dt, 0.f, 0.f, 0.f,
@@ -938,7 +961,9 @@ static int close_tail(mc_ctx *c) {
 int engine_flush_tail(mc_ctx *c) {
     if (!c->tail_pending) return MC_OK;
     cudaSetDevice(c->device);
-    int rc = close_tail(c);
+    int rc = collect_pending_epilogue(c, nullptr);  // (a pipelined call returns before its kernels have finished)
+    if (rc != MC_OK) return rc;
+    rc = close_tail(c);
     if (rc != MC_OK) return rc;
     MC_CUDA(c, cudaStreamSynchronize(c->st));
     return MC_OK;
@@ -974,6 +999,78 @@ static int wait_flag_tag(mc_ctx *c, volatile int *word, int tag) {
 
 static int apply_barostat(mc_ctx *c, float dt);
 
+// What follows the one synchronisation of an mc_step call: flag words, timing, warnings.  Run at the end of the call, or -- for a
+// pipelined call that returned early (StepEpilogue::pending) -- by the next call / by whoever closes the open step.
+static int step_epilogue(mc_ctx *c, const StepEpilogue &E) {
+    cudaStream_t st = c->st;
+    int *h_flag = reinterpret_cast<int *>(c->h_pinned) + 8;
+    int *h_agree = reinterpret_cast<int *>(c->h_pinned) + 12;
+    const int n_steps = E.n_steps;
+    MC_CUDA(c, cudaStreamSynchronize(st));
+    if (E.trace_dev) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, c->trace_ev[0], c->trace_ev[1]) == cudaSuccess) c->trace_dev[0] += t;
+        if (cudaEventElapsedTime(&t, c->trace_ev[2], c->trace_ev[3]) == cudaSuccess) c->trace_dev[1] += t;
+        if (cudaEventElapsedTime(&t, c->trace_ev[4], c->trace_ev[5]) == cudaSuccess) c->trace_dev[2] += t;
+        if (cudaEventElapsedTime(&t, c->trace_ev[5], c->ev_step_b) == cudaSuccess) c->trace_dev[3] += t;
+    }
+    float ms = 0.f;
+    MC_CUDA(c, cudaEventElapsedTime(&ms, c->ev_step_a, c->ev_step_b));
+    c->last_step_ms = ms;
+    // the flag of the last drift has not been acted upon: make the next evaluation rebuild first
+    if (E.pipelined && n_steps > 0 && !E.skip_prev && (h_flag[(n_steps - 1) & 1] & 3) != 0) c->list_valid = false;
+    if (E.pipelined && n_steps > 0 && (h_flag[(n_steps - 1) & 1] & 2))
+        return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
+    bool stale_list = false;
+    if (E.flags_arrive) {
+        // the previous call's flags, the same words on every rank: maximum over the ranks, then as below
+        h_agree[0] = h_agree[1] = 0;
+        for (int r = 0; r < E.n_ranks_f; ++r) {
+            h_agree[0] = std::max(h_agree[0], c->h_flags_all[2 * r]);
+            h_agree[1] |= c->h_flags_all[2 * r + 1];
+        }
+        // (a rebuild between the two calls has cleared the displacement word: nothing to report then)
+    }
+    if (E.check_flag || E.flags_arrive) {
+        if (h_agree[1] & MC_HALO_ERR_TIMEOUT)
+            return fail(c, MC_E_COMM, "mc_step: a neighbour rank did not signal its halo push within 2 s (peer died or ranks out of step)");
+        if (h_agree[0] & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
+        // An atom moved more than skin/2 between two builds: the schedule was too long for this system (sudden heating, a
+        // caller-chosen rebuild_every).  The list is rebuilt before the next evaluation -- on every rank of a decomposed
+        // run, which all see the same reduced flag -- the adaptive interval is halved, and the caller is told
+        // (MC_W_STALE_LIST: pairs inside the cutoff may have been missing from the last steps' forces).
+        if (h_agree[0] != 0) {
+            c->n_list_violations++;
+            c->list_valid = false;
+            stale_list = true;
+            if (c->comm_active) comm_shrink_interval(c);
+        }
+    }
+    if (c->n_hclusters > 0 && n_steps > 0) {
+        int bad = 0;
+        MC_CUDA(c, cudaMemcpy(&bad, c->shake_fail.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bad) {
+            MC_CUDA(c, cudaMemset(c->shake_fail.p, 0, sizeof(int)));
+            return fail(c, MC_E_INVALID, "mc_step: SHAKE did not converge for " + std::to_string(bad) + " hydrogen-bond cluster steps (time step too long?)");
+        }
+    }
+    c->collect_timings();
+    if (stale_list) {
+        c->err = "mc_step: an atom moved more than skin/2 between two list builds; the list is rebuilt before the next evaluation";
+        return MC_W_STALE_LIST;
+    }
+    return MC_OK;
+}
+
+// the epilogue a pipelined call left behind (errors are returned; a warning is kept in *warn)
+static int collect_pending_epilogue(mc_ctx *c, int *warn) {
+    if (!c->epi.pending) return MC_OK;
+    c->epi.pending = false;
+    const int rc = step_epilogue(c, c->epi);
+    if (rc > 0) { if (warn) *warn = rc; return MC_OK; }
+    return rc;
+}
+
 extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces) {
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);
@@ -993,7 +1090,11 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
             t = now;
         }
     } trc{c, c->trace_step && n_steps == 1 && ext_forces != nullptr /* the per-step calls of an end-to-end loop */, std::chrono::steady_clock::now()};
-    if (trc.on) c->trace_calls++;
+    if (trc.on) {
+        c->trace_calls++;
+        if (!c->trace_ev[0]) for (int k = 0; k < 8; ++k) cudaEventCreate(&c->trace_ev[k]);
+    }
+    const bool trace_dev = trc.on && c->trace_ev[7] != nullptr;
     // decomposed runs rebuild on a schedule every rank derives from the same numbers (no per-step agreement)
     const bool pipelined = !c->comm_active && c->rebuild_every <= 0 && !c->sync_rebuild;
     // External forces are the one per-call input of a step (MdState::step(dev, dt, Some(forces)), reference
@@ -1037,7 +1138,9 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
                 MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
             }
             upload_guard.s = c->st_up;
+            if (trace_dev) cudaEventRecord(c->trace_ev[0], c->st_up);
             if (cnt) MC_CUDA(c, cudaMemcpyAsync(buf.p + lo, ext_forces + lo, sizeof(float) * cnt, cudaMemcpyHostToDevice, c->st_up));
+            if (trace_dev) cudaEventRecord(c->trace_ev[1], c->st_up);
             MC_CUDA(c, cudaEventRecord(c->ev_up, c->st_up));
             wait_upload = true;
         } else if (cnt) {
@@ -1048,7 +1151,11 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         c->ext_upload_bytes = 0;
     }
     int rc;
+    c->drift_event_valid = false;  // (set again by a pipelined call right after its last drift)
+    int lazy_rc = MC_OK;  // warning of the previous (pipelined) call's epilogue, handed back by this call
+    if ((rc = collect_pending_epilogue(c, &lazy_rc)) != MC_OK) return rc;  // (the upload above is already on its way)
     trc.lap(0);
+    if (trace_dev) cudaEventRecord(c->trace_ev[2], st);
     // Small plain-NVE systems: all n_steps in ONE cooperative launch (md_fused.cu) instead of 2-4 launches + a host poll per
     // step.  Up to md_fused_brute_max_atoms() atoms the kernel keeps a private all-pairs Verlet list and rebuilds it inside the
     // launch: the host's list (sort, cells, tiles) is then not needed for stepping at all.  Larger systems (up to
@@ -1077,7 +1184,9 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         }
     }
     trc.lap(1);
+    if (trace_dev) cudaEventRecord(c->trace_ev[3], st);
     if (wait_upload) MC_CUDA(c, cudaStreamWaitEvent(st, c->ev_up, 0));
+    if (trace_dev) cudaEventRecord(c->trace_ev[4], st);
     // A pipelined call of a decomposed run ends after its drift: the flags of that drift are agreed upon at the NEXT call, where
     // they ride with the all-gather of the external forces (same NCCL launch) instead of costing an all-reduce per call.
     bool flags_arrive = false;
@@ -1095,6 +1204,7 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         }
     }
     trc.lap(2);
+    if (trace_dev) cudaEventRecord(c->trace_ev[5], st);
     const bool fused = fused_ok && (brute || !c->list_compact);
     if (fused) {
         int *h_out = reinterpret_cast<int *>(c->h_pinned) + 16;
@@ -1277,6 +1387,9 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         if (defer && s == n_steps - 1) {
             // last step of a pipelined call: stop after the drift.  Its flag word is read after the final
             // synchronisation below (no rebuild has happened since it was written, so it is never stale).
+            if (!c->ev_drift) MC_CUDA(c, cudaEventCreateWithFlags(&c->ev_drift, cudaEventDisableTiming));
+            MC_CUDA(c, cudaEventRecord(c->ev_drift, st));  // positions final: a snapshot need not queue behind the early force evaluation
+            c->drift_event_valid = true;
             c->tail_rebuild = c->comm_active && c->steps_since_build >= comm_interval(c);
             c->tail_use_split = fused_halo && !c->tail_rebuild;
             c->tail_split = split;
@@ -1364,54 +1477,28 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     }
     MC_CUDA(c, cudaGetLastError());
     trc.lap(4);
-    MC_CUDA(c, cudaStreamSynchronize(st));
+    StepEpilogue E;
+    E.pipelined = pipelined; E.n_steps = n_steps; E.skip_prev = skip_prev; E.check_flag = check_flag; E.flags_arrive = flags_arrive;
+    E.n_ranks_f = n_ranks_f; E.trace_dev = trace_dev && defer;
+    if (defer && c->lazy_sync) {
+        // A pipelined call has nothing to hand back but positions, and those are read in stream order (snapshots, mc_get_positions):
+        // it returns as soon as the caller's array is free again (UploadGuard) and leaves its kernels running.  What the
+        // synchronisation used to deliver -- the flag words, the timing -- is collected when the next call (or whoever closes the
+        // open step) comes back: the host side of a per-step loop then runs under the kernels instead of between them.
+        E.pending = true;
+        c->epi = E;
+        if (c->early_tail) {
+            const int64_t builds = c->n_rebuilds;
+            if ((rc = tail_forces(c)) != MC_OK) return rc;
+            // a rebuild here comes after the drift whose flag word is still to be read: that word refers to the old reference positions
+            if (c->n_rebuilds != builds) c->epi.skip_prev = true;
+        }
+        return lazy_rc;
+    }
+    const int rc_e = step_epilogue(c, E);
     trc.lap(5);
-    float ms = 0.f;
-    MC_CUDA(c, cudaEventElapsedTime(&ms, c->ev_step_a, c->ev_step_b));
-    c->last_step_ms = ms;
-    // the flag of the last drift has not been acted upon: make the next evaluation rebuild first
-    if (pipelined && n_steps > 0 && !skip_prev && (h_flag[(n_steps - 1) & 1] & 3) != 0) c->list_valid = false;
-    if (pipelined && n_steps > 0 && (h_flag[(n_steps - 1) & 1] & 2))
-        return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
-    bool stale_list = false;
-    if (flags_arrive) {
-        // the previous call's flags, the same words on every rank: maximum over the ranks, then as below
-        h_agree[0] = h_agree[1] = 0;
-        for (int r = 0; r < n_ranks_f; ++r) {
-            h_agree[0] = std::max(h_agree[0], c->h_flags_all[2 * r]);
-            h_agree[1] |= c->h_flags_all[2 * r + 1];
-        }
-        // (a rebuild between the two calls has cleared the displacement word: nothing to report then)
-    }
-    if (check_flag || flags_arrive) {
-        if (h_agree[1] & MC_HALO_ERR_TIMEOUT)
-            return fail(c, MC_E_COMM, "mc_step: a neighbour rank did not signal its halo push within 2 s (peer died or ranks out of step)");
-        if (h_agree[0] & 2) return fail(c, MC_E_INVALID, "mc_step: non-finite coordinates (the simulation blew up)");
-        // An atom moved more than skin/2 between two builds: the schedule was too long for this system (sudden heating, a
-        // caller-chosen rebuild_every).  The list is rebuilt before the next evaluation -- on every rank of a decomposed
-        // run, which all see the same reduced flag -- the adaptive interval is halved, and the caller is told
-        // (MC_W_STALE_LIST: pairs inside the cutoff may have been missing from the last steps' forces).
-        if (h_agree[0] != 0) {
-            c->n_list_violations++;
-            c->list_valid = false;
-            stale_list = true;
-            if (c->comm_active) comm_shrink_interval(c);
-        }
-    }
-    if (c->n_hclusters > 0 && n_steps > 0) {
-        int bad = 0;
-        MC_CUDA(c, cudaMemcpy(&bad, c->shake_fail.p, sizeof(int), cudaMemcpyDeviceToHost));
-        if (bad) {
-            MC_CUDA(c, cudaMemset(c->shake_fail.p, 0, sizeof(int)));
-            return fail(c, MC_E_INVALID, "mc_step: SHAKE did not converge for " + std::to_string(bad) + " hydrogen-bond cluster steps (time step too long?)");
-        }
-    }
-    c->collect_timings();
-    if (stale_list) {
-        c->err = "mc_step: an atom moved more than skin/2 between two list builds; the list is rebuilt before the next evaluation";
-        return MC_W_STALE_LIST;
-    }
-    return MC_OK;
+    if (defer && c->early_tail && rc_e >= 0 && (rc = tail_forces(c)) != MC_OK) return rc;
+    return rc_e != MC_OK ? rc_e : lazy_rc;
 }
 
 extern "C" double mc_last_step_ms(mc_ctx *c) { return c ? c->last_step_ms : 0.0; }
@@ -1591,20 +1678,30 @@ extern "C" int mc_snapshot_begin_xyz(mc_ctx *c, float *out_xyz, int32_t *out_ids
     const int64_t rows = c->n_rows_sorted();
     const int64_t n = c->comm_active ? rows : c->n_global;
     if (n_out) *n_out = n;
+    // *layout_epoch on entry: the layout the caller already holds the ids of (they travel only when it is another one)
+    const bool want_ids = out_ids != nullptr && (!layout_epoch || *layout_epoch != c->n_rebuilds);
     if (layout_epoch) *layout_epoch = c->n_rebuilds;
     if (n == 0) return MC_OK;
-    if (c->snap_pending[k]) MC_CUDA(c, cudaStreamWaitEvent(c->st, c->ev_snap_done[k], 0));
-    MC_CUDA(c, c->snap_stage[k].ensure((size_t)n));  // float4 elements: 3n floats fit
+    // A pipelined mc_step that has already launched the open step's force evaluation (early_tail) recorded an event right after
+    // its drift: the staging then runs on the copy stream behind that event instead of queueing behind the force kernel, and
+    // the engine stream waits for the staging before anything may move the atoms again.
+    const bool side = c->tail_pending && c->drift_event_valid && c->forces_valid && !(c->comm_active && c->tail_rebuild);
+    cudaStream_t ss = side ? c->st_copy : c->st;
+    if (side) MC_CUDA(c, cudaStreamWaitEvent(c->st_copy, c->ev_drift, 0));
+    else if (c->snap_pending[k]) MC_CUDA(c, cudaStreamWaitEvent(c->st, c->ev_snap_done[k], 0));
+    // (head-room: a decomposed rank owns a few atoms more or fewer after every rebuild, and growing a buffer means cudaFree)
+    MC_CUDA(c, c->snap_stage[k].ensure((size_t)n + (c->comm_active ? (size_t)n / 8 + 1024 : 0)));  // float4 elements: 3n floats fit
     float *stage = reinterpret_cast<float *>(c->snap_stage[k].p);
-    launch_pack_xyz((int)rows, c->xyzq[c->cur].p + c->row0, c->comm_active ? nullptr : c->orig[c->cur].p + c->row0, stage, c->st, &c->launches);
-    if (c->comm_active && out_ids) {
-        MC_CUDA(c, c->snap_ids[k].ensure((size_t)n));
-        MC_CUDA(c, cudaMemcpyAsync(c->snap_ids[k].p, c->orig[c->cur].p + c->row0, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->st));
+    launch_pack_xyz((int)rows, c->xyzq[c->cur].p + c->row0, c->comm_active ? nullptr : c->orig[c->cur].p + c->row0, stage, ss, &c->launches);
+    if (c->comm_active && want_ids) {
+        MC_CUDA(c, c->snap_ids[k].ensure((size_t)n + (size_t)n / 8 + 1024));
+        MC_CUDA(c, cudaMemcpyAsync(c->snap_ids[k].p, c->orig[c->cur].p + c->row0, sizeof(int) * n, cudaMemcpyDeviceToDevice, ss));
     }
-    MC_CUDA(c, cudaEventRecord(c->ev_snap_staged[k], c->st));
-    MC_CUDA(c, cudaStreamWaitEvent(c->st_copy, c->ev_snap_staged[k], 0));
+    MC_CUDA(c, cudaEventRecord(c->ev_snap_staged[k], ss));
+    if (side) MC_CUDA(c, cudaStreamWaitEvent(c->st, c->ev_snap_staged[k], 0));
+    else MC_CUDA(c, cudaStreamWaitEvent(c->st_copy, c->ev_snap_staged[k], 0));
     MC_CUDA(c, cudaMemcpyAsync(out_xyz, stage, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->st_copy));
-    if (c->comm_active && out_ids) MC_CUDA(c, cudaMemcpyAsync(out_ids, c->snap_ids[k].p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->st_copy));
+    if (c->comm_active && want_ids) MC_CUDA(c, cudaMemcpyAsync(out_ids, c->snap_ids[k].p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->st_copy));
     MC_CUDA(c, cudaEventRecord(c->ev_snap_done[k], c->st_copy));
     c->snap_pending[k] = true;
     return MC_OK;

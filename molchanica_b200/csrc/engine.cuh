@@ -17,7 +17,9 @@ struct DevBuf {
     // grow-only; contents are NOT preserved across a growth
     cudaError_t ensure(size_t want) {
         if (want <= n && p) return cudaSuccess;
-        if (p) cudaFree(p);
+        // a buffer that has to grow a second time gets head-room: sizes that follow the atoms a rank owns drift up and down by a
+        // few atoms per rebuild, and every cudaFree is a device-wide synchronisation (with a collective in flight: milliseconds)
+        if (p) { cudaFree(p); want += want / 8 + 256; }
         p = nullptr;
         n = 0;
         if (want == 0) want = 1;
@@ -44,6 +46,13 @@ struct EventPair {
 struct CommState;  // comm.cu
 struct HaloSplit { int n_first, last_begin; HaloWait wait; };
 
+// what an mc_step call still has to look at once its kernels have finished (engine.cu: step_epilogue)
+struct StepEpilogue {
+    bool pending = false;  // a pipelined call returned without synchronising: the next call / the closer of the open step collects
+    bool pipelined = false, skip_prev = false, check_flag = false, flags_arrive = false, trace_dev = false;
+    int n_steps = 0, n_ranks_f = 1;
+};
+
 struct mc_ctx {
     int device = 0;
     int n_sms = 148;
@@ -52,11 +61,21 @@ struct mc_ctx {
     std::string err;
     void *h_pinned = nullptr;
     int *h_flags_all = nullptr;   // pinned, 2 ints per rank: the flag words that ride with the external-force all-gather of a pipelined decomposed call
+    StepEpilogue epi;
+    cudaEvent_t ev_drift = nullptr;  // recorded right after the last drift of a pipelined call
+    bool drift_event_valid = false;
+    // Two ways to end a pipelined call, measured on B200s (profiles/e2e_r2_options.txt) and left OFF: both lose to the plain
+    // synchronised ending because the per-step loop is bound by its two PCIe transfers, which the plain ending already overlaps
+    // perfectly (the snapshot copy of step k under the upload of step k+1)
+    bool early_tail = false;      // option "early_tail": a pipelined call launches the open step's force evaluation before it returns
+    bool lazy_sync = false;       // option "lazy_sync": pipelined calls (external forces, defer_tail) return without waiting for their kernels
     bool flags_ride = false;      // the previous call was such a call: its flags arrive with this call's all-gather
     // MC_TRACE_STEP=1: host time spent in the phases of mc_step (seconds, summed; printed by mc_destroy) -- a debugging aid
     bool trace_step = false;
     double trace_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t trace_calls = 0;
+    cudaEvent_t trace_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double trace_dev[4] = {0, 0, 0, 0};  // device time of {upload, tail (forces + half kick), all-gather, kick + drift} of the traced calls (ms, summed)
 
     // system
     int64_t n = 0;         // atoms held locally (owned + ghosts)

@@ -246,9 +246,10 @@ class MdEngine:
         self._chk(self._L.mc_snapshot_begin_pv(self._h, _ptr(out_positions), _ptr(out_velocities), _ptr(out_ids), C.byref(n_out)))
         return int(n_out.value)
 
-    def snapshot_begin_xyz(self, out_xyz, out_ids=None):
-        """mc_snapshot_begin_xyz: packed float3 positions; returns (entries, layout epoch)."""
-        n_out, ep = C.c_int64(0), C.c_int64(0)
+    def snapshot_begin_xyz(self, out_xyz, out_ids=None, have_epoch=-1):
+        """mc_snapshot_begin_xyz: packed float3 positions; returns (entries, layout epoch).  have_epoch: the epoch whose ids the
+        caller already holds (out_ids is only filled when the layout is another one)."""
+        n_out, ep = C.c_int64(0), C.c_int64(have_epoch)
         self._chk(self._L.mc_snapshot_begin_xyz(self._h, _ptr(out_xyz), _ptr(out_ids), C.byref(n_out), C.byref(ep)))
         return int(n_out.value), int(ep.value)
 
