@@ -550,6 +550,9 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
     } else if (k == "tile_sweep") {
         c->use_tile = value != 0.0;
         c->list_valid = false;
+    } else if (k == "pair_tile_stages") {
+        MC_REQUIRE(c, value == 0.0 || (value >= 2.0 && value <= 4.0), "mc_set_option: pair_tile_stages is 0 (automatic), 2, 3 or 4");
+        c->pair_tile_stages = (int)value;
     } else if (k == "pair_tile") {
         c->use_pair_tile = value == 0.0 ? 0 : (value == 2.0 ? 2 : 1);
         c->pair_tile_fits = true;
@@ -861,6 +864,7 @@ int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs) {
         T.p = L.p; T.lj_on = L.lj_on; T.coul = L.coul; T.multi = L.multi; T.energy = L.energy; T.force = L.force;
         T.tile_cap = c->tile_max_m;
         T.rows_max_entries = c->rows_max_entries;
+        T.force_stages = c->pair_tile_stages;
         if (hs) T.wait = hs->wait;
         TimedRegion tr(c, c->pair_acc, true);
         launch_pair_tile(T, c->st, &c->launches);

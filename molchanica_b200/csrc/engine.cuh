@@ -111,6 +111,7 @@ struct mc_ctx {
     bool subcell_sort = false;  // Morton sub-cell code in the low sort-key bits (option "subcell_sort")
     bool use_tile = true;      // TMA-staged tile sweep for the list build (neighbor_tile.cu)
     uint32_t tile_cap = 1024;  // tile capacity in atoms, grows on demand
+    int pair_tile_stages = 0;  // option "pair_tile_stages": tiles in flight per CTA of pair_tile.cu (0 = from the shared-memory budget)
     int build_variant = 2;     // option "build_variant": 2 = rows_build_kernel (default), 1 = tile_build_kernel (tile_build.cu)
     uint32_t row_len_hint = 0; // longest row of the last build (0: none yet)
     int rows_min_blocks = 3;   // option "rows_min_blocks"

@@ -54,10 +54,12 @@ struct PairTileLaunch {
     float4 *force;
     uint32_t tile_cap;
     uint32_t rows_max_entries;  // largest row block of a cell
+    int force_stages = 0;       // option pair_tile_stages (0: chosen from the shared-memory budget)
     HaloWait wait{};
 };
 cudaError_t pair_tile_prepare();
-size_t pair_tile_smem(uint32_t tile_cap, uint32_t rows_max_entries, int n_types, bool multi, int *n_stages_out, uint32_t *rows_cap_out);
+size_t pair_tile_smem(uint32_t tile_cap, uint32_t rows_max_entries, int n_types, bool multi, int *n_stages_out, uint32_t *rows_cap_out,
+                      int force_stages = 0);
 void launch_pair_tile(const PairTileLaunch &L, cudaStream_t st, int64_t *launches);
 // per-build table of everything the force kernel's producer needs per cell (plan: n_cells x pair_tile_plan_words() words,
 // rowtab: n_cells x 32 words); ctl[3] is set to 2 when a cell cannot be staged (> 32 atoms, rows not one block, ...)

@@ -392,7 +392,8 @@ cudaError_t pair_tile_prepare() {
 // Shared memory the kernel needs; 0 = this system is not for it (use pair_force.cu): the kernel stages, per cell, the
 // 27-cell tile AND the cell's rows, which must be one block of <= 32 rows (max_cell_atoms) -- LJ-fluid-like systems, ~12 KB
 // of tile + ~5 KB of rows.  Dense / long-cutoff systems (hundreds of atoms per cell, rows of a thousand entries) are not.
-size_t pair_tile_smem(uint32_t tile_cap, uint32_t rows_max_entries, int n_types, bool multi, int *n_stages_out, uint32_t *rows_cap_out) {
+size_t pair_tile_smem(uint32_t tile_cap, uint32_t rows_max_entries, int n_types, bool multi, int *n_stages_out, uint32_t *rows_cap_out,
+                      int force_stages) {
     const size_t tab = multi ? (((size_t)n_types * n_types * sizeof(float2) + 127) & ~(size_t)127) : 0;
     const size_t tile_b = (size_t)tile_cap * (sizeof(float4) + (multi ? sizeof(uint16_t) : 0));
     const uint32_t rows_cap = (rows_max_entries + 7u) & ~7u;
@@ -400,10 +401,13 @@ size_t pair_tile_smem(uint32_t tile_cap, uint32_t rows_max_entries, int n_types,
     if (stage > 40u * 1024u || tab + 2 * stage > 200u * 1024u) return 0;
     // as many stages in flight as keep ~44 KB per CTA (five CTAs per SM), at least two
 #ifdef MC_PT_EXPERIMENT_STAGES
-    const int ns = MC_PT_EXPERIMENT_STAGES;
+    int ns = MC_PT_EXPERIMENT_STAGES;
 #else
-    const int ns = stage * 4 + tab <= 44u * 1024u ? 4 : (stage * 3 + tab <= 44u * 1024u ? 3 : 2);
+    int ns = stage * 4 + tab <= 44u * 1024u ? 4 : (stage * 3 + tab <= 44u * 1024u ? 3 : 2);
 #endif
+    // option pair_tile_stages: measured on C4 (profiles/pair_tile_r2_experiments.txt) three tiles in flight at four CTAs per SM
+    // beat both two tiles at five CTAs and four tiles at three
+    if (force_stages >= 2 && force_stages <= PT_MAX_STAGES && tab + (size_t)force_stages * stage <= 200u * 1024u) ns = force_stages;
     if (n_stages_out) *n_stages_out = ns;
     if (rows_cap_out) *rows_cap_out = rows_cap;
     return tab + (size_t)ns * stage;
@@ -426,7 +430,7 @@ void launch_pair_tile(const PairTileLaunch &L, cudaStream_t st, int64_t *launche
     A.p = L.p; A.lj_on = L.lj_on; A.force = L.force; A.tile_cap = L.tile_cap; A.wait = L.wait;
     int ns = 1;
     uint32_t rows_cap = 0;
-    const size_t smem = pair_tile_smem(L.tile_cap, L.rows_max_entries, L.p.n_types, L.multi, &ns, &rows_cap);
+    const size_t smem = pair_tile_smem(L.tile_cap, L.rows_max_entries, L.p.n_types, L.multi, &ns, &rows_cap, L.force_stages);
     A.n_stages = ns;
     A.rows_cap = rows_cap;
 #define MC_PT_E(M, C) \
