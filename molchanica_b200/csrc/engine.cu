@@ -581,6 +581,9 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
         MC_REQUIRE(c, value == 1.0 || value == 2.0, "mc_set_option: build_variant is 1 (tile_build_kernel) or 2 (rows_build_kernel)");
         c->build_variant = (int)value;
         c->list_valid = false;
+    } else if (k == "rows_interleave") {
+        c->rows_interleave = value != 0.0 ? 1 : 0;
+        c->list_valid = false;
     } else if (k == "rows_min_blocks") {  // register budget of rows_build_kernel: 3 CTAs per SM (72 registers) or 2 (112)
         MC_REQUIRE(c, value == 2.0 || value == 3.0, "mc_set_option: rows_min_blocks is 2 or 3");
         c->rows_min_blocks = (int)value;
@@ -700,6 +703,8 @@ int engine_build_rows(mc_ctx *c) {
     uint32_t *h_ctl = reinterpret_cast<uint32_t *>(c->h_pinned);
     size_t total = 0;
     bool tiled = c->use_tile;
+    bool ilv = false;
+    c->ilv_valid = false;
     const float rc_in = std::max(c->rc_lj, c->rc_q);
     const float rc2_inner = rc_in * rc_in;
     const int grid_cells = c->periodic ? c->h_grid.ncell : (int)c->ncell_cap;
@@ -724,6 +729,13 @@ int engine_build_rows(mc_ctx *c) {
                           (uint32_t)std::min<size_t>(cap_now, 0xffffffffu), tile_cap_now, c->tile_need.p, st, &c->launches,
                           c->build_variant, c->row_stage_limit ? std::min(c->row_len_hint, c->row_stage_limit) : c->row_len_hint,
                           rows_v2 ? c->rows_plan.p : nullptr, c->rows_min_blocks);
+        // quad-interleaved copy for the 8-lane force kernel: its sizes pass rides in front of the build's own host sync
+        // (ctl[7] = entries of the copy), the copy itself follows once the list is known to be complete
+        ilv = !compact && !c->pair_uniform && c->pair_lanes == 8 && c->rows_interleave;
+        if (ilv) {
+            MC_CUDA(c, c->ilv_qbase.ensure((size_t)(n_rows + 3) / 4 + 1));
+            launch_rows_interleave_sizes(n_rows, c->nbr_count.p, c->ilv_qbase.p, c->tile_need.p + 7, st, &c->launches);
+        }
         MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->tile_need.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         MC_CUDA(c, cudaStreamSynchronize(st));
         if (h_ctl[3] != 0) {  // a neighbourhood did not fit the tile
@@ -743,6 +755,11 @@ int engine_build_rows(mc_ctx *c) {
         c->tile_max_m = (h_ctl[2] + 31u) & ~31u;
         c->rows_max_entries = h_ctl[4];
         if (h_ctl[6]) c->row_len_hint = h_ctl[6];  // longest row: sizes the row staging of the next build (rows_build_kernel)
+        if (ilv && (uint64_t)h_ctl[7] + 4096u < 0xffffffffull) {
+            MC_CUDA(c, c->nbr_ilv.ensure((size_t)h_ctl[7] + 64));
+            launch_rows_interleave_copy(n_rows, c->nbr_start.p, c->nbr_count.p, c->nbr_list.p, c->ilv_qbase.p, c->nbr_ilv.p, st, &c->launches);
+            c->ilv_valid = true;
+        }
         // the TMA-staged force kernel wants every cell's rows as one block of <= 32 rows next to the tile in shared memory:
         // a system that is too dense for that (seen only now) is built again with global-slot rows, and stays that way
         if (compact && (h_ctl[5] > 32u || pair_tile_smem(c->tile_max_m, c->rows_max_entries, c->n_types, c->n_types > 1, nullptr, nullptr) == 0)) {
@@ -853,6 +870,7 @@ int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs) {
     L.multi = c->n_types > 1;
     L.lanes = c->pair_lanes;
     L.force = c->force.p;
+    if (c->ilv_valid && c->pair_lanes == 8 && !c->pair_uniform) { L.ilv_qbase = c->ilv_qbase.p; L.ilv_list = c->nbr_ilv.p; }
     if (c->list_compact) {
         // TMA-staged kernel over the compact rows (pair_tile.cu); a decomposed rank hands it the ready flags to wait on
         PairTileLaunch T;

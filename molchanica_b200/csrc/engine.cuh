@@ -112,6 +112,10 @@ struct mc_ctx {
     bool use_tile = true;      // TMA-staged tile sweep for the list build (neighbor_tile.cu)
     uint32_t tile_cap = 1024;  // tile capacity in atoms, grows on demand
     int pair_tile_stages = 0;  // option "pair_tile_stages": tiles in flight per CTA of pair_tile.cu (0 = from the shared-memory budget)
+    int rows_interleave = 0;   // option "rows_interleave": keep a quad-interleaved copy of the rows for the 8-lane force kernel
+                               // (measured on C4, profiles/rows_interleave_r2s1.txt: pair kernel 0.163 vs 0.1585 ms with plain rows
+                               // and +0.15 ms per rebuild -- the index loads are not what occupies the L1 data pipe; default off)
+    bool ilv_valid = false;    // nbr_ilv / ilv_qbase describe the current list
     int build_variant = 2;     // option "build_variant": 2 = rows_build_kernel (default), 1 = tile_build_kernel (tile_build.cu)
     uint32_t row_len_hint = 0; // longest row of the last build (0: none yet)
     int rows_min_blocks = 3;   // option "rows_min_blocks"
@@ -142,6 +146,7 @@ struct mc_ctx {
     DevBuf<uint8_t> flags[2];
     DevBuf<int> orig[2], slot_of_orig, rebuild_flag;
     DevBuf<uint32_t> keys[2], vals[2], scratch, cell_start, nbr_count, nbr_start, nbr_list;
+    DevBuf<uint32_t> nbr_ilv, ilv_qbase;  // quad-interleaved copy of the rows for the 8-lane force kernel (pair_force.cu)
     DevBuf<uint32_t> cnt_orig, start_orig, export_rows, tile_need, cell_plan, cell_rowtab, rows_plan;
     DevBuf<uint16_t> nbr_list16;
     DevBuf<int32_t> excl_start, excl_idx, p14_start, p14_idx;
@@ -260,6 +265,7 @@ struct mc_ctx {
         fused_dbg.release(); bl_list.release(); bl_count.release(); bl_flags.release(); bl_xref.release();
         force.release(); xref.release(); stage.release(); flush.release(); slot_of_orig.release(); rebuild_flag.release();
         scratch.release(); cell_start.release(); nbr_count.release(); nbr_start.release(); nbr_list.release();
+        nbr_ilv.release(); ilv_qbase.release();
         cnt_orig.release(); start_orig.release(); export_rows.release(); tile_need.release(); rows_plan.release(); cell_plan.release(); cell_rowtab.release(); nbr_list16.release();
         excl_start.release(); excl_idx.release(); p14_start.release(); p14_idx.release();
         ljtab.release(); d_dock_tab.release(); bbox.release(); ext_force.release(); ext_force2.release(); d_poses.release(); d_scores.release();

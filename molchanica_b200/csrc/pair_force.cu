@@ -28,16 +28,20 @@
 
 namespace {
 
-template <int LANES, bool MULTI, int COUL, bool WRAP, bool ENERGY>
+// KSTR: distance between a lane's consecutive entries in units of LANES -- 1 for plain rows (entry k of a row at lst[k]),
+// 4 for quad-interleaved rows (rows_interleave_*: the LANES-entry chunks of four consecutive rows alternate, so that the
+// index load of a warp's four rows is ONE 128-byte line instead of four 32-byte sectors in four lines).
+template <int LANES, bool MULTI, int COUL, bool WRAP, bool ENERGY, int KSTR>
 __device__ __forceinline__ void row_loop(const float4 xi, const uint32_t *__restrict__ lst, uint32_t cnt, int sub,
                                          const float4 *__restrict__ xyzq, const uint16_t *__restrict__ type,
                                          const float2 *row, const NbParams &p, bool lj_on, Acc &a) {
     const float2 lj1 = make_float2(p.sig2, p.eps24);
     const float rc2_lj = lj_on ? p.rc2_lj : -1.f;
     uint32_t k = sub;
+    lst += sub;
     // two gathers in flight per lane
-    for (; k + LANES < cnt; k += 2 * LANES) {
-        const uint32_t j0 = __ldg(lst + k), j1 = __ldg(lst + k + LANES);
+    for (; k + LANES < cnt; k += 2 * LANES, lst += 2 * LANES * KSTR) {
+        const uint32_t j0 = __ldg(lst), j1 = __ldg(lst + LANES * KSTR);
         const float4 x0 = __ldg(xyzq + j0), x1 = __ldg(xyzq + j1);
         float2 l0 = lj1, l1 = lj1;
         if (MULTI) { l0 = row[__ldg(type + j0)]; l1 = row[__ldg(type + j1)]; }
@@ -45,7 +49,7 @@ __device__ __forceinline__ void row_loop(const float4 xi, const uint32_t *__rest
         pair_term<COUL, WRAP, ENERGY>(xi, x1, l1, p, rc2_lj, a);
     }
     if (k < cnt) {
-        const uint32_t j0 = __ldg(lst + k);
+        const uint32_t j0 = __ldg(lst);
         const float4 x0 = __ldg(xyzq + j0);
         float2 l0 = lj1;
         if (MULTI) l0 = row[__ldg(type + j0)];
@@ -120,7 +124,9 @@ __device__ __forceinline__ void row_loop_uniform(const float4 xi, const uint32_t
     }
 }
 
-template <int LANES, bool MULTI, int COUL, bool PBC, bool ENERGY, bool UNIFORM>
+// ILV: nbr_start / nbr_list are the quad-interleaved copy of the rows (base of every quad of four slots, see
+// rows_interleave_sizes_kernel); nbr_count is the rows' own.
+template <int LANES, bool MULTI, int COUL, bool PBC, bool ENERGY, bool UNIFORM, bool ILV = false>
 __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, int row0, const float4 *__restrict__ xyzq,
                                                           const uint16_t *__restrict__ type,
                                                           const uint8_t *__restrict__ flags,
@@ -165,14 +171,16 @@ __global__ void __launch_bounds__(128) pair_force_kernel(int n_rows, int row0, c
         row_loop_uniform<LANES, MULTI, COUL, PBC, ENERGY>(xi, nbr_list + start, cnt, sub, wrap, xyzq, type, row, p, lj_on, a);
     } else if (live) {
         const float4 xi = __ldg(xyzq + i);
-        const uint32_t start = __ldg(nbr_start + i), cnt = __ldg(nbr_count + i);
+        const uint32_t start = ILV ? __ldg(nbr_start + (i >> 2)) + (uint32_t)(i & 3) * LANES : __ldg(nbr_start + i);
+        const uint32_t cnt = __ldg(nbr_count + i);
         const float2 *row = MULTI ? s_tab + (int)__ldg(type + i) * p.n_types : nullptr;
         const uint32_t *lst = nbr_list + start;
+        constexpr int KSTR = ILV ? 4 : 1;
         // Atoms of interior cells never see a wrapped neighbour between two list builds: their raw
         // differences already are the minimum image (n == 0), so the 9-instruction wrap is skipped.
         const bool wrap = PBC && !(__ldg(flags + i) & MC_FLAG_INTERIOR);
-        if (wrap) row_loop<LANES, MULTI, COUL, true, ENERGY>(xi, lst, cnt, sub, xyzq, type, row, p, lj_on, a);
-        else row_loop<LANES, MULTI, COUL, false, ENERGY>(xi, lst, cnt, sub, xyzq, type, row, p, lj_on, a);
+        if (wrap) row_loop<LANES, MULTI, COUL, true, ENERGY, KSTR>(xi, lst, cnt, sub, xyzq, type, row, p, lj_on, a);
+        else row_loop<LANES, MULTI, COUL, false, ENERGY, KSTR>(xi, lst, cnt, sub, xyzq, type, row, p, lj_on, a);
     }
     // warp-shuffle partial-force reduction across the LANES lanes of this row
 #pragma unroll
@@ -233,6 +241,66 @@ __global__ void __launch_bounds__(128) pairs14_kernel(int n_rows, int row0, cons
     force[k] = acc;
 }
 
+// Quad-interleaved copy of the rows for pair_force_kernel<LANES = 8, ..., ILV> (once per list build).  The slots are taken
+// four at a time; a quad's rows are cut into chunks of 8 entries and stored chunk-major: [row0 c0 | row1 c0 | row2 c0 |
+// row3 c0 | row0 c1 | ...], every row padded to the quad's longest one (entries past a row's count are never read).  A
+// warp of the force kernel -- four rows x 8 lanes -- then loads its 32 indices from ONE 128-byte line; with plain rows the
+// same load touches four lines, and the kernel is bound by exactly those L1 wavefronts.
+// Pass 1: chunks per quad, one block-wide scan, one claim per block on *cursor (units: entries); qbase[q] = first entry.
+constexpr int ILV_CHUNK = 8;
+__global__ void __launch_bounds__(256) rows_interleave_sizes_kernel(int n_slots, const uint32_t *__restrict__ nbr_count,
+                                                                     uint32_t *__restrict__ qbase, uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    const int n_quads = (n_slots + 3) >> 2;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t mx = 0;
+    if (q < n_quads) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = 4 * q + r;
+            if (i < n_slots) mx = max(mx, nbr_count[i]);
+        }
+    }
+    const uint32_t mine = ((mx + ILV_CHUNK - 1) / ILV_CHUNK) * (4 * ILV_CHUNK);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(MC_FULL_MASK, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int k = 0; k < 8; ++k) { const uint32_t t = s_warp[k]; s_warp[k] = tot; tot += t; }
+        s_base = tot ? atomicAdd(cursor, tot) : 0u;
+    }
+    __syncthreads();
+    if (q < n_quads) qbase[q] = s_base + s_warp[w] + incl - mine;
+}
+
+// Pass 2: one warp per quad copies the four rows chunk by chunk (reads: four 32-byte sectors, writes: one 128-byte line).
+__global__ void __launch_bounds__(256) rows_interleave_copy_kernel(int n_slots, const uint32_t *__restrict__ nbr_start,
+                                                                    const uint32_t *__restrict__ nbr_count,
+                                                                    const uint32_t *__restrict__ nbr_list,
+                                                                    const uint32_t *__restrict__ qbase, uint32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int q = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int n_quads = (n_slots + 3) >> 2;
+    if (q >= n_quads) return;  // whole warps
+    const int i = 4 * q + (lane >> 3), sub = lane & 7;
+    uint32_t cnt = 0, start = 0;
+    if (i < n_slots) { cnt = nbr_count[i]; start = nbr_start[i]; }
+    uint32_t mx = cnt;
+    mx = max(mx, __shfl_xor_sync(MC_FULL_MASK, mx, 8));
+    mx = max(mx, __shfl_xor_sync(MC_FULL_MASK, mx, 16));
+    uint32_t *dst = out + qbase[q] + lane;
+    for (uint32_t k = sub; k - sub < mx; k += ILV_CHUNK, dst += 4 * ILV_CHUNK)
+        *dst = k < cnt ? __ldg(nbr_list + start + k) : 0u;
+}
+
 // Two-stage deterministic reduction: per-block partials {sum e_i, sum 1/2 m v^2, n_mobile}.
 constexpr int RED_BLOCKS = 592;  // 4 x 148 SMs
 __global__ void __launch_bounds__(256) energy_partial_kernel(int n_rows, const float4 *__restrict__ force,
@@ -280,7 +348,11 @@ void launch_lanes(const PairLaunch &L, cudaStream_t st) {
     const size_t smem = L.multi ? sizeof(float2) * L.p.n_types * L.p.n_types : 0;
 #define MC_PF(M, C, P, E)                                                                                               \
     do {                                                                                                                \
-        if (L.uniform)                                                                                                  \
+        if (LANES == 8 && L.ilv_list && !L.uniform)                                                                     \
+            MC_LAUNCH(pair_force_kernel<8 MC_COMMA M MC_COMMA C MC_COMMA P MC_COMMA E MC_COMMA false MC_COMMA true>, blocks, 128, smem, st, \
+                      L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.ilv_qbase, L.nbr_count, L.ilv_list, L.ljtab, L.p, L.lj_on,   \
+                      L.force, L.n_interior, L.n_first, L.wait);                                                        \
+        else if (L.uniform)                                                                                                  \
             MC_LAUNCH(pair_force_kernel<LANES MC_COMMA M MC_COMMA C MC_COMMA P MC_COMMA E MC_COMMA true>, blocks, 128, smem, st, \
                       L.n_rows, L.row0, L.xyzq, L.type, L.flags, L.nbr_start, L.nbr_count, L.nbr_list, L.ljtab, L.p, L.lj_on,   \
                       L.force, L.n_interior, L.n_first, L.wait);                                                        \
@@ -320,6 +392,9 @@ cudaError_t pair_force_prepare() {
                                  200 * 1024);                                                                    \
     if (e == cudaSuccess)                                                                                        \
         e = cudaFuncSetAttribute(pair_force_kernel<LN, true, C, P, E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 200 * 1024);                                                                    \
+    if (e == cudaSuccess && LN == 8)                                                                             \
+        e = cudaFuncSetAttribute(pair_force_kernel<8, true, C, P, E, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  200 * 1024);
 #define MC_ATTR_C(LN, C) MC_ATTR(LN, C, true, true) MC_ATTR(LN, C, true, false) MC_ATTR(LN, C, false, true) MC_ATTR(LN, C, false, false)
 #define MC_ATTR_L(LN) MC_ATTR_C(LN, MC_COULOMB_NONE) MC_ATTR_C(LN, MC_COULOMB_PLAIN) MC_ATTR_C(LN, MC_COULOMB_ERFC)
@@ -348,6 +423,20 @@ void launch_pairs14(int n_rows, int row0, const float4 *xyzq, const uint16_t *ty
     if (n_rows <= 0) return;
     MC_LAUNCH(pairs14_kernel, div_up(n_rows, 128), 128, 0, st, n_rows, row0, xyzq, type, orig, slot_of_orig, p14_start, p14_idx, ljtab,
                                                        p, scale_lj, scale_q, lj_on, coul_on, force);
+    *launches += 1;
+}
+
+void launch_rows_interleave_sizes(int n_slots, const uint32_t *nbr_count, uint32_t *qbase, uint32_t *cursor, cudaStream_t st, int64_t *launches) {
+    if (n_slots <= 0) return;
+    MC_LAUNCH(rows_interleave_sizes_kernel, div_up((size_t)((n_slots + 3) >> 2), 256), 256, 0, st, n_slots, nbr_count, qbase, cursor);
+    *launches += 1;
+}
+
+void launch_rows_interleave_copy(int n_slots, const uint32_t *nbr_start, const uint32_t *nbr_count, const uint32_t *nbr_list,
+                                 const uint32_t *qbase, uint32_t *out, cudaStream_t st, int64_t *launches) {
+    if (n_slots <= 0) return;
+    MC_LAUNCH(rows_interleave_copy_kernel, div_up((size_t)((n_slots + 3) >> 2) * 32, 256), 256, 0, st, n_slots, nbr_start, nbr_count, nbr_list,
+              qbase, out);
     *launches += 1;
 }
 

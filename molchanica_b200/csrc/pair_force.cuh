@@ -24,9 +24,15 @@ struct PairLaunch {
     // interior rows wait on the neighbours' ready flags.  Defaults = plain order, no wait.
     int n_interior = 0, n_first = 0;
     HaloWait wait{};
+    // quad-interleaved copy of the rows (launch_rows_interleave_*), used by the 8-lane kernel when set
+    const uint32_t *ilv_qbase = nullptr, *ilv_list = nullptr;
 };
 
 int pair_force_max_types();
+// Quad-interleaved rows: sizes (qbase per quad of four slots, *cursor += entries claimed) then copy; see pair_force.cu.
+void launch_rows_interleave_sizes(int n_slots, const uint32_t *nbr_count, uint32_t *qbase, uint32_t *cursor, cudaStream_t st, int64_t *launches);
+void launch_rows_interleave_copy(int n_slots, const uint32_t *nbr_start, const uint32_t *nbr_count, const uint32_t *nbr_list,
+                                 const uint32_t *qbase, uint32_t *out, cudaStream_t st, int64_t *launches);
 cudaError_t pair_force_prepare();
 void launch_pair_force(const PairLaunch &L, cudaStream_t st, int64_t *launches);
 void launch_pairs14(int n_rows, int row0, const float4 *xyzq, const uint16_t *type, const int *orig, const int *slot_of_orig,

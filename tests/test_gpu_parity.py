@@ -132,6 +132,29 @@ def test_every_lane_width_gives_the_same_forces(lanes, Engine, oracle):
     e.close()
 
 
+@pytest.mark.parametrize("name", ["lj1728", "lj8000", "water648", "glob1231", "solv23558"])
+def test_interleaved_rows_are_the_same_rows(name, Engine):
+    """The 8-lane force kernel can read a quad-interleaved copy of the rows (option rows_interleave, default off: the chunks
+    of 8 entries of four consecutive rows alternate, one 128-byte line per warp-wide index load).  Same entries, same lanes, same
+    order of accumulation: forces and per-atom energies are the same BITS as from the plain rows, with and without energies,
+    and after steps through rebuilds."""
+    w = _cases()[name]()
+    out = []
+    for ilv in (1, 0):
+        e = Engine.from_workload(w)
+        e.set_option("rows_interleave", ilv)
+        e.compute_forces()
+        f0 = e.forces()
+        e.step(w["dt"], 12)
+        x = e.positions()
+        e.compute_forces()
+        out.append((f0, x, e.forces(), e.stats()["n_rebuilds"]))
+        e.close()
+    for a, b in zip(out[0][:3], out[1][:3]):
+        assert np.array_equal(a, b)
+    assert out[0][3] == out[1][3]
+
+
 def test_overrides_isolate_lj_and_coulomb(Engine, oracle):
     """MdOverrides.lj_disabled / coulomb_disabled (reference src/md/mod.rs:671-686)."""
     w = W.globule()
