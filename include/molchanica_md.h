@@ -130,8 +130,10 @@ int mc_set_exclusions(mc_ctx *ctx, const int32_t *start, const int32_t *idx);
 int mc_set_pairs14(mc_ctx *ctx, int64_t m, const int32_t *pairs, float scale_lj, float scale_q);
 
 /* Bonded terms, Amber functional forms, evaluated on the device in the same force evaluation
- * as the nonbonded terms (single-GPU handles).  Atom ids are the caller's; call after mc_set_atoms (which clears
- * them); m = 0 clears one kind.  Exclusions / 1-4 pairs that go with the bonds are set separately above.
+ * as the nonbonded terms.  Atom ids are the caller's; call after mc_set_atoms (which clears them); m = 0 clears one kind.
+ * Decomposed handles: every rank is given the WHOLE term list and evaluates the terms that touch an atom it owns (the
+ * partners are ghosts: a term must not reach further than cutoff + skin, MC_E_INVALID otherwise); mc_energy's bonded
+ * energies are summed over the ranks.  Exclusions / 1-4 pairs that go with the bonds are set separately above.
  *   bonds:     pairs[2m],   k_r0[2m]       E = k (r - r0)^2                    kcal/mol/A^2, A
  *   angles:    triples[3m] (vertex second), k_theta0[2m]  E = k (theta - theta0)^2   kcal/mol/rad^2, rad
  *   dihedrals: quads[4m],   pk_n_phase[3m] E = pk (1 + cos(n phi - phase))     kcal/mol, -, rad (IUPAC phi) */
@@ -145,7 +147,8 @@ int mc_set_dihedrals(mc_ctx *ctx, int64_t m, const int32_t *quads, const float *
  * not depend on the engine's internal atom order.  Static atoms are left alone.
  * MC_THERMOSTAT_CSVR (Bussi-Donadio-Parrinello): at the same point of the step all velocities are scaled by one
  * stochastic factor computed on the device from the kinetic energy; gamma_per_ps is then 1 / tau.  The factor is a
- * function of (seed, step, kinetic energy) only.  Single-GPU handles. */
+ * function of (seed, step, kinetic energy) only.  Langevin works on decomposed handles too (same noise on any
+ * decomposition); CSVR is for single-GPU handles. */
 int mc_set_thermostat(mc_ctx *ctx, int kind, float temperature_k, float gamma_per_ps, uint64_t seed);
 
 /* SPME reciprocal space (the reference's electrostatics, README.md:240): with coulomb_mode =
@@ -241,7 +244,7 @@ int mc_get_stats(mc_ctx *ctx, mc_stats *out);
 /* SnapshotEnergyData.pressure (reference ui/panels/md_viewer.rs:202-256): P = (2 KE + W) / 3V in bar and the virial
  * W = sum r_ij . f_ij in kcal/mol over nonbonded pairs inside the cutoffs, scaled 1-4 pairs, bonded terms and the SPME
  * reciprocal sum with its excluded-pair correction.  One extra pass over the neighbour list, on demand only.
- * Periodic, single-GPU handles.  With rigid waters / constrained bonds the virial of the constraint forces of the LAST
+ * Periodic boxes; on a decomposed handle a collective call (all ranks, one all-reduce).  With rigid waters / constrained bonds the virial of the constraint forces of the LAST
  * step is included (mass x constraint displacement / dt^2 on the old positions), so at least one step must have been taken.
  * Either output may be NULL. */
 int mc_get_pressure(mc_ctx *ctx, double *pressure_bar, double *virial);
@@ -264,7 +267,8 @@ int mc_get_box(mc_ctx *ctx, float lo[3], float hi[3]);
 /* SnapshotEnergyData.energy_potential_between_mols (src/md/mod.rs:1242-1245): mol_id[n] assigns every atom to a molecule;
  * mc_get_energy_between_mols sums the nonbonded pair energies (LJ + the Coulomb form in force, within the cutoffs)
  * over the listed pairs whose atoms belong to different molecules.  On demand, not on the step path; excluded
- * pairs and the reciprocal part of SPME are not in it.  Single-GPU handles; NULL clears the ids. */
+ * pairs and the reciprocal part of SPME are not in it.  On a decomposed handle mol_id covers all n_global atoms and
+ * the get is a collective call (one all-reduce); NULL clears the ids. */
 int mc_set_molecule_ids(mc_ctx *ctx, const uint16_t *mol_id);
 int mc_get_energy_between_mols(mc_ctx *ctx, double *out);
 

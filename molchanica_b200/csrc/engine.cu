@@ -373,7 +373,6 @@ extern "C" int mc_set_bonds(mc_ctx *c, int64_t m, const int32_t *pairs, const fl
     if (!c) return MC_E_INVALID;
     MC_FLUSH(c);
     cudaSetDevice(c->device);
-    MC_REQUIRE(c, !c->comm_active, "mc_set_bonds: bonded terms on a decomposed handle are not supported yet");
     MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || (pairs && k_r0)), "mc_set_bonds: bad arguments");
     int rc = upload_terms<2, int2>(c, "mc_set_bonds", m, pairs, c->bonds, &c->n_bonds);
     if (rc != MC_OK) { c->n_bonds = 0; return rc; }
@@ -386,7 +385,6 @@ extern "C" int mc_set_angles(mc_ctx *c, int64_t m, const int32_t *triples, const
     if (!c) return MC_E_INVALID;
     MC_FLUSH(c);
     cudaSetDevice(c->device);
-    MC_REQUIRE(c, !c->comm_active, "mc_set_angles: bonded terms on a decomposed handle are not supported yet");
     MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || (triples && k_theta0)), "mc_set_angles: bad arguments");
     int rc = upload_terms<3, int4>(c, "mc_set_angles", m, triples, c->angles, &c->n_angles);
     if (rc != MC_OK) { c->n_angles = 0; return rc; }
@@ -399,7 +397,6 @@ extern "C" int mc_set_dihedrals(mc_ctx *c, int64_t m, const int32_t *quads, cons
     if (!c) return MC_E_INVALID;
     MC_FLUSH(c);
     cudaSetDevice(c->device);
-    MC_REQUIRE(c, !c->comm_active, "mc_set_dihedrals: bonded terms on a decomposed handle are not supported yet");
     MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || (quads && pk_n_phase)), "mc_set_dihedrals: bad arguments");
     int rc = upload_terms<4, int4>(c, "mc_set_dihedrals", m, quads, c->dihedrals, &c->n_dihedrals);
     if (rc != MC_OK) { c->n_dihedrals = 0; return rc; }
@@ -466,7 +463,9 @@ extern "C" int mc_set_thermostat(mc_ctx *c, int kind, float temperature_k, float
     if (!c) return MC_E_INVALID;
     MC_FLUSH(c);
     MC_REQUIRE(c, kind == MC_THERMOSTAT_NONE || kind == MC_THERMOSTAT_LANGEVIN || kind == MC_THERMOSTAT_CSVR, "mc_set_thermostat: unknown kind");
-    MC_REQUIRE(c, !c->comm_active || kind == MC_THERMOSTAT_NONE, "mc_set_thermostat: thermostats on a decomposed handle are not supported yet");
+    // Langevin acts on owned rows with noise keyed by (seed, step, original atom id): the same numbers on any decomposition.
+    // CSVR needs the global kinetic energy inside the step (an all-reduce per step): single-GPU handles for now.
+    MC_REQUIRE(c, !c->comm_active || kind != MC_THERMOSTAT_CSVR, "mc_set_thermostat: the CSVR thermostat on a decomposed handle is not supported yet");
     MC_REQUIRE(c, kind == MC_THERMOSTAT_NONE || (temperature_k >= 0.f && gamma_per_ps >= 0.f), "mc_set_thermostat: negative temperature or friction");
     c->langevin = kind == MC_THERMOSTAT_LANGEVIN;
     c->csvr = kind == MC_THERMOSTAT_CSVR;
@@ -910,6 +909,15 @@ int engine_launch_forces(mc_ctx *c, bool want_energy, const HaloSplit *hs) {
         t.angles = c->angles.p; t.angle_kt0 = c->angle_kt0.p;
         t.dihedrals = c->dihedrals.p; t.dihedral_prm = c->dihedral_prm.p;
         MC_CUDA(c, c->bonded_e.ensure(4));
+        if (c->comm_active) {
+            // every rank holds the whole term list and evaluates the terms that touch its owned rows (bonded.cuh)
+            if (!c->bonded_missing.p) {
+                MC_CUDA(c, c->bonded_missing.ensure(1));
+                MC_CUDA(c, cudaMemsetAsync(c->bonded_missing.p, 0, sizeof(int), c->st));
+            }
+            t.own0 = (int)c->row0; t.own1 = (int)(c->row0 + c->n_rows_sorted());
+            t.missing = c->bonded_missing.p;
+        }
         launch_bonded(t, c->slot_of_orig.p, L.xyzq, L.p, c->force.p, c->bonded_e.p, want_energy, c->st, &c->launches);
     }
     if (c->pme.planned && c->periodic && !c->comm_active && L.coul == MC_COULOMB_ERFC) {
@@ -1066,6 +1074,14 @@ static int step_epilogue(mc_ctx *c, const StepEpilogue &E) {
             c->list_valid = false;
             stale_list = true;
             if (c->comm_active) comm_shrink_interval(c);
+        }
+    }
+    if (c->comm_active && c->bonded_missing.p && n_steps > 0) {
+        int bad = 0;
+        MC_CUDA(c, cudaMemcpy(&bad, c->bonded_missing.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bad) {
+            MC_CUDA(c, cudaMemset(c->bonded_missing.p, 0, sizeof(int)));
+            return fail(c, MC_E_INVALID, "mc_step: a bonded term reaches beyond this rank's ghost layer (bonded partners must lie within cutoff + skin)");
         }
     }
     if (c->n_hclusters > 0 && n_steps > 0) {
@@ -1779,6 +1795,17 @@ extern "C" int mc_get_energy(mc_ctx *c, mc_energy *out) {
     if (c->n_bonds + c->n_angles + c->n_dihedrals > 0) {
         double hb[3];
         MC_CUDA(c, cudaMemcpy(hb, c->bonded_e.p, sizeof(hb), cudaMemcpyDeviceToHost));
+        if (c->comm_active) {
+            // every rank added the share of each term that belongs to its owned atoms
+            int rc = comm_allreduce3(c, hb);
+            if (rc != MC_OK) return rc;
+            int bad = 0;
+            if (c->bonded_missing.p) MC_CUDA(c, cudaMemcpy(&bad, c->bonded_missing.p, sizeof(int), cudaMemcpyDeviceToHost));
+            if (bad) {
+                MC_CUDA(c, cudaMemset(c->bonded_missing.p, 0, sizeof(int)));
+                return fail(c, MC_E_INVALID, "mc_get_energy: a bonded term reaches beyond this rank's ghost layer (bonded partners must lie within cutoff + skin)");
+            }
+        }
         out->energy_bond = hb[0]; out->energy_angle = hb[1]; out->energy_dihedral = hb[2];
         out->energy_potential_bonded = hb[0] + hb[1] + hb[2];
     }
@@ -1833,6 +1860,13 @@ static int compute_pressure(mc_ctx *c, double *pressure_bar, double *virial) {
         MC_CUDA(c, cudaMemcpy(hp, c->pme.energy, sizeof(hp), cudaMemcpyDeviceToHost));
         w += hp[2] + (c->have_excl ? hp[3] : 0.0);  // the self term does not depend on the volume
     }
+    if (c->comm_active) {
+        // rows of owned atoms (each pair: half in either row), owned shares of the bonded terms, owned kinetic energy
+        double v[3] = {w, h[1], 0.0};
+        int rc = comm_allreduce3(c, v);
+        if (rc != MC_OK) return rc;
+        w = v[0]; h[1] = v[1];
+    }
     if (constrained) {
         // constraint forces of the last step (SETTLE / SHAKE displacement x mass / dt^2 on the old positions)
         double hc = 0.0;
@@ -1851,7 +1885,6 @@ extern "C" int mc_get_pressure(mc_ctx *c, double *pressure_bar, double *virial) 
     MC_FLUSH_OBS(c);
     cudaSetDevice(c->device);
     MC_REQUIRE(c, c->periodic, "mc_get_pressure: needs a periodic box");
-    MC_REQUIRE(c, !c->comm_active, "mc_get_pressure: not available on a decomposed handle yet");
     MC_REQUIRE(c, !(c->n_waters > 0 || c->n_hclusters > 0) || c->cons_virial_valid,
                "mc_get_pressure: the virial of the constraint forces is that of the last step; take a step first");
     int rc = ensure_ready(c, "mc_get_pressure");
@@ -1926,7 +1959,6 @@ extern "C" int mc_get_box(mc_ctx *c, float lo[3], float hi[3]) {
 extern "C" int mc_set_molecule_ids(mc_ctx *c, const uint16_t *mol_id) {
     if (!c) return MC_E_INVALID;
     cudaSetDevice(c->device);
-    MC_REQUIRE(c, !c->comm_active, "mc_set_molecule_ids: not available on a decomposed handle yet");
     if (!mol_id) { c->have_mols = false; return MC_OK; }
     MC_CUDA(c, c->mol_of_orig.ensure((size_t)std::max<int64_t>(c->n_global, 1)));
     if (c->n_global) MC_CUDA(c, cudaMemcpy(c->mol_of_orig.p, mol_id, sizeof(uint16_t) * (size_t)c->n_global, cudaMemcpyHostToDevice));
@@ -1948,6 +1980,11 @@ extern "C" int mc_get_energy_between_mols(mc_ctx *c, double *out) {
                         c->coul_disabled ? MC_COULOMB_NONE : c->coul_mode, c->red_out.p + 3, c->st, &c->launches);
     MC_CUDA(c, cudaMemcpyAsync(out, c->red_out.p + 3, sizeof(double), cudaMemcpyDeviceToHost, c->st));
     MC_CUDA(c, cudaStreamSynchronize(c->st));
+    if (c->comm_active) {  // every rank summed the rows of its owned atoms (each pair: half in either row)
+        double v[3] = {*out, 0.0, 0.0};
+        if ((rc = comm_allreduce3(c, v)) != MC_OK) return rc;
+        *out = v[0];
+    }
     return MC_OK;
 }
 

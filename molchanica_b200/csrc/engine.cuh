@@ -191,6 +191,7 @@ struct mc_ctx {
     DevBuf<int4> hclusters;
     DevBuf<float> hdist;
     DevBuf<int> shake_fail;
+    DevBuf<int> bonded_missing;  // decomposed handles: set by bonded_kernel when a term's partner is not held by this rank
     float shake_tol = 1e-6f;
     int n_vsites = 0;          // virtual sites of four-site water (settle.cu)
     DevBuf<int4> vsites;
@@ -274,7 +275,7 @@ struct mc_ctx {
         for (int b = 0; b < 2; ++b) { snap_stage[b].release(); snap_stage_v[b].release(); snap_ids[b].release(); }
         bonds.release(); bond_kr0.release(); angle_kt0.release(); angles.release(); dihedrals.release(); dihedral_prm.release();
         bonded_e.release(); cons_virial.release(); com_partial.release(); waters.release(); vsites.release(); csvr_lambda.release();
-        hclusters.release(); hdist.release(); shake_fail.release(); mol_of_orig.release(); min_x.release(); min_v.release();
+        hclusters.release(); hdist.release(); shake_fail.release(); bonded_missing.release(); mol_of_orig.release(); min_x.release(); min_v.release();
     }
 
     // resolve the CUDA-event pairs recorded since the last call (stream must be idle)

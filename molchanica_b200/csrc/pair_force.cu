@@ -28,6 +28,34 @@
 
 namespace {
 
+// Defaults from the A/B of profiles/pair_force_r2t_knobs.txt (C4, one B200): four gathers in flight per lane and index
+// loads that do not allocate in L1 (the list streams through once) -- 0.1536 ms against 0.1572 ms with two gathers and
+// allocating loads; each knob alone is within the noise.  Accumulation order per lane is unchanged (same bits).
+#ifndef MC_PF_DEPTH
+#define MC_PF_DEPTH 4
+#endif
+#if !defined(MC_PF_IDX_ALLOC) && !defined(MC_PF_IDX_NOALLOC)
+#define MC_PF_IDX_NOALLOC 1
+#endif
+__device__ __forceinline__ uint32_t pf_ld_idx(const uint32_t *p) {
+#if defined(MC_PF_IDX_NOALLOC) && !defined(MC_HOST_SHIM)
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ float4 pf_ld_pos(const float4 *p) {
+#if defined(MC_PF_POS_EVICT_LAST) && !defined(MC_HOST_SHIM)
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 // KSTR: distance between a lane's consecutive entries in units of LANES -- 1 for plain rows (entry k of a row at lst[k]),
 // 4 for quad-interleaved rows (rows_interleave_*: the LANES-entry chunks of four consecutive rows alternate, so that the
 // index load of a warp's four rows is ONE 128-byte line instead of four 32-byte sectors in four lines).
@@ -39,6 +67,30 @@ __device__ __forceinline__ void row_loop(const float4 xi, const uint32_t *__rest
     const float rc2_lj = lj_on ? p.rc2_lj : -1.f;
     uint32_t k = sub;
     lst += sub;
+#if MC_PF_DEPTH != 2 || defined(MC_PF_IDX_NOALLOC) || defined(MC_PF_POS_EVICT_LAST)
+    // A/B knobs (tools/gpu_r2_t.sh, profiles/pair_force_r2t_knobs.txt): MC_PF_DEPTH gathers in flight per lane, index loads that
+    // do not allocate in L1 (the list streams through once), position loads marked evict-last
+    for (; k + (MC_PF_DEPTH - 1) * LANES < cnt; k += MC_PF_DEPTH * LANES, lst += MC_PF_DEPTH * LANES * KSTR) {
+        uint32_t j[MC_PF_DEPTH];
+        float4 x[MC_PF_DEPTH];
+        float2 l[MC_PF_DEPTH];
+#pragma unroll
+        for (int u = 0; u < MC_PF_DEPTH; ++u) j[u] = pf_ld_idx(lst + u * LANES * KSTR);
+#pragma unroll
+        for (int u = 0; u < MC_PF_DEPTH; ++u) x[u] = pf_ld_pos(xyzq + j[u]);
+#pragma unroll
+        for (int u = 0; u < MC_PF_DEPTH; ++u) l[u] = MULTI ? row[__ldg(type + j[u])] : lj1;
+#pragma unroll
+        for (int u = 0; u < MC_PF_DEPTH; ++u) pair_term<COUL, WRAP, ENERGY>(xi, x[u], l[u], p, rc2_lj, a);
+    }
+    for (; k < cnt; k += LANES, lst += LANES * KSTR) {
+        const uint32_t j0 = pf_ld_idx(lst);
+        const float4 x0 = pf_ld_pos(xyzq + j0);
+        float2 l0 = lj1;
+        if (MULTI) l0 = row[__ldg(type + j0)];
+        pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, rc2_lj, a);
+    }
+#else
     // two gathers in flight per lane
     for (; k + LANES < cnt; k += 2 * LANES, lst += 2 * LANES * KSTR) {
         const uint32_t j0 = __ldg(lst), j1 = __ldg(lst + LANES * KSTR);
@@ -55,6 +107,7 @@ __device__ __forceinline__ void row_loop(const float4 xi, const uint32_t *__rest
         if (MULTI) l0 = row[__ldg(type + j0)];
         pair_term<COUL, WRAP, ENERGY>(xi, x0, l0, p, rc2_lj, a);
     }
+#endif
 }
 
 // Warp-uniform variant of the row loop: all 32 lanes run the same trip count (the longest of the

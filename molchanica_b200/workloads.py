@@ -381,6 +381,25 @@ def solvated_c3(seed=303, n_protein=2489, n_water=7023, L=62.23):
               rc_lj=12.0, rc_q=12.0, skin=2.0, coul_mode=1, excl_start=es, excl_idx=ei,
               pairs14=p14, dt=0.002, name=f"C3-solvated{n}")
     maxwell_boltzmann(w["vel"], 300.0, seed + 1)
+    w["bond_graph"] = [(int(i), int(j)) for i, j in bonds]
+    w["mol_id"] = np.concatenate([np.zeros(n_protein, np.uint16), (1 + np.arange(n_water).repeat(3)).astype(np.uint16)])
+    return w
+
+
+def solvated_bonded(small=False, seed=303):
+    """The C3 box with its bonded terms (flexible waters: O-H, O-H, H-H bonds and the angles they imply; the globule's bonds,
+    angles and proper dihedrals) -- the periodic, decomposable counterpart of bonded_globule.  small: 600 + 3 x 1,500 atoms in
+    a 40 A box with an 8 A cutoff + 1 A skin (four cell layers along z: two ranks), for the host build of the library."""
+    if small:
+        w = solvated_c3(seed=seed, n_protein=600, n_water=1500, L=40.0)
+        w["rc_lj"] = w["rc_q"] = 8.0
+        w["skin"] = 1.0
+    else:
+        w = solvated_c3(seed=seed)
+    w["coul_mode"] = 2  # continuous at the cutoff
+    w.update(bonded_terms_from_bonds(w["xyzq"][:, :3].astype(np.float64), w["bond_graph"], seed))
+    w["dt"] = 0.0005
+    w["name"] = "solvated-bonded%d" % len(w["xyzq"])
     return w
 
 

@@ -66,3 +66,54 @@ def test_decomposed_run_matches_oracle(world, case, halo, sched, oracle):
         assert int(r["interval"]) >= 10 and int(r["rebuilds"]) >= 2 and 0.0 < float(r["disp_frac"]) < 1.0
     assert bool(r["snap_ok"]), "rank-local snapshot differs from the gathered positions"
     assert int(r["n_owned"]) < len(w["xyzq"]) and int(r["n_ghosts"]) > 0
+
+
+def _single_handle_reference(w, n_steps, langevin):
+    """The same system on one handle of the same library: initial forces, energies, positions after n_steps."""
+    from molchanica_b200.engine import MdEngine
+    e = MdEngine.from_workload(w, bonded=True)
+    if langevin:
+        e.set_thermostat(1, 300.0, 5.0, seed=7)
+    e.set_option("rebuild_every", 2)
+    e.compute_forces()
+    f0, en = e.forces(), e.energy()
+    en["pressure"], en["virial"] = e.pressure()
+    en["between_mols"] = e.energy_between_mols(w["mol_id"])
+    e.step(w["dt"], n_steps)
+    x = e.positions()
+    e.close()
+    return f0, en, x
+
+
+def check_bonded_decomposed(r, w, n_steps, langevin):
+    """Shared with tests/test_library_on_host.py: a decomposed run with bonded terms against the single-handle run."""
+    f0, en, x = _single_handle_reference(w, n_steps, langevin)
+    # forces: same terms, fp32 atomics in another order -> a few ulp of the largest contribution per atom
+    scale = np.abs(f0[:, :3]).max(1) + 1e-2 * np.abs(f0[:, :3]).max()
+    assert (np.abs(r["f0"][:, :3] - f0[:, :3]).max(1) / scale).max() < 2e-5
+    assert abs(float(r["e_bonded"]) - en["energy_potential_bonded"]) < 1e-5 * abs(en["energy_potential_bonded"]) + 1e-3
+    assert abs(float(r["e_pot"]) - en["energy_potential_nonbonded"]) < 1e-5 * abs(en["energy_potential_nonbonded"]) + 1e-3
+    assert abs(float(r["virial"]) - en["virial"]) < 2e-5 * abs(en["virial"]) + 1e-2, (float(r["virial"]), en["virial"])
+    assert abs(float(r["pressure"]) - en["pressure"]) < 2e-5 * abs(en["pressure"]) + 1.0, (float(r["pressure"]), en["pressure"])
+    assert abs(float(r["e_mols"]) - en["between_mols"]) < 1e-5 * abs(en["between_mols"]) + 1e-3, (float(r["e_mols"]), en["between_mols"])
+    d = r["x"][:, :3] - x[:, :3]
+    d -= np.rint(d / w["box_ext"]) * w["box_ext"]
+    assert np.abs(d).max() < 2e-4, np.abs(d).max()
+    assert bool(r["snap_ok"]) and int(r["n_owned"]) < len(w["xyzq"]) and int(r["n_ghosts"]) > 0 and int(r["rebuilds"]) >= 2
+
+
+@pytest.mark.parametrize("case,halo", [("solvb", "fused"), ("solvb", "nccl"), ("solvl", "fused")])
+def test_bonded_terms_and_langevin_on_a_decomposed_handle(case, halo):
+    """SURVEY 8f row 3 across slab boundaries: bonds, angles and dihedrals (with their exclusions and 1-4 pairs) on two ranks
+    -- every rank evaluates the terms that touch its owned atoms, partners are ghosts, energies are shared out by owned atoms
+    and all-reduced -- and the Langevin thermostat, whose noise is keyed by (seed, step, original id) and therefore the same on
+    any decomposition.  Reference: the single-handle run of the same library (itself checked against the oracle in
+    tests/test_gpu_bonded.py / test_gpu_langevin.py)."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, HERE)
+    from dd_worker import case_workload
+    w, n_steps = case_workload(case, 2)
+    r = _run(2, case, halo, "fixed")
+    assert int(r["fused"]) == (1 if halo == "fused" else 0), str(r["why"])
+    check_bonded_decomposed(r, w, n_steps, case.startswith("solvl"))

@@ -99,6 +99,27 @@ def test_decomposed_run_on_the_host_build(case, world, halo, sched, host_env, or
         assert int(r["interval"]) >= 10 and int(r["rebuilds"]) >= 2 and 0.0 < float(r["disp_frac"]) < 1.0
 
 
+@pytest.mark.parametrize("case,halo", [("solvb_small", "fused"), ("solvl_small", "nccl")])
+def test_decomposed_bonded_terms_on_the_host_build(case, halo, host_env):
+    """Bonded terms (+ Langevin) on a two-rank decomposed handle of the host build against the single-handle run of the same
+    build (in a subprocess, so that this process does not load the library): tests/test_gpu_multi.py's check."""
+    import tempfile
+    env = dict(host_env, MOLCHANICA_NCCL_LIB=os.path.join(HERE, "cpp", "_build", "libnccl_standin.so"), MC_SHIM_THREADS="2",
+               MC_SHIM_SHARED_HEAP="1" if halo == "fused" else "0")
+    d = tempfile.mkdtemp()
+    idf, out = os.path.join(d, "nccl_id"), os.path.join(d, "out.npz")
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dd_worker.py"), str(r), "2", idf, case, out, halo, "fixed"],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT) for r in range(2)]
+    logs = [p.communicate(timeout=900)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from dd_worker import case_workload\nfrom test_gpu_multi import check_bonded_decomposed\n"
+            "w, n = case_workload(%r, 2)\ncheck_bonded_decomposed(np.load(%r), w, n, %r)\nprint('OK')\n"
+            % (ROOT, HERE, case, out, case.startswith("solvl")))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+    assert p.returncode == 0 and "OK" in p.stdout, p.stdout + p.stderr
+
+
 @pytest.mark.parametrize("world,halo,per_call,defer", [(2, "fused", 1, 1), (2, "fused", 3, 1), (4, "fused", 1, 1), (2, "nccl", 1, 1), (2, "fused", 1, 0)])
 def test_decomposed_external_forces_on_the_host_build(world, halo, per_call, defer, host_env, oracle):
     """mc_step(dt, k, ext) on a decomposed handle: every rank uploads its 1/N block of the caller's array, the blocks are
