@@ -32,6 +32,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -221,6 +222,7 @@ extern "C" int mc_comm_init(mc_ctx *c, const uint8_t id[128], int rank, int n_ra
     if (c->n != 0) { c->err = "mc_comm_init: must precede mc_set_atoms"; return MC_E_INVALID; }
     cudaSetDevice(c->device);
     if (!nccl_api().ok) { c->err = "mc_comm_init: " + nccl_api().err; return MC_E_COMM; }
+    g_devbuf_roomy = true;  // buffers that follow the atoms a rank holds: head-room from the first allocation on (engine.cuh)
     CommState *cs = new CommState();
     ncclUniqueId u;
     memcpy(&u, id, 128);
@@ -536,6 +538,16 @@ void comm_step_descriptors(mc_ctx *c, bool rebuild_step, HaloPush *push, HaloSpl
 int comm_rebuild(mc_ctx *c) {
     CommState *cs = c->comm;
     cudaStream_t st = c->st;
+    struct Lap {  // MC_TRACE_STEP: wall clock of a rebuild that takes more than 5 ms, by phase (stall hunting)
+        bool on; int dev; std::chrono::steady_clock::time_point t0, t; double ph[4] = {0, 0, 0, 0};
+        void lap(int k) { if (!on) return; const auto now = std::chrono::steady_clock::now(); ph[k] += std::chrono::duration<double>(now - t).count(); t = now; }
+        ~Lap() {
+            if (!on) return;
+            const double tot = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (tot > 5e-3) fprintf(stderr, "[comm_rebuild stall, device %d] %.2f ms: exchange launch %.2f, table all-gather + sync %.2f, rows %.2f, rest %.2f\n",
+                                    dev, tot * 1e3, ph[0] * 1e3, ph[1] * 1e3, ph[2] * 1e3, ph[3] * 1e3);
+        }
+    } lapc{c->trace_step, c->device, std::chrono::steady_clock::now(), std::chrono::steady_clock::now()};
     if (c->grid_dirty) { int rc = dd_setup_grid(c); if (rc != MC_OK) return rc; }
     if (c->halo_fused && (!cs->peer_tried || (cs->peer_ok && (cs->exported[0] != c->xyzq[0].p || cs->exported[1] != c->xyzq[1].p)))) {
         int rc = peer_setup(c);
@@ -669,9 +681,11 @@ int comm_rebuild(mc_ctx *c) {
     const size_t tw = MC_DD_TABLE_WORDS;
     MC_CUDAC(c, cs->d_layer_all.ensure(tw * (size_t)cs->n));
     if (!cs->h_layer_all) MC_CUDAC(c, cudaMallocHost(&cs->h_layer_all, sizeof(uint32_t) * tw * (size_t)cs->n));
+    lapc.lap(0);
     MC_NCCL(c, nccl_api().AllGather(cs->d_layer.p, cs->d_layer_all.p, tw, ncclUint32, cs->comm, st));
     MC_CUDAC(c, cudaMemcpyAsync(cs->h_layer_all, cs->d_layer_all.p, sizeof(uint32_t) * tw * (size_t)cs->n, cudaMemcpyDeviceToHost, st));
     MC_CUDAC(c, cudaStreamSynchronize(st));
+    lapc.lap(1);
     const uint32_t *h6 = cs->h_layer_all + tw * (size_t)cs->rank;
     cs->o_gp = h6[0]; cs->o_own = h6[1]; cs->o_first_end = h6[2]; cs->o_last_begin = h6[3]; cs->o_own_end = h6[4]; cs->o_end = h6[5];
     if (cs->o_end > cs->local_cap) { c->err = "domain decomposition: local atom capacity exceeded"; return MC_E_CAPACITY; }
@@ -726,7 +740,10 @@ int comm_rebuild(mc_ctx *c) {
     c->n_rows = cs->o_own_end - cs->o_own;
     c->identity_order = false;
     tr.stop();
-    return engine_build_rows(c);
+    lapc.lap(3);
+    const int rc_rows = engine_build_rows(c);
+    lapc.lap(2);
+    return rc_rows;
 }
 
 // Per-step ghost refresh: boundary blocks out, ghost blocks in, straight from / into xyzq.

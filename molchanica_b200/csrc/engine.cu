@@ -1124,7 +1124,10 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
         void lap(int k) {
             if (!on) return;
             const auto now = std::chrono::steady_clock::now();
-            c->trace_t[k] += std::chrono::duration<double>(now - t).count();
+            const double d = std::chrono::duration<double>(now - t).count();
+            c->trace_t[k] += d;
+            if (d > 5e-3) fprintf(stderr, "[mc_step stall, device %d] call %lld: phase %d took %.2f ms (steps since build %d)\n", c->device,
+                                  (long long)c->trace_calls, k, d * 1e3, c->steps_since_build);
             t = now;
         }
     } trc{c, c->trace_step && n_steps == 1 && ext_forces != nullptr /* the per-step calls of an end-to-end loop */, std::chrono::steady_clock::now()};

@@ -1,5 +1,7 @@
 // engine.cuh -- the handle behind include/molchanica_md.h (shared by engine.cu and comm.cu)
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -10,6 +12,12 @@
 #include "pme.cuh"
 #include "group_energy.cuh"
 
+// Decomposed handles size many buffers by what a rank holds (owned + ghost atoms), which drifts by a few atoms per rebuild: with
+// exact first allocations every such buffer is freed and allocated again the first time the count goes up -- possibly hundreds
+// of steps into a run, and a cudaFree is a device-wide synchronisation (seen as sporadic 40-190 ms steps in the 2-GPU
+// end-to-end leg, profiles/e2e_stall_r2w1.txt).  mc_comm_init sets this: first allocations get the head-room as well.
+inline bool g_devbuf_roomy = false;
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -19,7 +27,10 @@ struct DevBuf {
         if (want <= n && p) return cudaSuccess;
         // a buffer that has to grow a second time gets head-room: sizes that follow the atoms a rank owns drift up and down by a
         // few atoms per rebuild, and every cudaFree is a device-wide synchronisation (with a collective in flight: milliseconds)
-        if (p) { cudaFree(p); want += want / 8 + 256; }
+        static const bool trace = getenv("MC_TRACE_ALLOC") != nullptr;  // stderr line per (re)allocation: finds stalls of a steady loop
+        if (trace) fprintf(stderr, "[mc alloc] %zu -> %zu elements of %zu bytes%s\n", n, want, sizeof(T), p ? " (cudaFree + cudaMalloc)" : "");
+        if (p || g_devbuf_roomy) want += want / 8 + 256;
+        if (p) cudaFree(p);
         p = nullptr;
         n = 0;
         if (want == 0) want = 1;
