@@ -17,7 +17,9 @@ echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pair_force_kernel -s 40 -c 2 \
     -o gpurun_out/pair_force_$TAG -f python bench.py --steps 40 --warmup 10 --no-cpu --no-e2e --no-secondary --no-steady > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"
+if [ -n "$MC_BASELINE_ROWS_NCU" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:rows_build_kernel -s 4 -c 1 \
     -o gpurun_out/rows_build_$TAG -f python bench.py --steps 40 --warmup 150 --no-cpu --no-e2e --no-secondary --no-steady > gpurun_out/ncu_rb_$TAG.log 2>&1
 echo "ncu rows_build rc=$?"
+fi
 ls -la gpurun_out | tail -15
