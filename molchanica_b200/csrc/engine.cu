@@ -583,6 +583,11 @@ extern "C" int mc_set_option(mc_ctx *c, const char *name, double value) {
     } else if (k == "rows_interleave") {
         c->rows_interleave = value != 0.0 ? 1 : 0;
         c->list_valid = false;
+    } else if (k == "build_split") {
+        MC_REQUIRE(c, value >= 0.0 && value <= 64.0, "mc_set_option: build_split is 0 (automatic) .. 64");
+        c->build_split = (int)value;
+    } else if (k == "rows_dense") {  // A/B knob: 0 = dense systems build as in round 2 (8 consumer warps, count + second sweep)
+        c->rows_dense = value != 0.0;
     } else if (k == "rows_min_blocks") {  // register budget of rows_build_kernel: 3 CTAs per SM (72 registers) or 2 (112)
         MC_REQUIRE(c, value == 2.0 || value == 3.0, "mc_set_option: rows_min_blocks is 2 or 3");
         c->rows_min_blocks = (int)value;
@@ -702,13 +707,14 @@ int engine_build_rows(mc_ctx *c) {
     uint32_t *h_ctl = reinterpret_cast<uint32_t *>(c->h_pinned);
     size_t total = 0;
     bool tiled = c->use_tile;
-    bool ilv = false;
+    bool ilv = false, no_row_hint = false;
     c->ilv_valid = false;
     const float rc_in = std::max(c->rc_lj, c->rc_q);
     const float rc2_inner = rc_in * rc_in;
     const int grid_cells = c->periodic ? c->h_grid.ncell : (int)c->ncell_cap;
     const int est_cells = c->periodic ? c->h_grid.ncell : std::max(1, n / 256);
-    const int split = std::max(1, std::min(8, (4 * c->n_sms + est_cells - 1) / est_cells));
+    int split = std::max(1, std::min(8, (4 * c->n_sms + est_cells - 1) / est_cells));
+    if (c->build_split > 0) split = c->build_split;  // option "build_split" (A/B): slices per cell of the list build
     // compact rows (16-bit tile-local indices) for the TMA-staged force kernel whenever its tile + LJ table fit shared memory
     bool compact = tiled && c->periodic && c->pair_tile_fits && (c->use_pair_tile == 1 || (c->use_pair_tile == 2 && c->n_rows_sorted() >= 16384));
     while (tiled) {
@@ -726,8 +732,9 @@ int engine_build_rows(mc_ctx *c) {
                           c->orig[c->cur].p, es, ei, c->nbr_count.p, c->nbr_start.p,
                           compact ? static_cast<void *>(c->nbr_list16.p) : static_cast<void *>(c->nbr_list.p), compact, c->pair_uniform,
                           (uint32_t)std::min<size_t>(cap_now, 0xffffffffu), tile_cap_now, c->tile_need.p, st, &c->launches,
-                          c->build_variant, c->row_stage_limit ? std::min(c->row_len_hint, c->row_stage_limit) : c->row_len_hint,
-                          rows_v2 ? c->rows_plan.p : nullptr, c->rows_min_blocks);
+                          c->build_variant, no_row_hint ? 0u : (c->row_stage_limit ? std::min(c->row_len_hint, c->row_stage_limit) : c->row_len_hint),
+                          rows_v2 ? c->rows_plan.p : nullptr, c->rows_dense ? c->rows_min_blocks : -c->rows_min_blocks,
+                          c->rows_dense ? c->slot_of_orig.p : nullptr);
         // quad-interleaved copy for the 8-lane force kernel: its sizes pass rides in front of the build's own host sync
         // (ctl[7] = entries of the copy), the copy itself follows once the list is known to be complete
         ilv = !compact && !c->pair_uniform && c->pair_lanes == 8 && c->rows_interleave;
@@ -737,10 +744,19 @@ int engine_build_rows(mc_ctx *c) {
         }
         MC_CUDA(c, cudaMemcpyAsync(h_ctl, c->tile_need.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         MC_CUDA(c, cudaStreamSynchronize(st));
+        if ((h_ctl[3] & 2u) && !(h_ctl[3] & 1u)) {
+            // single-sweep build of a dense system: a row outgrew the space claimed from the previous build's longest row
+            // (+ 25 %); the sweep counted on, so the new longest row is known -- build again with it
+            // -- this time counting first (always fits), the next build of the system uses the new length
+            c->row_len_hint = std::max(c->row_len_hint, h_ctl[6]);
+            no_row_hint = true;
+            continue;
+        }
         if (h_ctl[3] != 0) {  // a neighbourhood did not fit the tile
             uint32_t need = (h_ctl[2] + h_ctl[2] / 4 + 127u) & ~31u;  // 25 % head-room + NaN padding to whole chunks
-            if (need > tile_sweep_max_atoms() && ((h_ctl[2] + 127u) & ~31u) <= tile_sweep_max_atoms()) need = tile_sweep_max_atoms();
-            if (need <= tile_sweep_max_atoms()) { c->tile_cap = std::max(c->tile_cap, need); c->tile_max_m = 0; continue; }
+            const uint32_t max_atoms = (rows_v2 && c->rows_dense) ? tile_sweep_max_atoms_dense() : tile_sweep_max_atoms();
+            if (need > max_atoms && ((h_ctl[2] + 127u) & ~31u) <= max_atoms) need = max_atoms;
+            if (need <= max_atoms) { c->tile_cap = std::max(c->tile_cap, need); c->tile_max_m = 0; continue; }
             tiled = c->use_tile = false;  // too dense for shared memory: two-pass global sweep from now on
             compact = false;
             break;

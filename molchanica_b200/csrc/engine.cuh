@@ -129,6 +129,8 @@ struct mc_ctx {
     bool ilv_valid = false;    // nbr_ilv / ilv_qbase describe the current list
     int build_variant = 2;     // option "build_variant": 2 = rows_build_kernel (default), 1 = tile_build_kernel (tile_build.cu)
     uint32_t row_len_hint = 0; // longest row of the last build (0: none yet)
+    int build_split = 0;       // option "build_split": slices per cell of the list build (0 = from the cell count)
+    bool rows_dense = true;    // option "rows_dense": 16 consumer warps + single direct sweep where a tile leaves room for one CTA per SM
     int rows_min_blocks = 3;   // option "rows_min_blocks"
     uint32_t row_stage_limit = 0;  // option "row_stage_limit" (testing): cap on the hint, forces the two-sweep path for longer rows
     int use_pair_tile = 0;     // option "pair_tile": compact rows (16-bit tile-local indices) + TMA-staged force kernel (pair_tile.cu):

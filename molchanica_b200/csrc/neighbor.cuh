@@ -28,11 +28,13 @@ void launch_export_rows(int n, const int *orig, const uint32_t *nbr_count, const
 // tile_build.cu -- single-pass TMA-staged build
 cudaError_t tile_sweep_prepare();
 uint32_t tile_sweep_max_atoms();
+uint32_t tile_sweep_max_atoms_dense();  // rows_build_kernel, one CTA per SM (dense systems)
 void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
                        const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
                        const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, void *nbr_list, bool compact, bool partition,
                        uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches, int variant = 1,
-                       uint32_t row_hint = 0, uint32_t *plan = nullptr, int variant_min_blocks = 3);
+                       uint32_t row_hint = 0, uint32_t *plan = nullptr, int variant_min_blocks = 3,
+                       const int *slot_of_orig = nullptr /* rows_build_kernel: exclusions filtered after the sweep */);
 size_t rows_plan_words(int grid_cells);  // size of `plan` (uint32_t), the per-cell staging records of variant 2
 // variant = 2 (the engine's default; needs `plan`): global-slot rows without partition are built by rows_build_kernel (ballot compaction, rows staged in
 // shared memory when row_hint -- the longest row of the previous build, ctl[6] -- says they fit); 1: tile_build_kernel always.

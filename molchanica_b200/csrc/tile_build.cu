@@ -474,6 +474,8 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MC_TILE_MIN_BLOCKS) til
 // Row content and order are those of tile_build_kernel (ascending tile index); row placement follows completion order.
 constexpr int RB_A = 4;           // atoms per quad
 constexpr int RB_MAX_STAGES = 4;  // tiles in flight per CTA
+constexpr int RB_WARPS_DENSE = 16;  // consumer warps of the one-CTA-per-SM configuration (dense systems)
+constexpr size_t RB_DENSE_BUDGET = 226u * 1024u;  // dynamic shared memory of that configuration
 
 __device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
 
@@ -518,7 +520,8 @@ struct RbQuad {
 
 // One pass of a quad over the tile.  MODE 0: stage the rows (16-bit tile indices, the first `stage_cap` entries of each)
 // and count; MODE 1: write the rows flagged in `direct` straight to nbr_list at row[k] (second pass of rows that did not
-// fit the staging space).  cnt[k] = row lengths (warp-uniform).  EXCL: some atom of the quad carries exclusions (rare; the
+// fit the staging space); MODE 2: ONE pass that writes every row straight to the space claimed for it beforehand (at most
+// `stage_cap` entries each -- the argument carries the row capacity here -- and counts on, so that an overflow is seen).  cnt[k] = row lengths (warp-uniform).  EXCL: some atom of the quad carries exclusions (rare; the
 // common instantiation keeps every decision in a predicate register).
 template <int WRAP, int MODE, bool EXCL>
 __device__ __forceinline__ void rb_sweep(const float4 *tile, const uint32_t *tile_slot, uint32_t m_pad, const GridParams &g, float rl2,
@@ -556,8 +559,11 @@ __device__ __forceinline__ void rb_sweep(const float4 *tile, const uint32_t *til
                 const rb_sptr q = sp[k] + 2u * RB_A * below;
                 if (hit && q < se) rb_store16(q, (uint16_t)t);
                 sp[k] += 2u * RB_A * all;
-            } else {
+            } else if (MODE == 1) {
                 if (hit && ((direct >> k) & 1u)) nbr_list[lo[k] + below] = tile_slot[t];
+                lo[k] += all;
+            } else {
+                if (hit && lo[k] + below - row[k] < stage_cap) nbr_list[lo[k] + below] = tile_slot[t];
                 lo[k] += all;
             }
         }
@@ -567,12 +573,38 @@ __device__ __forceinline__ void rb_sweep(const float4 *tile, const uint32_t *til
         cnt[k] = MODE == 0 ? (uint32_t)((sp[k] - rb_sptr_of(stage)) / (2u * RB_A)) : lo[k] - row[k];
 }
 
-template <int WRAP>
+// Exclusions of rows_build_kernel, after the sweep instead of inside it: the sweep lists every atom inside the radius (no
+// per-hit gather of the candidate's original id -- a dependent global round trip that bounded the build of dense solvated
+// systems), then the quad's rows are filtered in place: lane x < n_ex holds the SLOT of the atom's x-th excluded partner
+// (slot_of_orig of its original id; -1 = not held by this rank), a row entry equal to one of them is dropped and the entries
+// behind it move up.  Chunks of 32 entries: every lane has read its entry before the ballot, the kept ones are written at or
+// below the chunk's own first position.  Returns the new row length.
+__device__ __forceinline__ uint32_t rb_filter_row(uint32_t *__restrict__ nbr_list, uint32_t row, uint32_t n, uint32_t ps, int n_ex, int lane) {
+    const uint32_t lt = lanemask_lt(lane);
+    uint32_t w = 0u;
+    for (uint32_t b = 0u; b < n; b += 32u) {
+        const uint32_t e = b + (uint32_t)lane;
+        bool keep = e < n;
+        uint32_t v = 0xffffffffu;
+        if (keep) v = nbr_list[row + e];
+        for (int x = 0; x < n_ex; ++x) {
+            const uint32_t partner = __shfl_sync(MC_FULL_MASK, ps, x);  // every lane takes part (no short-circuit around it)
+            keep = keep && v != partner;
+        }
+        const uint32_t mask = __ballot_sync(MC_FULL_MASK, keep);
+        if (keep) nbr_list[row + w + (uint32_t)__popc(mask & lt)] = v;
+        w += (uint32_t)__popc(mask);
+    }
+    return w;
+}
+
+template <int WRAP, bool EXK /* the system carries exclusions (its own instantiation: the plain one keeps its 72 registers) */>
 __device__ __forceinline__ void rb_quad(const float4 *tile, const uint32_t *tile_slot, const StageMeta &M, uint32_t m_pad, uint32_t i0,
                                         int n_rows, const GridParams &g, float rl2, const int *__restrict__ orig,
                                         const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx, uint16_t *stage,
                                         uint32_t stage_cap, uint32_t *__restrict__ nbr_count, uint32_t *__restrict__ nbr_start,
-                                        uint32_t *__restrict__ nbr_list, uint32_t list_cap, uint32_t *__restrict__ ctl, int lane) {
+                                        uint32_t *__restrict__ nbr_list, uint32_t list_cap, uint32_t *__restrict__ ctl, int lane,
+                                        uint32_t row_cap, const int *__restrict__ slot_of_orig) {
     const float qnan = __int_as_float(0x7fffffff);
     RbQuad Q;
     uint32_t valid = 0u;
@@ -590,7 +622,7 @@ __device__ __forceinline__ void rb_quad(const float4 *tile, const uint32_t *tile
             const float4 p = tile[Q.t_self[k]];  // the own cell is part of the staged tile
             Q.npxy[k] = make_float2(-p.x, -p.y);
             Q.npz[k] = -p.z;
-            if (excl_start) {
+            if (EXK && excl_start) {
                 const int oi = orig[i];
                 Q.ex_lo[k] = excl_start[oi];
                 Q.ex_hi[k] = excl_start[oi + 1];
@@ -600,7 +632,54 @@ __device__ __forceinline__ void rb_quad(const float4 *tile, const uint32_t *tile
     }
     if (!valid) return;
     uint32_t cnt[RB_A], row[RB_A] = {0u, 0u, 0u, 0u};
-    if (any_excl) rb_sweep<WRAP, 0, true>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, stage_cap, row, 0u, nbr_list, lane, cnt);
+    if (!EXK) any_excl = false;
+    // exclusions: filtered after the sweep (rb_filter_row) when every atom of the quad has at most 32 partners and the slot
+    // table is there; else inside the sweep (EXCL instantiation)
+    bool post = EXK && any_excl && slot_of_orig != nullptr;
+    uint32_t ps[RB_A];
+#pragma unroll
+    for (int k = 0; k < RB_A; ++k) {
+        ps[k] = 0xffffffffu;
+        if (Q.ex_hi[k] - Q.ex_lo[k] > 32) post = false;
+    }
+    if (post) {
+#pragma unroll
+        for (int k = 0; k < RB_A; ++k)
+            if (lane < Q.ex_hi[k] - Q.ex_lo[k]) ps[k] = (uint32_t)slot_of_orig[excl_idx[Q.ex_lo[k] + lane]];
+    }
+    const bool sweep_excl = EXK && any_excl && !post;
+    if (row_cap) {
+        // Dense systems (rows of a thousand entries: no room to stage them next to a 100+ KB tile): the quad claims row_cap
+        // entries per row up front -- the longest row of the previous build + 25 % -- and writes them in ONE sweep instead of
+        // counting first and sweeping again.  A row that outgrows its space raises bit 1 of ctl[3]; the host then builds again
+        // with the longer hint.  Rows keep their own counts, the padding is never read.
+        uint32_t base = 0u;
+        if (lane == 0) base = atomicAdd(ctl + 1, RB_A * row_cap);
+        base = __shfl_sync(MC_FULL_MASK, base, 0);
+        if ((uint64_t)base + RB_A * row_cap > (uint64_t)list_cap) return;  // the host grows the list and builds again
+#pragma unroll
+        for (int k = 0; k < RB_A; ++k) row[k] = base + (uint32_t)k * row_cap;
+        if (EXK && sweep_excl) rb_sweep<WRAP, 2, EXK>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, row_cap, row, 0u, nbr_list, lane, cnt);
+        else rb_sweep<WRAP, 2, false>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, row_cap, row, 0u, nbr_list, lane, cnt);
+        uint32_t mx = 0u;
+        if (post) __syncwarp();  // the rows written by all lanes are visible to the warp
+#pragma unroll
+        for (int k = 0; k < RB_A; ++k) {
+            mx = max(mx, cnt[k]);  // (before the filter: the space is claimed for the unfiltered row)
+            uint32_t len = min(cnt[k], row_cap);
+            if (post && Q.ex_hi[k] > Q.ex_lo[k]) len = rb_filter_row(nbr_list, row[k], len, ps[k], Q.ex_hi[k] - Q.ex_lo[k], lane);
+            if (lane == k && ((valid >> k) & 1u)) {
+                nbr_start[i0 + (uint32_t)k] = row[k];
+                nbr_count[i0 + (uint32_t)k] = len;
+            }
+        }
+        if (lane == 0) {
+            if (mx > *reinterpret_cast<volatile uint32_t *>(ctl + 6)) atomicMax(ctl + 6, mx);
+            if (mx > row_cap) atomicOr(ctl + 3, 2u);
+        }
+        return;
+    }
+    if (EXK && sweep_excl) rb_sweep<WRAP, 0, EXK>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, stage_cap, row, 0u, nbr_list, lane, cnt);
     else rb_sweep<WRAP, 0, false>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, stage_cap, row, 0u, nbr_list, lane, cnt);
     // claim the quad's rows (each padded to 8 entries = whole 32-byte sectors) with one atomicAdd
     uint32_t tot = 0u, mx = 0u, direct = 0u;
@@ -634,10 +713,18 @@ __device__ __forceinline__ void rb_quad(const float4 *tile, const uint32_t *tile
     }
     if (direct) {
         uint32_t cnt2[RB_A];
-        if (any_excl) rb_sweep<WRAP, 1, true>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, stage_cap, row, direct, nbr_list, lane, cnt2);
+        if (EXK && sweep_excl) rb_sweep<WRAP, 1, EXK>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, stage_cap, row, direct, nbr_list, lane, cnt2);
         else rb_sweep<WRAP, 1, false>(tile, tile_slot, m_pad, g, rl2, Q, orig, excl_idx, stage, stage_cap, row, direct, nbr_list, lane, cnt2);
     }
-    __syncwarp();  // copy-out reads done before the next quad's staging overwrites the space
+    __syncwarp();  // copy-out reads done before the next quad's staging overwrites the space (and the rows are visible to the warp)
+    if (post) {
+#pragma unroll
+        for (int k = 0; k < RB_A; ++k) {
+            if (Q.ex_hi[k] <= Q.ex_lo[k]) continue;  // warp-uniform
+            const uint32_t len = rb_filter_row(nbr_list, row[k], cnt[k], ps[k], Q.ex_hi[k] - Q.ex_lo[k], lane);
+            if (lane == k && ((valid >> k) & 1u)) nbr_count[i0 + (uint32_t)k] = len;
+        }
+    }
 }
 
 // Per-cell staging record of rows_build_kernel's producer (RB_PLAN_WORDS words, written once per build by
@@ -703,13 +790,17 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) 
 inline void mbar_wait_sleep(uint64_t *bar, uint32_t parity) { shim_mbar_wait(bar, parity); }
 #endif
 
-template <int MINB>
-__global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MINB) rows_build_kernel(
+// NW consumer warps: 8 where several CTAs share an SM; 16 where the tile leaves room for one CTA only (dense systems), which
+// would otherwise run 9 warps per SM and wait on every shared-memory round trip.
+template <int MINB, int NW, bool EXK>
+__global__ void __launch_bounds__((NW + 1) * 32, MINB) rows_build_kernel(
     int n_rows, const float4 *__restrict__ xyzq, const uint32_t *__restrict__ plan, const GridParams *__restrict__ gp, float rl2,
     const int *__restrict__ orig, const int32_t *__restrict__ excl_start, const int32_t *__restrict__ excl_idx,
     uint32_t *__restrict__ nbr_count, uint32_t *__restrict__ nbr_start, uint32_t *__restrict__ nbr_list, uint32_t list_cap,
     uint32_t tile_cap, uint32_t stage_cap /* staged entries per row; 0: every row takes two sweeps */, int split, int n_stages,
-    uint32_t *__restrict__ ctl /* as tile_build_kernel; [6] longest row */) {
+    uint32_t *__restrict__ ctl /* as tile_build_kernel; [3] bit 1: a row outgrew row_cap; [6] longest row */,
+    uint32_t row_cap /* > 0 (with stage_cap == 0): single direct sweep into row_cap entries per row */,
+    const int *__restrict__ slot_of_orig /* exclusions are filtered after the sweep when given (rb_filter_row) */) {
     MC_DYN_SHARED_ALIGNED(unsigned char, smem_raw, 128);
     const size_t stage_bytes = (size_t)tile_cap * (sizeof(float4) + sizeof(uint32_t));
     __shared__ __align__(8) uint64_t full_bar[RB_MAX_STAGES], empty_bar[RB_MAX_STAGES];
@@ -720,7 +811,7 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MINB) rows_build_kernel
     if (threadIdx.x == 0) {
         for (int s = 0; s < RB_MAX_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], TILE_WARPS);
+            mbar_init(&empty_bar[s], NW);
         }
     }
     __syncthreads();
@@ -756,7 +847,7 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MINB) rows_build_kernel
             if (!done) {
                 if (cu.flags & 0x100u) continue;  // empty cell / ghost layer
                 if (((cu.m + 31u) & ~31u) > tile_cap) {  // does not fit: the host enlarges the tile (or falls back)
-                    if (lane == 0) ctl[3] = 1u;
+                    if (lane == 0) atomicOr(ctl + 3, 1u);
                     continue;
                 }
                 a0 = cu.a0; a1 = cu.a1; m = cu.m; self_off = cu.self_off; wrap = (int)(cu.flags & 0xffu);
@@ -792,7 +883,7 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MINB) rows_build_kernel
         // ===== consumers: decoupled warps, quads dealt round-robin across items =====
         const int cw = warp - 1;
         uint16_t *stage = reinterpret_cast<uint16_t *>(smem_raw + (size_t)n_stages * stage_bytes) + (size_t)cw * RB_A * stage_cap;
-        uint32_t rot = 0;  // quads dealt so far (mod TILE_WARPS): the same number on every warp
+        uint32_t rot = 0;  // quads dealt so far (mod NW): the same number on every warp
         int s = 0;
         uint32_t ph = 0;
         for (;;) {
@@ -808,14 +899,14 @@ __global__ void __launch_bounds__((TILE_WARPS + 1) * 32, MINB) rows_build_kernel
             // this item's quads: q = slice, slice + split, ...
             uint32_t nq = n_quads_cell;
             if (split > 1) nq = n_quads_cell > M.slice ? (n_quads_cell - M.slice + (uint32_t)split - 1u) / (uint32_t)split : 0u;
-            for (uint32_t j = ((uint32_t)cw - rot) & (TILE_WARPS - 1); j < nq; j += TILE_WARPS) {
+            for (uint32_t j = ((uint32_t)cw - rot) & (NW - 1); j < nq; j += NW) {
                 const uint32_t i0 = M.a0 + (M.slice + j * (uint32_t)split) * RB_A;
-#define MC_RBQ(W_) rb_quad<W_>(tile, tile_slot, M, m_pad, i0, n_rows, g, rl2, orig, excl_start, excl_idx, stage, stage_cap, nbr_count, \
-                               nbr_start, nbr_list, list_cap, ctl, lane)
+#define MC_RBQ(W_) rb_quad<W_, EXK>(tile, tile_slot, M, m_pad, i0, n_rows, g, rl2, orig, excl_start, excl_idx, stage, stage_cap, nbr_count, \
+                               nbr_start, nbr_list, list_cap, ctl, lane, row_cap, slot_of_orig)
                 if (M.wrap == 0) MC_RBQ(0); else if (M.wrap == 1) MC_RBQ(1); else MC_RBQ(2);
 #undef MC_RBQ
             }
-            rot = (rot + nq) & (TILE_WARPS - 1);
+            rot = (rot + nq) & (NW - 1);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
             if (++s == n_stages) { s = 0; ph ^= 1u; }
@@ -871,14 +962,21 @@ cudaError_t tile_sweep_prepare() {
 #define MC_TB_ATTR(I, P) if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_build_kernel<I, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     MC_TB_ATTR(uint32_t, false) MC_TB_ATTR(uint32_t, true) MC_TB_ATTR(uint16_t, false) MC_TB_ATTR(uint16_t, true)
 #undef MC_TB_ATTR
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_build_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_build_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+#define MC_RB_ATTR(X) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_build_kernel<2, TILE_WARPS, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_build_kernel<3, TILE_WARPS, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_build_kernel<1, RB_WARPS_DENSE, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_DENSE_BUDGET);
+    MC_RB_ATTR(false) MC_RB_ATTR(true)
+#undef MC_RB_ATTR
     return e;
 }
 
 // 16 B position + 4 B slot id per staged atom in 200 KB of shared memory; tiles above half of that run
 // single-buffered (no copy/sweep overlap, but still one L2 read per cell instead of one per atom)
 uint32_t tile_sweep_max_atoms() { return ((200u * 1024u) / 20u) & ~31u; }
+// rows_build_kernel's one-CTA-per-SM configuration takes all the shared memory a block can have (227 KB less the kernel's
+// few hundred static bytes): C3's largest 27-cell neighbourhood holds 11,355 atoms = 222 KB
+uint32_t tile_sweep_max_atoms_dense() { return (uint32_t)(RB_DENSE_BUDGET / 20u) & ~31u; }
 
 template <typename IDX, bool PART>
 static void launch_tile_build_t(int n_rows, long long items, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
@@ -903,9 +1001,12 @@ static void launch_tile_build_t(int n_rows, long long items, int split, int n_sm
 static void launch_rows_build(int n_rows, int grid_cells, long long items, int split, int n_sms, const float4 *xyzq, const uint32_t *cell_start,
                               const GridParams *g, float rl2, const int *orig, const int32_t *excl_start, const int32_t *excl_idx,
                               uint32_t *nbr_count, uint32_t *nbr_start, uint32_t *nbr_list, uint32_t list_cap, uint32_t tile_cap,
-                              uint32_t row_hint, uint32_t *plan, uint32_t *ctl, cudaStream_t st, int min_blocks) {
+                              uint32_t row_hint, uint32_t *plan, uint32_t *ctl, cudaStream_t st, int min_blocks, const int *slot_of_orig) {
+    const bool no_dense = min_blocks < 0;  // option rows_dense = 0 (A/B): the round-2 configuration, 8 consumer warps, two sweeps
+    if (min_blocks < 0) min_blocks = -min_blocks;
     const size_t budget = 200u * 1024u, per_tile = (size_t)tile_cap * 20u;
-    uint32_t stage_cap = row_hint ? ((row_hint + row_hint / 4u + 47u) & ~31u) : 0u;
+    const uint32_t want_stage = row_hint ? ((row_hint + row_hint / 4u + 47u) & ~31u) : 0u;
+    uint32_t stage_cap = want_stage, row_cap = 0u;
     size_t staging = (size_t)TILE_WARPS * RB_A * stage_cap * sizeof(uint16_t);
     if (per_tile + staging > budget) { stage_cap = 0u; staging = 0; }
     int n_stages = 1;
@@ -913,19 +1014,33 @@ static void launch_rows_build(int n_rows, int grid_cells, long long items, int s
     if (4 * per_tile + staging <= per_cta) n_stages = 4;
     else if (3 * per_tile + staging <= per_cta) n_stages = 3;
     else if (2 * per_tile + staging <= budget) n_stages = 2;
+    // Tiles that leave room for ONE CTA per SM (dense systems: C3's 27 cells hold 7,400 atoms = 148 KB): twice the consumer
+    // warps, and rows either staged (if that still fits) or written in a single direct sweep into row_cap entries each once
+    // the previous build has told how long rows get (the first build of a system counts first and sweeps again).
+    const bool dense = ((size_t)n_stages * per_tile + staging > 110u * 1024u || per_tile > budget) && !no_dense;
+    if (dense) {
+        const size_t staging16 = (size_t)RB_WARPS_DENSE * RB_A * want_stage * sizeof(uint16_t);
+        if (want_stage && per_tile + staging16 <= RB_DENSE_BUDGET) { stage_cap = want_stage; staging = staging16; }
+        else { stage_cap = 0u; staging = 0; row_cap = row_hint ? ((row_hint + row_hint / 4u + 15u) & ~7u) : 0u; }
+        n_stages = 2 * per_tile + staging <= RB_DENSE_BUDGET ? 2 : 1;
+    }
     const size_t smem = (size_t)n_stages * per_tile + staging;
     cudaMemsetAsync(ctl, 0, 8 * sizeof(uint32_t), st);
     MC_LAUNCH(rows_plan_kernel, div_up((size_t)grid_cells * 32, 256), 256, 0, st, cell_start, g, plan, ctl);
-#define MC_RB_GO(MINB_) do { \
+#define MC_RB_GO(MINB_, NW_) do { if (excl_start) MC_RB_GO_X(MINB_, NW_, true); else MC_RB_GO_X(MINB_, NW_, false); } while (0)
+#define MC_RB_GO_X(MINB_, NW_, X_) do { \
         int per_sm = 1; \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_build_kernel<MINB_>, (TILE_WARPS + 1) * 32, smem); \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_build_kernel<MINB_, NW_, X_>, (NW_ + 1) * 32, smem); \
         if (per_sm < 1) per_sm = 1; \
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, (long long)n_sms * per_sm)); \
-        MC_LAUNCH(rows_build_kernel<MINB_>, grid, (TILE_WARPS + 1) * 32, smem, st, n_rows, xyzq, plan, g, rl2, orig, excl_start, excl_idx, \
-                  nbr_count, nbr_start, nbr_list, list_cap, tile_cap, stage_cap, split, n_stages, ctl); \
+        MC_LAUNCH(rows_build_kernel<MINB_ MC_COMMA NW_ MC_COMMA X_>, grid, (NW_ + 1) * 32, smem, st, n_rows, xyzq, plan, g, rl2, orig, excl_start, excl_idx, \
+                  nbr_count, nbr_start, nbr_list, list_cap, tile_cap, stage_cap, split, n_stages, ctl, row_cap, slot_of_orig); \
     } while (0)
-    if (min_blocks == 2) MC_RB_GO(2); else MC_RB_GO(3);
+    if (dense) MC_RB_GO(1, RB_WARPS_DENSE);
+    else if (min_blocks == 2) MC_RB_GO(2, TILE_WARPS);
+    else MC_RB_GO(3, TILE_WARPS);
 #undef MC_RB_GO
+#undef MC_RB_GO_X
 }
 
 size_t rows_plan_words(int grid_cells) { return (size_t)grid_cells * RB_PLAN_WORDS; }
@@ -934,11 +1049,11 @@ void launch_tile_build(int n_rows, int grid_cells, int split, int n_sms, const f
                        const GridParams *g, float rl2, float rc2_inner, const int *orig, const int32_t *excl_start,
                        const int32_t *excl_idx, uint32_t *nbr_count, uint32_t *nbr_start, void *nbr_list, bool compact, bool partition,
                        uint32_t list_cap, uint32_t tile_cap, uint32_t *ctl, cudaStream_t st, int64_t *launches, int variant,
-                       uint32_t row_hint, uint32_t *plan, int variant_min_blocks) {
+                       uint32_t row_hint, uint32_t *plan, int variant_min_blocks, const int *slot_of_orig) {
     const long long items = (long long)grid_cells * split;
     if (variant == 2 && !compact && !partition && plan) {
         launch_rows_build(n_rows, grid_cells, items, split, n_sms, xyzq, cell_start, g, rl2, orig, excl_start, excl_idx, nbr_count, nbr_start,
-                          static_cast<uint32_t *>(nbr_list), list_cap, tile_cap, row_hint, plan, ctl, st, variant_min_blocks);
+                          static_cast<uint32_t *>(nbr_list), list_cap, tile_cap, row_hint, plan, ctl, st, variant_min_blocks, slot_of_orig);
         *launches += 2;
         return;
     }

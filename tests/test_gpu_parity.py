@@ -100,23 +100,27 @@ def test_both_list_build_kernels_write_the_same_rows(name, Engine, oracle):
     """rows_build_kernel (default: ballot compaction, rows staged in shared memory, decoupled warps) and tile_build_kernel
     (option build_variant = 1) list the oracle's pairs bit for bit -- on the first build (no row-length hint yet: every row
     takes the two-sweep path), on a rebuild (rows staged), and with the staging space capped below the row length (mixed) --
-    and the forces computed from either list are the same numbers (same row order: ascending tile index)."""
+    and the forces computed from either list are the same numbers (same row order: ascending tile index).
+    Dense systems (solv23558: a 148 KB tile, one CTA per SM) take rows_build_kernel's other configuration: 16 consumer warps,
+    first build count + second sweep, later builds ONE sweep into space claimed from the previous build's longest row; with
+    the hint capped (limit 1) that space overflows and the build must fall back; rows_dense = 0 is round 2's configuration."""
     w = _cases()[name]()
     o_start, o_idx = oracle.neighbors(w)
     forces = []
-    for variant, limit in ((1, 0), (2, 0), (2, 1)):
+    for variant, limit, dense in ((1, 0, 1), (2, 0, 1), (2, 1, 1), (2, 0, 0)):
         e = Engine.from_workload(w)
         e.set_option("build_variant", variant)
         e.set_option("row_stage_limit", limit)
-        for rep in range(2):  # second build: the hint of the first one is there
+        e.set_option("rows_dense", dense)
+        for rep in range(3):  # later builds: the hint of the first one is there
             e.build_neighbors()
             start, idx = e.neighbors()
-            assert np.array_equal(start, o_start) and np.array_equal(idx, o_idx), (variant, limit, rep)
+            assert np.array_equal(start, o_start) and np.array_equal(idx, o_idx), (variant, limit, dense, rep)
             e.set_positions(w["xyzq"])  # invalidates the list
         e.compute_forces()
         forces.append(e.forces())
         e.close()
-    assert np.array_equal(forces[0], forces[1]) and np.array_equal(forces[0], forces[2])
+    assert all(np.array_equal(forces[0], f) for f in forces[1:])
 
 
 @pytest.mark.parametrize("lanes", [4, 8, 16, 32])
