@@ -128,6 +128,7 @@ static inline double atomicAdd(double *a, double v) {
     return o;
 }
 static inline int atomicOr(int *a, int v) { return std::atomic_ref<int>(*a).fetch_or(v); }
+static inline unsigned atomicOr(unsigned *a, unsigned v) { return std::atomic_ref<unsigned>(*a).fetch_or(v); }
 static inline unsigned atomicAdd(unsigned *a, unsigned v) { return std::atomic_ref<unsigned>(*a).fetch_add(v); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
