@@ -268,6 +268,8 @@ extern "C" int mc_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const u
     c->n_waters = 0;
     c->n_vsites = 0;
     c->n_hclusters = c->n_hconstraints = 0;
+    c->h_in_water.clear();
+    c->h_in_hcluster.clear();
     c->have_mols = false;
     c->n_pairs_listed = 0;
     c->total_mass = 0.0;
@@ -422,6 +424,8 @@ extern "C" int mc_set_hbond_constraints(mc_ctx *c, int64_t m, const int32_t *clu
         for (int a = 0; a < 4; ++a) {
             if (q[a] < 0 || q[a] >= n) continue;  // range errors are reported below
             MC_REQUIRE(c, !seen[(size_t)q[a]], "mc_set_hbond_constraints: an atom appears in two clusters");
+            MC_REQUIRE(c, c->h_in_water.empty() || !c->h_in_water[(size_t)q[a]],
+                       "mc_set_hbond_constraints: an atom of a rigid water (mc_set_rigid_waters) cannot also sit in a hydrogen cluster");
             seen[(size_t)q[a]] = 1;
         }
         MC_REQUIRE(c, q[0] >= 0 && q[0] < n, "mc_set_hbond_constraints: heavy atom id out of range");
@@ -444,6 +448,7 @@ extern "C" int mc_set_hbond_constraints(mc_ctx *c, int64_t m, const int32_t *clu
     }
     c->n_hclusters = (int)m;
     c->n_hconstraints = n_con;
+    if (m) c->h_in_hcluster.swap(seen); else c->h_in_hcluster.clear();
     return MC_OK;
 }
 
@@ -453,6 +458,20 @@ extern "C" int mc_set_virtual_sites(mc_ctx *c, int64_t m, const int32_t *quads, 
     cudaSetDevice(c->device);
     MC_REQUIRE(c, !c->comm_active, "mc_set_virtual_sites: virtual sites on a decomposed handle are not supported yet");
     MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || quads), "mc_set_virtual_sites: bad arguments");
+    {
+        // vsite_spread hands a site's force to its parents with plain read-modify-writes, vsite_construct writes the site: a site
+        // id, or a parent, that appears in two sites would race (1 = used as a site, 2 = used as a parent)
+        std::vector<uint8_t> used((size_t)std::max<int64_t>(c->n_global, 1), 0);
+        for (int64_t k = 0; k < m; ++k) {
+            for (int a = 0; a < 4; ++a) {
+                const int32_t id = quads[4 * k + a];
+                if (id < 0 || id >= c->n_global) continue;  // range errors are reported by upload_terms below
+                MC_REQUIRE(c, !used[(size_t)id], a == 0 ? "mc_set_virtual_sites: a site id appears twice (or is a parent of another site)"
+                                                         : "mc_set_virtual_sites: a parent atom appears in two sites (or is itself a site)");
+                used[(size_t)id] = a == 0 ? 1 : 2;
+            }
+        }
+    }
     int rc = upload_terms<4, int4>(c, "mc_set_virtual_sites", m, quads, c->vsites, &c->n_vsites);
     if (rc != MC_OK) { c->n_vsites = 0; return rc; }
     c->vsite_a = a; c->vsite_b = b;
@@ -497,8 +516,18 @@ extern "C" int mc_set_rigid_waters(mc_ctx *c, int64_t m, const int32_t *triples,
     MC_REQUIRE(c, m >= 0 && m < ((int64_t)1 << 30) && (m == 0 || triples), "mc_set_rigid_waters: bad arguments");
     MC_REQUIRE(c, m == 0 || (d_oh > 0.f && d_hh > 0.f && d_hh < 2.f * d_oh && m_o > 0.f && m_h > 0.f),
                "mc_set_rigid_waters: need 0 < d_hh < 2 d_oh and positive masses");
+    std::vector<uint8_t> seen((size_t)std::max<int64_t>(c->n_global, 1), 0);  // one thread owns a molecule: no atom may be in two
+    for (int64_t k = 0; k < 3 * m; ++k) {
+        const int32_t id = triples[k];
+        if (id < 0 || id >= c->n_global) continue;  // range errors are reported by upload_terms below
+        MC_REQUIRE(c, !seen[(size_t)id], "mc_set_rigid_waters: an atom appears in two waters (or twice in one)");
+        MC_REQUIRE(c, c->h_in_hcluster.empty() || !c->h_in_hcluster[(size_t)id],
+                   "mc_set_rigid_waters: an atom of a hydrogen cluster (mc_set_hbond_constraints) cannot also sit in a rigid water");
+        seen[(size_t)id] = 1;
+    }
     int rc = upload_terms<3, int4>(c, "mc_set_rigid_waters", m, triples, c->waters, &c->n_waters);
-    if (rc != MC_OK) { c->n_waters = 0; return rc; }
+    if (rc != MC_OK) { c->n_waters = 0; c->h_in_water.clear(); return rc; }
+    if (m) c->h_in_water.swap(seen); else c->h_in_water.clear();
     c->water_d_oh = d_oh; c->water_d_hh = d_hh; c->water_m_o = m_o; c->water_m_h = m_h;
     return MC_OK;
 }

@@ -203,6 +203,9 @@ struct mc_ctx {
     int n_hclusters = 0, n_hconstraints = 0;   // SHAKE clusters of bonds to hydrogen (settle.cu)
     DevBuf<int4> hclusters;
     DevBuf<float> hdist;
+    // host-side record of which constraint owns an atom (original ids): 1 = a rigid water, 2 = a hydrogen cluster.  One thread
+    // owns a molecule / cluster and writes its atoms without atomics, so no atom may sit in two of them
+    std::vector<uint8_t> h_in_water, h_in_hcluster;
     DevBuf<int> shake_fail;
     DevBuf<int> bonded_missing;  // decomposed handles: set by bonded_kernel when a term's partner is not held by this rank
     float shake_tol = 1e-6f;

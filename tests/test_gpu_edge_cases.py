@@ -147,6 +147,32 @@ def test_degenerate_calls(Engine):
     e.close()
 
 
+def test_an_atom_cannot_sit_in_two_constraints(Engine):
+    """One thread owns a rigid water / a hydrogen cluster / a virtual site and writes its atoms without atomics: an atom that
+    sat in two of them would be raced over.  The setters refuse it (MC_E_INVALID) before anything reaches the device."""
+    from molchanica_b200.engine import McError
+    w = W.water_box_c1()
+    e = Engine.from_workload(w)
+    n = len(w["xyzq"])
+    tri = np.arange(n, dtype=np.int32).reshape(-1, 3)
+    e.set_rigid_waters(tri, 0.9572, 1.5139)                  # fine
+    with pytest.raises(McError, match="two waters"):
+        bad = tri.copy(); bad[1, 2] = bad[0, 1]
+        e.set_rigid_waters(bad, 0.9572, 1.5139)
+    e.set_rigid_waters(tri[:10], 0.9572, 1.5139)
+    with pytest.raises(McError, match="rigid water"):         # atom 0 already belongs to the first water
+        e.set_hbond_constraints(np.array([[0, 40, -1, -1]], np.int32), np.array([[1.0, 0, 0]], np.float32))
+    e.set_hbond_constraints(np.array([[30, 31, 32, -1]], np.int32), np.array([[0.9572, 0.9572, 0]], np.float32))   # outside the waters: fine
+    with pytest.raises(McError, match="hydrogen cluster"):
+        e.set_rigid_waters(tri[:11], 0.9572, 1.5139)         # the eleventh water is atoms 30, 31, 32
+    with pytest.raises(McError, match="two sites"):
+        e.set_virtual_sites(np.array([[60, 61, 62, 63], [64, 61, 65, 66]], np.int32), 0.1, 0.1)   # parent 61 shared
+    with pytest.raises(McError, match="site id"):
+        e.set_virtual_sites(np.array([[60, 61, 62, 63], [60, 64, 65, 66]], np.int32), 0.1, 0.1)   # site 60 twice
+    e.set_virtual_sites(np.array([[60, 61, 62, 63], [64, 65, 66, 67]], np.int32), 0.1, 0.1)
+    e.close()
+
+
 def test_docking_scan_edge_cases(Engine, oracle):
     """No poses, a one-atom ligand, a ligand beyond the shared-memory tile, an empty receptor."""
     from molchanica_b200.engine import McError
