@@ -201,8 +201,13 @@ int mc_set_overrides(mc_ctx *ctx, int lj_disabled, int coulomb_disabled);
  * of the reference; 0 = never (default)),
  * "defer_tail" (1: a single-GPU mc_step with ext_forces returns after its last drift and finishes that
  * step -- force evaluation, second half kick -- under the upload of the next call's array, or as soon as anything
- * but positions is asked for; results are the same, only the time at which the work is done moves; 0 (default until
- * the path has been confirmed on hardware) = finish every step inside its own call). */
+ * but positions is asked for; results are the same, only the time at which the work is done moves (confirmed on
+ * hardware in round 2; works on decomposed handles as well); 0 (default) = finish every step inside its own call),
+ * "fused_steps" (1 (default): small plain-NVE systems run all steps of a call in one cooperative launch, md_fused.cu),
+ * A/B knobs kept with their measurements under profiles/: "pair_tile" (TMA-staged pair kernel), "pair_tile_stages",
+ * "rows_interleave" (quad-interleaved index rows), "build_variant" (1 = tile_build_kernel, 2 = rows_build_kernel),
+ * "rows_dense" (0 = dense systems build their list as at the start of round 2), "build_split" (slices per cell),
+ * "rows_min_blocks", "row_stage_limit", "pair_uniform", "sync_rebuild", "lazy_sync", "early_tail", "tile_sweep". */
 int mc_set_option(mc_ctx *ctx, const char *name, double value);
 
 /* Replace positions (and optionally velocities) of the existing atoms, original order. */

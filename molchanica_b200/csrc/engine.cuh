@@ -225,7 +225,7 @@ struct mc_ctx {
     int64_t bl_n = 0;
     float bl_rl2 = 0.f;
     bool fused_steps = true;     // option "fused_steps": small plain-NVE systems take all steps of a call in one cooperative launch (md_fused.cu)
-    bool defer_tail = false;     // option "defer_tail" (off until the path has been confirmed on hardware; bench.py's e2e leg turns it on)
+    bool defer_tail = false;     // option "defer_tail" (opt-in; confirmed on hardware in round 2, bench.py's e2e leg turns it on)
     bool tail_pending = false;   // positions are one step ahead of forces / velocities (half kick outstanding)
     float tail_dt = 0.f;
     const float *tail_ext = nullptr;  // external forces of the outstanding half kick (device, one of the two buffers)
