@@ -147,8 +147,8 @@ int mc_set_dihedrals(mc_ctx *ctx, int64_t m, const int32_t *quads, const float *
  * not depend on the engine's internal atom order.  Static atoms are left alone.
  * MC_THERMOSTAT_CSVR (Bussi-Donadio-Parrinello): at the same point of the step all velocities are scaled by one
  * stochastic factor computed on the device from the kinetic energy; gamma_per_ps is then 1 / tau.  The factor is a
- * function of (seed, step, kinetic energy) only.  Langevin works on decomposed handles too (same noise on any
- * decomposition); CSVR is for single-GPU handles. */
+ * function of (seed, step, kinetic energy) only.  Both work on decomposed handles: Langevin draws the same noise on any
+ * decomposition, CSVR all-reduces the kinetic energy (24 bytes per step, on the stream). */
 int mc_set_thermostat(mc_ctx *ctx, int kind, float temperature_k, float gamma_per_ps, uint64_t seed);
 
 /* SPME reciprocal space (the reference's electrostatics, README.md:240): with coulomb_mode =

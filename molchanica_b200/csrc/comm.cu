@@ -806,6 +806,14 @@ int comm_allreduce3(mc_ctx *c, double v[3]) {
     return MC_OK;
 }
 
+// in-place sum over the ranks of n doubles in device memory, on the engine stream (no host synchronisation): the kinetic
+// energy the CSVR thermostat needs inside the step
+int comm_allreduce_dev_f64(mc_ctx *c, double *d, int n) {
+    CommState *cs = c->comm;
+    MC_NCCL(c, nccl_api().AllReduce(d, d, (size_t)n, ncclFloat64, ncclSum, cs->comm, c->st));
+    return MC_OK;
+}
+
 void comm_rank_size(const mc_ctx *c, int *rank, int *n_ranks) {
     *rank = c->comm ? c->comm->rank : 0;
     *n_ranks = c->comm ? c->comm->n : 1;

@@ -483,8 +483,7 @@ extern "C" int mc_set_thermostat(mc_ctx *c, int kind, float temperature_k, float
     MC_FLUSH(c);
     MC_REQUIRE(c, kind == MC_THERMOSTAT_NONE || kind == MC_THERMOSTAT_LANGEVIN || kind == MC_THERMOSTAT_CSVR, "mc_set_thermostat: unknown kind");
     // Langevin acts on owned rows with noise keyed by (seed, step, original atom id): the same numbers on any decomposition.
-    // CSVR needs the global kinetic energy inside the step (an all-reduce per step): single-GPU handles for now.
-    MC_REQUIRE(c, !c->comm_active || kind != MC_THERMOSTAT_CSVR, "mc_set_thermostat: the CSVR thermostat on a decomposed handle is not supported yet");
+    // CSVR needs the global kinetic energy inside the step: one 24-byte all-reduce per step on the engine stream.
     MC_REQUIRE(c, kind == MC_THERMOSTAT_NONE || (temperature_k >= 0.f && gamma_per_ps >= 0.f), "mc_set_thermostat: negative temperature or friction");
     c->langevin = kind == MC_THERMOSTAT_LANGEVIN;
     c->csvr = kind == MC_THERMOSTAT_CSVR;
@@ -1457,7 +1456,7 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
                                std::sqrt(std::max(0.f, 1.f - c1 * c1)), (float)MC_KB * c->lgv_temperature, c->lgv_seed, c->lgv_step++,
                                st, &c->launches);
         }
-        if (c->csvr && !c->comm_active) {
+        if (c->csvr) {
             // kinetic energy of the half-step velocities (two small reduction launches), then lambda, then the scaling
             MC_CUDA(c, c->red_partial.ensure((size_t)energy_partial_elems()));
             MC_CUDA(c, c->red_out.ensure(4));
@@ -1465,6 +1464,9 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
             const size_t r0 = (size_t)c->row0;
             launch_energy_reduce((int)c->n_rows_sorted(), c->force.p + r0, c->vel[c->cur].p + r0, c->flags[c->cur].p + r0, c->red_partial.p, c->red_out.p, st,
                                  &c->launches);
+            // decomposed: every rank reduced its owned atoms; one 24-byte all-reduce on the stream gives all of them the same
+            // kinetic energy and mobile-atom count, hence the same scaling factor (a function of seed, step and that energy)
+            if (c->comm_active && (rc = comm_allreduce_dev_f64(c, c->red_out.p, 3)) != MC_OK) return rc;
             launch_csvr((int)c->n_rows_sorted(), c->vel[c->cur].p + r0, c->red_out.p, MC_KB * (double)c->lgv_temperature,
                         std::exp(-(double)c->lgv_gamma * (double)dt), 3.0 * (double)c->n_waters + (double)c->n_hconstraints, c->lgv_seed, c->lgv_step++,
                         c->csvr_lambda.p, st, &c->launches);

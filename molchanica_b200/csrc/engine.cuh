@@ -358,6 +358,7 @@ int comm_agree_flag(mc_ctx *c, bool *flag);
 int comm_reduce_flags_async(mc_ctx *c, const int *d_flags2, int *h_out2);
 void comm_shrink_interval(mc_ctx *c);
 int comm_allreduce3(mc_ctx *c, double v[3]);
+int comm_allreduce_dev_f64(mc_ctx *c, double *d, int n);  // in place, device memory, engine stream, no host sync
 int comm_allreduce_f4(mc_ctx *c, float4 *buf, int64_t n);  // in-place sum over ranks
 void comm_rank_size(const mc_ctx *c, int *rank, int *n_ranks);
 int comm_allgather_ext_and_flags(mc_ctx *c, float *buf, size_t chunk, const int *d_flags2, int *h_flags);  // h_flags: pinned, 2 ints per rank

@@ -24,8 +24,8 @@ def case_workload(name, world=2):
         w = W.solvated_c3()
         w["coul_mode"] = 2  # continuous at the cutoff: trajectories are comparable
         return w, 6
-    if name in ("solvb", "solvb_small", "solvl", "solvl_small"):
-        # bonded terms (and, solvl, the Langevin thermostat) on a decomposed handle: every rank evaluates the terms that touch
+    if name in ("solvb", "solvb_small", "solvl", "solvl_small", "solvc", "solvc_small"):
+        # bonded terms (and, solvl / solvc, the Langevin / CSVR thermostat) on a decomposed handle: every rank evaluates the terms that touch
         # its owned atoms; compared with the single-handle run of the same library (tests/test_gpu_multi.py)
         return W.solvated_bonded(small=name.endswith("_small")), 8
     if name == "ljx":
@@ -70,11 +70,13 @@ def main():
     e.set_atoms(w["xyzq"], w["type"], w["vel"])
     e.set_exclusions(w.get("excl_start"), w.get("excl_idx"))
     e.set_pairs14(w.get("pairs14"), w.get("scale14_lj", 0.5), w.get("scale14_q", 1 / 1.2))
-    bonded = case.startswith(("solvb", "solvl"))
+    bonded = case.startswith(("solvb", "solvl", "solvc"))
     if bonded:
         e.set_bonded(w.get("bonds"), w.get("bond_kr0"), w.get("angles"), w.get("angle_kt0"), w.get("dihedrals"), w.get("dihedral_prm"))
     if case.startswith("solvl"):
         e.set_thermostat(1, 300.0, 5.0, seed=7)
+    if case.startswith("solvc"):
+        e.set_thermostat(2, 300.0, 5.0, seed=7)
     e.set_option("halo_fused", 1 if halo == "fused" else 0)
     # the unbonded solvated system has very fast hydrogens; "adaptive" leaves the interval to the engine
     e.set_option("rebuild_every", 0 if sched == "adaptive" else int(os.environ.get("DD_EVERY", "5")) if case in ("lj", "ljx") else 2)
@@ -96,6 +98,7 @@ def main():
         e.step(w["dt"], n_steps)
     x = e.positions()
     v = e.velocities()
+    ke_end = e.energy()["energy_kinetic"] if bonded else 0.0   # (collective: all ranks)
     st = e.stats()
     fused, why = e.halo_mode()
     interval, disp_frac = e.schedule()
@@ -115,7 +118,7 @@ def main():
     snap_ok = snap_ok and n3 == own and n3b == own and ep == ep2 and np.array_equal(i3[:n3], si[:n_snap]) and \
         np.array_equal(s3[:n3], x[i3[:n3], :3]) and np.array_equal(s3b[:n3], s3[:n3])
     if rank == 0:
-        np.savez(out, e_bonded=en0["energy_potential_bonded"], pressure=press, virial=virial, e_mols=e_mols, fused=fused, why=why, snap_ok=snap_ok, interval=interval, disp_frac=disp_frac, f0=f0, x=x, v=v, e_pot=en0["energy_potential_nonbonded"], n_owned=st0["n_atoms"],
+        np.savez(out, ke_end=ke_end, e_bonded=en0["energy_potential_bonded"], pressure=press, virial=virial, e_mols=e_mols, fused=fused, why=why, snap_ok=snap_ok, interval=interval, disp_frac=disp_frac, f0=f0, x=x, v=v, e_pot=en0["energy_potential_nonbonded"], n_owned=st0["n_atoms"],
                  n_ghosts=st0["n_ghosts"], rebuilds=st["n_rebuilds"], violations=st["n_list_violations"],
                  ext_upload_bytes=st["ext_upload_bytes"])
     e.close()

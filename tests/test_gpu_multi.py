@@ -68,12 +68,13 @@ def test_decomposed_run_matches_oracle(world, case, halo, sched, oracle):
     assert int(r["n_owned"]) < len(w["xyzq"]) and int(r["n_ghosts"]) > 0
 
 
-def _single_handle_reference(w, n_steps, langevin):
-    """The same system on one handle of the same library: initial forces, energies, positions after n_steps."""
+def _single_handle_reference(w, n_steps, thermostat):
+    """The same system on one handle of the same library: initial forces, energies, positions after n_steps.
+    thermostat: 0 none, 1 Langevin, 2 CSVR (bools of older callers: True = Langevin)."""
     from molchanica_b200.engine import MdEngine
     e = MdEngine.from_workload(w, bonded=True)
-    if langevin:
-        e.set_thermostat(1, 300.0, 5.0, seed=7)
+    if thermostat:
+        e.set_thermostat(int(thermostat), 300.0, 5.0, seed=7)
     e.set_option("rebuild_every", 2)
     e.compute_forces()
     f0, en = e.forces(), e.energy()
@@ -81,13 +82,14 @@ def _single_handle_reference(w, n_steps, langevin):
     en["between_mols"] = e.energy_between_mols(w["mol_id"])
     e.step(w["dt"], n_steps)
     x = e.positions()
+    en["ke_end"] = e.energy()["energy_kinetic"]
     e.close()
     return f0, en, x
 
 
-def check_bonded_decomposed(r, w, n_steps, langevin):
+def check_bonded_decomposed(r, w, n_steps, thermostat):
     """Shared with tests/test_library_on_host.py: a decomposed run with bonded terms against the single-handle run."""
-    f0, en, x = _single_handle_reference(w, n_steps, langevin)
+    f0, en, x = _single_handle_reference(w, n_steps, thermostat)
     # forces: same terms, fp32 atomics in another order -> a few ulp of the largest contribution per atom
     scale = np.abs(f0[:, :3]).max(1) + 1e-2 * np.abs(f0[:, :3]).max()
     assert (np.abs(r["f0"][:, :3] - f0[:, :3]).max(1) / scale).max() < 2e-5
@@ -99,15 +101,18 @@ def check_bonded_decomposed(r, w, n_steps, langevin):
     d = r["x"][:, :3] - x[:, :3]
     d -= np.rint(d / w["box_ext"]) * w["box_ext"]
     assert np.abs(d).max() < 2e-4, np.abs(d).max()
+    # the kinetic energy after the steps: a thermostat fed with one rank's share of it would scale differently
+    assert abs(float(r["ke_end"]) - en["ke_end"]) < 2e-5 * en["ke_end"], (float(r["ke_end"]), en["ke_end"])
     assert bool(r["snap_ok"]) and int(r["n_owned"]) < len(w["xyzq"]) and int(r["n_ghosts"]) > 0 and int(r["rebuilds"]) >= 2
 
 
-@pytest.mark.parametrize("case,halo", [("solvb", "fused"), ("solvb", "nccl"), ("solvl", "fused")])
+@pytest.mark.parametrize("case,halo", [("solvb", "fused"), ("solvb", "nccl"), ("solvl", "fused"), ("solvc", "fused")])
 def test_bonded_terms_and_langevin_on_a_decomposed_handle(case, halo):
     """SURVEY 8f row 3 across slab boundaries: bonds, angles and dihedrals (with their exclusions and 1-4 pairs) on two ranks
     -- every rank evaluates the terms that touch its owned atoms, partners are ghosts, energies are shared out by owned atoms
     and all-reduced -- and the Langevin thermostat, whose noise is keyed by (seed, step, original id) and therefore the same on
-    any decomposition.  Reference: the single-handle run of the same library (itself checked against the oracle in
+    any decomposition; solvc: the CSVR thermostat, whose one scaling factor per step is a function of (seed, step, kinetic
+    energy) -- the kinetic energy is all-reduced on the stream inside the step.  Reference: the single-handle run of the same library (itself checked against the oracle in
     tests/test_gpu_bonded.py / test_gpu_langevin.py)."""
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
@@ -116,4 +121,4 @@ def test_bonded_terms_and_langevin_on_a_decomposed_handle(case, halo):
     w, n_steps = case_workload(case, 2)
     r = _run(2, case, halo, "fixed")
     assert int(r["fused"]) == (1 if halo == "fused" else 0), str(r["why"])
-    check_bonded_decomposed(r, w, n_steps, case.startswith("solvl"))
+    check_bonded_decomposed(r, w, n_steps, 1 if case.startswith("solvl") else (2 if case.startswith("solvc") else 0))

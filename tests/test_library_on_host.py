@@ -99,7 +99,7 @@ def test_decomposed_run_on_the_host_build(case, world, halo, sched, host_env, or
         assert int(r["interval"]) >= 10 and int(r["rebuilds"]) >= 2 and 0.0 < float(r["disp_frac"]) < 1.0
 
 
-@pytest.mark.parametrize("case,halo", [("solvb_small", "fused"), ("solvl_small", "nccl")])
+@pytest.mark.parametrize("case,halo", [("solvb_small", "fused"), ("solvl_small", "nccl"), ("solvc_small", "fused")])
 def test_decomposed_bonded_terms_on_the_host_build(case, halo, host_env):
     """Bonded terms (+ Langevin) on a two-rank decomposed handle of the host build against the single-handle run of the same
     build (in a subprocess, so that this process does not load the library): tests/test_gpu_multi.py's check."""
@@ -115,7 +115,7 @@ def test_decomposed_bonded_terms_on_the_host_build(case, halo, host_env):
     code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "from dd_worker import case_workload\nfrom test_gpu_multi import check_bonded_decomposed\n"
             "w, n = case_workload(%r, 2)\ncheck_bonded_decomposed(np.load(%r), w, n, %r)\nprint('OK')\n"
-            % (ROOT, HERE, case, out, case.startswith("solvl")))
+            % (ROOT, HERE, case, out, 1 if case.startswith("solvl") else (2 if case.startswith("solvc") else 0)))
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
     assert p.returncode == 0 and "OK" in p.stdout, p.stdout + p.stderr
 
