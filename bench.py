@@ -247,7 +247,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        ks, ws = min(K, 100), min(W_, 10)
+        # at least two rebuild intervals of the fluid (28 steps each), so that the share of list builds in the window is the
+        # steady-state one whatever K the caller asked for (a 20-step window holds one rebuild or none: +-30 %)
+        ks, ws = min(max(K, 60), 100), min(W_, 10)
         cb = cpu_arm(args.cpu_side, ks, ws)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": cb["steps"], "warmup": ws, "ms_per_step": cb["seconds"] / cb["steps"] * 1e3,
