@@ -4,11 +4,11 @@
 # host-side testing (fenced launchers, shared headers) did not touch what was validated on hardware.
 # usage: tools/sass_diff.sh [commit]   (needs nvcc; no GPU)
 set -e
-BASE=${1:-c0a962d}
+BASE=${1:-ffc3728}
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 TMP=$(mktemp -d)
 mkdir -p $TMP/csrc $TMP/include
-FILES="sort_scan neighbor tile_build pair_force integrate dock comm"
+FILES="sort_scan neighbor tile_build pair_force pair_tile md_fused integrate thermostat dock dock_filter bonded settle pme group_energy comm"
 for f in $(git -C $ROOT ls-tree --name-only $BASE molchanica_b200/csrc/ | grep -E "\.(cu|cuh|h)$"); do
   git -C $ROOT show $BASE:$f > $TMP/csrc/$(basename $f)
 done
