@@ -34,7 +34,7 @@ def host_env():
 
 def test_gpu_parity_tests_pass_on_the_host_build(host_env):
     slow = "c4 or lane_width or variants or solv23558 or full_size or erfc_real_space or lj8000"  # (the 23.5k-atom cases: minutes on fibers)
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k", f"not ({slow})",
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-n", "4", "-m", "gpu", "-p", "no:cacheprovider", "-k", f"not ({slow})",
                         os.path.join(HERE, "test_gpu_parity.py"), os.path.join(HERE, "test_gpu_dock.py"),
                         os.path.join(HERE, "test_gpu_md_paths.py"), os.path.join(HERE, "test_gpu_edge_cases.py")],
                        capture_output=True, text=True, cwd=ROOT, env=host_env, timeout=1500)
