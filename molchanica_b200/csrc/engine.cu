@@ -1624,6 +1624,10 @@ extern "C" int mc_minimize_energy(mc_ctx *c, int max_iters, int *iters_accepted,
         launch_zero_velocities(n, c->vel[c->cur].p, st, &c->launches);
         launch_kick_drift(n, c->xyzq[c->cur].p, c->vel[c->cur].p, c->force.p, nullptr, c->orig[c->cur].p, c->flags[c->cur].p, c->xref.p,
                           tau, tau, 0.5f * c->skin, 0.f, c->rebuild_flag.p, st, &c->launches);
+        // virtual sites (massless, static: the drift leaves them where they were) follow their parents, as after every drift of mc_step
+        if (c->n_vsites > 0)
+            launch_vsite_construct(c->n_vsites, c->vsites.p, c->slot_of_orig.p, c->xyzq[c->cur].p, c->vsite_a, c->vsite_b,
+                                   make_params(c), st, &c->launches);
         MC_CUDA(c, cudaMemcpyAsync(h_flag, c->rebuild_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         MC_CUDA(c, cudaStreamSynchronize(st));
         const bool blew_up = (*h_flag & 2) != 0;

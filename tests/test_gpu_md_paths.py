@@ -342,6 +342,26 @@ def test_npt_of_rigid_water_with_stochastic_cell_rescaling(Engine):
     assert np.abs(d(m[:, 0], m[:, 1]) - 0.9572).max() < 2e-3 and np.abs(d(m[:, 1], m[:, 2]) - 1.5139).max() < 3e-3
 
 
+def test_minimiser_keeps_virtual_sites_on_their_parents(Engine):
+    """mc_minimize_energy moves atoms with the step path's drift, which leaves the massless site M of a four-site water where
+    it was: the minimiser has to place M again after every move (M = O + a (H1 - O) + b (H2 - O)), or sites and charges go
+    stale.  Flexible OPC waters (no constraints: the minimiser refuses those), 15 iterations."""
+    w = W.water_box_opc()
+    e = Engine.from_workload(w)
+    a, b = w["vsite_ab"]
+    e.set_virtual_sites(w["virtual_sites"], a, b)
+    x0 = e.positions()
+    acc, e0, e1 = e.minimize_energy(15)
+    x = e.positions()[:, :3].astype(np.float64)
+    assert acc >= 1 and e1 <= e0 and np.abs(x - x0[:, :3]).max() > 1e-4      # something moved, downhill
+    q = np.asarray(w["virtual_sites"])
+    ext = np.asarray(w["box_ext"], np.float64)
+    mi = lambda d: d - np.rint(d / ext) * ext
+    want = x[q[:, 1]] + a * mi(x[q[:, 2]] - x[q[:, 1]]) + b * mi(x[q[:, 3]] - x[q[:, 1]])
+    assert np.abs(mi(x[q[:, 0]] - want)).max() < 2e-5
+    e.close()
+
+
 def test_zero_com_drift_removes_the_net_momentum_of_the_mobile_atoms(Engine):
     """MdConfig.zero_com_drift (reference properties/crystal.rs:310): option zero_com_drift = k."""
     w = W.lj_fluid(m=12)
