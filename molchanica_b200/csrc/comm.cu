@@ -75,6 +75,8 @@ struct CommState {
     bool preconnected = false;              // the ring's point-to-point channels have been set up (first build)
     DevBuf<float4> pre_buf;                 // scratch of that warm-up exchange
     int interval = 10;                      // adaptive rebuild interval (option rebuild_every = 0)
+    float vmax0 = 0.f;                      // largest speed handed to mc_set_atoms (every rank sees the whole array: same number)
+    bool first_interval_pending = false;    // the first interval is still the default: comm_first_interval may shorten it
     double last_disp_frac = 0.0;            // largest displacement of the last interval / (skin/2)
     uint32_t epoch = 1;                     // the first step runs at epoch 2: its acks are real signals
     float4 *to_prev = nullptr, *to_next = nullptr;  // ghost blocks of the current build on the neighbours
@@ -303,8 +305,30 @@ int comm_set_atoms(mc_ctx *c, int64_t n, const mc_float4 *xyzq, const uint16_t *
     c->row0 = 0;
     cs->have_table = false;  // the atoms are index blocks again: the next build is an all-gather
     cs->interval = 10;
+    // the fastest atom of the system as handed over (for the first interval, see comm_first_interval)
+    double v2 = 0.0;
+    if (vel)
+        for (int64_t k = 0; k < n; ++k)
+            if (vel[k].w > 0.f) v2 = std::max(v2, (double)vel[k].x * vel[k].x + (double)vel[k].y * vel[k].y + (double)vel[k].z * vel[k].z);
+    cs->vmax0 = (float)std::sqrt(v2);
+    cs->first_interval_pending = true;
     MC_CUDAC(c, cudaMemset(c->slot_of_orig.p, 0xff, sizeof(int) * (size_t)n));
     return MC_OK;
+}
+
+// The adaptive schedule learns the interval from the displacements of the interval before; the very first one has nothing to
+// learn from and used to be 10 steps whatever the system -- too long for a hot fluid under a thin skin (900 K argon, 0.6 A:
+// the first interval overshot skin/2 and was reported as MC_W_STALE_LIST; found by tools/dd_fuzz_host.py).  With the time step
+// of the first mc_step known: the fastest atom, moving ballistically, may cover half of skin/2 -- between 4 and 10 steps.
+// Every rank computes it from the same numbers.
+void comm_first_interval(mc_ctx *c, float dt) {
+    CommState *cs = c->comm;
+    if (!cs || !cs->first_interval_pending) return;
+    cs->first_interval_pending = false;
+    const double per_step = (double)cs->vmax0 * std::fabs((double)dt);
+    if (per_step <= 0.0 || c->skin <= 0.f) return;
+    const double k = std::floor(0.5 * (0.5 * (double)c->skin) / per_step);
+    cs->interval = (int)std::max(4.0, std::min(10.0, k));
 }
 
 // The decomposition arithmetic, shared by the device path below and by mc_dd_plan (host only, no GPU):

@@ -1181,6 +1181,7 @@ extern "C" int mc_step(mc_ctx *c, float dt, int n_steps, const float *ext_forces
     }
     const bool trace_dev = trc.on && c->trace_ev[7] != nullptr;
     // decomposed runs rebuild on a schedule every rank derives from the same numbers (no per-step agreement)
+    if (c->comm_active && n_steps > 0) comm_first_interval(c, dt);
     const bool pipelined = !c->comm_active && c->rebuild_every <= 0 && !c->sync_rebuild;
     // External forces are the one per-call input of a step (MdState::step(dev, dt, Some(forces)), reference
     // src/mol_alignment.rs:346).  Their upload must not sit in front of the kernels: it goes to a stream of its own

@@ -357,6 +357,7 @@ void comm_step_descriptors(mc_ctx *c, bool rebuild_step, HaloPush *push, HaloSpl
 int comm_agree_flag(mc_ctx *c, bool *flag);
 int comm_reduce_flags_async(mc_ctx *c, const int *d_flags2, int *h_out2);
 void comm_shrink_interval(mc_ctx *c);
+void comm_first_interval(mc_ctx *c, float dt);  // first adaptive interval from the fastest atom and the time step (comm.cu)
 int comm_allreduce3(mc_ctx *c, double v[3]);
 int comm_allreduce_dev_f64(mc_ctx *c, double *d, int n);  // in place, device memory, engine stream, no host sync
 int comm_allreduce_f4(mc_ctx *c, float4 *buf, int64_t n);  // in-place sum over ranks
