@@ -1022,6 +1022,8 @@ static void launch_rows_build(int n_rows, int grid_cells, long long items, int s
         const size_t staging16 = (size_t)RB_WARPS_DENSE * RB_A * want_stage * sizeof(uint16_t);
         if (want_stage && per_tile + staging16 <= RB_DENSE_BUDGET) { stage_cap = want_stage; staging = staging16; }
         else { stage_cap = 0u; staging = 0; row_cap = row_hint ? ((row_hint + row_hint / 4u + 15u) & ~7u) : 0u; }
+        // list offsets are 32-bit: rows padded to row_cap must stay well inside them, else count first (exact rows)
+        if ((unsigned long long)std::max(n_rows, 0) * row_cap > 3500000000ull) row_cap = 0u;
         n_stages = 2 * per_tile + staging <= RB_DENSE_BUDGET ? 2 : 1;
     }
     const size_t smem = (size_t)n_stages * per_tile + staging;
